@@ -1,0 +1,329 @@
+"""Host-side Python mirror of the reference-facing interface, one thin layer above the C-ABI.
+
+Names and argument meaning follow the reference (the production host side is the C++ plugins under plugin/):
+  Context.orb_extract(img, nfeatures)   ~ the Svar module function gslam.b200.orb_extract(GImage, cfg)
+  Context.match_hamming(q, t)           ~ gslam.b200.match_hamming(GImage q, GImage t)
+  Optimizer.optimize(graph)             ~ GSLAM::Optimizer::optimize(BundleGraph&)        Optimizer.h:229
+  Optimizer.optimizePnP(matches, pose)  ~ GSLAM::Optimizer::optimizePnP(...)              Optimizer.h:202-207
+Errors: like the reference plugins, `Optimizer` methods return bool and never raise across the boundary
+(Optimizer.h:193-232); the lower-level Context methods raise GbError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+
+import numpy as np
+
+from . import capi
+from .capi import GbError, KP_DTYPE, ptr
+from .synth import BAProblem
+
+
+@dataclasses.dataclass
+class OptimzeConfig:  # spelling follows GSLAM::OptimzeConfig (Optimizer.h:174-182)
+    cameraProjectionType: int = 0            # PROJECTION_PINHOLE
+    projectErrorHuberThreshold: float = 0.01
+    maxIterations: int = 500
+    verbose: bool = False
+    # solver knobs the reference leaves to its backend
+    functionTolerance: float = 1e-6
+    lambdaInit: float = 1e-4
+    pcgMaxIterations: int = 50
+    pcgTolerance: float = 1e-10
+
+    def to_c(self) -> capi.BaOptions:
+        return capi.BaOptions(self.cameraProjectionType, self.projectErrorHuberThreshold, self.maxIterations,
+                              int(self.verbose), self.functionTolerance, self.lambdaInit, self.pcgMaxIterations,
+                              self.pcgTolerance)
+
+
+def _problem_c(pb: BAProblem):
+    keep = []
+
+    def arr(a, dt):
+        if a is None:
+            return None
+        b = np.ascontiguousarray(a, dtype=dt)
+        keep.append(b)
+        return b
+    assert pb.cam_pose_wc.dtype == np.float64 and pb.cam_pose_wc.flags.c_contiguous
+    assert pb.points.dtype == np.float64 and pb.points.flags.c_contiguous
+    dof = arr(pb.cam_dof, np.uint8); pf = arr(pb.point_free, np.uint8)
+    oc = arr(pb.obs_cam, np.int32); op = arr(pb.obs_point, np.int32)
+    ox = arr(pb.obs_xyz, np.float64); oi = arr(pb.obs_info, np.float64)
+
+    def p(a, t):
+        return None if a is None else a.ctypes.data_as(t)
+    c = capi.BaProblem(pb.n_cams, pb.n_points, pb.n_obs, p(pb.cam_pose_wc, capi.f64p), p(dof, capi.u8p),
+                       p(pb.points, capi.f64p), p(pf, capi.u8p), p(oc, capi.i32p), p(op, capi.i32p), p(ox, capi.f64p),
+                       p(oi, capi.f64p))
+    return c, keep
+
+
+class Context:
+    """One device + one stream (gb_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = capi.lib()
+        h = C.c_void_p()
+        rc = self._lib.gb_ctx_create(device, C.byref(h))
+        if rc != capi.GB_OK:
+            raise GbError(rc, self._lib.gb_last_error(None).decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != capi.GB_OK:
+            raise GbError(rc, self._lib.gb_last_error(self._h).decode())
+
+    @property
+    def handle(self):
+        return self._h
+
+    def sync(self):
+        self._check(self._lib.gb_ctx_sync(self._h))
+
+    def stream(self) -> int:
+        return int(self._lib.gb_ctx_stream(self._h) or 0)
+
+    def timer_begin(self):
+        self._check(self._lib.gb_timer_begin(self._h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.gb_timer_end(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        return int(self._lib.gb_launch_count(self._h))
+
+    # ---- ORB ---------------------------------------------------------------------------------------------------------
+    def orb_cfg(self, **kw) -> capi.OrbCfg:
+        cfg = capi.OrbCfg()
+        self._lib.gb_orb_cfg_default(C.byref(cfg))
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        return cfg
+
+    def orb_extract(self, img: np.ndarray, nfeatures: int = 500, capacity: int | None = None, **cfg_kw):
+        """img: (H, W) uint8.  Returns (keypoints[KP_DTYPE], descriptors (n,32) uint8) in canonical (octave,y,x) order."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        cfg = self.orb_cfg(nfeatures=nfeatures, **cfg_kw)
+        cap = capacity or (2 * nfeatures + 256)
+        while True:
+            kps = np.zeros(cap, dtype=KP_DTYPE)
+            desc = np.zeros((cap, 32), dtype=np.uint8)
+            n = C.c_int(cap)
+            rc = self._lib.gb_orb_extract(self._h, ptr(img), w, h, C.byref(cfg), ptr(kps), ptr(desc), C.byref(n))
+            if rc == capi.GB_ERR_CAPACITY and capacity is None and n.value > cap:
+                cap = n.value
+                continue
+            self._check(rc)
+            return kps[:n.value].copy(), desc[:n.value].copy()
+
+    # ---- match -------------------------------------------------------------------------------------------------------
+    def match_hamming(self, query: np.ndarray, train: np.ndarray):
+        """Returns (best_idx, best_dist, second_dist) int32 arrays, cv::BFMatcher(NORM_HAMMING) tie rules."""
+        q = np.ascontiguousarray(query, dtype=np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(train, dtype=np.uint8).reshape(-1, 32)
+        nq, nt = q.shape[0], t.shape[0]
+        idx = np.empty(nq, np.int32); d1 = np.empty(nq, np.int32); d2 = np.empty(nq, np.int32)
+        self._check(self._lib.gb_match_hamming(self._h, ptr(q), nq, ptr(t), nt, ptr(idx), ptr(d1), ptr(d2)))
+        return idx, d1, d2
+
+    # ---- BA ----------------------------------------------------------------------------------------------------------
+    def ba_solve(self, pb: BAProblem, cfg: OptimzeConfig | None = None) -> capi.BaResult:
+        c, keep = _problem_c(pb)
+        o = (cfg or OptimzeConfig()).to_c()
+        r = capi.BaResult()
+        self._check(self._lib.gb_ba_solve(self._h, C.byref(c), C.byref(o), C.byref(r)))
+        return r
+
+    def ba_pnp(self, xyz, xy1, pose_wc, dof: int = 63, want_info: bool = False, cfg: OptimzeConfig | None = None):
+        xyz = np.ascontiguousarray(xyz, np.float64); xy1 = np.ascontiguousarray(xy1, np.float64)
+        pose = np.ascontiguousarray(pose_wc, np.float64).copy()
+        info = np.zeros((6, 6)) if want_info else None
+        o = (cfg or OptimzeConfig()).to_c(); r = capi.BaResult()
+        self._check(self._lib.gb_ba_pnp(self._h, xyz.shape[0], ptr(xyz), ptr(xy1), ptr(pose), dof, ptr(info),
+                                        C.byref(o), C.byref(r)))
+        return pose, r, info
+
+
+class Features:
+    """A frame's keypoints + descriptors resident in HBM (gb_features)."""
+
+    def __init__(self, ctx: Context, capacity: int):
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx._check(ctx._lib.gb_features_create(ctx._h, capacity, C.byref(h)))
+        self._h = h
+        self.capacity = capacity
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self.ctx._lib.gb_features_destroy(self.ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def extract(self, img, width: int, height: int, cfg: capi.OrbCfg, device_ptr: bool = False, pitch: int | None = None):
+        """img: numpy (H,W) uint8 host array, or an integer device pointer when device_ptr."""
+        c = self.ctx
+        if device_ptr:
+            p = C.c_void_p(int(img))
+        else:
+            p = ptr(img)
+        c._check(c._lib.gb_orb_extract_to(c._h, p, 1 if device_ptr else 0, width, height, pitch or width, C.byref(cfg), self._h))
+
+    def count(self) -> int:
+        n = C.c_int()
+        self.ctx._check(self.ctx._lib.gb_features_count(self.ctx._h, self._h, C.byref(n)))
+        return n.value
+
+    def upload(self, desc: np.ndarray, kps: np.ndarray | None = None):
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        k = None if kps is None else np.ascontiguousarray(kps, KP_DTYPE)
+        self.ctx._check(self.ctx._lib.gb_features_upload(self.ctx._h, self._h, ptr(k), ptr(d), d.shape[0]))
+
+    def download(self):
+        n = C.c_int(self.capacity)
+        kps = np.zeros(self.capacity, KP_DTYPE); desc = np.zeros((self.capacity, 32), np.uint8)
+        self.ctx._check(self.ctx._lib.gb_features_download(self.ctx._h, self._h, ptr(kps), ptr(desc), C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def match(self, train: "Features"):
+        self.ctx._check(self.ctx._lib.gb_match_features(self.ctx._h, self._h, train._h))
+
+    def matches(self):
+        n = C.c_int(self.capacity)
+        idx = np.empty(self.capacity, np.int32); d1 = np.empty(self.capacity, np.int32); d2 = np.empty(self.capacity, np.int32)
+        self.ctx._check(self.ctx._lib.gb_match_download(self.ctx._h, self._h, ptr(idx), ptr(d1), ptr(d2), C.byref(n)))
+        return idx[:n.value].copy(), d1[:n.value].copy(), d2[:n.value].copy()
+
+
+class BAGraph:
+    """A bundle-adjustment graph resident in HBM (gb_ba_graph)."""
+
+    def __init__(self, ctx: Context, pb: BAProblem):
+        self.ctx = ctx
+        self.n_cams, self.n_points, self.n_obs = pb.n_cams, pb.n_points, pb.n_obs
+        c, keep = _problem_c(pb)
+        h = C.c_void_p()
+        ctx._check(ctx._lib.gb_ba_graph_create(ctx._h, C.byref(c), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self.ctx._lib.gb_ba_graph_destroy(self.ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self.ctx._check(self.ctx._lib.gb_ba_graph_reset(self.ctx._h, self._h))
+
+    def solve(self, cfg: OptimzeConfig | None = None) -> capi.BaResult:
+        o = (cfg or OptimzeConfig()).to_c(); r = capi.BaResult()
+        self.ctx._check(self.ctx._lib.gb_ba_graph_solve(self.ctx._h, self._h, C.byref(o), C.byref(r)))
+        return r
+
+    def download(self):
+        pose = np.zeros((self.n_cams, 7)); pts = np.zeros((self.n_points, 3))
+        self.ctx._check(self.ctx._lib.gb_ba_graph_download(self.ctx._h, self._h, ptr(pose), ptr(pts)))
+        return pose, pts
+
+    # stepwise interface (landmark-sharded multi-GPU BA; see gslam_b200/dist.py)
+    def reduce_size(self) -> int:
+        n = C.c_size_t()
+        self.ctx._check(self.ctx._lib.gb_ba_graph_reduce_size(self.ctx._h, self._h, C.byref(n)))
+        return int(n.value)
+
+    def begin(self, cfg: OptimzeConfig | None = None):
+        o = (cfg or OptimzeConfig()).to_c()
+        self.ctx._check(self.ctx._lib.gb_ba_graph_begin(self.ctx._h, self._h, C.byref(o)))
+
+    def reduce_local(self, d_buf: int):
+        self.ctx._check(self.ctx._lib.gb_ba_graph_reduce_local(self.ctx._h, self._h, C.c_void_p(d_buf)))
+
+    def step(self, d_buf: int, d_cost: int):
+        self.ctx._check(self.ctx._lib.gb_ba_graph_step(self.ctx._h, self._h, C.c_void_p(d_buf), C.c_void_p(d_cost)))
+
+    def commit(self, d_buf: int, d_cost: int):
+        self.ctx._check(self.ctx._lib.gb_ba_graph_commit(self.ctx._h, self._h, C.c_void_p(d_buf), C.c_void_p(d_cost)))
+
+    def finish(self) -> capi.BaResult:
+        r = capi.BaResult()
+        self.ctx._check(self.ctx._lib.gb_ba_graph_finish(self.ctx._h, self._h, C.byref(r)))
+        return r
+
+    # test hooks
+    def dbg_linearize(self, delta: float = 0.01):
+        U = np.zeros((self.n_cams, 6, 6)); gc = np.zeros((self.n_cams, 6)); V = np.zeros((self.n_points, 3, 3))
+        gp = np.zeros((self.n_points, 3)); W = np.zeros((self.n_obs, 6, 3)); cost = np.zeros(1)
+        self.ctx._check(self.ctx._lib.gb_dbg_ba_linearize(self.ctx._h, self._h, delta, ptr(U), ptr(gc), ptr(V), ptr(gp),
+                                                          ptr(W), ptr(cost)))
+        return dict(U=U, gc=gc, V=V, gp=gp, W=W, cost=float(cost[0]))
+
+    def dbg_reduced(self, cfg: OptimzeConfig | None = None):
+        n6 = 6 * self.n_cams
+        S = np.zeros((n6, n6)); gt = np.zeros(n6); dc = np.zeros(n6); it = C.c_int()
+        o = (cfg or OptimzeConfig()).to_c()
+        self.ctx._check(self.ctx._lib.gb_dbg_ba_reduced(self.ctx._h, self._h, C.byref(o), ptr(S), ptr(gt), ptr(dc), C.byref(it)))
+        return S, gt, dc, it.value
+
+
+class Optimizer:
+    """Mirror of GSLAM::Optimizer (Optimizer.h:184-253): bool returns, graph / pose updated in place, `_config` public."""
+
+    def __init__(self, config: OptimzeConfig | None = None, device: int = 0):
+        self._config = config or OptimzeConfig()
+        self._ctx = Context(device)
+        self.last_result: capi.BaResult | None = None
+
+    def optimize(self, graph: BAProblem) -> bool:
+        try:
+            self.last_result = self._ctx.ba_solve(graph, self._config)
+            return True
+        except GbError:
+            return False
+
+    def optimizePnP(self, matches_xyz, matches_anchor, pose: np.ndarray, dof: int = 63, information: np.ndarray | None = None) -> bool:
+        try:
+            out, res, info = self._ctx.ba_pnp(matches_xyz, matches_anchor, pose, dof, want_info=information is not None,
+                                              cfg=self._config)
+            pose[...] = out
+            if information is not None:
+                information[...] = info
+            self.last_result = res
+            return True
+        except GbError:
+            return False
+
+    @staticmethod
+    def create(pluginName: str = "", device: int = 0):
+        """GSLAM::Optimizer::create (Optimizer.h:234-248): returns None (the reference returns a null shared_ptr) on failure."""
+        try:
+            return Optimizer(device=device)
+        except (GbError, ImportError, OSError):
+            return None

@@ -1,0 +1,915 @@
+// gslam_b200/csrc/ba.cu — bundle adjustment behind GSLAM::Optimizer::optimize / optimizePnP
+// (GSLAM/core/Optimizer.h:202-207,229; graph PODs :106-172; OptimzeConfig :174-182).
+//
+// Generic stream-ordered path (any problem size; also the per-rank engine of the landmark-sharded global BA):
+//   K6a ba_linearize_points : fused residual + 2x3/2x6 Jacobian sweep, one thread per landmark over its (point-sorted)
+//                             observation segment -> V_j, g_p,j, W_k (6x3 per observation), per-landmark cost.  No J is
+//                             ever materialised.
+//   K6b ba_linearize_cams   : one CTA per camera over its (camera-sorted) observation list, recomputing the residual,
+//                             fixed-tree block reduction -> U_i (6x6), g_c,i.  Deterministic (no atomics).
+//   K7a ba_point_inv / ba_schur_init / ba_schur_accum : damped V^-1, S = U - sum_j W V^-1 W', g~ = g_c - sum W V^-1 g_p.
+//   K7b pcg_init / pcg_matvec / pcg_update : block-Jacobi PCG on the reduced camera system, convergence decided on device.
+//   ba_backsub / ba_retract / ba_cost_points / ba_commit / ba_apply : back-substitution, candidate estimate, LM accept/reject.
+// All LM state lives in BaScalars on the device; kernels early-exit on its flags, so an iteration needs no host sync.
+#include "ba_device.cuh"
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+using namespace ba;
+
+// ======================================================================================================================
+// kernels
+// ======================================================================================================================
+namespace {
+
+constexpr int kPtThreads = 128;
+constexpr int kCamThreads = 128;
+constexpr int kRedThreads = 1024;
+
+__global__ void ba_prepare_kernel(int nc, const double* __restrict__ pose_wc, double* __restrict__ pose_cw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  double in[7], out[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) in[k] = pose_wc[7 * i + k];
+  se3_inverse(in, out);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) pose_cw[7 * i + k] = out[k];
+}
+
+__global__ void ba_rt_kernel(int nc, const double* __restrict__ pose, double* __restrict__ Rt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  double q[4] = {pose[7 * i], pose[7 * i + 1], pose[7 * i + 2], pose[7 * i + 3]}, R[9];
+  quat_to_R(q, R);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Rt[12 * i + k] = R[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) Rt[12 * i + 9 + k] = pose[7 * i + 4 + k];
+}
+
+// K6a: one thread per landmark
+__global__ void __launch_bounds__(kPtThreads) ba_linearize_points_kernel(BaDev g) {
+  if (g.sc->stop || !g.sc->need_linearize) return;
+  const int j = blockIdx.x * kPtThreads + threadIdx.x;
+  if (j >= g.np) return;
+  const double delta = g.sc->delta;
+  const double p[3] = {g.pts[3 * j], g.pts[3 * j + 1], g.pts[3 * j + 2]};
+  const bool pf = g.pfree[j] != 0;
+  double V[9], gp[3], cost = 0.0;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) V[k] = 0.0;
+  gp[0] = gp[1] = gp[2] = 0.0;
+  const int e0 = g.pt_off[j], e1 = g.pt_off[j + 1];
+  for (int e = e0; e < e1; ++e) {
+    const int i = g.o_cam[e];
+    const double* Rt = g.Rt + 12 * i;
+    const ObsLin o = eval_obs(Rt, p, g.o_uv[2 * e], g.o_uv[2 * e + 1], g.has_info ? g.o_info + 3 * e : nullptr, delta);
+    double* W = g.W + 18 * (size_t)e;
+    if (!o.valid) {
+#pragma unroll
+      for (int k = 0; k < 18; ++k) W[k] = 0.0;
+      continue;
+    }
+    cost += o.rho;
+    double Jc[12], Jp[6], AJp[6];
+    jac_cam(o, g.dof[i], Jc);
+    jac_pt(o, Rt, pf, Jp);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      AJp[d] = o.A0 * Jp[d] + o.A1 * Jp[3 + d];
+      AJp[3 + d] = o.A1 * Jp[d] + o.A2 * Jp[3 + d];
+    }
+    const double Ar0 = o.A0 * o.r0 + o.A1 * o.r1, Ar1 = o.A1 * o.r0 + o.A2 * o.r1;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) W[a * 3 + b] = Jc[a] * AJp[b] + Jc[6 + a] * AJp[3 + b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int b = 0; b < 3; ++b) V[a * 3 + b] += Jp[a] * AJp[b] + Jp[3 + a] * AJp[3 + b];
+      gp[a] -= Jp[a] * Ar0 + Jp[3 + a] * Ar1;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) g.V[9 * (size_t)j + k] = V[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) g.gp[3 * (size_t)j + k] = gp[k];
+  g.cost_pt[j] = cost;
+}
+
+// K6b: one CTA per camera; deterministic tree reduction of the 21 upper-triangular U entries + 6 gradient entries
+__global__ void __launch_bounds__(kCamThreads) ba_linearize_cams_kernel(BaDev g) {
+  if (g.sc->stop || !g.sc->need_linearize) return;
+  __shared__ double s_part[kCamThreads / 32 + 1];
+  const int i = blockIdx.x;
+  const double delta = g.sc->delta;
+  const double* Rt = g.Rt + 12 * i;
+  const int dm = g.dof[i];
+  double acc[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+  for (int idx = g.cam_off[i] + threadIdx.x; idx < g.cam_off[i + 1]; idx += kCamThreads) {
+    const int e = g.cam_perm[idx];
+    const int j = g.o_pt[e];
+    const double p[3] = {g.pts[3 * j], g.pts[3 * j + 1], g.pts[3 * j + 2]};
+    const ObsLin o = eval_obs(Rt, p, g.o_uv[2 * e], g.o_uv[2 * e + 1], g.has_info ? g.o_info + 3 * e : nullptr, delta);
+    if (!o.valid) continue;
+    double Jc[12], AJc[12];
+    jac_cam(o, dm, Jc);
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+      AJc[d] = o.A0 * Jc[d] + o.A1 * Jc[6 + d];
+      AJc[6 + d] = o.A1 * Jc[d] + o.A2 * Jc[6 + d];
+    }
+    const double Ar0 = o.A0 * o.r0 + o.A1 * o.r1, Ar1 = o.A1 * o.r0 + o.A2 * o.r1;
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int b = a; b < 6; ++b) acc[t++] += Jc[a] * AJc[b] + Jc[6 + a] * AJc[6 + b];
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) acc[21 + a] -= Jc[a] * Ar0 + Jc[6 + a] * Ar1;
+  }
+  double red[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) red[k] = block_sum<kCamThreads>(acc[k], s_part);
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int a = 0; a < 6; ++a)
+      for (int b = a; b < 6; ++b) {
+        g.U[36 * i + a * 6 + b] = red[t];
+        g.U[36 * i + b * 6 + a] = red[t];
+        ++t;
+      }
+    for (int a = 0; a < 6; ++a) g.gc[6 * i + a] = red[21 + a];
+  }
+}
+
+// out[0] = 0.5 * sum(src[0..n)) — single CTA, deterministic
+__global__ void __launch_bounds__(kRedThreads) ba_reduce_cost_kernel(const BaScalars* sc, const double* __restrict__ src, int n,
+                                                                     double* __restrict__ out) {
+  if (sc->stop) return;
+  __shared__ double s_part[kRedThreads / 32 + 1];
+  double v = 0.0;
+  for (int k = threadIdx.x; k < n; k += kRedThreads) v += src[k];
+  const double t = block_sum<kRedThreads>(v, s_part);
+  if (threadIdx.x == 0) out[0] = 0.5 * t;
+}
+
+// damped inverse of the landmark blocks
+__global__ void ba_point_inv_kernel(BaDev g) {
+  if (g.sc->stop) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.np) return;
+  const double lambda = g.sc->lambda;
+  double Vi[9];
+  const bool active = g.pfree[j] != 0 && g.pt_off[j + 1] > g.pt_off[j];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Vi[k] = active ? g.V[9 * (size_t)j + k] : 0.0;
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) Vi[a * 4] += lambda * clampd(Vi[a * 4]);
+    if (!spd_inverse<3>(Vi)) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Vi[k] = 0.0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) g.Vinv[9 * (size_t)j + k] = Vi[k];
+}
+
+// buf = [S | gt | diagU | cost]; S must have been zeroed.  One thread per (camera, a, b).
+__global__ void ba_schur_init_kernel(BaDev g, double* __restrict__ buf) {
+  if (g.sc->stop) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.nc * 36) return;
+  const int i = t / 36, a = (t % 36) / 6, b = t % 6;
+  const size_t n6 = g.n6;
+  const double u = g.U[t];
+  buf[(size_t)(6 * i + a) * n6 + 6 * i + b] = u;
+  if (a == b) {
+    buf[n6 * n6 + n6 + 6 * i + a] = u;          // diag U
+    buf[n6 * n6 + 6 * i + a] = g.gc[6 * i + a];  // g~ starts from g_c
+  }
+}
+
+// one thread per observation e=(i,j): Y = W_e Vinv_j;  g~_i -= Y g_p,j;  S_{i,i'} -= Y W_f' for every f=(i',j)
+__global__ void ba_schur_accum_kernel(BaDev g, double* __restrict__ buf) {
+  if (g.sc->stop) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.no) return;
+  const int j = g.o_pt[e], i = g.o_cam[e];
+  if (!g.pfree[j]) return;
+  const size_t n6 = g.n6;
+  double Vi[9], Y[18];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Vi[k] = g.Vinv[9 * (size_t)j + k];
+  const double* W = g.W + 18 * (size_t)e;
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    const double w0 = W[a * 3], w1 = W[a * 3 + 1], w2 = W[a * 3 + 2];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) Y[a * 3 + b] = w0 * Vi[b] + w1 * Vi[3 + b] + w2 * Vi[6 + b];
+  }
+  const double g0 = g.gp[3 * (size_t)j], g1 = g.gp[3 * (size_t)j + 1], g2 = g.gp[3 * (size_t)j + 2];
+  double* gt = buf + n6 * n6;
+#pragma unroll
+  for (int a = 0; a < 6; ++a) atomicAdd(&gt[6 * i + a], -(Y[a * 3] * g0 + Y[a * 3 + 1] * g1 + Y[a * 3 + 2] * g2));
+  const int f0 = g.pt_off[j], f1 = g.pt_off[j + 1];
+  for (int f = f0; f < f1; ++f) {
+    const int i2 = g.o_cam[f];
+    const double* W2 = g.W + 18 * (size_t)f;
+    double w2[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) w2[k] = W2[k];
+    double* Sb = buf + (size_t)(6 * i) * n6 + 6 * i2;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b < 6; ++b)
+        atomicAdd(&Sb[(size_t)a * n6 + b], -(Y[a * 3] * w2[b * 3] + Y[a * 3 + 1] * w2[b * 3 + 1] + Y[a * 3 + 2] * w2[b * 3 + 2]));
+  }
+}
+
+// Marquardt damping of the camera blocks, reading the (possibly all-reduced) diag U; fixed dofs get a unit diagonal
+__global__ void ba_damp_kernel(BaDev g, double* __restrict__ buf) {
+  if (g.sc->stop) return;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= g.n6) return;
+  const size_t n6 = g.n6;
+  const int i = d / 6, a = d % 6;
+  const double lambda = g.sc->lambda;
+  if ((g.dof[i] >> a) & 1) buf[(size_t)d * n6 + d] += lambda * clampd(buf[n6 * n6 + n6 + d]);
+  else buf[(size_t)d * n6 + d] = 1.0;
+}
+
+// ---- PCG ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRedThreads) pcg_init_kernel(BaDev g, const double* __restrict__ buf) {
+  if (g.sc->stop) return;
+  __shared__ double s_part[kRedThreads / 32 + 1];
+  const size_t n6 = g.n6;
+  const double* S = buf;
+  const double* gt = buf + n6 * n6;
+  for (int i = threadIdx.x; i < g.nc; i += kRedThreads) {
+    double M[36];
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b < 6; ++b) M[a * 6 + b] = S[(size_t)(6 * i + a) * n6 + 6 * i + b];
+    if (!spd_inverse<6>(M)) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) M[a * 6 + b] = (a == b) ? 1.0 / S[(size_t)(6 * i + a) * n6 + 6 * i + a] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 36; ++k) g.Minv[36 * (size_t)i + k] = M[k];
+  }
+  for (int d = threadIdx.x; d < g.n6; d += kRedThreads) {
+    g.x[d] = 0.0;
+    g.r[d] = gt[d];
+  }
+  __syncthreads();
+  double part = 0.0;
+  for (int d = threadIdx.x; d < g.n6; d += kRedThreads) {
+    const int i = d / 6, a = d % 6;
+    double s = 0.0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) s += g.Minv[36 * (size_t)i + a * 6 + b] * gt[6 * i + b];
+    g.z[d] = s;
+    g.p[d] = s;
+    part += gt[d] * s;
+  }
+  const double rz = block_sum<kRedThreads>(part, s_part);
+  if (threadIdx.x == 0) {
+    g.sc->rz = rz;
+    g.sc->rz0 = rz;
+    g.sc->pcg_done = !(rz > 0.0);
+  }
+}
+
+// q = S p : one warp per row, coalesced row reads, fixed shuffle tree
+__global__ void __launch_bounds__(256) pcg_matvec_kernel(BaDev g, const double* __restrict__ buf) {
+  if (g.sc->stop || g.sc->pcg_done) return;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= g.n6) return;
+  const double* Srow = buf + (size_t)row * g.n6;
+  double s = 0.0;
+  for (int c = lane; c < g.n6; c += 32) s += Srow[c] * g.p[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) g.q[row] = s;
+}
+
+__global__ void __launch_bounds__(kRedThreads) pcg_update_kernel(BaDev g) {
+  if (g.sc->stop || g.sc->pcg_done) return;
+  __shared__ double s_part[kRedThreads / 32 + 1];
+  const double rz = g.sc->rz, rz0 = g.sc->rz0, tol = g.sc->pcg_tol;
+  double part = 0.0;
+  for (int d = threadIdx.x; d < g.n6; d += kRedThreads) part += g.p[d] * g.q[d];
+  const double pq = block_sum<kRedThreads>(part, s_part);
+  if (!(pq > 0.0)) {
+    if (threadIdx.x == 0) g.sc->pcg_done = 1;
+    return;
+  }
+  const double alpha = rz / pq;
+  for (int d = threadIdx.x; d < g.n6; d += kRedThreads) {
+    g.x[d] += alpha * g.p[d];
+    g.r[d] -= alpha * g.q[d];
+  }
+  __syncthreads();
+  part = 0.0;
+  for (int d = threadIdx.x; d < g.n6; d += kRedThreads) {
+    const int i = d / 6, a = d % 6;
+    double s = 0.0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) s += g.Minv[36 * (size_t)i + a * 6 + b] * g.r[6 * i + b];
+    g.z[d] = s;
+    part += g.r[d] * s;
+  }
+  const double rzn = block_sum<kRedThreads>(part, s_part);
+  if (threadIdx.x == 0) g.sc->pcg_iters++;
+  if (!(rzn > 0.0) || sqrt(rzn / rz0) < tol) {
+    if (threadIdx.x == 0) g.sc->pcg_done = 1;
+    return;
+  }
+  const double beta = rzn / rz;
+  for (int d = threadIdx.x; d < g.n6; d += kRedThreads) g.p[d] = g.z[d] + beta * g.p[d];
+  if (threadIdx.x == 0) g.sc->rz = rzn;
+}
+
+// ---- update ------------------------------------------------------------------------------------------------------------
+__global__ void ba_backsub_kernel(BaDev g) {
+  if (g.sc->stop) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.np) return;
+  double b[3] = {g.gp[3 * (size_t)j], g.gp[3 * (size_t)j + 1], g.gp[3 * (size_t)j + 2]};
+  for (int e = g.pt_off[j]; e < g.pt_off[j + 1]; ++e) {
+    const int i = g.o_cam[e];
+    const double* W = g.W + 18 * (size_t)e;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int a = 0; a < 6; ++a) b[c] -= W[a * 3 + c] * g.x[6 * i + a];
+  }
+  const double* Vi = g.Vinv + 9 * (size_t)j;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    g.pts_new[3 * (size_t)j + a] = g.pts[3 * (size_t)j + a] + Vi[a * 3] * b[0] + Vi[a * 3 + 1] * b[1] + Vi[a * 3 + 2] * b[2];
+}
+
+__global__ void ba_retract_kernel(BaDev g) {
+  if (g.sc->stop) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.nc) return;
+  double pose[7], d[6], out[7], R[9];
+  const int dm = g.dof[i];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) pose[k] = g.pose[7 * i + k];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) d[a] = ((dm >> a) & 1) ? g.x[6 * i + a] : 0.0;
+  se3_retract(pose, d, out);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) g.pose_new[7 * i + k] = out[k];
+  quat_to_R(out, R);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) g.Rt_new[12 * i + k] = R[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) g.Rt_new[12 * i + 9 + k] = out[4 + k];
+}
+
+// robustified cost of every landmark at the candidate estimate
+__global__ void ba_cost_points_kernel(BaDev g) {
+  if (g.sc->stop) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.np) return;
+  const double delta = g.sc->delta;
+  const double p[3] = {g.pts_new[3 * (size_t)j], g.pts_new[3 * (size_t)j + 1], g.pts_new[3 * (size_t)j + 2]};
+  double cost = 0.0;
+  for (int e = g.pt_off[j]; e < g.pt_off[j + 1]; ++e) {
+    const ObsLin o = eval_obs(g.Rt_new + 12 * g.o_cam[e], p, g.o_uv[2 * e], g.o_uv[2 * e + 1],
+                              g.has_info ? g.o_info + 3 * e : nullptr, delta);
+    cost += o.rho;
+  }
+  g.cost_pt_new[j] = cost;
+}
+
+// LM accept / reject from the (possibly all-reduced) costs
+__global__ void ba_commit_kernel(BaDev g, const double* __restrict__ buf, const double* __restrict__ d_cost) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  BaScalars* sc = g.sc;
+  if (sc->stop) return;
+  const size_t n6 = g.n6;
+  const double cost = buf[n6 * n6 + 2 * n6], cnew = d_cost[0];
+  if (sc->iterations == 0) sc->initial_cost = cost;
+  sc->cost = cost;
+  sc->cost_new = cnew;
+  sc->iterations++;
+  const bool ok = (cnew < cost) && isfinite(cnew);
+  sc->accept_flag = ok ? 1 : 0;
+  sc->need_linearize = ok ? 1 : 0;
+  if (ok) {
+    const double rel = (cost - cnew) / cost;
+    sc->cost = cnew;
+    double l = sc->lambda / 3.0;
+    sc->lambda = l < 1e-15 ? 1e-15 : l;
+    sc->nu = 2.0;
+    sc->accepted++;
+    if (rel < sc->ftol) { sc->stop = 1; sc->status = 1; }
+  } else {
+    sc->lambda *= sc->nu;
+    sc->nu *= 2.0;
+    if (sc->lambda > 1e16) { sc->stop = 1; sc->status = 2; }
+  }
+}
+
+// on accept: estimate <- candidate.  (runs even when ba_commit just set stop: the accepted step must land)
+__global__ void ba_apply_kernel(BaDev g) {
+  if (!g.sc->accept_flag) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < g.nc * 7) g.pose[t] = g.pose_new[t];
+  if (t < g.nc * 12) g.Rt[t] = g.Rt_new[t];
+  if (t < g.np * 3) g.pts[t] = g.pts_new[t];
+}
+
+__global__ void ba_clear_accept_kernel(BaScalars* sc) { sc->accept_flag = 0; }
+
+__global__ void ba_finalize_kernel(int nc, const double* __restrict__ pose_cw, double* __restrict__ pose_wc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  double in[7], out[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) in[k] = pose_cw[7 * i + k];
+  se3_inverse(in, out);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) pose_wc[7 * i + k] = out[k];
+}
+
+}  // namespace
+
+// ======================================================================================================================
+// host side
+// ======================================================================================================================
+struct gb_ba_graph {
+  BaDev d{};
+  std::vector<void*> allocs;
+  double *pose_init = nullptr, *pts_init = nullptr, *pose_wc_out = nullptr;
+  double* buf = nullptr;     // internal [S | gt | diagU | cost | pad]
+  double* d_cost = nullptr;  // internal candidate cost
+  size_t buf_doubles = 0;
+  gb_ba_options opt{};
+  std::vector<int> sorted_to_orig;  // sorted observation slot -> caller's edge index
+  bool begun = false;
+};
+
+static size_t ba_buf_doubles(int nc) {
+  const size_t n6 = 6 * (size_t)nc;
+  return n6 * n6 + 2 * n6 + 8;
+}
+
+template <typename T>
+static int ba_alloc(gb_ctx* ctx, gb_ba_graph* g, T** p, size_t n) {
+  void* v = nullptr;
+  GB_CUDA(ctx, cudaMalloc(&v, std::max<size_t>(n, 1) * sizeof(T)));
+  g->allocs.push_back(v);
+  *p = (T*)v;
+  return GB_OK;
+}
+
+static int ba_validate(gb_ctx* ctx, const gb_ba_problem* pb) {
+  if (!pb || pb->n_cams < 0 || pb->n_points < 0 || pb->n_obs < 0) {
+    gb_set_error(ctx, "gb_ba: negative sizes");
+    return GB_ERR_INVALID;
+  }
+  if ((pb->n_cams > 0 && !pb->cam_pose_wc) || (pb->n_points > 0 && !pb->points) ||
+      (pb->n_obs > 0 && (!pb->obs_cam || !pb->obs_point || !pb->obs_xyz))) {
+    gb_set_error(ctx, "gb_ba: null array");
+    return GB_ERR_INVALID;
+  }
+  if (pb->n_cams > 20000) {
+    gb_set_error(ctx, "gb_ba: %d cameras exceed the dense reduced-system limit (20000)", pb->n_cams);
+    return GB_ERR_INVALID;
+  }
+  for (int k = 0; k < pb->n_obs; ++k) {
+    if (pb->obs_cam[k] < 0 || pb->obs_cam[k] >= pb->n_cams || pb->obs_point[k] < 0 || pb->obs_point[k] >= pb->n_points) {
+      gb_set_error(ctx, "gb_ba: edge %d references camera %d / point %d out of range", k, pb->obs_cam[k], pb->obs_point[k]);
+      return GB_ERR_INVALID;
+    }
+    const double z = pb->obs_xyz[3 * (size_t)k + 2];
+    if (!(z != 0.0) || !std::isfinite(z)) {
+      gb_set_error(ctx, "gb_ba: edge %d has a zero/non-finite measurement z", k);
+      return GB_ERR_INVALID;
+    }
+  }
+  return GB_OK;
+}
+
+extern "C" {
+
+void gb_ba_options_default(gb_ba_options* o) {
+  if (!o) return;
+  o->projection = 0;
+  o->huber_delta = 0.01;  // OptimzeConfig::projectErrorHuberThreshold, Optimizer.h:177
+  o->max_iterations = 500;  // OptimzeConfig::maxIterations, Optimizer.h:179
+  o->verbose = 0;
+  o->function_tolerance = 1e-6;
+  o->lambda_init = 1e-4;
+  o->pcg_max_iters = 50;
+  o->pcg_tol = 1e-10;
+}
+
+int gb_ba_graph_destroy(gb_ctx* ctx, gb_ba_graph* g) {
+  if (!g) return GB_OK;
+  if (ctx) {
+    CtxLock lk(ctx);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  for (void* p : g->allocs) cudaFree(p);
+  delete g;
+  return GB_OK;
+}
+
+int gb_ba_graph_create(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out) {
+  if (!ctx || !out) return GB_ERR_INVALID;
+  *out = nullptr;
+  CtxLock lk(ctx);
+  GB_CHECK(ba_validate(ctx, pb));
+  const int nc = pb->n_cams, np = pb->n_points, no = pb->n_obs;
+  gb_ba_graph* g = new gb_ba_graph();
+  struct Guard {
+    gb_ctx* c; gb_ba_graph* g; bool ok = false;
+    ~Guard() { if (!ok) gb_ba_graph_destroy(c, g); }
+  } guard{ctx, g};
+  BaDev& d = g->d;
+  d.nc = nc; d.np = np; d.no = no; d.n6 = 6 * nc; d.has_info = pb->obs_info ? 1 : 0;
+
+  // ---- host-side ordering: stable counting sorts -> (point, camera) order, and the per-camera lists ----------------
+  std::vector<int> byc(no), order(no), cnt(std::max(nc, np) + 2, 0);
+  for (int k = 0; k < no; ++k) cnt[pb->obs_cam[k] + 1]++;
+  for (int i = 0; i < nc; ++i) cnt[i + 1] += cnt[i];
+  { std::vector<int> pos(cnt.begin(), cnt.begin() + nc + 1); for (int k = 0; k < no; ++k) byc[pos[pb->obs_cam[k]]++] = k; }
+  std::vector<int> pt_off(np + 1, 0);
+  for (int k = 0; k < no; ++k) pt_off[pb->obs_point[k] + 1]++;
+  for (int j = 0; j < np; ++j) pt_off[j + 1] += pt_off[j];
+  { std::vector<int> pos(pt_off.begin(), pt_off.end()); for (int t = 0; t < no; ++t) { int k = byc[t]; order[pos[pb->obs_point[k]]++] = k; } }
+  g->sorted_to_orig = order;
+  std::vector<int> cam_off(nc + 1, 0), cam_perm(no);
+  for (int e = 0; e < no; ++e) cam_off[pb->obs_cam[order[e]] + 1]++;
+  for (int i = 0; i < nc; ++i) cam_off[i + 1] += cam_off[i];
+  { std::vector<int> pos(cam_off.begin(), cam_off.end()); for (int e = 0; e < no; ++e) cam_perm[pos[pb->obs_cam[order[e]]]++] = e; }
+
+  // ---- one pinned blob, one H2D --------------------------------------------------------------------------------------
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_pose = al((size_t)nc * 7 * 8), b_pts = al((size_t)np * 3 * 8), b_dof = al(nc), b_pf = al(np),
+               b_oc = al((size_t)no * 4), b_op = al((size_t)no * 4), b_uv = al((size_t)no * 16),
+               b_info = d.has_info ? al((size_t)no * 24) : 0, b_po = al((size_t)(np + 1) * 4), b_co = al((size_t)(nc + 1) * 4),
+               b_cp = al((size_t)no * 4);
+  const size_t total = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + 256;
+  GB_CHECK(gb_stage_reserve(ctx, ctx->h_stage_off + total + 4096));
+  uint8_t* h = (uint8_t*)gb_stage_alloc(ctx, total);
+  uint8_t* dblob = nullptr;
+  GB_CHECK(ba_alloc(ctx, g, &dblob, total));
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += bytes; return o; };
+  const size_t o_pose = take(b_pose), o_pts = take(b_pts), o_dof = take(b_dof), o_pf = take(b_pf), o_oc = take(b_oc),
+               o_op = take(b_op), o_uv = take(b_uv), o_info = take(b_info), o_po = take(b_po), o_co = take(b_co), o_cp = take(b_cp);
+  memcpy(h + o_pose, pb->cam_pose_wc, (size_t)nc * 56);
+  memcpy(h + o_pts, pb->points, (size_t)np * 24);
+  for (int i = 0; i < nc; ++i) h[o_dof + i] = pb->cam_dof ? (pb->cam_dof[i] & 63) : 63;
+  for (int j = 0; j < np; ++j) h[o_pf + j] = pb->point_free ? (pb->point_free[j] ? 1 : 0) : 1;
+  int* hoc = (int*)(h + o_oc); int* hop = (int*)(h + o_op); double* huv = (double*)(h + o_uv); double* hin = (double*)(h + o_info);
+  for (int e = 0; e < no; ++e) {
+    const int k = order[e];
+    hoc[e] = pb->obs_cam[k];
+    hop[e] = pb->obs_point[k];
+    const double* m = pb->obs_xyz + 3 * (size_t)k;
+    huv[2 * e] = m[0] / m[2];
+    huv[2 * e + 1] = m[1] / m[2];
+    if (d.has_info) {
+      const double* L = pb->obs_info + 4 * (size_t)k;
+      hin[3 * e] = L[0]; hin[3 * e + 1] = 0.5 * (L[1] + L[2]); hin[3 * e + 2] = L[3];
+    }
+  }
+  memcpy(h + o_po, pt_off.data(), (size_t)(np + 1) * 4);
+  memcpy(h + o_co, cam_off.data(), (size_t)(nc + 1) * 4);
+  memcpy(h + o_cp, cam_perm.data(), (size_t)no * 4);
+  GB_CUDA(ctx, cudaMemcpyAsync(dblob, h, total, cudaMemcpyHostToDevice, ctx->stream));
+  double* d_pose_wc = (double*)(dblob + o_pose);
+  g->pts_init = (double*)(dblob + o_pts);
+  d.dof = dblob + o_dof; d.pfree = dblob + o_pf;
+  d.o_cam = (int*)(dblob + o_oc); d.o_pt = (int*)(dblob + o_op); d.o_uv = (double*)(dblob + o_uv);
+  d.o_info = d.has_info ? (double*)(dblob + o_info) : nullptr;
+  d.pt_off = (int*)(dblob + o_po); d.cam_off = (int*)(dblob + o_co); d.cam_perm = (int*)(dblob + o_cp);
+
+  // ---- working set ---------------------------------------------------------------------------------------------------
+  const size_t n6 = 6 * (size_t)nc;
+  GB_CHECK(ba_alloc(ctx, g, &g->pose_init, (size_t)nc * 7));
+  GB_CHECK(ba_alloc(ctx, g, &g->pose_wc_out, (size_t)nc * 7));
+  GB_CHECK(ba_alloc(ctx, g, &d.pose, (size_t)nc * 7));
+  GB_CHECK(ba_alloc(ctx, g, &d.pose_new, (size_t)nc * 7));
+  GB_CHECK(ba_alloc(ctx, g, &d.Rt, (size_t)nc * 12));
+  GB_CHECK(ba_alloc(ctx, g, &d.Rt_new, (size_t)nc * 12));
+  GB_CHECK(ba_alloc(ctx, g, &d.pts, (size_t)np * 3));
+  GB_CHECK(ba_alloc(ctx, g, &d.pts_new, (size_t)np * 3));
+  GB_CHECK(ba_alloc(ctx, g, &d.V, (size_t)np * 9));
+  GB_CHECK(ba_alloc(ctx, g, &d.gp, (size_t)np * 3));
+  GB_CHECK(ba_alloc(ctx, g, &d.Vinv, (size_t)np * 9));
+  GB_CHECK(ba_alloc(ctx, g, &d.W, (size_t)no * 18));
+  GB_CHECK(ba_alloc(ctx, g, &d.U, (size_t)nc * 36));
+  GB_CHECK(ba_alloc(ctx, g, &d.gc, (size_t)nc * 6));
+  GB_CHECK(ba_alloc(ctx, g, &d.cost_pt, (size_t)np));
+  GB_CHECK(ba_alloc(ctx, g, &d.cost_pt_new, (size_t)np));
+  GB_CHECK(ba_alloc(ctx, g, &d.Minv, (size_t)nc * 36));
+  GB_CHECK(ba_alloc(ctx, g, &d.x, n6));
+  GB_CHECK(ba_alloc(ctx, g, &d.r, n6));
+  GB_CHECK(ba_alloc(ctx, g, &d.z, n6));
+  GB_CHECK(ba_alloc(ctx, g, &d.p, n6));
+  GB_CHECK(ba_alloc(ctx, g, &d.q, n6));
+  GB_CHECK(ba_alloc(ctx, g, &d.sc, 1));
+  g->buf_doubles = ba_buf_doubles(nc);
+  GB_CHECK(ba_alloc(ctx, g, &g->buf, g->buf_doubles));
+  GB_CHECK(ba_alloc(ctx, g, &g->d_cost, 8));
+  GB_CUDA(ctx, cudaMemsetAsync(d.sc, 0, sizeof(BaScalars), ctx->stream));
+  if (nc > 0) {
+    ba_prepare_kernel<<<gb_div_up(nc, 128), 128, 0, ctx->stream>>>(nc, d_pose_wc, g->pose_init);
+    GB_LAUNCH_CHECK(ctx);
+  }
+  GB_CHECK(gb_ba_graph_reset(ctx, g));
+  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the pinned blob is reused by the next call
+  guard.ok = true;
+  *out = g;
+  return GB_OK;
+}
+
+int gb_ba_graph_reset(gb_ctx* ctx, gb_ba_graph* g) {
+  if (!ctx || !g) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  BaDev& d = g->d;
+  if (d.nc > 0) GB_CUDA(ctx, cudaMemcpyAsync(d.pose, g->pose_init, (size_t)d.nc * 56, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (d.np > 0) GB_CUDA(ctx, cudaMemcpyAsync(d.pts, g->pts_init, (size_t)d.np * 24, cudaMemcpyDeviceToDevice, ctx->stream));
+  g->begun = false;
+  return GB_OK;
+}
+
+int gb_ba_graph_reduce_size(gb_ctx* ctx, gb_ba_graph* g, size_t* n) {
+  if (!ctx || !g || !n) return GB_ERR_INVALID;
+  *n = g->buf_doubles;
+  return GB_OK;
+}
+
+int gb_ba_graph_begin(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt_in) {
+  if (!ctx || !g) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  gb_ba_options opt;
+  if (opt_in) opt = *opt_in; else gb_ba_options_default(&opt);
+  if (opt.projection != 0) {
+    gb_set_error(ctx, "gb_ba: only PROJECTION_PINHOLE (Optimizer.h:59) is implemented");
+    return GB_ERR_INVALID;
+  }
+  if (opt.max_iterations < 0 || opt.pcg_max_iters < 0) return GB_ERR_INVALID;
+  g->opt = opt;
+  BaScalars h;
+  memset(&h, 0, sizeof h);
+  h.delta = opt.huber_delta; h.ftol = opt.function_tolerance; h.pcg_tol = opt.pcg_tol; h.lambda_init = opt.lambda_init;
+  h.lambda = opt.lambda_init; h.nu = 2.0; h.need_linearize = 1;
+  GB_CHECK(gb_stage_reserve(ctx, ctx->h_stage_off + sizeof h + 512));
+  BaScalars* hs = (BaScalars*)gb_stage_alloc(ctx, sizeof h);
+  *hs = h;
+  GB_CUDA(ctx, cudaMemcpyAsync(g->d.sc, hs, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+  if (g->d.nc > 0) {
+    ba_rt_kernel<<<gb_div_up(g->d.nc, 128), 128, 0, ctx->stream>>>(g->d.nc, g->d.pose, g->d.Rt);
+    GB_LAUNCH_CHECK(ctx);
+  }
+  // hs lives in the per-call staging: drain before returning
+  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  g->begun = true;
+  return GB_OK;
+}
+
+int gb_ba_graph_reduce_local(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
+  if (!ctx || !g || !g->begun) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  BaDev& d = g->d;
+  if (!buf) buf = g->buf;
+  cudaStream_t s = ctx->stream;
+  const size_t n6 = d.n6;
+  if (d.np > 0) { ba_linearize_points_kernel<<<gb_div_up(d.np, kPtThreads), kPtThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
+  if (d.nc > 0) { ba_linearize_cams_kernel<<<d.nc, kCamThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
+  GB_CUDA(ctx, cudaMemsetAsync(buf, 0, g->buf_doubles * sizeof(double), s));
+  ba_reduce_cost_kernel<<<1, kRedThreads, 0, s>>>(d.sc, d.cost_pt, d.np, buf + n6 * n6 + 2 * n6); GB_LAUNCH_CHECK(ctx);
+  if (d.np > 0) { ba_point_inv_kernel<<<gb_div_up(d.np, 128), 128, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
+  if (d.nc > 0) { ba_schur_init_kernel<<<gb_div_up(d.nc * 36, 256), 256, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx); }
+  if (d.no > 0) { ba_schur_accum_kernel<<<gb_div_up(d.no, 128), 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx); }
+  return GB_OK;
+}
+
+int gb_ba_graph_step(gb_ctx* ctx, gb_ba_graph* g, const double* buf_in, double* d_cost) {
+  if (!ctx || !g || !g->begun) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  BaDev& d = g->d;
+  double* buf = buf_in ? (double*)buf_in : g->buf;
+  if (!d_cost) d_cost = g->d_cost;
+  cudaStream_t s = ctx->stream;
+  if (d.nc > 0) {
+    ba_damp_kernel<<<gb_div_up(d.n6, 128), 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+    pcg_init_kernel<<<1, kRedThreads, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+    for (int k = 0; k < g->opt.pcg_max_iters; ++k) {
+      pcg_matvec_kernel<<<gb_div_up(d.n6, 8), 256, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+      pcg_update_kernel<<<1, kRedThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
+    }
+    ba_retract_kernel<<<gb_div_up(d.nc, 128), 128, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
+  }
+  if (d.np > 0) {
+    ba_backsub_kernel<<<gb_div_up(d.np, 128), 128, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
+    ba_cost_points_kernel<<<gb_div_up(d.np, 128), 128, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
+  }
+  ba_reduce_cost_kernel<<<1, kRedThreads, 0, s>>>(d.sc, d.cost_pt_new, d.np, d_cost); GB_LAUNCH_CHECK(ctx);
+  return GB_OK;
+}
+
+int gb_ba_graph_commit(gb_ctx* ctx, gb_ba_graph* g, const double* buf_in, const double* d_cost) {
+  if (!ctx || !g || !g->begun) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  BaDev& d = g->d;
+  const double* buf = buf_in ? buf_in : g->buf;
+  if (!d_cost) d_cost = g->d_cost;
+  cudaStream_t s = ctx->stream;
+  ba_commit_kernel<<<1, 32, 0, s>>>(d, buf, d_cost); GB_LAUNCH_CHECK(ctx);
+  const int n = std::max(std::max(d.nc * 12, d.np * 3), 1);
+  ba_apply_kernel<<<gb_div_up(n, 256), 256, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
+  ba_clear_accept_kernel<<<1, 1, 0, s>>>(d.sc); GB_LAUNCH_CHECK(ctx);
+  return GB_OK;
+}
+
+static int ba_read_scalars(gb_ctx* ctx, gb_ba_graph* g, BaScalars* out) {
+  GB_CUDA(ctx, cudaMemcpyAsync(out, g->d.sc, sizeof(BaScalars), cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GB_OK;
+}
+
+int gb_ba_graph_finish(gb_ctx* ctx, gb_ba_graph* g, gb_ba_result* res) {
+  if (!ctx || !g || !g->begun) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  BaScalars h;
+  GB_CHECK(ba_read_scalars(ctx, g, &h));
+  if (res) {
+    res->initial_cost = h.initial_cost;
+    res->final_cost = h.cost;
+    res->iterations = h.iterations;
+    res->accepted = h.accepted;
+    res->pcg_iterations = h.pcg_iters;
+    res->status = h.status;
+    res->lambda_final = h.lambda;
+  }
+  if (!std::isfinite(h.cost)) {
+    gb_set_error(ctx, "gb_ba: non-finite cost");
+    return GB_ERR_NUMERIC;
+  }
+  return GB_OK;
+}
+
+int gb_ba_graph_solve(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, gb_ba_result* res) {
+  if (!ctx || !g) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  GB_CHECK(gb_ba_graph_begin(ctx, g, opt));
+  GB_CUDA(ctx, cudaEventRecord(ctx->evs, ctx->stream));
+  const bool poll = g->opt.function_tolerance > 0.0 || g->opt.verbose;
+  for (int it = 0; it < g->opt.max_iterations; ++it) {
+    GB_CHECK(gb_ba_graph_reduce_local(ctx, g, nullptr));
+    GB_CHECK(gb_ba_graph_step(ctx, g, nullptr, nullptr));
+    GB_CHECK(gb_ba_graph_commit(ctx, g, nullptr, nullptr));
+    if (poll) {
+      BaScalars h;
+      GB_CHECK(ba_read_scalars(ctx, g, &h));
+      if (g->opt.verbose)
+        fprintf(stderr, "[gb_ba] it %d cost %.12e lambda %.3e accepted %d pcg %d%s\n", it, h.cost, h.lambda, h.accepted,
+                h.pcg_iters, h.stop ? " stop" : "");
+      if (h.stop) break;
+    }
+  }
+  GB_CUDA(ctx, cudaEventRecord(ctx->eve, ctx->stream));
+  GB_CHECK(gb_ba_graph_finish(ctx, g, res));
+  if (res) {
+    GB_CUDA(ctx, cudaEventSynchronize(ctx->eve));
+    GB_CUDA(ctx, cudaEventElapsedTime(&res->gpu_ms, ctx->evs, ctx->eve));
+  }
+  return GB_OK;
+}
+
+int gb_ba_graph_download(gb_ctx* ctx, gb_ba_graph* g, double* cam_pose_wc, double* points) {
+  if (!ctx || !g) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  BaDev& d = g->d;
+  const size_t bp = (size_t)d.nc * 56, bx = (size_t)d.np * 24;
+  GB_CHECK(gb_stage_reserve(ctx, ctx->h_stage_off + bp + bx + 1024));
+  double* hp = (double*)gb_stage_alloc(ctx, bp + 8);
+  double* hx = (double*)gb_stage_alloc(ctx, bx + 8);
+  if (cam_pose_wc && d.nc > 0) {
+    ba_finalize_kernel<<<gb_div_up(d.nc, 128), 128, 0, ctx->stream>>>(d.nc, d.pose, g->pose_wc_out);
+    GB_LAUNCH_CHECK(ctx);
+    GB_CUDA(ctx, cudaMemcpyAsync(hp, g->pose_wc_out, bp, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (points && d.np > 0) GB_CUDA(ctx, cudaMemcpyAsync(hx, d.pts, bx, cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (cam_pose_wc && d.nc > 0) memcpy(cam_pose_wc, hp, bp);
+  if (points && d.np > 0) memcpy(points, hx, bx);
+  return GB_OK;
+}
+
+int gb_ba_solve(gb_ctx* ctx, gb_ba_problem* pb, const gb_ba_options* opt, gb_ba_result* res) {
+  if (!ctx || !pb) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  gb_ba_graph* g = nullptr;
+  GB_CHECK(gb_ba_graph_create(ctx, pb, &g));
+  int rc = gb_ba_graph_solve(ctx, g, opt, res);
+  if (rc == GB_OK) rc = gb_ba_graph_download(ctx, g, pb->cam_pose_wc, pb->points);
+  gb_ba_graph_destroy(ctx, g);
+  return rc;
+}
+
+int gb_ba_pnp(gb_ctx* ctx, int n, const double* xyz, const double* xy1, double* pose_wc, int dof, double* info6x6,
+              const gb_ba_options* opt, gb_ba_result* res) {
+  if (!ctx || n < 0 || !pose_wc || (n > 0 && (!xyz || !xy1))) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  // optimizePnP == the same solver on a one-camera graph whose landmarks are all fixed (Optimizer.h:202-207)
+  std::vector<double> pts(xyz, xyz + 3 * (size_t)n);
+  std::vector<uint8_t> pf((size_t)n + 1, 0);
+  std::vector<int32_t> oc((size_t)n + 1, 0), op((size_t)n + 1, 0);
+  for (int k = 0; k < n; ++k) op[k] = k;
+  uint8_t d = (uint8_t)(dof & 63);
+  gb_ba_problem pb;
+  memset(&pb, 0, sizeof pb);
+  pb.n_cams = 1; pb.n_points = n; pb.n_obs = n;
+  pb.cam_pose_wc = pose_wc; pb.cam_dof = &d; pb.points = pts.data(); pb.point_free = pf.data();
+  pb.obs_cam = oc.data(); pb.obs_point = op.data(); pb.obs_xyz = xy1; pb.obs_info = nullptr;
+  gb_ba_graph* g = nullptr;
+  GB_CHECK(gb_ba_graph_create(ctx, &pb, &g));
+  int rc = gb_ba_graph_solve(ctx, g, opt, res);
+  if (rc == GB_OK) rc = gb_ba_graph_download(ctx, g, pose_wc, nullptr);
+  if (rc == GB_OK && info6x6) {
+    // information of the returned pose: U at the final estimate (re-linearise once; the graph holds the final state)
+    BaScalars h;
+    rc = ba_read_scalars(ctx, g, &h);
+    if (rc == GB_OK) {
+      h.stop = 0; h.need_linearize = 1;
+      cudaMemcpyAsync(g->d.sc, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream);
+      ba_linearize_cams_kernel<<<1, kCamThreads, 0, ctx->stream>>>(g->d);
+      ctx->launches++;
+      cudaMemcpyAsync(info6x6, g->d.U, 36 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+      cudaError_t e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) { gb_set_error(ctx, "gb_ba_pnp info -> %s", cudaGetErrorString(e)); rc = GB_ERR_CUDA; }
+    }
+  }
+  gb_ba_graph_destroy(ctx, g);
+  return rc;
+}
+
+// ---- test hooks: expose the intermediates of one linearisation / reduced system in the CALLER's edge order -------------
+GB_API int gb_dbg_ba_linearize(gb_ctx* ctx, gb_ba_graph* g, double delta, double* U, double* gc, double* V, double* gp,
+                               double* W, double* cost) {
+  if (!ctx || !g) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  gb_ba_options o;
+  gb_ba_options_default(&o);
+  o.huber_delta = delta;
+  GB_CHECK(gb_ba_graph_begin(ctx, g, &o));
+  GB_CHECK(gb_ba_graph_reduce_local(ctx, g, nullptr));
+  BaDev& d = g->d;
+  const size_t n6 = d.n6;
+  std::vector<double> Ws((size_t)d.no * 18 + 1);
+  if (U) GB_CUDA(ctx, cudaMemcpyAsync(U, d.U, (size_t)d.nc * 36 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (gc) GB_CUDA(ctx, cudaMemcpyAsync(gc, d.gc, (size_t)d.nc * 6 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (V) GB_CUDA(ctx, cudaMemcpyAsync(V, d.V, (size_t)d.np * 9 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (gp) GB_CUDA(ctx, cudaMemcpyAsync(gp, d.gp, (size_t)d.np * 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (W) GB_CUDA(ctx, cudaMemcpyAsync(Ws.data(), d.W, (size_t)d.no * 18 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cost) GB_CUDA(ctx, cudaMemcpyAsync(cost, g->buf + n6 * n6 + 2 * n6, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (W)
+    for (int e = 0; e < d.no; ++e) memcpy(W + 18 * (size_t)g->sorted_to_orig[e], Ws.data() + 18 * (size_t)e, 18 * 8);
+  return GB_OK;
+}
+
+GB_API int gb_dbg_ba_reduced(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, double* S, double* gt, double* dc,
+                             int* pcg_iters) {
+  if (!ctx || !g) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  GB_CHECK(gb_ba_graph_begin(ctx, g, opt));
+  GB_CHECK(gb_ba_graph_reduce_local(ctx, g, nullptr));
+  GB_CHECK(gb_ba_graph_step(ctx, g, nullptr, nullptr));
+  BaDev& d = g->d;
+  const size_t n6 = d.n6;
+  if (S) GB_CUDA(ctx, cudaMemcpyAsync(S, g->buf, n6 * n6 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (gt) GB_CUDA(ctx, cudaMemcpyAsync(gt, g->buf + n6 * n6, n6 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (dc) GB_CUDA(ctx, cudaMemcpyAsync(dc, d.x, n6 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  BaScalars h;
+  GB_CHECK(ba_read_scalars(ctx, g, &h));
+  if (pcg_iters) *pcg_iters = h.pcg_iters;
+  return GB_OK;
+}
+
+}  // extern "C"

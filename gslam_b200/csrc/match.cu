@@ -1,0 +1,234 @@
+// gslam_b200/csrc/match.cu — 256-bit Hamming brute-force matcher (K5).
+//
+// Behind: Vocabulary::DistanceFactory::hamming32 (GSLAM/core/Vocabulary.h:485-491) as the distance; argmin/2nd-best with
+// cv::BFMatcher(NORM_HAMMING) tie rules (lowest train index).
+//
+// Shape of the work: Q x T pairs, each 8 XOR + 8 POPC + adds on 32-byte rows.  Algorithmic HBM traffic is only
+// 32(Q+T)+12Q bytes, so this kernel is bound by the integer POPC pipe, not by HBM.  One thread owns
+// one query row in registers; a CTA stages a chunk of train rows in shared memory and every lane reads the same row
+// (broadcast, conflict-free).  The train dimension is split across blockIdx.y so that Q=2000 still fills 148 SMs; the
+// last CTA of each query tile (atomic ticket) merges the per-chunk (best, 2nd) partials in ascending chunk order, which
+// reproduces the sequential "first minimum wins" tie rule exactly.  One launch, no atomics on the data path.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kQPerCta = 128;  // threads per CTA == queries per CTA
+
+struct MatchPartial {
+  int32_t d0, b0, d1;
+};
+
+__device__ __forceinline__ int ham256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
+         __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void __launch_bounds__(kQPerCta) match_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t,
+                                                         int nt, int chunk, MatchPartial* __restrict__ partial,
+                                                         unsigned int* __restrict__ tickets, int32_t* __restrict__ best_idx,
+                                                         int32_t* __restrict__ best_dist, int32_t* __restrict__ second_dist) {
+  extern __shared__ uint4 s_train[];  // chunk rows x 2 uint4
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+  const int qi = blockIdx.x * kQPerCta + tid;
+  const int t0 = blockIdx.y * chunk;
+  const int tn = min(chunk, nt - t0);
+
+  // stage the train chunk: 2 uint4 per row, fully coalesced
+  for (int i = tid; i < tn * 2; i += kQPerCta) s_train[i] = __ldg(t + (size_t)t0 * 2 + i);
+  uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+  if (qi < nq) {
+    q0 = __ldg(q + (size_t)qi * 2);
+    q1 = __ldg(q + (size_t)qi * 2 + 1);
+  }
+  __syncthreads();
+
+  int d0 = 257, d1 = 257, b0 = -1;
+#pragma unroll 4
+  for (int j = 0; j < tn; ++j) {
+    const uint4 a = s_train[2 * j], b = s_train[2 * j + 1];
+    const int d = ham256(q0, q1, a, b);
+    const bool lt = d < d0;
+    d1 = lt ? d0 : min(d1, d);
+    b0 = lt ? (t0 + j) : b0;
+    d0 = lt ? d : d0;
+  }
+
+  const int nsplit = gridDim.y;
+  if (nsplit == 1) {
+    if (qi < nq) {
+      if (best_idx) best_idx[qi] = b0;
+      if (best_dist) best_dist[qi] = d0;
+      if (second_dist) second_dist[qi] = d1;
+    }
+    return;
+  }
+  if (qi < nq) {
+    MatchPartial p;
+    p.d0 = d0;
+    p.b0 = b0;
+    p.d1 = d1;
+    partial[(size_t)blockIdx.y * nq + qi] = p;  // [split][query]: coalesced across the CTA
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int prev = atomicAdd(&tickets[blockIdx.x], 1u);
+    s_last = (prev == (unsigned int)nsplit - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (qi < nq) {
+    int D0 = 257, D1 = 257, B0 = -1;
+    for (int s = 0; s < nsplit; ++s) {  // ascending train index == sequential scan order
+      const MatchPartial* pp = partial + (size_t)s * nq + qi;
+      const int pd0 = __ldcg(&pp->d0), pb0 = __ldcg(&pp->b0), pd1 = __ldcg(&pp->d1);
+      if (pd0 < D0) {
+        D1 = min(D0, pd1);
+        D0 = pd0;
+        B0 = pb0;
+      } else {
+        D1 = min(D1, pd0);
+      }
+    }
+    if (best_idx) best_idx[qi] = B0;
+    if (best_dist) best_dist[qi] = D0;
+    if (second_dist) second_dist[qi] = D1;
+  }
+  if (tid == 0) tickets[blockIdx.x] = 0;  // re-arm for the next launch on this stream
+}
+
+}  // namespace
+
+struct MatchState {
+  void* d_partial = nullptr;
+  size_t partial_cap = 0;
+  void* d_tickets = nullptr;
+  size_t tickets_cap = 0;
+};
+
+void gb_match_state_free(gb_ctx* ctx) {
+  if (!ctx->match) return;
+  cudaFree(ctx->match->d_partial);
+  cudaFree(ctx->match->d_tickets);
+  delete ctx->match;
+  ctx->match = nullptr;
+}
+
+// Enqueue the match of (d_q, nq) against (d_t, nt) on the ctx stream.  Outputs are device pointers (may be null).
+int gb_match_launch(gb_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int32_t* d_best, int32_t* d_dist,
+                    int32_t* d_dist2) {
+  if (nq <= 0) return GB_OK;
+  if (!ctx->match) ctx->match = new MatchState();
+  MatchState* ms = ctx->match;
+  const int qtiles = gb_div_up(nq, kQPerCta);
+  // split the train rows so that ~2 CTAs land on every SM; chunk is a multiple of 8 rows, at most 1024 rows (32 KB)
+  int nsplit = 1, chunk = nt > 0 ? nt : 1;
+  if (nt > 0) {
+    nsplit = gb_div_up(2 * ctx->sm_count, qtiles);
+    const int max_split = gb_div_up(nt, 32);
+    if (nsplit > max_split) nsplit = max_split;
+    if (nsplit < 1) nsplit = 1;
+    chunk = gb_div_up(gb_div_up(nt, nsplit), 8) * 8;
+    if (chunk > 1024) chunk = 1024;
+    nsplit = gb_div_up(nt, chunk);
+  }
+  if (nt <= 0) {  // nothing to match against: -1 / 257 / 257 through the same kernel with an empty chunk
+    nsplit = 1;
+    chunk = 8;
+  }
+  GB_CHECK(gb_dev_realloc(ctx, &ms->d_partial, &ms->partial_cap, (size_t)nsplit * nq * sizeof(MatchPartial)));
+  if ((size_t)qtiles * sizeof(unsigned int) > ms->tickets_cap) {
+    GB_CHECK(gb_dev_realloc(ctx, &ms->d_tickets, &ms->tickets_cap, (size_t)qtiles * sizeof(unsigned int)));
+    GB_CUDA(ctx, cudaMemsetAsync(ms->d_tickets, 0, ms->tickets_cap, ctx->stream));
+  }
+  dim3 grid(qtiles, nsplit);
+  const size_t smem = (size_t)chunk * 32;
+  match_kernel<<<grid, kQPerCta, smem, ctx->stream>>>((const uint4*)d_q, nq, (const uint4*)d_t, nt > 0 ? nt : 0, chunk,
+                                                      (MatchPartial*)ms->d_partial, (unsigned int*)ms->d_tickets, d_best,
+                                                      d_dist, d_dist2);
+  GB_LAUNCH_CHECK(ctx);
+  return GB_OK;
+}
+
+extern "C" {
+
+int gb_match_features(gb_ctx* ctx, gb_features* fq, gb_features* ft) {
+  if (!ctx || !fq || !ft) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  int nq = 0, nt = 0;
+  GB_CHECK(gb_features_count(ctx, fq, &nq));
+  GB_CHECK(gb_features_count(ctx, ft, &nt));
+  fq->n_matched = nq;
+  return gb_match_launch(ctx, fq->d_desc, nq, ft->d_desc, nt, fq->d_best, fq->d_dist, fq->d_dist2);
+}
+
+int gb_match_download(gb_ctx* ctx, gb_features* fq, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist, int* n) {
+  if (!ctx || !fq || !n) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  const int cap = *n, cnt = fq->n_matched;
+  *n = cnt;
+  if (cnt > cap) {
+    gb_set_error(ctx, "gb_match_download: %d matches > caller capacity %d", cnt, cap);
+    return GB_ERR_CAPACITY;
+  }
+  if (cnt == 0) return GB_OK;
+  const size_t bytes = (size_t)cnt * sizeof(int32_t);
+  GB_CHECK(gb_stage_reserve(ctx, ctx->h_stage_off + 3 * bytes + 1024));
+  int32_t* h0 = (int32_t*)gb_stage_alloc(ctx, bytes);
+  int32_t* h1 = (int32_t*)gb_stage_alloc(ctx, bytes);
+  int32_t* h2 = (int32_t*)gb_stage_alloc(ctx, bytes);
+  if (best_idx) GB_CUDA(ctx, cudaMemcpyAsync(h0, fq->d_best, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (best_dist) GB_CUDA(ctx, cudaMemcpyAsync(h1, fq->d_dist, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (second_dist) GB_CUDA(ctx, cudaMemcpyAsync(h2, fq->d_dist2, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (best_idx) memcpy(best_idx, h0, bytes);
+  if (best_dist) memcpy(best_dist, h1, bytes);
+  if (second_dist) memcpy(second_dist, h2, bytes);
+  return GB_OK;
+}
+
+int gb_match_hamming(gb_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt, int32_t* best_idx,
+                     int32_t* best_dist, int32_t* second_dist) {
+  if (!ctx || nq < 0 || nt < 0 || (nq > 0 && !query) || (nt > 0 && !train)) return GB_ERR_INVALID;
+  if (nq == 0) return GB_OK;
+  CtxLock lk(ctx);
+  auto ensure = [&](gb_features** f, int n) -> int {
+    if (*f && (*f)->capacity >= n) return GB_OK;
+    if (*f) gb_features_destroy(ctx, *f);
+    *f = nullptr;
+    return gb_features_create(ctx, n + n / 4 + 64, f);
+  };
+  GB_CHECK(ensure(&ctx->tmp_q, nq));
+  GB_CHECK(ensure(&ctx->tmp_t, nt > 0 ? nt : 1));
+  gb_features *fq = ctx->tmp_q, *ft = ctx->tmp_t;
+  const size_t bq = (size_t)nq * 32, bt = (size_t)nt * 32, bo = (size_t)nq * sizeof(int32_t);
+  GB_CHECK(gb_stage_reserve(ctx, bq + bt + 3 * bo + 4096));
+  uint8_t* hq = (uint8_t*)gb_stage_alloc(ctx, bq);
+  memcpy(hq, query, bq);
+  GB_CUDA(ctx, cudaMemcpyAsync(fq->d_desc, hq, bq, cudaMemcpyHostToDevice, ctx->stream));
+  if (nt > 0) {
+    uint8_t* ht = (uint8_t*)gb_stage_alloc(ctx, bt);
+    memcpy(ht, train, bt);
+    GB_CUDA(ctx, cudaMemcpyAsync(ft->d_desc, ht, bt, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  fq->h_count = nq;
+  ft->h_count = nt;
+  fq->n_matched = nq;
+  GB_CHECK(gb_match_launch(ctx, fq->d_desc, nq, ft->d_desc, nt, fq->d_best, fq->d_dist, fq->d_dist2));
+  int32_t* h0 = (int32_t*)gb_stage_alloc(ctx, bo);
+  int32_t* h1 = (int32_t*)gb_stage_alloc(ctx, bo);
+  int32_t* h2 = (int32_t*)gb_stage_alloc(ctx, bo);
+  if (best_idx) GB_CUDA(ctx, cudaMemcpyAsync(h0, fq->d_best, bo, cudaMemcpyDeviceToHost, ctx->stream));
+  if (best_dist) GB_CUDA(ctx, cudaMemcpyAsync(h1, fq->d_dist, bo, cudaMemcpyDeviceToHost, ctx->stream));
+  if (second_dist) GB_CUDA(ctx, cudaMemcpyAsync(h2, fq->d_dist2, bo, cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (best_idx) memcpy(best_idx, h0, bo);
+  if (best_dist) memcpy(best_dist, h1, bo);
+  if (second_dist) memcpy(second_dist, h2, bo);
+  return GB_OK;
+}
+
+}  // extern "C"

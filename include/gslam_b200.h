@@ -1,0 +1,236 @@
+/*
+ * gslam_b200.h — the C-ABI drop-in boundary of the B200 backends for GSLAM's per-frame numeric hot path
+ * (ORB extract -> 256-bit Hamming brute-force match -> GSLAM::Optimizer bundle adjustment).
+ *
+ * Plain C: opaque handles, plain pointers and sizes, `int` status returns, caller-owned output buffers.  No STL, no
+ * Svar, no torch types.  Everything the reference-facing C++ plugins (under gslam_b200/plugin: `libgslam_optimizer.so`
+ * exporting `createOptimizerInstance`, and the Svar module `libgslam_b200.so`) need is here; so is everything a
+ * ctypes / cgo / JNI binding would need (INTEGRATION.md shows the stubs).
+ *
+ * Reference interfaces each entry point sits behind (paths relative to the GSLAM tree):
+ *   gb_orb_extract      <- consumes GSLAM::GImage            GSLAM/core/GImage.h:160-443   (dense 8UC1, no row stride :378)
+ *                          emits    GSLAM::KeyPoint           GSLAM/core/Map.h:122-195      (28-byte record, == gb_keypoint)
+ *                          emits    N x 32 8UC1 descriptors   GSLAM/core/Map.h:311-312,321  (MapFrame::setKeyPoints/getDescriptor)
+ *   gb_match_hamming    <- distance == Vocabulary::DistanceFactory::hamming32  GSLAM/core/Vocabulary.h:485-491
+ *   gb_ba_solve         <- GSLAM::Optimizer::optimize(BundleGraph&)            GSLAM/core/Optimizer.h:229 (graph PODs :106-172)
+ *   gb_ba_pnp           <- GSLAM::Optimizer::optimizePnP(matches, SE3&, dof, information)  GSLAM/core/Optimizer.h:202-207
+ *   gb_ba_options       <- GSLAM::OptimzeConfig                                GSLAM/core/Optimizer.h:174-182
+ *
+ * Error behaviour mirrors the reference's plugin convention (Optimizer.h:193-232: every virtual returns bool, nothing
+ * throws across the boundary): every function returns GB_OK (0) or a GB_ERR_* code and never throws; a human-readable
+ * message is available from gb_last_error().  There is NO CPU fallback: without a usable CUDA device gb_ctx_create
+ * fails with GB_ERR_NODEVICE and every compute entry point fails loudly.
+ *
+ * Threading: a gb_ctx owns one CUDA stream, its device buffers and pinned staging; calls on one ctx are serialised by an
+ * internal mutex (the reference documents no re-entrancy guarantee).  Use one ctx per calling thread for
+ * concurrency (e.g. tracking thread: extract/match/pnp; mapping thread: local BA).
+ */
+#ifndef GSLAM_B200_H_
+#define GSLAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GB_API __attribute__((visibility("default")))
+#else
+#define GB_API
+#endif
+
+#define GB_VERSION 100 /* major*100 + minor */
+
+/* ---- status codes --------------------------------------------------------------------------------------------- */
+enum {
+  GB_OK = 0,
+  GB_ERR_INVALID = 1,  /* bad argument / unsupported configuration                         */
+  GB_ERR_CUDA = 2,     /* a CUDA runtime call or kernel failed (message in gb_last_error)  */
+  GB_ERR_CAPACITY = 3, /* caller buffer too small; required size reported via the in/out n */
+  GB_ERR_NODEVICE = 4, /* no usable CUDA device (there is no CPU fallback)                 */
+  GB_ERR_NUMERIC = 5   /* solver produced a non-finite value                               */
+};
+
+typedef struct gb_ctx gb_ctx;           /* one device + one stream + cached buffers            */
+typedef struct gb_features gb_features; /* a frame's keypoints + descriptors resident in HBM   */
+typedef struct gb_ba_graph gb_ba_graph; /* a bundle-adjustment graph resident in HBM           */
+
+/* ---- context ---------------------------------------------------------------------------------------------------- */
+GB_API int gb_version(void);
+GB_API int gb_device_count(int* n);
+GB_API int gb_ctx_create(int device, gb_ctx** out);
+GB_API int gb_ctx_destroy(gb_ctx* ctx);
+/* Last error message of `ctx` (or of the calling thread when ctx==NULL).  Never NULL; valid until the next call. */
+GB_API const char* gb_last_error(const gb_ctx* ctx);
+/* The ctx's cudaStream_t (as void*) so a host can order its own work / record its own events on it. */
+GB_API void* gb_ctx_stream(gb_ctx* ctx);
+GB_API int gb_ctx_sync(gb_ctx* ctx);
+/* CUDA-event stopwatch on the ctx stream (begin records an event; end records another, synchronises, returns ms). */
+GB_API int gb_timer_begin(gb_ctx* ctx);
+GB_API int gb_timer_end(gb_ctx* ctx, float* ms);
+/* Number of kernels this ctx has launched so far (for bench.py's gpu_launches). */
+GB_API int64_t gb_launch_count(const gb_ctx* ctx);
+
+/* ---- ORB extract ------------------------------------------------------------------------------------------------ */
+/* Field-for-field GSLAM::KeyPoint (Map.h:180-194) == cv::KeyPoint: 28 bytes. */
+typedef struct gb_keypoint {
+  float x, y;       /* pt: level coords * float(scale^octave)          */
+  float size;       /* 31 * scale^octave                               */
+  float angle;      /* degrees [0,360), intensity-centroid orientation */
+  float response;   /* Harris response                                 */
+  int32_t octave;   /* pyramid level                                   */
+  int32_t class_id; /* -1                                              */
+} gb_keypoint;
+
+/* Same knobs (and defaults) as cv::ORB::create — the CPU path GSLAM's SLAM plugins call. */
+typedef struct gb_orb_cfg {
+  int32_t nfeatures;      /* 500 in OpenCV; benchmarks use 1000 / 2000 */
+  float scale_factor;     /* 1.2f                                       */
+  int32_t nlevels;        /* 8   (1..GB_ORB_MAX_LEVELS)                 */
+  int32_t edge_threshold; /* 31  (must be >= 22)         */
+  int32_t first_level;    /* 0   (only 0 supported)                     */
+  int32_t wta_k;          /* 2   (only 2 supported)                     */
+  int32_t score_type;     /* 0 = HARRIS_SCORE (only 0 supported)        */
+  int32_t patch_size;     /* 31  (only 31 supported)                    */
+  int32_t fast_threshold; /* 20                                         */
+} gb_orb_cfg;
+#define GB_ORB_MAX_LEVELS 12
+GB_API void gb_orb_cfg_default(gb_orb_cfg* cfg);
+
+/*
+ * Host-buffer entry point (what the Svar plugin's orb_extract binds).  `img` is a dense 8UC1 GImage payload
+ * (rows*cols bytes, row i at img + i*width, GImage.h:378), host memory, read-only.  On input *n is the capacity of `kps`
+ * (records) and `desc` (rows of 32 bytes); on output the number of keypoints.  Output order is canonical:
+ * ascending (octave, y, x) — OpenCV's own intra-level order is an artefact of std::nth_element.
+ * If more keypoints are kept than capacity (ties at the selection thresholds are kept, like OpenCV's retainBest) the
+ * call returns GB_ERR_CAPACITY with *n = required capacity and writes nothing.
+ */
+GB_API int gb_orb_extract(gb_ctx* ctx, const uint8_t* img, int width, int height, const gb_orb_cfg* cfg,
+                          gb_keypoint* kps, uint8_t* desc, int* n);
+
+/* Device-resident variants: the frame and/or the results stay in HBM (bench `value`, chained pipelines). */
+GB_API int gb_features_create(gb_ctx* ctx, int capacity, gb_features** out);
+GB_API int gb_features_destroy(gb_ctx* ctx, gb_features* f);
+/* img_is_device: 0 = host pointer (copied H2D through pinned staging), 1 = device pointer, `pitch` bytes per row. */
+GB_API int gb_orb_extract_to(gb_ctx* ctx, const uint8_t* img, int img_is_device, int width, int height, int pitch,
+                             const gb_orb_cfg* cfg, gb_features* out);
+/* Blocks until the extraction on `f` finished; returns its keypoint count. */
+GB_API int gb_features_count(gb_ctx* ctx, gb_features* f, int* n);
+/* Replace the contents of `f` with caller-provided descriptors (and optional keypoints) — e.g. map-point descriptors. */
+GB_API int gb_features_upload(gb_ctx* ctx, gb_features* f, const gb_keypoint* kps, const uint8_t* desc, int n);
+GB_API int gb_features_download(gb_ctx* ctx, gb_features* f, gb_keypoint* kps, uint8_t* desc, int* n);
+
+/* ---- 256-bit Hamming brute-force match ---------------------------------------------------------------------------- */
+/*
+ * For every query row q (32 bytes) find the train row with the smallest popcount(q XOR t) (== hamming32,
+ * Vocabulary.h:485-491); ties -> lowest train index (cv::BFMatcher(NORM_HAMMING) semantics).
+ * best_idx[i] = argmin (-1 if nt==0), best_dist[i] = its distance, second_dist[i] = distance of the 2nd-nearest
+ * neighbour in (distance, index) order (== knnMatch(k=2)[1].distance; 257 if nt<2).  Any output pointer may be NULL.
+ */
+GB_API int gb_match_hamming(gb_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt, int32_t* best_idx,
+                            int32_t* best_dist, int32_t* second_dist);
+/* Device-resident: match fq against ft; results stay on device until gb_match_download. */
+GB_API int gb_match_features(gb_ctx* ctx, gb_features* fq, gb_features* ft);
+GB_API int gb_match_download(gb_ctx* ctx, gb_features* fq, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist,
+                             int* n);
+
+/* ---- bundle adjustment ---------------------------------------------------------------------------------------------- */
+/*
+ * SoA mirror of GSLAM::BundleGraph's mappoint part (Optimizer.h:150-172).  The C++ plugin repacks the graph's AoS
+ * vectors into these arrays (and back) — INTEGRATION.md.
+ *   cam_pose_wc : n_cams x 7 doubles {qx,qy,qz,qw, tx,ty,tz} = the first 7 doubles of KeyFrameEstimzation::estimation
+ *                 (SIM3 = SE3{SO3{x,y,z,w},Point3d} + scale, SE3.h:337-339, SIM3.h:290-291): T_wc, camera -> world
+ *                 (Optimizer.h:117).  IN/OUT.
+ *   cam_dof     : n_cams bytes, low 6 bits of KeyFrameEstimzationDOF (Optimizer.h:70-84): bit k frees component k of the
+ *                 left tangent [v(3), w(3)] of T_cw.  0 = UPDATE_KF_NONE (fixed), 63 = UPDATE_KF_SE3.  NULL = all 63.
+ *   points      : n_points x 3 world coordinates (MapPointEstimation.first, Optimizer.h:113-114).  IN/OUT.
+ *   point_free  : n_points bytes, MapPointEstimation.second (true = NOT fixed).  NULL = all free.
+ *   obs_cam/obs_point : BundleEdge::frameId / pointId (indices into the two arrays above, Optimizer.h:121-125).
+ *   obs_xyz     : n_obs x 3, BundleEdge::measurement, a CameraAnchor (Optimizer.h:102-103); PROJECTION_PINHOLE uses
+ *                 (x/z, y/z).
+ *   obs_info    : n_obs x 4 row-major 2x2 information matrices, or NULL (= identity for every edge, the usual
+ *                 BundleEdge::information == NULL case).
+ */
+typedef struct gb_ba_problem {
+  int32_t n_cams, n_points, n_obs;
+  double* cam_pose_wc;
+  const uint8_t* cam_dof;
+  double* points;
+  const uint8_t* point_free;
+  const int32_t* obs_cam;
+  const int32_t* obs_point;
+  const double* obs_xyz;
+  const double* obs_info;
+} gb_ba_problem;
+
+/* GSLAM::OptimzeConfig (Optimizer.h:174-182) + the solver knobs the reference leaves to its (absent) Ceres plugin. */
+typedef struct gb_ba_options {
+  int32_t projection;       /* 0 = PROJECTION_PINHOLE (only 0 supported)                               */
+  double huber_delta;       /* projectErrorHuberThreshold, 0.01 (normalised units); <=0 disables Huber */
+  int32_t max_iterations;   /* LM iterations (linear solves), reference default 500                    */
+  int32_t verbose;          /* print one line per iteration to stderr                                  */
+  double function_tolerance;/* stop when |dcost|/cost < tol after an accepted step (1e-6); 0 = never   */
+  double lambda_init;       /* initial LM damping, 1e-4                                                 */
+  int32_t pcg_max_iters;    /* block-Jacobi PCG iteration cap on the reduced camera system, 50         */
+  double pcg_tol;           /* stop when sqrt(r'z / r0'z0) < tol, 1e-10                                 */
+} gb_ba_options;
+GB_API void gb_ba_options_default(gb_ba_options* opt);
+
+typedef struct gb_ba_result {
+  double initial_cost; /* 0.5 * sum rho(e^2) at the input estimate (Ceres convention) */
+  double final_cost;   /* ... at the returned estimate                                */
+  int32_t iterations;  /* LM iterations performed (linear solves)                     */
+  int32_t accepted;    /* of which accepted                                           */
+  int32_t pcg_iterations; /* total PCG iterations                                     */
+  int32_t status;      /* 0 = iteration cap, 1 = function tolerance, 2 = no progress (lambda overflow) */
+  double lambda_final;
+  float gpu_ms;        /* device time of the solve (CUDA events on the ctx stream)    */
+} gb_ba_result;
+
+/* Host-buffer entry point (what libgslam_optimizer.so's optimize() binds): uploads, solves, writes poses/points back. */
+GB_API int gb_ba_solve(gb_ctx* ctx, gb_ba_problem* problem, const gb_ba_options* opt, gb_ba_result* result);
+
+/*
+ * Pose-only refinement from 3D-2D matches (Optimizer::optimizePnP, Optimizer.h:202-207).
+ *   xyz: n x 3 world points; xy1: n x 3 CameraAnchor measurements; pose_wc: 7 doubles IN/OUT (SE3 layout, T_wc);
+ *   dof: KeyFrameEstimzationDOF low 6 bits; info6x6: NULL, or 36 doubles that RECEIVE the row-major 6x6 information
+ *   (Gauss-Newton Hessian sum w J'J, undamped, tangent order [v,w] of T_cw) of the returned pose.  The reference leaves
+ *   the meaning of this non-const `double* information` unspecified; an output is the reading we fix.
+ */
+GB_API int gb_ba_pnp(gb_ctx* ctx, int n, const double* xyz, const double* xy1, double* pose_wc, int dof,
+                     double* info6x6, const gb_ba_options* opt, gb_ba_result* result);
+
+/* Device-resident graph: upload once (host-side ordering + H2D), solve many times from the same initial estimate. */
+GB_API int gb_ba_graph_create(gb_ctx* ctx, const gb_ba_problem* problem, gb_ba_graph** out);
+GB_API int gb_ba_graph_destroy(gb_ctx* ctx, gb_ba_graph* g);
+GB_API int gb_ba_graph_reset(gb_ctx* ctx, gb_ba_graph* g); /* restore the uploaded estimate (device-to-device) */
+GB_API int gb_ba_graph_solve(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, gb_ba_result* result);
+GB_API int gb_ba_graph_download(gb_ctx* ctx, gb_ba_graph* g, double* cam_pose_wc, double* points);
+
+/*
+ * Stepwise interface for landmark-sharded multi-GPU global BA: every rank holds all cameras and a
+ * shard of the landmarks with all their edges.  One LM iteration is
+ *   gb_ba_graph_reduce_local   : linearise the shard at the current estimate (if needed), form the shard's Schur
+ *                                contribution into `d_buf` (device, gb_ba_graph_reduce_size doubles):
+ *                                [ S (6n x 6n, undamped) | g~ (6n) | diag U (6n) | cost (1) | pad ]
+ *   <all-reduce d_buf across ranks, sum, f64 — the path's single exchange step; the host does it with NCCL>
+ *   gb_ba_graph_step           : damp, block-Jacobi PCG on the reduced camera system (replicated, deterministic),
+ *                                back-substitute the shard's landmarks, build the candidate estimate and write the
+ *                                shard's candidate cost to d_cost[0] (device)
+ *   <all-reduce d_cost (1 double)>
+ *   gb_ba_graph_commit         : accept/reject on the device from the reduced costs, update lambda.
+ * No host synchronisation is needed between the calls.
+ */
+GB_API int gb_ba_graph_reduce_size(gb_ctx* ctx, gb_ba_graph* g, size_t* n_doubles);
+GB_API int gb_ba_graph_begin(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt);
+GB_API int gb_ba_graph_reduce_local(gb_ctx* ctx, gb_ba_graph* g, double* d_buf);
+GB_API int gb_ba_graph_step(gb_ctx* ctx, gb_ba_graph* g, const double* d_buf, double* d_cost);
+GB_API int gb_ba_graph_commit(gb_ctx* ctx, gb_ba_graph* g, const double* d_buf, const double* d_cost);
+GB_API int gb_ba_graph_finish(gb_ctx* ctx, gb_ba_graph* g, gb_ba_result* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSLAM_B200_H_ */

@@ -1,0 +1,153 @@
+"""Pins oracle/ba_ref.c: pose conventions against the reference's own SE3 class (oracle/_ref), Jacobians against finite
+differences, the optimum against scipy.optimize.least_squares (tests/golden/ba_golden.npz), plus known answers
+(SURVEY.md §8c KAT-B).  The reference ships no BA implementation or test, so beyond these the parity is unpinned."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from gslam_b200 import synth
+from gslam_b200.synth import BAProblem
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ba_golden.npz"))
+
+
+def golden_problem() -> BAProblem:
+    return BAProblem(cam_pose_wc=G["cam_pose_wc"].copy(), cam_dof=G["cam_dof"].copy(), points=G["points"].copy(),
+                     point_free=G["point_free"].copy(), obs_cam=G["obs_cam"].copy(), obs_point=G["obs_point"].copy(),
+                     obs_xyz=G["obs_xyz"].copy())
+
+
+def rand_pose(rng):
+    q = rng.standard_normal(4); q /= np.linalg.norm(q)
+    return np.concatenate([q, rng.standard_normal(3)])
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_layout_sizes_match_reference():
+    R = oracle.ref()
+    want = {"KeyPoint": 28, "SE3": 56, "SIM3": 64, "Point3d": 24, "BundleEdge": 48, "KeyFrameEstimzation": 72,
+            "MapPointEstimation": 32, "GImage": 32}
+    for k, v in want.items():
+        assert R.ref_sizeof(k.encode()) == v, k
+    offs = (C.c_int * 7)()
+    R.ref_keypoint_offsets(offs)
+    assert list(offs) == [0, 4, 8, 12, 16, 20, 24]  # == gb_keypoint / KP_DTYPE
+    from gslam_b200.capi import KP_DTYPE
+    assert [KP_DTYPE.fields[n][1] for n in KP_DTYPE.names] == list(offs)
+    # SIM3 raw memory = pose7 + scale: what the plugin memcpy's into gb_ba_problem.cam_pose_wc
+    p = rand_pose(np.random.default_rng(0)); raw = np.zeros(8)
+    R.ref_sim3_raw(p.ctypes.data, 2.5, raw.ctypes.data)
+    assert np.array_equal(raw[:7], p) and raw[7] == 2.5
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_se3_conventions_match_reference():
+    rng = np.random.default_rng(1)
+    R = oracle.ref(); L = oracle.lib()
+    for _ in range(200):
+        T = rand_pose(rng); p = rng.standard_normal(3)
+        inv_ref = np.zeros(7); inv_orc = np.zeros(7)
+        R.ref_se3_inverse(T.ctypes.data, inv_ref.ctypes.data)
+        L.orc_se3_inverse(T.ctypes.data, inv_orc.ctypes.data)
+        assert np.allclose(inv_ref, inv_orc, atol=1e-14)
+        # camera-frame point q = T_wc^-1 * p  (SE3.h:100-103,129-131) is what the residual uses
+        q_ref = np.zeros(3); R.ref_se3_transform(inv_ref.ctypes.data, p.ctypes.data, q_ref.ctypes.data)
+        Rm = synth._quat_to_R(inv_orc[:4])
+        assert np.allclose(q_ref, Rm @ p + inv_orc[4:], atol=1e-13)
+        # retraction Exp([v,w]) * T equals the reference's exp()*T away from w=0 (where the reference is NaN)
+        d = 0.3 * rng.standard_normal(6)
+        e = np.zeros(7); R.ref_se3_exp(d.ctypes.data, e.ctypes.data)
+        want = np.zeros(7); R.ref_se3_mul(e.ctypes.data, T.ctypes.data, want.ctypes.data)
+        got = np.zeros(7); L.orc_se3_retract(T.ctypes.data, d.ctypes.data, got.ctypes.data)
+        if want[3] * got[3] < 0: want[:4] = -want[:4]
+        assert np.allclose(want, got, atol=1e-12)
+    # small-angle: finite where the reference's exp is not (SE3.h:284-285)
+    d = np.array([0.1, 0.2, 0.3, 0, 0, 0.0]); T = rand_pose(rng); got = np.zeros(7)
+    L.orc_se3_retract(T.ctypes.data, d.ctypes.data, got.ctypes.data)
+    assert np.isfinite(got).all() and np.allclose(got[:4], T[:4]) and np.allclose(got[4:], T[4:] + d[:3])
+
+
+def test_gradient_matches_finite_differences():
+    pb = synth.synth_ba(6, 40, obs_per_point=4, n_fixed=1, seed=3)
+    delta = 0.01
+    lin = oracle.ba_linearize(pb, delta)
+    c0 = lin["cost"]
+    assert abs(c0 - oracle.ba_cost(pb, delta)) < 1e-15
+    eps = 1e-6
+    L = oracle.lib()
+    # cameras: perturb T_cw on the left, gradient g_c = -J'r  => dcost/dxi = -g_c
+    for i in [1, 3, 5]:
+        for a in range(6):
+            vals = []
+            for s in (+1, -1):
+                q = pb.copy()
+                cw = np.zeros(7); L.orc_se3_inverse(q.cam_pose_wc[i].ctypes.data, cw.ctypes.data)
+                d = np.zeros(6); d[a] = s * eps
+                out = np.zeros(7); L.orc_se3_retract(cw.ctypes.data, d.ctypes.data, out.ctypes.data)
+                wc = np.zeros(7); L.orc_se3_inverse(out.ctypes.data, wc.ctypes.data)
+                q.cam_pose_wc[i] = wc
+                vals.append(oracle.ba_cost(q, delta))
+            fd = (vals[0] - vals[1]) / (2 * eps)
+            assert abs(fd + lin["gc"][i, a]) < 1e-6 * max(1.0, abs(fd)), (i, a, fd, lin["gc"][i, a])
+    for j in [0, 7, 39]:
+        for a in range(3):
+            vals = []
+            for s in (+1, -1):
+                q = pb.copy(); q.points[j, a] += s * eps
+                vals.append(oracle.ba_cost(q, delta))
+            fd = (vals[0] - vals[1]) / (2 * eps)
+            assert abs(fd + lin["gp"][j, a]) < 1e-6 * max(1.0, abs(fd))
+    # fixed camera contributes no gradient
+    assert np.all(lin["gc"][0] == 0) and np.all(lin["U"][0] == 0)
+
+
+def test_noise_free_known_answer():
+    pb = synth.synth_ba(10, 200, all_visible=True, n_fixed=2, pixel_sigma=0.0, seed=7)
+    r = oracle.ba_solve(pb, max_iterations=50, function_tolerance=0.0, pcg_max_iters=200, pcg_tol=1e-14)
+    assert r.final_cost < 1e-20
+    assert np.abs(pb.points - pb.gt_points).max() < 1e-6
+    a = pb.cam_pose_wc.copy(); b = pb.gt_pose_wc
+    s = np.sign(np.sum(a[:, :4] * b[:, :4], axis=1))[:, None]
+    assert np.abs(a[:, :4] * s - b[:, :4]).max() < 1e-8 and np.abs(a[:, 4:] - b[:, 4:]).max() < 1e-7
+
+
+def test_optimum_matches_scipy_golden():
+    pb = golden_problem()
+    r = oracle.ba_solve(pb, huber_delta=0.0, max_iterations=200, function_tolerance=1e-14, pcg_max_iters=300, pcg_tol=1e-13)
+    want = float(G["scipy_cost_nohuber"])
+    assert abs(r.final_cost - want) / want < 1e-6, (r.final_cost, want)
+
+
+def test_fixed_everything_is_a_noop():
+    pb = synth.synth_ba(5, 30, obs_per_point=3, seed=2)
+    pb.cam_dof[:] = 0; pb.point_free[:] = 0
+    before = pb.copy()
+    r = oracle.ba_solve(pb, max_iterations=3)
+    assert np.array_equal(pb.points, before.points)
+    assert np.allclose(pb.cam_pose_wc, before.cam_pose_wc, atol=1e-15)
+    assert r.accepted == 0
+
+
+def test_pnp_recovers_pose():
+    rng = np.random.default_rng(5)
+    pose = rand_pose(rng); pose[4:] *= 0.1
+    cw = np.zeros(7); oracle.lib().orc_se3_inverse(pose.ctypes.data, cw.ctypes.data)
+    Rm = synth._quat_to_R(cw[:4])
+    pc = np.stack([rng.uniform(-2, 2, 100), rng.uniform(-2, 2, 100), rng.uniform(4, 10, 100)], axis=1)
+    xyz = (pc - cw[4:]) @ Rm  # p_w = R^T (p_c - t)
+    xy1 = np.concatenate([pc[:, :2] / pc[:, 2:3], np.ones((100, 1))], axis=1)
+    init = pose.copy(); init[4:] += 0.05; init[:4] += 0.01; init[:4] /= np.linalg.norm(init[:4])
+    out, r, info = oracle.ba_pnp(xyz, xy1, init, want_info=True, max_iterations=30, function_tolerance=0.0)
+    if out[3] * pose[3] < 0: out[:4] = -out[:4]
+    assert np.allclose(out, pose, atol=1e-9) and r.final_cost < 1e-20
+    assert np.allclose(info, info.T) and np.all(np.linalg.eigvalsh(info) > 0)
+
+
+def test_invalid_indices_rejected():
+    pb = synth.synth_ba(4, 10, obs_per_point=2, seed=1)
+    pb.obs_cam[0] = 99
+    with pytest.raises(RuntimeError):
+        oracle.ba_solve(pb, max_iterations=1)
