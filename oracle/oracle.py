@@ -213,3 +213,136 @@ def ba_pnp(xyz, xy1, pose_wc, dof=63, want_info=False, **opts):
     if rc != 0:
         raise RuntimeError(f"orc_ba_pnp failed rc={rc}")
     return pose, r, info
+
+
+# ---- ORB -----------------------------------------------------------------------------------------------------------
+_ORB_BOUND = False
+
+
+def _orb():
+    global _ORB_BOUND
+    L = lib()
+    if not _ORB_BOUND:
+        L.orc_orb_scale.restype = C.c_float; L.orc_orb_scale.argtypes = [C.c_float, C.c_int]
+        L.orc_orb_level_size.restype = None
+        L.orc_orb_level_size.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_resize_linear_exact.restype = None
+        L.orc_resize_linear_exact.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.orc_fast_score_map.restype = None
+        L.orc_fast_score_map.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.orc_fast_detect.restype = C.c_int
+        L.orc_fast_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_harris_response.restype = C.c_float; L.orc_harris_response.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_fast_atan2.restype = C.c_float; L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_ic_angle.restype = C.c_float; L.orc_ic_angle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_blur7.restype = None; L.orc_blur7.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_blur_pixel.restype = C.c_uint8; L.orc_blur_pixel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_det_sincos.restype = None; L.orc_det_sincos.argtypes = [C.c_double, f64p, f64p]
+        L.orc_brief_descriptor.restype = None
+        L.orc_brief_descriptor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]
+        L.orc_orb_quotas.restype = None; L.orc_orb_quotas.argtypes = [C.c_int, C.c_float, C.c_int, C.c_void_p]
+        L.orc_orb_pyramid_level.restype = C.c_void_p
+        L.orc_orb_pyramid_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_orb_extract.restype = C.c_int
+        L.orc_orb_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(OrbCfgC), C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        _ORB_BOUND = True
+    return L
+
+
+def orb_level_size(w, h, level, scale_factor=1.2):
+    lw, lh = C.c_int(), C.c_int()
+    _orb().orc_orb_level_size(w, h, scale_factor, level, C.byref(lw), C.byref(lh))
+    return lw.value, lh.value
+
+
+def orb_quotas(nfeatures, nlevels=8, scale_factor=1.2):
+    q = np.zeros(nlevels, np.int32)
+    _orb().orc_orb_quotas(nfeatures, scale_factor, nlevels, _p(q))
+    return q
+
+
+def resize_linear_exact(img, dw, dh):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty((dh, dw), np.uint8)
+    _orb().orc_resize_linear_exact(_p(img), img.shape[1], img.shape[0], _p(out), dw, dh)
+    return out
+
+
+def orb_pyramid_level(img, level, scale_factor=1.2):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cur = img
+    for l in range(1, level + 1):
+        lw, lh = orb_level_size(w, h, l, scale_factor)
+        cur = resize_linear_exact(cur, lw, lh)
+    return cur
+
+
+def fast_detect(img, threshold=20, nms=True):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cap = 1 << 16
+    while True:
+        xs = np.empty(cap, np.int32); ys = np.empty(cap, np.int32); sc = np.empty(cap, np.int32)
+        n = _orb().orc_fast_detect(_p(img), w, h, threshold, int(nms), _p(xs), _p(ys), _p(sc), cap)
+        if n <= cap:
+            return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+        cap = n
+
+
+def fast_score_map(img, threshold=20):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    _orb().orc_fast_score_map(_p(img), img.shape[1], img.shape[0], threshold, _p(out))
+    return out
+
+
+def harris_response(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    return float(_orb().orc_harris_response(_p(img), img.shape[1], int(x), int(y)))
+
+
+def ic_angle(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    return float(_orb().orc_ic_angle(_p(img), img.shape[1], int(x), int(y)))
+
+
+def fast_atan2(y, x):
+    return float(_orb().orc_fast_atan2(float(y), float(x)))
+
+
+def blur7(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    _orb().orc_blur7(_p(img), img.shape[1], img.shape[0], _p(out))
+    return out
+
+
+def det_sincos(x):
+    s, c = C.c_double(), C.c_double()
+    _orb().orc_det_sincos(float(x), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def brief_descriptor(blurred, x, y, angle_deg):
+    b = np.ascontiguousarray(blurred, np.uint8)
+    d = np.zeros(32, np.uint8)
+    _orb().orc_brief_descriptor(_p(b), b.shape[1], int(x), int(y), float(angle_deg), _p(d))
+    return d
+
+
+def orb_extract(img, nfeatures=500, **cfg_kw):
+    """Full pipeline. Returns (keypoints[KP_DTYPE], descriptors (n,32) u8) in canonical (octave, y, x) order."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cfg = default_orb_cfg(nfeatures=nfeatures, **cfg_kw)
+    cap = 2 * nfeatures + 1024
+    while True:
+        kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8); n = C.c_int(cap)
+        rc = _orb().orc_orb_extract(_p(img), w, h, C.byref(cfg), _p(kps), _p(desc), C.byref(n))
+        if rc == 3 and n.value > cap:
+            cap = n.value
+            continue
+        if rc != 0:
+            raise RuntimeError(f"orc_orb_extract failed rc={rc}")
+        return kps[:n.value].copy(), desc[:n.value].copy()

@@ -1,0 +1,106 @@
+"""Pins oracle/orb_ref.c against cv2 4.13 golden vectors, stage by stage and end to end (SURVEY.md App. A, §8c KAT-O).
+OpenCV is the third-party dependency that holds the ORB arithmetic of the reference's CPU path (absent from the tree)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from gslam_b200 import synth
+
+GD = os.path.join(os.path.dirname(__file__), "golden")
+ST = np.load(os.path.join(GD, "orb_stages.npz"))
+CASES = ["orb_320x240_n300", "orb_480x360_n400", "orb_752x480_n2000", "orb_1280x720_n1000", "orb_1920x1080_n2000"]
+
+
+def load_case(name):
+    g = np.load(os.path.join(GD, name + ".npz"))
+    img = g["image"] if "image" in g else synth.synth_frame(int(g["width"]), int(g["height"]), int(g["seed"]))
+    if hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest() != str(g["image_sha256"]):
+        pytest.skip("synthetic image generator drifted from the fixture")
+    return g, img
+
+
+def test_gauss_kernel_bits():
+    import struct
+    bits = [0x3d8fafb1, 0x3e06387e, 0x3e434a39, 0x3e5d4ae0, 0x3e434a39, 0x3e06387e, 0x3d8fafb1]
+    assert [struct.unpack("<I", struct.pack("<f", float(v)))[0] for v in ST["gauss_kernel"]] == bits
+
+
+def test_resize_linear_exact_golden():
+    assert np.array_equal(oracle.resize_linear_exact(ST["image"], 167, 125), ST["resized_167x125"])
+
+
+def test_fast_golden():
+    for nms, key in ((True, "fast_nms"), (False, "fast_all")):
+        xs, ys, sc = oracle.fast_detect(ST["image"], 20, nms)
+        got = np.stack([xs, ys, sc], axis=1)
+        if not nms:  # cv2 reports response 0 when it does not run NMS: compare positions only
+            got[:, 2] = 0
+        assert np.array_equal(got, ST[key]), key  # same positions, same row-major order, same scores
+
+
+def test_fast_atan2_golden():
+    got = np.array([oracle.fast_atan2(y, x) for y, x in zip(ST["atan_y"], ST["atan_x"])], np.float32)
+    assert np.array_equal(got, ST["atan"])
+
+
+def test_blur_golden():
+    assert np.array_equal(oracle.blur7(ST["image"]), ST["blur"])
+    img = ST["image"]
+    for (x, y) in [(0, 0), (199, 149), (50, 60), (3, 146)]:
+        assert oracle.lib().orc_blur_pixel(img.ctypes.data, 200, 150, x, y) == ST["blur"][y, x]
+
+
+def test_quotas_and_level_sizes():
+    assert oracle.orb_quotas(2000).tolist() == [434, 362, 302, 251, 209, 175, 145, 122]
+    assert [oracle.orb_level_size(1920, 1080, l) for l in range(8)] == [(1920, 1080), (1600, 900), (1333, 750), (1111, 625), (926, 521), (772, 434), (643, 362), (536, 301)]
+    assert [oracle.orb_level_size(1280, 720, l) for l in range(8)] == [(1280, 720), (1067, 600), (889, 500), (741, 417), (617, 347), (514, 289), (429, 241), (357, 201)]
+
+
+def test_det_sincos_matches_libm_after_float_rounding():
+    ang = np.float32(np.linspace(0, 360, 20001, dtype=np.float32))
+    th = ang * np.float32(np.pi / 180.0)
+    bad = 0
+    for t in th:
+        s, c = oracle.det_sincos(float(t))
+        bad += (np.float32(s) != np.float32(np.sin(np.float64(t)))) + (np.float32(c) != np.float32(np.cos(np.float64(t))))
+        assert abs(s - np.sin(np.float64(t))) < 4e-16 and abs(c - np.cos(np.float64(t))) < 4e-16
+    assert bad == 0
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_full_pipeline_matches_cv2_golden(name):
+    g, img = load_case(name)
+    kps, desc = oracle.orb_extract(img, int(g["nfeatures"]))
+    want = g["kps"]
+    assert len(kps) == len(want)
+    for f in ("octave", "x", "y", "size", "angle", "response", "class_id"):
+        assert np.array_equal(kps[f], want[f]), f  # bit-exact, canonical order
+    assert np.array_equal(desc, g["desc"])
+
+
+def test_live_cv2_other_resolution_and_params():
+    cv2 = pytest.importorskip("cv2")
+    import sys
+    sys.path.insert(0, GD)
+    from make_golden_orb import cv2_orb_canonical
+    img = synth.synth_frame(517, 389, 77)  # odd sizes: level sizes land on non-trivial roundings
+    for n, kw, okw in [(350, {}, {}), (200, dict(nlevels=5, fastThreshold=12), dict(nlevels=5, fast_threshold=12)),
+                       (300, dict(scaleFactor=1.35, nlevels=6), dict(scale_factor=1.35, nlevels=6))]:
+        want, wdesc, _ = cv2_orb_canonical(img, n, **kw)
+        kps, desc = oracle.orb_extract(img, n, **okw)
+        assert len(kps) == len(want)
+        for f in ("octave", "x", "y", "size", "angle", "response"):
+            assert np.array_equal(kps[f], want[f]), (f, kw)
+        assert np.array_equal(desc, wdesc)
+
+
+def test_degenerate_images():
+    flat = np.full((100, 120), 77, np.uint8)
+    kps, desc = oracle.orb_extract(flat, 100)
+    assert len(kps) == 0 and desc.shape == (0, 32)
+    tiny = synth.synth_frame(40, 40, 1)  # smaller than 2*edgeThreshold: nothing can be kept
+    kps, _ = oracle.orb_extract(tiny, 100)
+    assert len(kps) == 0
