@@ -285,6 +285,12 @@ class BAGraph:
                                                           ptr(W), ptr(cost)))
         return dict(U=U, gc=gc, V=V, gp=gp, W=W, cost=float(cost[0]))
 
+    def force_generic_pcg(self, on: bool = True):
+        self.ctx._check(self.ctx._lib.gb_dbg_ba_force_generic_pcg(self.ctx._h, self._h, int(on)))
+
+    def pcg_cluster_size(self) -> int:
+        return int(self.ctx._lib.gb_dbg_ba_pcg_cluster_size(self.ctx._h, self._h))
+
     def dbg_reduced(self, cfg: OptimzeConfig | None = None):
         n6 = 6 * self.n_cams
         S = np.zeros((n6, n6)); gt = np.zeros(n6); dc = np.zeros(n6); it = C.c_int()

@@ -93,6 +93,8 @@ _SIGNATURES = [
 _DEBUG_SIGNATURES = [
     ("gb_dbg_ba_linearize", C.c_int, [_VP, _VP, C.c_double, _VP, _VP, _VP, _VP, _VP, _VP]),
     ("gb_dbg_ba_reduced", C.c_int, [_VP, _VP, C.POINTER(BaOptions), _VP, _VP, _VP, C.POINTER(C.c_int)]),
+    ("gb_dbg_ba_force_generic_pcg", C.c_int, [_VP, _VP, C.c_int]),
+    ("gb_dbg_ba_pcg_cluster_size", C.c_int, [_VP, _VP]),
 ]
 
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]

@@ -14,6 +14,8 @@
 #include "ba_device.cuh"
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
 
@@ -161,43 +163,6 @@ __global__ void __launch_bounds__(kRedThreads) ba_reduce_cost_kernel(const BaSca
   if (threadIdx.x == 0) out[0] = 0.5 * t;
 }
 
-// damped inverse of the landmark blocks
-__global__ void ba_point_inv_kernel(BaDev g) {
-  if (g.sc->stop) return;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= g.np) return;
-  const double lambda = g.sc->lambda;
-  double Vi[9];
-  const bool active = g.pfree[j] != 0 && g.pt_off[j + 1] > g.pt_off[j];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) Vi[k] = active ? g.V[9 * (size_t)j + k] : 0.0;
-  if (active) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) Vi[a * 4] += lambda * clampd(Vi[a * 4]);
-    if (!spd_inverse<3>(Vi)) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) Vi[k] = 0.0;
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 9; ++k) g.Vinv[9 * (size_t)j + k] = Vi[k];
-}
-
-// buf = [S | gt | diagU | cost]; S must have been zeroed.  One thread per (camera, a, b).
-__global__ void ba_schur_init_kernel(BaDev g, double* __restrict__ buf) {
-  if (g.sc->stop) return;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= g.nc * 36) return;
-  const int i = t / 36, a = (t % 36) / 6, b = t % 6;
-  const size_t n6 = g.n6;
-  const double u = g.U[t];
-  buf[(size_t)(6 * i + a) * n6 + 6 * i + b] = u;
-  if (a == b) {
-    buf[n6 * n6 + n6 + 6 * i + a] = u;          // diag U
-    buf[n6 * n6 + 6 * i + a] = g.gc[6 * i + a];  // g~ starts from g_c
-  }
-}
-
 // one thread per observation e=(i,j): Y = W_e Vinv_j;  g~_i -= Y g_p,j;  S_{i,i'} -= Y W_f' for every f=(i',j)
 __global__ void ba_schur_accum_kernel(BaDev g, double* __restrict__ buf) {
   if (g.sc->stop) return;
@@ -334,33 +299,13 @@ __global__ void __launch_bounds__(kRedThreads) pcg_update_kernel(BaDev g) {
   }
   const double rzn = block_sum<kRedThreads>(part, s_part);
   if (threadIdx.x == 0) g.sc->pcg_iters++;
-  if (!(rzn > 0.0) || sqrt(rzn / rz0) < tol) {
+  if (!(rzn > 0.0) || rzn < tol * tol * rz0) {
     if (threadIdx.x == 0) g.sc->pcg_done = 1;
     return;
   }
   const double beta = rzn / rz;
   for (int d = threadIdx.x; d < g.n6; d += kRedThreads) g.p[d] = g.z[d] + beta * g.p[d];
   if (threadIdx.x == 0) g.sc->rz = rzn;
-}
-
-// ---- update ------------------------------------------------------------------------------------------------------------
-__global__ void ba_backsub_kernel(BaDev g) {
-  if (g.sc->stop) return;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= g.np) return;
-  double b[3] = {g.gp[3 * (size_t)j], g.gp[3 * (size_t)j + 1], g.gp[3 * (size_t)j + 2]};
-  for (int e = g.pt_off[j]; e < g.pt_off[j + 1]; ++e) {
-    const int i = g.o_cam[e];
-    const double* W = g.W + 18 * (size_t)e;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int a = 0; a < 6; ++a) b[c] -= W[a * 3 + c] * g.x[6 * i + a];
-  }
-  const double* Vi = g.Vinv + 9 * (size_t)j;
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-    g.pts_new[3 * (size_t)j + a] = g.pts[3 * (size_t)j + a] + Vi[a * 3] * b[0] + Vi[a * 3 + 1] * b[1] + Vi[a * 3 + 2] * b[2];
 }
 
 __global__ void ba_retract_kernel(BaDev g) {
@@ -381,22 +326,6 @@ __global__ void ba_retract_kernel(BaDev g) {
   for (int k = 0; k < 9; ++k) g.Rt_new[12 * i + k] = R[k];
 #pragma unroll
   for (int k = 0; k < 3; ++k) g.Rt_new[12 * i + 9 + k] = out[4 + k];
-}
-
-// robustified cost of every landmark at the candidate estimate
-__global__ void ba_cost_points_kernel(BaDev g) {
-  if (g.sc->stop) return;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= g.np) return;
-  const double delta = g.sc->delta;
-  const double p[3] = {g.pts_new[3 * (size_t)j], g.pts_new[3 * (size_t)j + 1], g.pts_new[3 * (size_t)j + 2]};
-  double cost = 0.0;
-  for (int e = g.pt_off[j]; e < g.pt_off[j + 1]; ++e) {
-    const ObsLin o = eval_obs(g.Rt_new + 12 * g.o_cam[e], p, g.o_uv[2 * e], g.o_uv[2 * e + 1],
-                              g.has_info ? g.o_info + 3 * e : nullptr, delta);
-    cost += o.rho;
-  }
-  g.cost_pt_new[j] = cost;
 }
 
 // LM accept / reject from the (possibly all-reduced) costs
@@ -450,6 +379,294 @@ __global__ void ba_finalize_kernel(int nc, const double* __restrict__ pose_cw, d
   for (int k = 0; k < 7; ++k) pose_wc[7 * i + k] = out[k];
 }
 
+
+// ---- fused helpers of the short-launch-chain path -------------------------------------------------------------------------
+// buf <- [S = blockdiag(U) | gt = gc | diagU | cost]; Vinv for every landmark.  Single writer per entry (no memset needed).
+__global__ void __launch_bounds__(256) ba_prepare_schur_kernel(BaDev g, double* __restrict__ buf) {
+  if (g.sc->stop) return;
+  __shared__ double s_part[256 / 32 + 1];
+  const size_t n6 = g.n6, nS = n6 * n6;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t idx = t0; idx < nS; idx += stride) {
+    const int row = (int)(idx / n6), col = (int)(idx % n6);
+    const int i = row / 6, i2 = col / 6;
+    buf[idx] = (i == i2) ? g.U[36 * i + (row % 6) * 6 + (col % 6)] : 0.0;
+  }
+  for (size_t d = t0; d < n6; d += stride) {
+    buf[nS + d] = g.gc[d];
+    buf[nS + n6 + d] = g.U[36 * (d / 6) + (d % 6) * 7];
+  }
+  const double lambda = g.sc->lambda;
+  for (size_t j = t0; j < (size_t)g.np; j += stride) {
+    double Vi[9];
+    const bool active = g.pfree[j] != 0 && g.pt_off[j + 1] > g.pt_off[j];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Vi[k] = active ? g.V[9 * j + k] : 0.0;
+    if (active) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) Vi[a * 4] += lambda * clampd(Vi[a * 4]);
+      if (!spd_inverse<3>(Vi)) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Vi[k] = 0.0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g.Vinv[9 * j + k] = Vi[k];
+  }
+  if (blockIdx.x == 0) {  // deterministic cost reduction (strided partials + fixed tree)
+    double v = 0.0;
+    for (int k = threadIdx.x; k < g.np; k += 256) v += g.cost_pt[k];
+    const double t = block_sum<256>(v, s_part);
+    if (threadIdx.x == 0) buf[nS + 2 * n6] = 0.5 * t;
+  }
+}
+
+// back-substitution of landmark j followed by its robustified cost at the candidate estimate
+__global__ void ba_backsub_cost_kernel(BaDev g) {
+  if (g.sc->stop) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.np) return;
+  const double delta = g.sc->delta;
+  double b[3] = {g.gp[3 * (size_t)j], g.gp[3 * (size_t)j + 1], g.gp[3 * (size_t)j + 2]};
+  const int e0 = g.pt_off[j], e1 = g.pt_off[j + 1];
+  for (int e = e0; e < e1; ++e) {
+    const int i = g.o_cam[e];
+    const double* W = g.W + 18 * (size_t)e;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int a = 0; a < 6; ++a) b[c] -= W[a * 3 + c] * g.x[6 * i + a];
+  }
+  const double* Vi = g.Vinv + 9 * (size_t)j;
+  double p[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    p[a] = g.pts[3 * (size_t)j + a] + Vi[a * 3] * b[0] + Vi[a * 3 + 1] * b[1] + Vi[a * 3 + 2] * b[2];
+    g.pts_new[3 * (size_t)j + a] = p[a];
+  }
+  double cost = 0.0;
+  for (int e = e0; e < e1; ++e) {
+    const ObsLin o = eval_obs(g.Rt_new + 12 * g.o_cam[e], p, g.o_uv[2 * e], g.o_uv[2 * e + 1], g.has_info ? g.o_info + 3 * e : nullptr, delta);
+    cost += o.rho;
+  }
+  g.cost_pt_new[j] = cost;
+}
+
+// single CTA: reduce the candidate cost, LM accept/reject, apply.  (small problems; the stepwise path keeps them apart)
+__global__ void __launch_bounds__(kRedThreads) ba_commit_fused_kernel(BaDev g, const double* __restrict__ buf) {
+  BaScalars* sc = g.sc;
+  if (sc->stop) return;
+  __shared__ double s_part[kRedThreads / 32 + 1];
+  __shared__ int s_ok;
+  double v = 0.0;
+  for (int k = threadIdx.x; k < g.np; k += kRedThreads) v += g.cost_pt_new[k];
+  const double cnew = 0.5 * block_sum<kRedThreads>(v, s_part);
+  if (threadIdx.x == 0) {
+    const size_t n6 = g.n6;
+    const double cost = buf[n6 * n6 + 2 * n6];
+    if (sc->iterations == 0) sc->initial_cost = cost;
+    sc->cost = cost;
+    sc->cost_new = cnew;
+    sc->iterations++;
+    const bool ok = (cnew < cost) && isfinite(cnew);
+    sc->need_linearize = ok ? 1 : 0;
+    if (ok) {
+      const double rel = (cost - cnew) / cost;
+      sc->cost = cnew;
+      const double l = sc->lambda / 3.0;
+      sc->lambda = l < 1e-15 ? 1e-15 : l;
+      sc->nu = 2.0;
+      sc->accepted++;
+      if (rel < sc->ftol) { sc->stop = 1; sc->status = 1; }
+    } else {
+      sc->lambda *= sc->nu;
+      sc->nu *= 2.0;
+      if (sc->lambda > 1e16) { sc->stop = 1; sc->status = 2; }
+    }
+    s_ok = ok ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  for (int t = threadIdx.x; t < g.nc * 7; t += kRedThreads) g.pose[t] = g.pose_new[t];
+  for (int t = threadIdx.x; t < g.nc * 12; t += kRedThreads) g.Rt[t] = g.Rt_new[t];
+  for (int t = threadIdx.x; t < g.np * 3; t += kRedThreads) g.pts[t] = g.pts_new[t];
+}
+
+// ---- K7b (local BA): block-Jacobi PCG inside ONE thread-block cluster ------------------------------------------------------
+// Each CTA of the cluster keeps a block-row slice of the (damped) reduced camera matrix S resident in its shared memory for the
+// whole solve; per iteration it computes its rows of q = S p, scatters them into every CTA's shared memory through DSMEM, and
+// after ONE cluster barrier every CTA redundantly (and bit-identically) performs the O(6N) vector part of CG.  q is
+// double-buffered so a fast CTA can never overwrite data a slow one still reads.  No global-memory traffic inside the loop.
+constexpr int kPcgThreads = 512;
+
+__global__ void __launch_bounds__(kPcgThreads, 1) ba_pcg_cluster_kernel(BaDev g, double* __restrict__ buf, int maxit) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  if (g.sc->stop) return;  // uniform over the cluster
+  extern __shared__ __align__(16) double sm[];
+  const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int n6 = g.n6, nc = g.nc, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cpc = (nc + C - 1) / C;
+  const int c0 = min(rank * cpc, nc), c1 = min(c0 + cpc, nc);
+  const int r0 = 6 * c0, nrows = 6 * (c1 - c0);
+  double* S = sm;                          // [6*cpc][n6]
+  double* Minv = S + (size_t)6 * cpc * n6; // [nc*36]
+  double* qbuf = Minv + (size_t)nc * 36;   // [2][n6]
+  double* vp = qbuf + 2 * (size_t)n6;      // p, r, z, x : [n6] each
+  double* vr = vp + n6;
+  double* vz = vr + n6;
+  double* vx = vz + n6;
+  const size_t nS = (size_t)n6 * n6;
+  const double lambda = g.sc->lambda, tol = g.sc->pcg_tol;
+  // A. slice of S -> shared memory, Marquardt damping on the diagonal (written back so the damped system is observable)
+  for (int idx = tid; idx < nrows * n6; idx += kPcgThreads) {
+    const int row = idx / n6, col = idx - row * n6, d = r0 + row;
+    double v = buf[(size_t)d * n6 + col];
+    if (col == d) {
+      v = ((g.dof[d / 6] >> (d % 6)) & 1) ? v + lambda * clampd(buf[nS + n6 + d]) : 1.0;
+      buf[(size_t)d * n6 + col] = v;
+    }
+    S[idx] = v;
+  }
+  __syncthreads();
+  // B. block-Jacobi preconditioner: owners invert their 6x6 diagonal blocks, everyone gathers all of them
+  if (tid < c1 - c0) {
+    double M[36];
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b < 6; ++b) M[a * 6 + b] = S[(size_t)(6 * tid + a) * n6 + r0 + 6 * tid + b];
+    if (!spd_inverse<6>(M)) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) M[a * 6 + b] = (a == b) ? 1.0 / S[(size_t)(6 * tid + a) * n6 + r0 + 6 * tid + a] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 36; ++k) g.Minv[36 * (size_t)(c0 + tid) + k] = M[k];
+  }
+  __threadfence();
+  cluster.sync();
+  for (int k = tid; k < nc * 36; k += kPcgThreads) Minv[k] = __ldcg(&g.Minv[k]);
+  for (int d = tid; d < n6; d += kPcgThreads) {
+    vx[d] = 0.0;
+    vr[d] = buf[nS + d];
+  }
+  __syncthreads();
+  // From here on thread d < n6 owns vector element d (n6 <= kPcgThreads is guaranteed by the host-side dispatch).
+  // r is double-buffered (vr / vz) so that the fused update "r -= alpha q ; z = Minv r" needs no barrier.
+  const bool own = tid < n6;
+  const int ci = own ? tid / 6 : 0, ca = own ? tid - 6 * ci : 0;
+  double xd = 0.0, zd = 0.0, pd = 0.0, rd = own ? vr[tid] : 0.0;
+  if (own) {
+#pragma unroll
+    for (int b = 0; b < 6; ++b) zd += Minv[36 * ci + ca * 6 + b] * vr[6 * ci + b];
+    pd = zd;
+    vp[tid] = pd;
+  }
+  __shared__ double s_red[2][kPcgThreads / 32];
+  const int nw_act = (n6 + 31) >> 5;
+  // deterministic block reduction with ONE barrier: shuffle tree per warp, then every thread sums the per-warp partials
+  // in the same fixed order (identical result in every thread and in every CTA of the cluster)
+  auto reduce = [&](double v, int buf) -> double {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[buf][warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < nw_act; ++w) t += s_red[buf][w];
+    return t;
+  };
+  double rz = reduce(rd * zd, 0);
+  const double rz0 = rz, tol2 = tol * tol;
+  int iters = 0;
+  bool done = !(rz0 > 0.0);
+  double* rcur = vr;
+  double* rnew = vz;
+  const int hl = tid & 15, grp = tid >> 4;  // 16 lanes per matrix row
+#define PCG_STAMP(k) do { if (g.prof && rank == 0 && tid == 0 && it == 3) g.prof[k] = clock64(); } while (0)
+  // C. CG iterations: one cluster barrier each
+  for (int it = 0; it < maxit && !done; ++it) {
+    double* q = qbuf + (size_t)(it & 1) * n6;
+    PCG_STAMP(0);
+    for (int row = grp; row < nrows; row += kPcgThreads / 16) {
+      const double* Srow = S + (size_t)row * n6;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int c = hl;
+      for (; c + 48 < n6; c += 64) {
+        s0 += Srow[c] * vp[c];
+        s1 += Srow[c + 16] * vp[c + 16];
+        s2 += Srow[c + 32] * vp[c + 32];
+        s3 += Srow[c + 48] * vp[c + 48];
+      }
+      for (; c < n6; c += 16) s0 += Srow[c] * vp[c];
+      double sv = (s0 + s1) + (s2 + s3);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o, 16);  // a+b == b+a: all 16 lanes agree
+      if (hl < C) cluster.map_shared_rank(q, hl)[r0 + row] = sv;
+    }
+    PCG_STAMP(1);
+    cluster.sync();
+    PCG_STAMP(2);
+    const double pq = reduce(own ? pd * q[tid] : 0.0, 1);
+    PCG_STAMP(3);
+    if (!(pq > 0.0)) break;
+    const double alpha = rz / pq;
+    double rzp = 0.0;
+    if (own) {
+      xd += alpha * pd;
+      zd = 0.0;
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {
+        const double rb = rcur[6 * ci + b] - alpha * q[6 * ci + b];
+        if (b == ca) rd = rb;
+        zd += Minv[36 * ci + ca * 6 + b] * rb;
+      }
+      rnew[tid] = rd;
+      rzp = rd * zd;
+    }
+    PCG_STAMP(4);
+    const double rzn = reduce(rzp, 0);  // its barrier also publishes rnew
+    PCG_STAMP(5);
+    { double* t = rcur; rcur = rnew; rnew = t; }
+    ++iters;
+    if (!(rzn > 0.0) || rzn < tol2 * rz0) break;
+    const double beta = rzn / rz;
+    if (own) {
+      pd = zd + beta * pd;
+      vp[tid] = pd;
+    }
+    rz = rzn;
+    __syncthreads();
+    PCG_STAMP(6);
+  }
+  if (own) vx[tid] = xd;
+  __syncthreads();
+  // every CTA leaves the loop at the same iteration (bit-identical redundant arithmetic); make sure nobody exits while a
+  // peer could still be storing into its shared memory
+  cluster.sync();
+  if (rank != 0) return;
+  // D. CTA 0 publishes the solution, the iteration count and the candidate camera poses
+  for (int d = tid; d < n6; d += kPcgThreads) g.x[d] = vx[d];
+  if (tid == 0) g.sc->pcg_iters += iters;
+  for (int i = tid; i < nc; i += kPcgThreads) {
+    double pose[7], dd[6], out[7], R[9];
+    const int dm = g.dof[i];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) pose[k] = g.pose[7 * i + k];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) dd[a] = ((dm >> a) & 1) ? vx[6 * i + a] : 0.0;
+    se3_retract(pose, dd, out);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) g.pose_new[7 * i + k] = out[k];
+    quat_to_R(out, R);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g.Rt_new[12 * i + k] = R[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) g.Rt_new[12 * i + 9 + k] = out[4 + k];
+  }
+}
+
 }  // namespace
 
 // ======================================================================================================================
@@ -457,7 +674,9 @@ __global__ void ba_finalize_kernel(int nc, const double* __restrict__ pose_cw, d
 // ======================================================================================================================
 struct gb_ba_graph {
   BaDev d{};
-  std::vector<void*> allocs;
+  uint8_t* slab = nullptr;  // one device allocation (or the ctx arena) holding everything below
+  size_t slab_bytes = 0;
+  bool from_arena = false;
   double *pose_init = nullptr, *pts_init = nullptr, *pose_wc_out = nullptr;
   double* buf = nullptr;     // internal [S | gt | diagU | cost | pad]
   double* d_cost = nullptr;  // internal candidate cost
@@ -465,6 +684,9 @@ struct gb_ba_graph {
   gb_ba_options opt{};
   std::vector<int> sorted_to_orig;  // sorted observation slot -> caller's edge index
   bool begun = false;
+  // cluster-PCG configuration (0 = generic multi-kernel PCG)
+  int pcg_cluster = 0;
+  size_t pcg_smem = 0;
 };
 
 static size_t ba_buf_doubles(int nc) {
@@ -472,14 +694,16 @@ static size_t ba_buf_doubles(int nc) {
   return n6 * n6 + 2 * n6 + 8;
 }
 
-template <typename T>
-static int ba_alloc(gb_ctx* ctx, gb_ba_graph* g, T** p, size_t n) {
-  void* v = nullptr;
-  GB_CUDA(ctx, cudaMalloc(&v, std::max<size_t>(n, 1) * sizeof(T)));
-  g->allocs.push_back(v);
-  *p = (T*)v;
-  return GB_OK;
-}
+struct Slab {
+  uint8_t* base = nullptr;
+  size_t off = 0;
+  template <typename T>
+  void take(T** p, size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    if (base) *p = (T*)(base + off);
+    off += std::max<size_t>(n, 1) * sizeof(T);
+  }
+};
 
 static int ba_validate(gb_ctx* ctx, const gb_ba_problem* pb) {
   if (!pb || pb->n_cams < 0 || pb->n_points < 0 || pb->n_obs < 0) {
@@ -509,12 +733,54 @@ static int ba_validate(gb_ctx* ctx, const gb_ba_problem* pb) {
   return GB_OK;
 }
 
+// Can the reduced camera system be solved by the one-cluster PCG kernel?  Pick the cluster size, remember the smem need.
+static void ba_pick_pcg(gb_ctx* ctx, gb_ba_graph* g) {
+  g->pcg_cluster = 0;
+  const int nc = g->d.nc, n6 = g->d.n6;
+  if (nc <= 0 || n6 > kPcgThreads) return;  // the cluster kernel maps one thread per element of the 6N vectors
+  static bool attr_done = false;
+  static bool np_ok = false;
+  if (!attr_done) {
+    attr_done = true;
+    np_ok = cudaFuncSetAttribute(ba_pcg_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    cudaGetLastError();
+  }
+  const int sizes[2] = {16, 8};
+  for (int t = 0; t < 2; ++t) {
+    const int C = sizes[t];
+    if (C == 16 && !np_ok) continue;
+    const int cpc = (nc + C - 1) / C;
+    const size_t smem = ((size_t)6 * cpc * n6 + (size_t)nc * 36 + 6 * (size_t)n6) * sizeof(double) + 64;
+    if (smem > (size_t)ctx->max_smem_optin) continue;
+    if (cudaFuncSetAttribute(ba_pcg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C); cfg.blockDim = dim3(kPcgThreads); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, ba_pcg_cluster_kernel, &cfg) != cudaSuccess || nclusters < 1) {
+      cudaGetLastError();
+      continue;
+    }
+    g->pcg_cluster = C;
+    g->pcg_smem = smem;
+    return;
+  }
+}
+
+static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out, bool use_arena);
+
 extern "C" {
 
 void gb_ba_options_default(gb_ba_options* o) {
   if (!o) return;
   o->projection = 0;
-  o->huber_delta = 0.01;  // OptimzeConfig::projectErrorHuberThreshold, Optimizer.h:177
+  o->huber_delta = 0.01;    // OptimzeConfig::projectErrorHuberThreshold, Optimizer.h:177
   o->max_iterations = 500;  // OptimzeConfig::maxIterations, Optimizer.h:179
   o->verbose = 0;
   o->function_tolerance = 1e-6;
@@ -525,16 +791,26 @@ void gb_ba_options_default(gb_ba_options* o) {
 
 int gb_ba_graph_destroy(gb_ctx* ctx, gb_ba_graph* g) {
   if (!g) return GB_OK;
-  if (ctx) {
-    CtxLock lk(ctx);
-    cudaStreamSynchronize(ctx->stream);
+  if (g->from_arena) {
+    if (ctx) ctx->ba_arena_busy = false;
+  } else {
+    if (ctx) {
+      CtxLock lk(ctx);
+      cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(g->slab);
   }
-  for (void* p : g->allocs) cudaFree(p);
   delete g;
   return GB_OK;
 }
 
 int gb_ba_graph_create(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out) {
+  return ba_graph_create_impl(ctx, pb, out, false);
+}
+
+}  // extern "C"
+
+static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out, bool use_arena) {
   if (!ctx || !out) return GB_ERR_INVALID;
   *out = nullptr;
   CtxLock lk(ctx);
@@ -547,6 +823,7 @@ int gb_ba_graph_create(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out) 
   } guard{ctx, g};
   BaDev& d = g->d;
   d.nc = nc; d.np = np; d.no = no; d.n6 = 6 * nc; d.has_info = pb->obs_info ? 1 : 0;
+  g->buf_doubles = ba_buf_doubles(nc);
 
   // ---- host-side ordering: stable counting sorts -> (point, camera) order, and the per-camera lists ----------------
   std::vector<int> byc(no), order(no), cnt(std::max(nc, np) + 2, 0);
@@ -557,23 +834,62 @@ int gb_ba_graph_create(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out) 
   for (int k = 0; k < no; ++k) pt_off[pb->obs_point[k] + 1]++;
   for (int j = 0; j < np; ++j) pt_off[j + 1] += pt_off[j];
   { std::vector<int> pos(pt_off.begin(), pt_off.end()); for (int t = 0; t < no; ++t) { int k = byc[t]; order[pos[pb->obs_point[k]]++] = k; } }
-  g->sorted_to_orig = order;
   std::vector<int> cam_off(nc + 1, 0), cam_perm(no);
   for (int e = 0; e < no; ++e) cam_off[pb->obs_cam[order[e]] + 1]++;
   for (int i = 0; i < nc; ++i) cam_off[i + 1] += cam_off[i];
   { std::vector<int> pos(cam_off.begin(), cam_off.end()); for (int e = 0; e < no; ++e) cam_perm[pos[pb->obs_cam[order[e]]]++] = e; }
 
-  // ---- one pinned blob, one H2D --------------------------------------------------------------------------------------
+  // ---- layout: one slab = [uploaded blob | working set] ----------------------------------------------------------------
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t b_pose = al((size_t)nc * 7 * 8), b_pts = al((size_t)np * 3 * 8), b_dof = al(nc), b_pf = al(np),
                b_oc = al((size_t)no * 4), b_op = al((size_t)no * 4), b_uv = al((size_t)no * 16),
                b_info = d.has_info ? al((size_t)no * 24) : 0, b_po = al((size_t)(np + 1) * 4), b_co = al((size_t)(nc + 1) * 4),
                b_cp = al((size_t)no * 4);
-  const size_t total = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + 256;
-  GB_CHECK(gb_stage_reserve(ctx, ctx->h_stage_off + total + 4096));
-  uint8_t* h = (uint8_t*)gb_stage_alloc(ctx, total);
+  const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + 256;
+  const size_t n6 = 6 * (size_t)nc;
   uint8_t* dblob = nullptr;
-  GB_CHECK(ba_alloc(ctx, g, &dblob, total));
+  auto layout = [&](Slab& sl) {
+    sl.take(&dblob, blob);
+    sl.take(&g->pose_init, (size_t)nc * 7); sl.take(&g->pose_wc_out, (size_t)nc * 7);
+    sl.take(&d.pose, (size_t)nc * 7); sl.take(&d.pose_new, (size_t)nc * 7);
+    sl.take(&d.Rt, (size_t)nc * 12); sl.take(&d.Rt_new, (size_t)nc * 12);
+    sl.take(&d.pts, (size_t)np * 3); sl.take(&d.pts_new, (size_t)np * 3);
+    sl.take(&d.V, (size_t)np * 9); sl.take(&d.gp, (size_t)np * 3); sl.take(&d.Vinv, (size_t)np * 9);
+    sl.take(&d.W, (size_t)no * 18); sl.take(&d.U, (size_t)nc * 36); sl.take(&d.gc, (size_t)nc * 6);
+    sl.take(&d.cost_pt, (size_t)np); sl.take(&d.cost_pt_new, (size_t)np);
+    sl.take(&d.Minv, (size_t)nc * 36);
+    sl.take(&d.x, n6); sl.take(&d.r, n6); sl.take(&d.z, n6); sl.take(&d.p, n6); sl.take(&d.q, n6);
+    sl.take(&d.sc, 1);
+    sl.take(&g->buf, g->buf_doubles);
+    sl.take(&g->d_cost, 8);
+  };
+  Slab measure;
+  layout(measure);
+  const size_t need = measure.off + 256;
+  if (use_arena && !ctx->ba_arena_busy) {
+    if (need > ctx->ba_arena_cap) {
+      GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->ba_arena);
+      ctx->ba_arena = nullptr;
+      ctx->ba_arena_cap = 0;
+      const size_t want = need + need / 4;
+      GB_CUDA(ctx, cudaMalloc(&ctx->ba_arena, want));
+      ctx->ba_arena_cap = want;
+    }
+    g->slab = (uint8_t*)ctx->ba_arena;
+    g->from_arena = true;
+    ctx->ba_arena_busy = true;
+  } else {
+    GB_CUDA(ctx, cudaMalloc((void**)&g->slab, need));
+  }
+  g->slab_bytes = need;
+  Slab real;
+  real.base = g->slab;
+  layout(real);
+
+  // ---- one pinned blob, one H2D ------------------------------------------------------------------------------------------
+  GB_CHECK(gb_stage_reserve(ctx, ctx->h_stage_off + blob + 4096));
+  uint8_t* h = (uint8_t*)gb_stage_alloc(ctx, blob);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += bytes; return o; };
   const size_t o_pose = take(b_pose), o_pts = take(b_pts), o_dof = take(b_dof), o_pf = take(b_pf), o_oc = take(b_oc),
@@ -598,53 +914,27 @@ int gb_ba_graph_create(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out) 
   memcpy(h + o_po, pt_off.data(), (size_t)(np + 1) * 4);
   memcpy(h + o_co, cam_off.data(), (size_t)(nc + 1) * 4);
   memcpy(h + o_cp, cam_perm.data(), (size_t)no * 4);
-  GB_CUDA(ctx, cudaMemcpyAsync(dblob, h, total, cudaMemcpyHostToDevice, ctx->stream));
+  g->sorted_to_orig.swap(order);
+  GB_CUDA(ctx, cudaMemcpyAsync(dblob, h, blob, cudaMemcpyHostToDevice, ctx->stream));
   double* d_pose_wc = (double*)(dblob + o_pose);
   g->pts_init = (double*)(dblob + o_pts);
   d.dof = dblob + o_dof; d.pfree = dblob + o_pf;
   d.o_cam = (int*)(dblob + o_oc); d.o_pt = (int*)(dblob + o_op); d.o_uv = (double*)(dblob + o_uv);
   d.o_info = d.has_info ? (double*)(dblob + o_info) : nullptr;
   d.pt_off = (int*)(dblob + o_po); d.cam_off = (int*)(dblob + o_co); d.cam_perm = (int*)(dblob + o_cp);
-
-  // ---- working set ---------------------------------------------------------------------------------------------------
-  const size_t n6 = 6 * (size_t)nc;
-  GB_CHECK(ba_alloc(ctx, g, &g->pose_init, (size_t)nc * 7));
-  GB_CHECK(ba_alloc(ctx, g, &g->pose_wc_out, (size_t)nc * 7));
-  GB_CHECK(ba_alloc(ctx, g, &d.pose, (size_t)nc * 7));
-  GB_CHECK(ba_alloc(ctx, g, &d.pose_new, (size_t)nc * 7));
-  GB_CHECK(ba_alloc(ctx, g, &d.Rt, (size_t)nc * 12));
-  GB_CHECK(ba_alloc(ctx, g, &d.Rt_new, (size_t)nc * 12));
-  GB_CHECK(ba_alloc(ctx, g, &d.pts, (size_t)np * 3));
-  GB_CHECK(ba_alloc(ctx, g, &d.pts_new, (size_t)np * 3));
-  GB_CHECK(ba_alloc(ctx, g, &d.V, (size_t)np * 9));
-  GB_CHECK(ba_alloc(ctx, g, &d.gp, (size_t)np * 3));
-  GB_CHECK(ba_alloc(ctx, g, &d.Vinv, (size_t)np * 9));
-  GB_CHECK(ba_alloc(ctx, g, &d.W, (size_t)no * 18));
-  GB_CHECK(ba_alloc(ctx, g, &d.U, (size_t)nc * 36));
-  GB_CHECK(ba_alloc(ctx, g, &d.gc, (size_t)nc * 6));
-  GB_CHECK(ba_alloc(ctx, g, &d.cost_pt, (size_t)np));
-  GB_CHECK(ba_alloc(ctx, g, &d.cost_pt_new, (size_t)np));
-  GB_CHECK(ba_alloc(ctx, g, &d.Minv, (size_t)nc * 36));
-  GB_CHECK(ba_alloc(ctx, g, &d.x, n6));
-  GB_CHECK(ba_alloc(ctx, g, &d.r, n6));
-  GB_CHECK(ba_alloc(ctx, g, &d.z, n6));
-  GB_CHECK(ba_alloc(ctx, g, &d.p, n6));
-  GB_CHECK(ba_alloc(ctx, g, &d.q, n6));
-  GB_CHECK(ba_alloc(ctx, g, &d.sc, 1));
-  g->buf_doubles = ba_buf_doubles(nc);
-  GB_CHECK(ba_alloc(ctx, g, &g->buf, g->buf_doubles));
-  GB_CHECK(ba_alloc(ctx, g, &g->d_cost, 8));
-  GB_CUDA(ctx, cudaMemsetAsync(d.sc, 0, sizeof(BaScalars), ctx->stream));
   if (nc > 0) {
     ba_prepare_kernel<<<gb_div_up(nc, 128), 128, 0, ctx->stream>>>(nc, d_pose_wc, g->pose_init);
     GB_LAUNCH_CHECK(ctx);
   }
   GB_CHECK(gb_ba_graph_reset(ctx, g));
+  ba_pick_pcg(ctx, g);
   GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the pinned blob is reused by the next call
   guard.ok = true;
   *out = g;
   return GB_OK;
 }
+
+extern "C" {
 
 int gb_ba_graph_reset(gb_ctx* ctx, gb_ba_graph* g) {
   if (!ctx || !g) return GB_ERR_INVALID;
@@ -677,17 +967,41 @@ int gb_ba_graph_begin(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt_in) 
   memset(&h, 0, sizeof h);
   h.delta = opt.huber_delta; h.ftol = opt.function_tolerance; h.pcg_tol = opt.pcg_tol; h.lambda_init = opt.lambda_init;
   h.lambda = opt.lambda_init; h.nu = 2.0; h.need_linearize = 1;
-  GB_CHECK(gb_stage_reserve(ctx, ctx->h_stage_off + sizeof h + 512));
-  BaScalars* hs = (BaScalars*)gb_stage_alloc(ctx, sizeof h);
-  *hs = h;
-  GB_CUDA(ctx, cudaMemcpyAsync(g->d.sc, hs, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+  // kernel-argument-sized payload: no staging, no sync
+  GB_CUDA(ctx, cudaMemcpyAsync(g->d.sc, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
   if (g->d.nc > 0) {
     ba_rt_kernel<<<gb_div_up(g->d.nc, 128), 128, 0, ctx->stream>>>(g->d.nc, g->d.pose, g->d.Rt);
     GB_LAUNCH_CHECK(ctx);
   }
-  // hs lives in the per-call staging: drain before returning
-  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   g->begun = true;
+  return GB_OK;
+}
+
+// generic (any size) PCG: damp + init + max_iters x (matvec, update) + retract
+static int ba_pcg_generic(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
+  BaDev& d = g->d;
+  cudaStream_t s = ctx->stream;
+  ba_damp_kernel<<<gb_div_up(d.n6, 128), 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+  pcg_init_kernel<<<1, kRedThreads, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+  for (int k = 0; k < g->opt.pcg_max_iters; ++k) {
+    pcg_matvec_kernel<<<gb_div_up(d.n6, 8), 256, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+    pcg_update_kernel<<<1, kRedThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
+  }
+  ba_retract_kernel<<<gb_div_up(d.nc, 128), 128, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
+  return GB_OK;
+}
+
+// local-BA PCG: one thread-block cluster, S resident in shared memory, one cluster barrier per iteration
+static int ba_pcg_cluster(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g->pcg_cluster); cfg.blockDim = dim3(kPcgThreads); cfg.dynamicSmemBytes = g->pcg_smem; cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = g->pcg_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  GB_CUDA(ctx, cudaFuncSetAttribute(ba_pcg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_smem));
+  GB_CUDA(ctx, cudaLaunchKernelEx(&cfg, ba_pcg_cluster_kernel, g->d, buf, (int)g->opt.pcg_max_iters));
+  GB_LAUNCH_CHECK(ctx);
   return GB_OK;
 }
 
@@ -697,14 +1011,24 @@ int gb_ba_graph_reduce_local(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   BaDev& d = g->d;
   if (!buf) buf = g->buf;
   cudaStream_t s = ctx->stream;
-  const size_t n6 = d.n6;
   if (d.np > 0) { ba_linearize_points_kernel<<<gb_div_up(d.np, kPtThreads), kPtThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
   if (d.nc > 0) { ba_linearize_cams_kernel<<<d.nc, kCamThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
-  GB_CUDA(ctx, cudaMemsetAsync(buf, 0, g->buf_doubles * sizeof(double), s));
-  ba_reduce_cost_kernel<<<1, kRedThreads, 0, s>>>(d.sc, d.cost_pt, d.np, buf + n6 * n6 + 2 * n6); GB_LAUNCH_CHECK(ctx);
-  if (d.np > 0) { ba_point_inv_kernel<<<gb_div_up(d.np, 128), 128, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
-  if (d.nc > 0) { ba_schur_init_kernel<<<gb_div_up(d.nc * 36, 256), 256, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx); }
-  if (d.no > 0) { ba_schur_accum_kernel<<<gb_div_up(d.no, 128), 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx); }
+  {
+    const size_t work = std::max<size_t>((size_t)d.n6 * d.n6, (size_t)d.np);
+    const int blocks = (int)std::min<size_t>(std::max<size_t>((work + 255) / 256, 1), (size_t)ctx->sm_count * 8);
+    ba_prepare_schur_kernel<<<blocks, 256, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+  }
+  if (d.no > 0 && d.nc > 0) { ba_schur_accum_kernel<<<gb_div_up(d.no, 128), 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx); }
+  return GB_OK;
+}
+
+static int ba_step_core(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
+  BaDev& d = g->d;
+  cudaStream_t s = ctx->stream;
+  if (d.nc > 0) {
+    if (g->pcg_cluster > 0) GB_CHECK(ba_pcg_cluster(ctx, g, buf)); else GB_CHECK(ba_pcg_generic(ctx, g, buf));
+  }
+  if (d.np > 0) { ba_backsub_cost_kernel<<<gb_div_up(d.np, 128), 128, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
   return GB_OK;
 }
 
@@ -714,21 +1038,8 @@ int gb_ba_graph_step(gb_ctx* ctx, gb_ba_graph* g, const double* buf_in, double* 
   BaDev& d = g->d;
   double* buf = buf_in ? (double*)buf_in : g->buf;
   if (!d_cost) d_cost = g->d_cost;
-  cudaStream_t s = ctx->stream;
-  if (d.nc > 0) {
-    ba_damp_kernel<<<gb_div_up(d.n6, 128), 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
-    pcg_init_kernel<<<1, kRedThreads, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
-    for (int k = 0; k < g->opt.pcg_max_iters; ++k) {
-      pcg_matvec_kernel<<<gb_div_up(d.n6, 8), 256, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
-      pcg_update_kernel<<<1, kRedThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
-    }
-    ba_retract_kernel<<<gb_div_up(d.nc, 128), 128, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
-  }
-  if (d.np > 0) {
-    ba_backsub_kernel<<<gb_div_up(d.np, 128), 128, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
-    ba_cost_points_kernel<<<gb_div_up(d.np, 128), 128, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
-  }
-  ba_reduce_cost_kernel<<<1, kRedThreads, 0, s>>>(d.sc, d.cost_pt_new, d.np, d_cost); GB_LAUNCH_CHECK(ctx);
+  GB_CHECK(ba_step_core(ctx, g, buf));
+  ba_reduce_cost_kernel<<<1, kRedThreads, 0, ctx->stream>>>(d.sc, d.cost_pt_new, d.np, d_cost); GB_LAUNCH_CHECK(ctx);
   return GB_OK;
 }
 
@@ -779,10 +1090,17 @@ int gb_ba_graph_solve(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, gb_
   GB_CHECK(gb_ba_graph_begin(ctx, g, opt));
   GB_CUDA(ctx, cudaEventRecord(ctx->evs, ctx->stream));
   const bool poll = g->opt.function_tolerance > 0.0 || g->opt.verbose;
+  // one fused commit kernel while the estimate fits a single CTA's copy loop; the stepwise kernels otherwise
+  const bool fused_commit = (size_t)g->d.np * 3 + (size_t)g->d.nc * 19 <= (size_t)1 << 16;
   for (int it = 0; it < g->opt.max_iterations; ++it) {
     GB_CHECK(gb_ba_graph_reduce_local(ctx, g, nullptr));
-    GB_CHECK(gb_ba_graph_step(ctx, g, nullptr, nullptr));
-    GB_CHECK(gb_ba_graph_commit(ctx, g, nullptr, nullptr));
+    if (fused_commit) {
+      GB_CHECK(ba_step_core(ctx, g, g->buf));
+      ba_commit_fused_kernel<<<1, kRedThreads, 0, ctx->stream>>>(g->d, g->buf); GB_LAUNCH_CHECK(ctx);
+    } else {
+      GB_CHECK(gb_ba_graph_step(ctx, g, nullptr, nullptr));
+      GB_CHECK(gb_ba_graph_commit(ctx, g, nullptr, nullptr));
+    }
     if (poll) {
       BaScalars h;
       GB_CHECK(ba_read_scalars(ctx, g, &h));
@@ -825,7 +1143,7 @@ int gb_ba_solve(gb_ctx* ctx, gb_ba_problem* pb, const gb_ba_options* opt, gb_ba_
   if (!ctx || !pb) return GB_ERR_INVALID;
   CtxLock lk(ctx);
   gb_ba_graph* g = nullptr;
-  GB_CHECK(gb_ba_graph_create(ctx, pb, &g));
+  GB_CHECK(ba_graph_create_impl(ctx, pb, &g, true));
   int rc = gb_ba_graph_solve(ctx, g, opt, res);
   if (rc == GB_OK) rc = gb_ba_graph_download(ctx, g, pb->cam_pose_wc, pb->points);
   gb_ba_graph_destroy(ctx, g);
@@ -848,7 +1166,7 @@ int gb_ba_pnp(gb_ctx* ctx, int n, const double* xyz, const double* xy1, double* 
   pb.cam_pose_wc = pose_wc; pb.cam_dof = &d; pb.points = pts.data(); pb.point_free = pf.data();
   pb.obs_cam = oc.data(); pb.obs_point = op.data(); pb.obs_xyz = xy1; pb.obs_info = nullptr;
   gb_ba_graph* g = nullptr;
-  GB_CHECK(gb_ba_graph_create(ctx, &pb, &g));
+  GB_CHECK(ba_graph_create_impl(ctx, &pb, &g, true));
   int rc = gb_ba_graph_solve(ctx, g, opt, res);
   if (rc == GB_OK) rc = gb_ba_graph_download(ctx, g, pose_wc, nullptr);
   if (rc == GB_OK && info6x6) {
@@ -894,6 +1212,7 @@ GB_API int gb_dbg_ba_linearize(gb_ctx* ctx, gb_ba_graph* g, double delta, double
   return GB_OK;
 }
 
+// mode: 0 = whatever gb_ba_graph_solve would use, 1 = force the generic multi-kernel PCG
 GB_API int gb_dbg_ba_reduced(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, double* S, double* gt, double* dc,
                              int* pcg_iters) {
   if (!ctx || !g) return GB_ERR_INVALID;
@@ -909,6 +1228,30 @@ GB_API int gb_dbg_ba_reduced(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* o
   BaScalars h;
   GB_CHECK(ba_read_scalars(ctx, g, &h));
   if (pcg_iters) *pcg_iters = h.pcg_iters;
+  return GB_OK;
+}
+
+// force (1) / release (0) the generic multi-kernel PCG on this graph — lets the tests cover both solver paths
+GB_API int gb_dbg_ba_force_generic_pcg(gb_ctx* ctx, gb_ba_graph* g, int on) {
+  if (!ctx || !g) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  if (on) g->pcg_cluster = 0; else ba_pick_pcg(ctx, g);
+  return GB_OK;
+}
+
+GB_API int gb_dbg_ba_pcg_cluster_size(gb_ctx* ctx, gb_ba_graph* g) { return (ctx && g) ? g->pcg_cluster : -1; }
+
+// clock64 stamps of PCG iteration 3 on CTA 0 (8 values): enable, solve, then read
+GB_API int gb_dbg_ba_pcg_profile(gb_ctx* ctx, gb_ba_graph* g, long long* out8) {
+  if (!ctx || !g) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  if (!g->d.prof) {
+    GB_CUDA(ctx, cudaMalloc((void**)&g->d.prof, 64));
+    GB_CUDA(ctx, cudaMemset(g->d.prof, 0, 64));
+    return GB_OK;
+  }
+  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  GB_CUDA(ctx, cudaMemcpy(out8, g->d.prof, 64, cudaMemcpyDeviceToHost));
   return GB_OK;
 }
 

@@ -33,6 +33,7 @@ struct BaDev {
   // PCG
   double *Minv, *x, *r, *z, *p, *q;
   BaScalars* sc;
+  long long* prof;  // optional clock64 stamps of the cluster PCG (test hook), or nullptr
 };
 
 namespace ba {

@@ -35,6 +35,9 @@ struct gb_ctx {
   gb_features* tmp_q = nullptr;  // temporaries of the host-buffer match entry point
   gb_features* tmp_t = nullptr;
   gb_features* tmp_f = nullptr;  // temporary of the host-buffer extract entry point
+  void* ba_arena = nullptr;      // grow-only slab reused by the host-buffer BA entry points (no cudaMalloc per call)
+  size_t ba_arena_cap = 0;
+  bool ba_arena_busy = false;
 };
 
 struct gb_features {

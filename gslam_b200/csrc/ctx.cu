@@ -113,6 +113,7 @@ int gb_ctx_destroy(gb_ctx* ctx) {
     gb_orb_state_free(ctx);
     gb_match_state_free(ctx);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    cudaFree(ctx->ba_arena);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->evs);
@@ -200,6 +201,11 @@ int gb_features_count(gb_ctx* ctx, gb_features* f, int* n) {
     int hc[2] = {0, 0};
     GB_CUDA(ctx, cudaMemcpyAsync(hc, f->d_count, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
     GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hc[1] < 0) {
+      *n = 0;
+      gb_set_error(ctx, "extract: internal overflow (%s)", hc[1] == -2 ? "more than 4096 keypoints kept on one level" : "candidate buffer");
+      return GB_ERR_CAPACITY;
+    }
     if (hc[1] != 0) {
       *n = hc[1];
       gb_set_error(ctx, "extract kept %d keypoints but the feature set holds %d", hc[1], f->capacity);

@@ -1,12 +1,810 @@
-// placeholder until the ORB kernels land
+// gslam_b200/csrc/orb.cu — ORB extract (K1-K4): pyramid -> FAST-9/16 + NMS -> Harris / per-level top-N -> IC angle + rBRIEF.
+//
+// Consumes a GSLAM::GImage payload (dense 8UC1, GSLAM/core/GImage.h:160-443, no row stride :378); produces
+// GSLAM::KeyPoint records (GSLAM/core/Map.h:122-195 == gb_keypoint) and N x 32 8UC1 descriptor rows for
+// MapFrame::setKeyPoints (Map.h:311-312).  The arithmetic is OpenCV's ORB as specified in SURVEY.md Appendix A and
+// restated by oracle/orb_ref.c; every stage here is bit-exact against it (integer stages trivially; float stages by
+// using explicitly rounded intrinsics / explicit fma in the same order).
+//
+// Launch structure per frame (all on the ctx stream, no host sync inside):
+//   orb_resize_kernel   x (nlevels-1) : INTER_LINEAR_EXACT from the previous level (Q8 fixed point), padded pitch
+//   orb_fast_kernel     x 1           : all levels, 64x16 tiles staged in shared memory; quick-reject -> shared worklist ->
+//                                       dense score pass -> strict 3x3 NMS -> border filter -> candidate append + histogram
+//   orb_harris_kernel   x 1           : FAST-score threshold from the histogram (top 2n, ties kept), Harris response
+//   orb_select_kernel   x 1           : one CTA per level: 4-pass radix select of the n-th largest response (ties kept),
+//                                       compaction, bitonic sort by (y,x) -> canonical order
+//   orb_describe_kernel x 1           : one warp per keypoint: 45x45 patch in shared memory, IC angle, 7x7 float blur of the
+//                                       patch, 256 rotated tests, coalesced 32-byte descriptor row + KeyPoint record
 #include "common.cuh"
-void gb_orb_state_free(gb_ctx* ctx) { (void)ctx; }
+#include "orb_pattern.h"
+
+#include <cmath>
+
+namespace {
+
+constexpr int kMaxLevels = GB_ORB_MAX_LEVELS;
+constexpr int kTileW = 64, kTileH = 16;
+constexpr int kInW = kTileW + 8, kInH = kTileH + 8;    // 72 x 24 input tile (3 ring + 1 nms halo each side)
+constexpr int kScW = kTileW + 2, kScH = kTileH + 2;    // 66 x 18 score tile
+constexpr int kFastThreads = 256;
+constexpr int kSelThreads = 1024;
+constexpr int kSelMax = 4096;                          // max kept keypoints per level (bitonic sort in shared memory)
+constexpr int kDescWarps = 4;
+
+struct LevelInfo {
+  int w, h, pitch;        // pitch in bytes, multiple of 128
+  int quota;              // n_l
+  size_t off;             // byte offset of the level in the pyramid buffer
+  int tiles_x, tile_start;  // FAST tiling
+  int cand_off, cand_cap;   // slice of the candidate arrays
+  int coef_off;           // offset (in entries) of this level's resize tables: x table then y table
+  float scale;            // s_l = (float)pow((double)scaleFactor, l)
+};
+
+struct OrbParams {
+  int nlevels, total_tiles, fast_threshold, border;
+  LevelInfo lv[kMaxLevels];
+};
+
+// ---- K1: pyramid ---------------------------------------------------------------------------------------------------------
+// dst(x,y) = (b0*(a0*S[iy][ix] + a1*S[iy][ix+1]) + b1*(a0*S[iy+1][ix] + a1*S[iy+1][ix+1]) + 2^15) >> 16, weights Q8.
+// Table entry: idx | (a1 << 16).  One thread writes 4 consecutive pixels as one 32-bit store.
+__global__ void __launch_bounds__(256) orb_resize_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
+                                                         uint8_t* __restrict__ dst, int dw, int dh, int dpitch,
+                                                         const uint32_t* __restrict__ xtab, const uint32_t* __restrict__ ytab) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x4 >= dw || y >= dh) return;
+  const uint32_t ye = ytab[y];
+  const int iy = ye & 0xffff, b1 = ye >> 16, b0 = 256 - b1;
+  const uint8_t* r0 = src + (size_t)iy * spitch;
+  const uint8_t* r1 = src + (size_t)min(iy + 1, sh - 1) * spitch;
+  uint32_t out = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int x = x4 + k;
+    uint32_t v = 0;
+    if (x < dw) {
+      const uint32_t xe = xtab[x];
+      const int ix = xe & 0xffff, a1 = xe >> 16, a0 = 256 - a1, ix1 = min(ix + 1, sw - 1);
+      const uint32_t h0 = a0 * r0[ix] + a1 * r0[ix1];
+      const uint32_t h1 = a0 * r1[ix] + a1 * r1[ix1];
+      v = (b0 * h0 + b1 * h1 + (1u << 15)) >> 16;
+    }
+    out |= v << (8 * k);
+  }
+  *reinterpret_cast<uint32_t*>(dst + (size_t)y * dpitch + x4) = out;
+}
+
+// ---- K2: FAST-9/16 -----------------------------------------------------------------------------------------------------
+// Corner score of one pixel: m = max over the 16 cyclic 9-arcs of max(min_i d_i, min_i -d_i), score = m-1 if m > t.
+// Sliding 9-window minimum over the ring by doubling (windows 2, 4, 8, then +1), once on d = ring - centre (bright arcs) and
+// once on the explicitly negated array (dark arcs).  NB: the obvious formulation max(best, max(mn, -mx)) inside one unrolled
+// loop is MISCOMPILED by ptxas 12.9 for sm_100a (the negation is dropped when it fuses the chain into VIMNMX3) — keep the
+// two arrays separate; tests/test_orb_gpu.py::test_fast_candidates_match_oracle guards this.
+__device__ __forceinline__ int ring_arc9_maxmin(const int* v) {
+  int m2[16], m4[16], m8[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) m2[i] = min(v[i], v[(i + 1) & 15]);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) m4[i] = min(m2[i], m2[(i + 2) & 15]);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) m8[i] = min(m4[i], m4[(i + 4) & 15]);
+  int best = min(m8[0], v[8]);
+#pragma unroll
+  for (int i = 1; i < 16; ++i) best = max(best, min(m8[i], v[(i + 8) & 15]));
+  return best;
+}
+
+__device__ __forceinline__ int fast_full_score(const uint8_t* p /* centre inside the shared tile */, int threshold) {
+  // ring offsets (dx,dy), radius 3
+  const int c = p[0];
+  int r[16];
+  r[0] = p[3 * kInW + 0]; r[1] = p[3 * kInW + 1]; r[2] = p[2 * kInW + 2]; r[3] = p[1 * kInW + 3];
+  r[4] = p[3]; r[5] = p[-1 * kInW + 3]; r[6] = p[-2 * kInW + 2]; r[7] = p[-3 * kInW + 1];
+  r[8] = p[-3 * kInW]; r[9] = p[-3 * kInW - 1]; r[10] = p[-2 * kInW - 2]; r[11] = p[-1 * kInW - 3];
+  r[12] = p[-3]; r[13] = p[1 * kInW - 3]; r[14] = p[2 * kInW - 2]; r[15] = p[3 * kInW - 1];
+  int d[16], nd[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    d[k] = r[k] - c;
+    nd[k] = c - r[k];
+    asm volatile("" : "+r"(nd[k]));  // opaque to the optimiser: it must not re-derive nd from d (see NB above)
+  }
+  const int bright = ring_arc9_maxmin(d);
+  const int dark = ring_arc9_maxmin(nd);
+  const int best = bright > dark ? bright : dark;
+  return best > threshold ? best - 1 : 0;
+}
+
+__global__ void __launch_bounds__(kFastThreads) orb_fast_kernel(const __grid_constant__ OrbParams P, const uint8_t* __restrict__ pyr,
+                                                                uint32_t* __restrict__ cand_pos, uint8_t* __restrict__ cand_score,
+                                                                int* __restrict__ counts, int* __restrict__ hist) {
+  __shared__ __align__(16) uint8_t s_in[kInH * kInW];
+  __shared__ uint8_t s_sc[kScH * kScW];
+  __shared__ uint16_t s_work[kScH * kScW];
+  __shared__ int s_nwork;
+  // which level / tile
+  int l = 0;
+#pragma unroll 1
+  for (int k = 1; k < P.nlevels; ++k)
+    if ((int)blockIdx.x >= P.lv[k].tile_start) l = k;
+  const LevelInfo& L = P.lv[l];
+  const int t = blockIdx.x - L.tile_start;
+  const int x0 = (t % L.tiles_x) * kTileW, y0 = (t / L.tiles_x) * kTileH;
+  const uint8_t* img = pyr + L.off;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_nwork = 0;
+  // stage the input tile with 32-bit loads (x0-4 and the pitch are 4-byte aligned); zero outside the image rows / pitch
+  for (int i = tid; i < kInH * (kInW / 4); i += kFastThreads) {
+    const int ry = i / (kInW / 4), rx = (i % (kInW / 4)) * 4;
+    const int gy = y0 - 4 + ry, gx = x0 - 4 + rx;
+    uint32_t v = 0;
+    if (gy >= 0 && gy < L.h && gx >= 0 && gx + 3 < L.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * L.pitch + gx));
+    *reinterpret_cast<uint32_t*>(&s_in[ry * kInW + rx]) = v;
+  }
+  __syncthreads();
+  const int thr = P.fast_threshold;
+  // phase 1: quick reject (any 9-arc contains one pixel of each opposite pair) -> worklist
+  for (int i = tid; i < kScH * kScW; i += kFastThreads) {
+    const int lx = i % kScW, ly = i / kScW;
+    const int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
+    s_sc[i] = 0;
+    if (gx >= 3 && gx < L.w - 3 && gy >= 3 && gy < L.h - 3) {
+      const uint8_t* p = &s_in[(ly + 3) * kInW + lx + 3];
+      const int c = p[0], lo = c - thr, hi = c + thr;
+      const int a = p[3 * kInW], b = p[-3 * kInW], e = p[3], f = p[-3];
+      const bool in0 = (a >= lo) & (a <= hi) & (b >= lo) & (b <= hi);
+      const bool in1 = (e >= lo) & (e <= hi) & (f >= lo) & (f <= hi);
+      if (!in0 && !in1) s_work[atomicAdd(&s_nwork, 1)] = (uint16_t)i;
+    }
+  }
+  __syncthreads();
+  // phase 2: dense full-score pass over the survivors
+  const int nwork = s_nwork;
+  for (int k = tid; k < nwork; k += kFastThreads) {
+    const int i = s_work[k];
+    const int lx = i % kScW, ly = i / kScW;
+    s_sc[i] = (uint8_t)fast_full_score(&s_in[(ly + 3) * kInW + lx + 3], thr);
+  }
+  __syncthreads();
+  // phase 3: strict 3x3 NMS, border filter, emit
+  for (int i = tid; i < kTileH * kTileW; i += kFastThreads) {
+    const int lx = i % kTileW, ly = i / kTileW;
+    const int gx = x0 + lx, gy = y0 + ly;
+    const uint8_t* q = &s_sc[(ly + 1) * kScW + lx + 1];
+    const int s = q[0];
+    if (s == 0) continue;
+    if (gx < P.border || gx >= L.w - P.border || gy < P.border || gy >= L.h - P.border) continue;
+    if (s > q[-1] && s > q[1] && s > q[-kScW - 1] && s > q[-kScW] && s > q[-kScW + 1] && s > q[kScW - 1] && s > q[kScW] && s > q[kScW + 1]) {
+      const int idx = atomicAdd(&counts[l], 1);
+      if (idx < L.cand_cap) {
+        cand_pos[L.cand_off + idx] = ((uint32_t)gy << 16) | (uint32_t)gx;
+        cand_score[L.cand_off + idx] = (uint8_t)s;
+      }
+      atomicAdd(&hist[l * 256 + s], 1);
+    }
+  }
+}
+
+// ---- K3: Harris ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_key(float f) {  // order-preserving map float -> uint32 (larger float, larger key)
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ float harris_response(const uint8_t* __restrict__ img, int pitch, int x, int y) {
+  int a = 0, b = 0, c = 0;
+#pragma unroll 1
+  for (int dy = -3; dy <= 3; ++dy) {
+    const uint8_t* pm = img + (size_t)(y + dy - 1) * pitch + x;
+    const uint8_t* p0 = pm + pitch;
+    const uint8_t* pp = p0 + pitch;
+#pragma unroll
+    for (int dx = -3; dx <= 3; ++dx) {
+      const int Ix = ((int)p0[dx + 1] - (int)p0[dx - 1]) * 2 + ((int)pm[dx + 1] - (int)pm[dx - 1]) + ((int)pp[dx + 1] - (int)pp[dx - 1]);
+      const int Iy = ((int)pp[dx] - (int)pm[dx]) * 2 + ((int)pp[dx - 1] - (int)pm[dx - 1]) + ((int)pp[dx + 1] - (int)pm[dx + 1]);
+      a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+    }
+  }
+  const float scale = __fdiv_rn(1.f, __fmul_rn((float)(4 * 7), 255.f));
+  const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+  const float fa = (float)a, fb = (float)b, fc = (float)c, sab = __fadd_rn(fa, fb);
+  const float v = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, sab), sab));
+  return __fmul_rn(v, s4);
+}
+
+// FAST-score threshold of level l: the (2 n_l)-th largest score (ties kept); 0 keeps everything; 256 keeps nothing
+__device__ __forceinline__ int fast_keep_threshold(const int* __restrict__ hist_l, int quota) {
+  const int want = 2 * quota;
+  if (want <= 0) return 256;
+  int cum = 0;
+  for (int s = 255; s >= 1; --s) {
+    cum += hist_l[s];
+    if (cum >= want) return s;
+  }
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) orb_harris_kernel(const __grid_constant__ OrbParams P, const uint8_t* __restrict__ pyr,
+                                                         const uint32_t* __restrict__ cand_pos, const uint8_t* __restrict__ cand_score,
+                                                         const int* __restrict__ counts, const int* __restrict__ hist,
+                                                         uint32_t* __restrict__ cand_key, float* __restrict__ cand_resp) {
+  __shared__ int s_thr;
+  const int l = blockIdx.y;
+  const LevelInfo& L = P.lv[l];
+  if (threadIdx.x == 0) s_thr = fast_keep_threshold(hist + l * 256, L.quota);
+  __syncthreads();
+  const int thr = s_thr;
+  const int n = min(counts[l], L.cand_cap);
+  const uint8_t* img = pyr + L.off;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int g = L.cand_off + i;
+    uint32_t key = 0;
+    float r = 0.f;
+    if ((int)cand_score[g] >= thr) {
+      const uint32_t pos = cand_pos[g];
+      r = harris_response(img, L.pitch, pos & 0xffff, pos >> 16);
+      key = float_key(r);
+    }
+    cand_key[g] = key;
+    cand_resp[g] = r;
+  }
+}
+
+// ---- K3b: per-level selection + canonical ordering ------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSelThreads) orb_select_kernel(const __grid_constant__ OrbParams P, const uint32_t* __restrict__ cand_pos,
+                                                                 const uint32_t* __restrict__ cand_key, const float* __restrict__ cand_resp,
+                                                                 const int* __restrict__ counts, uint32_t* __restrict__ kept_pos,
+                                                                 float* __restrict__ kept_resp, int* __restrict__ kept_count,
+                                                                 int* __restrict__ status) {
+  __shared__ int s_hist[256];
+  __shared__ unsigned long long s_keys[kSelMax];
+  __shared__ int s_n, s_k;
+  __shared__ uint32_t s_prefix;
+  const int l = blockIdx.x, tid = threadIdx.x;
+  const LevelInfo& L = P.lv[l];
+  const int n = min(counts[l], L.cand_cap);
+  const uint32_t* keys = cand_key + L.cand_off;
+  if (counts[l] > L.cand_cap && tid == 0) atomicMin(status, -1);  // cannot happen (cap = w*h/4): flag loudly if it does
+  // how many survived the FAST-score cut
+  int local = 0;
+  for (int i = tid; i < n; i += kSelThreads) local += keys[i] != 0;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  if (local) atomicAdd(&s_n, local);
+  __syncthreads();
+  const int m = s_n;
+  __syncthreads();  // every thread must have read s_n before it is reused below
+  uint32_t T = 1;  // keep every key >= T; key 0 = dropped
+  if (L.quota <= 0) T = 0xffffffffu;
+  else if (m > L.quota) {
+    // 4-pass MSB-first radix select of the quota-th largest key
+    if (tid == 0) { s_prefix = 0; s_k = L.quota; }
+    uint32_t mask = 0;
+    for (int pass = 3; pass >= 0; --pass) {
+      const int shift = 8 * pass;
+      for (int b = tid; b < 256; b += kSelThreads) s_hist[b] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      for (int i = tid; i < n; i += kSelThreads) {
+        const uint32_t k = keys[i];
+        if (k != 0 && (k & mask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int cum = 0, b = 255, want = s_k;
+        for (; b > 0; --b) {
+          if (cum + s_hist[b] >= want) break;
+          cum += s_hist[b];
+        }
+        s_k = want - cum;
+        s_prefix = prefix | ((uint32_t)b << shift);
+      }
+      __syncthreads();
+      mask |= 0xffu << shift;
+    }
+    T = s_prefix;
+  }
+  // compaction of the kept candidates: (pos << 32) | candidate index
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += kSelThreads) {
+    const uint32_t k = keys[i];
+    if (k != 0 && k >= T) {
+      const int slot = atomicAdd(&s_n, 1);
+      if (slot < kSelMax) s_keys[slot] = ((unsigned long long)cand_pos[L.cand_off + i] << 32) | (unsigned)i;
+    }
+  }
+  __syncthreads();
+  const int cnt = s_n;
+  if (cnt > kSelMax) {
+    if (tid == 0) { atomicMin(status, -2); kept_count[l] = 0; }
+    return;
+  }
+  int np2 = 1;
+  while (np2 < cnt) np2 <<= 1;
+  for (int i = cnt + tid; i < np2; i += kSelThreads) s_keys[i] = ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < np2; i += kSelThreads) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = s_keys[i], b = s_keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { s_keys[i] = b; s_keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = tid; i < cnt; i += kSelThreads) {
+    const unsigned long long e = s_keys[i];
+    kept_pos[l * kSelMax + i] = (uint32_t)(e >> 32);
+    kept_resp[l * kSelMax + i] = cand_resp[L.cand_off + (uint32_t)e];
+  }
+  if (tid == 0) kept_count[l] = cnt;
+}
+
+// ---- K4: orientation + rBRIEF ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {  // cv::fastAtan2, bit-exact (App. A.4): no FMA
+  const float k = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = __fmul_rn(0.9997878412794807f, k), p3 = __fmul_rn(-0.3258083974640975f, k),
+              p5 = __fmul_rn(0.1555786518463281f, k), p7 = __fmul_rn(-0.04432655554792128f, k);
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float eps = (float)2.220446049250313e-16;
+  float a;
+  if (ax >= ay) {
+    const float c = __fdiv_rn(ay, __fadd_rn(ax, eps)), c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    const float c = __fdiv_rn(ax, __fadd_rn(ay, eps)), c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0.f) a = __fsub_rn(180.f, a);
+  if (y < 0.f) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+// deterministic double sincos: Cody-Waite by pi/2 + fdlibm kernel polynomials, explicit fma only (same op sequence as the oracle)
+__device__ __forceinline__ void det_sincos(double x, double* sn, double* cs) {
+  const double kf = rint(__dmul_rn(x, 0.63661977236758134308));
+  const int q = (int)kf & 3;
+  double r = fma(-kf, 1.57079632673412561417e+00, x);
+  r = fma(-kf, 6.07710050650619224932e-11, r);
+  const double z = __dmul_rn(r, r);
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  const double s = fma(__dmul_rn(z, r), ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  const double c = fma(__dmul_rn(z, z), pc, fma(z, -0.5, 1.0));
+  switch (q) {
+    case 0: *sn = s; *cs = c; break;
+    case 1: *sn = c; *cs = -s; break;
+    case 2: *sn = -s; *cs = -c; break;
+    default: *sn = -c; *cs = s; break;
+  }
+}
+
+constexpr int kPatch = 45, kPatchPitch = 48, kPR = 22;  // raw patch: rows/cols -22..22
+constexpr int kBl = 39, kBlPitch = 40, kBR = 19;        // blurred patch: -19..19
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+struct DescSmem {
+  uint8_t patch[kPatch * kPatchPitch];
+  float rows[kPatch * kBlPitch];
+  uint8_t blur[kBl * kBlPitch];
+};
+
+__global__ void __launch_bounds__(kDescWarps * 32) orb_describe_kernel(const __grid_constant__ OrbParams P, const uint8_t* __restrict__ pyr,
+                                                                      const uint32_t* __restrict__ kept_pos, const float* __restrict__ kept_resp,
+                                                                      const int* __restrict__ kept_count, const signed char* __restrict__ pattern,
+                                                                      gb_keypoint* __restrict__ out_kps, uint8_t* __restrict__ out_desc,
+                                                                      int capacity, int* __restrict__ out_count, int* __restrict__ out_status,
+                                                                      const int* __restrict__ status_in) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ signed char s_pat[1024];
+  DescSmem* sm = reinterpret_cast<DescSmem*>(smem_raw) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<int*>(s_pat)[i] = __ldg(reinterpret_cast<const int*>(pattern) + i);
+  // level prefix
+  int total = 0, l = -1, base = 0;
+  const int g = blockIdx.x * kDescWarps + warp;
+  for (int k = 0; k < P.nlevels; ++k) {
+    const int c = kept_count[k];
+    if (l < 0 && g < total + c) { l = k; base = total; }
+    total += c;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int st = *status_in;
+    out_count[0] = (total <= capacity && st == 0) ? total : 0;
+    out_status[0] = st != 0 ? st : (total > capacity ? total : 0);
+  }
+  __syncthreads();
+  if (l < 0 || total > capacity || *status_in != 0) return;
+  const LevelInfo& L = P.lv[l];
+  const uint32_t pos = kept_pos[l * kSelMax + (g - base)];
+  const int x = pos & 0xffff, y = pos >> 16;
+  const uint8_t* img = pyr + L.off;
+  // raw 45x45 patch (always inside the level: border >= 22)
+  for (int i = lane; i < kPatch * kPatch; i += 32) {
+    const int r = i / kPatch, c = i % kPatch;
+    sm->patch[r * kPatchPitch + c] = __ldg(img + (size_t)(y - kPR + r) * L.pitch + (x - kPR + c));
+  }
+  __syncwarp();
+  // intensity-centroid orientation over the radius-15 disc: lane = row v+15
+  int m01 = 0, m10 = 0;
+  if (lane < 31) {
+    const int v = lane - 15, d = c_umax[v < 0 ? -v : v];
+    const uint8_t* row = &sm->patch[(kPR + v) * kPatchPitch + kPR];
+    int rs = 0, ru = 0;
+    for (int u = -d; u <= d; ++u) { const int val = row[u]; rs += val; ru += u * val; }
+    m01 = v * rs; m10 = ru;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { m01 += __shfl_xor_sync(0xffffffffu, m01, o); m10 += __shfl_xor_sync(0xffffffffu, m10, o); }
+  const float angle = fast_atan2_deg((float)m01, (float)m10);
+  // separable 7-tap float blur of the patch, cv2.sepFilter2D order: rows sequential-fma, columns symmetric-fma
+  const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu), k2 = __uint_as_float(0x3e434a39u), k3 = __uint_as_float(0x3e5d4ae0u);
+  for (int i = lane; i < kPatch * kBl; i += 32) {
+    const int r = i / kBl, c = i % kBl;  // output col c <-> patch cols c..c+6
+    const uint8_t* p = &sm->patch[r * kPatchPitch + c];
+    float s = __fmul_rn(k0, (float)p[0]);
+    s = __fmaf_rn((float)p[1], k1, s);
+    s = __fmaf_rn((float)p[2], k2, s);
+    s = __fmaf_rn((float)p[3], k3, s);
+    s = __fmaf_rn((float)p[4], k2, s);
+    s = __fmaf_rn((float)p[5], k1, s);
+    s = __fmaf_rn((float)p[6], k0, s);
+    sm->rows[r * kBlPitch + c] = s;
+  }
+  __syncwarp();
+  for (int i = lane; i < kBl * kBl; i += 32) {
+    const int r = i / kBl, c = i % kBl;
+    const float* q = &sm->rows[r * kBlPitch + c];
+    float s = __fmul_rn(k3, q[3 * kBlPitch]);
+    s = __fmaf_rn(__fadd_rn(q[2 * kBlPitch], q[4 * kBlPitch]), k2, s);
+    s = __fmaf_rn(__fadd_rn(q[1 * kBlPitch], q[5 * kBlPitch]), k1, s);
+    s = __fmaf_rn(__fadd_rn(q[0], q[6 * kBlPitch]), k0, s);
+    int v = __float2int_rn(s);
+    v = v < 0 ? 0 : (v > 255 ? 255 : v);
+    sm->blur[r * kBlPitch + c] = (uint8_t)v;
+  }
+  __syncwarp();
+  // 256 rotated binary tests: lane j produces descriptor byte j
+  const float theta = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.0));
+  double sd, cd;
+  det_sincos((double)theta, &sd, &cd);
+  const float a = (float)cd, b = (float)sd;
+  const uint8_t* center = &sm->blur[kBR * kBlPitch + kBR];
+  int byte = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const signed char* pt = &s_pat[4 * (8 * lane + k)];
+    const float px0 = (float)pt[0], py0 = (float)pt[1], px1 = (float)pt[2], py1 = (float)pt[3];
+    const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(px0, a), __fmul_rn(py0, b)));
+    const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(px0, b), __fmul_rn(py0, a)));
+    const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(px1, a), __fmul_rn(py1, b)));
+    const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(px1, b), __fmul_rn(py1, a)));
+    const int t0 = center[iy0 * kBlPitch + ix0], t1 = center[iy1 * kBlPitch + ix1];
+    byte |= (t0 < t1) << k;
+  }
+  out_desc[(size_t)g * 32 + lane] = (uint8_t)byte;
+  if (lane == 0) {
+    gb_keypoint kp;
+    kp.x = __fmul_rn((float)x, L.scale);
+    kp.y = __fmul_rn((float)y, L.scale);
+    kp.size = __fmul_rn(31.f, L.scale);
+    kp.angle = angle;
+    kp.response = kept_resp[l * kSelMax + (g - base)];
+    kp.octave = l;
+    kp.class_id = -1;
+    out_kps[g] = kp;
+  }
+}
+
+}  // namespace
+
+// ==========================================================================================================================
+// host side
+// ==========================================================================================================================
+struct OrbState {
+  // configuration the buffers were built for
+  int w = 0, h = 0;
+  gb_orb_cfg cfg{};
+  OrbParams P{};
+  // device buffers
+  uint8_t* d_pyr = nullptr; size_t pyr_bytes = 0;
+  uint32_t* d_tabs = nullptr;           // resize tables
+  uint32_t* d_cand_pos = nullptr; uint8_t* d_cand_score = nullptr; uint32_t* d_cand_key = nullptr; float* d_cand_resp = nullptr;
+  int* d_counts = nullptr;              // [kMaxLevels] candidates | [kMaxLevels] kept | [1] status | hist [kMaxLevels*256]
+  uint32_t* d_kept_pos = nullptr; float* d_kept_resp = nullptr;
+  signed char* d_pattern = nullptr;
+  int total_cand = 0;
+  bool valid = false;
+};
+
+static void orb_free_buffers(OrbState* s) {
+  cudaFree(s->d_pyr); cudaFree(s->d_tabs); cudaFree(s->d_cand_pos); cudaFree(s->d_cand_score); cudaFree(s->d_cand_key);
+  cudaFree(s->d_cand_resp); cudaFree(s->d_counts); cudaFree(s->d_kept_pos); cudaFree(s->d_kept_resp);
+  s->d_pyr = nullptr; s->d_tabs = nullptr; s->d_cand_pos = nullptr; s->d_cand_score = nullptr; s->d_cand_key = nullptr;
+  s->d_cand_resp = nullptr; s->d_counts = nullptr; s->d_kept_pos = nullptr; s->d_kept_resp = nullptr;
+  s->valid = false;
+}
+
+void gb_orb_state_free(gb_ctx* ctx) {
+  if (!ctx->orb) return;
+  orb_free_buffers(ctx->orb);
+  cudaFree(ctx->orb->d_pattern);
+  delete ctx->orb;
+  ctx->orb = nullptr;
+}
+
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+
+static int orb_cfg_check(gb_ctx* ctx, const gb_orb_cfg* c) {
+  if (!c || c->nfeatures <= 0 || c->nlevels < 1 || c->nlevels > kMaxLevels || !(c->scale_factor > 1.0f) || c->edge_threshold < 22 ||
+      c->first_level != 0 || c->wta_k != 2 || c->score_type != 0 || c->patch_size != 31 || c->fast_threshold < 1 || c->fast_threshold > 254) {
+    gb_set_error(ctx, "gb_orb: unsupported configuration (need nlevels 1..%d, scale>1, edge_threshold>=22, first_level 0, wta_k 2, "
+                 "HARRIS score, patch 31, fast_threshold 1..254)", kMaxLevels);
+    return GB_ERR_INVALID;
+  }
+  return GB_OK;
+}
+
+// (Re)build the per-resolution state: level geometry, quotas, resize tables, buffers.
+static int orb_prepare(gb_ctx* ctx, int w, int h, const gb_orb_cfg* cfg) {
+  if (!ctx->orb) {
+    ctx->orb = new OrbState();
+    GB_CUDA(ctx, cudaMalloc((void**)&ctx->orb->d_pattern, 1024));
+    GB_CUDA(ctx, cudaMemcpyAsync(ctx->orb->d_pattern, kOrbPattern, 1024, cudaMemcpyHostToDevice, ctx->stream));
+    GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  OrbState* s = ctx->orb;
+  if (s->valid && s->w == w && s->h == h && memcmp(&s->cfg, cfg, sizeof *cfg) == 0) return GB_OK;
+  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  orb_free_buffers(s);
+  if (w > 16384 || h > 16384) {
+    gb_set_error(ctx, "gb_orb: image %dx%d too large (max 16384)", w, h);
+    return GB_ERR_INVALID;
+  }
+  OrbParams& P = s->P;
+  memset(&P, 0, sizeof P);
+  P.fast_threshold = cfg->fast_threshold;
+  P.border = cfg->edge_threshold;
+  // quotas (App. A.3, float arithmetic as OpenCV)
+  int quota[kMaxLevels];
+  {
+    const float factor = (float)(1.0 / (double)cfg->scale_factor);
+    float nd = (float)cfg->nfeatures * (1.f - factor) / (1.f - (float)pow((double)factor, (double)cfg->nlevels));
+    int sum = 0;
+    for (int l = 0; l < cfg->nlevels - 1; ++l) {
+      quota[l] = cv_round_f(nd);
+      sum += quota[l];
+      nd *= factor;
+    }
+    quota[cfg->nlevels - 1] = std::max(cfg->nfeatures - sum, 0);
+  }
+  size_t off = 0;
+  int tiles = 0, cand = 0, coef = 0, nl = 0;
+  for (int l = 0; l < cfg->nlevels; ++l) {
+    const float sc = (float)pow((double)cfg->scale_factor, (double)l);
+    const int lw = cv_round_f((float)w / sc), lh = cv_round_f((float)h / sc);
+    if (lw < 1 || lh < 1) break;
+    LevelInfo& L = P.lv[l];
+    L.w = lw; L.h = lh; L.pitch = (lw + 127) & ~127; L.quota = quota[l]; L.scale = sc;
+    L.off = off;
+    off += (size_t)L.pitch * lh;
+    L.tiles_x = gb_div_up(lw, kTileW);
+    L.tile_start = tiles;
+    // levels too small to hold a keypoint produce none (and the oracle skips them): give them zero tiles
+    const bool usable = lw > 2 * P.border && lh > 2 * P.border;
+    if (!usable) L.tiles_x = 0;
+    tiles += usable ? L.tiles_x * gb_div_up(lh, kTileH) : 0;
+    L.cand_off = cand;
+    L.cand_cap = usable ? (lw * lh) / 4 + 1024 : 0;
+    cand += L.cand_cap;
+    L.coef_off = coef;
+    coef += lw + lh;
+    nl = l + 1;
+  }
+  P.nlevels = nl;
+  P.total_tiles = tiles;
+  s->total_cand = cand;
+  s->pyr_bytes = off + 256;
+  // resize tables
+  std::vector<uint32_t> tabs((size_t)coef + 1, 0);
+  for (int l = 1; l < nl; ++l) {
+    const LevelInfo &S = P.lv[l - 1], &D = P.lv[l];
+    auto fill = [&](int src, int dst, uint32_t* out) {
+      const double scale = (double)src / (double)dst;
+      for (int d = 0; d < dst; ++d) {
+        const double f = ((double)d + 0.5) * scale - 0.5;
+        int i = (int)floor(f);
+        int a = (int)lrint((f - (double)i) * 256.0);
+        if (i < 0) { i = 0; a = 0; }
+        if (i >= src - 1) { i = src - 1; a = 0; }
+        out[d] = (uint32_t)i | ((uint32_t)a << 16);
+      }
+    };
+    fill(S.w, D.w, tabs.data() + D.coef_off);
+    fill(S.h, D.h, tabs.data() + D.coef_off + D.w);
+  }
+  GB_CUDA(ctx, cudaMalloc((void**)&s->d_pyr, s->pyr_bytes));
+  GB_CUDA(ctx, cudaMemsetAsync(s->d_pyr, 0, s->pyr_bytes, ctx->stream));
+  GB_CUDA(ctx, cudaMalloc((void**)&s->d_tabs, tabs.size() * 4));
+  GB_CUDA(ctx, cudaMemcpyAsync(s->d_tabs, tabs.data(), tabs.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  const size_t nc = (size_t)std::max(cand, 1);
+  GB_CUDA(ctx, cudaMalloc((void**)&s->d_cand_pos, nc * 4));
+  GB_CUDA(ctx, cudaMalloc((void**)&s->d_cand_score, nc));
+  GB_CUDA(ctx, cudaMalloc((void**)&s->d_cand_key, nc * 4));
+  GB_CUDA(ctx, cudaMalloc((void**)&s->d_cand_resp, nc * 4));
+  GB_CUDA(ctx, cudaMalloc((void**)&s->d_counts, (2 * kMaxLevels + 8 + kMaxLevels * 256) * sizeof(int)));
+  GB_CUDA(ctx, cudaMalloc((void**)&s->d_kept_pos, (size_t)kMaxLevels * kSelMax * 4));
+  GB_CUDA(ctx, cudaMalloc((void**)&s->d_kept_resp, (size_t)kMaxLevels * kSelMax * 4));
+  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // tabs is a local vector
+  static bool attr_set = false;
+  if (!attr_set) {
+    GB_CUDA(ctx, cudaFuncSetAttribute(orb_describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(DescSmem) * kDescWarps)));
+    attr_set = true;
+  }
+  s->w = w; s->h = h; s->cfg = *cfg; s->valid = true;
+  return GB_OK;
+}
+
+// Enqueue the whole extraction of the frame already sitting in level 0 of the pyramid buffer.
+static int orb_launch(gb_ctx* ctx, gb_features* out) {
+  OrbState* s = ctx->orb;
+  const OrbParams& P = s->P;
+  cudaStream_t st = ctx->stream;
+  int* d_counts = s->d_counts;
+  int* d_kept = d_counts + kMaxLevels;
+  int* d_status = d_counts + 2 * kMaxLevels;
+  int* d_hist = d_counts + 2 * kMaxLevels + 8;
+  GB_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (2 * kMaxLevels + 8 + kMaxLevels * 256) * sizeof(int), st));
+  for (int l = 1; l < P.nlevels; ++l) {
+    const LevelInfo &S = P.lv[l - 1], &D = P.lv[l];
+    dim3 blk(64, 4), grd(gb_div_up(gb_div_up(D.w, 4), 64), gb_div_up(D.h, 4));
+    orb_resize_kernel<<<grd, blk, 0, st>>>(s->d_pyr + S.off, S.w, S.h, S.pitch, s->d_pyr + D.off, D.w, D.h, D.pitch,
+                                           s->d_tabs + D.coef_off, s->d_tabs + D.coef_off + D.w);
+    GB_LAUNCH_CHECK(ctx);
+  }
+  if (P.total_tiles > 0) {
+    orb_fast_kernel<<<P.total_tiles, kFastThreads, 0, st>>>(P, s->d_pyr, s->d_cand_pos, s->d_cand_score, d_counts, d_hist);
+    GB_LAUNCH_CHECK(ctx);
+    orb_harris_kernel<<<dim3(32, P.nlevels), 256, 0, st>>>(P, s->d_pyr, s->d_cand_pos, s->d_cand_score, d_counts, d_hist,
+                                                           s->d_cand_key, s->d_cand_resp);
+    GB_LAUNCH_CHECK(ctx);
+    orb_select_kernel<<<P.nlevels, kSelThreads, 0, st>>>(P, s->d_cand_pos, s->d_cand_key, s->d_cand_resp, d_counts, s->d_kept_pos,
+                                                         s->d_kept_resp, d_kept, d_status);
+    GB_LAUNCH_CHECK(ctx);
+  }
+  const int blocks = std::max(1, gb_div_up(out->capacity, kDescWarps));
+  orb_describe_kernel<<<blocks, kDescWarps * 32, sizeof(DescSmem) * kDescWarps, st>>>(
+      P, s->d_pyr, s->d_kept_pos, s->d_kept_resp, d_kept, s->d_pattern, out->d_kps, out->d_desc, out->capacity, out->d_count,
+      out->d_status, d_status);
+  GB_LAUNCH_CHECK(ctx);
+  out->h_count = -1;
+  return GB_OK;
+}
+
 extern "C" {
+
 void gb_orb_cfg_default(gb_orb_cfg* c) {
   if (!c) return;
-  c->nfeatures = 500; c->scale_factor = 1.2f; c->nlevels = 8; c->edge_threshold = 31; c->first_level = 0; c->wta_k = 2;
-  c->score_type = 0; c->patch_size = 31; c->fast_threshold = 20;
+  c->nfeatures = 500;
+  c->scale_factor = 1.2f;
+  c->nlevels = 8;
+  c->edge_threshold = 31;
+  c->first_level = 0;
+  c->wta_k = 2;
+  c->score_type = 0;
+  c->patch_size = 31;
+  c->fast_threshold = 20;
 }
-int gb_orb_extract(gb_ctx* ctx, const uint8_t*, int, int, const gb_orb_cfg*, gb_keypoint*, uint8_t*, int*) { gb_set_error(ctx, "not built yet"); return GB_ERR_INVALID; }
-int gb_orb_extract_to(gb_ctx* ctx, const uint8_t*, int, int, int, int, const gb_orb_cfg*, gb_features*) { gb_set_error(ctx, "not built yet"); return GB_ERR_INVALID; }
+
+int gb_orb_extract_to(gb_ctx* ctx, const uint8_t* img, int img_is_device, int width, int height, int pitch, const gb_orb_cfg* cfg_in,
+                      gb_features* out) {
+  if (!ctx || !img || !out || width < 1 || height < 1 || pitch < width) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  gb_orb_cfg cfg;
+  if (cfg_in) cfg = *cfg_in; else gb_orb_cfg_default(&cfg);
+  GB_CHECK(orb_cfg_check(ctx, &cfg));
+  GB_CHECK(orb_prepare(ctx, width, height, &cfg));
+  OrbState* s = ctx->orb;
+  const LevelInfo& L0 = s->P.lv[0];
+  if (img_is_device) {
+    GB_CUDA(ctx, cudaMemcpy2DAsync(s->d_pyr + L0.off, L0.pitch, img, pitch, width, height, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    // pinned caller memory goes straight over PCIe; pageable memory is staged through the ctx's pinned buffer
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, img) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const uint8_t* src = img;
+    int spitch = pitch;
+    if (!pinned) {
+      GB_CHECK(gb_stage_reserve(ctx, ctx->h_stage_off + (size_t)width * height + 1024));
+      uint8_t* hs = (uint8_t*)gb_stage_alloc(ctx, (size_t)width * height);
+      for (int y = 0; y < height; ++y) memcpy(hs + (size_t)y * width, img + (size_t)y * pitch, width);
+      src = hs;
+      spitch = width;
+    }
+    GB_CUDA(ctx, cudaMemcpy2DAsync(s->d_pyr + L0.off, L0.pitch, src, spitch, width, height, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  GB_CHECK(orb_launch(ctx, out));
+  if (!img_is_device) GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // staging / caller buffer may be reused
+  return GB_OK;
 }
+
+int gb_orb_extract(gb_ctx* ctx, const uint8_t* img, int width, int height, const gb_orb_cfg* cfg_in, gb_keypoint* kps, uint8_t* desc,
+                   int* n) {
+  if (!ctx || !img || !n || *n < 0) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  gb_orb_cfg cfg;
+  if (cfg_in) cfg = *cfg_in; else gb_orb_cfg_default(&cfg);
+  GB_CHECK(orb_cfg_check(ctx, &cfg));
+  const int want_cap = std::max(*n, 2 * cfg.nfeatures + 256);
+  if (!ctx->tmp_f || ctx->tmp_f->capacity < want_cap) {
+    if (ctx->tmp_f) gb_features_destroy(ctx, ctx->tmp_f);
+    ctx->tmp_f = nullptr;
+    GB_CHECK(gb_features_create(ctx, want_cap, &ctx->tmp_f));
+  }
+  gb_features* f = ctx->tmp_f;
+  GB_CHECK(gb_orb_extract_to(ctx, img, 0, width, height, width, &cfg, f));
+  const int cap = *n;
+  int cnt = 0;
+  int rc = gb_features_count(ctx, f, &cnt);
+  *n = cnt;
+  if (rc != GB_OK) return rc;
+  if (cnt > cap) {
+    gb_set_error(ctx, "gb_orb_extract: %d keypoints > caller capacity %d", cnt, cap);
+    return GB_ERR_CAPACITY;
+  }
+  int m = cap;
+  return gb_features_download(ctx, f, kps, desc, &m);
+}
+
+// ---- test hook: candidates of the LAST extraction on this ctx (after FAST+NMS+border), and the kept lists --------------
+GB_API int gb_dbg_orb_candidates(gb_ctx* ctx, int level, uint32_t* pos, uint8_t* score, float* resp, uint32_t* key, int cap, int* n,
+                                 uint32_t* kept_pos, int kept_cap, int* n_kept) {
+  if (!ctx || !ctx->orb || !ctx->orb->valid || level < 0 || level >= ctx->orb->P.nlevels) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  OrbState* s = ctx->orb;
+  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int counts[2 * kMaxLevels];
+  GB_CUDA(ctx, cudaMemcpy(counts, s->d_counts, sizeof counts, cudaMemcpyDeviceToHost));
+  const LevelInfo& L = s->P.lv[level];
+  const int c = std::min(counts[level], L.cand_cap);
+  *n = c;
+  const int m = std::min(c, cap);
+  if (pos) GB_CUDA(ctx, cudaMemcpy(pos, s->d_cand_pos + L.cand_off, (size_t)m * 4, cudaMemcpyDeviceToHost));
+  if (score) GB_CUDA(ctx, cudaMemcpy(score, s->d_cand_score + L.cand_off, (size_t)m, cudaMemcpyDeviceToHost));
+  if (resp) GB_CUDA(ctx, cudaMemcpy(resp, s->d_cand_resp + L.cand_off, (size_t)m * 4, cudaMemcpyDeviceToHost));
+  if (key) GB_CUDA(ctx, cudaMemcpy(key, s->d_cand_key + L.cand_off, (size_t)m * 4, cudaMemcpyDeviceToHost));
+  const int k = counts[kMaxLevels + level];
+  if (n_kept) *n_kept = k;
+  if (kept_pos) GB_CUDA(ctx, cudaMemcpy(kept_pos, s->d_kept_pos + (size_t)level * kSelMax, (size_t)std::min(k, kept_cap) * 4, cudaMemcpyDeviceToHost));
+  return GB_OK;
+}
+
+// test hook: download pyramid level `level` of the LAST extraction (dense w*h bytes); returns its size through w/h
+GB_API int gb_dbg_orb_level(gb_ctx* ctx, int level, uint8_t* out, int cap, int* w, int* h) {
+  if (!ctx || !ctx->orb || !ctx->orb->valid || level < 0 || level >= ctx->orb->P.nlevels) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  OrbState* s = ctx->orb;
+  const LevelInfo& L = s->P.lv[level];
+  *w = L.w; *h = L.h;
+  if (!out || cap < L.w * L.h) return GB_ERR_CAPACITY;
+  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  GB_CUDA(ctx, cudaMemcpy2D(out, L.w, s->d_pyr + L.off, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+  return GB_OK;
+}
+
+}  // extern "C"

@@ -350,7 +350,7 @@ static int ba_pcg(int nc, const double* S, const double* g, double* x, int maxit
       double rzn = 0.0;
       for (int a = 0; a < n6; ++a) rzn += r[a] * z[a];
       ++it;
-      if (!(rzn > 0.0) || sqrt(rzn / rz0) < tol) break;
+      if (!(rzn > 0.0) || rzn < tol * tol * rz0) break; /* == sqrt(rzn/rz0) < tol without the sqrt/div */
       double beta = rzn / rz;
       for (int a = 0; a < n6; ++a) p[a] = z[a] + beta * p[a];
       rz = rzn;
