@@ -1,0 +1,115 @@
+// gslam_b200/plugin/host_test.cpp -> gslam_b200_host_test
+//
+// A stand-in for a GSLAM SLAM plugin: it uses ONLY the reference's public API (Optimizer::create, Registry::load, Svar calls,
+// BundleGraph, GImage, KeyPoint) to drive the B200 backends, reading a case from a binary file and writing the results back,
+// so the Python tests can compare the plugin-level outputs with the oracle.  Usage:
+//   gslam_b200_host_test ba   <plugin-dir> in.bin out.bin      optimize(BundleGraph&) through GSLAM::Optimizer::create()
+//   gslam_b200_host_test pnp  <plugin-dir> in.bin out.bin      optimizePnP(...)
+//   gslam_b200_host_test orb  <plugin-dir> in.bin out.bin      Registry::load("b200") -> gslam.b200.orb_extract + match_hamming
+#include <GSLAM/core/GSLAM.h>
+#include <GSLAM/core/Optimizer.h>
+
+#include <cstdio>
+#include <fstream>
+#include <vector>
+
+using namespace GSLAM;
+
+template <typename T>
+static void rd(std::ifstream& f, T* p, size_t n) { f.read(reinterpret_cast<char*>(p), sizeof(T) * n); }
+template <typename T>
+static void wr(std::ofstream& f, const T* p, size_t n) { f.write(reinterpret_cast<const char*>(p), sizeof(T) * n); }
+
+static int runBA(const std::string& dir, const char* in, const char* out, bool pnp) {
+  svar.Set<std::string>("GSLAM_LIBRARY_PATH", dir);  // Registry search path is a svar variable, not process env (Registry.h:95-131)
+  OptimizerPtr opt = Optimizer::create();             // default name "libgslam_optimizer" (Optimizer.h:237)
+  if (!opt) { fprintf(stderr, "Optimizer::create() returned null\n"); return 2; }
+  std::ifstream f(in, std::ios::binary);
+  int32_t hdr[8];
+  rd(f, hdr, 8);
+  const int nc = hdr[0], np = hdr[1], no = hdr[2], iters = hdr[3], has_info = hdr[4];
+  double ftol; rd(f, &ftol, 1);
+  svar.Set<double>("b200.ftol", ftol);
+  opt->_config.maxIterations = iters;
+  std::vector<double> pose(7 * (size_t)nc), pts(3 * (size_t)np), xyz(3 * (size_t)no), info(has_info ? 4 * (size_t)no : 0);
+  std::vector<uint8_t> dof(nc), pf(np);
+  std::vector<int32_t> oc(no), op(no);
+  rd(f, pose.data(), pose.size()); rd(f, dof.data(), dof.size()); rd(f, pts.data(), pts.size()); rd(f, pf.data(), pf.size());
+  rd(f, oc.data(), oc.size()); rd(f, op.data(), op.size()); rd(f, xyz.data(), xyz.size());
+  if (has_info) rd(f, info.data(), info.size());
+  bool ok;
+  std::ofstream o(out, std::ios::binary);
+  if (pnp) {
+    std::vector<std::pair<Point3d, CameraAnchor> > matches(no);
+    for (int k = 0; k < no; ++k)
+      matches[k] = std::make_pair(Point3d(pts[3 * op[k]], pts[3 * op[k] + 1], pts[3 * op[k] + 2]), CameraAnchor(xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2]));
+    SE3 T(SO3(pose[0], pose[1], pose[2], pose[3]), Point3d(pose[4], pose[5], pose[6]));
+    double information[36];
+    ok = opt->optimizePnP(matches, T, (KeyFrameEstimzationDOF)dof[0], information);
+    double p[7] = {T.get_rotation().x, T.get_rotation().y, T.get_rotation().z, T.get_rotation().w, T.get_translation().x, T.get_translation().y, T.get_translation().z};
+    int32_t okv = ok; wr(o, &okv, 1); wr(o, p, 7); wr(o, information, 36);
+    return ok ? 0 : 1;
+  }
+  BundleGraph g;
+  g.keyframes.resize(nc); g.mappoints.resize(np); g.mappointObserves.resize(no);
+  for (int i = 0; i < nc; ++i) {
+    const double* p = &pose[7 * i];
+    g.keyframes[i].estimation = SIM3(SE3(SO3(p[0], p[1], p[2], p[3]), Point3d(p[4], p[5], p[6])), 1.0 + 0.01 * i);  // scales must survive
+    g.keyframes[i].dof = (KeyFrameEstimzationDOF)dof[i];
+  }
+  for (int j = 0; j < np; ++j) g.mappoints[j] = MapPointEstimation(Point3d(pts[3 * j], pts[3 * j + 1], pts[3 * j + 2]), pf[j] != 0);
+  for (int k = 0; k < no; ++k) {
+    BundleEdge& e = g.mappointObserves[k];
+    e.pointId = op[k]; e.frameId = oc[k]; e.measurement = CameraAnchor(xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2]);
+    e.information = has_info ? &info[4 * (size_t)k] : NULL;
+  }
+  g.cameraDOF = UPDATE_CAMERA_NONE;
+  ok = opt->optimize(g);
+  int32_t okv = ok; wr(o, &okv, 1);
+  for (int i = 0; i < nc; ++i) {
+    const SE3& T = g.keyframes[i].estimation.get_se3();
+    double p[8] = {T.get_rotation().x, T.get_rotation().y, T.get_rotation().z, T.get_rotation().w, T.get_translation().x, T.get_translation().y, T.get_translation().z,
+                   g.keyframes[i].estimation.get_scale()};
+    wr(o, p, 8);
+  }
+  for (int j = 0; j < np; ++j) { double p[3] = {g.mappoints[j].first.x, g.mappoints[j].first.y, g.mappoints[j].first.z}; wr(o, p, 3); }
+  return ok ? 0 : 1;
+}
+
+static int runORB(const std::string& dir, const char* in, const char* out) {
+  svar.Set<std::string>("GSLAM_LIBRARY_PATH", dir);
+  Svar mod = Registry::load("b200");  // dlopen + svarInstance() (Registry.h:48-77)
+  if (mod.isUndefined()) { fprintf(stderr, "Registry::load(\"b200\") failed\n"); return 2; }
+  Svar orb = mod["gslam"]["b200"]["orb_extract"], match = mod["gslam"]["b200"]["match_hamming"];
+  std::ifstream f(in, std::ios::binary);
+  int32_t hdr[4];
+  rd(f, hdr, 4);
+  const int w = hdr[0], h = hdr[1], nfeat = hdr[2];
+  GImage a(h, w, GImageType<uchar, 1>::Type), b(h, w, GImageType<uchar, 1>::Type);
+  rd(f, a.data, (size_t)w * h); rd(f, b.data, (size_t)w * h);
+  Svar cfg = Svar::object();
+  cfg["nfeatures"] = nfeat;
+  Svar ra = orb(a, cfg), rb = orb(b, cfg);
+  if (ra.isUndefined() || rb.isUndefined()) return 1;
+  std::vector<KeyPoint> ka = ra["keypoints"].castAs<std::vector<KeyPoint> >(), kb = rb["keypoints"].castAs<std::vector<KeyPoint> >();
+  GImage da = ra["descriptors"].castAs<GImage>(), db = rb["descriptors"].castAs<GImage>();
+  Svar m = match(db, da);
+  if (m.isUndefined()) return 1;
+  std::vector<int> idx = m["trainIdx"].castAs<std::vector<int> >(), d1 = m["distance"].castAs<std::vector<int> >(), d2 = m["distance2"].castAs<std::vector<int> >();
+  std::ofstream o(out, std::ios::binary);
+  int32_t n[2] = {(int32_t)ka.size(), (int32_t)kb.size()};
+  wr(o, n, 2);
+  wr(o, ka.data(), ka.size()); wr(o, da.data, (size_t)da.rows * 32);
+  wr(o, kb.data(), kb.size()); wr(o, db.data, (size_t)db.rows * 32);
+  wr(o, idx.data(), idx.size()); wr(o, d1.data(), d1.size()); wr(o, d2.data(), d2.size());
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 5) { fprintf(stderr, "usage: %s ba|pnp|orb <plugin-dir> in.bin out.bin\n", argv[0]); return 64; }
+  const std::string mode = argv[1];
+  if (mode == "ba") return runBA(argv[2], argv[3], argv[4], false);
+  if (mode == "pnp") return runBA(argv[2], argv[3], argv[4], true);
+  if (mode == "orb") return runORB(argv[2], argv[3], argv[4]);
+  return 64;
+}

@@ -1,0 +1,167 @@
+// gslam_b200/plugin/optimizer_b200.cpp -> libgslam_optimizer.so
+//
+// The drop-in: a GSLAM::Optimizer (GSLAM/core/Optimizer.h:184-253) whose optimize()/optimizePnP() run on the B200 through
+// the C-ABI of include/gslam_b200.h.  Found by GSLAM::Optimizer::create() exactly like the (absent) Ceres plugin:
+// Registry::get("libgslam_optimizer") -> dlsym("createOptimizerInstance") (Optimizer.h:234-248, 42-51).
+// This TU is built with default symbol visibility: GSLAM_REGISTER_OPTIMIZER adds no visibility attribute.
+//
+// Contract kept from the reference: bool returns, never throws across the boundary, BundleGraph& / SE3& updated in place,
+// `_config` is honoured on every call (callers may edit it between calls, Optimizer.h:252).
+#include <GSLAM/core/GSLAM.h>
+#include <GSLAM/core/Optimizer.h>
+
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/gslam_b200.h"
+
+namespace {
+
+class OptimizerB200 : public GSLAM::Optimizer {
+ public:
+  OptimizerB200() : ctx_(nullptr) {}
+  ~OptimizerB200() override {
+    if (ctx_) gb_ctx_destroy(ctx_);
+  }
+
+  // MAPPING: bundle adjustment over BundleGraph::keyframes / mappoints / mappointObserves (Optimizer.h:150-172,229)
+  bool optimize(GSLAM::BundleGraph& graph) override {
+    try {
+      if (!graph.invDepths.empty() || !graph.invDepthObserves.empty() || !graph.se3Graph.empty() || !graph.sim3Graph.empty() ||
+          !graph.gpsGraph.empty()) {
+        LOG(ERROR) << "gslam_b200 optimizer: inverse-depth / pose-graph / GPS edges are not implemented (SURVEY.md §8f)";
+        return false;
+      }
+      if (graph.camera.isValid() && graph.cameraDOF != GSLAM::UPDATE_CAMERA_NONE) {
+        LOG(ERROR) << "gslam_b200 optimizer: camera self-calibration (cameraDOF) is not implemented";
+        return false;
+      }
+      if (_config.cameraProjectionType != GSLAM::PROJECTION_PINHOLE) {
+        LOG(ERROR) << "gslam_b200 optimizer: only PROJECTION_PINHOLE is implemented";
+        return false;
+      }
+      if (!ensureContext()) return false;
+      const size_t nc = graph.keyframes.size(), np = graph.mappoints.size(), no = graph.mappointObserves.size();
+      std::vector<double> pose(7 * nc), pts(3 * np), xyz(3 * no), info;
+      std::vector<uint8_t> dof(nc), pfree(np);
+      std::vector<int32_t> oc(no), op(no);
+      for (size_t i = 0; i < nc; ++i) {
+        // SIM3 memory = {SO3{x,y,z,w}, Point3d, scale}: the first 7 doubles are the SE3 T_wc (SE3.h:337-339, SIM3.h:290-291)
+        const GSLAM::SE3& T = graph.keyframes[i].estimation.get_se3();
+        const GSLAM::SO3& r = T.get_rotation();
+        const GSLAM::Point3d& t = T.get_translation();
+        double* p = &pose[7 * i];
+        p[0] = r.x; p[1] = r.y; p[2] = r.z; p[3] = r.w; p[4] = t.x; p[5] = t.y; p[6] = t.z;
+        dof[i] = (uint8_t)(graph.keyframes[i].dof & 63);
+      }
+      for (size_t j = 0; j < np; ++j) {
+        const GSLAM::Point3d& p = graph.mappoints[j].first;
+        pts[3 * j] = p.x; pts[3 * j + 1] = p.y; pts[3 * j + 2] = p.z;
+        pfree[j] = graph.mappoints[j].second ? 1 : 0;
+      }
+      bool any_info = false;
+      for (size_t k = 0; k < no; ++k) any_info |= graph.mappointObserves[k].information != NULL;
+      if (any_info) info.resize(4 * no);
+      for (size_t k = 0; k < no; ++k) {
+        const GSLAM::BundleEdge& e = graph.mappointObserves[k];
+        if (e.frameId >= nc || e.pointId >= np) {
+          LOG(ERROR) << "gslam_b200 optimizer: edge " << k << " references frame " << e.frameId << " / point " << e.pointId;
+          return false;
+        }
+        oc[k] = (int32_t)e.frameId; op[k] = (int32_t)e.pointId;
+        xyz[3 * k] = e.measurement.x; xyz[3 * k + 1] = e.measurement.y; xyz[3 * k + 2] = e.measurement.z;
+        if (any_info) {
+          double* L = &info[4 * k];
+          if (e.information) std::memcpy(L, e.information, 4 * sizeof(double));
+          else { L[0] = 1; L[1] = 0; L[2] = 0; L[3] = 1; }
+        }
+      }
+      gb_ba_problem pb;
+      std::memset(&pb, 0, sizeof pb);
+      pb.n_cams = (int32_t)nc; pb.n_points = (int32_t)np; pb.n_obs = (int32_t)no;
+      pb.cam_pose_wc = pose.data(); pb.cam_dof = dof.data(); pb.points = pts.data(); pb.point_free = pfree.data();
+      pb.obs_cam = oc.data(); pb.obs_point = op.data(); pb.obs_xyz = xyz.data(); pb.obs_info = any_info ? info.data() : NULL;
+      gb_ba_options opt = options();
+      gb_ba_result res;
+      const int rc = gb_ba_solve(ctx_, &pb, &opt, &res);
+      if (rc != GB_OK) {
+        LOG(ERROR) << "gslam_b200 optimizer: " << gb_last_error(ctx_);
+        return false;
+      }
+      for (size_t i = 0; i < nc; ++i) {
+        const double* p = &pose[7 * i];
+        GSLAM::SIM3& S = graph.keyframes[i].estimation;
+        S = GSLAM::SIM3(GSLAM::SE3(GSLAM::SO3(p[0], p[1], p[2], p[3]), GSLAM::Point3d(p[4], p[5], p[6])), S.get_scale());
+      }
+      for (size_t j = 0; j < np; ++j) graph.mappoints[j].first = GSLAM::Point3d(pts[3 * j], pts[3 * j + 1], pts[3 * j + 2]);
+      if (_config.verbose)
+        LOG(INFO) << "gslam_b200 optimizer: cost " << res.initial_cost << " -> " << res.final_cost << " in " << res.iterations
+                  << " iterations (" << res.gpu_ms << " ms on device)";
+      return true;
+    } catch (...) {
+      return false;  // nothing may escape a plugin (Optimizer.h:193-232 convention)
+    }
+  }
+
+  // TRACKING: pose from 3D-2D correspondences (Optimizer.h:202-207)
+  bool optimizePnP(const std::vector<std::pair<GSLAM::Point3d, GSLAM::CameraAnchor> >& matches, GSLAM::SE3& pose,
+                   GSLAM::KeyFrameEstimzationDOF dof = GSLAM::UPDATE_KF_SE3, double* information = NULL) override {
+    try {
+      if (!ensureContext()) return false;
+      const size_t n = matches.size();
+      std::vector<double> xyz(3 * n), xy1(3 * n);
+      for (size_t k = 0; k < n; ++k) {
+        xyz[3 * k] = matches[k].first.x; xyz[3 * k + 1] = matches[k].first.y; xyz[3 * k + 2] = matches[k].first.z;
+        xy1[3 * k] = matches[k].second.x; xy1[3 * k + 1] = matches[k].second.y; xy1[3 * k + 2] = matches[k].second.z;
+      }
+      const GSLAM::SO3& r = pose.get_rotation();
+      const GSLAM::Point3d& t = pose.get_translation();
+      double p[7] = {r.x, r.y, r.z, r.w, t.x, t.y, t.z};
+      gb_ba_options opt = options();
+      gb_ba_result res;
+      const int rc = gb_ba_pnp(ctx_, (int)n, xyz.data(), xy1.data(), p, (int)dof & 63, information, &opt, &res);
+      if (rc != GB_OK) {
+        LOG(ERROR) << "gslam_b200 optimizer: " << gb_last_error(ctx_);
+        return false;
+      }
+      pose = GSLAM::SE3(GSLAM::SO3(p[0], p[1], p[2], p[3]), GSLAM::Point3d(p[4], p[5], p[6]));
+      return true;
+    } catch (...) {
+      return false;
+    }
+  }
+
+ private:
+  bool ensureContext() {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (ctx_) return true;
+    const int device = svar.GetInt("b200.device", 0);
+    if (gb_ctx_create(device, &ctx_) != GB_OK) {
+      LOG(ERROR) << "gslam_b200 optimizer: no usable CUDA device (" << gb_last_error(NULL) << "); there is no CPU fallback";
+      ctx_ = nullptr;
+      return false;
+    }
+    return true;
+  }
+
+  gb_ba_options options() const {
+    gb_ba_options o;
+    gb_ba_options_default(&o);
+    o.huber_delta = _config.projectErrorHuberThreshold;  // OptimzeConfig, Optimizer.h:174-182
+    o.max_iterations = _config.maxIterations;
+    o.verbose = _config.verbose ? 1 : 0;
+    o.function_tolerance = svar.GetDouble("b200.ftol", o.function_tolerance);
+    o.lambda_init = svar.GetDouble("b200.lambda", o.lambda_init);
+    o.pcg_max_iters = svar.GetInt("b200.pcg_iters", o.pcg_max_iters);
+    o.pcg_tol = svar.GetDouble("b200.pcg_tol", o.pcg_tol);
+    return o;
+  }
+
+  gb_ctx* ctx_;
+  std::mutex mu_;
+};
+
+}  // namespace
+
+GSLAM_REGISTER_OPTIMIZER(OptimizerB200)

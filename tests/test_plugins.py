@@ -1,0 +1,139 @@
+"""The GSLAM-facing plugins, driven ONLY through the reference's public API by gslam_b200_host_test (a stand-in for a SLAM
+plugin): Optimizer::create() -> optimize / optimizePnP, Registry::load("b200") -> orb_extract / match_hamming.
+CPU part: discovery + symbol export + the no-device failure convention.  GPU part: plugin-level parity with the oracle."""
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import oracle
+from gslam_b200 import capi, synth
+
+LIB = os.path.join(os.path.dirname(capi.LIB_PATH))
+EXE = os.path.join(LIB, "gslam_b200_host_test")
+needs_plugins = pytest.mark.skipif(not all(os.path.exists(os.path.join(LIB, f)) for f in
+                                           ("gslam_b200_host_test", "libgslam_optimizer.so", "libgslam_b200.so")),
+                                   reason="plugins not built (they need the reference headers: built in the build container)")
+
+
+def write_ba(path, pb, iters, ftol):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<8i", pb.n_cams, pb.n_points, pb.n_obs, iters, 0 if pb.obs_info is None else 1, 0, 0, 0))
+        f.write(struct.pack("<d", ftol))
+        for a, dt in ((pb.cam_pose_wc, np.float64), (pb.cam_dof, np.uint8), (pb.points, np.float64), (pb.point_free, np.uint8),
+                      (pb.obs_cam, np.int32), (pb.obs_point, np.int32), (pb.obs_xyz, np.float64)):
+            f.write(np.ascontiguousarray(a, dt).tobytes())
+        if pb.obs_info is not None:
+            f.write(np.ascontiguousarray(pb.obs_info, np.float64).tobytes())
+
+
+def run(mode, inp, out):
+    return subprocess.run([EXE, mode, LIB, inp, out], capture_output=True, text=True, timeout=300)
+
+
+@needs_plugins
+def test_exports():
+    import ctypes
+    o = ctypes.CDLL(os.path.join(LIB, "libgslam_optimizer.so"))
+    assert hasattr(o, "createOptimizerInstance")       # Optimizer.h:43-45,241-247
+    m = ctypes.CDLL(os.path.join(LIB, "libgslam_b200.so"))
+    assert hasattr(m, "svarInstance")                  # Svar.h:71
+
+
+@needs_plugins
+def test_discovery_and_failure_convention_without_gpu():
+    """Optimizer::create() must find the plugin; without a device optimize() returns false (no throw, no CPU fallback)."""
+    import ctypes
+    n = ctypes.c_int(0)
+    if capi.lib().gb_device_count(ctypes.byref(n)) == 0 and n.value > 0:
+        pytest.skip("GPU present: covered by the gpu tests")
+    pb = synth.synth_ba(4, 12, obs_per_point=3, n_fixed=1, seed=1)
+    with tempfile.TemporaryDirectory() as d:
+        write_ba(os.path.join(d, "in.bin"), pb, 3, 0.0)
+        r = run("ba", os.path.join(d, "in.bin"), os.path.join(d, "out.bin"))
+        assert r.returncode == 1, (r.returncode, r.stderr)   # 2 would mean create() returned null
+        assert "no usable CUDA device" in (r.stderr + r.stdout)
+        ok = struct.unpack("<i", open(os.path.join(d, "out.bin"), "rb").read(4))[0]
+        assert ok == 0
+
+
+@needs_plugins
+@pytest.mark.gpu
+def test_optimize_through_reference_api_matches_oracle():
+    """BASELINE config 1 (10 cams / 200 pts) + a local-BA window through GSLAM::Optimizer::create()->optimize(BundleGraph&)."""
+    for kw, iters in ((dict(n_cams=10, n_points=200, all_visible=True, n_fixed=2, seed=42), 8), (dict(n_cams=50, n_points=2000, obs_per_point=5, n_fixed=2, seed=42), 6)):
+        pb = synth.synth_ba(**kw)
+        want = pb.copy()
+        oracle.ba_solve(want, max_iterations=iters, function_tolerance=0.0)
+        with tempfile.TemporaryDirectory() as d:
+            write_ba(os.path.join(d, "in.bin"), pb, iters, 0.0)
+            r = run("ba", os.path.join(d, "in.bin"), os.path.join(d, "out.bin"))
+            assert r.returncode == 0, r.stderr
+            raw = open(os.path.join(d, "out.bin"), "rb").read()
+        ok = struct.unpack("<i", raw[:4])[0]
+        assert ok == 1
+        poses = np.frombuffer(raw[4:4 + 64 * pb.n_cams], np.float64).reshape(-1, 8)
+        pts = np.frombuffer(raw[4 + 64 * pb.n_cams:], np.float64).reshape(-1, 3)
+        s = np.sign(np.sum(poses[:, :4] * want.cam_pose_wc[:, :4], axis=1))[:, None]
+        assert np.abs(poses[:, :4] * s - want.cam_pose_wc[:, :4]).max() < 1e-5
+        assert np.abs(poses[:, 4:7] - want.cam_pose_wc[:, 4:]).max() < 1e-5 * max(1.0, np.abs(want.cam_pose_wc[:, 4:]).max())
+        assert np.abs(pts - want.points).max() < 1e-5 * np.abs(want.points).max()
+        assert np.allclose(poses[:, 7], 1.0 + 0.01 * np.arange(pb.n_cams))   # SIM3 scale untouched (UPDATE_KF_SE3)
+
+
+@needs_plugins
+@pytest.mark.gpu
+def test_optimize_pnp_through_reference_api():
+    rng = np.random.default_rng(5)
+    q = rng.standard_normal(4); q /= np.linalg.norm(q)
+    pose = np.concatenate([q, 0.1 * rng.standard_normal(3)])
+    cw = np.zeros(7); oracle.lib().orc_se3_inverse(pose.ctypes.data, cw.ctypes.data)
+    Rm = synth._quat_to_R(cw[:4])
+    pc = np.stack([rng.uniform(-2, 2, 500), rng.uniform(-2, 2, 500), rng.uniform(4, 10, 500)], axis=1)
+    xyz = (pc - cw[4:]) @ Rm
+    xy1 = np.concatenate([pc[:, :2] / pc[:, 2:3] + 1e-3 * rng.standard_normal((500, 2)), np.ones((500, 1))], axis=1)
+    init = pose.copy(); init[4:] += 0.05; init[:4] += 0.01; init[:4] /= np.linalg.norm(init[:4])
+    p0, r0, i0 = oracle.ba_pnp(xyz, xy1, init, want_info=True, max_iterations=10, function_tolerance=0.0)
+    pb = synth.BAProblem(cam_pose_wc=init[None].copy(), cam_dof=np.array([63], np.uint8), points=xyz.copy(), point_free=np.zeros(500, np.uint8),
+                         obs_cam=np.zeros(500, np.int32), obs_point=np.arange(500, dtype=np.int32), obs_xyz=xy1)
+    with tempfile.TemporaryDirectory() as d:
+        write_ba(os.path.join(d, "in.bin"), pb, 10, 0.0)
+        r = run("pnp", os.path.join(d, "in.bin"), os.path.join(d, "out.bin"))
+        assert r.returncode == 0, r.stderr
+        raw = open(os.path.join(d, "out.bin"), "rb").read()
+    got = np.frombuffer(raw[4:4 + 56], np.float64); info = np.frombuffer(raw[60:60 + 288], np.float64).reshape(6, 6)
+    if got[3] * p0[3] < 0:
+        got = np.concatenate([-got[:4], got[4:]])
+    assert np.abs(got - p0).max() < 1e-5
+    assert np.abs(info - i0).max() < 1e-6 * np.abs(i0).max()
+
+
+@needs_plugins
+@pytest.mark.gpu
+def test_orb_and_match_through_svar_module():
+    frames = synth.synth_stream(640, 480, 2, seed=12)
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "in.bin"), "wb") as f:
+            f.write(struct.pack("<4i", 640, 480, 500, 0)); f.write(frames[0].tobytes()); f.write(frames[1].tobytes())
+        r = run("orb", os.path.join(d, "in.bin"), os.path.join(d, "out.bin"))
+        assert r.returncode == 0, r.stderr
+        raw = open(os.path.join(d, "out.bin"), "rb").read()
+    na, nb = struct.unpack("<2i", raw[:8]); off = 8
+    ka = np.frombuffer(raw[off:off + 28 * na], capi.KP_DTYPE); off += 28 * na
+    da = np.frombuffer(raw[off:off + 32 * na], np.uint8).reshape(-1, 32); off += 32 * na
+    kb = np.frombuffer(raw[off:off + 28 * nb], capi.KP_DTYPE); off += 28 * nb
+    db = np.frombuffer(raw[off:off + 32 * nb], np.uint8).reshape(-1, 32); off += 32 * nb
+    idx = np.frombuffer(raw[off:off + 4 * nb], np.int32); off += 4 * nb
+    d1 = np.frombuffer(raw[off:off + 4 * nb], np.int32); off += 4 * nb
+    d2 = np.frombuffer(raw[off:off + 4 * nb], np.int32)
+    wa, wda = oracle.orb_extract(frames[0], 500); wb, wdb = oracle.orb_extract(frames[1], 500)
+    for got, want in ((ka, wa), (kb, wb)):
+        assert len(got) == len(want)
+        for fld in ("x", "y", "size", "angle", "response", "octave", "class_id"):
+            assert np.array_equal(got[fld], want[fld]), fld
+    assert np.array_equal(da, wda) and np.array_equal(db, wdb)
+    w = oracle.match_hamming(wdb, wda)
+    assert np.array_equal(idx, w[0]) and np.array_equal(d1, w[1]) and np.array_equal(d2, w[2])

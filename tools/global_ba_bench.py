@@ -1,0 +1,43 @@
+"""Global BA (BASELINE config 5 shape: 500 cams x 100k landmarks x 1M obs) on N GPUs, landmark-sharded, one NCCL all-reduce of
+the reduced camera system per LM iteration.  Launch: torchrun --nproc-per-node N tools/global_ba_bench.py [--cams 500 ...]
+Prints one JSON line (rank 0): ms per LM iteration (device time, max over ranks), Jacobian-sweep GB/s, all-reduce bytes."""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+from gslam_b200 import synth
+from gslam_b200.api import Context, OptimzeConfig
+from gslam_b200.dist import DistributedBA
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--cams", type=int, default=500); ap.add_argument("--points", type=int, default=100000)
+ap.add_argument("--obs-per-point", type=int, default=10); ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--pcg", type=int, default=30); ap.add_argument("--reps", type=int, default=3)
+a = ap.parse_args()
+local = int(os.environ.get("LOCAL_RANK", 0)); torch.cuda.set_device(local)
+world = int(os.environ.get("WORLD_SIZE", 1))
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank = dist.get_rank() if world > 1 else 0
+ctx = Context(local)
+pb = synth.synth_ba(a.cams, a.points, a.obs_per_point, seed=42, n_fixed=2)
+cfg = OptimzeConfig(maxIterations=a.iters, functionTolerance=0.0, pcgMaxIterations=a.pcg)
+d = DistributedBA(ctx, pb, rank, world)
+best = None
+for rep in range(a.reps + 1):
+    d.graph.reset()
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    ctx.timer_begin()
+    res = d.solve(cfg)
+    ms = ctx.timer_end()
+    t = torch.tensor([ms], device="cuda")
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rep > 0: best = float(t.item()) if best is None else min(best, float(t.item()))
+if rank == 0:
+    n_obs = pb.n_obs
+    sweep_bytes = 168 * n_obs + 96 * pb.n_points + 272 * pb.n_cams
+    print(json.dumps({"workload": f"global BA {a.cams} cams / {a.points} pts / {n_obs} obs, {a.iters} LM it, PCG cap {a.pcg}", "n_gpus": world,
+                      "ms_total": best, "ms_per_lm_iteration": best / a.iters, "final_cost": res.final_cost, "initial_cost": res.initial_cost,
+                      "allreduce_bytes_per_iteration": d.reduce_bytes + 64, "sweep_algorithmic_bytes": sweep_bytes}))
+d.close()
+if world > 1: dist.destroy_process_group()
