@@ -246,6 +246,9 @@ def main():
     h2d = W * H + 2 * NKP * 32 + ba_problem.n_cams * 57 + ba_problem.n_points * 25 + ba_problem.n_obs * (8 + 24)
     d2h = NKP * 60 + NKP * 12 + ba_problem.n_cams * 56 + ba_problem.n_points * 24
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     fps = world * args.steps / (ms * 1e-3)
@@ -277,7 +280,7 @@ def main():
             line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": f"{n_cpu} frames: {what}"}
         except Exception as e:  # the GPU numbers stand on their own
             line["cpu_baseline"] = {"value": None, "error": repr(e)}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
