@@ -248,6 +248,10 @@ class BAGraph:
         self.ctx._check(self.ctx._lib.gb_ba_graph_solve(self.ctx._h, self._h, C.byref(o), C.byref(r)))
         return r
 
+    def sweep(self, delta: float = 0.01):
+        """One fused residual+Jacobian sweep (K6) at the current estimate, enqueued on the ctx stream."""
+        self.ctx._check(self.ctx._lib.gb_ba_graph_sweep(self.ctx._h, self._h, delta))
+
     def download(self):
         pose = np.zeros((self.n_cams, 7)); pts = np.zeros((self.n_points, 3))
         self.ctx._check(self.ctx._lib.gb_ba_graph_download(self.ctx._h, self._h, ptr(pose), ptr(pts)))
@@ -285,8 +289,12 @@ class BAGraph:
                                                           ptr(W), ptr(cost)))
         return dict(U=U, gc=gc, V=V, gp=gp, W=W, cost=float(cost[0]))
 
-    def force_generic_pcg(self, on: bool = True):
-        self.ctx._check(self.ctx._lib.gb_dbg_ba_force_generic_pcg(self.ctx._h, self._h, int(on)))
+    def force_generic_pcg(self, mode=1):
+        """PCG dispatch override (test hook): 0 auto, 1 generic multi-kernel, 2 one-cluster DSMEM, 3 single-CTA block-sparse."""
+        self.ctx._check(self.ctx._lib.gb_dbg_ba_force_generic_pcg(self.ctx._h, self._h, int(mode)))
+
+    def pcg_sparse_blocks(self) -> int:
+        return int(self.ctx._lib.gb_dbg_ba_pcg_sparse(self.ctx._h, self._h))
 
     def pcg_cluster_size(self) -> int:
         return int(self.ctx._lib.gb_dbg_ba_pcg_cluster_size(self.ctx._h, self._h))

@@ -82,6 +82,7 @@ _SIGNATURES = [
     ("gb_ba_graph_reset", C.c_int, [_VP, _VP]),
     ("gb_ba_graph_solve", C.c_int, [_VP, _VP, C.POINTER(BaOptions), C.POINTER(BaResult)]),
     ("gb_ba_graph_download", C.c_int, [_VP, _VP, _VP, _VP]),
+    ("gb_ba_graph_sweep", C.c_int, [_VP, _VP, C.c_double]),
     ("gb_ba_graph_reduce_size", C.c_int, [_VP, _VP, C.POINTER(C.c_size_t)]),
     ("gb_ba_graph_begin", C.c_int, [_VP, _VP, C.POINTER(BaOptions)]),
     ("gb_ba_graph_reduce_local", C.c_int, [_VP, _VP, _VP]),
@@ -95,6 +96,7 @@ _DEBUG_SIGNATURES = [
     ("gb_dbg_ba_reduced", C.c_int, [_VP, _VP, C.POINTER(BaOptions), _VP, _VP, _VP, C.POINTER(C.c_int)]),
     ("gb_dbg_ba_force_generic_pcg", C.c_int, [_VP, _VP, C.c_int]),
     ("gb_dbg_ba_pcg_cluster_size", C.c_int, [_VP, _VP]),
+    ("gb_dbg_ba_pcg_sparse", C.c_int, [_VP, _VP]),
 ]
 
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]

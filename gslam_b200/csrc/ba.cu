@@ -52,20 +52,23 @@ __global__ void ba_rt_kernel(int nc, const double* __restrict__ pose, double* __
   for (int k = 0; k < 3; ++k) Rt[12 * i + 9 + k] = pose[7 * i + 4 + k];
 }
 
-// K6a: one thread per landmark
+// K6a: fused residual + Jacobian sweep, 8 lanes per landmark (lane k takes observations k, k+8, ... of the point-sorted
+// segment), fixed xor-tree over the 8 lanes -> V_j, g_p,j, cost_j; every lane writes the W blocks of its own observations.
+constexpr int kLpp = 8;
 __global__ void __launch_bounds__(kPtThreads) ba_linearize_points_kernel(BaDev g) {
   if (g.sc->stop || !g.sc->need_linearize) return;
-  const int j = blockIdx.x * kPtThreads + threadIdx.x;
-  if (j >= g.np) return;
+  const int gt = blockIdx.x * kPtThreads + threadIdx.x;
+  const int jraw = gt / kLpp, sub = gt % kLpp;
+  const bool valid = jraw < g.np;
+  const int j = valid ? jraw : 0;
   const double delta = g.sc->delta;
-  const double p[3] = {g.pts[3 * j], g.pts[3 * j + 1], g.pts[3 * j + 2]};
+  const double p[3] = {g.pts[3 * (size_t)j], g.pts[3 * (size_t)j + 1], g.pts[3 * (size_t)j + 2]};
   const bool pf = g.pfree[j] != 0;
-  double V[9], gp[3], cost = 0.0;
+  double acc[10];  // V upper triangle (6), g_p (3), cost (1)
 #pragma unroll
-  for (int k = 0; k < 9; ++k) V[k] = 0.0;
-  gp[0] = gp[1] = gp[2] = 0.0;
-  const int e0 = g.pt_off[j], e1 = g.pt_off[j + 1];
-  for (int e = e0; e < e1; ++e) {
+  for (int k = 0; k < 10; ++k) acc[k] = 0.0;
+  const int e0 = g.pt_off[j], e1 = valid ? g.pt_off[j + 1] : e0;
+  for (int e = e0 + sub; e < e1; e += kLpp) {
     const int i = g.o_cam[e];
     const double* Rt = g.Rt + 12 * i;
     const ObsLin o = eval_obs(Rt, p, g.o_uv[2 * e], g.o_uv[2 * e + 1], g.has_info ? g.o_info + 3 * e : nullptr, delta);
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(kPtThreads) ba_linearize_points_kernel(BaDev g
       for (int k = 0; k < 18; ++k) W[k] = 0.0;
       continue;
     }
-    cost += o.rho;
+    acc[9] += o.rho;
     double Jc[12], Jp[6], AJp[6];
     jac_cam(o, g.dof[i], Jc);
     jac_pt(o, Rt, pf, Jp);
@@ -88,25 +91,33 @@ __global__ void __launch_bounds__(kPtThreads) ba_linearize_points_kernel(BaDev g
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
-      for (int b = 0; b < 3; ++b) W[a * 3 + b] = Jc[a] * AJp[b] + Jc[6 + a] * AJp[3 + b];
+      for (int c = 0; c < 3; ++c) W[a * 3 + c] = Jc[a] * AJp[c] + Jc[6 + a] * AJp[3 + c];
+    int t = 0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
 #pragma unroll
-      for (int b = 0; b < 3; ++b) V[a * 3 + b] += Jp[a] * AJp[b] + Jp[3 + a] * AJp[3 + b];
-      gp[a] -= Jp[a] * Ar0 + Jp[3 + a] * Ar1;
+      for (int c = a; c < 3; ++c) acc[t++] += Jp[a] * AJp[c] + Jp[3 + a] * AJp[3 + c];
+      acc[6 + a] -= Jp[a] * Ar0 + Jp[3 + a] * Ar1;
     }
   }
 #pragma unroll
-  for (int k = 0; k < 9; ++k) g.V[9 * (size_t)j + k] = V[k];
+  for (int k = 0; k < 10; ++k) {
 #pragma unroll
-  for (int k = 0; k < 3; ++k) g.gp[3 * (size_t)j + k] = gp[k];
-  g.cost_pt[j] = cost;
+    for (int o = kLpp / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o, kLpp);
+  }
+  if (valid && sub == 0) {
+    double* V = g.V + 9 * (size_t)j;
+    V[0] = acc[0]; V[1] = acc[1]; V[2] = acc[2];
+    V[3] = acc[1]; V[4] = acc[3]; V[5] = acc[4];
+    V[6] = acc[2]; V[7] = acc[4]; V[8] = acc[5];
+    g.gp[3 * (size_t)j] = acc[6]; g.gp[3 * (size_t)j + 1] = acc[7]; g.gp[3 * (size_t)j + 2] = acc[8];
+    g.cost_pt[j] = acc[9];
+  }
 }
 
 // K6b: one CTA per camera; deterministic tree reduction of the 21 upper-triangular U entries + 6 gradient entries
 __global__ void __launch_bounds__(kCamThreads) ba_linearize_cams_kernel(BaDev g) {
   if (g.sc->stop || !g.sc->need_linearize) return;
-  __shared__ double s_part[kCamThreads / 32 + 1];
   const int i = blockIdx.x;
   const double delta = g.sc->delta;
   const double* Rt = g.Rt + 12 * i;
@@ -137,19 +148,31 @@ __global__ void __launch_bounds__(kCamThreads) ba_linearize_cams_kernel(BaDev g)
 #pragma unroll
     for (int a = 0; a < 6; ++a) acc[21 + a] -= Jc[a] * Ar0 + Jc[6 + a] * Ar1;
   }
-  double red[27];
+  // deterministic reduction: fixed shuffle tree inside each warp, then the 4 warp partials are summed in order
+  __shared__ double s_red[kCamThreads / 32][27];
 #pragma unroll
-  for (int k = 0; k < 27; ++k) red[k] = block_sum<kCamThreads>(acc[k], s_part);
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int a = 0; a < 6; ++a)
-      for (int b = a; b < 6; ++b) {
-        g.U[36 * i + a * 6 + b] = red[t];
-        g.U[36 * i + b * 6 + a] = red[t];
-        ++t;
-      }
-    for (int a = 0; a < 6; ++a) g.gc[6 * i + a] = red[21 + a];
+  for (int k = 0; k < 27; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
   }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 27; ++k) s_red[threadIdx.x >> 5][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < kCamThreads / 32; ++w) r += s_red[w][threadIdx.x];
+    s_red[0][threadIdx.x] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x < 36) {
+    const int a = threadIdx.x / 6, c = threadIdx.x % 6, lo = a < c ? a : c, hi = a < c ? c : a;
+    const int t = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);  // index of (lo,hi) in the packed upper triangle
+    g.U[36 * i + threadIdx.x] = s_red[0][t];
+  }
+  if (threadIdx.x < 6) g.gc[6 * i + threadIdx.x] = s_red[0][21 + threadIdx.x];
 }
 
 // out[0] = 0.5 * sum(src[0..n)) — single CTA, deterministic
@@ -188,6 +211,7 @@ __global__ void ba_schur_accum_kernel(BaDev g, double* __restrict__ buf) {
   const int f0 = g.pt_off[j], f1 = g.pt_off[j + 1];
   for (int f = f0; f < f1; ++f) {
     const int i2 = g.o_cam[f];
+    if (i2 < i) continue;  // S is symmetric: accumulate the upper block triangle only, ba_mirror_kernel fills the rest
     const double* W2 = g.W + 18 * (size_t)f;
     double w2[18];
 #pragma unroll
@@ -198,6 +222,121 @@ __global__ void ba_schur_accum_kernel(BaDev g, double* __restrict__ buf) {
 #pragma unroll
       for (int b = 0; b < 6; ++b)
         atomicAdd(&Sb[(size_t)a * n6 + b], -(Y[a * 3] * w2[b * 3] + Y[a * 3 + 1] * w2[b * 3 + 1] + Y[a * 3 + 2] * w2[b * 3 + 2]));
+  }
+}
+
+// K7a (local BA): deterministic Schur complement, one warp per structurally non-zero UPPER block (i,i'), no atomics.
+// The warp walks camera i's observation list (lanes stride it), looks up whether camera i' sees the same landmark, and
+// accumulates Y W' (Y = W V^-1) in registers; a fixed shuffle tree reduces the 36 entries; the block and its transpose are
+// written once.  The diagonal warps also produce g~_i = g_c,i - sum_j Y g_p,j and diag U.  Bit-reproducible run to run.
+__global__ void __launch_bounds__(128) ba_schur_blocks_kernel(BaDev g, double* __restrict__ buf) {
+  if (g.sc->stop) return;
+  // one CTA (4 warps) per upper block: the warps split camera i's observation list, a fixed shuffle tree reduces inside each
+  // warp and warp 0 adds the four partials in order
+  __shared__ double s_part[4][42];
+  const int wid = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blk = g.s_upper[wid];
+  const int i = g.s_brow[blk], i2 = g.s_col[blk];
+  const bool diag = i == i2;
+  double acc[36], ga[6];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) ga[k] = 0.0;
+  for (int idx = g.cam_off[i] + threadIdx.x; idx < g.cam_off[i + 1]; idx += 128) {
+    const int e = g.cam_perm[idx];
+    const int j = g.o_pt[e];
+    if (!g.pfree[j]) continue;
+    int f = -1;
+    if (diag) f = e;
+    else {
+      const int f0 = g.pt_off[j], f1 = g.pt_off[j + 1];
+      int cam8[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) cam8[t] = (f0 + t < f1) ? g.o_cam[f0 + t] : -1;  // independent loads
+#pragma unroll
+      for (int t = 7; t >= 0; --t) if (cam8[t] == i2) f = f0 + t;
+      for (int t = f0 + 8; t < f1 && f < 0; ++t)
+        if (g.o_cam[t] == i2) f = t;
+    }
+    if (f < 0) continue;
+    double Vi[9], Y[18];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Vi[k] = g.Vinv[9 * (size_t)j + k];
+    const double* We = g.W + 18 * (size_t)e;
+    const double* Wf = g.W + 18 * (size_t)f;
+    double wf[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) wf[k] = Wf[k];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const double w0 = We[a * 3], w1 = We[a * 3 + 1], w2 = We[a * 3 + 2];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Y[a * 3 + c] = w0 * Vi[c] + w1 * Vi[3 + c] + w2 * Vi[6 + c];
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b < 6; ++b) acc[a * 6 + b] += Y[a * 3] * wf[b * 3] + Y[a * 3 + 1] * wf[b * 3 + 1] + Y[a * 3 + 2] * wf[b * 3 + 2];
+    if (diag) {
+      const double g0 = g.gp[3 * (size_t)j], g1 = g.gp[3 * (size_t)j + 1], g2 = g.gp[3 * (size_t)j + 2];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) ga[a] += Y[a * 3] * g0 + Y[a * 3 + 1] * g1 + Y[a * 3 + 2] * g2;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 36; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ga[k] += __shfl_down_sync(0xffffffffu, ga[k], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 36; ++k) s_part[warp][k] = acc[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s_part[warp][36 + k] = ga[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 42) {
+    const int k = threadIdx.x;
+    const double sum = ((s_part[0][k] + s_part[1][k]) + s_part[2][k]) + s_part[3][k];
+    if (k < 36) {
+      const int a = k / 6, b = k - 6 * a;
+      const double v = (diag ? g.U[36 * i + k] : 0.0) - sum;
+      g.Sb[36 * (size_t)blk + k] = v;
+      if (!diag) g.Sb[36 * (size_t)g.s_tidx[blk] + b * 6 + a] = v;
+    } else if (diag) {
+      const int a = k - 36;
+      const size_t n6 = g.n6, nS = n6 * n6;
+      buf[nS + 6 * i + a] = g.gc[6 * i + a] - sum;
+      buf[nS + n6 + 6 * i + a] = g.U[36 * i + a * 7];
+    }
+  }
+}
+
+// test hook helper: scatter the block-CSR values into the dense S of `buf`
+__global__ void ba_densify_kernel(BaDev g, double* __restrict__ buf) {
+  const size_t n6 = g.n6, nS = n6 * n6;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nS; idx += (size_t)gridDim.x * blockDim.x) buf[idx] = 0.0;
+}
+__global__ void ba_densify_fill_kernel(BaDev g, double* __restrict__ buf) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= g.s_nnzb * 36) return;
+  const int blk = w / 36, k = w - 36 * blk, a = k / 6, b = k - 6 * a;
+  buf[(size_t)(6 * g.s_brow[blk] + a) * g.n6 + 6 * g.s_col[blk] + b] = g.Sb[w];
+}
+
+// lower block triangle <- transpose of the upper one (S_{i',i} = S_{i,i'}^T)
+__global__ void ba_mirror_kernel(BaDev g, double* __restrict__ buf) {
+  if (g.sc->stop) return;
+  const size_t n6 = g.n6, nS = n6 * n6;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nS; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = idx / n6, col = idx - row * n6;
+    if (col / 6 < row / 6) buf[idx] = buf[col * n6 + row];
   }
 }
 
@@ -216,7 +355,6 @@ __global__ void ba_damp_kernel(BaDev g, double* __restrict__ buf) {
 // ---- PCG ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRedThreads) pcg_init_kernel(BaDev g, const double* __restrict__ buf) {
   if (g.sc->stop) return;
-  __shared__ double s_part[kRedThreads / 32 + 1];
   const size_t n6 = g.n6;
   const double* S = buf;
   const double* gt = buf + n6 * n6;
@@ -235,77 +373,105 @@ __global__ void __launch_bounds__(kRedThreads) pcg_init_kernel(BaDev g, const do
 #pragma unroll
     for (int k = 0; k < 36; ++k) g.Minv[36 * (size_t)i + k] = M[k];
   }
+  // Chronopoulos-Gear PCG (same recurrence as oracle/ba_ref.c::ba_pcg): u = Minv r is kept in g.z, w = S u in g.q, s = S p in g.sv
   for (int d = threadIdx.x; d < g.n6; d += kRedThreads) {
     g.x[d] = 0.0;
     g.r[d] = gt[d];
+    g.p[d] = 0.0;
+    g.sv[d] = 0.0;
   }
   __syncthreads();
-  double part = 0.0;
   for (int d = threadIdx.x; d < g.n6; d += kRedThreads) {
     const int i = d / 6, a = d % 6;
     double s = 0.0;
 #pragma unroll
     for (int b = 0; b < 6; ++b) s += g.Minv[36 * (size_t)i + a * 6 + b] * gt[6 * i + b];
     g.z[d] = s;
-    g.p[d] = s;
-    part += gt[d] * s;
   }
-  const double rz = block_sum<kRedThreads>(part, s_part);
   if (threadIdx.x == 0) {
-    g.sc->rz = rz;
-    g.sc->rz0 = rz;
-    g.sc->pcg_done = !(rz > 0.0);
+    g.sc->pcg_first = 1;
+    g.sc->pcg_k = 0;
+    g.sc->pcg_done = 0;
   }
 }
 
-// q = S p : one warp per row, coalesced row reads, fixed shuffle tree
+// w = S u : one warp per row, coalesced row reads, fixed shuffle tree
 __global__ void __launch_bounds__(256) pcg_matvec_kernel(BaDev g, const double* __restrict__ buf) {
   if (g.sc->stop || g.sc->pcg_done) return;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= g.n6) return;
   const double* Srow = buf + (size_t)row * g.n6;
   double s = 0.0;
-  for (int c = lane; c < g.n6; c += 32) s += Srow[c] * g.p[c];
+  for (int c = lane; c < g.n6; c += 32) s += Srow[c] * g.z[c];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
   if (lane == 0) g.q[row] = s;
 }
 
-__global__ void __launch_bounds__(kRedThreads) pcg_update_kernel(BaDev g) {
+__global__ void __launch_bounds__(kRedThreads) pcg_update_kernel(BaDev g, int maxit) {
   if (g.sc->stop || g.sc->pcg_done) return;
   __shared__ double s_part[kRedThreads / 32 + 1];
-  const double rz = g.sc->rz, rz0 = g.sc->rz0, tol = g.sc->pcg_tol;
-  double part = 0.0;
-  for (int d = threadIdx.x; d < g.n6; d += kRedThreads) part += g.p[d] * g.q[d];
-  const double pq = block_sum<kRedThreads>(part, s_part);
-  if (!(pq > 0.0)) {
-    if (threadIdx.x == 0) g.sc->pcg_done = 1;
+  BaScalars* sc = g.sc;
+  const double gamma_prev = sc->rz, gamma0_prev = sc->rz0, alpha_prev = sc->pcg_alpha, tol = sc->pcg_tol;
+  const int first = sc->pcg_first, k = sc->pcg_k;
+  double pa = 0.0, pb = 0.0;
+  for (int d = threadIdx.x; d < g.n6; d += kRedThreads) {
+    pa += g.r[d] * g.z[d];
+    pb += g.q[d] * g.z[d];
+  }
+  const double gn = block_sum<kRedThreads>(pa, s_part);
+  const double dl = block_sum<kRedThreads>(pb, s_part);
+  double alpha, beta, gamma0 = gamma0_prev;
+  if (first) {
+    gamma0 = gn;
+    if (!(gn > 0.0) || !(dl > 0.0)) {
+      if (threadIdx.x == 0) sc->pcg_done = 1;
+      return;
+    }
+    alpha = gn / dl;
+    beta = 0.0;
+  } else {
+    if (!(gn > 0.0) || gn < tol * tol * gamma0) {  // convergence test of the previous update
+      if (threadIdx.x == 0) sc->pcg_done = 1;
+      return;
+    }
+    beta = gn / gamma_prev;
+    const double den = dl - beta * gn / alpha_prev;
+    if (!(den > 0.0)) {
+      if (threadIdx.x == 0) sc->pcg_done = 1;
+      return;
+    }
+    alpha = gn / den;
+  }
+  if (k >= maxit) {
+    if (threadIdx.x == 0) sc->pcg_done = 1;
     return;
   }
-  const double alpha = rz / pq;
   for (int d = threadIdx.x; d < g.n6; d += kRedThreads) {
-    g.x[d] += alpha * g.p[d];
-    g.r[d] -= alpha * g.q[d];
+    const double pd = g.z[d] + beta * g.p[d];
+    const double sd = g.q[d] + beta * g.sv[d];
+    g.p[d] = pd;
+    g.sv[d] = sd;
+    g.x[d] += alpha * pd;
+    g.r[d] -= alpha * sd;
   }
   __syncthreads();
-  part = 0.0;
   for (int d = threadIdx.x; d < g.n6; d += kRedThreads) {
     const int i = d / 6, a = d % 6;
     double s = 0.0;
 #pragma unroll
     for (int b = 0; b < 6; ++b) s += g.Minv[36 * (size_t)i + a * 6 + b] * g.r[6 * i + b];
     g.z[d] = s;
-    part += g.r[d] * s;
   }
-  const double rzn = block_sum<kRedThreads>(part, s_part);
-  if (threadIdx.x == 0) g.sc->pcg_iters++;
-  if (!(rzn > 0.0) || rzn < tol * tol * rz0) {
-    if (threadIdx.x == 0) g.sc->pcg_done = 1;
-    return;
+  if (threadIdx.x == 0) {
+    sc->rz = gn;
+    sc->rz0 = gamma0;
+    sc->pcg_alpha = alpha;
+    sc->pcg_beta = beta;
+    sc->pcg_first = 0;
+    sc->pcg_k = k + 1;
+    sc->pcg_iters++;
   }
-  const double beta = rzn / rz;
-  for (int d = threadIdx.x; d < g.n6; d += kRedThreads) g.p[d] = g.z[d] + beta * g.p[d];
-  if (threadIdx.x == 0) g.sc->rz = rzn;
 }
 
 __global__ void ba_retract_kernel(BaDev g) {
@@ -382,17 +548,18 @@ __global__ void ba_finalize_kernel(int nc, const double* __restrict__ pose_cw, d
 
 // ---- fused helpers of the short-launch-chain path -------------------------------------------------------------------------
 // buf <- [S = blockdiag(U) | gt = gc | diagU | cost]; Vinv for every landmark.  Single writer per entry (no memset needed).
-__global__ void __launch_bounds__(256) ba_prepare_schur_kernel(BaDev g, double* __restrict__ buf) {
+__global__ void __launch_bounds__(256) ba_prepare_schur_kernel(BaDev g, double* __restrict__ buf, int dense) {
   if (g.sc->stop) return;
   __shared__ double s_part[256 / 32 + 1];
   const size_t n6 = g.n6, nS = n6 * n6;
   const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (size_t idx = t0; idx < nS; idx += stride) {
+  // (the block-gather path writes S, g~ and diag U itself: ba_schur_blocks_kernel)
+  for (size_t idx = t0; dense && idx < nS; idx += stride) {
     const int row = (int)(idx / n6), col = (int)(idx % n6);
     const int i = row / 6, i2 = col / 6;
     buf[idx] = (i == i2) ? g.U[36 * i + (row % 6) * 6 + (col % 6)] : 0.0;
   }
-  for (size_t d = t0; d < n6; d += stride) {
+  for (size_t d = t0; dense && d < n6; d += stride) {
     buf[nS + d] = g.gc[d];
     buf[nS + n6 + d] = g.U[36 * (d / 6) + (d % 6) * 7];
   }
@@ -421,15 +588,17 @@ __global__ void __launch_bounds__(256) ba_prepare_schur_kernel(BaDev g, double* 
   }
 }
 
-// back-substitution of landmark j followed by its robustified cost at the candidate estimate
-__global__ void ba_backsub_cost_kernel(BaDev g) {
+// back-substitution of landmark j followed by its robustified cost at the candidate estimate; 8 lanes per landmark
+__global__ void __launch_bounds__(128) ba_backsub_cost_kernel(BaDev g) {
   if (g.sc->stop) return;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= g.np) return;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jraw = gt / kLpp, sub = gt % kLpp;
+  const bool valid = jraw < g.np;
+  const int j = valid ? jraw : 0;
   const double delta = g.sc->delta;
-  double b[3] = {g.gp[3 * (size_t)j], g.gp[3 * (size_t)j + 1], g.gp[3 * (size_t)j + 2]};
-  const int e0 = g.pt_off[j], e1 = g.pt_off[j + 1];
-  for (int e = e0; e < e1; ++e) {
+  const int e0 = g.pt_off[j], e1 = valid ? g.pt_off[j + 1] : e0;
+  double b[3] = {0.0, 0.0, 0.0};
+  for (int e = e0 + sub; e < e1; e += kLpp) {
     const int i = g.o_cam[e];
     const double* W = g.W + 18 * (size_t)e;
 #pragma unroll
@@ -437,19 +606,28 @@ __global__ void ba_backsub_cost_kernel(BaDev g) {
 #pragma unroll
       for (int a = 0; a < 6; ++a) b[c] -= W[a * 3 + c] * g.x[6 * i + a];
   }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int o = kLpp / 2; o > 0; o >>= 1) b[c] += __shfl_xor_sync(0xffffffffu, b[c], o, kLpp);
+    b[c] += g.gp[3 * (size_t)j + c];
+  }
   const double* Vi = g.Vinv + 9 * (size_t)j;
   double p[3];
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    p[a] = g.pts[3 * (size_t)j + a] + Vi[a * 3] * b[0] + Vi[a * 3 + 1] * b[1] + Vi[a * 3 + 2] * b[2];
-    g.pts_new[3 * (size_t)j + a] = p[a];
-  }
+  for (int a = 0; a < 3; ++a) p[a] = g.pts[3 * (size_t)j + a] + Vi[a * 3] * b[0] + Vi[a * 3 + 1] * b[1] + Vi[a * 3 + 2] * b[2];
   double cost = 0.0;
-  for (int e = e0; e < e1; ++e) {
+  for (int e = e0 + sub; e < e1; e += kLpp) {
     const ObsLin o = eval_obs(g.Rt_new + 12 * g.o_cam[e], p, g.o_uv[2 * e], g.o_uv[2 * e + 1], g.has_info ? g.o_info + 3 * e : nullptr, delta);
     cost += o.rho;
   }
-  g.cost_pt_new[j] = cost;
+#pragma unroll
+  for (int o = kLpp / 2; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o, kLpp);
+  if (valid && sub == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) g.pts_new[3 * (size_t)j + a] = p[a];
+    g.cost_pt_new[j] = cost;
+  }
 }
 
 // single CTA: reduce the candidate cost, LM accept/reject, apply.  (small problems; the stepwise path keeps them apart)
@@ -491,6 +669,210 @@ __global__ void __launch_bounds__(kRedThreads) ba_commit_fused_kernel(BaDev g, c
   for (int t = threadIdx.x; t < g.nc * 12; t += kRedThreads) g.Rt[t] = g.Rt_new[t];
   for (int t = threadIdx.x; t < g.np * 3; t += kRedThreads) g.pts[t] = g.pts_new[t];
 }
+
+// ---- K7b (local BA, sparse covisibility): block-Jacobi PCG in ONE CTA -------------------------------------------------------
+// When the structurally non-zero 6x6 blocks of the reduced camera matrix fit one SM (sequential-SLAM windows: a band of
+// co-visible keyframes) the whole solve needs no inter-CTA exchange.  Thread d owns row d of S and element d of every CG
+// vector.  One SM's shared-memory port (128 B/clk) would bound a mat-vec that re-reads the blocks every iteration
+// (130 KB -> >1000 clk), so each thread keeps the first kMaxB blocks of ITS row in registers for the whole solve (the shared
+// copy serves rows with more blocks); per iteration only p is read from shared memory (broadcast across the 6 rows of a
+// camera).  An iteration = register mat-vec, two single-barrier deterministic reductions, fused r/z/p updates.
+template <int THREADS, int MAXB>
+__global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, double* __restrict__ buf, int maxit) {
+  if (g.sc->stop) return;
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double s_red[2][2 * (THREADS / 32)];
+  const int n6 = g.n6, nc = g.nc, nnzb = g.s_nnzb, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long t_start = clock64();
+  double* B = sm;                          // [nnzb][36] row-major blocks
+  double* Minv = B + (size_t)nnzb * 36;    // [nc][36]
+  double* vp = Minv + (size_t)nc * 36;     // six vectors of n6: u, w, s[2], r[2]
+  double* vq = vp + n6;
+  double* vr = vq + n6;
+  double* vz = vr + n6;
+  int* rowptr = reinterpret_cast<int*>(vz + 3 * (size_t)n6);  // [nc+1]
+  int* col = rowptr + nc + 1;                     // [nnzb]
+  const size_t nS = (size_t)n6 * n6;
+  const double lambda = g.sc->lambda, tol = g.sc->pcg_tol;
+  for (int k = tid; k <= nc; k += THREADS) rowptr[k] = g.s_rowptr[k];
+  for (int k = tid; k < nnzb; k += THREADS) col[k] = g.s_col[k];
+  // A. copy the block-CSR values of S (written by ba_schur_blocks_kernel) into shared memory; Marquardt damping on the
+  //    diagonal entries (written back so the damped system is observable)
+  for (int w = tid; w < nnzb * 36; w += THREADS) {
+    const int blk = w / 36, k = w - 36 * blk, a = k / 6, b = k - 6 * a;
+    double v = g.Sb[w];
+    if (a == b) {
+      const int i = g.s_brow[blk];
+      if (i == g.s_col[blk]) {
+        v = ((g.dof[i] >> a) & 1) ? v + lambda * clampd(buf[nS + n6 + 6 * i + a]) : 1.0;
+        g.Sb[w] = v;
+      }
+    }
+    B[w] = v;
+  }
+  __syncthreads();
+  // B. block-Jacobi preconditioner
+  for (int i = tid; i < nc; i += THREADS) {
+    int dblk = rowptr[i];
+    while (col[dblk] != i) ++dblk;  // the diagonal block is always present
+    double M[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) M[k] = B[(size_t)dblk * 36 + k];
+    if (!spd_inverse<6>(M)) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b < 6; ++b) M[a * 6 + b] = (a == b) ? 1.0 / B[(size_t)dblk * 36 + a * 7] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 36; ++k) Minv[36 * i + k] = M[k];
+  }
+  __syncthreads();  // Minv complete
+  const bool own = tid < n6;
+  const int ci = own ? tid / 6 : 0, ca = own ? tid - 6 * ci : 0;
+  const int b0 = own ? rowptr[ci] : 0, b1 = own ? rowptr[ci + 1] : 0;
+  // this thread's row of S: first MAXB blocks in registers (empty slots: zero block pointing at the camera's own segment)
+  double breg[MAXB * 6];
+  int creg[MAXB];
+#pragma unroll
+  for (int s = 0; s < MAXB; ++s) {
+    const bool ok = b0 + s < b1;
+    creg[s] = ok ? col[b0 + s] : ci;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) breg[s * 6 + k] = ok ? B[(size_t)(b0 + s) * 36 + ca * 6 + k] : 0.0;
+  }
+  // shared vectors: u (mat-vec input), w = S u, s = S p (double-buffered), r (double-buffered)
+  double* vu = vp;
+  double* vw = vq;
+  double* vs[2] = {vr, vz};
+  double* vrr[2] = {vz + n6, vz + 2 * (size_t)n6};
+  // w_d = row d of S times u (registers for the first MAXB blocks, shared-memory copy beyond)
+  auto matvec = [&]() -> double {
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+    double2 pv[MAXB][3];
+#pragma unroll
+    for (int s = 0; s < MAXB; ++s) {
+      const double2* pc = reinterpret_cast<const double2*>(vu + 6 * creg[s]);
+      pv[s][0] = pc[0]; pv[s][1] = pc[1]; pv[s][2] = pc[2];
+    }
+#pragma unroll
+    for (int s = 0; s < MAXB; ++s) {
+      q0 += breg[s * 6 + 0] * pv[s][0].x; q1 += breg[s * 6 + 1] * pv[s][0].y;
+      q2 += breg[s * 6 + 2] * pv[s][1].x; q0 += breg[s * 6 + 3] * pv[s][1].y;
+      q1 += breg[s * 6 + 4] * pv[s][2].x; q2 += breg[s * 6 + 5] * pv[s][2].y;
+    }
+    for (int blk = b0 + MAXB; blk < b1; ++blk) {
+      const double* Brow = B + (size_t)blk * 36 + ca * 6;
+      const double* pc = vu + 6 * col[blk];
+      q0 += Brow[0] * pc[0]; q1 += Brow[1] * pc[1]; q2 += Brow[2] * pc[2];
+      q0 += Brow[3] * pc[3]; q1 += Brow[4] * pc[4]; q2 += Brow[5] * pc[5];
+    }
+    return (q0 + q1) + q2;
+  };
+  // deterministic fused reduction of two values with ONE barrier: shuffle trees per warp, then every thread adds the
+  // per-warp partials with the same fixed pairwise tree (identical result in every thread)
+  auto reduce2 = [&](double a, double b, int bufi, double* oa, double* ob) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_down_sync(0xffffffffu, a, o);
+      b += __shfl_down_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) { s_red[bufi][2 * warp] = a; s_red[bufi][2 * warp + 1] = b; }
+    __syncthreads();
+    double pa[THREADS / 32], pb[THREADS / 32];
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) { pa[w] = s_red[bufi][2 * w]; pb[w] = s_red[bufi][2 * w + 1]; }
+#pragma unroll
+    for (int st = 1; st < THREADS / 32; st <<= 1) {
+#pragma unroll
+      for (int w = 0; w + st < THREADS / 32; w += 2 * st) { pa[w] += pa[w + st]; pb[w] += pb[w + st]; }
+    }
+    *oa = pa[0]; *ob = pb[0];
+  };
+  // ---- Chronopoulos-Gear PCG (same recurrence as oracle/ba_ref.c::ba_pcg) ----
+  double xd = 0.0, pd = 0.0, sd = 0.0, rd = 0.0, ud = 0.0, wd = 0.0;
+  if (own) {
+    rd = buf[nS + tid];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) ud += Minv[36 * ci + ca * 6 + b] * buf[nS + 6 * ci + b];
+    vu[tid] = ud;
+    vrr[0][tid] = rd;
+    vs[0][tid] = 0.0;
+  }
+  __syncthreads();
+  if (own) { wd = matvec(); vw[tid] = wd; }
+  double gamma, delta;
+  reduce2(rd * ud, wd * ud, 0, &gamma, &delta);  // barrier also publishes vw
+  const double gamma0 = gamma, tol2 = tol * tol;
+  int iters = 0;
+  double alpha = 0.0, beta = 0.0;
+  bool done = !(gamma0 > 0.0) || !(delta > 0.0);
+  if (!done) alpha = gamma / delta;
+#define SP_STAMP(k) do { if (g.prof && tid == 0 && it == 3) g.prof[k] = clock64(); } while (0)
+  if (g.prof && tid == 0) g.prof[7] = clock64() - t_start;
+  for (int it = 0; it < maxit && !done; ++it) {
+    SP_STAMP(0);
+    const int cur = it & 1, nxt = cur ^ 1;
+    if (own) {
+      // own element: p, s, x;  the camera's six r entries (and the s they need) are recomputed redundantly so that
+      // u = Minv r needs no barrier
+      pd = ud + beta * pd;
+      sd = wd + beta * sd;
+      xd += alpha * pd;
+      ud = 0.0;
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {
+        const double sb = vw[6 * ci + b] + beta * vs[cur][6 * ci + b];
+        const double rb = vrr[cur][6 * ci + b] - alpha * sb;
+        if (b == ca) rd = rb;
+        ud += Minv[36 * ci + ca * 6 + b] * rb;
+      }
+      vs[nxt][tid] = sd;
+      vrr[nxt][tid] = rd;
+    }
+    if (own) vu[tid] = ud;  // (last read by the previous mat-vec, which completed before the previous reduction barrier)
+    SP_STAMP(1);
+    __syncthreads();  // u published; every read of vw by the updates above is done
+    if (own) { wd = matvec(); vw[tid] = wd; }
+    SP_STAMP(2);
+    double gn, dl;
+    reduce2(rd * ud, wd * ud, (it + 1) & 1, &gn, &dl);  // barrier also publishes vw, vs[nxt], vrr[nxt]
+    SP_STAMP(3);
+    ++iters;
+    if (!(gn > 0.0) || gn < tol2 * gamma0) break;
+    beta = gn / gamma;
+    const double den = dl - beta * gn / alpha;
+    if (!(den > 0.0)) break;
+    alpha = gn / den;
+    gamma = gn;
+    SP_STAMP(4);
+  }
+  if (g.prof && tid == 0) g.prof[6] = clock64();
+  // publish the solution, the iteration count and the candidate camera poses
+  __syncthreads();
+  if (own) { g.x[tid] = xd; vq[tid] = xd; }
+  if (tid == 0) g.sc->pcg_iters += iters;
+  __syncthreads();
+  for (int i = tid; i < nc; i += THREADS) {
+    double pose[7], dd[6], out[7], R[9];
+    const int dm = g.dof[i];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) pose[k] = g.pose[7 * i + k];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) dd[a] = ((dm >> a) & 1) ? vq[6 * i + a] : 0.0;
+    se3_retract(pose, dd, out);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) g.pose_new[7 * i + k] = out[k];
+    quat_to_R(out, R);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g.Rt_new[12 * i + k] = R[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) g.Rt_new[12 * i + 9 + k] = out[4 + k];
+  }
+}
+constexpr int kSpThreads = 512;  // upper bound on 6N for the single-CTA path
+#define BA_SPARSE_SMALL ba_pcg_sparse_kernel<320, 12>
+#define BA_SPARSE_LARGE ba_pcg_sparse_kernel<512, 6>
 
 // ---- K7b (local BA): block-Jacobi PCG inside ONE thread-block cluster ------------------------------------------------------
 // Each CTA of the cluster keeps a block-row slice of the (damped) reduced camera matrix S resident in its shared memory for the
@@ -554,92 +936,114 @@ __global__ void __launch_bounds__(kPcgThreads, 1) ba_pcg_cluster_kernel(BaDev g,
   }
   __syncthreads();
   // From here on thread d < n6 owns vector element d (n6 <= kPcgThreads is guaranteed by the host-side dispatch).
-  // r is double-buffered (vr / vz) so that the fused update "r -= alpha q ; z = Minv r" needs no barrier.
+  // Chronopoulos-Gear PCG (same recurrence as oracle/ba_ref.c::ba_pcg): vectors u (vp), s and r double-buffered, w arrives
+  // from all CTAs through distributed shared memory into qbuf[parity].
   const bool own = tid < n6;
   const int ci = own ? tid / 6 : 0, ca = own ? tid - 6 * ci : 0;
-  double xd = 0.0, zd = 0.0, pd = 0.0, rd = own ? vr[tid] : 0.0;
-  if (own) {
+  __shared__ double s_red[2][2 * (kPcgThreads / 32)];
+  double* vu = vp;
+  double* vs[2] = {vz, vx};                 // (vx is free: x lives in registers)
+  double* vrr[2] = {vr, qbuf + 2 * (size_t)n6 + 4 * (size_t)n6};  // second r buffer sits after the four n6 vectors
+  auto reduce2 = [&](double a, double b, int bufi, double* oa, double* ob) {
 #pragma unroll
-    for (int b = 0; b < 6; ++b) zd += Minv[36 * ci + ca * 6 + b] * vr[6 * ci + b];
-    pd = zd;
-    vp[tid] = pd;
-  }
-  __shared__ double s_red[2][kPcgThreads / 32];
-  const int nw_act = (n6 + 31) >> 5;
-  // deterministic block reduction with ONE barrier: shuffle tree per warp, then every thread sums the per-warp partials
-  // in the same fixed order (identical result in every thread and in every CTA of the cluster)
-  auto reduce = [&](double v, int buf) -> double {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) s_red[buf][warp] = v;
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_down_sync(0xffffffffu, a, o);
+      b += __shfl_down_sync(0xffffffffu, b, o);
+    }
+    if (lane == 0) { s_red[bufi][2 * warp] = a; s_red[bufi][2 * warp + 1] = b; }
     __syncthreads();
-    double t = 0.0;
-    for (int w = 0; w < nw_act; ++w) t += s_red[buf][w];
-    return t;
+    double pa[kPcgThreads / 32], pb[kPcgThreads / 32];
+#pragma unroll
+    for (int w = 0; w < kPcgThreads / 32; ++w) { pa[w] = s_red[bufi][2 * w]; pb[w] = s_red[bufi][2 * w + 1]; }
+#pragma unroll
+    for (int st = 1; st < kPcgThreads / 32; st <<= 1) {
+#pragma unroll
+      for (int w = 0; w + st < kPcgThreads / 32; w += 2 * st) { pa[w] += pa[w + st]; pb[w] += pb[w + st]; }
+    }
+    *oa = pa[0]; *ob = pb[0];
   };
-  double rz = reduce(rd * zd, 0);
-  const double rz0 = rz, tol2 = tol * tol;
-  int iters = 0;
-  bool done = !(rz0 > 0.0);
-  double* rcur = vr;
-  double* rnew = vz;
   const int hl = tid & 15, grp = tid >> 4;  // 16 lanes per matrix row
-#define PCG_STAMP(k) do { if (g.prof && rank == 0 && tid == 0 && it == 3) g.prof[k] = clock64(); } while (0)
-  // C. CG iterations: one cluster barrier each
-  for (int it = 0; it < maxit && !done; ++it) {
-    double* q = qbuf + (size_t)(it & 1) * n6;
-    PCG_STAMP(0);
+  // rows of this CTA of w = S u, scattered into every CTA's wbuf through DSMEM
+  auto matvec_scatter = [&](double* wbuf) {
     for (int row = grp; row < nrows; row += kPcgThreads / 16) {
       const double* Srow = S + (size_t)row * n6;
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       int c = hl;
       for (; c + 48 < n6; c += 64) {
-        s0 += Srow[c] * vp[c];
-        s1 += Srow[c + 16] * vp[c + 16];
-        s2 += Srow[c + 32] * vp[c + 32];
-        s3 += Srow[c + 48] * vp[c + 48];
+        s0 += Srow[c] * vu[c];
+        s1 += Srow[c + 16] * vu[c + 16];
+        s2 += Srow[c + 32] * vu[c + 32];
+        s3 += Srow[c + 48] * vu[c + 48];
       }
-      for (; c < n6; c += 16) s0 += Srow[c] * vp[c];
+      for (; c < n6; c += 16) s0 += Srow[c] * vu[c];
       double sv = (s0 + s1) + (s2 + s3);
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o, 16);  // a+b == b+a: all 16 lanes agree
-      if (hl < C) cluster.map_shared_rank(q, hl)[r0 + row] = sv;
+      if (hl < C) cluster.map_shared_rank(wbuf, hl)[r0 + row] = sv;
     }
-    PCG_STAMP(1);
-    cluster.sync();
-    PCG_STAMP(2);
-    const double pq = reduce(own ? pd * q[tid] : 0.0, 1);
-    PCG_STAMP(3);
-    if (!(pq > 0.0)) break;
-    const double alpha = rz / pq;
-    double rzp = 0.0;
+  };
+  double xd = 0.0, pd = 0.0, sd = 0.0, rd = 0.0, ud = 0.0, wd = 0.0;
+  if (own) {
+    rd = vr[tid];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) ud += Minv[36 * ci + ca * 6 + b] * vr[6 * ci + b];
+    vs[0][tid] = 0.0;
+  }
+  __syncthreads();  // all reads of vr (as g~) done before anyone could overwrite; vu written next
+  if (own) vu[tid] = ud;
+  __syncthreads();
+  matvec_scatter(qbuf);
+  cluster.sync();
+  if (own) wd = qbuf[tid];
+  double gamma, delta;
+  reduce2(rd * ud, wd * ud, 0, &gamma, &delta);
+  const double gamma0 = gamma, tol2 = tol * tol;
+  int iters = 0;
+  double alpha = 0.0, beta = 0.0;
+  bool done = !(gamma0 > 0.0) || !(delta > 0.0);
+  if (!done) alpha = gamma / delta;
+#define PCG_STAMP(k) do { if (g.prof && rank == 0 && tid == 0 && it == 3) g.prof[k] = clock64(); } while (0)
+  for (int it = 0; it < maxit && !done; ++it) {
+    PCG_STAMP(0);
+    const int cur = it & 1, nxt = cur ^ 1;
+    const double* wcur = qbuf + (size_t)cur * n6;  // w of the current u (iteration parity)
+    double* wnxt = qbuf + (size_t)nxt * n6;
     if (own) {
+      pd = ud + beta * pd;
+      sd = wd + beta * sd;
       xd += alpha * pd;
-      zd = 0.0;
+      ud = 0.0;
 #pragma unroll
       for (int b = 0; b < 6; ++b) {
-        const double rb = rcur[6 * ci + b] - alpha * q[6 * ci + b];
+        const double sb = wcur[6 * ci + b] + beta * vs[cur][6 * ci + b];
+        const double rb = vrr[cur][6 * ci + b] - alpha * sb;
         if (b == ca) rd = rb;
-        zd += Minv[36 * ci + ca * 6 + b] * rb;
+        ud += Minv[36 * ci + ca * 6 + b] * rb;
       }
-      rnew[tid] = rd;
-      rzp = rd * zd;
+      vs[nxt][tid] = sd;
+      vrr[nxt][tid] = rd;
+      vu[tid] = ud;
     }
+    __syncthreads();  // u (and s, r) published inside the CTA
+    PCG_STAMP(1);
+    matvec_scatter(wnxt);
+    PCG_STAMP(2);
+    cluster.sync();   // w of every CTA has landed in everybody's wnxt
+    PCG_STAMP(3);
+    if (own) wd = wnxt[tid];
+    double gn, dl;
+    reduce2(rd * ud, wd * ud, (it + 1) & 1, &gn, &dl);
     PCG_STAMP(4);
-    const double rzn = reduce(rzp, 0);  // its barrier also publishes rnew
-    PCG_STAMP(5);
-    { double* t = rcur; rcur = rnew; rnew = t; }
     ++iters;
-    if (!(rzn > 0.0) || rzn < tol2 * rz0) break;
-    const double beta = rzn / rz;
-    if (own) {
-      pd = zd + beta * pd;
-      vp[tid] = pd;
-    }
-    rz = rzn;
-    __syncthreads();
-    PCG_STAMP(6);
+    if (!(gn > 0.0) || gn < tol2 * gamma0) break;
+    beta = gn / gamma;
+    const double den = dl - beta * gn / alpha;
+    if (!(den > 0.0)) break;
+    alpha = gn / den;
+    gamma = gn;
+    PCG_STAMP(5);
   }
+  __syncthreads();
   if (own) vx[tid] = xd;
   __syncthreads();
   // every CTA leaves the loop at the same iteration (bit-identical redundant arithmetic); make sure nobody exits while a
@@ -684,7 +1088,9 @@ struct gb_ba_graph {
   gb_ba_options opt{};
   std::vector<int> sorted_to_orig;  // sorted observation slot -> caller's edge index
   bool begun = false;
-  // cluster-PCG configuration (0 = generic multi-kernel PCG)
+  // PCG dispatch: single-CTA block-sparse kernel, else one-cluster kernel (pcg_cluster = 8/16), else generic multi-kernel
+  bool pcg_sparse = false;
+  size_t pcg_sparse_smem = 0;
   int pcg_cluster = 0;
   size_t pcg_smem = 0;
 };
@@ -736,7 +1142,18 @@ static int ba_validate(gb_ctx* ctx, const gb_ba_problem* pb) {
 // Can the reduced camera system be solved by the one-cluster PCG kernel?  Pick the cluster size, remember the smem need.
 static void ba_pick_pcg(gb_ctx* ctx, gb_ba_graph* g) {
   g->pcg_cluster = 0;
+  g->pcg_sparse = false;
   const int nc = g->d.nc, n6 = g->d.n6;
+  if (nc > 0 && n6 <= kSpThreads && g->d.s_nnzb > 0) {
+    const size_t smem = ((size_t)g->d.s_nnzb * 36 + (size_t)nc * 36 + 6 * (size_t)n6) * sizeof(double) + ((size_t)nc + 1 + g->d.s_nnzb) * sizeof(int) + 64;
+    const cudaError_t ea = n6 <= 320 ? cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                     : cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem <= (size_t)ctx->max_smem_optin && ea == cudaSuccess) {
+      g->pcg_sparse = true;
+      g->pcg_sparse_smem = smem;
+    }
+    cudaGetLastError();
+  }
   if (nc <= 0 || n6 > kPcgThreads) return;  // the cluster kernel maps one thread per element of the 6N vectors
   static bool attr_done = false;
   static bool np_ok = false;
@@ -750,7 +1167,7 @@ static void ba_pick_pcg(gb_ctx* ctx, gb_ba_graph* g) {
     const int C = sizes[t];
     if (C == 16 && !np_ok) continue;
     const int cpc = (nc + C - 1) / C;
-    const size_t smem = ((size_t)6 * cpc * n6 + (size_t)nc * 36 + 6 * (size_t)n6) * sizeof(double) + 64;
+    const size_t smem = ((size_t)6 * cpc * n6 + (size_t)nc * 36 + 7 * (size_t)n6) * sizeof(double) + 64;
     if (smem > (size_t)ctx->max_smem_optin) continue;
     if (cudaFuncSetAttribute(ba_pcg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       cudaGetLastError();
@@ -845,7 +1262,35 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
                b_oc = al((size_t)no * 4), b_op = al((size_t)no * 4), b_uv = al((size_t)no * 16),
                b_info = d.has_info ? al((size_t)no * 24) : 0, b_po = al((size_t)(np + 1) * 4), b_co = al((size_t)(nc + 1) * 4),
                b_cp = al((size_t)no * 4);
-  const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + 256;
+  // covisibility block structure of S: block (i,i') is structurally non-zero iff some landmark is seen by both cameras
+  std::vector<int> s_rowptr(nc + 1, 0), s_col, s_brow;
+  if (nc > 0 && nc <= 1024) {
+    std::vector<uint8_t> mark((size_t)nc * nc, 0);
+    for (int i = 0; i < nc; ++i) mark[(size_t)i * nc + i] = 1;
+    for (int j = 0; j < np; ++j)
+      for (int e = pt_off[j]; e < pt_off[j + 1]; ++e) {
+        const int i = pb->obs_cam[order[e]];
+        uint8_t* row = &mark[(size_t)i * nc];
+        for (int f = pt_off[j]; f < pt_off[j + 1]; ++f) row[pb->obs_cam[order[f]]] = 1;
+      }
+    for (int i = 0; i < nc; ++i) {
+      for (int k = 0; k < nc; ++k)
+        if (mark[(size_t)i * nc + k]) { s_col.push_back(k); s_brow.push_back(i); }
+      s_rowptr[i + 1] = (int)s_col.size();
+    }
+  }
+  d.s_nnzb = (int)s_col.size();
+  std::vector<int> s_upper, s_tidx(s_col.size(), 0);
+  for (int blk = 0; blk < (int)s_col.size(); ++blk) {
+    const int i = s_brow[blk], i2 = s_col[blk];
+    if (i2 >= i) s_upper.push_back(blk);
+    int t = s_rowptr[i2];
+    while (s_col[t] != i) ++t;  // the structure is symmetric
+    s_tidx[blk] = t;
+  }
+  d.s_nupper = (int)s_upper.size();
+  const size_t b_sr = al((size_t)(nc + 1) * 4), b_sc = al((size_t)s_col.size() * 4 + 4);
+  const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + b_sr + 4 * b_sc + 256;
   const size_t n6 = 6 * (size_t)nc;
   uint8_t* dblob = nullptr;
   auto layout = [&](Slab& sl) {
@@ -858,7 +1303,8 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
     sl.take(&d.W, (size_t)no * 18); sl.take(&d.U, (size_t)nc * 36); sl.take(&d.gc, (size_t)nc * 6);
     sl.take(&d.cost_pt, (size_t)np); sl.take(&d.cost_pt_new, (size_t)np);
     sl.take(&d.Minv, (size_t)nc * 36);
-    sl.take(&d.x, n6); sl.take(&d.r, n6); sl.take(&d.z, n6); sl.take(&d.p, n6); sl.take(&d.q, n6);
+    sl.take(&d.Sb, (size_t)d.s_nnzb * 36);
+    sl.take(&d.x, n6); sl.take(&d.r, n6); sl.take(&d.z, n6); sl.take(&d.p, n6); sl.take(&d.q, n6); sl.take(&d.sv, n6);
     sl.take(&d.sc, 1);
     sl.take(&g->buf, g->buf_doubles);
     sl.take(&g->d_cost, 8);
@@ -893,7 +1339,8 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += bytes; return o; };
   const size_t o_pose = take(b_pose), o_pts = take(b_pts), o_dof = take(b_dof), o_pf = take(b_pf), o_oc = take(b_oc),
-               o_op = take(b_op), o_uv = take(b_uv), o_info = take(b_info), o_po = take(b_po), o_co = take(b_co), o_cp = take(b_cp);
+               o_op = take(b_op), o_uv = take(b_uv), o_info = take(b_info), o_po = take(b_po), o_co = take(b_co), o_cp = take(b_cp),
+               o_sr = take(b_sr), o_sc = take(b_sc), o_sb = take(b_sc), o_su = take(b_sc), o_st = take(b_sc);
   memcpy(h + o_pose, pb->cam_pose_wc, (size_t)nc * 56);
   memcpy(h + o_pts, pb->points, (size_t)np * 24);
   for (int i = 0; i < nc; ++i) h[o_dof + i] = pb->cam_dof ? (pb->cam_dof[i] & 63) : 63;
@@ -914,6 +1361,11 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   memcpy(h + o_po, pt_off.data(), (size_t)(np + 1) * 4);
   memcpy(h + o_co, cam_off.data(), (size_t)(nc + 1) * 4);
   memcpy(h + o_cp, cam_perm.data(), (size_t)no * 4);
+  memcpy(h + o_sr, s_rowptr.data(), (size_t)(nc + 1) * 4);
+  if (!s_col.empty()) memcpy(h + o_sc, s_col.data(), s_col.size() * 4);
+  if (!s_brow.empty()) memcpy(h + o_sb, s_brow.data(), s_brow.size() * 4);
+  if (!s_upper.empty()) memcpy(h + o_su, s_upper.data(), s_upper.size() * 4);
+  if (!s_tidx.empty()) memcpy(h + o_st, s_tidx.data(), s_tidx.size() * 4);
   g->sorted_to_orig.swap(order);
   GB_CUDA(ctx, cudaMemcpyAsync(dblob, h, blob, cudaMemcpyHostToDevice, ctx->stream));
   double* d_pose_wc = (double*)(dblob + o_pose);
@@ -922,6 +1374,8 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   d.o_cam = (int*)(dblob + o_oc); d.o_pt = (int*)(dblob + o_op); d.o_uv = (double*)(dblob + o_uv);
   d.o_info = d.has_info ? (double*)(dblob + o_info) : nullptr;
   d.pt_off = (int*)(dblob + o_po); d.cam_off = (int*)(dblob + o_co); d.cam_perm = (int*)(dblob + o_cp);
+  d.s_rowptr = (int*)(dblob + o_sr); d.s_col = (int*)(dblob + o_sc); d.s_brow = (int*)(dblob + o_sb);
+  d.s_upper = (int*)(dblob + o_su); d.s_tidx = (int*)(dblob + o_st);
   if (nc > 0) {
     ba_prepare_kernel<<<gb_div_up(nc, 128), 128, 0, ctx->stream>>>(nc, d_pose_wc, g->pose_init);
     GB_LAUNCH_CHECK(ctx);
@@ -983,9 +1437,9 @@ static int ba_pcg_generic(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   cudaStream_t s = ctx->stream;
   ba_damp_kernel<<<gb_div_up(d.n6, 128), 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
   pcg_init_kernel<<<1, kRedThreads, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
-  for (int k = 0; k < g->opt.pcg_max_iters; ++k) {
+  for (int k = 0; k <= g->opt.pcg_max_iters; ++k) {  // one extra pair: the convergence test of update k runs in pair k+1
     pcg_matvec_kernel<<<gb_div_up(d.n6, 8), 256, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
-    pcg_update_kernel<<<1, kRedThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
+    pcg_update_kernel<<<1, kRedThreads, 0, s>>>(d, (int)g->opt.pcg_max_iters); GB_LAUNCH_CHECK(ctx);
   }
   ba_retract_kernel<<<gb_div_up(d.nc, 128), 128, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
   return GB_OK;
@@ -1005,20 +1459,44 @@ static int ba_pcg_cluster(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   return GB_OK;
 }
 
+int gb_ba_graph_sweep(gb_ctx* ctx, gb_ba_graph* g, double huber_delta) {
+  if (!ctx || !g) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  gb_ba_options o;
+  gb_ba_options_default(&o);
+  o.huber_delta = huber_delta;
+  GB_CHECK(gb_ba_graph_begin(ctx, g, &o));
+  BaDev& d = g->d;
+  if (d.np > 0) { ba_linearize_points_kernel<<<gb_div_up(d.np * kLpp, kPtThreads), kPtThreads, 0, ctx->stream>>>(d); GB_LAUNCH_CHECK(ctx); }
+  if (d.nc > 0) { ba_linearize_cams_kernel<<<d.nc, kCamThreads, 0, ctx->stream>>>(d); GB_LAUNCH_CHECK(ctx); }
+  return GB_OK;
+}
+
 int gb_ba_graph_reduce_local(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   if (!ctx || !g || !g->begun) return GB_ERR_INVALID;
   CtxLock lk(ctx);
   BaDev& d = g->d;
   if (!buf) buf = g->buf;
   cudaStream_t s = ctx->stream;
-  if (d.np > 0) { ba_linearize_points_kernel<<<gb_div_up(d.np, kPtThreads), kPtThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
+  if (d.np > 0) { ba_linearize_points_kernel<<<gb_div_up(d.np * kLpp, kPtThreads), kPtThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
   if (d.nc > 0) { ba_linearize_cams_kernel<<<d.nc, kCamThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
+  const bool blocks = g->pcg_sparse && buf == g->buf;  // local-BA path: deterministic block-gather Schur into the block-CSR
   {
-    const size_t work = std::max<size_t>((size_t)d.n6 * d.n6, (size_t)d.np);
-    const int blocks = (int)std::min<size_t>(std::max<size_t>((work + 255) / 256, 1), (size_t)ctx->sm_count * 8);
-    ba_prepare_schur_kernel<<<blocks, 256, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+    const size_t work = std::max<size_t>(blocks ? 0 : (size_t)d.n6 * d.n6, (size_t)d.np);
+    const int nblk = (int)std::min<size_t>(std::max<size_t>((work + 255) / 256, 1), (size_t)ctx->sm_count * 8);
+    ba_prepare_schur_kernel<<<nblk, 256, 0, s>>>(d, buf, blocks ? 0 : 1); GB_LAUNCH_CHECK(ctx);
   }
-  if (d.no > 0 && d.nc > 0) { ba_schur_accum_kernel<<<gb_div_up(d.no, 128), 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx); }
+  if (d.no > 0 && d.nc > 0) {
+    if (blocks) {
+      ba_schur_blocks_kernel<<<d.s_nupper, 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+    } else {
+      ba_schur_accum_kernel<<<gb_div_up(d.no, 128), 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+      const int nblk = (int)std::min<size_t>(((size_t)d.n6 * d.n6 + 255) / 256, (size_t)ctx->sm_count * 8);
+      ba_mirror_kernel<<<nblk, 256, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+    }
+  } else if (blocks && d.nc > 0) {
+    ba_schur_blocks_kernel<<<d.s_nupper, 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+  }
   return GB_OK;
 }
 
@@ -1026,9 +1504,22 @@ static int ba_step_core(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   BaDev& d = g->d;
   cudaStream_t s = ctx->stream;
   if (d.nc > 0) {
-    if (g->pcg_cluster > 0) GB_CHECK(ba_pcg_cluster(ctx, g, buf)); else GB_CHECK(ba_pcg_generic(ctx, g, buf));
+    if (g->pcg_sparse && buf == g->buf) {
+      if (d.n6 <= 320) {
+        GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
+        BA_SPARSE_SMALL<<<1, 320, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
+      } else {
+        GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
+        BA_SPARSE_LARGE<<<1, 512, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
+      }
+      GB_LAUNCH_CHECK(ctx);
+    } else if (g->pcg_cluster > 0) {
+      GB_CHECK(ba_pcg_cluster(ctx, g, buf));
+    } else {
+      GB_CHECK(ba_pcg_generic(ctx, g, buf));
+    }
   }
-  if (d.np > 0) { ba_backsub_cost_kernel<<<gb_div_up(d.np, 128), 128, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
+  if (d.np > 0) { ba_backsub_cost_kernel<<<gb_div_up(d.np * kLpp, 128), 128, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
   return GB_OK;
 }
 
@@ -1222,6 +1713,10 @@ GB_API int gb_dbg_ba_reduced(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* o
   GB_CHECK(gb_ba_graph_step(ctx, g, nullptr, nullptr));
   BaDev& d = g->d;
   const size_t n6 = d.n6;
+  if (g->pcg_sparse && d.nc > 0) {  // the local-BA path keeps S as block-CSR: scatter it into the dense layout for inspection
+    ba_densify_kernel<<<64, 256, 0, ctx->stream>>>(d, g->buf);
+    ba_densify_fill_kernel<<<gb_div_up(d.s_nnzb * 36, 256), 256, 0, ctx->stream>>>(d, g->buf);
+  }
   if (S) GB_CUDA(ctx, cudaMemcpyAsync(S, g->buf, n6 * n6 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (gt) GB_CUDA(ctx, cudaMemcpyAsync(gt, g->buf + n6 * n6, n6 * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (dc) GB_CUDA(ctx, cudaMemcpyAsync(dc, d.x, n6 * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1232,12 +1727,18 @@ GB_API int gb_dbg_ba_reduced(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* o
 }
 
 // force (1) / release (0) the generic multi-kernel PCG on this graph — lets the tests cover both solver paths
+// on: 0 = automatic dispatch, 1 = generic multi-kernel PCG, 2 = one-cluster DSMEM PCG (if it fits), 3 = single-CTA sparse
 GB_API int gb_dbg_ba_force_generic_pcg(gb_ctx* ctx, gb_ba_graph* g, int on) {
   if (!ctx || !g) return GB_ERR_INVALID;
   CtxLock lk(ctx);
-  if (on) g->pcg_cluster = 0; else ba_pick_pcg(ctx, g);
+  ba_pick_pcg(ctx, g);
+  if (on == 1) { g->pcg_cluster = 0; g->pcg_sparse = false; }
+  if (on == 2) g->pcg_sparse = false;
+  if (on == 3) g->pcg_cluster = 0;
   return GB_OK;
 }
+
+GB_API int gb_dbg_ba_pcg_sparse(gb_ctx* ctx, gb_ba_graph* g) { return (ctx && g) ? (g->pcg_sparse ? g->d.s_nnzb : 0) : -1; }
 
 GB_API int gb_dbg_ba_pcg_cluster_size(gb_ctx* ctx, gb_ba_graph* g) { return (ctx && g) ? g->pcg_cluster : -1; }
 

@@ -13,8 +13,9 @@ struct BaScalars {
   double delta, ftol, pcg_tol, lambda_init;
   // LM state
   double lambda, nu, cost, cost_new, initial_cost;
-  // PCG state
-  double rz, rz0;
+  // PCG state (generic multi-kernel path): gamma = r'u, gamma0 its initial value, CG step sizes
+  double rz, rz0, pcg_alpha, pcg_beta;
+  int pcg_first, pcg_k;
   int need_linearize, stop, status, iterations, accepted, accept_flag;
   int pcg_iters, pcg_done;
 };
@@ -28,10 +29,16 @@ struct BaDev {
   const int *o_cam, *o_pt;
   const double *o_uv, *o_info;
   const int *pt_off, *cam_off, *cam_perm;
+  // block structure of the reduced camera matrix S (covisibility): CSR over 6x6 blocks, built on the host
+  const int *s_rowptr, *s_col, *s_brow;  // s_brow[blk] = block row of blk
+  const int *s_upper, *s_tidx;           // list of blocks with col >= row; s_tidx[blk] = index of the transposed block
+  int s_nupper;
+  double* Sb;                            // [s_nnzb][36] block-CSR values of S (local-BA path)
+  int s_nnzb;
   // linearisation
   double *V, *gp, *Vinv, *W, *U, *gc, *cost_pt, *cost_pt_new;
   // PCG
-  double *Minv, *x, *r, *z, *p, *q;
+  double *Minv, *x, *r, *z, *p, *q, *sv;  // generic PCG: z = u = Minv r, q = w = S u, sv = S p
   BaScalars* sc;
   long long* prof;  // optional clock64 stamps of the cluster PCG (test hook), or nullptr
 };
@@ -93,7 +100,7 @@ __device__ __forceinline__ double clampd(double d) { return d < 1e-6 ? 1e-6 : (d
 // Cholesky inverse of a small SPD matrix, row-major, in place; returns false if not positive definite.
 template <int N>
 __device__ __forceinline__ bool spd_inverse(double* A) {
-  double L[N * N], Li[N * N];
+  double L[N * N], Li[N * N], id[N];  // id[i] = 1 / L_ii (one division per pivot; everything else multiplies)
 #pragma unroll
   for (int i = 0; i < N * N; ++i) { L[i] = 0.0; Li[i] = 0.0; }
 #pragma unroll
@@ -106,8 +113,9 @@ __device__ __forceinline__ bool spd_inverse(double* A) {
       if (i == j) {
         if (!(s > 0.0)) return false;
         L[i * N + i] = sqrt(s);
+        id[i] = 1.0 / L[i * N + i];
       } else {
-        L[i * N + j] = s / L[j * N + j];
+        L[i * N + j] = s * id[j];
       }
     }
 #pragma unroll
@@ -117,7 +125,7 @@ __device__ __forceinline__ bool spd_inverse(double* A) {
       double s = (i == c) ? 1.0 : 0.0;
 #pragma unroll
       for (int k = c; k < i; ++k) s -= L[i * N + k] * Li[k * N + c];
-      Li[i * N + c] = s / L[i * N + i];
+      Li[i * N + c] = s * id[i];
     }
 #pragma unroll
   for (int i = 0; i < N; ++i)

@@ -96,6 +96,27 @@ __device__ __forceinline__ int ring_arc9_maxmin(const int* v) {
   return best;
 }
 
+// Is there a 9-arc of the 16-ring entirely brighter than c+t or entirely darker than c-t?  (bit masks + doubling)
+__device__ __forceinline__ bool fast_is_corner(const uint8_t* p, int threshold) {
+  const int c = p[0], hi = c + threshold, lo = c - threshold;
+  int r[16];
+  r[0] = p[3 * kInW + 0]; r[1] = p[3 * kInW + 1]; r[2] = p[2 * kInW + 2]; r[3] = p[1 * kInW + 3];
+  r[4] = p[3]; r[5] = p[-1 * kInW + 3]; r[6] = p[-2 * kInW + 2]; r[7] = p[-3 * kInW + 1];
+  r[8] = p[-3 * kInW]; r[9] = p[-3 * kInW - 1]; r[10] = p[-2 * kInW - 2]; r[11] = p[-1 * kInW - 3];
+  r[12] = p[-3]; r[13] = p[1 * kInW - 3]; r[14] = p[2 * kInW - 2]; r[15] = p[3 * kInW - 1];
+  unsigned mb = 0, md = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    mb |= (r[k] > hi ? 1u : 0u) << k;
+    md |= (r[k] < lo ? 1u : 0u) << k;
+  }
+  mb |= mb << 16;
+  md |= md << 16;
+  unsigned b = mb & (mb >> 1); b &= b >> 2; b &= b >> 4; b &= mb >> 8;  // bit i set <=> bits i..i+8 all set
+  unsigned d = md & (md >> 1); d &= d >> 2; d &= d >> 4; d &= md >> 8;
+  return ((b | d) & 0xffffu) != 0;
+}
+
 __device__ __forceinline__ int fast_full_score(const uint8_t* p /* centre inside the shared tile */, int threshold) {
   // ring offsets (dx,dy), radius 3
   const int c = p[0];
@@ -122,8 +143,9 @@ __global__ void __launch_bounds__(kFastThreads) orb_fast_kernel(const __grid_con
                                                                 int* __restrict__ counts, int* __restrict__ hist) {
   __shared__ __align__(16) uint8_t s_in[kInH * kInW];
   __shared__ uint8_t s_sc[kScH * kScW];
-  __shared__ uint16_t s_work[kScH * kScW];
-  __shared__ int s_nwork;
+  __shared__ uint16_t s_work[kScH * kScW];   // positions that survive the opposite-pair quick reject
+  __shared__ uint16_t s_work2[kScH * kScW];  // ... of which: true corners (9 contiguous), the only ones scored exactly
+  __shared__ int s_nwork, s_nwork2;
   // which level / tile
   int l = 0;
 #pragma unroll 1
@@ -134,7 +156,7 @@ __global__ void __launch_bounds__(kFastThreads) orb_fast_kernel(const __grid_con
   const int x0 = (t % L.tiles_x) * kTileW, y0 = (t / L.tiles_x) * kTileH;
   const uint8_t* img = pyr + L.off;
   const int tid = threadIdx.x;
-  if (tid == 0) s_nwork = 0;
+  if (tid == 0) { s_nwork = 0; s_nwork2 = 0; }
   // stage the input tile with 32-bit loads (x0-4 and the pitch are 4-byte aligned); zero outside the image rows / pitch
   for (int i = tid; i < kInH * (kInW / 4); i += kFastThreads) {
     const int ry = i / (kInW / 4), rx = (i % (kInW / 4)) * 4;
@@ -160,10 +182,18 @@ __global__ void __launch_bounds__(kFastThreads) orb_fast_kernel(const __grid_con
     }
   }
   __syncthreads();
-  // phase 2: dense full-score pass over the survivors
+  // phase 2a: dense 9-contiguity test (bit masks) over the quick-reject survivors -> second worklist
   const int nwork = s_nwork;
   for (int k = tid; k < nwork; k += kFastThreads) {
     const int i = s_work[k];
+    const int lx = i % kScW, ly = i / kScW;
+    if (fast_is_corner(&s_in[(ly + 3) * kInW + lx + 3], thr)) s_work2[atomicAdd(&s_nwork2, 1)] = (uint16_t)i;
+  }
+  __syncthreads();
+  // phase 2b: dense exact score over the true corners only
+  const int nwork2 = s_nwork2;
+  for (int k = tid; k < nwork2; k += kFastThreads) {
+    const int i = s_work2[k];
     const int lx = i % kScW, ly = i / kScW;
     s_sc[i] = (uint8_t)fast_full_score(&s_in[(ly + 3) * kInW + lx + 3], thr);
   }
@@ -194,18 +224,25 @@ __device__ __forceinline__ uint32_t float_key(float f) {  // order-preserving ma
 }
 
 __device__ __forceinline__ float harris_response(const uint8_t* __restrict__ img, int pitch, int x, int y) {
+  // 9x9 byte window held in a rolling 3-row register file: 81 loads instead of 49 x 6
   int a = 0, b = 0, c = 0;
-#pragma unroll 1
-  for (int dy = -3; dy <= 3; ++dy) {
-    const uint8_t* pm = img + (size_t)(y + dy - 1) * pitch + x;
-    const uint8_t* p0 = pm + pitch;
-    const uint8_t* pp = p0 + pitch;
+  int r0[9], r1[9], r2[9];
+  const uint8_t* p = img + (size_t)(y - 4) * pitch + (x - 4);
 #pragma unroll
-    for (int dx = -3; dx <= 3; ++dx) {
-      const int Ix = ((int)p0[dx + 1] - (int)p0[dx - 1]) * 2 + ((int)pm[dx + 1] - (int)pm[dx - 1]) + ((int)pp[dx + 1] - (int)pp[dx - 1]);
-      const int Iy = ((int)pp[dx] - (int)pm[dx]) * 2 + ((int)pp[dx - 1] - (int)pm[dx - 1]) + ((int)pp[dx + 1] - (int)pm[dx + 1]);
+  for (int k = 0; k < 9; ++k) { r0[k] = p[k]; r1[k] = p[pitch + k]; }
+#pragma unroll
+  for (int dy = 0; dy < 7; ++dy) {
+    const uint8_t* q = p + (size_t)(dy + 2) * pitch;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) r2[k] = q[k];
+#pragma unroll
+    for (int dx = 0; dx < 7; ++dx) {
+      const int Ix = (r1[dx + 2] - r1[dx]) * 2 + (r0[dx + 2] - r0[dx]) + (r2[dx + 2] - r2[dx]);
+      const int Iy = (r2[dx + 1] - r0[dx + 1]) * 2 + (r2[dx] - r0[dx]) + (r2[dx + 2] - r0[dx + 2]);
       a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
     }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { r0[k] = r1[k]; r1[k] = r2[k]; }
   }
   const float scale = __fdiv_rn(1.f, __fmul_rn((float)(4 * 7), 255.f));
   const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
@@ -229,7 +266,8 @@ __device__ __forceinline__ int fast_keep_threshold(const int* __restrict__ hist_
 __global__ void __launch_bounds__(256) orb_harris_kernel(const __grid_constant__ OrbParams P, const uint8_t* __restrict__ pyr,
                                                          const uint32_t* __restrict__ cand_pos, const uint8_t* __restrict__ cand_score,
                                                          const int* __restrict__ counts, const int* __restrict__ hist,
-                                                         uint32_t* __restrict__ cand_key, float* __restrict__ cand_resp) {
+                                                         uint32_t* __restrict__ surv_key, float* __restrict__ surv_resp,
+                                                         uint32_t* __restrict__ surv_pos, int* __restrict__ surv_count) {
   __shared__ int s_thr;
   const int l = blockIdx.y;
   const LevelInfo& L = P.lv[l];
@@ -238,24 +276,26 @@ __global__ void __launch_bounds__(256) orb_harris_kernel(const __grid_constant__
   const int thr = s_thr;
   const int n = min(counts[l], L.cand_cap);
   const uint8_t* img = pyr + L.off;
+  // survivors of the FAST-score cut are appended to a compact per-level list (order is irrelevant: the selection below is
+  // order-independent and ends with a sort), so the selection kernel scans ~2n entries instead of every FAST corner
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int g = L.cand_off + i;
-    uint32_t key = 0;
-    float r = 0.f;
     if ((int)cand_score[g] >= thr) {
       const uint32_t pos = cand_pos[g];
-      r = harris_response(img, L.pitch, pos & 0xffff, pos >> 16);
-      key = float_key(r);
+      const float r = harris_response(img, L.pitch, pos & 0xffff, pos >> 16);
+      const int slot = L.cand_off + atomicAdd(&surv_count[l], 1);
+      surv_key[slot] = float_key(r);
+      surv_resp[slot] = r;
+      surv_pos[slot] = pos;
     }
-    cand_key[g] = key;
-    cand_resp[g] = r;
   }
 }
 
 // ---- K3b: per-level selection + canonical ordering ------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSelThreads) orb_select_kernel(const __grid_constant__ OrbParams P, const uint32_t* __restrict__ cand_pos,
                                                                  const uint32_t* __restrict__ cand_key, const float* __restrict__ cand_resp,
-                                                                 const int* __restrict__ counts, uint32_t* __restrict__ kept_pos,
+                                                                 const int* __restrict__ counts, const int* __restrict__ raw_counts,
+                                                                 uint32_t* __restrict__ kept_pos,
                                                                  float* __restrict__ kept_resp, int* __restrict__ kept_count,
                                                                  int* __restrict__ status) {
   __shared__ int s_hist[256];
@@ -264,18 +304,10 @@ __global__ void __launch_bounds__(kSelThreads) orb_select_kernel(const __grid_co
   __shared__ uint32_t s_prefix;
   const int l = blockIdx.x, tid = threadIdx.x;
   const LevelInfo& L = P.lv[l];
-  const int n = min(counts[l], L.cand_cap);
+  const int n = min(counts[l], L.cand_cap);  // counts here = number of survivors of the FAST-score cut (compact list)
   const uint32_t* keys = cand_key + L.cand_off;
-  if (counts[l] > L.cand_cap && tid == 0) atomicMin(status, -1);  // cannot happen (cap = w*h/4): flag loudly if it does
-  // how many survived the FAST-score cut
-  int local = 0;
-  for (int i = tid; i < n; i += kSelThreads) local += keys[i] != 0;
-  if (tid == 0) s_n = 0;
-  __syncthreads();
-  if (local) atomicAdd(&s_n, local);
-  __syncthreads();
-  const int m = s_n;
-  __syncthreads();  // every thread must have read s_n before it is reused below
+  if (raw_counts[l] > L.cand_cap && tid == 0) atomicMin(status, -1);  // cannot happen (cap = w*h/4): flag loudly if it does
+  const int m = n;
   uint32_t T = 1;  // keep every key >= T; key 0 = dropped
   if (L.quota <= 0) T = 0xffffffffu;
   else if (m > L.quota) {
@@ -524,6 +556,7 @@ struct OrbState {
   uint8_t* d_pyr = nullptr; size_t pyr_bytes = 0;
   uint32_t* d_tabs = nullptr;           // resize tables
   uint32_t* d_cand_pos = nullptr; uint8_t* d_cand_score = nullptr; uint32_t* d_cand_key = nullptr; float* d_cand_resp = nullptr;
+  uint32_t* d_surv_pos = nullptr;       // compact survivor lists share d_cand_key / d_cand_resp
   int* d_counts = nullptr;              // [kMaxLevels] candidates | [kMaxLevels] kept | [1] status | hist [kMaxLevels*256]
   uint32_t* d_kept_pos = nullptr; float* d_kept_resp = nullptr;
   signed char* d_pattern = nullptr;
@@ -532,6 +565,7 @@ struct OrbState {
 };
 
 static void orb_free_buffers(OrbState* s) {
+  cudaFree(s->d_surv_pos); s->d_surv_pos = nullptr;
   cudaFree(s->d_pyr); cudaFree(s->d_tabs); cudaFree(s->d_cand_pos); cudaFree(s->d_cand_score); cudaFree(s->d_cand_key);
   cudaFree(s->d_cand_resp); cudaFree(s->d_counts); cudaFree(s->d_kept_pos); cudaFree(s->d_kept_resp);
   s->d_pyr = nullptr; s->d_tabs = nullptr; s->d_cand_pos = nullptr; s->d_cand_score = nullptr; s->d_cand_key = nullptr;
@@ -646,7 +680,8 @@ static int orb_prepare(gb_ctx* ctx, int w, int h, const gb_orb_cfg* cfg) {
   GB_CUDA(ctx, cudaMalloc((void**)&s->d_cand_score, nc));
   GB_CUDA(ctx, cudaMalloc((void**)&s->d_cand_key, nc * 4));
   GB_CUDA(ctx, cudaMalloc((void**)&s->d_cand_resp, nc * 4));
-  GB_CUDA(ctx, cudaMalloc((void**)&s->d_counts, (2 * kMaxLevels + 8 + kMaxLevels * 256) * sizeof(int)));
+  GB_CUDA(ctx, cudaMalloc((void**)&s->d_counts, (3 * kMaxLevels + 8 + kMaxLevels * 256) * sizeof(int)));
+  GB_CUDA(ctx, cudaMalloc((void**)&s->d_surv_pos, nc * 4));
   GB_CUDA(ctx, cudaMalloc((void**)&s->d_kept_pos, (size_t)kMaxLevels * kSelMax * 4));
   GB_CUDA(ctx, cudaMalloc((void**)&s->d_kept_resp, (size_t)kMaxLevels * kSelMax * 4));
   GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // tabs is a local vector
@@ -668,7 +703,8 @@ static int orb_launch(gb_ctx* ctx, gb_features* out) {
   int* d_kept = d_counts + kMaxLevels;
   int* d_status = d_counts + 2 * kMaxLevels;
   int* d_hist = d_counts + 2 * kMaxLevels + 8;
-  GB_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (2 * kMaxLevels + 8 + kMaxLevels * 256) * sizeof(int), st));
+  int* d_surv = d_hist + kMaxLevels * 256;
+  GB_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (3 * kMaxLevels + 8 + kMaxLevels * 256) * sizeof(int), st));
   for (int l = 1; l < P.nlevels; ++l) {
     const LevelInfo &S = P.lv[l - 1], &D = P.lv[l];
     dim3 blk(64, 4), grd(gb_div_up(gb_div_up(D.w, 4), 64), gb_div_up(D.h, 4));
@@ -680,9 +716,9 @@ static int orb_launch(gb_ctx* ctx, gb_features* out) {
     orb_fast_kernel<<<P.total_tiles, kFastThreads, 0, st>>>(P, s->d_pyr, s->d_cand_pos, s->d_cand_score, d_counts, d_hist);
     GB_LAUNCH_CHECK(ctx);
     orb_harris_kernel<<<dim3(32, P.nlevels), 256, 0, st>>>(P, s->d_pyr, s->d_cand_pos, s->d_cand_score, d_counts, d_hist,
-                                                           s->d_cand_key, s->d_cand_resp);
+                                                           s->d_cand_key, s->d_cand_resp, s->d_surv_pos, d_surv);
     GB_LAUNCH_CHECK(ctx);
-    orb_select_kernel<<<P.nlevels, kSelThreads, 0, st>>>(P, s->d_cand_pos, s->d_cand_key, s->d_cand_resp, d_counts, s->d_kept_pos,
+    orb_select_kernel<<<P.nlevels, kSelThreads, 0, st>>>(P, s->d_surv_pos, s->d_cand_key, s->d_cand_resp, d_surv, d_counts, s->d_kept_pos,
                                                          s->d_kept_resp, d_kept, d_status);
     GB_LAUNCH_CHECK(ctx);
   }

@@ -208,6 +208,9 @@ GB_API int gb_ba_graph_destroy(gb_ctx* ctx, gb_ba_graph* g);
 GB_API int gb_ba_graph_reset(gb_ctx* ctx, gb_ba_graph* g); /* restore the uploaded estimate (device-to-device) */
 GB_API int gb_ba_graph_solve(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, gb_ba_result* result);
 GB_API int gb_ba_graph_download(gb_ctx* ctx, gb_ba_graph* g, double* cam_pose_wc, double* points);
+/* One fused residual + Jacobian sweep at the current estimate (K6: V, g_p, W, U, g_c, cost stay on the device) — the
+ * "BA Jacobian-eval" of the BASELINE metric in isolation; enqueued on the ctx stream, no host synchronisation. */
+GB_API int gb_ba_graph_sweep(gb_ctx* ctx, gb_ba_graph* g, double huber_delta);
 
 /*
  * Stepwise interface for landmark-sharded multi-GPU global BA: every rank holds all cameras and a

@@ -319,12 +319,16 @@ static void ba_schur(const ba_state* s, double lambda, double* S, double* gt, do
   }
 }
 
-/* Block-Jacobi PCG on S x = g.  Returns iterations. */
+/* Block-Jacobi preconditioned CG on S x = g in the Chronopoulos-Gear arrangement (one fused pair of inner products per
+ * iteration: gamma = r'u and delta = w'u with u = M^-1 r, w = S u; p and s = S p follow by recurrence).  In exact arithmetic it
+ * is the classical PCG iteration; it is stated this way because it is what the GPU kernels run (two barriers and one
+ * reduction per iteration instead of four and two).  Returns the number of x updates. */
 static int ba_pcg(int nc, const double* S, const double* g, double* x, int maxit, double tol) {
   int n6 = 6 * nc;
   double* Minv = (double*)malloc(sizeof(double) * 36 * (size_t)(nc + 1));
-  double *r = (double*)malloc(sizeof(double) * (size_t)(n6 + 1)), *z = (double*)malloc(sizeof(double) * (size_t)(n6 + 1)),
-         *p = (double*)malloc(sizeof(double) * (size_t)(n6 + 1)), *q = (double*)malloc(sizeof(double) * (size_t)(n6 + 1));
+  size_t nb = sizeof(double) * (size_t)(n6 + 1);
+  double *r = (double*)malloc(nb), *u = (double*)malloc(nb), *w = (double*)malloc(nb), *p = (double*)calloc((size_t)n6 + 1, sizeof(double)),
+         *sv = (double*)calloc((size_t)n6 + 1, sizeof(double));
   for (int i = 0; i < nc; ++i) {
     for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) Minv[36 * i + a * 6 + b] = S[(size_t)(6 * i + a) * n6 + 6 * i + b];
     if (spd_inverse(Minv + 36 * i, 6)) { /* fall back to the diagonal */
@@ -333,31 +337,42 @@ static int ba_pcg(int nc, const double* S, const double* g, double* x, int maxit
   }
 #define APPLY_MINV(src, dst) \
   for (int i = 0; i < nc; ++i) for (int a = 0; a < 6; ++a) { double sacc = 0.0; for (int b = 0; b < 6; ++b) sacc += Minv[36 * i + a * 6 + b] * (src)[6 * i + b]; (dst)[6 * i + a] = sacc; }
+#define MATVEC(src, dst) \
+  for (int a = 0; a < n6; ++a) { double sacc = 0.0; const double* row = S + (size_t)a * n6; for (int b = 0; b < n6; ++b) sacc += row[b] * (src)[b]; (dst)[a] = sacc; }
   int it = 0;
-  double rz = 0.0;
   for (int a = 0; a < n6; ++a) { x[a] = 0.0; r[a] = g[a]; }
-  APPLY_MINV(r, z);
-  for (int a = 0; a < n6; ++a) { p[a] = z[a]; rz += r[a] * z[a]; }
-  double rz0 = rz;
-  if (rz0 > 0.0) {
+  APPLY_MINV(r, u);
+  MATVEC(u, w);
+  double gamma = 0.0, delta = 0.0;
+  for (int a = 0; a < n6; ++a) { gamma += r[a] * u[a]; delta += w[a] * u[a]; }
+  const double gamma0 = gamma;
+  if (gamma0 > 0.0 && delta > 0.0) {
+    double alpha = gamma / delta, beta = 0.0;
     while (it < maxit) {
-      double pq = 0.0;
-      for (int a = 0; a < n6; ++a) { double sacc = 0.0; const double* row = S + (size_t)a * n6; for (int b = 0; b < n6; ++b) sacc += row[b] * p[b]; q[a] = sacc; pq += p[a] * sacc; }
-      if (!(pq > 0.0)) break;
-      double alpha = rz / pq;
-      for (int a = 0; a < n6; ++a) { x[a] += alpha * p[a]; r[a] -= alpha * q[a]; }
-      APPLY_MINV(r, z);
-      double rzn = 0.0;
-      for (int a = 0; a < n6; ++a) rzn += r[a] * z[a];
+      for (int a = 0; a < n6; ++a) {
+        p[a] = u[a] + beta * p[a];
+        sv[a] = w[a] + beta * sv[a];
+        x[a] += alpha * p[a];
+        r[a] -= alpha * sv[a];
+      }
+      APPLY_MINV(r, u);
       ++it;
-      if (!(rzn > 0.0) || rzn < tol * tol * rz0) break; /* == sqrt(rzn/rz0) < tol without the sqrt/div */
-      double beta = rzn / rz;
-      for (int a = 0; a < n6; ++a) p[a] = z[a] + beta * p[a];
-      rz = rzn;
+      double gn = 0.0;
+      for (int a = 0; a < n6; ++a) gn += r[a] * u[a];
+      if (!(gn > 0.0) || gn < tol * tol * gamma0) break; /* == sqrt(gn/gamma0) < tol without the sqrt/div */
+      MATVEC(u, w);
+      delta = 0.0;
+      for (int a = 0; a < n6; ++a) delta += w[a] * u[a];
+      beta = gn / gamma;
+      const double den = delta - beta * gn / alpha;
+      if (!(den > 0.0)) break;
+      alpha = gn / den;
+      gamma = gn;
     }
   }
 #undef APPLY_MINV
-  free(Minv); free(r); free(z); free(p); free(q);
+#undef MATVEC
+  free(Minv); free(r); free(u); free(w); free(p); free(sv);
   return it;
 }
 

@@ -53,17 +53,26 @@ def test_linearisation_matches_oracle(ctx, name):
     g.close()
 
 
-@pytest.mark.parametrize("generic", [False, True], ids=["cluster_pcg", "generic_pcg"])
+PCG_MODES = {"sparse_pcg": 0, "cluster_pcg": 2, "generic_pcg": 1}
+
+
+def force_mode(g, mode):
+    g.force_generic_pcg(PCG_MODES[mode])
+    if mode == "sparse_pcg":
+        assert g.pcg_sparse_blocks() > 0        # local-BA sizes must take the single-CTA block-sparse path by default
+    elif mode == "cluster_pcg":
+        assert g.pcg_sparse_blocks() == 0 and g.pcg_cluster_size() in (8, 16)
+    else:
+        assert g.pcg_sparse_blocks() == 0 and g.pcg_cluster_size() == 0
+
+
+@pytest.mark.parametrize("mode", list(PCG_MODES))
 @pytest.mark.parametrize("name", list(PROBLEMS))
-def test_reduced_system_and_pcg_match_oracle(ctx, name, generic):
+def test_reduced_system_and_pcg_match_oracle(ctx, name, mode):
     pb = synth.synth_ba(**PROBLEMS[name])
     S0, gt0, dc0, it0 = oracle.ba_reduced_system(pb, 0.01, 1e-4, 50, 1e-10)
     g = BAGraph(ctx, pb)
-    if generic:
-        g.force_generic_pcg(True)
-        assert g.pcg_cluster_size() == 0
-    else:
-        assert g.pcg_cluster_size() in (8, 16)  # local-BA sizes must take the one-cluster DSMEM path
+    force_mode(g, mode)
     S, gt, dc, it = g.dbg_reduced(cfg(pcgMaxIterations=50, pcgTolerance=1e-10))
     assert rel(S, S0) < 1e-10 and rel(gt, gt0) < 1e-9
     assert np.abs(S - S.T).max() < 1e-9 * np.abs(S).max()
@@ -72,16 +81,16 @@ def test_reduced_system_and_pcg_match_oracle(ctx, name, generic):
     g.close()
 
 
-@pytest.mark.parametrize("generic", [False, True], ids=["cluster_pcg", "generic_pcg"])
+@pytest.mark.parametrize("mode", list(PCG_MODES))
 @pytest.mark.parametrize("name,iters", [("config1_10cam_200pt", 10), ("tiny", 8), ("local_50kf", 10)])
-def test_solve_matches_oracle_fixed_iterations(ctx, name, iters, generic):
+def test_solve_matches_oracle_fixed_iterations(ctx, name, iters, mode):
     a = synth.synth_ba(**PROBLEMS[name]); b = a.copy()
     kw = dict(max_iterations=iters, function_tolerance=0.0, pcg_max_iters=50, pcg_tol=1e-10)
     r0 = oracle.ba_solve(a, **kw)
     c = cfg(maxIterations=iters, functionTolerance=0.0, pcgMaxIterations=50, pcgTolerance=1e-10)
-    if generic:
+    if mode != "sparse_pcg":
         g = BAGraph(ctx, b)
-        g.force_generic_pcg(True)
+        force_mode(g, mode)
         r1 = g.solve(c)
         b.cam_pose_wc[...], b.points[...] = g.download()
         g.close()
