@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kPtThreads) ba_linearize_points_kernel(BaDev g
     double* W = g.W + 18 * (size_t)e;
     if (!o.valid) {
 #pragma unroll
-      for (int k = 0; k < 18; ++k) W[k] = 0.0;
+      for (int k = 0; k < 9; ++k) reinterpret_cast<double2*>(W)[k] = make_double2(0.0, 0.0);
       continue;
     }
     acc[9] += o.rho;
@@ -88,10 +88,13 @@ __global__ void __launch_bounds__(kPtThreads) ba_linearize_points_kernel(BaDev g
       AJp[3 + d] = o.A1 * Jp[d] + o.A2 * Jp[3 + d];
     }
     const double Ar0 = o.A0 * o.r0 + o.A1 * o.r1, Ar1 = o.A1 * o.r0 + o.A2 * o.r1;
+    double wv[18];
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) W[a * 3 + c] = Jc[a] * AJp[c] + Jc[6 + a] * AJp[3 + c];
+      for (int c = 0; c < 3; ++c) wv[a * 3 + c] = Jc[a] * AJp[c] + Jc[6 + a] * AJp[3 + c];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) reinterpret_cast<double2*>(W)[k] = make_double2(wv[2 * k], wv[2 * k + 1]);  // 144 B = 9 x 16 B
     int t = 0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -126,10 +129,10 @@ __global__ void __launch_bounds__(kCamThreads) ba_linearize_cams_kernel(BaDev g)
 #pragma unroll
   for (int k = 0; k < 27; ++k) acc[k] = 0.0;
   for (int idx = g.cam_off[i] + threadIdx.x; idx < g.cam_off[i + 1]; idx += kCamThreads) {
-    const int e = g.cam_perm[idx];
-    const int j = g.o_pt[e];
-    const double p[3] = {g.pts[3 * j], g.pts[3 * j + 1], g.pts[3 * j + 2]};
-    const ObsLin o = eval_obs(Rt, p, g.o_uv[2 * e], g.o_uv[2 * e + 1], g.has_info ? g.o_info + 3 * e : nullptr, delta);
+    const int j = g.c_pt[idx];
+    const double2 uv = *reinterpret_cast<const double2*>(g.c_uv + 2 * (size_t)idx);
+    const double p[3] = {g.pts[3 * (size_t)j], g.pts[3 * (size_t)j + 1], g.pts[3 * (size_t)j + 2]};
+    const ObsLin o = eval_obs(Rt, p, uv.x, uv.y, g.has_info ? g.o_info + 3 * (size_t)g.cam_perm[idx] : nullptr, delta);
     if (!o.valid) continue;
     double Jc[12], AJc[12];
     jac_cam(o, dm, Jc);
@@ -1261,7 +1264,7 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   const size_t b_pose = al((size_t)nc * 7 * 8), b_pts = al((size_t)np * 3 * 8), b_dof = al(nc), b_pf = al(np),
                b_oc = al((size_t)no * 4), b_op = al((size_t)no * 4), b_uv = al((size_t)no * 16),
                b_info = d.has_info ? al((size_t)no * 24) : 0, b_po = al((size_t)(np + 1) * 4), b_co = al((size_t)(nc + 1) * 4),
-               b_cp = al((size_t)no * 4);
+               b_cp = al((size_t)no * 4), b_cpt = al((size_t)no * 4), b_cuv = al((size_t)no * 16);
   // covisibility block structure of S: block (i,i') is structurally non-zero iff some landmark is seen by both cameras
   std::vector<int> s_rowptr(nc + 1, 0), s_col, s_brow;
   if (nc > 0 && nc <= 1024) {
@@ -1290,7 +1293,7 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   }
   d.s_nupper = (int)s_upper.size();
   const size_t b_sr = al((size_t)(nc + 1) * 4), b_sc = al((size_t)s_col.size() * 4 + 4);
-  const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + b_sr + 4 * b_sc + 256;
+  const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + b_sr + 4 * b_sc + b_cpt + b_cuv + 256;
   const size_t n6 = 6 * (size_t)nc;
   uint8_t* dblob = nullptr;
   auto layout = [&](Slab& sl) {
@@ -1340,7 +1343,7 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   auto take = [&](size_t bytes) { size_t o = off; off += bytes; return o; };
   const size_t o_pose = take(b_pose), o_pts = take(b_pts), o_dof = take(b_dof), o_pf = take(b_pf), o_oc = take(b_oc),
                o_op = take(b_op), o_uv = take(b_uv), o_info = take(b_info), o_po = take(b_po), o_co = take(b_co), o_cp = take(b_cp),
-               o_sr = take(b_sr), o_sc = take(b_sc), o_sb = take(b_sc), o_su = take(b_sc), o_st = take(b_sc);
+               o_sr = take(b_sr), o_sc = take(b_sc), o_sb = take(b_sc), o_su = take(b_sc), o_st = take(b_sc), o_cpt = take(b_cpt), o_cuv = take(b_cuv);
   memcpy(h + o_pose, pb->cam_pose_wc, (size_t)nc * 56);
   memcpy(h + o_pts, pb->points, (size_t)np * 24);
   for (int i = 0; i < nc; ++i) h[o_dof + i] = pb->cam_dof ? (pb->cam_dof[i] & 63) : 63;
@@ -1361,6 +1364,16 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   memcpy(h + o_po, pt_off.data(), (size_t)(np + 1) * 4);
   memcpy(h + o_co, cam_off.data(), (size_t)(nc + 1) * 4);
   memcpy(h + o_cp, cam_perm.data(), (size_t)no * 4);
+  {
+    int* hcpt = (int*)(h + o_cpt);
+    double* hcuv = (double*)(h + o_cuv);
+    for (int idx = 0; idx < no; ++idx) {
+      const int e = cam_perm[idx];
+      hcpt[idx] = hop[e];
+      hcuv[2 * idx] = huv[2 * e];
+      hcuv[2 * idx + 1] = huv[2 * e + 1];
+    }
+  }
   memcpy(h + o_sr, s_rowptr.data(), (size_t)(nc + 1) * 4);
   if (!s_col.empty()) memcpy(h + o_sc, s_col.data(), s_col.size() * 4);
   if (!s_brow.empty()) memcpy(h + o_sb, s_brow.data(), s_brow.size() * 4);
@@ -1374,6 +1387,7 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   d.o_cam = (int*)(dblob + o_oc); d.o_pt = (int*)(dblob + o_op); d.o_uv = (double*)(dblob + o_uv);
   d.o_info = d.has_info ? (double*)(dblob + o_info) : nullptr;
   d.pt_off = (int*)(dblob + o_po); d.cam_off = (int*)(dblob + o_co); d.cam_perm = (int*)(dblob + o_cp);
+  d.c_pt = (int*)(dblob + o_cpt); d.c_uv = (double*)(dblob + o_cuv);
   d.s_rowptr = (int*)(dblob + o_sr); d.s_col = (int*)(dblob + o_sc); d.s_brow = (int*)(dblob + o_sb);
   d.s_upper = (int*)(dblob + o_su); d.s_tidx = (int*)(dblob + o_st);
   if (nc > 0) {
@@ -1480,22 +1494,23 @@ int gb_ba_graph_reduce_local(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   cudaStream_t s = ctx->stream;
   if (d.np > 0) { ba_linearize_points_kernel<<<gb_div_up(d.np * kLpp, kPtThreads), kPtThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
   if (d.nc > 0) { ba_linearize_cams_kernel<<<d.nc, kCamThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
-  const bool blocks = g->pcg_sparse && buf == g->buf;  // local-BA path: deterministic block-gather Schur into the block-CSR
+  // Schur complement.  With the covisibility block structure at hand (<= 1024 cameras) S is formed block by block without
+  // atomics (deterministic); the local-BA solver consumes the block-CSR directly, every other consumer (one-cluster / generic
+  // PCG, the multi-GPU all-reduce) gets it scattered into the dense layout of `buf`.
+  const bool have_blocks = d.s_nnzb > 0 && d.nc > 0;
+  const bool csr_only = have_blocks && g->pcg_sparse && buf == g->buf;
   {
-    const size_t work = std::max<size_t>(blocks ? 0 : (size_t)d.n6 * d.n6, (size_t)d.np);
+    const size_t work = std::max<size_t>(csr_only ? 0 : (size_t)d.n6 * d.n6, (size_t)d.np);
     const int nblk = (int)std::min<size_t>(std::max<size_t>((work + 255) / 256, 1), (size_t)ctx->sm_count * 8);
-    ba_prepare_schur_kernel<<<nblk, 256, 0, s>>>(d, buf, blocks ? 0 : 1); GB_LAUNCH_CHECK(ctx);
+    ba_prepare_schur_kernel<<<nblk, 256, 0, s>>>(d, buf, csr_only ? 0 : 1); GB_LAUNCH_CHECK(ctx);
   }
-  if (d.no > 0 && d.nc > 0) {
-    if (blocks) {
-      ba_schur_blocks_kernel<<<d.s_nupper, 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
-    } else {
-      ba_schur_accum_kernel<<<gb_div_up(d.no, 128), 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
-      const int nblk = (int)std::min<size_t>(((size_t)d.n6 * d.n6 + 255) / 256, (size_t)ctx->sm_count * 8);
-      ba_mirror_kernel<<<nblk, 256, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
-    }
-  } else if (blocks && d.nc > 0) {
+  if (have_blocks) {
     ba_schur_blocks_kernel<<<d.s_nupper, 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+    if (!csr_only) { ba_densify_fill_kernel<<<gb_div_up(d.s_nnzb * 36, 256), 256, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx); }
+  } else if (d.no > 0 && d.nc > 0) {
+    ba_schur_accum_kernel<<<gb_div_up(d.no, 128), 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+    const int nblk = (int)std::min<size_t>(((size_t)d.n6 * d.n6 + 255) / 256, (size_t)ctx->sm_count * 8);
+    ba_mirror_kernel<<<nblk, 256, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
   }
   return GB_OK;
 }
@@ -1713,7 +1728,7 @@ GB_API int gb_dbg_ba_reduced(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* o
   GB_CHECK(gb_ba_graph_step(ctx, g, nullptr, nullptr));
   BaDev& d = g->d;
   const size_t n6 = d.n6;
-  if (g->pcg_sparse && d.nc > 0) {  // the local-BA path keeps S as block-CSR: scatter it into the dense layout for inspection
+  if (g->pcg_sparse && d.s_nnzb > 0 && d.nc > 0) {  // the local-BA path keeps S as block-CSR: scatter it into the dense layout for inspection
     ba_densify_kernel<<<64, 256, 0, ctx->stream>>>(d, g->buf);
     ba_densify_fill_kernel<<<gb_div_up(d.s_nnzb * 36, 256), 256, 0, ctx->stream>>>(d, g->buf);
   }

@@ -29,6 +29,9 @@ struct BaDev {
   const int *o_cam, *o_pt;
   const double *o_uv, *o_info;
   const int *pt_off, *cam_off, *cam_perm;
+  // camera-sorted copies (same order as cam_perm) so that the per-camera pass streams instead of chasing indices
+  const int* c_pt;
+  const double* c_uv;
   // block structure of the reduced camera matrix S (covisibility): CSR over 6x6 blocks, built on the host
   const int *s_rowptr, *s_col, *s_brow;  // s_brow[blk] = block row of blk
   const int *s_upper, *s_tidx;           // list of blocks with col >= row; s_tidx[blk] = index of the transposed block
