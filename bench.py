@@ -285,7 +285,7 @@ def main():
             # dominant HBM-bound kernel of the path = the BA Jacobian sweep (BASELINE metric, 2nd clause), at config-5 size
             "roofline": {"kernel": "BA Jacobian sweep K6 (ba_linearize_points + ba_linearize_cams), 500 cams/100k pts/1M obs",
                          "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": 223.3e6, "traffic_source": "profiles/r01_ncu_summary.md (dram read+write of the two kernels)",
+                         "traffic": 152.1e6, "traffic_source": "profiles/r01_ncu_summary.md (dram read+write of the two kernels, ncu --set full)",
                          "peak_source": peak_src, "algorithmic_bytes": int(big_bytes), "ms_per_sweep": t_sweep_big},
             # the same quantity for the kernels as they run inside the timed step (one frame / one 10k-observation window:
             # launch-latency-bound, reported for completeness)

@@ -55,9 +55,8 @@ __global__ void ba_rt_kernel(int nc, const double* __restrict__ pose, double* __
 // K6a: fused residual + Jacobian sweep, 8 lanes per landmark (lane k takes observations k, k+8, ... of the point-sorted
 // segment), fixed xor-tree over the 8 lanes -> V_j, g_p,j, cost_j; every lane writes the W blocks of its own observations.
 constexpr int kLpp = 8;
-__global__ void __launch_bounds__(kPtThreads) ba_linearize_points_kernel(BaDev g) {
-  if (g.sc->stop || !g.sc->need_linearize) return;
-  const int gt = blockIdx.x * kPtThreads + threadIdx.x;
+__device__ __forceinline__ void ba_linearize_points_body(const BaDev& g, int block) {
+  const int gt = block * kPtThreads + threadIdx.x;
   const int jraw = gt / kLpp, sub = gt % kLpp;
   const bool valid = jraw < g.np;
   const int j = valid ? jraw : 0;
@@ -119,9 +118,7 @@ __global__ void __launch_bounds__(kPtThreads) ba_linearize_points_kernel(BaDev g
 }
 
 // K6b: one CTA per camera; deterministic tree reduction of the 21 upper-triangular U entries + 6 gradient entries
-__global__ void __launch_bounds__(kCamThreads) ba_linearize_cams_kernel(BaDev g) {
-  if (g.sc->stop || !g.sc->need_linearize) return;
-  const int i = blockIdx.x;
+__device__ __forceinline__ void ba_linearize_cams_body(const BaDev& g, int i) {
   const double delta = g.sc->delta;
   const double* Rt = g.Rt + 12 * i;
   const int dm = g.dof[i];
@@ -176,6 +173,20 @@ __global__ void __launch_bounds__(kCamThreads) ba_linearize_cams_kernel(BaDev g)
     g.U[36 * i + threadIdx.x] = s_red[0][t];
   }
   if (threadIdx.x < 6) g.gc[6 * i + threadIdx.x] = s_red[0][21 + threadIdx.x];
+}
+
+// One launch for the whole sweep: the first `pt_blocks` CTAs run the landmark pass (K6a), the remaining CTAs the camera
+// pass (K6b); the two are independent.
+static_assert(kPtThreads == kCamThreads, "the fused sweep launch uses one block size");
+__global__ void __launch_bounds__(kPtThreads) ba_linearize_kernel(BaDev g, int pt_blocks) {
+  if (g.sc->stop || !g.sc->need_linearize) return;
+  if ((int)blockIdx.x < pt_blocks) ba_linearize_points_body(g, blockIdx.x);
+  else ba_linearize_cams_body(g, blockIdx.x - pt_blocks);
+}
+// (the camera pass alone: used for the pose information matrix of optimizePnP)
+__global__ void __launch_bounds__(kCamThreads) ba_linearize_cams_kernel(BaDev g) {
+  if (g.sc->stop || !g.sc->need_linearize) return;
+  ba_linearize_cams_body(g, blockIdx.x);
 }
 
 // out[0] = 0.5 * sum(src[0..n)) — single CTA, deterministic
@@ -684,7 +695,8 @@ template <int THREADS, int MAXB>
 __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, double* __restrict__ buf, int maxit) {
   if (g.sc->stop) return;
   extern __shared__ __align__(16) double sm[];
-  __shared__ double s_red[2][2 * (THREADS / 32)];
+  __shared__ double s_red[2][32];
+  static_assert(THREADS / 32 <= 16, "reduce2 folds at most 16 per-warp partials");
   const int n6 = g.n6, nc = g.nc, nnzb = g.s_nnzb, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long t_start = clock64();
   double* B = sm;                          // [nnzb][36] row-major blocks
@@ -699,19 +711,29 @@ __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, doub
   const double lambda = g.sc->lambda, tol = g.sc->pcg_tol;
   for (int k = tid; k <= nc; k += THREADS) rowptr[k] = g.s_rowptr[k];
   for (int k = tid; k < nnzb; k += THREADS) col[k] = g.s_col[k];
-  // A. copy the block-CSR values of S (written by ba_schur_blocks_kernel) into shared memory; Marquardt damping on the
-  //    diagonal entries (written back so the damped system is observable)
-  for (int w = tid; w < nnzb * 36; w += THREADS) {
-    const int blk = w / 36, k = w - 36 * blk, a = k / 6, b = k - 6 * a;
-    double v = g.Sb[w];
-    if (a == b) {
-      const int i = g.s_brow[blk];
-      if (i == g.s_col[blk]) {
-        v = ((g.dof[i] >> a) & 1) ? v + lambda * clampd(buf[nS + n6 + 6 * i + a]) : 1.0;
-        g.Sb[w] = v;
-      }
+  // A. copy the block-CSR values of S (written by ba_schur_blocks_kernel) into shared memory (8 independent loads in
+  //    flight per thread), then Marquardt damping on the 6N diagonal entries (written back so the damped system is observable)
+  {
+    const int n = nnzb * 36;
+    int w = tid;
+    for (; w + 7 * THREADS < n; w += 8 * THREADS) {
+      double v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = g.Sb[w + k * THREADS];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) B[w + k * THREADS] = v[k];
     }
+    for (; w < n; w += THREADS) B[w] = g.Sb[w];
+  }
+  __syncthreads();
+  if (tid < n6) {
+    const int i = tid / 6, a = tid - 6 * i;
+    int dblk = rowptr[i];
+    while (col[dblk] != i) ++dblk;  // the diagonal block is always present
+    const int w = dblk * 36 + a * 7;
+    const double v = ((g.dof[i] >> a) & 1) ? B[w] + lambda * clampd(buf[nS + n6 + tid]) : 1.0;
     B[w] = v;
+    g.Sb[w] = v;
   }
   __syncthreads();
   // B. block-Jacobi preconditioner
@@ -744,11 +766,13 @@ __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, doub
 #pragma unroll
     for (int k = 0; k < 6; ++k) breg[s * 6 + k] = ok ? B[(size_t)(b0 + s) * 36 + ca * 6 + k] : 0.0;
   }
-  // shared vectors: u (mat-vec input), w = S u, s = S p (double-buffered), r (double-buffered)
+  // shared vectors: u (mat-vec input) and r (so that u = Minv r can read the camera's six entries); p, s, x, w live in
+  // registers (thread d owns element d).  This thread's row of Minv is constant over the solve: registers too.
   double* vu = vp;
-  double* vw = vq;
-  double* vs[2] = {vr, vz};
-  double* vrr[2] = {vz + n6, vz + 2 * (size_t)n6};
+  double* vrs = vq;
+  double mrow[6];
+#pragma unroll
+  for (int b = 0; b < 6; ++b) mrow[b] = own ? Minv[36 * ci + ca * 6 + b] : 0.0;
   // w_d = row d of S times u (registers for the first MAXB blocks, shared-memory copy beyond)
   auto matvec = [&]() -> double {
     double q0 = 0.0, q1 = 0.0, q2 = 0.0;
@@ -772,40 +796,36 @@ __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, doub
     }
     return (q0 + q1) + q2;
   };
-  // deterministic fused reduction of two values with ONE barrier: shuffle trees per warp, then every thread adds the
-  // per-warp partials with the same fixed pairwise tree (identical result in every thread)
+  // deterministic fused reduction of two values, ONE barrier: per-warp shuffle trees, then every warp re-reduces the
+  // (<= 16) per-warp partials with a second fixed shuffle tree (lanes 0..15: gamma partials, lanes 16..31: delta partials)
+  // -> identical result in every thread, one LDS per thread instead of 2 x #warps broadcast loads
   auto reduce2 = [&](double a, double b, int bufi, double* oa, double* ob) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       a += __shfl_down_sync(0xffffffffu, a, o);
       b += __shfl_down_sync(0xffffffffu, b, o);
     }
-    if (lane == 0) { s_red[bufi][2 * warp] = a; s_red[bufi][2 * warp + 1] = b; }
+    if (lane == 0) { s_red[bufi][warp] = a; s_red[bufi][16 + warp] = b; }
     __syncthreads();
-    double pa[THREADS / 32], pb[THREADS / 32];
+    const int wl = lane & 15;
+    double v = (wl < THREADS / 32) ? s_red[bufi][(lane & 16) + wl] : 0.0;
 #pragma unroll
-    for (int w = 0; w < THREADS / 32; ++w) { pa[w] = s_red[bufi][2 * w]; pb[w] = s_red[bufi][2 * w + 1]; }
-#pragma unroll
-    for (int st = 1; st < THREADS / 32; st <<= 1) {
-#pragma unroll
-      for (int w = 0; w + st < THREADS / 32; w += 2 * st) { pa[w] += pa[w + st]; pb[w] += pb[w + st]; }
-    }
-    *oa = pa[0]; *ob = pb[0];
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);  // a+b == b+a: all 16 lanes agree
+    *oa = __shfl_sync(0xffffffffu, v, 0);
+    *ob = __shfl_sync(0xffffffffu, v, 16);
   };
   // ---- Chronopoulos-Gear PCG (same recurrence as oracle/ba_ref.c::ba_pcg) ----
   double xd = 0.0, pd = 0.0, sd = 0.0, rd = 0.0, ud = 0.0, wd = 0.0;
   if (own) {
     rd = buf[nS + tid];
 #pragma unroll
-    for (int b = 0; b < 6; ++b) ud += Minv[36 * ci + ca * 6 + b] * buf[nS + 6 * ci + b];
+    for (int b = 0; b < 6; ++b) ud += mrow[b] * buf[nS + 6 * ci + b];
     vu[tid] = ud;
-    vrr[0][tid] = rd;
-    vs[0][tid] = 0.0;
   }
   __syncthreads();
-  if (own) { wd = matvec(); vw[tid] = wd; }
+  if (own) wd = matvec();
   double gamma, delta;
-  reduce2(rd * ud, wd * ud, 0, &gamma, &delta);  // barrier also publishes vw
+  reduce2(rd * ud, wd * ud, 0, &gamma, &delta);
   const double gamma0 = gamma, tol2 = tol * tol;
   int iters = 0;
   double alpha = 0.0, beta = 0.0;
@@ -815,31 +835,26 @@ __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, doub
   if (g.prof && tid == 0) g.prof[7] = clock64() - t_start;
   for (int it = 0; it < maxit && !done; ++it) {
     SP_STAMP(0);
-    const int cur = it & 1, nxt = cur ^ 1;
-    if (own) {
-      // own element: p, s, x;  the camera's six r entries (and the s they need) are recomputed redundantly so that
-      // u = Minv r needs no barrier
+    if (own) {  // element-wise recurrences, registers only
       pd = ud + beta * pd;
       sd = wd + beta * sd;
       xd += alpha * pd;
-      ud = 0.0;
-#pragma unroll
-      for (int b = 0; b < 6; ++b) {
-        const double sb = vw[6 * ci + b] + beta * vs[cur][6 * ci + b];
-        const double rb = vrr[cur][6 * ci + b] - alpha * sb;
-        if (b == ca) rd = rb;
-        ud += Minv[36 * ci + ca * 6 + b] * rb;
-      }
-      vs[nxt][tid] = sd;
-      vrr[nxt][tid] = rd;
+      rd -= alpha * sd;
+      vrs[tid] = rd;
     }
-    if (own) vu[tid] = ud;  // (last read by the previous mat-vec, which completed before the previous reduction barrier)
+    __syncthreads();  // r published (the previous mat-vec's reads of vu are long done: reduction barrier in between)
+    if (own) {
+      const double2* rc = reinterpret_cast<const double2*>(vrs + 6 * ci);
+      const double2 r01 = rc[0], r23 = rc[1], r45 = rc[2];
+      ud = ((mrow[0] * r01.x + mrow[1] * r01.y) + (mrow[2] * r23.x + mrow[3] * r23.y)) + (mrow[4] * r45.x + mrow[5] * r45.y);
+      vu[tid] = ud;
+    }
     SP_STAMP(1);
-    __syncthreads();  // u published; every read of vw by the updates above is done
-    if (own) { wd = matvec(); vw[tid] = wd; }
+    __syncthreads();  // u published
+    if (own) wd = matvec();
     SP_STAMP(2);
     double gn, dl;
-    reduce2(rd * ud, wd * ud, (it + 1) & 1, &gn, &dl);  // barrier also publishes vw, vs[nxt], vrr[nxt]
+    reduce2(rd * ud, wd * ud, (it + 1) & 1, &gn, &dl);
     SP_STAMP(3);
     ++iters;
     if (!(gn > 0.0) || gn < tol2 * gamma0) break;
@@ -875,6 +890,7 @@ __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, doub
 }
 constexpr int kSpThreads = 512;  // upper bound on 6N for the single-CTA path
 #define BA_SPARSE_SMALL ba_pcg_sparse_kernel<320, 12>
+#define BA_SPARSE_SMALL9 ba_pcg_sparse_kernel<320, 9>
 #define BA_SPARSE_LARGE ba_pcg_sparse_kernel<512, 6>
 
 // ---- K7b (local BA): block-Jacobi PCG inside ONE thread-block cluster ------------------------------------------------------
@@ -1094,6 +1110,7 @@ struct gb_ba_graph {
   // PCG dispatch: single-CTA block-sparse kernel, else one-cluster kernel (pcg_cluster = 8/16), else generic multi-kernel
   bool pcg_sparse = false;
   size_t pcg_sparse_smem = 0;
+  int pcg_max_row_blocks = 0;  // longest block row of S (picks the register-cache depth of the sparse kernel)
   int pcg_cluster = 0;
   size_t pcg_smem = 0;
 };
@@ -1149,8 +1166,9 @@ static void ba_pick_pcg(gb_ctx* ctx, gb_ba_graph* g) {
   const int nc = g->d.nc, n6 = g->d.n6;
   if (nc > 0 && n6 <= kSpThreads && g->d.s_nnzb > 0) {
     const size_t smem = ((size_t)g->d.s_nnzb * 36 + (size_t)nc * 36 + 6 * (size_t)n6) * sizeof(double) + ((size_t)nc + 1 + g->d.s_nnzb) * sizeof(int) + 64;
-    const cudaError_t ea = n6 <= 320 ? cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                     : cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ea = n6 <= 320 ? cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                               : cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ea == cudaSuccess && n6 <= 320) ea = cudaFuncSetAttribute(BA_SPARSE_SMALL9, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (smem <= (size_t)ctx->max_smem_optin && ea == cudaSuccess) {
       g->pcg_sparse = true;
       g->pcg_sparse_smem = smem;
@@ -1292,6 +1310,7 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
     s_tidx[blk] = t;
   }
   d.s_nupper = (int)s_upper.size();
+  for (int i = 0; i < nc && !s_col.empty(); ++i) g->pcg_max_row_blocks = std::max(g->pcg_max_row_blocks, s_rowptr[i + 1] - s_rowptr[i]);
   const size_t b_sr = al((size_t)(nc + 1) * 4), b_sc = al((size_t)s_col.size() * 4 + 4);
   const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + b_sr + 4 * b_sc + b_cpt + b_cuv + 256;
   const size_t n6 = 6 * (size_t)nc;
@@ -1481,8 +1500,8 @@ int gb_ba_graph_sweep(gb_ctx* ctx, gb_ba_graph* g, double huber_delta) {
   o.huber_delta = huber_delta;
   GB_CHECK(gb_ba_graph_begin(ctx, g, &o));
   BaDev& d = g->d;
-  if (d.np > 0) { ba_linearize_points_kernel<<<gb_div_up(d.np * kLpp, kPtThreads), kPtThreads, 0, ctx->stream>>>(d); GB_LAUNCH_CHECK(ctx); }
-  if (d.nc > 0) { ba_linearize_cams_kernel<<<d.nc, kCamThreads, 0, ctx->stream>>>(d); GB_LAUNCH_CHECK(ctx); }
+  const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads);
+  if (pt_blocks + d.nc > 0) { ba_linearize_kernel<<<pt_blocks + d.nc, kPtThreads, 0, ctx->stream>>>(d, pt_blocks); GB_LAUNCH_CHECK(ctx); }
   return GB_OK;
 }
 
@@ -1492,8 +1511,10 @@ int gb_ba_graph_reduce_local(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   BaDev& d = g->d;
   if (!buf) buf = g->buf;
   cudaStream_t s = ctx->stream;
-  if (d.np > 0) { ba_linearize_points_kernel<<<gb_div_up(d.np * kLpp, kPtThreads), kPtThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
-  if (d.nc > 0) { ba_linearize_cams_kernel<<<d.nc, kCamThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
+  {
+    const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads);
+    if (pt_blocks + d.nc > 0) { ba_linearize_kernel<<<pt_blocks + d.nc, kPtThreads, 0, s>>>(d, pt_blocks); GB_LAUNCH_CHECK(ctx); }
+  }
   // Schur complement.  With the covisibility block structure at hand (<= 1024 cameras) S is formed block by block without
   // atomics (deterministic); the local-BA solver consumes the block-CSR directly, every other consumer (one-cluster / generic
   // PCG, the multi-GPU all-reduce) gets it scattered into the dense layout of `buf`.
@@ -1520,7 +1541,10 @@ static int ba_step_core(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   cudaStream_t s = ctx->stream;
   if (d.nc > 0) {
     if (g->pcg_sparse && buf == g->buf) {
-      if (d.n6 <= 320) {
+      if (d.n6 <= 320 && g->pcg_max_row_blocks <= 9) {
+        GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_SMALL9, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
+        BA_SPARSE_SMALL9<<<1, 320, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
+      } else if (d.n6 <= 320) {
         GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
         BA_SPARSE_SMALL<<<1, 320, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
       } else {
