@@ -114,6 +114,22 @@ __device__ __forceinline__ void ba_linearize_points_body(const BaDev& g, int blo
     V[6] = acc[2]; V[7] = acc[4]; V[8] = acc[5];
     g.gp[3 * (size_t)j] = acc[6]; g.gp[3 * (size_t)j + 1] = acc[7]; g.gp[3 * (size_t)j + 2] = acc[8];
     g.cost_pt[j] = acc[9];
+    // damped inverse right away (ba_prepare_schur_kernel redoes it only when a rejected step changed lambda)
+    const double lambda = g.sc->lambda;
+    double Vi[9];
+    const bool active = pf && e1 > e0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Vi[k] = active ? V[k] : 0.0;
+    if (active) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) Vi[a * 4] += lambda * clampd(Vi[a * 4]);
+      if (!spd_inverse<3>(Vi)) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) Vi[k] = 0.0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g.Vinv[9 * (size_t)j + k] = Vi[k];
   }
 }
 
@@ -578,7 +594,8 @@ __global__ void __launch_bounds__(256) ba_prepare_schur_kernel(BaDev g, double* 
     buf[nS + n6 + d] = g.U[36 * (d / 6) + (d % 6) * 7];
   }
   const double lambda = g.sc->lambda;
-  for (size_t j = t0; j < (size_t)g.np; j += stride) {
+  const bool fresh = g.sc->need_linearize != 0;  // the sweep of this iteration already produced Vinv with this lambda
+  for (size_t j = t0; !fresh && j < (size_t)g.np; j += stride) {
     double Vi[9];
     const bool active = g.pfree[j] != 0 && g.pt_off[j + 1] > g.pt_off[j];
 #pragma unroll
@@ -828,9 +845,9 @@ __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, doub
   reduce2(rd * ud, wd * ud, 0, &gamma, &delta);
   const double gamma0 = gamma, tol2 = tol * tol;
   int iters = 0;
-  double alpha = 0.0, beta = 0.0;
+  double alpha = 0.0, beta = 0.0, inv_alpha = 0.0, inv_gamma = 0.0;
   bool done = !(gamma0 > 0.0) || !(delta > 0.0);
-  if (!done) alpha = gamma / delta;
+  if (!done) { alpha = gamma / delta; inv_alpha = delta / gamma; inv_gamma = 1.0 / gamma; }
 #define SP_STAMP(k) do { if (g.prof && tid == 0 && it == 3) g.prof[k] = clock64(); } while (0)
   if (g.prof && tid == 0) g.prof[7] = clock64() - t_start;
   for (int it = 0; it < maxit && !done; ++it) {
@@ -858,11 +875,14 @@ __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, doub
     SP_STAMP(3);
     ++iters;
     if (!(gn > 0.0) || gn < tol2 * gamma0) break;
-    beta = gn / gamma;
-    const double den = dl - beta * gn / alpha;
+    // beta = gn/gamma, alpha = gn/(dl - beta*gn/alpha_prev) with the reciprocals of gamma and alpha carried along: the three
+    // divisions below are independent (one DDIV latency instead of two in a row)
+    beta = gn * inv_gamma;
+    const double den = dl - beta * (gn * inv_alpha);
     if (!(den > 0.0)) break;
     alpha = gn / den;
-    gamma = gn;
+    inv_alpha = den / gn;
+    inv_gamma = 1.0 / gn;
     SP_STAMP(4);
   }
   if (g.prof && tid == 0) g.prof[6] = clock64();

@@ -251,28 +251,36 @@ __device__ __forceinline__ float harris_response(const uint8_t* __restrict__ img
   return __fmul_rn(v, s4);
 }
 
-// FAST-score threshold of level l: the (2 n_l)-th largest score (ties kept); 0 keeps everything; 256 keeps nothing
-__device__ __forceinline__ int fast_keep_threshold(const int* __restrict__ hist_l, int quota) {
-  const int want = 2 * quota;
-  if (want <= 0) return 256;
-  int cum = 0;
-  for (int s = 255; s >= 1; --s) {
-    cum += hist_l[s];
-    if (cum >= want) return s;
-  }
-  return 0;
-}
-
 __global__ void __launch_bounds__(256) orb_harris_kernel(const __grid_constant__ OrbParams P, const uint8_t* __restrict__ pyr,
                                                          const uint32_t* __restrict__ cand_pos, const uint8_t* __restrict__ cand_score,
                                                          const int* __restrict__ counts, const int* __restrict__ hist,
                                                          uint32_t* __restrict__ surv_key, float* __restrict__ surv_resp,
                                                          uint32_t* __restrict__ surv_pos, int* __restrict__ surv_count) {
+  // FAST-score threshold of this level = the (2 n_l)-th largest score (ties kept): suffix sums of the 256-bin histogram,
+  // one bin per thread (blockDim.x == 256), thr = number of scores s whose suffix count  #{score >= s}  reaches 2 n_l
+  __shared__ int s_suffix[256];
   __shared__ int s_thr;
   const int l = blockIdx.y;
   const LevelInfo& L = P.lv[l];
-  if (threadIdx.x == 0) s_thr = fast_keep_threshold(hist + l * 256, L.quota);
-  __syncthreads();
+  {
+    const int t = threadIdx.x;
+    int v = t >= 1 ? hist[l * 256 + t] : 0;
+    s_suffix[t] = v;
+    if (t == 0) s_thr = 0;
+    __syncthreads();
+    // inclusive suffix scan (Hillis-Steele, 8 steps)
+    for (int off = 1; off < 256; off <<= 1) {
+      const int add = (t + off < 256) ? s_suffix[t + off] : 0;
+      __syncthreads();
+      s_suffix[t] += add;
+      __syncthreads();
+    }
+    const int want = 2 * L.quota;
+    // suffix counts are non-increasing in s: the threshold is the LARGEST s >= 1 with suffix[s] >= want (0 if none)
+    if (want > 0 && t >= 1 && s_suffix[t] >= want && (t == 255 || s_suffix[t + 1] < want)) s_thr = t;
+    if (want <= 0 && t == 0) s_thr = 256;
+    __syncthreads();
+  }
   const int thr = s_thr;
   const int n = min(counts[l], L.cand_cap);
   const uint8_t* img = pyr + L.off;
@@ -425,7 +433,7 @@ __device__ __forceinline__ void det_sincos(double x, double* sn, double* cs) {
   }
 }
 
-constexpr int kPatch = 45, kPatchPitch = 48, kPR = 22;  // raw patch: rows/cols -22..22
+constexpr int kPatch = 45, kPatchWords = 13, kPatchPitch = 52, kPR = 22;  // raw patch: rows/cols -22..22 (13 aligned words per row)
 constexpr int kBl = 39, kBlPitch = 40, kBR = 19;        // blurred patch: -19..19
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
@@ -465,17 +473,23 @@ __global__ void __launch_bounds__(kDescWarps * 32) orb_describe_kernel(const __g
   const uint32_t pos = kept_pos[l * kSelMax + (g - base)];
   const int x = pos & 0xffff, y = pos >> 16;
   const uint8_t* img = pyr + L.off;
-  // raw 45x45 patch (always inside the level: border >= 22)
-  for (int i = lane; i < kPatch * kPatch; i += 32) {
-    const int r = i / kPatch, c = i % kPatch;
-    sm->patch[r * kPatchPitch + c] = __ldg(img + (size_t)(y - kPR + r) * L.pitch + (x - kPR + c));
+  // raw 45x45 patch (always inside the level: border >= 22), staged with aligned 32-bit loads: 12 (or 13) words cover the 45
+  // columns starting at the 4-byte boundary below x-22; `sh` is the byte offset of column x-22 inside the staged row
+  const int xa = (x - kPR) & ~3, sh = (x - kPR) - xa;
+  for (int i = lane; i < kPatch * kPatchWords; i += 32) {
+    const int r = i / kPatchWords, wq = i - r * kPatchWords;
+    const int gx = xa + 4 * wq;
+    uint32_t v = 0;
+    if (gx + 3 < L.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)(y - kPR + r) * L.pitch + gx));
+    *reinterpret_cast<uint32_t*>(&sm->patch[r * kPatchPitch + 4 * wq]) = v;
   }
   __syncwarp();
+  const uint8_t* patch = sm->patch + sh;  // patch[r * kPatchPitch + c] == level(y-22+r, x-22+c)
   // intensity-centroid orientation over the radius-15 disc: lane = row v+15
   int m01 = 0, m10 = 0;
   if (lane < 31) {
     const int v = lane - 15, d = c_umax[v < 0 ? -v : v];
-    const uint8_t* row = &sm->patch[(kPR + v) * kPatchPitch + kPR];
+    const uint8_t* row = &patch[(kPR + v) * kPatchPitch + kPR];
     int rs = 0, ru = 0;
     for (int u = -d; u <= d; ++u) { const int val = row[u]; rs += val; ru += u * val; }
     m01 = v * rs; m10 = ru;
@@ -487,7 +501,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) orb_describe_kernel(const __g
   const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu), k2 = __uint_as_float(0x3e434a39u), k3 = __uint_as_float(0x3e5d4ae0u);
   for (int i = lane; i < kPatch * kBl; i += 32) {
     const int r = i / kBl, c = i % kBl;  // output col c <-> patch cols c..c+6
-    const uint8_t* p = &sm->patch[r * kPatchPitch + c];
+    const uint8_t* p = &patch[r * kPatchPitch + c];
     float s = __fmul_rn(k0, (float)p[0]);
     s = __fmaf_rn((float)p[1], k1, s);
     s = __fmaf_rn((float)p[2], k2, s);
