@@ -661,6 +661,125 @@ __global__ void __launch_bounds__(128) ba_backsub_cost_kernel(BaDev g) {
   }
 }
 
+// Local-BA tail in ONE launch: back-substitution + candidate cost (8 lanes per landmark), then the LAST CTA to finish
+// (atomic ticket) reduces both costs in a fixed order, takes the LM accept/reject decision, and either installs the candidate
+// (accept) or refreshes the damped V^-1 with the new lambda (reject: the next iteration skips the sweep).  Replaces
+// ba_prepare_schur + ba_backsub_cost + ba_commit_fused on the block-CSR path.
+constexpr int kTailThreads = 256;
+// CTA-wide copy of n doubles (16-byte accesses; both pointers are slab-aligned)
+__device__ __forceinline__ void cta_copy_f64(double* __restrict__ dst, const double* __restrict__ src, int n, int nthreads) {
+  const int n2 = n >> 1;
+  for (int t = threadIdx.x; t < n2; t += nthreads) reinterpret_cast<double2*>(dst)[t] = __ldcg(reinterpret_cast<const double2*>(src) + t);
+  if ((n & 1) && threadIdx.x == 0) dst[n - 1] = __ldcg(src + n - 1);
+}
+
+__global__ void __launch_bounds__(kTailThreads) ba_backsub_commit_kernel(BaDev g, const double* __restrict__ buf) {
+  BaScalars* sc = g.sc;
+  if (sc->stop) return;
+  __shared__ double s_part[kTailThreads / 32 + 1];
+  __shared__ int s_flag;
+  {  // ---- part 1: identical to ba_backsub_cost_kernel
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int jraw = gt / kLpp, sub = gt % kLpp;
+    const bool valid = jraw < g.np;
+    const int j = valid ? jraw : 0;
+    const double delta = sc->delta;
+    const int e0 = g.pt_off[j], e1 = valid ? g.pt_off[j + 1] : e0;
+    double b[3] = {0.0, 0.0, 0.0};
+    for (int e = e0 + sub; e < e1; e += kLpp) {
+      const int i = g.o_cam[e];
+      const double* W = g.W + 18 * (size_t)e;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int a = 0; a < 6; ++a) b[c] -= W[a * 3 + c] * g.x[6 * i + a];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int o = kLpp / 2; o > 0; o >>= 1) b[c] += __shfl_xor_sync(0xffffffffu, b[c], o, kLpp);
+      b[c] += g.gp[3 * (size_t)j + c];
+    }
+    const double* Vi = g.Vinv + 9 * (size_t)j;
+    double p[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) p[a] = g.pts[3 * (size_t)j + a] + Vi[a * 3] * b[0] + Vi[a * 3 + 1] * b[1] + Vi[a * 3 + 2] * b[2];
+    double cost = 0.0;
+    for (int e = e0 + sub; e < e1; e += kLpp) {
+      const ObsLin o = eval_obs(g.Rt_new + 12 * g.o_cam[e], p, g.o_uv[2 * e], g.o_uv[2 * e + 1], g.has_info ? g.o_info + 3 * e : nullptr, delta);
+      cost += o.rho;
+    }
+#pragma unroll
+    for (int o = kLpp / 2; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o, kLpp);
+    if (valid && sub == 0) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) g.pts_new[3 * (size_t)j + a] = p[a];
+      g.cost_pt_new[j] = cost;
+    }
+  }
+  // ---- part 2: last CTA done
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_flag = (atomicAdd(&sc->ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+  double v0 = 0.0, v1 = 0.0;
+  for (int k = threadIdx.x; k < g.np; k += kTailThreads) {
+    v0 += __ldcg(&g.cost_pt[k]);
+    v1 += __ldcg(&g.cost_pt_new[k]);
+  }
+  const double cost = 0.5 * block_sum<kTailThreads>(v0, s_part);
+  const double cnew = 0.5 * block_sum<kTailThreads>(v1, s_part);
+  if (threadIdx.x == 0) {
+    sc->ticket = 0;
+    if (sc->iterations == 0) sc->initial_cost = cost;
+    sc->cost = cost;
+    sc->cost_new = cnew;
+    sc->iterations++;
+    const bool ok = (cnew < cost) && isfinite(cnew);
+    sc->need_linearize = ok ? 1 : 0;
+    if (ok) {
+      const double rel = (cost - cnew) / cost;
+      sc->cost = cnew;
+      const double l = sc->lambda / 3.0;
+      sc->lambda = l < 1e-15 ? 1e-15 : l;
+      sc->nu = 2.0;
+      sc->accepted++;
+      if (rel < sc->ftol) { sc->stop = 1; sc->status = 1; }
+    } else {
+      sc->lambda *= sc->nu;
+      sc->nu *= 2.0;
+      if (sc->lambda > 1e16) { sc->stop = 1; sc->status = 2; }
+    }
+    s_flag = ok ? 2 : 1;
+  }
+  __syncthreads();
+  if (s_flag == 2) {  // accept: estimate <- candidate
+    cta_copy_f64(g.pts, g.pts_new, g.np * 3, kTailThreads);
+    cta_copy_f64(g.Rt, g.Rt_new, g.nc * 12, kTailThreads);
+    cta_copy_f64(g.pose, g.pose_new, g.nc * 7, kTailThreads);
+  } else {  // reject: same linearisation, new lambda -> refresh the damped landmark inverses
+    const double lambda = sc->lambda;
+    for (int j = threadIdx.x; j < g.np; j += kTailThreads) {
+      double Vi[9];
+      const bool active = g.pfree[j] != 0 && g.pt_off[j + 1] > g.pt_off[j];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) Vi[k] = active ? g.V[9 * (size_t)j + k] : 0.0;
+      if (active) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) Vi[a * 4] += lambda * clampd(Vi[a * 4]);
+        if (!spd_inverse<3>(Vi)) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) Vi[k] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) g.Vinv[9 * (size_t)j + k] = Vi[k];
+    }
+  }
+}
+
 // single CTA: reduce the candidate cost, LM accept/reject, apply.  (small problems; the stepwise path keeps them apart)
 __global__ void __launch_bounds__(kRedThreads) ba_commit_fused_kernel(BaDev g, const double* __restrict__ buf) {
   BaScalars* sc = g.sc;
@@ -1556,28 +1675,34 @@ int gb_ba_graph_reduce_local(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   return GB_OK;
 }
 
+static int ba_pcg_dispatch(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
+  BaDev& d = g->d;
+  cudaStream_t s = ctx->stream;
+  if (d.nc <= 0) return GB_OK;
+  if (g->pcg_sparse && buf == g->buf) {
+    if (d.n6 <= 320 && g->pcg_max_row_blocks <= 9) {
+      GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_SMALL9, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
+      BA_SPARSE_SMALL9<<<1, 320, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
+    } else if (d.n6 <= 320) {
+      GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
+      BA_SPARSE_SMALL<<<1, 320, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
+    } else {
+      GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
+      BA_SPARSE_LARGE<<<1, 512, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
+    }
+    GB_LAUNCH_CHECK(ctx);
+  } else if (g->pcg_cluster > 0) {
+    GB_CHECK(ba_pcg_cluster(ctx, g, buf));
+  } else {
+    GB_CHECK(ba_pcg_generic(ctx, g, buf));
+  }
+  return GB_OK;
+}
+
 static int ba_step_core(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   BaDev& d = g->d;
   cudaStream_t s = ctx->stream;
-  if (d.nc > 0) {
-    if (g->pcg_sparse && buf == g->buf) {
-      if (d.n6 <= 320 && g->pcg_max_row_blocks <= 9) {
-        GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_SMALL9, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
-        BA_SPARSE_SMALL9<<<1, 320, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
-      } else if (d.n6 <= 320) {
-        GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
-        BA_SPARSE_SMALL<<<1, 320, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
-      } else {
-        GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
-        BA_SPARSE_LARGE<<<1, 512, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
-      }
-      GB_LAUNCH_CHECK(ctx);
-    } else if (g->pcg_cluster > 0) {
-      GB_CHECK(ba_pcg_cluster(ctx, g, buf));
-    } else {
-      GB_CHECK(ba_pcg_generic(ctx, g, buf));
-    }
-  }
+  GB_CHECK(ba_pcg_dispatch(ctx, g, buf));
   if (d.np > 0) { ba_backsub_cost_kernel<<<gb_div_up(d.np * kLpp, 128), 128, 0, s>>>(d); GB_LAUNCH_CHECK(ctx); }
   return GB_OK;
 }
@@ -1642,7 +1767,18 @@ int gb_ba_graph_solve(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, gb_
   const bool poll = g->opt.function_tolerance > 0.0 || g->opt.verbose;
   // one fused commit kernel while the estimate fits a single CTA's copy loop; the stepwise kernels otherwise
   const bool fused_commit = (size_t)g->d.np * 3 + (size_t)g->d.nc * 19 <= (size_t)1 << 16;
+  // local-BA fast path (block-CSR Schur + single-CTA PCG): 4 launches per LM iteration
+  const bool local4 = fused_commit && g->pcg_sparse && g->d.s_nnzb > 0 && g->d.nc > 0 && g->d.np > 0;
   for (int it = 0; it < g->opt.max_iterations; ++it) {
+    if (local4) {
+      BaDev& d = g->d;
+      cudaStream_t s = ctx->stream;
+      const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads);
+      ba_linearize_kernel<<<pt_blocks + d.nc, kPtThreads, 0, s>>>(d, pt_blocks); GB_LAUNCH_CHECK(ctx);
+      ba_schur_blocks_kernel<<<d.s_nupper, 128, 0, s>>>(d, g->buf); GB_LAUNCH_CHECK(ctx);
+      GB_CHECK(ba_pcg_dispatch(ctx, g, g->buf));
+      ba_backsub_commit_kernel<<<gb_div_up(d.np * kLpp, kTailThreads), kTailThreads, 0, s>>>(d, g->buf); GB_LAUNCH_CHECK(ctx);
+    } else {
     GB_CHECK(gb_ba_graph_reduce_local(ctx, g, nullptr));
     if (fused_commit) {
       GB_CHECK(ba_step_core(ctx, g, g->buf));
@@ -1650,6 +1786,7 @@ int gb_ba_graph_solve(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, gb_
     } else {
       GB_CHECK(gb_ba_graph_step(ctx, g, nullptr, nullptr));
       GB_CHECK(gb_ba_graph_commit(ctx, g, nullptr, nullptr));
+    }
     }
     if (poll) {
       BaScalars h;

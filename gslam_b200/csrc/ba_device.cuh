@@ -17,6 +17,7 @@ struct BaScalars {
   double rz, rz0, pcg_alpha, pcg_beta;
   int pcg_first, pcg_k;
   int need_linearize, stop, status, iterations, accepted, accept_flag;
+  unsigned int ticket;  // last-CTA-done counter of the fused back-substitution + commit kernel
   int pcg_iters, pcg_done;
 };
 

@@ -104,6 +104,27 @@ def test_solve_matches_oracle_fixed_iterations(ctx, name, iters, mode):
     assert rel(b.points, a.points) < RTOL
 
 
+@pytest.mark.parametrize("mode", list(PCG_MODES))
+def test_rejected_steps_follow_the_oracle(ctx, mode):
+    """A badly perturbed start makes LM reject steps: lambda grows, the linearisation is reused, only V^-1 / S are redone.
+    (PCG is run to convergence: a truncated solve far from the optimum amplifies rounding differences.)"""
+    a = synth.synth_ba(n_cams=12, n_points=150, obs_per_point=4, n_fixed=2, seed=1, pose_sigma_t=1.0, pose_sigma_deg=10,
+                       point_sigma=2.0)
+    b = a.copy()
+    r0 = oracle.ba_solve(a, max_iterations=12, function_tolerance=0.0, pcg_max_iters=400, pcg_tol=1e-13)
+    assert r0.accepted <= r0.iterations - 3  # the case is only meaningful with rejections
+    g = BAGraph(ctx, b)
+    if mode != "sparse_pcg":
+        force_mode(g, mode)
+    r1 = g.solve(cfg(maxIterations=12, functionTolerance=0.0, pcgMaxIterations=400, pcgTolerance=1e-13))
+    b.cam_pose_wc[...], b.points[...] = g.download()
+    g.close()
+    assert r1.iterations == r0.iterations and r1.accepted == r0.accepted
+    assert abs(r1.final_cost - r0.final_cost) / r0.final_cost < RTOL
+    assert abs(r1.lambda_final - r0.lambda_final) <= 1e-12 * r0.lambda_final
+    pose_close(b.cam_pose_wc, a.cam_pose_wc, RTOL)
+
+
 def test_golden_optimum_scipy(ctx):
     pb = BAProblem(cam_pose_wc=G["cam_pose_wc"].copy(), cam_dof=G["cam_dof"].copy(), points=G["points"].copy(),
                    point_free=G["point_free"].copy(), obs_cam=G["obs_cam"].copy(), obs_point=G["obs_point"].copy(),
