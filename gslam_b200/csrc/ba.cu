@@ -822,22 +822,27 @@ __global__ void __launch_bounds__(kRedThreads) ba_commit_fused_kernel(BaDev g, c
 
 // ---- K7b (local BA, sparse covisibility): block-Jacobi PCG in ONE CTA -------------------------------------------------------
 // When the structurally non-zero 6x6 blocks of the reduced camera matrix fit one SM (sequential-SLAM windows: a band of
-// co-visible keyframes) the whole solve needs no inter-CTA exchange.  Thread d owns row d of S and element d of every CG
-// vector.  One SM's shared-memory port (128 B/clk) would bound a mat-vec that re-reads the blocks every iteration
-// (130 KB -> >1000 clk), so each thread keeps the first kMaxB blocks of ITS row in registers for the whole solve (the shared
-// copy serves rows with more blocks); per iteration only p is read from shared memory (broadcast across the 6 rows of a
-// camera).  An iteration = register mat-vec, two single-barrier deterministic reductions, fused r/z/p updates.
-template <int THREADS, int MAXB>
-__global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, double* __restrict__ buf, int maxit) {
+// co-visible keyframes) the whole solve needs no inter-CTA exchange.
+// Layout: EIGHT lanes per camera (one warp = four cameras).  A block row of S (nb blocks = 6*nb columns) is split BY COLUMN
+// over the eight lanes: lane l keeps columns l, l+8, ... (six coefficients each) in registers for the whole solve, so a
+// mat-vec needs ONE shared-memory read of u per column instead of one per (row, column) -- the shared-memory port
+// (128 B/clk, requested bytes count even when lanes broadcast) was what bounded the row-per-thread version (1076 -> ~450 clk).
+// The eight lanes then hold six partial sums each; a 3-stage transposing butterfly (6 exchanges) leaves row r of the camera
+// in lane {0,1,2,-,3,4,5,-}[l] (lanes 3 and 7 duplicate rows 2 and 5).  Those six lanes own element 6i+r of every CG vector;
+// u = Minv r gathers the camera's six residuals with shuffles (no shared-memory round trip, no barrier).
+// An iteration = element-wise recurrences, u = Minv r, ONE barrier (u published), register mat-vec, ONE fused deterministic
+// reduction (second barrier), scalar recurrences.
+template <int THREADS, int KC>
+__global__ void __maxnreg__(((65536 / THREADS) / 8) * 8) ba_pcg_sparse_kernel(BaDev g, double* __restrict__ buf, int maxit) {
   if (g.sc->stop) return;
   extern __shared__ __align__(16) double sm[];
-  __shared__ double s_red[2][32];
-  static_assert(THREADS / 32 <= 16, "reduce2 folds at most 16 per-warp partials");
+  __shared__ double s_red[2][64];
+  constexpr int NW = THREADS / 32;
   const int n6 = g.n6, nc = g.nc, nnzb = g.s_nnzb, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long t_start = clock64();
   double* B = sm;                          // [nnzb][36] row-major blocks
   double* Minv = B + (size_t)nnzb * 36;    // [nc][36]
-  double* vp = Minv + (size_t)nc * 36;     // six vectors of n6: u, w, s[2], r[2]
+  double* vp = Minv + (size_t)nc * 36;     // vectors of n6: u (mat-vec input), x (for the retraction)
   double* vq = vp + n6;
   double* vr = vq + n6;
   double* vz = vr + n6;
@@ -862,12 +867,12 @@ __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, doub
     for (; w < n; w += THREADS) B[w] = g.Sb[w];
   }
   __syncthreads();
-  if (tid < n6) {
-    const int i = tid / 6, a = tid - 6 * i;
+  for (int d = tid; d < n6; d += THREADS) {
+    const int i = d / 6, a = d - 6 * i;
     int dblk = rowptr[i];
     while (col[dblk] != i) ++dblk;  // the diagonal block is always present
     const int w = dblk * 36 + a * 7;
-    const double v = ((g.dof[i] >> a) & 1) ? B[w] + lambda * clampd(buf[nS + n6 + tid]) : 1.0;
+    const double v = ((g.dof[i] >> a) & 1) ? B[w] + lambda * clampd(buf[nS + n6 + d]) : 1.0;
     B[w] = v;
     g.Sb[w] = v;
   }
@@ -889,79 +894,101 @@ __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, doub
     for (int k = 0; k < 36; ++k) Minv[36 * i + k] = M[k];
   }
   __syncthreads();  // Minv complete
-  const bool own = tid < n6;
-  const int ci = own ? tid / 6 : 0, ca = own ? tid - 6 * ci : 0;
-  const int b0 = own ? rowptr[ci] : 0, b1 = own ? rowptr[ci + 1] : 0;
-  // this thread's row of S: first MAXB blocks in registers (empty slots: zero block pointing at the camera's own segment)
-  double breg[MAXB * 6];
-  int creg[MAXB];
+  // ---- thread roles
+  const int ci_raw = tid >> 3, l8 = tid & 7;
+  const bool cam_ok = ci_raw < nc;
+  const int ci = cam_ok ? ci_raw : 0;
+  const int row = (l8 >> 2) * 3 + ((l8 & 3) < 2 ? (l8 & 3) : 2);  // which row of the camera this lane ends up with
+  const bool own = cam_ok && (l8 & 3) != 3;                       // lanes 3 / 7 duplicate rows 2 / 5
+  const int d = 6 * ci + row;
+  const int b0 = cam_ok ? rowptr[ci] : 0, b1 = cam_ok ? rowptr[ci + 1] : 0;
+  const int ncols = 6 * (b1 - b0);
+  // this lane's columns of the block row: coefficients in registers (absent columns: zeros, reading the camera's own u)
+  double cf[KC][6];
+  int pidx[KC];
 #pragma unroll
-  for (int s = 0; s < MAXB; ++s) {
-    const bool ok = b0 + s < b1;
-    creg[s] = ok ? col[b0 + s] : ci;
+  for (int k = 0; k < KC; ++k) {
+    const int c = l8 + 8 * k;
+    const bool ok = c < ncols;
+    const int sblk = ok ? b0 + c / 6 : 0, a = ok ? c % 6 : 0;
+    pidx[k] = ok ? 6 * col[sblk] + a : 6 * ci;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) breg[s * 6 + k] = ok ? B[(size_t)(b0 + s) * 36 + ca * 6 + k] : 0.0;
+    for (int r = 0; r < 6; ++r) cf[k][r] = ok ? B[(size_t)sblk * 36 + r * 6 + a] : 0.0;
   }
-  // shared vectors: u (mat-vec input) and r (so that u = Minv r can read the camera's six entries); p, s, x, w live in
-  // registers (thread d owns element d).  This thread's row of Minv is constant over the solve: registers too.
   double* vu = vp;
-  double* vrs = vq;
-  double mrow[6];
+  double mrow[6];  // this lane's row of the camera's Minv block (constant over the solve)
 #pragma unroll
-  for (int b = 0; b < 6; ++b) mrow[b] = own ? Minv[36 * ci + ca * 6 + b] : 0.0;
-  // w_d = row d of S times u (registers for the first MAXB blocks, shared-memory copy beyond)
+  for (int b = 0; b < 6; ++b) mrow[b] = cam_ok ? Minv[36 * ci + row * 6 + b] : 0.0;
+  // w_d = row d of S times u
   auto matvec = [&]() -> double {
-    double q0 = 0.0, q1 = 0.0, q2 = 0.0;
-    double2 pv[MAXB][3];
+    double pv[KC];
 #pragma unroll
-    for (int s = 0; s < MAXB; ++s) {
-      const double2* pc = reinterpret_cast<const double2*>(vu + 6 * creg[s]);
-      pv[s][0] = pc[0]; pv[s][1] = pc[1]; pv[s][2] = pc[2];
-    }
+    for (int k = 0; k < KC; ++k) pv[k] = vu[pidx[k]];
+    double y[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int s = 0; s < MAXB; ++s) {
-      q0 += breg[s * 6 + 0] * pv[s][0].x; q1 += breg[s * 6 + 1] * pv[s][0].y;
-      q2 += breg[s * 6 + 2] * pv[s][1].x; q0 += breg[s * 6 + 3] * pv[s][1].y;
-      q1 += breg[s * 6 + 4] * pv[s][2].x; q2 += breg[s * 6 + 5] * pv[s][2].y;
+    for (int k = 0; k < KC; ++k)
+#pragma unroll
+      for (int r = 0; r < 6; ++r) y[r] += cf[k][r] * pv[k];
+    for (int c = l8 + 8 * KC; c < ncols; c += 8) {  // block rows longer than the register cache: shared-memory copy
+      const int sblk = b0 + c / 6, a = c % 6;
+      const double pc = vu[6 * col[sblk] + a];
+      const double* Bc = B + (size_t)sblk * 36 + a;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) y[r] += Bc[r * 6] * pc;
     }
-    for (int blk = b0 + MAXB; blk < b1; ++blk) {
-      const double* Brow = B + (size_t)blk * 36 + ca * 6;
-      const double* pc = vu + 6 * col[blk];
-      q0 += Brow[0] * pc[0]; q1 += Brow[1] * pc[1]; q2 += Brow[2] * pc[2];
-      q0 += Brow[3] * pc[3]; q1 += Brow[4] * pc[4]; q2 += Brow[5] * pc[5];
+    // transposing butterfly over the 8 lanes of the camera: rows {0,1,2} go to lanes 0-3, rows {3,4,5} to lanes 4-7 ...
+    const bool hi = (l8 & 4) != 0, mid = (l8 & 2) != 0, odd = (l8 & 1) != 0;
+    double v[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double recv = __shfl_xor_sync(0xffffffffu, hi ? y[j] : y[3 + j], 4);
+      v[j] = (hi ? y[3 + j] : y[j]) + recv;
     }
-    return (q0 + q1) + q2;
+    // ... then {first two} to lanes x0/x1 and {third} to lanes x2/x3 of each half ...
+    const double r1 = __shfl_xor_sync(0xffffffffu, mid ? v[0] : v[2], 2);
+    const double r2 = __shfl_xor_sync(0xffffffffu, v[1], 2);
+    const double t0 = (mid ? v[2] : v[0]) + r1;
+    const double t1 = v[1] + r2;  // (meaningful in the !mid lanes only)
+    // ... and the last exchange finishes the sums (the two `mid` lanes of a half both end with the third row)
+    const double keep = mid ? t0 : (odd ? t1 : t0);
+    const double send = mid ? t0 : (odd ? t0 : t1);
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
   };
   // deterministic fused reduction of two values, ONE barrier: per-warp shuffle trees, then every warp re-reduces the
-  // (<= 16) per-warp partials with a second fixed shuffle tree (lanes 0..15: gamma partials, lanes 16..31: delta partials)
-  // -> identical result in every thread, one LDS per thread instead of 2 x #warps broadcast loads
+  // per-warp partials with a second fixed shuffle tree (lanes 0..15: gamma partials, lanes 16..31: delta partials)
+  // -> identical result in every thread
   auto reduce2 = [&](double a, double b, int bufi, double* oa, double* ob) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       a += __shfl_down_sync(0xffffffffu, a, o);
       b += __shfl_down_sync(0xffffffffu, b, o);
     }
-    if (lane == 0) { s_red[bufi][warp] = a; s_red[bufi][16 + warp] = b; }
+    if (lane == 0) { s_red[bufi][warp] = a; s_red[bufi][32 + warp] = b; }
     __syncthreads();
-    const int wl = lane & 15;
-    double v = (wl < THREADS / 32) ? s_red[bufi][(lane & 16) + wl] : 0.0;
+    const int wl = lane & 15, base = (lane & 16) * 2;
+    double v = (wl < NW) ? s_red[bufi][base + wl] : 0.0;
+    if (NW > 16 && wl + 16 < NW) v += s_red[bufi][base + wl + 16];
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);  // a+b == b+a: all 16 lanes agree
     *oa = __shfl_sync(0xffffffffu, v, 0);
     *ob = __shfl_sync(0xffffffffu, v, 16);
   };
+  // u_d = (Minv r)_d: the camera's six residual entries sit in lanes {0,1,2,4,5,6} of its 8-lane group
+  auto precond = [&](double rd) -> double {
+    const double q0 = __shfl_sync(0xffffffffu, rd, 0, 8), q1 = __shfl_sync(0xffffffffu, rd, 1, 8);
+    const double q2 = __shfl_sync(0xffffffffu, rd, 2, 8), q3 = __shfl_sync(0xffffffffu, rd, 4, 8);
+    const double q4 = __shfl_sync(0xffffffffu, rd, 5, 8), q5 = __shfl_sync(0xffffffffu, rd, 6, 8);
+    return ((mrow[0] * q0 + mrow[1] * q1) + (mrow[2] * q2 + mrow[3] * q3)) + (mrow[4] * q4 + mrow[5] * q5);
+  };
   // ---- Chronopoulos-Gear PCG (same recurrence as oracle/ba_ref.c::ba_pcg) ----
   double xd = 0.0, pd = 0.0, sd = 0.0, rd = 0.0, ud = 0.0, wd = 0.0;
-  if (own) {
-    rd = buf[nS + tid];
-#pragma unroll
-    for (int b = 0; b < 6; ++b) ud += mrow[b] * buf[nS + 6 * ci + b];
-    vu[tid] = ud;
-  }
+  if (cam_ok) rd = buf[nS + d];
+  ud = precond(rd);
+  if (own) vu[d] = ud;
   __syncthreads();
-  if (own) wd = matvec();
+  wd = matvec();
   double gamma, delta;
-  reduce2(rd * ud, wd * ud, 0, &gamma, &delta);
+  reduce2(own ? rd * ud : 0.0, own ? wd * ud : 0.0, 0, &gamma, &delta);
   const double gamma0 = gamma, tol2 = tol * tol;
   int iters = 0;
   double alpha = 0.0, beta = 0.0, inv_alpha = 0.0, inv_gamma = 0.0;
@@ -971,26 +998,19 @@ __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, doub
   if (g.prof && tid == 0) g.prof[7] = clock64() - t_start;
   for (int it = 0; it < maxit && !done; ++it) {
     SP_STAMP(0);
-    if (own) {  // element-wise recurrences, registers only
-      pd = ud + beta * pd;
-      sd = wd + beta * sd;
-      xd += alpha * pd;
-      rd -= alpha * sd;
-      vrs[tid] = rd;
-    }
-    __syncthreads();  // r published (the previous mat-vec's reads of vu are long done: reduction barrier in between)
-    if (own) {
-      const double2* rc = reinterpret_cast<const double2*>(vrs + 6 * ci);
-      const double2 r01 = rc[0], r23 = rc[1], r45 = rc[2];
-      ud = ((mrow[0] * r01.x + mrow[1] * r01.y) + (mrow[2] * r23.x + mrow[3] * r23.y)) + (mrow[4] * r45.x + mrow[5] * r45.y);
-      vu[tid] = ud;
-    }
+    // element-wise recurrences, registers only (duplicate lanes compute duplicates)
+    pd = ud + beta * pd;
+    sd = wd + beta * sd;
+    xd += alpha * pd;
+    rd -= alpha * sd;
+    ud = precond(rd);
+    if (own) vu[d] = ud;  // (the previous mat-vec's reads of vu are long done: reduction barrier in between)
     SP_STAMP(1);
     __syncthreads();  // u published
-    if (own) wd = matvec();
+    wd = matvec();
     SP_STAMP(2);
     double gn, dl;
-    reduce2(rd * ud, wd * ud, (it + 1) & 1, &gn, &dl);
+    reduce2(own ? rd * ud : 0.0, own ? wd * ud : 0.0, (it + 1) & 1, &gn, &dl);
     SP_STAMP(3);
     ++iters;
     if (!(gn > 0.0) || gn < tol2 * gamma0) break;
@@ -1007,7 +1027,7 @@ __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, doub
   if (g.prof && tid == 0) g.prof[6] = clock64();
   // publish the solution, the iteration count and the candidate camera poses
   __syncthreads();
-  if (own) { g.x[tid] = xd; vq[tid] = xd; }
+  if (own) { g.x[d] = xd; vq[d] = xd; }
   if (tid == 0) g.sc->pcg_iters += iters;
   __syncthreads();
   for (int i = tid; i < nc; i += THREADS) {
@@ -1027,10 +1047,10 @@ __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, doub
     for (int k = 0; k < 3; ++k) g.Rt_new[12 * i + 9 + k] = out[4 + k];
   }
 }
-constexpr int kSpThreads = 512;  // upper bound on 6N for the single-CTA path
-#define BA_SPARSE_SMALL ba_pcg_sparse_kernel<320, 12>
-#define BA_SPARSE_SMALL9 ba_pcg_sparse_kernel<320, 9>
-#define BA_SPARSE_LARGE ba_pcg_sparse_kernel<512, 6>
+constexpr int kSpMaxCams = 88;       // upper bound on the cameras of the single-CTA path (8 lanes each: 704 threads)
+constexpr int kSpSmallCams = 52;     // up to here: 416 threads, 7 register columns per lane (block rows of <= 9 blocks)
+#define BA_SPARSE_SMALL ba_pcg_sparse_kernel<416, 7>
+#define BA_SPARSE_LARGE ba_pcg_sparse_kernel<704, 5>
 
 // ---- K7b (local BA): block-Jacobi PCG inside ONE thread-block cluster ------------------------------------------------------
 // Each CTA of the cluster keeps a block-row slice of the (damped) reduced camera matrix S resident in its shared memory for the
@@ -1303,11 +1323,10 @@ static void ba_pick_pcg(gb_ctx* ctx, gb_ba_graph* g) {
   g->pcg_cluster = 0;
   g->pcg_sparse = false;
   const int nc = g->d.nc, n6 = g->d.n6;
-  if (nc > 0 && n6 <= kSpThreads && g->d.s_nnzb > 0) {
+  if (nc > 0 && nc <= kSpMaxCams && g->d.s_nnzb > 0) {
     const size_t smem = ((size_t)g->d.s_nnzb * 36 + (size_t)nc * 36 + 6 * (size_t)n6) * sizeof(double) + ((size_t)nc + 1 + g->d.s_nnzb) * sizeof(int) + 64;
-    cudaError_t ea = n6 <= 320 ? cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                               : cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ea == cudaSuccess && n6 <= 320) ea = cudaFuncSetAttribute(BA_SPARSE_SMALL9, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ea = nc <= kSpSmallCams ? cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                        : cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (smem <= (size_t)ctx->max_smem_optin && ea == cudaSuccess) {
       g->pcg_sparse = true;
       g->pcg_sparse_smem = smem;
@@ -1680,15 +1699,12 @@ static int ba_pcg_dispatch(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   cudaStream_t s = ctx->stream;
   if (d.nc <= 0) return GB_OK;
   if (g->pcg_sparse && buf == g->buf) {
-    if (d.n6 <= 320 && g->pcg_max_row_blocks <= 9) {
-      GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_SMALL9, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
-      BA_SPARSE_SMALL9<<<1, 320, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
-    } else if (d.n6 <= 320) {
+    if (d.nc <= kSpSmallCams) {
       GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
-      BA_SPARSE_SMALL<<<1, 320, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
+      BA_SPARSE_SMALL<<<1, 416, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
     } else {
       GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
-      BA_SPARSE_LARGE<<<1, 512, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
+      BA_SPARSE_LARGE<<<1, 704, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
     }
     GB_LAUNCH_CHECK(ctx);
   } else if (g->pcg_cluster > 0) {
