@@ -822,36 +822,58 @@ __global__ void __launch_bounds__(kRedThreads) ba_commit_fused_kernel(BaDev g, c
 
 // ---- K7b (local BA, sparse covisibility): block-Jacobi PCG in ONE CTA -------------------------------------------------------
 // When the structurally non-zero 6x6 blocks of the reduced camera matrix fit one SM (sequential-SLAM windows: a band of
-// co-visible keyframes) the whole solve needs no inter-CTA exchange.
-// Layout: EIGHT lanes per camera (one warp = four cameras).  A block row of S (nb blocks = 6*nb columns) is split BY COLUMN
-// over the eight lanes: lane l keeps columns l, l+8, ... (six coefficients each) in registers for the whole solve, so a
-// mat-vec needs ONE shared-memory read of u per column instead of one per (row, column) -- the shared-memory port
-// (128 B/clk, requested bytes count even when lanes broadcast) was what bounded the row-per-thread version (1076 -> ~450 clk).
-// The eight lanes then hold six partial sums each; a 3-stage transposing butterfly (6 exchanges) leaves row r of the camera
-// in lane {0,1,2,-,3,4,5,-}[l] (lanes 3 and 7 duplicate rows 2 and 5).  Those six lanes own element 6i+r of every CG vector;
-// u = Minv r gathers the camera's six residuals with shuffles (no shared-memory round trip, no barrier).
-// An iteration = element-wise recurrences, u = Minv r, ONE barrier (u published), register mat-vec, ONE fused deterministic
-// reduction (second barrier), scalar recurrences.
+// co-visible keyframes) the whole solve needs no inter-CTA exchange.  What bounds an iteration on one SM is ISSUE, not memory:
+// fp64 runs at 64 lanes/clk/SM (a warp DFMA every 2 clk per sub-partition, a DDIV ~10 clk of the SM's pipe), SHFL at one
+// warp-instruction/clk/SM (tools/mb/microbench2.cu) -- so the kernel does nothing redundantly:
+//  * EIGHT lanes per ACTIVE camera (fixed keyframes have identity rows and a zero right-hand side: they get no lanes).  A block
+//    row of S (nb blocks = 6*nb columns) is split BY COLUMN over the eight lanes: lane l keeps columns l, l+8, ... (six
+//    coefficients each) in registers for the whole solve, so a mat-vec is one shared-memory read of u and six DFMAs per column
+//    (no lane repeats another's work) followed by a 3-stage transposing butterfly (6 exchanges) that leaves row r of the camera
+//    in lane {0,1,2,-,3,4,5,-}[l] (lanes 3 and 7 duplicate rows 2 and 5).  Those lanes own element 6i+r of every CG vector;
+//    u = Minv r gathers the camera's six residuals with shuffles (no shared-memory round trip, no barrier).
+//  * (gamma, delta) are reduced packed into ONE butterfly per warp (a in lanes 0-15, b in lanes 16-31); warp 0 alone folds the
+//    per-warp partials and runs the alpha/beta recurrences (three DDIVs) while the others wait at the barrier.
+//  * <= 48 active cameras run as 12 warps = 3 per sub-partition -> 168 registers per thread, enough for 7 columns per lane
+//    (block rows of <= 9 blocks) without spilling; the wide variant (<= 80 cameras) keeps 5 columns and reads the rest from
+//    the shared-memory copy of S.
+// An iteration = [partials | warp 0: scalars | element-wise recurrences, u = Minv r | u published | register mat-vec], three
+// barriers.
 template <int THREADS, int KC>
-__global__ void __maxnreg__(((65536 / THREADS) / 8) * 8) ba_pcg_sparse_kernel(BaDev g, double* __restrict__ buf, int maxit) {
+__global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, double* __restrict__ buf, int maxit) {
   if (g.sc->stop) return;
   extern __shared__ __align__(16) double sm[];
-  __shared__ double s_red[2][64];
+  __shared__ double2 s_red[32];  // per-warp (gamma, delta) partials
+  __shared__ double s_scal[2][2];
+  __shared__ int s_flag[2];
+  __shared__ int s_nact;
   constexpr int NW = THREADS / 32;
+  static_assert(NW <= 32, "the fold handles at most 32 per-warp partials");
   const int n6 = g.n6, nc = g.nc, nnzb = g.s_nnzb, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long t_start = clock64();
   double* B = sm;                          // [nnzb][36] row-major blocks
   double* Minv = B + (size_t)nnzb * 36;    // [nc][36]
-  double* vp = Minv + (size_t)nc * 36;     // vectors of n6: u (mat-vec input), x (for the retraction)
-  double* vq = vp + n6;
-  double* vr = vq + n6;
-  double* vz = vr + n6;
-  int* rowptr = reinterpret_cast<int*>(vz + 3 * (size_t)n6);  // [nc+1]
+  double* vu = Minv + (size_t)nc * 36;     // u (mat-vec input), n6
+  double* vx = vu + n6;                    // x (for the retraction), n6
+  double* vr = vx + n6;                    // r (warp-local exchange for u = Minv r), n6
+  int* rowptr = reinterpret_cast<int*>(vr + n6);  // [nc+1]
   int* col = rowptr + nc + 1;                     // [nnzb]
+  int* act = col + nnzb;                          // [nc] active (not fully fixed) cameras, ascending
   const size_t nS = (size_t)n6 * n6;
   const double lambda = g.sc->lambda, tol = g.sc->pcg_tol;
   for (int k = tid; k <= nc; k += THREADS) rowptr[k] = g.s_rowptr[k];
   for (int k = tid; k < nnzb; k += THREADS) col[k] = g.s_col[k];
+  for (int k = tid; k < n6; k += THREADS) { vu[k] = 0.0; vx[k] = 0.0; }
+  if (warp == NW - 1) {  // stream compaction of the active cameras (ballot scan)
+    int cnt = 0;
+    for (int base = 0; base < nc; base += 32) {
+      const int i = base + lane;
+      const bool f = i < nc && g.dof[i] != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, f);
+      if (f) act[cnt + __popc(m & ((1u << lane) - 1u))] = i;
+      cnt += __popc(m);
+    }
+    if (lane == 0) s_nact = cnt;
+  }
   // A. copy the block-CSR values of S (written by ba_schur_blocks_kernel) into shared memory (8 independent loads in
   //    flight per thread), then Marquardt damping on the 6N diagonal entries (written back so the damped system is observable)
   {
@@ -895,9 +917,9 @@ __global__ void __maxnreg__(((65536 / THREADS) / 8) * 8) ba_pcg_sparse_kernel(Ba
   }
   __syncthreads();  // Minv complete
   // ---- thread roles
-  const int ci_raw = tid >> 3, l8 = tid & 7;
-  const bool cam_ok = ci_raw < nc;
-  const int ci = cam_ok ? ci_raw : 0;
+  const int l8 = tid & 7;
+  const bool cam_ok = (tid >> 3) < s_nact;
+  const int ci = cam_ok ? act[tid >> 3] : 0;
   const int row = (l8 >> 2) * 3 + ((l8 & 3) < 2 ? (l8 & 3) : 2);  // which row of the camera this lane ends up with
   const bool own = cam_ok && (l8 & 3) != 3;                       // lanes 3 / 7 duplicate rows 2 / 5
   const int d = 6 * ci + row;
@@ -915,7 +937,6 @@ __global__ void __maxnreg__(((65536 / THREADS) / 8) * 8) ba_pcg_sparse_kernel(Ba
 #pragma unroll
     for (int r = 0; r < 6; ++r) cf[k][r] = ok ? B[(size_t)sblk * 36 + r * 6 + a] : 0.0;
   }
-  double* vu = vp;
   double mrow[6];  // this lane's row of the camera's Minv block (constant over the solve)
 #pragma unroll
   for (int b = 0; b < 6; ++b) mrow[b] = cam_ok ? Minv[36 * ci + row * 6 + b] : 0.0;
@@ -954,89 +975,106 @@ __global__ void __maxnreg__(((65536 / THREADS) / 8) * 8) ba_pcg_sparse_kernel(Ba
     const double send = mid ? t0 : (odd ? t0 : t1);
     return keep + __shfl_xor_sync(0xffffffffu, send, 1);
   };
-  // deterministic fused reduction of two values, ONE barrier: per-warp shuffle trees, then every warp re-reduces the
-  // per-warp partials with a second fixed shuffle tree (lanes 0..15: gamma partials, lanes 16..31: delta partials)
-  // -> identical result in every thread
-  auto reduce2 = [&](double a, double b, int bufi, double* oa, double* ob) {
+  // per-warp part of the fused deterministic reduction: lanes 0-15 fold a, lanes 16-31 fold b (ONE butterfly for both)
+  auto warp_partials = [&](double a, double b) {
+    const bool up = (lane & 16) != 0;
+    double v = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 16);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_down_sync(0xffffffffu, a, o);
-      b += __shfl_down_sync(0xffffffffu, b, o);
-    }
-    if (lane == 0) { s_red[bufi][warp] = a; s_red[bufi][32 + warp] = b; }
-    __syncthreads();
-    const int wl = lane & 15, base = (lane & 16) * 2;
-    double v = (wl < NW) ? s_red[bufi][base + wl] : 0.0;
-    if (NW > 16 && wl + 16 < NW) v += s_red[bufi][base + wl + 16];
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);  // a+b == b+a: all 16 lanes agree
-    *oa = __shfl_sync(0xffffffffu, v, 0);
-    *ob = __shfl_sync(0xffffffffu, v, 16);
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[warp].x = v;
+    if (lane == 16) s_red[warp].y = v;
   };
-  // u_d = (Minv r)_d: the camera's six residual entries sit in lanes {0,1,2,4,5,6} of its 8-lane group
+  // u_d = (Minv r)_d: the camera's six residual entries are exchanged through shared memory INSIDE the warp (a camera never
+  // straddles warps): 2 + 3 shared-memory wavefronts instead of 12 SHFLs
   auto precond = [&](double rd) -> double {
-    const double q0 = __shfl_sync(0xffffffffu, rd, 0, 8), q1 = __shfl_sync(0xffffffffu, rd, 1, 8);
-    const double q2 = __shfl_sync(0xffffffffu, rd, 2, 8), q3 = __shfl_sync(0xffffffffu, rd, 4, 8);
-    const double q4 = __shfl_sync(0xffffffffu, rd, 5, 8), q5 = __shfl_sync(0xffffffffu, rd, 6, 8);
-    return ((mrow[0] * q0 + mrow[1] * q1) + (mrow[2] * q2 + mrow[3] * q3)) + (mrow[4] * q4 + mrow[5] * q5);
+    if (own) vr[d] = rd;
+    __syncwarp();
+    const double2* rc = reinterpret_cast<const double2*>(vr + 6 * ci);
+    const double2 q01 = rc[0], q23 = rc[1], q45 = rc[2];
+    return ((mrow[0] * q01.x + mrow[1] * q01.y) + (mrow[2] * q23.x + mrow[3] * q23.y)) + (mrow[4] * q45.x + mrow[5] * q45.y);
   };
+#define SP_STAMP(k) do { if (g.prof && tid == 0 && it == 3) g.prof[k] = clock64(); } while (0)
+  if (g.prof && tid == 0) g.prof[7] = clock64() - t_start;
   // ---- Chronopoulos-Gear PCG (same recurrence as oracle/ba_ref.c::ba_pcg) ----
-  double xd = 0.0, pd = 0.0, sd = 0.0, rd = 0.0, ud = 0.0, wd = 0.0;
+  double xd = 0.0, pd = 0.0, sd = 0.0, rd = 0.0, ud, wd;
   if (cam_ok) rd = buf[nS + d];
   ud = precond(rd);
   if (own) vu[d] = ud;
-  __syncthreads();
+  __syncthreads();  // u published
   wd = matvec();
-  double gamma, delta;
-  reduce2(own ? rd * ud : 0.0, own ? wd * ud : 0.0, 0, &gamma, &delta);
-  const double gamma0 = gamma, tol2 = tol * tol;
+  warp_partials(own ? rd * ud : 0.0, own ? wd * ud : 0.0);
+  // scalar recurrences: live in warp 0 only
+  const double tol2 = tol * tol;
+  double gamma0 = 0.0, alpha_s = 0.0, beta_s = 0.0, inv_alpha = 0.0, inv_gamma = 0.0;
   int iters = 0;
-  double alpha = 0.0, beta = 0.0, inv_alpha = 0.0, inv_gamma = 0.0;
-  bool done = !(gamma0 > 0.0) || !(delta > 0.0);
-  if (!done) { alpha = gamma / delta; inv_alpha = delta / gamma; inv_gamma = 1.0 / gamma; }
-#define SP_STAMP(k) do { if (g.prof && tid == 0 && it == 3) g.prof[k] = clock64(); } while (0)
-  if (g.prof && tid == 0) g.prof[7] = clock64() - t_start;
-  for (int it = 0; it < maxit && !done; ++it) {
+  for (int it = 0;; ++it) {
     SP_STAMP(0);
+    __syncthreads();  // the partials of round `it` are in s_red (round 0: the initial gamma, delta; round k: iteration k-1)
+    if (warp == 0) {
+      double gn = 0.0, dl = 0.0;  // fixed-order fold of the per-warp partials (broadcast loads, two independent chains)
+#pragma unroll
+      for (int w = 0; w < NW; ++w) { const double2 t = s_red[w]; gn += t.x; dl += t.y; }
+      // alpha = gn/den, 1/alpha = den/gn and 1/gn from ONE reciprocal: t = 1/(gn*den) (a DDIV is ~113 clk and three of them do
+      // not overlap); the guarded fallback covers products outside the double range
+      auto scalars = [&](double den) {
+        const double t = __drcp_rn(gn * den);
+        if (t > 0.0 && t < 1.0e300) {
+          const double inv_gn = den * t, inv_den = gn * t;
+          alpha_s = gn * inv_den; inv_alpha = den * inv_gn; inv_gamma = inv_gn;
+        } else {
+          alpha_s = gn / den; inv_alpha = den / gn; inv_gamma = 1.0 / gn;
+        }
+      };
+      bool stop;
+      if (it == 0) {
+        gamma0 = gn;
+        stop = !(gamma0 > 0.0) || !(dl > 0.0) || maxit <= 0;
+        if (!stop) scalars(dl);
+      } else {
+        iters = it;
+        stop = !(gn > 0.0) || gn < tol2 * gamma0;
+        if (!stop) {
+          // beta = gn/gamma, alpha = gn/(dl - beta*gn/alpha_prev) with the reciprocals of gamma and alpha carried along
+          beta_s = gn * inv_gamma;
+          const double den = dl - beta_s * (gn * inv_alpha);
+          stop = !(den > 0.0);
+          if (!stop) scalars(den);
+        }
+        stop = stop || it >= maxit;
+      }
+      if (lane == 0) { s_scal[it & 1][0] = alpha_s; s_scal[it & 1][1] = beta_s; s_flag[it & 1] = stop ? 1 : 0; }
+    }
+    SP_STAMP(1);
+    __syncthreads();  // scalars of round `it` published
+    if (s_flag[it & 1]) break;
+    const double alpha = s_scal[it & 1][0], beta = s_scal[it & 1][1];
     // element-wise recurrences, registers only (duplicate lanes compute duplicates)
     pd = ud + beta * pd;
     sd = wd + beta * sd;
     xd += alpha * pd;
     rd -= alpha * sd;
     ud = precond(rd);
-    if (own) vu[d] = ud;  // (the previous mat-vec's reads of vu are long done: reduction barrier in between)
-    SP_STAMP(1);
+    if (own) vu[d] = ud;  // (every mat-vec read of the previous u happened before the two barriers above)
+    SP_STAMP(2);
     __syncthreads();  // u published
     wd = matvec();
-    SP_STAMP(2);
-    double gn, dl;
-    reduce2(own ? rd * ud : 0.0, own ? wd * ud : 0.0, (it + 1) & 1, &gn, &dl);
     SP_STAMP(3);
-    ++iters;
-    if (!(gn > 0.0) || gn < tol2 * gamma0) break;
-    // beta = gn/gamma, alpha = gn/(dl - beta*gn/alpha_prev) with the reciprocals of gamma and alpha carried along: the three
-    // divisions below are independent (one DDIV latency instead of two in a row)
-    beta = gn * inv_gamma;
-    const double den = dl - beta * (gn * inv_alpha);
-    if (!(den > 0.0)) break;
-    alpha = gn / den;
-    inv_alpha = den / gn;
-    inv_gamma = 1.0 / gn;
+    warp_partials(own ? rd * ud : 0.0, own ? wd * ud : 0.0);
     SP_STAMP(4);
   }
   if (g.prof && tid == 0) g.prof[6] = clock64();
   // publish the solution, the iteration count and the candidate camera poses
-  __syncthreads();
-  if (own) { g.x[d] = xd; vq[d] = xd; }
+  if (own) vx[d] = xd;
   if (tid == 0) g.sc->pcg_iters += iters;
   __syncthreads();
+  for (int k = tid; k < n6; k += THREADS) g.x[k] = vx[k];
   for (int i = tid; i < nc; i += THREADS) {
     double pose[7], dd[6], out[7], R[9];
     const int dm = g.dof[i];
 #pragma unroll
     for (int k = 0; k < 7; ++k) pose[k] = g.pose[7 * i + k];
 #pragma unroll
-    for (int a = 0; a < 6; ++a) dd[a] = ((dm >> a) & 1) ? vq[6 * i + a] : 0.0;
+    for (int a = 0; a < 6; ++a) dd[a] = ((dm >> a) & 1) ? vx[6 * i + a] : 0.0;
     se3_retract(pose, dd, out);
 #pragma unroll
     for (int k = 0; k < 7; ++k) g.pose_new[7 * i + k] = out[k];
@@ -1047,10 +1085,11 @@ __global__ void __maxnreg__(((65536 / THREADS) / 8) * 8) ba_pcg_sparse_kernel(Ba
     for (int k = 0; k < 3; ++k) g.Rt_new[12 * i + 9 + k] = out[4 + k];
   }
 }
-constexpr int kSpMaxCams = 88;       // upper bound on the cameras of the single-CTA path (8 lanes each: 704 threads)
-constexpr int kSpSmallCams = 52;     // up to here: 416 threads, 7 register columns per lane (block rows of <= 9 blocks)
-#define BA_SPARSE_SMALL ba_pcg_sparse_kernel<416, 7>
-#define BA_SPARSE_LARGE ba_pcg_sparse_kernel<704, 5>
+constexpr int kSpSmallCams = 48;     // active cameras of the 12-warp variant (168 registers, 7 register columns per lane)
+constexpr int kSpMaxCams = 80;       // active cameras of the 20-warp variant (96 registers, 5 register columns per lane)
+constexpr int kSpSmallThreads = 8 * kSpSmallCams, kSpLargeThreads = 8 * kSpMaxCams;
+#define BA_SPARSE_SMALL ba_pcg_sparse_kernel<kSpSmallThreads, 7>
+#define BA_SPARSE_LARGE ba_pcg_sparse_kernel<kSpLargeThreads, 5>
 
 // ---- K7b (local BA): block-Jacobi PCG inside ONE thread-block cluster ------------------------------------------------------
 // Each CTA of the cluster keeps a block-row slice of the (damped) reduced camera matrix S resident in its shared memory for the
@@ -1269,7 +1308,8 @@ struct gb_ba_graph {
   // PCG dispatch: single-CTA block-sparse kernel, else one-cluster kernel (pcg_cluster = 8/16), else generic multi-kernel
   bool pcg_sparse = false;
   size_t pcg_sparse_smem = 0;
-  int pcg_max_row_blocks = 0;  // longest block row of S (picks the register-cache depth of the sparse kernel)
+  int pcg_max_row_blocks = 0;  // longest block row of S
+  int pcg_nact = 0;            // cameras with at least one free dof (the sparse PCG kernel gives lanes to these only)
   int pcg_cluster = 0;
   size_t pcg_smem = 0;
 };
@@ -1323,10 +1363,10 @@ static void ba_pick_pcg(gb_ctx* ctx, gb_ba_graph* g) {
   g->pcg_cluster = 0;
   g->pcg_sparse = false;
   const int nc = g->d.nc, n6 = g->d.n6;
-  if (nc > 0 && nc <= kSpMaxCams && g->d.s_nnzb > 0) {
-    const size_t smem = ((size_t)g->d.s_nnzb * 36 + (size_t)nc * 36 + 6 * (size_t)n6) * sizeof(double) + ((size_t)nc + 1 + g->d.s_nnzb) * sizeof(int) + 64;
-    cudaError_t ea = nc <= kSpSmallCams ? cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                        : cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (nc > 0 && g->pcg_nact <= kSpMaxCams && g->d.s_nnzb > 0) {
+    const size_t smem = ((size_t)g->d.s_nnzb * 36 + (size_t)nc * 36 + 3 * (size_t)n6) * sizeof(double) + (2 * (size_t)nc + 1 + g->d.s_nnzb) * sizeof(int) + 64;
+    cudaError_t ea = g->pcg_nact <= kSpSmallCams ? cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                                 : cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (smem <= (size_t)ctx->max_smem_optin && ea == cudaSuccess) {
       g->pcg_sparse = true;
       g->pcg_sparse_smem = smem;
@@ -1468,6 +1508,7 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
     s_tidx[blk] = t;
   }
   d.s_nupper = (int)s_upper.size();
+  for (int i = 0; i < nc; ++i) g->pcg_nact += (pb->cam_dof ? (pb->cam_dof[i] & 63) : 63) != 0;
   for (int i = 0; i < nc && !s_col.empty(); ++i) g->pcg_max_row_blocks = std::max(g->pcg_max_row_blocks, s_rowptr[i + 1] - s_rowptr[i]);
   const size_t b_sr = al((size_t)(nc + 1) * 4), b_sc = al((size_t)s_col.size() * 4 + 4);
   const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + b_sr + 4 * b_sc + b_cpt + b_cuv + 256;
@@ -1699,12 +1740,12 @@ static int ba_pcg_dispatch(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   cudaStream_t s = ctx->stream;
   if (d.nc <= 0) return GB_OK;
   if (g->pcg_sparse && buf == g->buf) {
-    if (d.nc <= kSpSmallCams) {
+    if (g->pcg_nact <= kSpSmallCams) {
       GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
-      BA_SPARSE_SMALL<<<1, 416, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
+      BA_SPARSE_SMALL<<<1, kSpSmallThreads, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
     } else {
       GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
-      BA_SPARSE_LARGE<<<1, 704, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
+      BA_SPARSE_LARGE<<<1, kSpLargeThreads, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
     }
     GB_LAUNCH_CHECK(ctx);
   } else if (g->pcg_cluster > 0) {

@@ -38,6 +38,8 @@ PROBLEMS = {
     "config1_10cam_200pt": dict(n_cams=10, n_points=200, all_visible=True, n_fixed=2, seed=42),
     "tiny": dict(n_cams=4, n_points=12, obs_per_point=3, n_fixed=1, seed=1),
     "local_50kf": dict(n_cams=50, n_points=2000, obs_per_point=5, n_fixed=2, seed=42),
+    "local_70kf": dict(n_cams=70, n_points=1500, obs_per_point=4, n_fixed=2, seed=9),      # the wide single-CTA PCG variant
+    "wide_band_30kf": dict(n_cams=30, n_points=600, obs_per_point=7, n_fixed=2, seed=11),  # 13 blocks per row of S
 }
 
 
@@ -70,10 +72,13 @@ def force_mode(g, mode):
 @pytest.mark.parametrize("name", list(PROBLEMS))
 def test_reduced_system_and_pcg_match_oracle(ctx, name, mode):
     pb = synth.synth_ba(**PROBLEMS[name])
-    S0, gt0, dc0, it0 = oracle.ba_reduced_system(pb, 0.01, 1e-4, 50, 1e-10)
+    # (the wide-band system is still 17 % away from its solution after 50 iterations: a truncated Krylov iterate amplifies
+    #  summation-order differences, so that case is compared at convergence -- 77 iterations)
+    cap = 200 if name == "wide_band_30kf" else 50
+    S0, gt0, dc0, it0 = oracle.ba_reduced_system(pb, 0.01, 1e-4, cap, 1e-10)
     g = BAGraph(ctx, pb)
     force_mode(g, mode)
-    S, gt, dc, it = g.dbg_reduced(cfg(pcgMaxIterations=50, pcgTolerance=1e-10))
+    S, gt, dc, it = g.dbg_reduced(cfg(pcgMaxIterations=cap, pcgTolerance=1e-10))
     assert rel(S, S0) < 1e-10 and rel(gt, gt0) < 1e-9
     assert np.abs(S - S.T).max() < 1e-9 * np.abs(S).max()
     assert abs(it - it0) <= 1
@@ -82,7 +87,7 @@ def test_reduced_system_and_pcg_match_oracle(ctx, name, mode):
 
 
 @pytest.mark.parametrize("mode", list(PCG_MODES))
-@pytest.mark.parametrize("name,iters", [("config1_10cam_200pt", 10), ("tiny", 8), ("local_50kf", 10)])
+@pytest.mark.parametrize("name,iters", [("config1_10cam_200pt", 10), ("tiny", 8), ("local_50kf", 10), ("local_70kf", 6), ("wide_band_30kf", 6)])
 def test_solve_matches_oracle_fixed_iterations(ctx, name, iters, mode):
     a = synth.synth_ba(**PROBLEMS[name]); b = a.copy()
     kw = dict(max_iterations=iters, function_tolerance=0.0, pcg_max_iters=50, pcg_tol=1e-10)
