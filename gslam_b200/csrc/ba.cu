@@ -195,6 +195,8 @@ __device__ __forceinline__ void ba_linearize_cams_body(const BaDev& g, int i) {
 // pass (K6b); the two are independent.
 static_assert(kPtThreads == kCamThreads, "the fused sweep launch uses one block size");
 __global__ void __launch_bounds__(kPtThreads) ba_linearize_kernel(BaDev g, int pt_blocks) {
+  gb_pdl_launch_dependents();
+  gb_pdl_wait();
   if (g.sc->stop || !g.sc->need_linearize) return;
   if ((int)blockIdx.x < pt_blocks) ba_linearize_points_body(g, blockIdx.x);
   else ba_linearize_cams_body(g, blockIdx.x - pt_blocks);
@@ -260,6 +262,8 @@ __global__ void ba_schur_accum_kernel(BaDev g, double* __restrict__ buf) {
 // accumulates Y W' (Y = W V^-1) in registers; a fixed shuffle tree reduces the 36 entries; the block and its transpose are
 // written once.  The diagonal warps also produce g~_i = g_c,i - sum_j Y g_p,j and diag U.  Bit-reproducible run to run.
 __global__ void __launch_bounds__(128) ba_schur_blocks_kernel(BaDev g, double* __restrict__ buf) {
+  gb_pdl_launch_dependents();
+  gb_pdl_wait();
   if (g.sc->stop) return;
   // one CTA (4 warps) per upper block: the warps split camera i's observation list, a fixed shuffle tree reduces inside each
   // warp and warp 0 adds the four partials in order
@@ -674,6 +678,8 @@ __device__ __forceinline__ void cta_copy_f64(double* __restrict__ dst, const dou
 }
 
 __global__ void __launch_bounds__(kTailThreads) ba_backsub_commit_kernel(BaDev g, const double* __restrict__ buf) {
+  gb_pdl_launch_dependents();
+  gb_pdl_wait();
   BaScalars* sc = g.sc;
   if (sc->stop) return;
   __shared__ double s_part[kTailThreads / 32 + 1];
@@ -840,6 +846,8 @@ __global__ void __launch_bounds__(kRedThreads) ba_commit_fused_kernel(BaDev g, c
 // barriers.
 template <int THREADS, int KC>
 __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, double* __restrict__ buf, int maxit) {
+  gb_pdl_launch_dependents();
+  gb_pdl_wait();
   if (g.sc->stop) return;
   extern __shared__ __align__(16) double sm[];
   __shared__ double2 s_red[32];  // per-warp (gamma, delta) partials
@@ -1826,15 +1834,22 @@ int gb_ba_graph_solve(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, gb_
   const bool fused_commit = (size_t)g->d.np * 3 + (size_t)g->d.nc * 19 <= (size_t)1 << 16;
   // local-BA fast path (block-CSR Schur + single-CTA PCG): 4 launches per LM iteration
   const bool local4 = fused_commit && g->pcg_sparse && g->d.s_nnzb > 0 && g->d.nc > 0 && g->d.np > 0;
+  if (local4) {  // (a per-function attribute: another graph may have lowered it since)
+    if (g->pcg_nact <= kSpSmallCams) GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
+    else GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
+  }
   for (int it = 0; it < g->opt.max_iterations; ++it) {
     if (local4) {
       BaDev& d = g->d;
       cudaStream_t s = ctx->stream;
       const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads);
-      ba_linearize_kernel<<<pt_blocks + d.nc, kPtThreads, 0, s>>>(d, pt_blocks); GB_LAUNCH_CHECK(ctx);
-      ba_schur_blocks_kernel<<<d.s_nupper, 128, 0, s>>>(d, g->buf); GB_LAUNCH_CHECK(ctx);
-      GB_CHECK(ba_pcg_dispatch(ctx, g, g->buf));
-      ba_backsub_commit_kernel<<<gb_div_up(d.np * kLpp, kTailThreads), kTailThreads, 0, s>>>(d, g->buf); GB_LAUNCH_CHECK(ctx);
+      // (programmatic dependent launches: each kernel is scheduled while its predecessor drains)
+      GB_CUDA(ctx, gb_launch_pdl(ba_linearize_kernel, dim3(pt_blocks + d.nc), dim3(kPtThreads), 0, s, d, pt_blocks)); GB_LAUNCH_CHECK(ctx);
+      GB_CUDA(ctx, gb_launch_pdl(ba_schur_blocks_kernel, dim3(d.s_nupper), dim3(128), 0, s, d, g->buf)); GB_LAUNCH_CHECK(ctx);
+      if (g->pcg_nact <= kSpSmallCams) GB_CUDA(ctx, gb_launch_pdl(BA_SPARSE_SMALL, dim3(1), dim3(kSpSmallThreads), g->pcg_sparse_smem, s, d, g->buf, (int)g->opt.pcg_max_iters));
+      else GB_CUDA(ctx, gb_launch_pdl(BA_SPARSE_LARGE, dim3(1), dim3(kSpLargeThreads), g->pcg_sparse_smem, s, d, g->buf, (int)g->opt.pcg_max_iters));
+      GB_LAUNCH_CHECK(ctx);
+      GB_CUDA(ctx, gb_launch_pdl(ba_backsub_commit_kernel, dim3(gb_div_up(d.np * kLpp, kTailThreads)), dim3(kTailThreads), 0, s, d, (const double*)g->buf)); GB_LAUNCH_CHECK(ctx);
     } else {
     GB_CHECK(gb_ba_graph_reduce_local(ctx, g, nullptr));
     if (fused_commit) {

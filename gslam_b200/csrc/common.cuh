@@ -83,6 +83,25 @@ int gb_dev_realloc(gb_ctx* ctx, void** p, size_t* cap, size_t bytes);  // grow-o
     }                                                                                                   \
   } while (0)
 
+// ---- programmatic dependent launch (sm_90+): a kernel launched with gb_launch_pdl may be scheduled while its predecessor on
+// the stream is still running; it must call gb_pdl_wait() before touching anything the predecessor wrote.  Calling
+// gb_pdl_launch_dependents() first lets ITS successor start getting scheduled in turn.  Both are no-ops in a plain launch.
+// What is hidden: the ~2-3 us launch + CTA-scheduling latency between short dependent kernels (40 launches per local-BA solve).
+#ifdef __CUDACC__
+__device__ __forceinline__ void gb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void gb_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gb_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 struct CtxLock {
   gb_ctx* c;
   explicit CtxLock(gb_ctx* ctx) : c(ctx) {

@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(kQPerCta) match_kernel(const uint4* __restrict
                                                          int nt, int chunk, MatchPartial* __restrict__ partial,
                                                          unsigned int* __restrict__ tickets, int32_t* __restrict__ best_idx,
                                                          int32_t* __restrict__ best_dist, int32_t* __restrict__ second_dist) {
+  gb_pdl_launch_dependents();
+  gb_pdl_wait();
   extern __shared__ uint4 s_train[];  // chunk rows x 2 uint4
   __shared__ bool s_last;
   const int tid = threadIdx.x;
@@ -146,9 +148,8 @@ int gb_match_launch(gb_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t,
   }
   dim3 grid(qtiles, nsplit);
   const size_t smem = (size_t)chunk * 32;
-  match_kernel<<<grid, kQPerCta, smem, ctx->stream>>>((const uint4*)d_q, nq, (const uint4*)d_t, nt > 0 ? nt : 0, chunk,
-                                                      (MatchPartial*)ms->d_partial, (unsigned int*)ms->d_tickets, d_best,
-                                                      d_dist, d_dist2);
+  GB_CUDA(ctx, gb_launch_pdl(match_kernel, grid, dim3(kQPerCta), smem, ctx->stream, (const uint4*)d_q, nq, (const uint4*)d_t, nt > 0 ? nt : 0, chunk,
+                             (MatchPartial*)ms->d_partial, (unsigned int*)ms->d_tickets, d_best, d_dist, d_dist2));
   GB_LAUNCH_CHECK(ctx);
   return GB_OK;
 }

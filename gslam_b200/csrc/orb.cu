@@ -52,6 +52,8 @@ struct OrbParams {
 __global__ void __launch_bounds__(256) orb_resize_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
                                                          uint8_t* __restrict__ dst, int dw, int dh, int dpitch,
                                                          const uint32_t* __restrict__ xtab, const uint32_t* __restrict__ ytab) {
+  gb_pdl_launch_dependents();
+  gb_pdl_wait();
   const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x4 >= dw || y >= dh) return;
@@ -141,6 +143,8 @@ __device__ __forceinline__ int fast_full_score(const uint8_t* p /* centre inside
 __global__ void __launch_bounds__(kFastThreads) orb_fast_kernel(const __grid_constant__ OrbParams P, const uint8_t* __restrict__ pyr,
                                                                 uint32_t* __restrict__ cand_pos, uint8_t* __restrict__ cand_score,
                                                                 int* __restrict__ counts, int* __restrict__ hist) {
+  gb_pdl_launch_dependents();
+  gb_pdl_wait();
   __shared__ __align__(16) uint8_t s_in[kInH * kInW];
   __shared__ uint8_t s_sc[kScH * kScW];
   __shared__ uint16_t s_work[kScH * kScW];   // positions that survive the opposite-pair quick reject
@@ -256,6 +260,8 @@ __global__ void __launch_bounds__(256) orb_harris_kernel(const __grid_constant__
                                                          const int* __restrict__ counts, const int* __restrict__ hist,
                                                          uint32_t* __restrict__ surv_key, float* __restrict__ surv_resp,
                                                          uint32_t* __restrict__ surv_pos, int* __restrict__ surv_count) {
+  gb_pdl_launch_dependents();
+  gb_pdl_wait();
   // FAST-score threshold of this level = the (2 n_l)-th largest score (ties kept): suffix sums of the 256-bin histogram,
   // one bin per thread (blockDim.x == 256), thr = number of scores s whose suffix count  #{score >= s}  reaches 2 n_l
   __shared__ int s_suffix[256];
@@ -306,6 +312,8 @@ __global__ void __launch_bounds__(kSelThreads) orb_select_kernel(const __grid_co
                                                                  uint32_t* __restrict__ kept_pos,
                                                                  float* __restrict__ kept_resp, int* __restrict__ kept_count,
                                                                  int* __restrict__ status) {
+  gb_pdl_launch_dependents();
+  gb_pdl_wait();
   __shared__ int s_hist[256];
   __shared__ unsigned long long s_keys[kSelMax];
   __shared__ int s_n, s_k;
@@ -449,6 +457,8 @@ __global__ void __launch_bounds__(kDescWarps * 32) orb_describe_kernel(const __g
                                                                       gb_keypoint* __restrict__ out_kps, uint8_t* __restrict__ out_desc,
                                                                       int capacity, int* __restrict__ out_count, int* __restrict__ out_status,
                                                                       const int* __restrict__ status_in) {
+  gb_pdl_launch_dependents();
+  gb_pdl_wait();
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ signed char s_pat[1024];
   DescSmem* sm = reinterpret_cast<DescSmem*>(smem_raw) + (threadIdx.x >> 5);
@@ -722,24 +732,23 @@ static int orb_launch(gb_ctx* ctx, gb_features* out) {
   for (int l = 1; l < P.nlevels; ++l) {
     const LevelInfo &S = P.lv[l - 1], &D = P.lv[l];
     dim3 blk(64, 4), grd(gb_div_up(gb_div_up(D.w, 4), 64), gb_div_up(D.h, 4));
-    orb_resize_kernel<<<grd, blk, 0, st>>>(s->d_pyr + S.off, S.w, S.h, S.pitch, s->d_pyr + D.off, D.w, D.h, D.pitch,
-                                           s->d_tabs + D.coef_off, s->d_tabs + D.coef_off + D.w);
+    GB_CUDA(ctx, gb_launch_pdl(orb_resize_kernel, grd, blk, 0, st, s->d_pyr + S.off, S.w, S.h, S.pitch, s->d_pyr + D.off, D.w, D.h, D.pitch,
+                               s->d_tabs + D.coef_off, s->d_tabs + D.coef_off + D.w));
     GB_LAUNCH_CHECK(ctx);
   }
   if (P.total_tiles > 0) {
-    orb_fast_kernel<<<P.total_tiles, kFastThreads, 0, st>>>(P, s->d_pyr, s->d_cand_pos, s->d_cand_score, d_counts, d_hist);
+    GB_CUDA(ctx, gb_launch_pdl(orb_fast_kernel, dim3(P.total_tiles), dim3(kFastThreads), 0, st, P, s->d_pyr, s->d_cand_pos, s->d_cand_score, d_counts, d_hist));
     GB_LAUNCH_CHECK(ctx);
-    orb_harris_kernel<<<dim3(32, P.nlevels), 256, 0, st>>>(P, s->d_pyr, s->d_cand_pos, s->d_cand_score, d_counts, d_hist,
-                                                           s->d_cand_key, s->d_cand_resp, s->d_surv_pos, d_surv);
+    GB_CUDA(ctx, gb_launch_pdl(orb_harris_kernel, dim3(32, P.nlevels), dim3(256), 0, st, P, s->d_pyr, s->d_cand_pos, s->d_cand_score, d_counts,
+                               d_hist, s->d_cand_key, s->d_cand_resp, s->d_surv_pos, d_surv));
     GB_LAUNCH_CHECK(ctx);
-    orb_select_kernel<<<P.nlevels, kSelThreads, 0, st>>>(P, s->d_surv_pos, s->d_cand_key, s->d_cand_resp, d_surv, d_counts, s->d_kept_pos,
-                                                         s->d_kept_resp, d_kept, d_status);
+    GB_CUDA(ctx, gb_launch_pdl(orb_select_kernel, dim3(P.nlevels), dim3(kSelThreads), 0, st, P, s->d_surv_pos, s->d_cand_key, s->d_cand_resp, d_surv,
+                               d_counts, s->d_kept_pos, s->d_kept_resp, d_kept, d_status));
     GB_LAUNCH_CHECK(ctx);
   }
   const int blocks = std::max(1, gb_div_up(out->capacity, kDescWarps));
-  orb_describe_kernel<<<blocks, kDescWarps * 32, sizeof(DescSmem) * kDescWarps, st>>>(
-      P, s->d_pyr, s->d_kept_pos, s->d_kept_resp, d_kept, s->d_pattern, out->d_kps, out->d_desc, out->capacity, out->d_count,
-      out->d_status, d_status);
+  GB_CUDA(ctx, gb_launch_pdl(orb_describe_kernel, dim3(blocks), dim3(kDescWarps * 32), sizeof(DescSmem) * kDescWarps, st, P, s->d_pyr, s->d_kept_pos,
+                             s->d_kept_resp, d_kept, s->d_pattern, out->d_kps, out->d_desc, out->capacity, out->d_count, out->d_status, d_status));
   GB_LAUNCH_CHECK(ctx);
   out->h_count = -1;
   return GB_OK;
