@@ -283,9 +283,9 @@ def main():
                     "steps": e2e_steps},
             "stages_ms": {"extract": t_ext, "match": t_match, "local_ba": t_ba},
             # dominant HBM-bound kernel of the path = the BA Jacobian sweep (BASELINE metric, 2nd clause), at config-5 size
-            "roofline": {"kernel": "BA Jacobian sweep K6 (ba_linearize_points + ba_linearize_cams), 500 cams/100k pts/1M obs",
+            "roofline": {"kernel": "BA Jacobian sweep K6 (ba_linearize_kernel: camera pass + landmark pass in one launch), 500 cams/100k pts/1M obs",
                          "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": 152.1e6, "traffic_source": "profiles/r01_ncu_summary.md (dram read+write of the two kernels, ncu --set full)",
+                         "traffic": 150.6e6, "traffic_source": "profiles/r01_ncu_summary.md (dram__bytes_read 44.25 MB + dram__bytes_write 106.36 MB of one launch, ncu --set full)",
                          "peak_source": peak_src, "algorithmic_bytes": int(big_bytes), "ms_per_sweep": t_sweep_big},
             # the same quantity for the kernels as they run inside the timed step (one frame / one 10k-observation window:
             # launch-latency-bound, reported for completeness)

@@ -55,9 +55,14 @@ __global__ void ba_rt_kernel(int nc, const double* __restrict__ pose, double* __
 // K6a: fused residual + Jacobian sweep, 8 lanes per landmark (lane k takes observations k, k+8, ... of the point-sorted
 // segment), fixed xor-tree over the 8 lanes -> V_j, g_p,j, cost_j; every lane writes the W blocks of its own observations.
 constexpr int kLpp = 8;
+// The W blocks (144 B per observation) leave through a per-warp shared-memory tile: a lane's nine 16-byte pieces would hit 32
+// half-written sectors per store instruction (144-byte lane stride); staged, the eight lanes of a landmark write its run of
+// consecutive blocks as full 128-byte lines.  The loop is warp-uniform (max over the four landmarks of a warp) and the camera
+// index / measurement of the NEXT round are requested before the current one is evaluated.
 __device__ __forceinline__ void ba_linearize_points_body(const BaDev& g, int block) {
+  __shared__ __align__(16) double s_w[kPtThreads / 32][32 * 18];
   const int gt = block * kPtThreads + threadIdx.x;
-  const int jraw = gt / kLpp, sub = gt % kLpp;
+  const int jraw = gt / kLpp, sub = gt % kLpp, lane = threadIdx.x & 31;
   const bool valid = jraw < g.np;
   const int j = valid ? jraw : 0;
   const double delta = g.sc->delta;
@@ -67,40 +72,68 @@ __device__ __forceinline__ void ba_linearize_points_body(const BaDev& g, int blo
 #pragma unroll
   for (int k = 0; k < 10; ++k) acc[k] = 0.0;
   const int e0 = g.pt_off[j], e1 = valid ? g.pt_off[j + 1] : e0;
-  for (int e = e0 + sub; e < e1; e += kLpp) {
-    const int i = g.o_cam[e];
-    const double* Rt = g.Rt + 12 * i;
-    const ObsLin o = eval_obs(Rt, p, g.o_uv[2 * e], g.o_uv[2 * e + 1], g.has_info ? g.o_info + 3 * e : nullptr, delta);
-    double* W = g.W + 18 * (size_t)e;
-    if (!o.valid) {
+  const int rounds = __reduce_max_sync(0xffffffffu, (e1 - e0 + kLpp - 1) / kLpp);
+  double* tile = s_w[threadIdx.x >> 5];
+  double2* mine = reinterpret_cast<double2*>(tile + 18 * lane);                     // this lane's block in the tile
+  const double2* run = reinterpret_cast<const double2*>(tile + 18 * (lane - sub));  // the landmark's eight blocks
+  int e = e0 + sub;
+  bool act = e < e1;
+  int i = act ? g.o_cam[e] : 0;
+  double2 uv = act ? *reinterpret_cast<const double2*>(g.o_uv + 2 * (size_t)e) : make_double2(0.0, 0.0);
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int en = e + kLpp;
+    const bool actn = en < e1;
+    const int i_nx = actn ? g.o_cam[en] : 0;
+    const double2 uv_nx = actn ? *reinterpret_cast<const double2*>(g.o_uv + 2 * (size_t)en) : make_double2(0.0, 0.0);
+    bool have = false;
+    if (act) {
+      const double* Rt = g.Rt + 12 * i;
+      const ObsLin o = eval_obs(Rt, p, uv.x, uv.y, g.has_info ? g.o_info + 3 * (size_t)e : nullptr, delta);
+      if (o.valid) {
+        have = true;
+        acc[9] += o.rho;
+        double Jc[12], Jp[6], AJp[6];
+        jac_cam(o, g.dof[i], Jc);
+        jac_pt(o, Rt, pf, Jp);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) reinterpret_cast<double2*>(W)[k] = make_double2(0.0, 0.0);
-      continue;
+        for (int d = 0; d < 3; ++d) {
+          AJp[d] = o.A0 * Jp[d] + o.A1 * Jp[3 + d];
+          AJp[3 + d] = o.A1 * Jp[d] + o.A2 * Jp[3 + d];
+        }
+        const double Ar0 = o.A0 * o.r0 + o.A1 * o.r1, Ar1 = o.A1 * o.r0 + o.A2 * o.r1;
+        double wv[18];
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) wv[a * 3 + c] = Jc[a] * AJp[c] + Jc[6 + a] * AJp[3 + c];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) mine[k] = make_double2(wv[2 * k], wv[2 * k + 1]);
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+#pragma unroll
+          for (int c = a; c < 3; ++c) acc[t++] += Jp[a] * AJp[c] + Jp[3 + a] * AJp[3 + c];
+          acc[6 + a] -= Jp[a] * Ar0 + Jp[3 + a] * Ar1;
+        }
+      }
     }
-    acc[9] += o.rho;
-    double Jc[12], Jp[6], AJp[6];
-    jac_cam(o, g.dof[i], Jc);
-    jac_pt(o, Rt, pf, Jp);
+    if (!have) {  // behind the camera / no observation in this round: a zero block
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      AJp[d] = o.A0 * Jp[d] + o.A1 * Jp[3 + d];
-      AJp[3 + d] = o.A1 * Jp[d] + o.A2 * Jp[3 + d];
+      for (int k = 0; k < 9; ++k) mine[k] = make_double2(0.0, 0.0);
     }
-    const double Ar0 = o.A0 * o.r0 + o.A1 * o.r1, Ar1 = o.A1 * o.r0 + o.A2 * o.r1;
-    double wv[18];
+    __syncwarp();
+    {  // the landmark's run of (at most eight) consecutive blocks: 9 x 16-byte pieces each, copied by its eight lanes
+      const int first = e0 + rd * kLpp;
+      const int pieces = 9 * max(0, min(kLpp, e1 - first));
+      double2* dst = reinterpret_cast<double2*>(g.W + 18 * (size_t)first);
 #pragma unroll
-    for (int a = 0; a < 6; ++a)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) wv[a * 3 + c] = Jc[a] * AJp[c] + Jc[6 + a] * AJp[3 + c];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) reinterpret_cast<double2*>(W)[k] = make_double2(wv[2 * k], wv[2 * k + 1]);  // 144 B = 9 x 16 B
-    int t = 0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-      for (int c = a; c < 3; ++c) acc[t++] += Jp[a] * AJp[c] + Jp[3 + a] * AJp[3 + c];
-      acc[6 + a] -= Jp[a] * Ar0 + Jp[3 + a] * Ar1;
+      for (int k = 0; k < 9; ++k) {
+        const int q = sub + kLpp * k;
+        if (q < pieces) dst[q] = run[q];
+      }
     }
+    __syncwarp();
+    e = en; act = actn; i = i_nx; uv = uv_nx;
   }
 #pragma unroll
   for (int k = 0; k < 10; ++k) {
@@ -133,15 +166,21 @@ __device__ __forceinline__ void ba_linearize_points_body(const BaDev& g, int blo
   }
 }
 
-// K6b: one CTA per camera; deterministic tree reduction of the 21 upper-triangular U entries + 6 gradient entries
-__device__ __forceinline__ void ba_linearize_cams_body(const BaDev& g, int i) {
+// K6b: cam_split CTAs per camera (each a contiguous slice of its camera-sorted observations); deterministic tree reduction of
+// the 21 upper-triangular U entries + 6 gradient entries inside the CTA, then -- when a camera is split -- the LAST CTA of the
+// camera to finish (per-camera ticket) folds the slices' partial sums in slice order.  Bit-reproducible run to run.
+__device__ __forceinline__ void ba_linearize_cams_body(const BaDev& g, int cta) {
+  const int K = g.cam_split, i = cta / K, slice = cta - i * K;
   const double delta = g.sc->delta;
   const double* Rt = g.Rt + 12 * i;
   const int dm = g.dof[i];
+  const int c0 = g.cam_off[i], c1 = g.cam_off[i + 1];
+  const int per = (c1 - c0 + K - 1) / K;
+  const int s0 = min(c0 + slice * per, c1), s1 = min(s0 + per, c1);
   double acc[27];
 #pragma unroll
   for (int k = 0; k < 27; ++k) acc[k] = 0.0;
-  for (int idx = g.cam_off[i] + threadIdx.x; idx < g.cam_off[i + 1]; idx += kCamThreads) {
+  for (int idx = s0 + threadIdx.x; idx < s1; idx += kCamThreads) {
     const int j = g.c_pt[idx];
     const double2 uv = *reinterpret_cast<const double2*>(g.c_uv + 2 * (size_t)idx);
     const double p[3] = {g.pts[3 * (size_t)j], g.pts[3 * (size_t)j + 1], g.pts[3 * (size_t)j + 2]};
@@ -166,6 +205,7 @@ __device__ __forceinline__ void ba_linearize_cams_body(const BaDev& g, int i) {
   }
   // deterministic reduction: fixed shuffle tree inside each warp, then the 4 warp partials are summed in order
   __shared__ double s_red[kCamThreads / 32][27];
+  __shared__ int s_last;
 #pragma unroll
   for (int k = 0; k < 27; ++k) {
 #pragma unroll
@@ -181,6 +221,21 @@ __device__ __forceinline__ void ba_linearize_cams_body(const BaDev& g, int i) {
 #pragma unroll
     for (int w = 0; w < kCamThreads / 32; ++w) r += s_red[w][threadIdx.x];
     s_red[0][threadIdx.x] = r;
+    if (K > 1) g.cam_part[((size_t)i * K + slice) * 27 + threadIdx.x] = r;
+  }
+  if (K > 1) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&g.cam_ticket[i], 1u) == (unsigned)(K - 1)) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < 27) {
+      double r = 0.0;
+      for (int k = 0; k < K; ++k) r += __ldcg(&g.cam_part[((size_t)i * K + k) * 27 + threadIdx.x]);
+      s_red[0][threadIdx.x] = r;
+    }
+    if (threadIdx.x == 0) g.cam_ticket[i] = 0;
   }
   __syncthreads();
   if (threadIdx.x < 36) {
@@ -191,15 +246,15 @@ __device__ __forceinline__ void ba_linearize_cams_body(const BaDev& g, int i) {
   if (threadIdx.x < 6) g.gc[6 * i + threadIdx.x] = s_red[0][21 + threadIdx.x];
 }
 
-// One launch for the whole sweep: the first `pt_blocks` CTAs run the landmark pass (K6a), the remaining CTAs the camera
-// pass (K6b); the two are independent.
+// One launch for the whole sweep: the first `cam_blocks` CTAs run the camera pass (K6b: long serial slices, so they start
+// first), the remaining CTAs the landmark pass (K6a); the two are independent.
 static_assert(kPtThreads == kCamThreads, "the fused sweep launch uses one block size");
-__global__ void __launch_bounds__(kPtThreads) ba_linearize_kernel(BaDev g, int pt_blocks) {
+__global__ void __launch_bounds__(kPtThreads) ba_linearize_kernel(BaDev g, int cam_blocks) {
   gb_pdl_launch_dependents();
   gb_pdl_wait();
   if (g.sc->stop || !g.sc->need_linearize) return;
-  if ((int)blockIdx.x < pt_blocks) ba_linearize_points_body(g, blockIdx.x);
-  else ba_linearize_cams_body(g, blockIdx.x - pt_blocks);
+  if ((int)blockIdx.x < cam_blocks) ba_linearize_cams_body(g, blockIdx.x);
+  else ba_linearize_points_body(g, blockIdx.x - cam_blocks);
 }
 // (the camera pass alone: used for the pose information matrix of optimizePnP)
 __global__ void __launch_bounds__(kCamThreads) ba_linearize_cams_kernel(BaDev g) {
@@ -1317,6 +1372,7 @@ struct gb_ba_graph {
   bool pcg_sparse = false;
   size_t pcg_sparse_smem = 0;
   int pcg_max_row_blocks = 0;  // longest block row of S
+  bool sweep_only = false;     // the last begin came from gb_ba_graph_sweep and nothing else ran since
   int pcg_nact = 0;            // cameras with at least one free dof (the sparse PCG kernel gives lanes to these only)
   int pcg_cluster = 0;
   size_t pcg_smem = 0;
@@ -1522,6 +1578,14 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + b_sr + 4 * b_sc + b_cpt + b_cuv + 256;
   const size_t n6 = 6 * (size_t)nc;
   uint8_t* dblob = nullptr;
+  double* cam_ticket_d = nullptr;
+  {  // camera-pass split: ~256 observations per CTA, at most 16 CTAs per camera
+    int max_obs = 0;
+    for (int i = 0; i < nc; ++i) max_obs = std::max(max_obs, cam_off[i + 1] - cam_off[i]);
+    // measured on the 1M-observation graph: 25 us unsplit, 31 / 38 / 54 us at 2 / 4 / 8 slices (the 27-value block reduction per
+    // CTA outweighs the shorter serial slices) -> split only cameras that would otherwise run alone for a long time
+    d.cam_split = std::min(16, std::max(1, max_obs / 8192));
+  }
   auto layout = [&](Slab& sl) {
     sl.take(&dblob, blob);
     sl.take(&g->pose_init, (size_t)nc * 7); sl.take(&g->pose_wc_out, (size_t)nc * 7);
@@ -1531,6 +1595,7 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
     sl.take(&d.V, (size_t)np * 9); sl.take(&d.gp, (size_t)np * 3); sl.take(&d.Vinv, (size_t)np * 9);
     sl.take(&d.W, (size_t)no * 18); sl.take(&d.U, (size_t)nc * 36); sl.take(&d.gc, (size_t)nc * 6);
     sl.take(&d.cost_pt, (size_t)np); sl.take(&d.cost_pt_new, (size_t)np);
+    sl.take(&d.cam_part, (size_t)nc * d.cam_split * 27); sl.take(&cam_ticket_d, (size_t)nc / 2 + 1);
     sl.take(&d.Minv, (size_t)nc * 36);
     sl.take(&d.Sb, (size_t)d.s_nnzb * 36);
     sl.take(&d.x, n6); sl.take(&d.r, n6); sl.take(&d.z, n6); sl.take(&d.p, n6); sl.take(&d.q, n6); sl.take(&d.sv, n6);
@@ -1607,6 +1672,8 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   if (!s_tidx.empty()) memcpy(h + o_st, s_tidx.data(), s_tidx.size() * 4);
   g->sorted_to_orig.swap(order);
   GB_CUDA(ctx, cudaMemcpyAsync(dblob, h, blob, cudaMemcpyHostToDevice, ctx->stream));
+  d.cam_ticket = reinterpret_cast<unsigned int*>(cam_ticket_d);
+  GB_CUDA(ctx, cudaMemsetAsync(d.cam_ticket, 0, ((size_t)nc / 2 + 1) * 8, ctx->stream));
   double* d_pose_wc = (double*)(dblob + o_pose);
   g->pts_init = (double*)(dblob + o_pts);
   d.dof = dblob + o_dof; d.pfree = dblob + o_pf;
@@ -1668,6 +1735,7 @@ int gb_ba_graph_begin(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt_in) 
     GB_LAUNCH_CHECK(ctx);
   }
   g->begun = true;
+  g->sweep_only = false;
   return GB_OK;
 }
 
@@ -1705,10 +1773,13 @@ int gb_ba_graph_sweep(gb_ctx* ctx, gb_ba_graph* g, double huber_delta) {
   gb_ba_options o;
   gb_ba_options_default(&o);
   o.huber_delta = huber_delta;
-  GB_CHECK(gb_ba_graph_begin(ctx, g, &o));
+  if (!g->begun || !g->sweep_only || g->opt.huber_delta != huber_delta) {  // (repeated sweeps re-use the scalars: nothing resets need_linearize)
+    GB_CHECK(gb_ba_graph_begin(ctx, g, &o));
+    g->sweep_only = true;
+  }
   BaDev& d = g->d;
-  const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads);
-  if (pt_blocks + d.nc > 0) { ba_linearize_kernel<<<pt_blocks + d.nc, kPtThreads, 0, ctx->stream>>>(d, pt_blocks); GB_LAUNCH_CHECK(ctx); }
+  const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads), cam_blocks = d.nc * d.cam_split;
+  if (pt_blocks + cam_blocks > 0) { ba_linearize_kernel<<<pt_blocks + cam_blocks, kPtThreads, 0, ctx->stream>>>(d, cam_blocks); GB_LAUNCH_CHECK(ctx); }
   return GB_OK;
 }
 
@@ -1719,8 +1790,8 @@ int gb_ba_graph_reduce_local(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   if (!buf) buf = g->buf;
   cudaStream_t s = ctx->stream;
   {
-    const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads);
-    if (pt_blocks + d.nc > 0) { ba_linearize_kernel<<<pt_blocks + d.nc, kPtThreads, 0, s>>>(d, pt_blocks); GB_LAUNCH_CHECK(ctx); }
+    const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads), cam_blocks = d.nc * d.cam_split;
+    if (pt_blocks + cam_blocks > 0) { ba_linearize_kernel<<<pt_blocks + cam_blocks, kPtThreads, 0, s>>>(d, cam_blocks); GB_LAUNCH_CHECK(ctx); }
   }
   // Schur complement.  With the covisibility block structure at hand (<= 1024 cameras) S is formed block by block without
   // atomics (deterministic); the local-BA solver consumes the block-CSR directly, every other consumer (one-cluster / generic
@@ -1842,9 +1913,9 @@ int gb_ba_graph_solve(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, gb_
     if (local4) {
       BaDev& d = g->d;
       cudaStream_t s = ctx->stream;
-      const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads);
+      const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads), cam_blocks = d.nc * d.cam_split;
       // (programmatic dependent launches: each kernel is scheduled while its predecessor drains)
-      GB_CUDA(ctx, gb_launch_pdl(ba_linearize_kernel, dim3(pt_blocks + d.nc), dim3(kPtThreads), 0, s, d, pt_blocks)); GB_LAUNCH_CHECK(ctx);
+      GB_CUDA(ctx, gb_launch_pdl(ba_linearize_kernel, dim3(pt_blocks + cam_blocks), dim3(kPtThreads), 0, s, d, cam_blocks)); GB_LAUNCH_CHECK(ctx);
       GB_CUDA(ctx, gb_launch_pdl(ba_schur_blocks_kernel, dim3(d.s_nupper), dim3(128), 0, s, d, g->buf)); GB_LAUNCH_CHECK(ctx);
       if (g->pcg_nact <= kSpSmallCams) GB_CUDA(ctx, gb_launch_pdl(BA_SPARSE_SMALL, dim3(1), dim3(kSpSmallThreads), g->pcg_sparse_smem, s, d, g->buf, (int)g->opt.pcg_max_iters));
       else GB_CUDA(ctx, gb_launch_pdl(BA_SPARSE_LARGE, dim3(1), dim3(kSpLargeThreads), g->pcg_sparse_smem, s, d, g->buf, (int)g->opt.pcg_max_iters));
@@ -1935,7 +2006,7 @@ int gb_ba_pnp(gb_ctx* ctx, int n, const double* xyz, const double* xy1, double* 
     if (rc == GB_OK) {
       h.stop = 0; h.need_linearize = 1;
       cudaMemcpyAsync(g->d.sc, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream);
-      ba_linearize_cams_kernel<<<1, kCamThreads, 0, ctx->stream>>>(g->d);
+      ba_linearize_cams_kernel<<<g->d.nc * g->d.cam_split, kCamThreads, 0, ctx->stream>>>(g->d);
       ctx->launches++;
       cudaMemcpyAsync(info6x6, g->d.U, 36 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
       cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -2007,6 +2078,20 @@ GB_API int gb_dbg_ba_force_generic_pcg(gb_ctx* ctx, gb_ba_graph* g, int on) {
 }
 
 GB_API int gb_dbg_ba_pcg_sparse(gb_ctx* ctx, gb_ba_graph* g) { return (ctx && g) ? (g->pcg_sparse ? g->d.s_nnzb : 0) : -1; }
+
+// one half of the sweep alone (which = 1: camera pass, 2: landmark pass), with an explicit camera split (0 = the graph's own)
+GB_API int gb_dbg_ba_sweep_part(gb_ctx* ctx, gb_ba_graph* g, int which, int split) {
+  if (!ctx || !g || !g->begun) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  BaDev d = g->d;
+  if (split > 0 && split <= g->d.cam_split) d.cam_split = split;
+  const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads), cam_blocks = d.nc * d.cam_split;
+  if (which == 1 && cam_blocks > 0) ba_linearize_kernel<<<cam_blocks, kPtThreads, 0, ctx->stream>>>(d, cam_blocks);
+  if (which == 2 && pt_blocks > 0) ba_linearize_kernel<<<pt_blocks, kPtThreads, 0, ctx->stream>>>(d, 0);
+  if (which == 3) ba_linearize_kernel<<<pt_blocks + cam_blocks, kPtThreads, 0, ctx->stream>>>(d, cam_blocks);
+  GB_LAUNCH_CHECK(ctx);
+  return GB_OK;
+}
 
 GB_API int gb_dbg_ba_pcg_cluster_size(gb_ctx* ctx, gb_ba_graph* g) { return (ctx && g) ? g->pcg_cluster : -1; }
 

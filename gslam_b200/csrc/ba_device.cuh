@@ -41,6 +41,10 @@ struct BaDev {
   int s_nnzb;
   // linearisation
   double *V, *gp, *Vinv, *W, *U, *gc, *cost_pt, *cost_pt_new;
+  // camera pass split: cam_split CTAs per camera, partial [27] sums + a per-camera ticket (the last CTA folds them in order)
+  int cam_split;
+  double* cam_part;
+  unsigned int* cam_ticket;
   // PCG
   double *Minv, *x, *r, *z, *p, *q, *sv;  // generic PCG: z = u = Minv r, q = w = S u, sv = S p
   BaScalars* sc;

@@ -1,0 +1,29 @@
+"""Times the fused BA residual+Jacobian sweep on the config-5-shaped graph (500 cams / 100k landmarks / 1M observations)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gslam_b200 import synth
+from gslam_b200.api import Context, BAGraph
+
+ctx = Context(0)
+for shape in ((500, 100000, 10), (50, 2000, 5)):
+    pb = synth.synth_ba(*shape, seed=42, n_fixed=2)
+    g = BAGraph(ctx, pb)
+    g.sweep(0.01); ctx.sync()
+    best = 1e9
+    for _ in range(3):
+        ctx.timer_begin()
+        for r in range(20):
+            g.sweep(0.01)
+        best = min(best, ctx.timer_end() / 20)
+    b = 168 * pb.n_obs + 96 * pb.n_points + 272 * pb.n_cams
+    print(f"{shape}: {best * 1e3:.1f} us per sweep, {b / best / 1e6:.0f} GB/s algorithmic")
+    import ctypes as C
+    from gslam_b200 import capi
+    L = capi.lib(); L.gb_dbg_ba_sweep_part.restype = C.c_int; L.gb_dbg_ba_sweep_part.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    for which, split in ((1, 0), (2, 0), (3, 0)):
+        L.gb_dbg_ba_sweep_part(ctx._h, g._h, which, split); ctx.sync()
+        ctx.timer_begin()
+        for r in range(20):
+            L.gb_dbg_ba_sweep_part(ctx._h, g._h, which, split)
+        print(f"   part {which} split {split}: {ctx.timer_end() / 20 * 1e3:.1f} us")
+    g.close()
