@@ -293,6 +293,10 @@ class BAGraph:
         """PCG dispatch override (test hook): 0 auto, 1 generic multi-kernel, 2 one-cluster DSMEM, 3 single-CTA block-sparse."""
         self.ctx._check(self.ctx._lib.gb_dbg_ba_force_generic_pcg(self.ctx._h, self._h, int(mode)))
 
+    def set_cam_split(self, split: int):
+        """CTAs per camera of the sweep's camera pass (test hook, 1..4; production graphs pick it from the longest camera)."""
+        self.ctx._check(self.ctx._lib.gb_dbg_ba_set_cam_split(self.ctx._h, self._h, int(split)))
+
     def pcg_sparse_blocks(self) -> int:
         return int(self.ctx._lib.gb_dbg_ba_pcg_sparse(self.ctx._h, self._h))
 

@@ -97,6 +97,8 @@ _DEBUG_SIGNATURES = [
     ("gb_dbg_ba_force_generic_pcg", C.c_int, [_VP, _VP, C.c_int]),
     ("gb_dbg_ba_pcg_cluster_size", C.c_int, [_VP, _VP]),
     ("gb_dbg_ba_pcg_sparse", C.c_int, [_VP, _VP]),
+    ("gb_dbg_ba_set_cam_split", C.c_int, [_VP, _VP, C.c_int]),
+    ("gb_dbg_ba_sweep_part", C.c_int, [_VP, _VP, C.c_int]),
 ]
 
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]

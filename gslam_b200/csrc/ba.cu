@@ -1595,7 +1595,7 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
     sl.take(&d.V, (size_t)np * 9); sl.take(&d.gp, (size_t)np * 3); sl.take(&d.Vinv, (size_t)np * 9);
     sl.take(&d.W, (size_t)no * 18); sl.take(&d.U, (size_t)nc * 36); sl.take(&d.gc, (size_t)nc * 6);
     sl.take(&d.cost_pt, (size_t)np); sl.take(&d.cost_pt_new, (size_t)np);
-    sl.take(&d.cam_part, (size_t)nc * d.cam_split * 27); sl.take(&cam_ticket_d, (size_t)nc / 2 + 1);
+    sl.take(&d.cam_part, (size_t)nc * std::max(d.cam_split, 4) * 27); sl.take(&cam_ticket_d, (size_t)nc / 2 + 1);
     sl.take(&d.Minv, (size_t)nc * 36);
     sl.take(&d.Sb, (size_t)d.s_nnzb * 36);
     sl.take(&d.x, n6); sl.take(&d.r, n6); sl.take(&d.z, n6); sl.take(&d.p, n6); sl.take(&d.q, n6); sl.take(&d.sv, n6);
@@ -2079,12 +2079,20 @@ GB_API int gb_dbg_ba_force_generic_pcg(gb_ctx* ctx, gb_ba_graph* g, int on) {
 
 GB_API int gb_dbg_ba_pcg_sparse(gb_ctx* ctx, gb_ba_graph* g) { return (ctx && g) ? (g->pcg_sparse ? g->d.s_nnzb : 0) : -1; }
 
-// one half of the sweep alone (which = 1: camera pass, 2: landmark pass), with an explicit camera split (0 = the graph's own)
-GB_API int gb_dbg_ba_sweep_part(gb_ctx* ctx, gb_ba_graph* g, int which, int split) {
+// force the camera-pass split (1..4 CTAs per camera; the partial-sum buffer always has room for 4): lets the tests cover the
+// sliced path on small graphs
+GB_API int gb_dbg_ba_set_cam_split(gb_ctx* ctx, gb_ba_graph* g, int split) {
+  if (!ctx || !g || split < 1 || split > 4) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  g->d.cam_split = split;
+  return GB_OK;
+}
+
+// one half of the sweep alone (which = 1: camera pass, 2: landmark pass, 3: both) -- timing experiments (tools/sweep_bench.py)
+GB_API int gb_dbg_ba_sweep_part(gb_ctx* ctx, gb_ba_graph* g, int which) {
   if (!ctx || !g || !g->begun) return GB_ERR_INVALID;
   CtxLock lk(ctx);
-  BaDev d = g->d;
-  if (split > 0 && split <= g->d.cam_split) d.cam_split = split;
+  BaDev& d = g->d;
   const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads), cam_blocks = d.nc * d.cam_split;
   if (which == 1 && cam_blocks > 0) ba_linearize_kernel<<<cam_blocks, kPtThreads, 0, ctx->stream>>>(d, cam_blocks);
   if (which == 2 && pt_blocks > 0) ba_linearize_kernel<<<pt_blocks, kPtThreads, 0, ctx->stream>>>(d, 0);

@@ -1,7 +1,7 @@
 """Times the fused BA residual+Jacobian sweep on the config-5-shaped graph (500 cams / 100k landmarks / 1M observations)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from gslam_b200 import synth
+from gslam_b200 import capi, synth
 from gslam_b200.api import Context, BAGraph
 
 ctx = Context(0)
@@ -17,13 +17,11 @@ for shape in ((500, 100000, 10), (50, 2000, 5)):
         best = min(best, ctx.timer_end() / 20)
     b = 168 * pb.n_obs + 96 * pb.n_points + 272 * pb.n_cams
     print(f"{shape}: {best * 1e3:.1f} us per sweep, {b / best / 1e6:.0f} GB/s algorithmic")
-    import ctypes as C
-    from gslam_b200 import capi
-    L = capi.lib(); L.gb_dbg_ba_sweep_part.restype = C.c_int; L.gb_dbg_ba_sweep_part.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
-    for which, split in ((1, 0), (2, 0), (3, 0)):
-        L.gb_dbg_ba_sweep_part(ctx._h, g._h, which, split); ctx.sync()
+    L = capi.lib()
+    for which in (1, 2, 3):
+        L.gb_dbg_ba_sweep_part(ctx._h, g._h, which); ctx.sync()
         ctx.timer_begin()
         for r in range(20):
-            L.gb_dbg_ba_sweep_part(ctx._h, g._h, which, split)
-        print(f"   part {which} split {split}: {ctx.timer_end() / 20 * 1e3:.1f} us")
+            L.gb_dbg_ba_sweep_part(ctx._h, g._h, which)
+        print(f"   part {which} (1 camera pass, 2 landmark pass, 3 both): {ctx.timer_end() / 20 * 1e3:.1f} us")
     g.close()
