@@ -17,7 +17,9 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 
 using namespace ba;
 
@@ -1475,6 +1477,19 @@ static void ba_pick_pcg(gb_ctx* ctx, gb_ba_graph* g) {
 
 static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out, bool use_arena);
 
+// GB_BA_TRACE=1: wall-clock stamps of the host-side phases of a host-buffer solve (stderr), for tools/e2e_breakdown.py
+struct BaTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  BaTrace() : on(getenv("GB_BA_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void stamp(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gb_ba trace] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 extern "C" {
 
 void gb_ba_options_default(gb_ba_options* o) {
@@ -1514,7 +1529,9 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   if (!ctx || !out) return GB_ERR_INVALID;
   *out = nullptr;
   CtxLock lk(ctx);
+  BaTrace tr;
   GB_CHECK(ba_validate(ctx, pb));
+  tr.stamp("validate");
   const int nc = pb->n_cams, np = pb->n_points, no = pb->n_obs;
   gb_ba_graph* g = new gb_ba_graph();
   struct Guard {
@@ -1539,6 +1556,7 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   for (int i = 0; i < nc; ++i) cam_off[i + 1] += cam_off[i];
   { std::vector<int> pos(cam_off.begin(), cam_off.end()); for (int e = 0; e < no; ++e) cam_perm[pos[pb->obs_cam[order[e]]]++] = e; }
 
+  tr.stamp("counting sorts");
   // ---- layout: one slab = [uploaded blob | working set] ----------------------------------------------------------------
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t b_pose = al((size_t)nc * 7 * 8), b_pts = al((size_t)np * 3 * 8), b_dof = al(nc), b_pf = al(np),
@@ -1548,17 +1566,29 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   // covisibility block structure of S: block (i,i') is structurally non-zero iff some landmark is seen by both cameras
   std::vector<int> s_rowptr(nc + 1, 0), s_col, s_brow;
   if (nc > 0 && nc <= 1024) {
-    std::vector<uint8_t> mark((size_t)nc * nc, 0);
-    for (int i = 0; i < nc; ++i) mark[(size_t)i * nc + i] = 1;
-    for (int j = 0; j < np; ++j)
-      for (int e = pt_off[j]; e < pt_off[j + 1]; ++e) {
-        const int i = pb->obs_cam[order[e]];
-        uint8_t* row = &mark[(size_t)i * nc];
-        for (int f = pt_off[j]; f < pt_off[j + 1]; ++f) row[pb->obs_cam[order[f]]] = 1;
+    // one bit row per camera; a landmark ORs the bit mask of its observers into the row of each of them
+    const int words = (nc + 63) / 64;
+    std::vector<uint64_t> rows((size_t)nc * words, 0), mask(words);
+    for (int i = 0; i < nc; ++i) rows[(size_t)i * words + (i >> 6)] |= 1ull << (i & 63);
+    for (int j = 0; j < np; ++j) {
+      const int a = pt_off[j], b = pt_off[j + 1];
+      if (b - a < 2) continue;
+      std::fill(mask.begin(), mask.end(), 0ull);
+      for (int e = a; e < b; ++e) { const int i = pb->obs_cam[order[e]]; mask[i >> 6] |= 1ull << (i & 63); }
+      for (int e = a; e < b; ++e) {
+        uint64_t* row = &rows[(size_t)pb->obs_cam[order[e]] * words];
+        for (int w = 0; w < words; ++w) row[w] |= mask[w];
       }
+    }
     for (int i = 0; i < nc; ++i) {
-      for (int k = 0; k < nc; ++k)
-        if (mark[(size_t)i * nc + k]) { s_col.push_back(k); s_brow.push_back(i); }
+      for (int w = 0; w < words; ++w) {
+        uint64_t m = rows[(size_t)i * words + w];
+        while (m) {
+          const int k = (w << 6) + __builtin_ctzll(m);
+          m &= m - 1;
+          s_col.push_back(k); s_brow.push_back(i);
+        }
+      }
       s_rowptr[i + 1] = (int)s_col.size();
     }
   }
@@ -1572,6 +1602,7 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
     s_tidx[blk] = t;
   }
   d.s_nupper = (int)s_upper.size();
+  tr.stamp("covisibility block-CSR");
   for (int i = 0; i < nc; ++i) g->pcg_nact += (pb->cam_dof ? (pb->cam_dof[i] & 63) : 63) != 0;
   for (int i = 0; i < nc && !s_col.empty(); ++i) g->pcg_max_row_blocks = std::max(g->pcg_max_row_blocks, s_rowptr[i + 1] - s_rowptr[i]);
   const size_t b_sr = al((size_t)(nc + 1) * 4), b_sc = al((size_t)s_col.size() * 4 + 4);
@@ -1627,6 +1658,7 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   real.base = g->slab;
   layout(real);
 
+  tr.stamp("slab");
   // ---- one pinned blob, one H2D ------------------------------------------------------------------------------------------
   GB_CHECK(gb_stage_reserve(ctx, ctx->h_stage_off + blob + 4096));
   uint8_t* h = (uint8_t*)gb_stage_alloc(ctx, blob);
@@ -1671,6 +1703,7 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   if (!s_upper.empty()) memcpy(h + o_su, s_upper.data(), s_upper.size() * 4);
   if (!s_tidx.empty()) memcpy(h + o_st, s_tidx.data(), s_tidx.size() * 4);
   g->sorted_to_orig.swap(order);
+  tr.stamp("blob fill");
   GB_CUDA(ctx, cudaMemcpyAsync(dblob, h, blob, cudaMemcpyHostToDevice, ctx->stream));
   d.cam_ticket = reinterpret_cast<unsigned int*>(cam_ticket_d);
   GB_CUDA(ctx, cudaMemsetAsync(d.cam_ticket, 0, ((size_t)nc / 2 + 1) * 8, ctx->stream));
@@ -1689,7 +1722,11 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   }
   GB_CHECK(gb_ba_graph_reset(ctx, g));
   ba_pick_pcg(ctx, g);
-  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the pinned blob is reused by the next call
+  tr.stamp("enqueue H2D + prepare");
+  // the pinned blob is reused by the next outermost call on this ctx: a graph handed to the caller must have consumed it; the
+  // one-shot host-buffer paths (gb_ba_solve / gb_ba_pnp) synchronise in their own finish + download before they return
+  if (!use_arena) GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  tr.stamp("sync");
   guard.ok = true;
   *out = g;
   return GB_OK;
@@ -1895,7 +1932,9 @@ int gb_ba_graph_finish(gb_ctx* ctx, gb_ba_graph* g, gb_ba_result* res) {
   return GB_OK;
 }
 
-int gb_ba_graph_solve(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, gb_ba_result* res) {
+// LM loop of a whole solve, then ONE synchronisation for everything the host wants back: the LM scalars and, for the one-shot
+// host-buffer paths, the final T_wc poses / points (pose_out / pts_out may be null).
+static int ba_graph_solve_impl(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, gb_ba_result* res, double* pose_out, double* pts_out) {
   if (!ctx || !g) return GB_ERR_INVALID;
   CtxLock lk(ctx);
   GB_CHECK(gb_ba_graph_begin(ctx, g, opt));
@@ -1941,12 +1980,42 @@ int gb_ba_graph_solve(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, gb_
     }
   }
   GB_CUDA(ctx, cudaEventRecord(ctx->eve, ctx->stream));
-  GB_CHECK(gb_ba_graph_finish(ctx, g, res));
+  BaDev& dd = g->d;
+  const size_t bp = pose_out ? (size_t)dd.nc * 56 : 0, bx = pts_out ? (size_t)dd.np * 24 : 0;
+  GB_CHECK(gb_stage_reserve(ctx, ctx->h_stage_off + bp + bx + sizeof(BaScalars) + 1024));
+  BaScalars* hs = (BaScalars*)gb_stage_alloc(ctx, sizeof(BaScalars));
+  double* hp = bp ? (double*)gb_stage_alloc(ctx, bp + 8) : nullptr;
+  double* hx = bx ? (double*)gb_stage_alloc(ctx, bx + 8) : nullptr;
+  GB_CUDA(ctx, cudaMemcpyAsync(hs, dd.sc, sizeof(BaScalars), cudaMemcpyDeviceToHost, ctx->stream));
+  if (hp) {
+    ba_finalize_kernel<<<gb_div_up(dd.nc, 128), 128, 0, ctx->stream>>>(dd.nc, dd.pose, g->pose_wc_out);
+    GB_LAUNCH_CHECK(ctx);
+    GB_CUDA(ctx, cudaMemcpyAsync(hp, g->pose_wc_out, bp, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (hx) GB_CUDA(ctx, cudaMemcpyAsync(hx, dd.pts, bx, cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const BaScalars& h = *hs;
   if (res) {
-    GB_CUDA(ctx, cudaEventSynchronize(ctx->eve));
+    res->initial_cost = h.initial_cost;
+    res->final_cost = h.cost;
+    res->iterations = h.iterations;
+    res->accepted = h.accepted;
+    res->pcg_iterations = h.pcg_iters;
+    res->status = h.status;
+    res->lambda_final = h.lambda;
     GB_CUDA(ctx, cudaEventElapsedTime(&res->gpu_ms, ctx->evs, ctx->eve));
   }
+  if (!std::isfinite(h.cost)) {
+    gb_set_error(ctx, "gb_ba: non-finite cost");
+    return GB_ERR_NUMERIC;
+  }
+  if (hp) memcpy(pose_out, hp, bp);
+  if (hx) memcpy(pts_out, hx, bx);
   return GB_OK;
+}
+
+int gb_ba_graph_solve(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, gb_ba_result* res) {
+  return ba_graph_solve_impl(ctx, g, opt, res, nullptr, nullptr);
 }
 
 int gb_ba_graph_download(gb_ctx* ctx, gb_ba_graph* g, double* cam_pose_wc, double* points) {
@@ -1974,9 +2043,11 @@ int gb_ba_solve(gb_ctx* ctx, gb_ba_problem* pb, const gb_ba_options* opt, gb_ba_
   CtxLock lk(ctx);
   gb_ba_graph* g = nullptr;
   GB_CHECK(ba_graph_create_impl(ctx, pb, &g, true));
-  int rc = gb_ba_graph_solve(ctx, g, opt, res);
-  if (rc == GB_OK) rc = gb_ba_graph_download(ctx, g, pb->cam_pose_wc, pb->points);
+  BaTrace tr;
+  const int rc = ba_graph_solve_impl(ctx, g, opt, res, g->d.nc > 0 ? pb->cam_pose_wc : nullptr, g->d.np > 0 ? pb->points : nullptr);
+  tr.stamp("solve + download (one sync)");
   gb_ba_graph_destroy(ctx, g);
+  tr.stamp("destroy");
   return rc;
 }
 
@@ -1997,8 +2068,7 @@ int gb_ba_pnp(gb_ctx* ctx, int n, const double* xyz, const double* xy1, double* 
   pb.obs_cam = oc.data(); pb.obs_point = op.data(); pb.obs_xyz = xy1; pb.obs_info = nullptr;
   gb_ba_graph* g = nullptr;
   GB_CHECK(ba_graph_create_impl(ctx, &pb, &g, true));
-  int rc = gb_ba_graph_solve(ctx, g, opt, res);
-  if (rc == GB_OK) rc = gb_ba_graph_download(ctx, g, pose_wc, nullptr);
+  int rc = ba_graph_solve_impl(ctx, g, opt, res, pose_wc, nullptr);
   if (rc == GB_OK && info6x6) {
     // information of the returned pose: U at the final estimate (re-linearise once; the graph holds the final state)
     BaScalars h;

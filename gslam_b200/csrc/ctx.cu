@@ -249,22 +249,53 @@ int gb_features_upload(gb_ctx* ctx, gb_features* f, const gb_keypoint* kps, cons
 int gb_features_download(gb_ctx* ctx, gb_features* f, gb_keypoint* kps, uint8_t* desc, int* n) {
   if (!ctx || !f || !n) return GB_ERR_INVALID;
   CtxLock lk(ctx);
-  int cap = *n, cnt = 0;
-  GB_CHECK(gb_features_count(ctx, f, &cnt));
-  *n = cnt;
-  if (cnt > cap) {
-    gb_set_error(ctx, "gb_features_download: %d keypoints > caller capacity %d", cnt, cap);
-    return GB_ERR_CAPACITY;
+  const int cap = *n;
+  int cnt = 0;
+  if (f->h_count >= 0) {
+    cnt = f->h_count;
+  } else if (cap <= 0) {
+    GB_CHECK(gb_features_count(ctx, f, &cnt));
   }
-  if (cnt == 0) return GB_OK;
-  GB_CHECK(gb_stage_reserve(ctx, ctx->h_stage_off + (size_t)cnt * 60 + 1024));
-  gb_keypoint* hk = kps ? (gb_keypoint*)gb_stage_alloc(ctx, (size_t)cnt * sizeof(gb_keypoint)) : nullptr;
-  uint8_t* hd = desc ? (uint8_t*)gb_stage_alloc(ctx, (size_t)cnt * 32) : nullptr;
-  if (hk) GB_CUDA(ctx, cudaMemcpyAsync(hk, f->d_kps, (size_t)cnt * sizeof(gb_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
-  if (hd) GB_CUDA(ctx, cudaMemcpyAsync(hd, f->d_desc, (size_t)cnt * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  // When the count is not on the host yet (the extraction is still in flight) the count word travels WITH the rows: up to
+  // min(cap, capacity) rows are copied speculatively, so that a host-buffer extraction costs ONE synchronisation, not two.
+  const bool speculative = f->h_count < 0 && cap > 0;
+  const int rows = speculative ? std::min(cap, f->capacity) : cnt;
+  if (!speculative) {
+    *n = cnt;
+    if (cnt > cap) {
+      gb_set_error(ctx, "gb_features_download: %d keypoints > caller capacity %d", cnt, cap);
+      return GB_ERR_CAPACITY;
+    }
+    if (cnt == 0) return GB_OK;
+  }
+  GB_CHECK(gb_stage_reserve(ctx, ctx->h_stage_off + (size_t)rows * 60 + 1024));
+  int* hc = (int*)gb_stage_alloc(ctx, 16);
+  gb_keypoint* hk = kps ? (gb_keypoint*)gb_stage_alloc(ctx, (size_t)rows * sizeof(gb_keypoint)) : nullptr;
+  uint8_t* hd = desc ? (uint8_t*)gb_stage_alloc(ctx, (size_t)rows * 32) : nullptr;
+  if (speculative) GB_CUDA(ctx, cudaMemcpyAsync(hc, f->d_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (hk && rows > 0) GB_CUDA(ctx, cudaMemcpyAsync(hk, f->d_kps, (size_t)rows * sizeof(gb_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
+  if (hd && rows > 0) GB_CUDA(ctx, cudaMemcpyAsync(hd, f->d_desc, (size_t)rows * 32, cudaMemcpyDeviceToHost, ctx->stream));
   GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  if (hk) memcpy(kps, hk, (size_t)cnt * sizeof(gb_keypoint));
-  if (hd) memcpy(desc, hd, (size_t)cnt * 32);
+  if (speculative) {
+    if (hc[1] < 0) {
+      *n = 0;
+      gb_set_error(ctx, "extract: internal overflow (%s)", hc[1] == -2 ? "more than 4096 keypoints kept on one level" : "candidate buffer");
+      return GB_ERR_CAPACITY;
+    }
+    if (hc[1] != 0) {
+      *n = hc[1];
+      gb_set_error(ctx, "extract kept %d keypoints but the feature set holds %d", hc[1], f->capacity);
+      return GB_ERR_CAPACITY;
+    }
+    f->h_count = cnt = hc[0];
+    *n = cnt;
+    if (cnt > cap) {
+      gb_set_error(ctx, "gb_features_download: %d keypoints > caller capacity %d", cnt, cap);
+      return GB_ERR_CAPACITY;
+    }
+  }
+  if (hk && cnt > 0) memcpy(kps, hk, (size_t)cnt * sizeof(gb_keypoint));
+  if (hd && cnt > 0) memcpy(desc, hd, (size_t)cnt * 32);
   return GB_OK;
 }
 

@@ -769,8 +769,10 @@ void gb_orb_cfg_default(gb_orb_cfg* c) {
   c->fast_threshold = 20;
 }
 
-int gb_orb_extract_to(gb_ctx* ctx, const uint8_t* img, int img_is_device, int width, int height, int pitch, const gb_orb_cfg* cfg_in,
-                      gb_features* out) {
+// sync_after: a host image (or its staging copy) must have been consumed before the caller may touch it again; the one-shot
+// gb_orb_extract synchronises in its own download instead (one synchronisation per host-buffer extraction)
+static int orb_extract_to_impl(gb_ctx* ctx, const uint8_t* img, int img_is_device, int width, int height, int pitch, const gb_orb_cfg* cfg_in,
+                               gb_features* out, bool sync_after) {
   if (!ctx || !img || !out || width < 1 || height < 1 || pitch < width) return GB_ERR_INVALID;
   CtxLock lk(ctx);
   gb_orb_cfg cfg;
@@ -798,8 +800,13 @@ int gb_orb_extract_to(gb_ctx* ctx, const uint8_t* img, int img_is_device, int wi
     GB_CUDA(ctx, cudaMemcpy2DAsync(s->d_pyr + L0.off, L0.pitch, src, spitch, width, height, cudaMemcpyHostToDevice, ctx->stream));
   }
   GB_CHECK(orb_launch(ctx, out));
-  if (!img_is_device) GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // staging / caller buffer may be reused
+  if (!img_is_device && sync_after) GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // staging / caller buffer may be reused
   return GB_OK;
+}
+
+int gb_orb_extract_to(gb_ctx* ctx, const uint8_t* img, int img_is_device, int width, int height, int pitch, const gb_orb_cfg* cfg_in,
+                      gb_features* out) {
+  return orb_extract_to_impl(ctx, img, img_is_device, width, height, pitch, cfg_in, out, true);
 }
 
 int gb_orb_extract(gb_ctx* ctx, const uint8_t* img, int width, int height, const gb_orb_cfg* cfg_in, gb_keypoint* kps, uint8_t* desc,
@@ -816,18 +823,24 @@ int gb_orb_extract(gb_ctx* ctx, const uint8_t* img, int width, int height, const
     GB_CHECK(gb_features_create(ctx, want_cap, &ctx->tmp_f));
   }
   gb_features* f = ctx->tmp_f;
-  GB_CHECK(gb_orb_extract_to(ctx, img, 0, width, height, width, &cfg, f));
+  GB_CHECK(orb_extract_to_impl(ctx, img, 0, width, height, width, &cfg, f, *n <= 0));
   const int cap = *n;
+  if (cap > 0) {  // one synchronisation: the count travels with the rows
+    int m = cap;
+    const int rc = gb_features_download(ctx, f, kps, desc, &m);
+    *n = m;
+    if (rc == GB_ERR_CAPACITY && m > cap) gb_set_error(ctx, "gb_orb_extract: %d keypoints > caller capacity %d", m, cap);
+    return rc;
+  }
   int cnt = 0;
-  int rc = gb_features_count(ctx, f, &cnt);
+  const int rc = gb_features_count(ctx, f, &cnt);
   *n = cnt;
   if (rc != GB_OK) return rc;
-  if (cnt > cap) {
+  if (cnt > 0) {
     gb_set_error(ctx, "gb_orb_extract: %d keypoints > caller capacity %d", cnt, cap);
     return GB_ERR_CAPACITY;
   }
-  int m = cap;
-  return gb_features_download(ctx, f, kps, desc, &m);
+  return GB_OK;
 }
 
 // ---- test hook: candidates of the LAST extraction on this ctx (after FAST+NMS+border), and the kept lists --------------
