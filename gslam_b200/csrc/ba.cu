@@ -67,21 +67,25 @@ __device__ __forceinline__ void ba_linearize_points_body(const BaDev& g, int blo
   const int jraw = gt / kLpp, sub = gt % kLpp, lane = threadIdx.x & 31;
   const bool valid = jraw < g.np;
   const int j = valid ? jraw : 0;
-  const double delta = g.sc->delta;
-  const double p[3] = {g.pts[3 * (size_t)j], g.pts[3 * (size_t)j + 1], g.pts[3 * (size_t)j + 2]};
+  // -- static graph structure first: under a programmatic dependent launch this runs while the predecessor kernel drains
   const bool pf = g.pfree[j] != 0;
-  double acc[10];  // V upper triangle (6), g_p (3), cost (1)
-#pragma unroll
-  for (int k = 0; k < 10; ++k) acc[k] = 0.0;
   const int e0 = g.pt_off[j], e1 = valid ? g.pt_off[j + 1] : e0;
-  const int rounds = __reduce_max_sync(0xffffffffu, (e1 - e0 + kLpp - 1) / kLpp);
-  double* tile = s_w[threadIdx.x >> 5];
-  double2* mine = reinterpret_cast<double2*>(tile + 18 * lane);                     // this lane's block in the tile
-  const double2* run = reinterpret_cast<const double2*>(tile + 18 * (lane - sub));  // the landmark's eight blocks
   int e = e0 + sub;
   bool act = e < e1;
   int i = act ? g.o_cam[e] : 0;
   double2 uv = act ? *reinterpret_cast<const double2*>(g.o_uv + 2 * (size_t)e) : make_double2(0.0, 0.0);
+  gb_pdl_wait();
+  if (g.sc->stop || !g.sc->need_linearize) return;
+  // -- the estimate (written by the predecessor)
+  const double delta = g.sc->delta;
+  const double p[3] = {g.pts[3 * (size_t)j], g.pts[3 * (size_t)j + 1], g.pts[3 * (size_t)j + 2]};
+  double acc[10];  // V upper triangle (6), g_p (3), cost (1)
+#pragma unroll
+  for (int k = 0; k < 10; ++k) acc[k] = 0.0;
+  const int rounds = __reduce_max_sync(0xffffffffu, (e1 - e0 + kLpp - 1) / kLpp);
+  double* tile = s_w[threadIdx.x >> 5];
+  double2* mine = reinterpret_cast<double2*>(tile + 18 * lane);                     // this lane's block in the tile
+  const double2* run = reinterpret_cast<const double2*>(tile + 18 * (lane - sub));  // the landmark's eight blocks
   for (int rd = 0; rd < rounds; ++rd) {
     const int en = e + kLpp;
     const bool actn = en < e1;
@@ -173,12 +177,15 @@ __device__ __forceinline__ void ba_linearize_points_body(const BaDev& g, int blo
 // camera to finish (per-camera ticket) folds the slices' partial sums in slice order.  Bit-reproducible run to run.
 __device__ __forceinline__ void ba_linearize_cams_body(const BaDev& g, int cta) {
   const int K = g.cam_split, i = cta / K, slice = cta - i * K;
-  const double delta = g.sc->delta;
-  const double* Rt = g.Rt + 12 * i;
+  // -- static graph structure first (see the landmark pass)
   const int dm = g.dof[i];
   const int c0 = g.cam_off[i], c1 = g.cam_off[i + 1];
   const int per = (c1 - c0 + K - 1) / K;
   const int s0 = min(c0 + slice * per, c1), s1 = min(s0 + per, c1);
+  gb_pdl_wait();  // (prefetching the first observation here costs 40 registers: ptxas pipelines the whole loop body)
+  if (g.sc->stop || !g.sc->need_linearize) return;
+  const double delta = g.sc->delta;
+  const double* Rt = g.Rt + 12 * i;
   double acc[27];
 #pragma unroll
   for (int k = 0; k < 27; ++k) acc[k] = 0.0;
@@ -252,15 +259,12 @@ __device__ __forceinline__ void ba_linearize_cams_body(const BaDev& g, int cta) 
 // first), the remaining CTAs the landmark pass (K6a); the two are independent.
 static_assert(kPtThreads == kCamThreads, "the fused sweep launch uses one block size");
 __global__ void __launch_bounds__(kPtThreads) ba_linearize_kernel(BaDev g, int cam_blocks) {
-  gb_pdl_launch_dependents();
-  gb_pdl_wait();
-  if (g.sc->stop || !g.sc->need_linearize) return;
+  gb_pdl_launch_dependents();  // (both bodies wait for the predecessor after their static prologue and test the LM flags there)
   if ((int)blockIdx.x < cam_blocks) ba_linearize_cams_body(g, blockIdx.x);
   else ba_linearize_points_body(g, blockIdx.x - cam_blocks);
 }
 // (the camera pass alone: used for the pose information matrix of optimizePnP)
 __global__ void __launch_bounds__(kCamThreads) ba_linearize_cams_kernel(BaDev g) {
-  if (g.sc->stop || !g.sc->need_linearize) return;
   ba_linearize_cams_body(g, blockIdx.x);
 }
 
@@ -320,8 +324,6 @@ __global__ void ba_schur_accum_kernel(BaDev g, double* __restrict__ buf) {
 // written once.  The diagonal warps also produce g~_i = g_c,i - sum_j Y g_p,j and diag U.  Bit-reproducible run to run.
 __global__ void __launch_bounds__(128) ba_schur_blocks_kernel(BaDev g, double* __restrict__ buf) {
   gb_pdl_launch_dependents();
-  gb_pdl_wait();
-  if (g.sc->stop) return;
   // one CTA (4 warps) per upper block: the warps split camera i's observation list, a fixed shuffle tree reduces inside each
   // warp and warp 0 adds the four partials in order
   __shared__ double s_part[4][42];
@@ -329,27 +331,39 @@ __global__ void __launch_bounds__(128) ba_schur_blocks_kernel(BaDev g, double* _
   const int blk = g.s_upper[wid];
   const int i = g.s_brow[blk], i2 = g.s_col[blk];
   const bool diag = i == i2;
+  // which edge pair (e, f) on which landmark: static graph structure -- the chain cam_perm -> o_pt -> pt_off -> o_cam of the
+  // thread's first observation is walked BEFORE waiting for the predecessor kernel (programmatic dependent launch)
+  auto find_pair = [&](int idx, int* e_out, int* j_out) -> int {
+    const int e = g.cam_perm[idx];
+    const int j = g.o_pt[e];
+    *e_out = e; *j_out = j;
+    if (!g.pfree[j]) return -1;
+    if (diag) return e;
+    const int f0 = g.pt_off[j], f1 = g.pt_off[j + 1];
+    int f = -1;
+    int cam8[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) cam8[t] = (f0 + t < f1) ? g.o_cam[f0 + t] : -1;  // independent loads
+#pragma unroll
+    for (int t = 7; t >= 0; --t) if (cam8[t] == i2) f = f0 + t;
+    for (int t = f0 + 8; t < f1 && f < 0; ++t)
+      if (g.o_cam[t] == i2) f = t;
+    return f;
+  };
+  const int c0 = g.cam_off[i], c1 = g.cam_off[i + 1];
+  int e_first = 0, j_first = 0, f_first = -1;
+  if (c0 + (int)threadIdx.x < c1) f_first = find_pair(c0 + threadIdx.x, &e_first, &j_first);
+  gb_pdl_wait();
+  if (g.sc->stop) return;
   double acc[36], ga[6];
 #pragma unroll
   for (int k = 0; k < 36; ++k) acc[k] = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) ga[k] = 0.0;
-  for (int idx = g.cam_off[i] + threadIdx.x; idx < g.cam_off[i + 1]; idx += 128) {
-    const int e = g.cam_perm[idx];
-    const int j = g.o_pt[e];
-    if (!g.pfree[j]) continue;
-    int f = -1;
-    if (diag) f = e;
-    else {
-      const int f0 = g.pt_off[j], f1 = g.pt_off[j + 1];
-      int cam8[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) cam8[t] = (f0 + t < f1) ? g.o_cam[f0 + t] : -1;  // independent loads
-#pragma unroll
-      for (int t = 7; t >= 0; --t) if (cam8[t] == i2) f = f0 + t;
-      for (int t = f0 + 8; t < f1 && f < 0; ++t)
-        if (g.o_cam[t] == i2) f = t;
-    }
+#pragma unroll 1
+  for (int idx = c0 + threadIdx.x; idx < c1; idx += 128) {
+    int e = e_first, j = j_first, f = f_first;
+    if (idx != c0 + (int)threadIdx.x) f = find_pair(idx, &e, &j);
     if (f < 0) continue;
     double Vi[9], Y[18];
 #pragma unroll
@@ -736,21 +750,23 @@ __device__ __forceinline__ void cta_copy_f64(double* __restrict__ dst, const dou
 
 __global__ void __launch_bounds__(kTailThreads) ba_backsub_commit_kernel(BaDev g, const double* __restrict__ buf) {
   gb_pdl_launch_dependents();
-  gb_pdl_wait();
   BaScalars* sc = g.sc;
-  if (sc->stop) return;
   __shared__ double s_part[kTailThreads / 32 + 1];
   __shared__ int s_flag;
+  // static graph structure of this lane's first observation, requested before waiting for the PCG kernel
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int jraw = gt / kLpp, sub = gt % kLpp;
+  const bool valid = jraw < g.np;
+  const int j = valid ? jraw : 0;
+  const int e0 = g.pt_off[j], e1 = valid ? g.pt_off[j + 1] : e0;
+  const int i_first = (e0 + sub < e1) ? g.o_cam[e0 + sub] : 0;
+  gb_pdl_wait();
+  if (sc->stop) return;
   {  // ---- part 1: identical to ba_backsub_cost_kernel
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const int jraw = gt / kLpp, sub = gt % kLpp;
-    const bool valid = jraw < g.np;
-    const int j = valid ? jraw : 0;
     const double delta = sc->delta;
-    const int e0 = g.pt_off[j], e1 = valid ? g.pt_off[j + 1] : e0;
     double b[3] = {0.0, 0.0, 0.0};
     for (int e = e0 + sub; e < e1; e += kLpp) {
-      const int i = g.o_cam[e];
+      const int i = (e == e0 + sub) ? i_first : g.o_cam[e];
       const double* W = g.W + 18 * (size_t)e;
 #pragma unroll
       for (int c = 0; c < 3; ++c)
@@ -769,7 +785,8 @@ __global__ void __launch_bounds__(kTailThreads) ba_backsub_commit_kernel(BaDev g
     for (int a = 0; a < 3; ++a) p[a] = g.pts[3 * (size_t)j + a] + Vi[a * 3] * b[0] + Vi[a * 3 + 1] * b[1] + Vi[a * 3 + 2] * b[2];
     double cost = 0.0;
     for (int e = e0 + sub; e < e1; e += kLpp) {
-      const ObsLin o = eval_obs(g.Rt_new + 12 * g.o_cam[e], p, g.o_uv[2 * e], g.o_uv[2 * e + 1], g.has_info ? g.o_info + 3 * e : nullptr, delta);
+      const int i = (e == e0 + sub) ? i_first : g.o_cam[e];
+      const ObsLin o = eval_obs(g.Rt_new + 12 * i, p, g.o_uv[2 * e], g.o_uv[2 * e + 1], g.has_info ? g.o_info + 3 * e : nullptr, delta);
       cost += o.rho;
     }
 #pragma unroll
@@ -893,9 +910,10 @@ __global__ void __launch_bounds__(kRedThreads) ba_commit_fused_kernel(BaDev g, c
 //    coefficients each) in registers for the whole solve, so a mat-vec is one shared-memory read of u and six DFMAs per column
 //    (no lane repeats another's work) followed by a 3-stage transposing butterfly (6 exchanges) that leaves row r of the camera
 //    in lane {0,1,2,-,3,4,5,-}[l] (lanes 3 and 7 duplicate rows 2 and 5).  Those lanes own element 6i+r of every CG vector;
-//    u = Minv r gathers the camera's six residuals with shuffles (no shared-memory round trip, no barrier).
+//    u = Minv r exchanges the camera's six residuals through a warp-local shared-memory tile (a camera never straddles
+//    warps: __syncwarp, no CTA barrier).
 //  * (gamma, delta) are reduced packed into ONE butterfly per warp (a in lanes 0-15, b in lanes 16-31); warp 0 alone folds the
-//    per-warp partials and runs the alpha/beta recurrences (three DDIVs) while the others wait at the barrier.
+//    per-warp partials and runs the alpha/beta recurrences (one reciprocal) while the others wait at the barrier.
 //  * <= 48 active cameras run as 12 warps = 3 per sub-partition -> 168 registers per thread, enough for 7 columns per lane
 //    (block rows of <= 9 blocks) without spilling; the wide variant (<= 80 cameras) keeps 5 columns and reads the rest from
 //    the shared-memory copy of S.
@@ -904,8 +922,6 @@ __global__ void __launch_bounds__(kRedThreads) ba_commit_fused_kernel(BaDev g, c
 template <int THREADS, int KC>
 __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, double* __restrict__ buf, int maxit) {
   gb_pdl_launch_dependents();
-  gb_pdl_wait();
-  if (g.sc->stop) return;
   extern __shared__ __align__(16) double sm[];
   __shared__ double2 s_red[32];  // per-warp (gamma, delta) partials
   __shared__ double s_scal[2][2];
@@ -924,7 +940,7 @@ __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, doub
   int* col = rowptr + nc + 1;                     // [nnzb]
   int* act = col + nnzb;                          // [nc] active (not fully fixed) cameras, ascending
   const size_t nS = (size_t)n6 * n6;
-  const double lambda = g.sc->lambda, tol = g.sc->pcg_tol;
+  // static graph structure first: under a programmatic dependent launch this part overlaps the Schur kernel
   for (int k = tid; k <= nc; k += THREADS) rowptr[k] = g.s_rowptr[k];
   for (int k = tid; k < nnzb; k += THREADS) col[k] = g.s_col[k];
   for (int k = tid; k < n6; k += THREADS) { vu[k] = 0.0; vx[k] = 0.0; }
@@ -939,6 +955,9 @@ __global__ void __launch_bounds__(THREADS, 1) ba_pcg_sparse_kernel(BaDev g, doub
     }
     if (lane == 0) s_nact = cnt;
   }
+  gb_pdl_wait();
+  if (g.sc->stop) return;
+  const double lambda = g.sc->lambda, tol = g.sc->pcg_tol;
   // A. copy the block-CSR values of S (written by ba_schur_blocks_kernel) into shared memory (8 independent loads in
   //    flight per thread), then Marquardt damping on the 6N diagonal entries (written back so the damped system is observable)
   {
