@@ -1562,18 +1562,17 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   g->buf_doubles = ba_buf_doubles(nc);
 
   // ---- host-side ordering: stable counting sorts -> (point, camera) order, and the per-camera lists ----------------
-  std::vector<int> byc(no), order(no), cnt(std::max(nc, np) + 2, 0);
-  for (int k = 0; k < no; ++k) cnt[pb->obs_cam[k] + 1]++;
-  for (int i = 0; i < nc; ++i) cnt[i + 1] += cnt[i];
-  { std::vector<int> pos(cnt.begin(), cnt.begin() + nc + 1); for (int k = 0; k < no; ++k) byc[pos[pb->obs_cam[k]]++] = k; }
-  std::vector<int> pt_off(np + 1, 0);
-  for (int k = 0; k < no; ++k) pt_off[pb->obs_point[k] + 1]++;
-  for (int j = 0; j < np; ++j) pt_off[j + 1] += pt_off[j];
-  { std::vector<int> pos(pt_off.begin(), pt_off.end()); for (int t = 0; t < no; ++t) { int k = byc[t]; order[pos[pb->obs_point[k]]++] = k; } }
-  std::vector<int> cam_off(nc + 1, 0), cam_perm(no);
-  for (int e = 0; e < no; ++e) cam_off[pb->obs_cam[order[e]] + 1]++;
+  // (one histogram pass over both keys; `scam` keeps the camera of each sorted edge so that later passes stream it)
+  std::vector<int> byc(no), order(no), scam(no), cam_off(nc + 1, 0), pt_off(np + 1, 0), cam_perm(no);
+  for (int k = 0; k < no; ++k) { cam_off[pb->obs_cam[k] + 1]++; pt_off[pb->obs_point[k] + 1]++; }
   for (int i = 0; i < nc; ++i) cam_off[i + 1] += cam_off[i];
-  { std::vector<int> pos(cam_off.begin(), cam_off.end()); for (int e = 0; e < no; ++e) cam_perm[pos[pb->obs_cam[order[e]]]++] = e; }
+  for (int j = 0; j < np; ++j) pt_off[j + 1] += pt_off[j];
+  { std::vector<int> pos(cam_off.begin(), cam_off.end()); for (int k = 0; k < no; ++k) byc[pos[pb->obs_cam[k]]++] = k; }
+  {
+    std::vector<int> pos(pt_off.begin(), pt_off.end());
+    for (int t = 0; t < no; ++t) { const int k = byc[t]; const int e = pos[pb->obs_point[k]]++; order[e] = k; scam[e] = pb->obs_cam[k]; }
+  }
+  { std::vector<int> pos(cam_off.begin(), cam_off.end()); for (int e = 0; e < no; ++e) cam_perm[pos[scam[e]]++] = e; }
 
   tr.stamp("counting sorts");
   // ---- layout: one slab = [uploaded blob | working set] ----------------------------------------------------------------
@@ -1593,9 +1592,9 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
       const int a = pt_off[j], b = pt_off[j + 1];
       if (b - a < 2) continue;
       std::fill(mask.begin(), mask.end(), 0ull);
-      for (int e = a; e < b; ++e) { const int i = pb->obs_cam[order[e]]; mask[i >> 6] |= 1ull << (i & 63); }
+      for (int e = a; e < b; ++e) { const int i = scam[e]; mask[i >> 6] |= 1ull << (i & 63); }
       for (int e = a; e < b; ++e) {
-        uint64_t* row = &rows[(size_t)pb->obs_cam[order[e]] * words];
+        uint64_t* row = &rows[(size_t)scam[e] * words];
         for (int w = 0; w < words; ++w) row[w] |= mask[w];
       }
     }
@@ -1693,7 +1692,7 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   int* hoc = (int*)(h + o_oc); int* hop = (int*)(h + o_op); double* huv = (double*)(h + o_uv); double* hin = (double*)(h + o_info);
   for (int e = 0; e < no; ++e) {
     const int k = order[e];
-    hoc[e] = pb->obs_cam[k];
+    hoc[e] = scam[e];
     hop[e] = pb->obs_point[k];
     const double* m = pb->obs_xyz + 3 * (size_t)k;
     huv[2 * e] = m[0] / m[2];
