@@ -76,9 +76,14 @@ __device__ __forceinline__ void ba_linearize_points_body(const BaDev& g, int blo
   double2 uv = act ? *reinterpret_cast<const double2*>(g.o_uv + 2 * (size_t)e) : make_double2(0.0, 0.0);
   gb_pdl_wait();
   if (g.sc->stop || !g.sc->need_linearize) return;
-  // -- the estimate (written by the predecessor)
+  // -- the estimate (written by the predecessor); an accepted-but-not-installed candidate is read from the candidate arrays
+  //    and installed here (every reader of this launch takes the same branch, nobody reads what is being written)
   const double delta = g.sc->delta;
-  const double p[3] = {g.pts[3 * (size_t)j], g.pts[3 * (size_t)j + 1], g.pts[3 * (size_t)j + 2]};
+  const bool pend = g.sc->pending != 0;
+  const double* PTS = pend ? g.pts_new : g.pts;
+  const double* RT = pend ? g.Rt_new : g.Rt;
+  const double p[3] = {PTS[3 * (size_t)j], PTS[3 * (size_t)j + 1], PTS[3 * (size_t)j + 2]};
+  if (pend && valid && sub == 0) { g.pts[3 * (size_t)j] = p[0]; g.pts[3 * (size_t)j + 1] = p[1]; g.pts[3 * (size_t)j + 2] = p[2]; }
   double acc[10];  // V upper triangle (6), g_p (3), cost (1)
 #pragma unroll
   for (int k = 0; k < 10; ++k) acc[k] = 0.0;
@@ -93,7 +98,7 @@ __device__ __forceinline__ void ba_linearize_points_body(const BaDev& g, int blo
     const double2 uv_nx = actn ? *reinterpret_cast<const double2*>(g.o_uv + 2 * (size_t)en) : make_double2(0.0, 0.0);
     bool have = false;
     if (act) {
-      const double* Rt = g.Rt + 12 * i;
+      const double* Rt = RT + 12 * i;
       const ObsLin o = eval_obs(Rt, p, uv.x, uv.y, g.has_info ? g.o_info + 3 * (size_t)e : nullptr, delta);
       if (o.valid) {
         have = true;
@@ -185,14 +190,20 @@ __device__ __forceinline__ void ba_linearize_cams_body(const BaDev& g, int cta) 
   gb_pdl_wait();  // (prefetching the first observation here costs 40 registers: ptxas pipelines the whole loop body)
   if (g.sc->stop || !g.sc->need_linearize) return;
   const double delta = g.sc->delta;
-  const double* Rt = g.Rt + 12 * i;
+  const bool pend = g.sc->pending != 0;  // (see the landmark pass)
+  const double* PTS = pend ? g.pts_new : g.pts;
+  const double* Rt = (pend ? g.Rt_new : g.Rt) + 12 * i;
+  if (pend && slice == 0) {  // install this camera's accepted pose
+    if (threadIdx.x < 12) g.Rt[12 * i + threadIdx.x] = g.Rt_new[12 * i + threadIdx.x];
+    else if (threadIdx.x >= 32 && threadIdx.x < 39) g.pose[7 * i + threadIdx.x - 32] = g.pose_new[7 * i + threadIdx.x - 32];
+  }
   double acc[27];
 #pragma unroll
   for (int k = 0; k < 27; ++k) acc[k] = 0.0;
   for (int idx = s0 + threadIdx.x; idx < s1; idx += kCamThreads) {
     const int j = g.c_pt[idx];
     const double2 uv = *reinterpret_cast<const double2*>(g.c_uv + 2 * (size_t)idx);
-    const double p[3] = {g.pts[3 * (size_t)j], g.pts[3 * (size_t)j + 1], g.pts[3 * (size_t)j + 2]};
+    const double p[3] = {PTS[3 * (size_t)j], PTS[3 * (size_t)j + 1], PTS[3 * (size_t)j + 2]};
     const ObsLin o = eval_obs(Rt, p, uv.x, uv.y, g.has_info ? g.o_info + 3 * (size_t)g.cam_perm[idx] : nullptr, delta);
     if (!o.valid) continue;
     double Jc[12], AJc[12];
@@ -355,6 +366,7 @@ __global__ void __launch_bounds__(128) ba_schur_blocks_kernel(BaDev g, double* _
   if (c0 + (int)threadIdx.x < c1) f_first = find_pair(c0 + threadIdx.x, &e_first, &j_first);
   gb_pdl_wait();
   if (g.sc->stop) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) g.sc->pending = 0;  // the sweep before this kernel has installed the candidate
   double acc[36], ga[6];
 #pragma unroll
   for (int k = 0; k < 36; ++k) acc[k] = 0.0;
@@ -835,10 +847,8 @@ __global__ void __launch_bounds__(kTailThreads) ba_backsub_commit_kernel(BaDev g
     s_flag = ok ? 2 : 1;
   }
   __syncthreads();
-  if (s_flag == 2) {  // accept: estimate <- candidate
-    cta_copy_f64(g.pts, g.pts_new, g.np * 3, kTailThreads);
-    cta_copy_f64(g.Rt, g.Rt_new, g.nc * 12, kTailThreads);
-    cta_copy_f64(g.pose, g.pose_new, g.nc * 7, kTailThreads);
+  if (s_flag == 2) {  // accept: the next sweep reads the candidate arrays and installs them on the fly (no serial copy here)
+    if (threadIdx.x == 0) sc->pending = 1;
   } else {  // reject: same linearisation, new lambda -> refresh the damped landmark inverses
     const double lambda = sc->lambda;
     for (int j = threadIdx.x; j < g.np; j += kTailThreads) {
@@ -858,6 +868,20 @@ __global__ void __launch_bounds__(kTailThreads) ba_backsub_commit_kernel(BaDev g
       for (int k = 0; k < 9; ++k) g.Vinv[9 * (size_t)j + k] = Vi[k];
     }
   }
+}
+
+// end of a solve on the local path: install an accepted candidate the next sweep never came to pick up (single CTA: the flag is
+// read by everybody before it is cleared)
+__global__ void __launch_bounds__(1024) ba_install_pending_kernel(BaDev g) {
+  gb_pdl_wait();
+  __shared__ int s_p;
+  if (threadIdx.x == 0) s_p = g.sc->pending;
+  __syncthreads();
+  if (!s_p) return;
+  cta_copy_f64(g.pts, g.pts_new, g.np * 3, 1024);
+  cta_copy_f64(g.Rt, g.Rt_new, g.nc * 12, 1024);
+  cta_copy_f64(g.pose, g.pose_new, g.nc * 7, 1024);
+  if (threadIdx.x == 0) g.sc->pending = 0;
 }
 
 // single CTA: reduce the candidate cost, LM accept/reject, apply.  (small problems; the stepwise path keeps them apart)
@@ -1997,6 +2021,7 @@ static int ba_graph_solve_impl(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options*
       if (h.stop) break;
     }
   }
+  if (local4) { ba_install_pending_kernel<<<1, 1024, 0, ctx->stream>>>(g->d); GB_LAUNCH_CHECK(ctx); }
   GB_CUDA(ctx, cudaEventRecord(ctx->eve, ctx->stream));
   BaDev& dd = g->d;
   const size_t bp = pose_out ? (size_t)dd.nc * 56 : 0, bx = pts_out ? (size_t)dd.np * 24 : 0;

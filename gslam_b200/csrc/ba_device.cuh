@@ -18,6 +18,8 @@ struct BaScalars {
   int pcg_first, pcg_k;
   int need_linearize, stop, status, iterations, accepted, accept_flag;
   unsigned int ticket;  // last-CTA-done counter of the fused back-substitution + commit kernel
+  int pending;          // an accepted candidate (pose_new / Rt_new / pts_new) has not been installed yet: the next sweep reads the
+                        // candidate arrays and installs them on the fly (ba_install_pending_kernel at the end of a solve)
   int pcg_iters, pcg_done;
 };
 
