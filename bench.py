@@ -33,8 +33,8 @@ RING = 72  # frames resident in HBM: 72 * 2.07 MB = 149 MB > 126 MB L2
 def level_sizes(w, h, nlevels=8, sf=1.2):
     out = []
     for l in range(nlevels):
-        s = np.float32(np.float64(np.float32(sf)) ** l)
-        out.append((int(np.rint(np.float32(w) / s)), int(np.rint(np.float32(h) / s))))
+        inv = np.float32(1.0) / np.float32(np.float64(np.float32(sf)) ** l)  # cv2: cols * (1/scale) in float, half-even
+        out.append((int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv))))
     return out
 
 

@@ -99,6 +99,7 @@ _DEBUG_SIGNATURES = [
     ("gb_dbg_ba_pcg_sparse", C.c_int, [_VP, _VP]),
     ("gb_dbg_ba_set_cam_split", C.c_int, [_VP, _VP, C.c_int]),
     ("gb_dbg_ba_sweep_part", C.c_int, [_VP, _VP, C.c_int]),
+    ("gb_dbg_orb_level_size", C.c_int, [C.c_int, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 ]
 
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]

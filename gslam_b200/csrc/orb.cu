@@ -606,6 +606,13 @@ void gb_orb_state_free(gb_ctx* ctx) {
 }
 
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
+// level size as cv2 computes it: cols * (1/scale) in float, round-half-even (NOT cols / scale: 477 / 1.2f -> 397, cv2 -> 398;
+// pinned by tests/test_oracle_orb.py::test_level_sizes_match_cv2 and ::test_product_level_size_rule_equals_oracle)
+static inline void orb_level_size(int w, int h, float scale, int* lw, int* lh) {
+  const volatile float inv = 1.0f / scale;  // (volatile: the reciprocal must be rounded to float before the multiply)
+  *lw = cv_round_f((float)w * inv);
+  *lh = cv_round_f((float)h * inv);
+}
 
 static int orb_cfg_check(gb_ctx* ctx, const gb_orb_cfg* c) {
   if (!c || c->nfeatures <= 0 || c->nlevels < 1 || c->nlevels > kMaxLevels || !(c->scale_factor > 1.0f) || c->edge_threshold < 22 ||
@@ -654,7 +661,8 @@ static int orb_prepare(gb_ctx* ctx, int w, int h, const gb_orb_cfg* cfg) {
   int tiles = 0, cand = 0, coef = 0, nl = 0;
   for (int l = 0; l < cfg->nlevels; ++l) {
     const float sc = (float)pow((double)cfg->scale_factor, (double)l);
-    const int lw = cv_round_f((float)w / sc), lh = cv_round_f((float)h / sc);
+    int lw, lh;
+    orb_level_size(w, h, sc, &lw, &lh);
     if (lw < 1 || lh < 1) break;
     LevelInfo& L = P.lv[l];
     L.w = lw; L.h = lh; L.pitch = (lw + 127) & ~127; L.quota = quota[l]; L.scale = sc;
@@ -840,6 +848,13 @@ int gb_orb_extract(gb_ctx* ctx, const uint8_t* img, int width, int height, const
     gb_set_error(ctx, "gb_orb_extract: %d keypoints > caller capacity %d", cnt, cap);
     return GB_ERR_CAPACITY;
   }
+  return GB_OK;
+}
+
+// host-only (no device needed): the pyramid level size the extractor uses, for the CPU parity test against the oracle / cv2
+GB_API int gb_dbg_orb_level_size(int w, int h, float scale_factor, int level, int* lw, int* lh) {
+  if (!lw || !lh || level < 0) return GB_ERR_INVALID;
+  orb_level_size(w, h, (float)pow((double)scale_factor, (double)level), lw, lh);
   return GB_OK;
 }
 

@@ -59,6 +59,76 @@ def test_quotas_and_level_sizes():
     assert [oracle.orb_level_size(1280, 720, l) for l in range(8)] == [(1280, 720), (1067, 600), (889, 500), (741, 417), (617, 347), (514, 289), (429, 241), (357, 201)]
 
 
+# cv2 4.13 level sizes, recovered from cv2 itself (the Harris responses of its keypoints only reproduce on a level image of
+# exactly the right size): cv2 evaluates cols/scale as cols*(1/scale) in float, so 477/1.2f -> 397.5f -> 398 where a true float
+# division rounds to 397.  Rows where the two rules differ (found by fuzzing the oracle against live cv2):
+CV2_LEVEL_SIZES = {
+    (456, 477, 1.2): [(456, 477), (380, 398), (317, 331), (264, 276), (220, 230), (183, 192), (153, 160), (127, 133)],
+    (303, 249, 1.2): [(303, 249), (252, 208), (210, 173), (175, 144), (146, 120), (122, 100), (101, 83), (85, 69)],
+    (645, 333, 1.2): [(645, 333), (538, 278), (448, 231), (373, 193), (311, 161), (259, 134), (216, 112), (180, 93)],
+    (342, 630, 1.2): [(342, 630), (285, 525), (237, 437), (198, 365), (165, 304), (137, 253), (115, 211), (95, 176)],
+    (702, 342, 1.2): [(702, 342), (585, 285), (487, 237), (406, 198), (339, 165), (282, 137), (235, 115), (196, 95)],
+    (432, 522, 1.25): [(432, 522), (346, 418), (276, 334), (221, 267), (177, 214), (142, 171), (113, 137), (91, 109)],
+}
+
+
+def test_level_sizes_match_cv2():
+    for (w, h, sf), want in CV2_LEVEL_SIZES.items():
+        assert [oracle.orb_level_size(w, h, l, sf) for l in range(len(want))] == want, (w, h, sf)
+
+
+def test_level_size_rule_live_cv2():
+    """Re-derive one discriminating size from the installed cv2: only a level-1 image of 380x398 reproduces its responses."""
+    cv2 = pytest.importorskip("cv2")
+    import sys
+    sys.path.insert(0, GD)
+    from make_golden_orb import cv2_orb_canonical
+    img = synth.synth_frame(456, 477, 5634)
+    want, _, lvl = cv2_orb_canonical(img, 1500)
+    sel = np.nonzero(want["octave"] == 1)[0][:60]
+    assert len(sel) > 20
+    hits = {}
+    for size in ((380, 397), (380, 398)):
+        im = cv2.resize(img, size, interpolation=cv2.INTER_LINEAR_EXACT)
+        hits[size] = sum(float(oracle.harris_response(im, int(lvl[i, 2]), int(lvl[i, 1]))) == float(want["response"][i]) for i in sel)
+    assert hits[(380, 398)] == len(sel) and hits[(380, 397)] == 0
+    assert oracle.orb_level_size(456, 477, 1) == (380, 398)
+
+
+def test_full_pipeline_live_cv2_at_sizes_with_half_way_levels():
+    cv2 = pytest.importorskip("cv2")
+    import sys
+    sys.path.insert(0, GD)
+    from make_golden_orb import cv2_orb_canonical
+    for (w, h, seed, n, kw, okw) in [(456, 477, 5634, 4000, dict(fastThreshold=30), dict(fast_threshold=30)),
+                                     (303, 249, 11, 600, {}, {}), (702, 342, 12, 900, {}, {})]:
+        img = synth.synth_frame(w, h, seed)
+        want, wdesc, _ = cv2_orb_canonical(img, n, **kw)
+        kps, desc = oracle.orb_extract(img, n, **okw)
+        assert len(kps) == len(want), (w, h)
+        for f in ("octave", "x", "y", "size", "angle", "response"):
+            assert np.array_equal(kps[f], want[f]), (f, w, h)
+        assert np.array_equal(desc, wdesc)
+
+
+def test_product_level_size_rule_equals_oracle():
+    """The extractor's host code (gslam_b200/csrc/orb.cu) and the oracle must size the pyramid identically; the helper is pure
+    host code, so this runs without a GPU."""
+    import ctypes as C
+    from gslam_b200 import capi
+    L = C.CDLL(capi.LIB_PATH)
+    L.gb_dbg_orb_level_size.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.gb_dbg_orb_level_size.restype = C.c_int
+    lw, lh = C.c_int(), C.c_int()
+    rng = np.random.default_rng(9)
+    cases = [(w, h, sf) for (w, h, sf) in CV2_LEVEL_SIZES] + [(int(rng.integers(40, 4000)), int(rng.integers(40, 3000)), float(sf))
+                                                             for sf in (1.1, 1.2, 1.25, 1.35, 1.5, 2.0) for _ in range(60)]
+    for w, h, sf in cases:
+        for l in range(8):
+            assert L.gb_dbg_orb_level_size(w, h, sf, l, C.byref(lw), C.byref(lh)) == 0
+            assert (lw.value, lh.value) == oracle.orb_level_size(w, h, l, sf), (w, h, sf, l)
+
+
 def test_det_sincos_matches_libm_after_float_rounding():
     ang = np.float32(np.linspace(0, 360, 20001, dtype=np.float32))
     th = ang * np.float32(np.pi / 180.0)

@@ -41,6 +41,8 @@ def test_golden_cv2(ctx, name):
     (131, 97, 150, {}),                                    # upper levels too small to hold a keypoint
     (1000, 64, 100, {}),                                   # nothing fits the 31-px border vertically
     (2048, 1536, 5000, {}),                                # larger than BASELINE sizes
+    (456, 477, 4000, dict(fast_threshold=30)),             # 477/1.2 lands on a half: cv2 sizes level 1 as 380x398 (not 397)
+    (303, 249, 600, {}),                                   # same rule on both axes at different levels
 ])
 def test_vs_oracle(ctx, w, h, n, kw):
     img = synth.synth_frame(w, h, 1000 + w)
