@@ -111,6 +111,25 @@ def test_full_pipeline_live_cv2_at_sizes_with_half_way_levels():
         assert np.array_equal(desc, wdesc)
 
 
+from _images import KIND_CASES, image_of_kind  # noqa: E402
+
+
+@pytest.mark.parametrize("kind,w,h,seed,n,nl,sf,ft", KIND_CASES)
+def test_live_cv2_image_kinds(kind, w, h, seed, n, nl, sf, ft):
+    """Other image statistics than the synthetic scene generator (ties, saturation, flat regions), odd parameter corners."""
+    pytest.importorskip("cv2")
+    import sys
+    sys.path.insert(0, GD)
+    from make_golden_orb import cv2_orb_canonical
+    img = np.ascontiguousarray(image_of_kind(kind, w, h, seed))
+    want, wdesc, _ = cv2_orb_canonical(img, n, nlevels=nl, scaleFactor=sf, fastThreshold=ft)
+    kps, desc = oracle.orb_extract(img, n, nlevels=nl, scale_factor=sf, fast_threshold=ft)
+    assert len(kps) == len(want)
+    for f in ("octave", "x", "y", "size", "angle", "response"):
+        assert np.array_equal(kps[f], want[f]), f
+    assert np.array_equal(desc, wdesc)
+
+
 def test_product_level_size_rule_equals_oracle():
     """The extractor's host code (gslam_b200/csrc/orb.cu) and the oracle must size the pyramid identically; the helper is pure
     host code, so this runs without a GPU."""
