@@ -66,7 +66,7 @@ def default_orb_cfg(**kw) -> OrbCfgC:
 
 def build(force: bool = False) -> None:
     """Compile liboracle.so (always possible) and _ref/libgslam_ref.so (only where /root/reference exists)."""
-    srcs = [os.path.join(_HERE, f) for f in ("hamming_ref.c", "ba_ref.c", "orb_ref.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("hamming_ref.c", "ba_ref.c", "orb_ref.c", "pnp_ref.c", "Makefile")]
     lib = os.path.join(_HERE, "liboracle.so")
     if force or not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "liboracle.so", "CC=gcc"])
@@ -346,3 +346,46 @@ def orb_extract(img, nfeatures=500, **cfg_kw):
         if rc != 0:
             raise RuntimeError(f"orc_orb_extract failed rc={rc}")
         return kps[:n.value].copy(), desc[:n.value].copy()
+
+
+# ---- PnP (Estimator::findPnP) -------------------------------------------------------------------------
+class PnpStatsC(C.Structure):
+    _fields_ = [("hypotheses", C.c_int), ("best_hypothesis", C.c_int), ("best_root", C.c_int), ("inliers_minimal", C.c_int),
+                ("inliers_refined", C.c_int)]
+
+
+def quartic_roots(coeffs):
+    """Real roots of c[0] + c[1] x + ... + c[4] x^4 (orc_quartic_roots)."""
+    c = np.ascontiguousarray(coeffs, np.float64); out = np.zeros(4)
+    L = lib(); L.orc_quartic_roots.restype = C.c_int
+    n = L.orc_quartic_roots(_p(c), _p(out))
+    return out[:n]
+
+
+def p3p(X, f):
+    """X: 3x3 world points, f: 3x3 unit bearings -> list of (R, t) with x_cam = R X + t."""
+    X = np.ascontiguousarray(X, np.float64); f = np.ascontiguousarray(f, np.float64); out = np.zeros(48)
+    L = lib(); L.orc_p3p.restype = C.c_int
+    n = L.orc_p3p(_p(X), _p(f), _p(out))
+    return [(out[12 * k:12 * k + 9].reshape(3, 3).copy(), out[12 * k + 9:12 * k + 12].copy()) for k in range(n)]
+
+
+def pnp_sample(seed, h, n):
+    idx = (C.c_int * 3)()
+    L = lib(); L.orc_pnp_sample.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.orc_pnp_sample(seed, h, n, idx)
+    return list(idx)
+
+
+def pnp_ransac(xyz, xy, threshold=0.01, confidence=0.99, max_hypotheses=1024, seed=1):
+    """-> (pose_cw[7] {qx,qy,qz,qw,tx,ty,tz}, mask[n] uint8, stats) or raises."""
+    xyz = np.ascontiguousarray(xyz, np.float64); xy = np.ascontiguousarray(xy, np.float64)
+    pose = np.zeros(7); mask = np.zeros(xyz.shape[0], np.uint8); st = PnpStatsC()
+    L = lib()
+    L.orc_pnp_ransac.restype = C.c_int
+    L.orc_pnp_ransac.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p,
+                                 C.POINTER(PnpStatsC)]
+    rc = L.orc_pnp_ransac(xyz.shape[0], _p(xyz), _p(xy), threshold, confidence, max_hypotheses, seed, _p(pose), _p(mask), C.byref(st))
+    if rc != 0:
+        raise RuntimeError(f"orc_pnp_ransac failed rc={rc}")
+    return pose, mask, st
