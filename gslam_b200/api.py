@@ -145,6 +145,14 @@ class Context:
         return idx, d1, d2
 
     # ---- BA ----------------------------------------------------------------------------------------------------------
+    def pnp_ransac(self, xyz, xy, threshold=0.01, confidence=0.99, max_hypotheses=1024, seed=1):
+        """Estimator::findPnP (P3P + RANSAC + refinement): -> (pose_cw[7] {qx,qy,qz,qw,tx,ty,tz}, mask[n] uint8, PnpStats)."""
+        xyz = np.ascontiguousarray(xyz, np.float64); xy = np.ascontiguousarray(xy, np.float64)
+        pose = np.zeros(7); mask = np.zeros(xyz.shape[0], np.uint8); st = capi.PnpStats()
+        self._check(self._lib.gb_pnp_ransac(self._h, xyz.shape[0], ptr(xyz), ptr(xy), float(threshold), float(confidence),
+                                            int(max_hypotheses), int(seed), ptr(pose), ptr(mask), C.byref(st)))
+        return pose, mask, st
+
     def ba_solve(self, pb: BAProblem, cfg: OptimzeConfig | None = None) -> capi.BaResult:
         c, keep = _problem_c(pb)
         o = (cfg or OptimzeConfig()).to_c()

@@ -26,6 +26,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
 
+# pnp.cu compares integer inlier counts across hypotheses and against the CPU checker: no FMA contraction there
+PER_FILE_FLAGS = {"pnp.cu": ["--fmad=false"]}
+
+
 def _nvcc() -> str:
     for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if c and os.path.exists(c):
@@ -52,7 +56,7 @@ def _sources():
 def build_kernels(force: bool = False, verbose: bool = False) -> str:
     cu, hdr = _sources()
     stamp_path = os.path.join(LIBDIR, ".stamp_kernels")
-    want = _hash(cu + hdr, " ".join(NVCC_FLAGS))
+    want = _hash(cu + hdr, " ".join(NVCC_FLAGS) + repr(sorted(PER_FILE_FLAGS.items())))
     if not force and os.path.exists(KERNEL_LIB) and os.path.exists(stamp_path) and open(stamp_path).read() == want:
         return KERNEL_LIB
     os.makedirs(LIBDIR, exist_ok=True)
@@ -61,7 +65,7 @@ def build_kernels(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *PER_FILE_FLAGS.get(os.path.basename(src), []), "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".ptxas.log")
         with open(log, "w") as f:

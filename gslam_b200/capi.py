@@ -50,6 +50,11 @@ class BaResult(C.Structure):
                 ("lambda_final", C.c_double), ("gpu_ms", C.c_float)]
 
 
+class PnpStats(C.Structure):
+    _fields_ = [("hypotheses", C.c_int32), ("best_hypothesis", C.c_int32), ("best_root", C.c_int32), ("inliers_minimal", C.c_int32),
+                ("inliers_refined", C.c_int32)]
+
+
 # every symbol include/gslam_b200.h declares: (name, restype, argtypes)
 _VP = C.c_void_p
 _SIGNATURES = [
@@ -89,6 +94,7 @@ _SIGNATURES = [
     ("gb_ba_graph_step", C.c_int, [_VP, _VP, _VP, _VP]),
     ("gb_ba_graph_commit", C.c_int, [_VP, _VP, _VP, _VP]),
     ("gb_ba_graph_finish", C.c_int, [_VP, _VP, C.POINTER(BaResult)]),
+    ("gb_pnp_ransac", C.c_int, [_VP, C.c_int, _VP, _VP, C.c_double, C.c_double, C.c_int, C.c_uint64, _VP, _VP, C.POINTER(PnpStats)]),
 ]
 # test hooks (not part of the reference-facing surface)
 _DEBUG_SIGNATURES = [

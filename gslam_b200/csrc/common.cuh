@@ -38,6 +38,8 @@ struct gb_ctx {
   void* ba_arena = nullptr;      // grow-only slab reused by the host-buffer BA entry points (no cudaMalloc per call)
   size_t ba_arena_cap = 0;
   bool ba_arena_busy = false;
+  void* pnp_scratch = nullptr;   // grow-only device scratch of gb_pnp_ransac (points, measurements, per-hypothesis results)
+  size_t pnp_scratch_cap = 0;
 };
 
 struct gb_features {

@@ -114,6 +114,7 @@ int gb_ctx_destroy(gb_ctx* ctx) {
     gb_match_state_free(ctx);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaFree(ctx->ba_arena);
+    cudaFree(ctx->pnp_scratch);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->evs);

@@ -233,6 +233,30 @@ GB_API int gb_ba_graph_step(gb_ctx* ctx, gb_ba_graph* g, const double* d_buf, do
 GB_API int gb_ba_graph_commit(gb_ctx* ctx, gb_ba_graph* g, const double* d_buf, const double* d_cost);
 GB_API int gb_ba_graph_finish(gb_ctx* ctx, gb_ba_graph* g, gb_ba_result* result);
 
+/* =====================================================================================================================
+ * Pose from 3D-2D matches with outliers: minimal P3P solver + RANSAC + non-linear refinement.
+ * Sits behind GSLAM::Estimator::findPnP(SE3* world2camera, objectPoints, imagePoints, method = P3_ITERATIVE&RANSAC,
+ * threshold = 0.01, confidence = 0.99, mask)  GSLAM/core/Estimator.h:158-164 (factory createEstimatorInstance :43-45,175-191);
+ * SURVEY.md section 8f-1.  STATUS: compiled for sm_100a, mirrors the CPU checker operation for operation, NOT yet validated on a
+ * B200 (round 2 starts with tools/gpu_pnp_check.py).
+ *   xyz: n x 3 world points; xy: n x 2 normalised image points (x/z, y/z);
+ *   threshold: inlier bound on the normalised reprojection error; confidence in (0,1); max_hypotheses >= 1; seed: any;
+ *   pose_cw: 7 doubles OUT, world->camera as the reference signature asks, layout {qx,qy,qz,qw,tx,ty,tz};
+ *   mask: NULL or n bytes OUT (1 = inlier of the returned pose).
+ * Definition (deterministic, independent of how many hypotheses run in parallel): hypothesis h draws its three matches from
+ * splitmix64(seed, h); best = (most inliers, lowest h, lowest root); hypotheses count in batches of 64 and stop at the first batch
+ * boundary with h >= log(1-confidence)/log(1-w^3), w the best inlier ratio so far; the winner is refined by the optimizePnP solver
+ * on its inliers and kept if it loses none.  GB_ERR_NUMERIC when no pose reaches 4 inliers. */
+typedef struct gb_pnp_stats {
+  int32_t hypotheses;       /* hypotheses that counted (a multiple of 64, or max_hypotheses) */
+  int32_t best_hypothesis;  /* index of the winning hypothesis, -1 if none */
+  int32_t best_root;        /* which P3P solution of that hypothesis */
+  int32_t inliers_minimal;  /* inliers of the winning minimal solution */
+  int32_t inliers_refined;  /* inliers of the returned pose */
+} gb_pnp_stats;
+GB_API int gb_pnp_ransac(gb_ctx* ctx, int n, const double* xyz, const double* xy, double threshold, double confidence,
+                         int max_hypotheses, uint64_t seed, double* pose_cw, uint8_t* mask, gb_pnp_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from gslam_b200 import capi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -56,3 +58,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 s = open(os.path.join(dp, f), errors="ignore").read()
                 assert "import oracle" not in s and "from oracle" not in s and "liboracle" not in s and "orc_" not in s, f
+
+
+def test_estimator_plugin_exports_the_reference_factory():
+    """libgslam_estimator.so is what GSLAM::Estimator::create() dlopens (Estimator.h:175-191): the factory symbol must be there
+    and constructing the estimator must not need a device (the context is created lazily, on the first findPnP)."""
+    import ctypes
+    path = os.path.join(os.path.dirname(capi.LIB_PATH), "libgslam_estimator.so")
+    if not os.path.exists(path):
+        pytest.skip("plugins are built where the reference headers are (gslam_b200/plugin/Makefile)")
+    L = ctypes.CDLL(path)
+    L.createEstimatorInstance.restype = ctypes.c_void_p
+    assert L.createEstimatorInstance()
