@@ -46,13 +46,13 @@ __host__ __device__ inline void pnp_sample(uint64_t seed, int h, int n, int idx[
   idx[0] = i0; idx[1] = i1; idx[2] = i2;
 }
 
-__device__ inline void cross3(const double* a, const double* b, double* o) {
+__host__ __device__ inline void cross3(const double* a, const double* b, double* o) {
   o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
 }
-__device__ inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__host__ __device__ inline double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
 // all real roots of x^3 + a x^2 + b x + c
-__device__ int cubic_real_roots(double a, double b, double c, double* x) {
+__host__ __device__ int cubic_real_roots(double a, double b, double c, double* x) {
   const double q = (a * a - 3.0 * b) / 9.0, r = (2.0 * a * a * a - 9.0 * a * b + 27.0 * c) / 54.0;
   const double q3 = q * q * q;
   if (r * r < q3) {
@@ -70,7 +70,7 @@ __device__ int cubic_real_roots(double a, double b, double c, double* x) {
 }
 
 // real roots of c[0] + ... + c[4] x^4, ascending: brackets between the critical points, bisection + guarded Newton
-__device__ int quartic_roots(const double* c, double* roots) {
+__host__ __device__ int quartic_roots(const double* c, double* roots) {
   if (c[4] == 0.0) return 0;
   const double a3 = c[3] / c[4], a2 = c[2] / c[4], a1 = c[1] / c[4], a0 = c[0] / c[4];
 #define QF(x) (((((x) + a3) * (x) + a2) * (x) + a1) * (x) + a0)
@@ -120,14 +120,14 @@ __device__ int quartic_roots(const double* c, double* roots) {
   return n;
 }
 
-__device__ inline void poly_mul(const double* a, int da, const double* b, int db, double* o) {
+__host__ __device__ inline void poly_mul(const double* a, int da, const double* b, int db, double* o) {
   for (int i = 0; i <= da + db; ++i) o[i] = 0.0;
   for (int i = 0; i <= da; ++i)
     for (int j = 0; j <= db; ++j) o[i + j] += a[i] * b[j];
 }
 
 // X: three world points, f: three unit bearings; up to 4 solutions Rt[12] = R (row-major, world->camera) | t
-__device__ int p3p(const double* X, const double* f, double* Rt_out) {
+__host__ __device__ int p3p(const double* X, const double* f, double* Rt_out) {
   const double *P1 = X, *P2 = X + 3, *P3 = X + 6, *f1 = f, *f2 = f + 3, *f3 = f + 6;
   double v12[3], v13[3], v23[3];
   for (int k = 0; k < 3; ++k) { v12[k] = P2[k] - P1[k]; v13[k] = P3[k] - P1[k]; v23[k] = P3[k] - P2[k]; }
@@ -288,6 +288,23 @@ int count_inliers_h(int n, const double* xyz, const double* xy, const double* Rt
   return c;
 }
 
+// The sequential definition replayed over per-hypothesis results: batches of 64, stop at the first batch boundary where
+// h >= log(1-confidence)/log(1-w^3) (w = best inlier ratio so far); best = (most inliers, lowest h).  Returns the hypotheses counted.
+int replay_stopping_rule(int n, int H, double confidence, const int* cnt, const int* root, gb_pnp_stats* st, int* best_out) {
+  int best = 0, h = 0;
+  double needed = (double)H;
+  while (h < H && (double)h < needed) {
+    const int h_end = h + 64 < H ? h + 64 : H;
+    for (; h < h_end; ++h)
+      if (cnt[h] > best) { best = cnt[h]; st->best_hypothesis = h; st->best_root = root[h]; }
+    const double w = (double)best / (double)n, w3 = w * w * w;
+    if (w3 >= 1.0) needed = 0.0;
+    else if (w3 > 0.0) needed = log(1.0 - confidence) / log(1.0 - w3);
+  }
+  *best_out = best;
+  return h;
+}
+
 }  // namespace
 
 extern "C" {
@@ -329,16 +346,8 @@ int gb_pnp_ransac(gb_ctx* ctx, int n, const double* xyz, const double* xy, doubl
   GB_CUDA(ctx, cudaMemcpyAsync(h_root, d_root, b_cnt, cudaMemcpyDeviceToHost, ctx->stream));
   GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   // replay of the sequential stopping rule over the speculatively computed hypotheses
-  int best = 0, h = 0;
-  double needed = (double)H;
-  while (h < H && (double)h < needed) {
-    const int h_end = h + 64 < H ? h + 64 : H;
-    for (; h < h_end; ++h)
-      if (h_cnt[h] > best) { best = h_cnt[h]; st.best_hypothesis = h; st.best_root = h_root[h]; }
-    const double w = (double)best / (double)n, w3 = w * w * w;
-    if (w3 >= 1.0) needed = 0.0;
-    else if (w3 > 0.0) needed = log(1.0 - confidence) / log(1.0 - w3);
-  }
+  int best = 0;
+  const int h = replay_stopping_rule(n, H, confidence, h_cnt, h_root, &st, &best);
   st.hypotheses = h;
   st.inliers_minimal = best;
   if (stats) *stats = st;
@@ -377,6 +386,46 @@ int gb_pnp_ransac(gb_ctx* ctx, int n, const double* xyz, const double* xy, doubl
   if (mask) memcpy(mask, m.data(), (size_t)n);
   if (stats) *stats = st;
   return GB_OK;
+}
+
+// ---- host-only checks (no device needed): the SAME source as the kernel, instantiated for the host, so that the CPU test suite can
+// compare the port with the CPU checker before the kernel has ever run (tests/test_oracle_pnp.py::test_product_host_instantiation_*)
+GB_API int gb_dbg_pnp_p3p_host(const double* X, const double* f, double* Rt_out) { return p3p(X, f, Rt_out); }
+
+// the minimal stage of gb_pnp_ransac (sampling, P3P, scoring, stopping-rule replay) with the hypotheses evaluated on the host
+GB_API int gb_dbg_pnp_minimal_host(int n, const double* xyz, const double* xy, double threshold, double confidence, int max_hypotheses,
+                                   uint64_t seed, double* best_Rt, gb_pnp_stats* stats) {
+  if (n < 4 || !xyz || !xy || !best_Rt || !stats || max_hypotheses < 1) return GB_ERR_INVALID;
+  const double thr2 = threshold * threshold;
+  std::vector<int> cnt((size_t)max_hypotheses), root((size_t)max_hypotheses);
+  std::vector<double> Rts((size_t)max_hypotheses * 12);
+  for (int h = 0; h < max_hypotheses; ++h) {
+    int idx[3];
+    pnp_sample(seed, h, n, idx);
+    double X[9], f[9], sol[48];
+    for (int k = 0; k < 3; ++k) {
+      memcpy(X + 3 * k, xyz + 3 * (size_t)idx[k], 24);
+      const double bx = xy[2 * (size_t)idx[k]], by = xy[2 * (size_t)idx[k] + 1], l = sqrt(bx * bx + by * by + 1.0);
+      f[3 * k] = bx / l; f[3 * k + 1] = by / l; f[3 * k + 2] = 1.0 / l;
+    }
+    const int ns = p3p(X, f, sol);
+    int best = 0, best_r = -1;
+    for (int r = 0; r < ns; ++r) {
+      const int c = count_inliers_h(n, xyz, xy, sol + 12 * r, thr2, nullptr);
+      if (c > best) { best = c; best_r = r; }
+    }
+    cnt[(size_t)h] = best; root[(size_t)h] = best_r;
+    if (best_r >= 0) memcpy(&Rts[12 * (size_t)h], sol + 12 * best_r, 96);
+  }
+  gb_pnp_stats st;
+  memset(&st, 0, sizeof st);
+  st.best_hypothesis = -1;
+  int best = 0;
+  st.hypotheses = replay_stopping_rule(n, max_hypotheses, confidence, cnt.data(), root.data(), &st, &best);
+  st.inliers_minimal = best;
+  *stats = st;
+  if (st.best_hypothesis >= 0) memcpy(best_Rt, &Rts[12 * (size_t)st.best_hypothesis], 96);
+  return best >= 4 ? GB_OK : GB_ERR_NUMERIC;
 }
 
 }  // extern "C"

@@ -112,3 +112,47 @@ def test_ransac_rejects_garbage():
         oracle.pnp_ransac(Xw, xy, threshold=1e-4, max_hypotheses=256)
     with pytest.raises(RuntimeError):
         oracle.pnp_ransac(Xw[:3], xy[:3])  # fewer than four correspondences
+
+
+# ---- the product's port (gslam_b200/csrc/pnp.cu), instantiated for the HOST: same source as the kernel, no device needed --------
+def _product_lib():
+    import ctypes as C
+    from gslam_b200 import capi
+    L = C.CDLL(capi.LIB_PATH)
+    L.gb_dbg_pnp_p3p_host.restype = C.c_int
+    L.gb_dbg_pnp_p3p_host.argtypes = [C.c_void_p] * 3
+    L.gb_dbg_pnp_minimal_host.restype = C.c_int
+    L.gb_dbg_pnp_minimal_host.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_uint64, C.c_void_p,
+                                          C.POINTER(capi.PnpStats)]
+    return L, capi
+
+
+def test_product_host_instantiation_of_p3p_equals_oracle():
+    L, _ = _product_lib()
+    rng = np.random.default_rng(3)
+    for _ in range(500):
+        Rg, tg = _random_pose(rng); tg = tg + np.array([0, 0, rng.uniform(4, 10)])
+        Xc = np.column_stack([rng.uniform(-2, 2, 3), rng.uniform(-2, 2, 3), rng.uniform(2, 9, 3)])
+        Xw = np.ascontiguousarray((Xc - tg) @ Rg); f = np.ascontiguousarray(Xc / np.linalg.norm(Xc, axis=1, keepdims=True))
+        out = np.zeros(48)
+        ns = L.gb_dbg_pnp_p3p_host(Xw.ctypes.data, f.ctypes.data, out.ctypes.data)
+        want = oracle.p3p(Xw, f)
+        assert ns == len(want)
+        for k, (Rs, ts) in enumerate(want):  # same source, same compiler family, no contraction on either side: bit-identical
+            assert np.array_equal(out[12 * k:12 * k + 9].reshape(3, 3), Rs) and np.array_equal(out[12 * k + 9:12 * k + 12], ts)
+
+
+@pytest.mark.parametrize("n,outliers,sigma", [(50, 0.0, 0.0), (300, 0.4, 1 / 718), (1500, 0.6, 1 / 718), (4, 0.0, 0.0)])
+def test_product_host_instantiation_of_the_minimal_stage_equals_oracle(n, outliers, sigma):
+    """Sampling, P3P, scoring and the stopping-rule replay of gb_pnp_ransac (host instantiation) pick the oracle's winner."""
+    import ctypes as C
+    L, capi = _product_lib()
+    rng = np.random.default_rng(n + 1)
+    for rep in range(4):
+        Xw, xy, Rg, tg, good = _scene(rng, n, outliers, sigma)
+        Xw = np.ascontiguousarray(Xw); xy = np.ascontiguousarray(xy)
+        _, _, want = oracle.pnp_ransac(Xw, xy, threshold=4 / 718, confidence=0.99, max_hypotheses=512, seed=rep + 1)
+        Rt = np.zeros(12); st = capi.PnpStats()
+        assert L.gb_dbg_pnp_minimal_host(n, Xw.ctypes.data, xy.ctypes.data, 4 / 718, 0.99, 512, rep + 1, Rt.ctypes.data, C.byref(st)) == 0
+        assert (st.hypotheses, st.best_hypothesis, st.best_root, st.inliers_minimal) == \
+               (want.hypotheses, want.best_hypothesis, want.best_root, want.inliers_minimal)
