@@ -6,7 +6,9 @@
 //   gslam_b200_host_test ba   <plugin-dir> in.bin out.bin      optimize(BundleGraph&) through GSLAM::Optimizer::create()
 //   gslam_b200_host_test pnp  <plugin-dir> in.bin out.bin      optimizePnP(...)
 //   gslam_b200_host_test orb  <plugin-dir> in.bin out.bin      Registry::load("b200") -> gslam.b200.orb_extract + match_hamming
+//   gslam_b200_host_test findpnp <plugin-dir> in.bin out.bin   Estimator::create() -> findPnP (P3P + RANSAC), Estimator.h:158-164
 #include <GSLAM/core/GSLAM.h>
+#include <GSLAM/core/Estimator.h>
 #include <GSLAM/core/Optimizer.h>
 
 #include <cstdio>
@@ -105,11 +107,44 @@ static int runORB(const std::string& dir, const char* in, const char* out) {
   return 0;
 }
 
+// in : int32 n, 3 x int32 pad, double threshold, double confidence, n x 3 doubles (world points), n x 2 doubles (normalised image points)
+// out: int32 ok, 7 doubles world2camera {qx,qy,qz,qw,tx,ty,tz}, n bytes mask
+static int runFindPnP(const std::string& dir, const char* in, const char* out) {
+  svar.Set<std::string>("GSLAM_LIBRARY_PATH", dir);
+  EstimatorPtr est = Estimator::create();  // default name "libgslam_estimator" (Estimator.h:181)
+  if (!est) { fprintf(stderr, "Estimator::create() returned null\n"); return 2; }
+  std::ifstream f(in, std::ios::binary);
+  int32_t hdr[4];
+  rd(f, hdr, 4);
+  const int n = hdr[0];
+  double thr, conf;
+  rd(f, &thr, 1); rd(f, &conf, 1);
+  std::vector<double> xyz(3 * (size_t)n), xy(2 * (size_t)n);
+  rd(f, xyz.data(), xyz.size()); rd(f, xy.data(), xy.size());
+  std::vector<Point3d> obj(n);
+  std::vector<Point2d> img(n);
+  for (int k = 0; k < n; ++k) { obj[k] = Point3d(xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2]); img[k] = Point2d(xy[2 * k], xy[2 * k + 1]); }
+  SE3 w2c;
+  std::vector<uchar> mask;
+  const bool ok = est->findPnP(&w2c, obj, img, P3_ITERATIVE & RANSAC, thr, conf, &mask);
+  std::ofstream o(out, std::ios::binary);
+  const int32_t okv = ok ? 1 : 0;
+  wr(o, &okv, 1);
+  const SO3& r = w2c.get_rotation();
+  const Point3d& t = w2c.get_translation();
+  const double p[7] = {r.x, r.y, r.z, r.w, t.x, t.y, t.z};
+  wr(o, p, 7);
+  mask.resize((size_t)n, 0);
+  wr(o, mask.data(), mask.size());
+  return ok ? 0 : 3;
+}
+
 int main(int argc, char** argv) {
-  if (argc < 5) { fprintf(stderr, "usage: %s ba|pnp|orb <plugin-dir> in.bin out.bin\n", argv[0]); return 64; }
+  if (argc < 5) { fprintf(stderr, "usage: %s ba|pnp|orb|findpnp <plugin-dir> in.bin out.bin\n", argv[0]); return 64; }
   const std::string mode = argv[1];
   if (mode == "ba") return runBA(argv[2], argv[3], argv[4], false);
   if (mode == "pnp") return runBA(argv[2], argv[3], argv[4], true);
   if (mode == "orb") return runORB(argv[2], argv[3], argv[4]);
+  if (mode == "findpnp") return runFindPnP(argv[2], argv[3], argv[4]);
   return 64;
 }

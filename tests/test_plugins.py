@@ -61,6 +61,26 @@ def test_discovery_and_failure_convention_without_gpu():
 
 
 @needs_plugins
+def test_estimator_discovery_and_failure_convention_without_gpu():
+    """Estimator::create() must find libgslam_estimator.so (Estimator.h:175-191); without a device findPnP returns false."""
+    import ctypes
+    if not os.path.exists(os.path.join(LIB, "libgslam_estimator.so")):
+        pytest.skip("estimator plugin not built")
+    n = ctypes.c_int(0)
+    if capi.lib().gb_device_count(ctypes.byref(n)) == 0 and n.value > 0:
+        pytest.skip("GPU present: the kernel behind findPnP is validated by tools/gpu_pnp_check.py first (DESIGN.md section 1, row f)")
+    rng = np.random.default_rng(0)
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "in.bin"), "wb") as f:
+            f.write(struct.pack("<4i", 20, 0, 0, 0)); f.write(struct.pack("<2d", 0.01, 0.99))
+            f.write(rng.normal(size=(20, 3)).tobytes()); f.write(rng.normal(size=(20, 2)).tobytes())
+        r = run("findpnp", os.path.join(d, "in.bin"), os.path.join(d, "out.bin"))
+        assert r.returncode == 3, (r.returncode, r.stderr)   # 2 would mean create() returned null
+        assert "no usable CUDA device" in (r.stderr + r.stdout)
+        assert struct.unpack("<i", open(os.path.join(d, "out.bin"), "rb").read(4))[0] == 0
+
+
+@needs_plugins
 @pytest.mark.gpu
 def test_optimize_through_reference_api_matches_oracle():
     """BASELINE config 1 (10 cams / 200 pts) + a local-BA window through GSLAM::Optimizer::create()->optimize(BundleGraph&)."""
