@@ -1,5 +1,5 @@
 """FIRST thing to run on a B200 in round 2: gb_pnp_ransac (gslam_b200/csrc/pnp.cu, written after round 1's GPU budget was spent)
-against the CPU checker oracle/pnp_ref.c on synthetic 2D-3D sets — same winning hypothesis, same inlier mask, pose within 1e-9.
+against the CPU checker oracle/pnp_ref.c on synthetic 2D-3D sets — same winning hypothesis, same inlier mask, pose within 1e-7.
 Run it once under `compute-sanitizer --tool memcheck` too, then turn the cases into tests/test_pnp_gpu.py."""
 import os, sys, time
 R_ = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -25,7 +25,7 @@ for (n, of, sig) in [(50, 0.0, 0.0), (200, 0.3, 1 / 718), (2000, 0.5, 1 / 718), 
         got = ctx.pnp_ransac(Xw, xy, threshold=4 / 718, confidence=0.99, max_hypotheses=1024, seed=rep + 1)
         dt = time.perf_counter() - t0
         same = (got[2].best_hypothesis == want[2].best_hypothesis and got[2].best_root == want[2].best_root
-                and got[2].hypotheses == want[2].hypotheses and np.array_equal(got[1], want[1]) and np.abs(got[0] - want[0]).max() < 1e-9)
+                and got[2].hypotheses == want[2].hypotheses and np.array_equal(got[1], want[1]) and np.abs(got[0] - want[0]).max() < 1e-7)
         bad += not same
         print("ok      " if same else "MISMATCH", n, of, rep, "hyp", got[2].hypotheses, want[2].hypotheses, "winner", got[2].best_hypothesis,
               want[2].best_hypothesis, "inliers", got[2].inliers_refined, want[2].inliers_refined, f"pose diff {np.abs(got[0] - want[0]).max():.2e}",

@@ -1,7 +1,7 @@
 """PENDING (move to tests/ once tools/gpu_pnp_check.py has been seen green on a B200, ideally after one compute-sanitizer pass):
 GPU parity of gb_pnp_ransac and of Estimator::findPnP through the reference API against oracle/pnp_ref.c.
 
-Bar: same number of counted hypotheses, same winning hypothesis and root, identical inlier mask, pose within 1e-9 (the minimal
+Bar: same number of counted hypotheses, same winning hypothesis and root, identical inlier mask, pose within 1e-7 (the refinement is an LM solve on both sides: agreement at its convergence level; the minimal
 solver runs in fp64 on both sides with contraction disabled; only libm-vs-CUDA-math ulp differences in acos/cos/cbrt can move a
 bracket, and the bisection + Newton steps converge to the same root)."""
 import os
@@ -41,7 +41,7 @@ def test_ransac_matches_oracle(ctx, n, outliers, sigma):
         for f in ("hypotheses", "best_hypothesis", "best_root", "inliers_minimal", "inliers_refined"):
             assert getattr(got[2], f) == getattr(want[2], f), f
         assert np.array_equal(got[1], want[1])
-        assert np.abs(got[0] - want[0]).max() < 1e-9
+        assert np.abs(got[0] - want[0]).max() < 1e-7
 
 
 def test_no_consistent_pose_is_an_error(ctx):
@@ -66,4 +66,4 @@ def test_find_pnp_through_reference_api():
         raw = open(os.path.join(d, "out.bin"), "rb").read()
     assert struct.unpack("<i", raw[:4])[0] == 1
     pose = np.frombuffer(raw[4:60], np.float64); mask = np.frombuffer(raw[60:560], np.uint8)
-    assert np.abs(pose - want[0]).max() < 1e-9 and np.array_equal(mask, want[1])
+    assert np.abs(pose - want[0]).max() < 1e-7 and np.array_equal(mask, want[1])
