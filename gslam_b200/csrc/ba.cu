@@ -13,6 +13,7 @@
 // All LM state lives in BaScalars on the device; kernels early-exit on its flags, so an iteration needs no host sync.
 #include "ba_device.cuh"
 #include "common.cuh"
+#include "ba_internal.cuh"
 
 #include <cooperative_groups.h>
 
@@ -28,6 +29,7 @@ using namespace ba;
 // ======================================================================================================================
 namespace {
 
+constexpr int kMaxBlockCams = 2048;  // covisibility block structure of S is derived on the host up to this many cameras
 constexpr int kPtThreads = 128;
 constexpr int kCamThreads = 128;
 constexpr int kRedThreads = 1024;
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(128) ba_schur_blocks_kernel(BaDev g, double* _
       if (!diag) g.Sb[36 * (size_t)g.s_tidx[blk] + b * 6 + a] = v;
     } else if (diag) {
       const int a = k - 36;
-      const size_t n6 = g.n6, nS = n6 * n6;
+      const size_t n6 = g.n6, nS = g.r_gt;
       buf[nS + 6 * i + a] = g.gc[6 * i + a] - sum;
       buf[nS + n6 + 6 * i + a] = g.U[36 * i + a * 7];
     }
@@ -617,7 +619,7 @@ __global__ void ba_commit_kernel(BaDev g, const double* __restrict__ buf, const 
   BaScalars* sc = g.sc;
   if (sc->stop) return;
   const size_t n6 = g.n6;
-  const double cost = buf[n6 * n6 + 2 * n6], cnew = d_cost[0];
+  const double cost = buf[g.r_gt + 2 * n6], cnew = d_cost[0];
   if (sc->iterations == 0) sc->initial_cost = cost;
   sc->cost = cost;
   sc->cost_new = cnew;
@@ -638,6 +640,43 @@ __global__ void ba_commit_kernel(BaDev g, const double* __restrict__ buf, const 
     sc->nu *= 2.0;
     if (sc->lambda > 1e16) { sc->stop = 1; sc->status = 2; }
   }
+}
+
+// LM accept / reject AND the installation of an accepted candidate in one launch (compact path).  Every thread derives the
+// decision from the two (possibly all-reduced) costs alone; only thread 0 of CTA 0 touches the LM scalars, so nobody reads what it
+// writes.  Re-running it after a stop is harmless: the candidate arrays are frozen once `stop` is set.
+__global__ void ba_commit_apply_kernel(BaDev g, const double* __restrict__ buf, const double* __restrict__ d_cost) {
+  const size_t n6 = g.n6;
+  const double cost = buf[g.r_gt + 2 * n6], cnew = d_cost[0];
+  const bool ok = (cnew < cost) && isfinite(cnew);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    BaScalars* sc = g.sc;
+    if (!sc->stop) {
+      if (sc->iterations == 0) sc->initial_cost = cost;
+      sc->cost = cost;
+      sc->cost_new = cnew;
+      sc->iterations++;
+      sc->need_linearize = ok ? 1 : 0;
+      if (ok) {
+        const double rel = (cost - cnew) / cost;
+        sc->cost = cnew;
+        const double l = sc->lambda / 3.0;
+        sc->lambda = l < 1e-15 ? 1e-15 : l;
+        sc->nu = 2.0;
+        sc->accepted++;
+        if (rel < sc->ftol) { sc->stop = 1; sc->status = 1; }
+      } else {
+        sc->lambda *= sc->nu;
+        sc->nu *= 2.0;
+        if (sc->lambda > 1e16) { sc->stop = 1; sc->status = 2; }
+      }
+    }
+  }
+  if (!ok) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < g.nc * 7) g.pose[t] = g.pose_new[t];
+  if (t < g.nc * 12) g.Rt[t] = g.Rt_new[t];
+  if (t < g.np * 3) g.pts[t] = g.pts_new[t];
 }
 
 // on accept: estimate <- candidate.  (runs even when ba_commit just set stop: the accepted step must land)
@@ -677,8 +716,8 @@ __global__ void __launch_bounds__(256) ba_prepare_schur_kernel(BaDev g, double* 
     buf[idx] = (i == i2) ? g.U[36 * i + (row % 6) * 6 + (col % 6)] : 0.0;
   }
   for (size_t d = t0; dense && d < n6; d += stride) {
-    buf[nS + d] = g.gc[d];
-    buf[nS + n6 + d] = g.U[36 * (d / 6) + (d % 6) * 7];
+    buf[g.r_gt + d] = g.gc[d];
+    buf[g.r_gt + n6 + d] = g.U[36 * (d / 6) + (d % 6) * 7];
   }
   const double lambda = g.sc->lambda;
   const bool fresh = g.sc->need_linearize != 0;  // the sweep of this iteration already produced Vinv with this lambda
@@ -702,7 +741,7 @@ __global__ void __launch_bounds__(256) ba_prepare_schur_kernel(BaDev g, double* 
     double v = 0.0;
     for (int k = threadIdx.x; k < g.np; k += 256) v += g.cost_pt[k];
     const double t = block_sum<256>(v, s_part);
-    if (threadIdx.x == 0) buf[nS + 2 * n6] = 0.5 * t;
+    if (threadIdx.x == 0) buf[g.r_gt + 2 * n6] = 0.5 * t;
   }
 }
 
@@ -1401,27 +1440,6 @@ __global__ void __launch_bounds__(kPcgThreads, 1) ba_pcg_cluster_kernel(BaDev g,
 // ======================================================================================================================
 // host side
 // ======================================================================================================================
-struct gb_ba_graph {
-  BaDev d{};
-  uint8_t* slab = nullptr;  // one device allocation (or the ctx arena) holding everything below
-  size_t slab_bytes = 0;
-  bool from_arena = false;
-  double *pose_init = nullptr, *pts_init = nullptr, *pose_wc_out = nullptr;
-  double* buf = nullptr;     // internal [S | gt | diagU | cost | pad]
-  double* d_cost = nullptr;  // internal candidate cost
-  size_t buf_doubles = 0;
-  gb_ba_options opt{};
-  std::vector<int> sorted_to_orig;  // sorted observation slot -> caller's edge index
-  bool begun = false;
-  // PCG dispatch: single-CTA block-sparse kernel, else one-cluster kernel (pcg_cluster = 8/16), else generic multi-kernel
-  bool pcg_sparse = false;
-  size_t pcg_sparse_smem = 0;
-  int pcg_max_row_blocks = 0;  // longest block row of S
-  bool sweep_only = false;     // the last begin came from gb_ba_graph_sweep and nothing else ran since
-  int pcg_nact = 0;            // cameras with at least one free dof (the sparse PCG kernel gives lanes to these only)
-  int pcg_cluster = 0;
-  size_t pcg_smem = 0;
-};
 
 static size_t ba_buf_doubles(int nc) {
   const size_t n6 = 6 * (size_t)nc;
@@ -1467,40 +1485,50 @@ static int ba_validate(gb_ctx* ctx, const gb_ba_problem* pb) {
   return GB_OK;
 }
 
+// The dynamic shared-memory limit of a kernel is per-function, per-DEVICE global state: raise it ONCE per device to the opt-in
+// maximum and never lower it -- several ctxs (tracking thread: gb_ba_pnp on a 1-camera graph; mapping thread: local BA) share
+// the functions, and a per-graph value set by one could be too small for a launch already planned by the other.
+static bool g_cluster16_ok[64] = {false};
+static bool ba_raise_smem_limits(gb_ctx* ctx) {
+  static std::mutex mu;
+  static int state[64] = {0};  // 0 = not done, 1 = ok, 2 = failed
+  const int dev = ctx->device;
+  if (dev < 0 || dev >= 64) return false;
+  std::lock_guard<std::mutex> lk(mu);
+  if (state[dev] == 0) {
+    g_cluster16_ok[dev] = cudaFuncSetAttribute(ba_pcg_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    const int lim = ctx->max_smem_optin;
+    bool ok = cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) == cudaSuccess;
+    ok = (cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) == cudaSuccess) && ok;
+    ok = (cudaFuncSetAttribute(ba_pcg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) == cudaSuccess) && ok;
+    cudaGetLastError();
+    state[dev] = ok ? 1 : 2;
+  }
+  return state[dev] == 1;
+}
+
 // Can the reduced camera system be solved by the one-cluster PCG kernel?  Pick the cluster size, remember the smem need.
 static void ba_pick_pcg(gb_ctx* ctx, gb_ba_graph* g) {
   g->pcg_cluster = 0;
   g->pcg_sparse = false;
   const int nc = g->d.nc, n6 = g->d.n6;
+  const bool smem_ok = ba_raise_smem_limits(ctx);
   if (nc > 0 && g->pcg_nact <= kSpMaxCams && g->d.s_nnzb > 0) {
     const size_t smem = ((size_t)g->d.s_nnzb * 36 + (size_t)nc * 36 + 3 * (size_t)n6) * sizeof(double) + (2 * (size_t)nc + 1 + g->d.s_nnzb) * sizeof(int) + 64;
-    cudaError_t ea = g->pcg_nact <= kSpSmallCams ? cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                                 : cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (smem <= (size_t)ctx->max_smem_optin && ea == cudaSuccess) {
+    if (smem <= (size_t)ctx->max_smem_optin && smem_ok) {
       g->pcg_sparse = true;
       g->pcg_sparse_smem = smem;
     }
-    cudaGetLastError();
   }
   if (nc <= 0 || n6 > kPcgThreads) return;  // the cluster kernel maps one thread per element of the 6N vectors
-  static bool attr_done = false;
-  static bool np_ok = false;
-  if (!attr_done) {
-    attr_done = true;
-    np_ok = cudaFuncSetAttribute(ba_pcg_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
-    cudaGetLastError();
-  }
+  const bool np_ok = smem_ok && g_cluster16_ok[ctx->device];
   const int sizes[2] = {16, 8};
   for (int t = 0; t < 2; ++t) {
     const int C = sizes[t];
     if (C == 16 && !np_ok) continue;
     const int cpc = (nc + C - 1) / C;
     const size_t smem = ((size_t)6 * cpc * n6 + (size_t)nc * 36 + 7 * (size_t)n6) * sizeof(double) + 64;
-    if (smem > (size_t)ctx->max_smem_optin) continue;
-    if (cudaFuncSetAttribute(ba_pcg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      cudaGetLastError();
-      continue;
-    }
+    if (smem > (size_t)ctx->max_smem_optin || !smem_ok) continue;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(C); cfg.blockDim = dim3(kPcgThreads); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
     cudaLaunchAttribute at[1];
@@ -1518,7 +1546,6 @@ static void ba_pick_pcg(gb_ctx* ctx, gb_ba_graph* g) {
   }
 }
 
-static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out, bool use_arena);
 
 // GB_BA_TRACE=1: wall-clock stamps of the host-side phases of a host-buffer solve (stderr), for tools/e2e_breakdown.py
 struct BaTrace {
@@ -1549,6 +1576,10 @@ void gb_ba_options_default(gb_ba_options* o) {
 
 int gb_ba_graph_destroy(gb_ctx* ctx, gb_ba_graph* g) {
   if (!g) return GB_OK;
+  if (g->bcsr_cta_cam) {
+    if (ctx) { CtxLock lk(ctx); cudaStreamSynchronize(ctx->stream); }
+    ba_pcg_bcsr_free(g);
+  }
   if (g->from_arena) {
     if (ctx) ctx->ba_arena_busy = false;
   } else {
@@ -1563,63 +1594,86 @@ int gb_ba_graph_destroy(gb_ctx* ctx, gb_ba_graph* g) {
 }
 
 int gb_ba_graph_create(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out) {
-  return ba_graph_create_impl(ctx, pb, out, false);
+  return ba_graph_create_impl(ctx, pb, out, false, 0, 1);
 }
 
 }  // extern "C"
 
-static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out, bool use_arena) {
+int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out, bool use_arena, int shard_rank, int shard_world) {
   if (!ctx || !out) return GB_ERR_INVALID;
   *out = nullptr;
   CtxLock lk(ctx);
   BaTrace tr;
   GB_CHECK(ba_validate(ctx, pb));
+  if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return GB_ERR_INVALID;
   tr.stamp("validate");
-  const int nc = pb->n_cams, np = pb->n_points, no = pb->n_obs;
+  const int nc = pb->n_cams, np_full = pb->n_points, no_full = pb->n_obs;
   gb_ba_graph* g = new gb_ba_graph();
   struct Guard {
     gb_ctx* c; gb_ba_graph* g; bool ok = false;
     ~Guard() { if (!ok) gb_ba_graph_destroy(c, g); }
   } guard{ctx, g};
   BaDev& d = g->d;
-  d.nc = nc; d.np = np; d.no = no; d.n6 = 6 * nc; d.has_info = pb->obs_info ? 1 : 0;
-  g->buf_doubles = ba_buf_doubles(nc);
 
-  // ---- host-side ordering: stable counting sorts -> (point, camera) order, and the per-camera lists ----------------
+  // ---- host-side ordering over the WHOLE graph: stable counting sorts -> (point, camera) order -------------------------
   // (one histogram pass over both keys; `scam` keeps the camera of each sorted edge so that later passes stream it)
-  std::vector<int> byc(no), order(no), scam(no), cam_off(nc + 1, 0), pt_off(np + 1, 0), cam_perm(no);
-  for (int k = 0; k < no; ++k) { cam_off[pb->obs_cam[k] + 1]++; pt_off[pb->obs_point[k] + 1]++; }
-  for (int i = 0; i < nc; ++i) cam_off[i + 1] += cam_off[i];
-  for (int j = 0; j < np; ++j) pt_off[j + 1] += pt_off[j];
-  { std::vector<int> pos(cam_off.begin(), cam_off.end()); for (int k = 0; k < no; ++k) byc[pos[pb->obs_cam[k]]++] = k; }
+  std::vector<int> order, scam, pt_off;
   {
-    std::vector<int> pos(pt_off.begin(), pt_off.end());
-    for (int t = 0; t < no; ++t) { const int k = byc[t]; const int e = pos[pb->obs_point[k]]++; order[e] = k; scam[e] = pb->obs_cam[k]; }
+    std::vector<int> byc(no_full), cam_off_full(nc + 1, 0);
+    order.resize(no_full); scam.resize(no_full); pt_off.assign(np_full + 1, 0);
+    for (int k = 0; k < no_full; ++k) { cam_off_full[pb->obs_cam[k] + 1]++; pt_off[pb->obs_point[k] + 1]++; }
+    for (int i = 0; i < nc; ++i) cam_off_full[i + 1] += cam_off_full[i];
+    for (int j = 0; j < np_full; ++j) pt_off[j + 1] += pt_off[j];
+    { std::vector<int> pos(cam_off_full.begin(), cam_off_full.end()); for (int k = 0; k < no_full; ++k) byc[pos[pb->obs_cam[k]]++] = k; }
+    std::vector<int> pos(pt_off.begin(), pt_off.end() - 1);
+    for (int t = 0; t < no_full; ++t) { const int k = byc[t]; const int e = pos[pb->obs_point[k]]++; order[e] = k; scam[e] = pb->obs_cam[k]; }
   }
-  { std::vector<int> pos(cam_off.begin(), cam_off.end()); for (int e = 0; e < no; ++e) cam_perm[pos[scam[e]]++] = e; }
-
-  tr.stamp("counting sorts");
-  // ---- layout: one slab = [uploaded blob | working set] ----------------------------------------------------------------
-  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t b_pose = al((size_t)nc * 7 * 8), b_pts = al((size_t)np * 3 * 8), b_dof = al(nc), b_pf = al(np),
-               b_oc = al((size_t)no * 4), b_op = al((size_t)no * 4), b_uv = al((size_t)no * 16),
-               b_info = d.has_info ? al((size_t)no * 24) : 0, b_po = al((size_t)(np + 1) * 4), b_co = al((size_t)(nc + 1) * 4),
-               b_cp = al((size_t)no * 4), b_cpt = al((size_t)no * 4), b_cuv = al((size_t)no * 16);
-  // covisibility block structure of S: block (i,i') is structurally non-zero iff some landmark is seen by both cameras
+  {  // duplicate (camera, point) edges would make the block-gather Schur complement drop their cross terms: reject them
+    for (int e = 1; e < no_full; ++e)
+      if (scam[e] == scam[e - 1] && pb->obs_point[order[e]] == pb->obs_point[order[e - 1]]) {
+        gb_set_error(ctx, "gb_ba: edges %d and %d both connect camera %d and point %d (merge duplicate observations)", order[e - 1], order[e],
+                     scam[e], pb->obs_point[order[e]]);
+        return GB_ERR_INVALID;
+      }
+  }
+  // ---- landmark shard: a contiguous landmark range balanced by observation count; since the edges are sorted by landmark the
+  //      shard's edges are ONE contiguous slice [e_lo, e_hi) of the sorted order
+  int lo = 0, hi = np_full;
+  if (shard_world > 1) {
+    auto bound = [&](int r) {
+      if (r <= 0) return 0;
+      if (r >= shard_world) return np_full;
+      const double target = (double)no_full * (double)r / (double)shard_world;
+      return (int)(std::lower_bound(pt_off.begin(), pt_off.end(), target, [](int a, double t) { return (double)a < t; }) - pt_off.begin());
+    };
+    lo = std::min(bound(shard_rank), np_full);
+    hi = std::min(std::max(bound(shard_rank + 1), lo), np_full);
+  }
+  g->shard_lo = lo; g->shard_hi = hi; g->shard_rank = shard_rank; g->shard_world = shard_world;
+  const int e_lo = pt_off[lo], e_hi = pt_off[hi];
+  const int np = hi - lo, no = e_hi - e_lo;
+  d.nc = nc; d.np = np; d.no = no; d.n6 = 6 * nc; d.has_info = pb->obs_info ? 1 : 0;
+  d.r_gt = (size_t)d.n6 * d.n6;  // dense layout unless a launch says otherwise (ba_reduce_local_compact / ba_commit_compact)
+  g->buf_doubles = ba_buf_doubles(nc);
+  // covisibility block structure of S over the WHOLE graph (every rank of a sharded solve must agree on the layout): block
+  // (i,i') is structurally non-zero iff some landmark is seen by both cameras
   std::vector<int> s_rowptr(nc + 1, 0), s_col, s_brow;
-  if (nc > 0 && nc <= 1024) {
+  if (nc > 0 && nc <= kMaxBlockCams) {
     // one bit row per camera; a landmark ORs the bit mask of its observers into the row of each of them
     const int words = (nc + 63) / 64;
     std::vector<uint64_t> rows((size_t)nc * words, 0), mask(words);
     for (int i = 0; i < nc; ++i) rows[(size_t)i * words + (i >> 6)] |= 1ull << (i & 63);
-    for (int j = 0; j < np; ++j) {
+    for (int j = 0; j < np_full; ++j) {
       const int a = pt_off[j], b = pt_off[j + 1];
       if (b - a < 2) continue;
-      std::fill(mask.begin(), mask.end(), 0ull);
+      if (pb->point_free && !pb->point_free[j]) continue;  // a fixed landmark couples nothing
+      int wlo = words, whi = -1;
+      for (int e = a; e < b; ++e) { const int w = scam[e] >> 6; wlo = std::min(wlo, w); whi = std::max(whi, w); }
+      for (int w = wlo; w <= whi; ++w) mask[w] = 0ull;
       for (int e = a; e < b; ++e) { const int i = scam[e]; mask[i >> 6] |= 1ull << (i & 63); }
       for (int e = a; e < b; ++e) {
         uint64_t* row = &rows[(size_t)scam[e] * words];
-        for (int w = 0; w < words; ++w) row[w] |= mask[w];
+        for (int w = wlo; w <= whi; ++w) row[w] |= mask[w];
       }
     }
     for (int i = 0; i < nc; ++i) {
@@ -1634,6 +1688,24 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
       s_rowptr[i + 1] = (int)s_col.size();
     }
   }
+  tr.stamp("counting sorts + covisibility");
+  // ---- restrict to the shard ---------------------------------------------------------------------------------------------
+  if (shard_world > 1) {
+    std::vector<int> o2(order.begin() + e_lo, order.begin() + e_hi), c2(scam.begin() + e_lo, scam.begin() + e_hi), p2(np + 1);
+    for (int j = 0; j <= np; ++j) p2[j] = pt_off[lo + j] - e_lo;
+    order.swap(o2); scam.swap(c2); pt_off.swap(p2);
+  }
+  std::vector<int> cam_off(nc + 1, 0), cam_perm(no);
+  for (int e = 0; e < no; ++e) cam_off[scam[e] + 1]++;
+  for (int i = 0; i < nc; ++i) cam_off[i + 1] += cam_off[i];
+  { std::vector<int> pos(cam_off.begin(), cam_off.end()); for (int e = 0; e < no; ++e) cam_perm[pos[scam[e]]++] = e; }
+
+  // ---- layout: one slab = [uploaded blob | working set] ----------------------------------------------------------------
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_pose = al((size_t)nc * 7 * 8), b_pts = al((size_t)np * 3 * 8), b_dof = al(nc), b_pf = al(np),
+               b_oc = al((size_t)no * 4), b_op = al((size_t)no * 4), b_uv = al((size_t)no * 16),
+               b_info = d.has_info ? al((size_t)no * 24) : 0, b_po = al((size_t)(np + 1) * 4), b_co = al((size_t)(nc + 1) * 4),
+               b_cp = al((size_t)no * 4), b_cpt = al((size_t)no * 4), b_cuv = al((size_t)no * 16);
   d.s_nnzb = (int)s_col.size();
   std::vector<int> s_upper, s_tidx(s_col.size(), 0);
   for (int blk = 0; blk < (int)s_col.size(); ++blk) {
@@ -1648,6 +1720,8 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   for (int i = 0; i < nc; ++i) g->pcg_nact += (pb->cam_dof ? (pb->cam_dof[i] & 63) : 63) != 0;
   for (int i = 0; i < nc && !s_col.empty(); ++i) g->pcg_max_row_blocks = std::max(g->pcg_max_row_blocks, s_rowptr[i + 1] - s_rowptr[i]);
   const size_t b_sr = al((size_t)(nc + 1) * 4), b_sc = al((size_t)s_col.size() * 4 + 4);
+  const bool compact_only = shard_world > 1;  // a shard only ever sees the compact reduced layout: no dense 6N x 6N buffer
+  g->rbuf_doubles = d.s_nnzb > 0 ? (size_t)d.s_nnzb * 36 + 2 * (size_t)d.n6 + 8 : 0;
   const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + b_sr + 4 * b_sc + b_cpt + b_cuv + 256;
   const size_t n6 = 6 * (size_t)nc;
   uint8_t* dblob = nullptr;
@@ -1673,8 +1747,9 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
     sl.take(&d.Sb, (size_t)d.s_nnzb * 36);
     sl.take(&d.x, n6); sl.take(&d.r, n6); sl.take(&d.z, n6); sl.take(&d.p, n6); sl.take(&d.q, n6); sl.take(&d.sv, n6);
     sl.take(&d.sc, 1);
-    sl.take(&g->buf, g->buf_doubles);
+    sl.take(&g->buf, compact_only ? 8 : g->buf_doubles);
     sl.take(&g->d_cost, 8);
+    sl.take(&g->rbuf, g->rbuf_doubles);
   };
   Slab measure;
   layout(measure);
@@ -1710,14 +1785,14 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
                o_op = take(b_op), o_uv = take(b_uv), o_info = take(b_info), o_po = take(b_po), o_co = take(b_co), o_cp = take(b_cp),
                o_sr = take(b_sr), o_sc = take(b_sc), o_sb = take(b_sc), o_su = take(b_sc), o_st = take(b_sc), o_cpt = take(b_cpt), o_cuv = take(b_cuv);
   memcpy(h + o_pose, pb->cam_pose_wc, (size_t)nc * 56);
-  memcpy(h + o_pts, pb->points, (size_t)np * 24);
+  if (np > 0) memcpy(h + o_pts, pb->points + 3 * (size_t)lo, (size_t)np * 24);
   for (int i = 0; i < nc; ++i) h[o_dof + i] = pb->cam_dof ? (pb->cam_dof[i] & 63) : 63;
-  for (int j = 0; j < np; ++j) h[o_pf + j] = pb->point_free ? (pb->point_free[j] ? 1 : 0) : 1;
+  for (int j = 0; j < np; ++j) h[o_pf + j] = pb->point_free ? (pb->point_free[lo + j] ? 1 : 0) : 1;
   int* hoc = (int*)(h + o_oc); int* hop = (int*)(h + o_op); double* huv = (double*)(h + o_uv); double* hin = (double*)(h + o_info);
   for (int e = 0; e < no; ++e) {
     const int k = order[e];
     hoc[e] = scam[e];
-    hop[e] = pb->obs_point[k];
+    hop[e] = pb->obs_point[k] - lo;
     const double* m = pb->obs_xyz + 3 * (size_t)k;
     huv[2 * e] = m[0] / m[2];
     huv[2 * e + 1] = m[1] / m[2];
@@ -1764,6 +1839,11 @@ static int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_grap
   }
   GB_CHECK(gb_ba_graph_reset(ctx, g));
   ba_pick_pcg(ctx, g);
+  if (!g->pcg_sparse && d.s_nnzb > 0) GB_CHECK(ba_pcg_bcsr_plan(ctx, g, s_rowptr.data()));
+  if (compact_only && !g->pcg_bcsr) {
+    gb_set_error(ctx, "gb_ba: the sharded solve needs the block-CSR reduced system (<= %d cameras)", kMaxBlockCams);
+    return GB_ERR_INVALID;
+  }
   tr.stamp("enqueue H2D + prepare");
   // the pinned blob is reused by the next outermost call on this ctx: a graph handed to the caller must have consumed it; the
   // one-shot host-buffer paths (gb_ba_solve / gb_ba_pnp) synchronise in their own finish + download before they return
@@ -1840,7 +1920,6 @@ static int ba_pcg_cluster(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = g->pcg_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  GB_CUDA(ctx, cudaFuncSetAttribute(ba_pcg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_smem));
   GB_CUDA(ctx, cudaLaunchKernelEx(&cfg, ba_pcg_cluster_kernel, g->d, buf, (int)g->opt.pcg_max_iters));
   GB_LAUNCH_CHECK(ctx);
   return GB_OK;
@@ -1893,16 +1972,61 @@ int gb_ba_graph_reduce_local(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   return GB_OK;
 }
 
+}  // extern "C"
+
+// ---- the LM iteration on the COMPACT reduced layout rbuf = [Sb (nnzb x 36) | g~ | diag U | cost | pad] ------------------------------
+// (large graphs on one GPU and every rank of the landmark-sharded solve: the shard's contribution is what the collective sums)
+int ba_reduce_local_compact(gb_ctx* ctx, gb_ba_graph* g, double* rbuf) {
+  if (!ctx || !g || !g->begun || !rbuf || g->d.s_nnzb <= 0) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  BaDev d = g->d;
+  d.Sb = rbuf;
+  d.r_gt = (size_t)d.s_nnzb * 36;
+  cudaStream_t s = ctx->stream;
+  const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads), cam_blocks = d.nc * d.cam_split;
+  if (pt_blocks + cam_blocks > 0) { ba_linearize_kernel<<<pt_blocks + cam_blocks, kPtThreads, 0, s>>>(d, cam_blocks); GB_LAUNCH_CHECK(ctx); }
+  {
+    const int nblk = (int)std::min<size_t>(std::max<size_t>(((size_t)d.np + 255) / 256, 1), (size_t)ctx->sm_count * 8);
+    ba_prepare_schur_kernel<<<nblk, 256, 0, s>>>(d, rbuf, 0); GB_LAUNCH_CHECK(ctx);
+  }
+  ba_schur_blocks_kernel<<<d.s_nupper, 128, 0, s>>>(d, rbuf); GB_LAUNCH_CHECK(ctx);
+  return GB_OK;
+}
+
+int ba_backsub_cost_compact(gb_ctx* ctx, gb_ba_graph* g, double* d_cost) {
+  if (!ctx || !g || !g->begun) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  BaDev& d = g->d;
+  if (!d_cost) d_cost = g->d_cost;
+  if (d.np > 0) { ba_backsub_cost_kernel<<<gb_div_up(d.np * kLpp, 128), 128, 0, ctx->stream>>>(d); GB_LAUNCH_CHECK(ctx); }
+  ba_reduce_cost_kernel<<<1, kRedThreads, 0, ctx->stream>>>(d.sc, d.cost_pt_new, d.np, d_cost); GB_LAUNCH_CHECK(ctx);
+  return GB_OK;
+}
+
+int ba_commit_compact(gb_ctx* ctx, gb_ba_graph* g, const double* rbuf, const double* d_cost) {
+  if (!ctx || !g || !g->begun || !rbuf) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  BaDev d = g->d;
+  d.r_gt = (size_t)d.s_nnzb * 36;
+  if (!d_cost) d_cost = g->d_cost;
+  cudaStream_t s = ctx->stream;
+  const int n = std::max(std::max(d.nc * 12, d.np * 3), 1);
+  ba_commit_apply_kernel<<<gb_div_up(n, 256), 256, 0, s>>>(d, rbuf, d_cost); GB_LAUNCH_CHECK(ctx);
+  return GB_OK;
+}
+
+int ba_read_result(gb_ctx* ctx, gb_ba_graph* g, gb_ba_result* res) { return gb_ba_graph_finish(ctx, g, res); }
+
+extern "C" {
+
 static int ba_pcg_dispatch(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   BaDev& d = g->d;
   cudaStream_t s = ctx->stream;
   if (d.nc <= 0) return GB_OK;
   if (g->pcg_sparse && buf == g->buf) {
     if (g->pcg_nact <= kSpSmallCams) {
-      GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
       BA_SPARSE_SMALL<<<1, kSpSmallThreads, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
     } else {
-      GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
       BA_SPARSE_LARGE<<<1, kSpLargeThreads, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
     }
     GB_LAUNCH_CHECK(ctx);
@@ -1986,10 +2110,6 @@ static int ba_graph_solve_impl(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options*
   const bool fused_commit = (size_t)g->d.np * 3 + (size_t)g->d.nc * 19 <= (size_t)1 << 16;
   // local-BA fast path (block-CSR Schur + single-CTA PCG): 4 launches per LM iteration
   const bool local4 = fused_commit && g->pcg_sparse && g->d.s_nnzb > 0 && g->d.nc > 0 && g->d.np > 0;
-  if (local4) {  // (a per-function attribute: another graph may have lowered it since)
-    if (g->pcg_nact <= kSpSmallCams) GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
-    else GB_CUDA(ctx, cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->pcg_sparse_smem));
-  }
   for (int it = 0; it < g->opt.max_iterations; ++it) {
     if (local4) {
       BaDev& d = g->d;
@@ -2002,6 +2122,11 @@ static int ba_graph_solve_impl(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options*
       else GB_CUDA(ctx, gb_launch_pdl(BA_SPARSE_LARGE, dim3(1), dim3(kSpLargeThreads), g->pcg_sparse_smem, s, d, g->buf, (int)g->opt.pcg_max_iters));
       GB_LAUNCH_CHECK(ctx);
       GB_CUDA(ctx, gb_launch_pdl(ba_backsub_commit_kernel, dim3(gb_div_up(d.np * kLpp, kTailThreads)), dim3(kTailThreads), 0, s, d, (const double*)g->buf)); GB_LAUNCH_CHECK(ctx);
+    } else if (g->pcg_bcsr) {  // large graph: compact block-CSR reduced system + the persistent multi-CTA PCG
+      GB_CHECK(ba_reduce_local_compact(ctx, g, g->rbuf));
+      GB_CHECK(ba_pcg_bcsr_launch(ctx, g, g->rbuf));
+      GB_CHECK(ba_backsub_cost_compact(ctx, g, nullptr));
+      GB_CHECK(ba_commit_compact(ctx, g, g->rbuf, nullptr));
     } else {
     GB_CHECK(gb_ba_graph_reduce_local(ctx, g, nullptr));
     if (fused_commit) {
@@ -2085,7 +2210,7 @@ int gb_ba_solve(gb_ctx* ctx, gb_ba_problem* pb, const gb_ba_options* opt, gb_ba_
   if (!ctx || !pb) return GB_ERR_INVALID;
   CtxLock lk(ctx);
   gb_ba_graph* g = nullptr;
-  GB_CHECK(ba_graph_create_impl(ctx, pb, &g, true));
+  GB_CHECK(ba_graph_create_impl(ctx, pb, &g, true, 0, 1));
   BaTrace tr;
   const int rc = ba_graph_solve_impl(ctx, g, opt, res, g->d.nc > 0 ? pb->cam_pose_wc : nullptr, g->d.np > 0 ? pb->points : nullptr);
   tr.stamp("solve + download (one sync)");
@@ -2110,7 +2235,7 @@ int gb_ba_pnp(gb_ctx* ctx, int n, const double* xyz, const double* xy1, double* 
   pb.cam_pose_wc = pose_wc; pb.cam_dof = &d; pb.points = pts.data(); pb.point_free = pf.data();
   pb.obs_cam = oc.data(); pb.obs_point = op.data(); pb.obs_xyz = xy1; pb.obs_info = nullptr;
   gb_ba_graph* g = nullptr;
-  GB_CHECK(ba_graph_create_impl(ctx, &pb, &g, true));
+  GB_CHECK(ba_graph_create_impl(ctx, &pb, &g, true, 0, 1));
   int rc = ba_graph_solve_impl(ctx, g, opt, res, pose_wc, nullptr);
   if (rc == GB_OK && info6x6) {
     // information of the returned pose: U at the final estimate (re-linearise once; the graph holds the final state)

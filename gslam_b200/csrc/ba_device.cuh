@@ -41,6 +41,9 @@ struct BaDev {
   int s_nupper;
   double* Sb;                            // [s_nnzb][36] block-CSR values of S (local-BA path)
   int s_nnzb;
+  // where [g~ | diag U | cost] start inside the reduced-system buffer handed to a kernel, in doubles: n6*n6 for the dense
+  // layout [S (6N x 6N) | ...], s_nnzb*36 for the compact layout [Sb | ...] of the multi-GPU path (set per launch)
+  size_t r_gt;
   // linearisation
   double *V, *gp, *Vinv, *W, *U, *gc, *cost_pt, *cost_pt_new;
   // camera pass split: cam_split CTAs per camera, partial [27] sums + a per-camera ticket (the last CTA folds them in order)

@@ -1,0 +1,60 @@
+// gslam_b200/csrc/ba_internal.cuh — host-side types and entry points shared by the bundle-adjustment translation units
+// (ba.cu: graph upload, kernels of the sweep / Schur / local PCG paths; ba_pcg_bcsr.cu: the multi-CTA block-CSR PCG of large
+// reduced systems; ba_dist.cu: the landmark-sharded multi-GPU solve and its communicator).  Not part of the C-ABI.
+#pragma once
+#include <vector>
+
+#include "ba_device.cuh"
+#include "common.cuh"
+
+struct gb_ba_graph {
+  BaDev d{};
+  uint8_t* slab = nullptr;  // one device allocation (or the ctx arena) holding everything below
+  size_t slab_bytes = 0;
+  bool from_arena = false;
+  double *pose_init = nullptr, *pts_init = nullptr, *pose_wc_out = nullptr;
+  double* buf = nullptr;     // internal [S | gt | diagU | cost | pad]
+  double* d_cost = nullptr;  // internal candidate cost
+  size_t buf_doubles = 0;
+  gb_ba_options opt{};
+  std::vector<int> sorted_to_orig;  // sorted observation slot -> caller's edge index
+  bool begun = false;
+  // PCG dispatch: single-CTA block-sparse kernel, else one-cluster kernel (pcg_cluster = 8/16), else generic multi-kernel
+  bool pcg_sparse = false;
+  size_t pcg_sparse_smem = 0;
+  int pcg_max_row_blocks = 0;  // longest block row of S
+  bool sweep_only = false;     // the last begin came from gb_ba_graph_sweep and nothing else ran since
+  int pcg_nact = 0;            // cameras with at least one free dof (the sparse PCG kernel gives lanes to these only)
+  int pcg_cluster = 0;
+  size_t pcg_smem = 0;
+  // multi-CTA block-CSR PCG (ba_pcg_bcsr.cu): plan made at graph creation when the block structure exists and the single-CTA
+  // kernel does not apply
+  bool pcg_bcsr = false;
+  int bcsr_ctas = 0, bcsr_K = 0, bcsr_in_smem = 0, bcsr_max_cams = 0, bcsr_max_blocks = 0;
+  size_t bcsr_smem = 0;
+  int* bcsr_cta_cam = nullptr;   // device [bcsr_ctas + 1]: first camera of each CTA's block-row range (base of one allocation)
+  double* bcsr_part = nullptr;   // device [bcsr_ctas * 2]: per-CTA (gamma, delta) partials
+  double* bcsr_u = nullptr;      // device [n6]: the published u = Minv r
+  unsigned int* bcsr_bar = nullptr;  // device: grid barrier counter
+  double* rbuf = nullptr;        // device: compact reduced system [Sb (nnzb*36) | g~ | diag U | cost | pad]
+  size_t rbuf_doubles = 0;
+  // landmark shard (multi-GPU global BA): this graph holds landmarks [shard_lo, shard_hi) of the caller's problem
+  int shard_lo = 0, shard_hi = 0, shard_rank = 0, shard_world = 1;
+};
+
+// ---- ba.cu ------------------------------------------------------------------------------------------------------------------
+// shard_world > 1: keep only the landmarks of `shard_rank` (contiguous range balanced by observation count) and their edges;
+// all cameras and the GLOBAL covisibility block structure are kept, so that every rank's reduced system has the same layout.
+int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out, bool use_arena, int shard_rank, int shard_world);
+// one LM iteration in pieces, on the COMPACT reduced layout rbuf = [Sb | g~ | diag U | cost | pad] (g->rbuf_doubles doubles):
+int ba_reduce_local_compact(gb_ctx* ctx, gb_ba_graph* g, double* rbuf);           // sweep (if needed) + Schur blocks of the shard
+int ba_backsub_cost_compact(gb_ctx* ctx, gb_ba_graph* g, double* d_cost);         // back-substitution + candidate cost of the shard
+int ba_commit_compact(gb_ctx* ctx, gb_ba_graph* g, const double* rbuf, const double* d_cost);  // LM accept / reject + install
+int ba_read_result(gb_ctx* ctx, gb_ba_graph* g, gb_ba_result* res);               // one sync; fills res from the device scalars
+
+// ---- ba_pcg_bcsr.cu ---------------------------------------------------------------------------------------------------------
+// Decide whether / how the multi-CTA block-CSR PCG applies to `g` (fills the bcsr_* fields, allocates its small device buffers).
+int ba_pcg_bcsr_plan(gb_ctx* ctx, gb_ba_graph* g, const int* s_rowptr_host);
+void ba_pcg_bcsr_free(gb_ba_graph* g);
+// damp + block-Jacobi PCG on the reduced camera system held in `rbuf` + retraction of the cameras (pose_new, Rt_new, x)
+int ba_pcg_bcsr_launch(gb_ctx* ctx, gb_ba_graph* g, const double* rbuf);

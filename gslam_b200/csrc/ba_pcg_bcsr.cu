@@ -1,0 +1,340 @@
+// gslam_b200/csrc/ba_pcg_bcsr.cu — block-Jacobi PCG on the reduced camera system of a LARGE bundle adjustment (global BA:
+// hundreds of cameras), kept in covisibility block-CSR, solved by ONE persistent cooperative kernel.
+// Behind GSLAM::Optimizer::optimize(BundleGraph&) (GSLAM/core/Optimizer.h:229); same Chronopoulos-Gear recurrence as the
+// CPU checker (oracle/ba_ref.c::ba_pcg) and as the generic multi-kernel path it replaces (ba.cu: pcg_matvec / pcg_update).
+//
+// Why: at BASELINE config 5 (500 cameras / 100k landmarks / 1M observations) the dense S is 72 MB and one PCG iteration of the
+// generic path is two launches that re-read it from HBM; the covisibility fill is ~20 %, so block-CSR S is ~14 MB -- 97 KB per SM
+// when the block rows are dealt out over the 148 SMs, i.e. it FITS IN SHARED MEMORY for the whole solve.  What remains per
+// iteration is latency: two grid barriers (the inner products; the publication of u = M^-1 r), a 24 KB read of u from L2 and
+// ~12 k DFMA per CTA.  The same kernel runs replicated and bit-identically on every rank of the landmark-sharded solve (the
+// all-reduced compact system is its input), so the ranks take identical LM decisions without any broadcast.
+//
+//   CTA c owns the contiguous block rows (cameras) [cta_cam[c], cta_cam[c+1]) -- balanced by block count on the host.
+//   A local row (camera, component) is worked by K lanes (K = 2^k <= 32, chosen on the host so that rows * K fills the CTA):
+//   lane `sub` takes blocks sub, sub+K, ... of the block row, 6 DFMA each, then a fixed xor tree over the K lanes.
+//   Reductions are fixed-order everywhere (shuffle trees, per-warp partials summed in order, per-CTA partials summed in order by
+//   every CTA): run-to-run and rank-to-rank bit-reproducible.
+#include "ba_internal.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+using namespace ba;
+
+namespace {
+
+constexpr int kBcsrThreads = 512;
+constexpr int kBlkStride = 37;  // doubles per 6x6 block in shared memory (37: the K lanes of a row hit distinct banks)
+
+struct BcsrArgs {
+  const int* cta_cam;   // [G+1]
+  double* part;         // [2G] per-CTA (gamma, delta)
+  double* u_glob;       // [n6]
+  unsigned int* bar;    // grid barrier counter (zeroed before the launch)
+  int K, in_smem, maxit, max_cams, max_blocks;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// All CTAs are co-resident (cooperative launch).  Monotonic ticket barrier: phase t completes when the counter reaches t*G.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& target, unsigned int G) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += G;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (ld_acquire_u32(bar) < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, double* __restrict__ rbuf, BcsrArgs a) {
+  if (g.sc->stop) return;  // uniform over the grid
+  extern __shared__ __align__(16) double sm[];
+  __shared__ double s_warp[2][kBcsrThreads / 32];
+  __shared__ double s_scal[4];  // gamma, delta (this iteration), broadcast
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x, b = blockIdx.x;
+  const int n6 = g.n6;
+  const int cam0 = a.cta_cam[b], cam1 = a.cta_cam[b + 1], ncl = cam1 - cam0, rows = 6 * ncl;
+  const int blk0 = g.s_rowptr[cam0], blk1 = g.s_rowptr[cam1], nb = blk1 - blk0;
+  // ---- shared-memory carve-up (sizes from the host plan: max over CTAs) ----
+  double* u_full = sm;                                         // [n6]
+  double* vec = u_full + ((n6 + 1) & ~1);                      // r, p, s, x, w, u_own : 6 x [6*max_cams]
+  const int vstride = 6 * a.max_cams;
+  double *vr = vec, *vp = vec + vstride, *vs = vec + 2 * vstride, *vx = vec + 3 * vstride, *vw = vec + 4 * vstride, *vu = vec + 5 * vstride;
+  double* Minv = vec + 6 * vstride;                            // [max_cams][36]
+  double* Ssm = Minv + 36 * a.max_cams;                        // [max_blocks][37] when in_smem
+  int* col = reinterpret_cast<int*>(Ssm + (a.in_smem ? (size_t)a.max_blocks * kBlkStride : 0));  // [max_blocks]
+  int* rp = col + a.max_blocks;                                // [max_cams + 1]
+  const size_t r_gt = (size_t)g.s_nnzb * 36;
+  const double lambda = g.sc->lambda, tol = g.sc->pcg_tol;
+
+  // ---- A. block structure + values of the owned block rows ----
+  for (int t = tid; t < nb; t += kBcsrThreads) col[t] = g.s_col[blk0 + t];
+  for (int t = tid; t <= ncl; t += kBcsrThreads) rp[t] = g.s_rowptr[cam0 + t] - blk0;
+  double* Sg = rbuf + (size_t)blk0 * 36;  // the owned blocks in global memory
+  if (a.in_smem) {
+    const int n = nb * 36;
+    for (int t = tid; t < n; t += kBcsrThreads) Ssm[(t / 36) * kBlkStride + (t % 36)] = __ldcg(Sg + t);
+  }
+  __syncthreads();
+  const double* Sp = a.in_smem ? Ssm : Sg;
+  const int bstride = a.in_smem ? kBlkStride : 36;
+  // ---- B. Marquardt damping of the diagonal (fixed dofs: unit diagonal), then the 6x6 block-Jacobi inverses ----
+  for (int r = tid; r < rows; r += kBcsrThreads) {
+    const int c = r / 6, comp = r - 6 * c, cam = cam0 + c;
+    int diag = -1;
+    for (int t = rp[c]; t < rp[c + 1]; ++t)
+      if (col[t] == cam) diag = t;
+    if (diag >= 0) {
+      double* e = (a.in_smem ? Ssm + (size_t)diag * kBlkStride : Sg + (size_t)diag * 36) + comp * 7;
+      const double du = __ldcg(rbuf + r_gt + n6 + 6 * cam + comp);
+      *e = ((g.dof[cam] >> comp) & 1) ? *e + lambda * clampd(du) : 1.0;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < ncl; c += kBcsrThreads) {
+    const int cam = cam0 + c;
+    int diag = rp[c];
+    for (int t = rp[c]; t < rp[c + 1]; ++t)
+      if (col[t] == cam) diag = t;
+    const double* D = Sp + (size_t)diag * bstride;
+    double M[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) M[k] = D[k];
+    if (!spd_inverse<6>(M)) {
+#pragma unroll
+      for (int k = 0; k < 36; ++k) M[k] = (k % 7 == 0) ? 1.0 / D[k] : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < 36; ++k) Minv[36 * c + k] = M[k];
+  }
+  for (int r = tid; r < rows; r += kBcsrThreads) {
+    vr[r] = __ldcg(rbuf + r_gt + 6 * cam0 + r);
+    vp[r] = 0.0; vs[r] = 0.0; vx[r] = 0.0;
+  }
+  __syncthreads();
+  // u = Minv r for the owned rows, published for everybody
+  auto apply_minv_publish = [&]() {
+    for (int r = tid; r < rows; r += kBcsrThreads) {
+      const int c = r / 6, comp = r - 6 * c;
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s += Minv[36 * c + comp * 6 + k] * vr[6 * c + k];
+      vu[r] = s;
+      a.u_glob[6 * cam0 + r] = s;
+    }
+  };
+  apply_minv_publish();
+  unsigned int target = 0;
+  grid_barrier(a.bar, target, G);
+
+  const int K = a.K, sub = tid & (K - 1), groups = kBcsrThreads / K;
+  double gamma_prev = 0.0, gamma0 = 0.0, alpha_prev = 1.0;
+  int k_it = 0;
+  bool first = true;
+  for (;;) {
+    // ---- C. w = S u on the owned rows ----
+    for (int t = tid; t < n6; t += kBcsrThreads) u_full[t] = __ldcg(a.u_glob + t);
+    __syncthreads();
+    double pg = 0.0, pd = 0.0;
+    for (int rbase = 0; rbase < rows; rbase += groups) {  // (uniform trip count: whole groups of K lanes share a row)
+      const int r = rbase + tid / K;
+      double acc = 0.0;
+      if (r < rows) {
+        const int c = r / 6, comp = r - 6 * c;
+        for (int t = rp[c] + sub; t < rp[c + 1]; t += K) {
+          const double* row = Sp + (size_t)t * bstride + comp * 6;
+          const double* uc = u_full + 6 * col[t];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) acc += row[q] * uc[q];
+        }
+      }
+      for (int o = K >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (r < rows && sub == 0) {
+        vw[r] = acc;
+        pg += vr[r] * vu[r];
+        pd += acc * vu[r];
+      }
+    }
+    // ---- D. (gamma, delta): fixed tree inside the CTA, per-CTA partials folded in CTA order by everybody ----
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      pg += __shfl_down_sync(0xffffffffu, pg, o);
+      pd += __shfl_down_sync(0xffffffffu, pd, o);
+    }
+    if (lane == 0) { s_warp[0][warp] = pg; s_warp[1][warp] = pd; }
+    __syncthreads();
+    if (tid == 0) {
+      double sg = 0.0, sd = 0.0;
+#pragma unroll
+      for (int w = 0; w < kBcsrThreads / 32; ++w) { sg += s_warp[0][w]; sd += s_warp[1][w]; }
+      a.part[2 * b] = sg;
+      a.part[2 * b + 1] = sd;
+    }
+    grid_barrier(a.bar, target, G);
+    if (warp == 0) {
+      double sg = 0.0, sd = 0.0;
+      for (int c = lane; c < G; c += 32) { sg += __ldcg(a.part + 2 * c); sd += __ldcg(a.part + 2 * c + 1); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sg += __shfl_down_sync(0xffffffffu, sg, o);
+        sd += __shfl_down_sync(0xffffffffu, sd, o);
+      }
+      if (lane == 0) { s_scal[0] = sg; s_scal[1] = sd; }
+    }
+    __syncthreads();
+    const double gn = s_scal[0], dl = s_scal[1];
+    double alpha, beta;
+    if (first) {
+      gamma0 = gn;
+      if (!(gn > 0.0) || !(dl > 0.0)) break;
+      alpha = gn / dl;
+      beta = 0.0;
+    } else {
+      if (!(gn > 0.0) || gn < tol * tol * gamma0) break;  // convergence test of the previous update
+      beta = gn / gamma_prev;
+      const double den = dl - beta * gn / alpha_prev;
+      if (!(den > 0.0)) break;
+      alpha = gn / den;
+    }
+    if (k_it >= a.maxit) break;
+    // ---- E. element-wise recurrences on the owned rows, u = Minv r, publish ----
+    for (int r = tid; r < rows; r += kBcsrThreads) {
+      const double pn = vu[r] + beta * vp[r];
+      const double sn = vw[r] + beta * vs[r];
+      vp[r] = pn;
+      vs[r] = sn;
+      vx[r] += alpha * pn;
+      vr[r] -= alpha * sn;
+    }
+    __syncthreads();
+    apply_minv_publish();
+    gamma_prev = gn; alpha_prev = alpha; first = false; ++k_it;
+    grid_barrier(a.bar, target, G);
+  }
+  // ---- F. solution + retraction of the owned cameras ----
+  for (int r = tid; r < rows; r += kBcsrThreads) g.x[6 * cam0 + r] = vx[r];
+  for (int c = tid; c < ncl; c += kBcsrThreads) {
+    const int i = cam0 + c, dm = g.dof[i];
+    double pose[7], d[6], out[7], R[9];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) pose[k] = g.pose[7 * i + k];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) d[q] = ((dm >> q) & 1) ? vx[6 * c + q] : 0.0;
+    se3_retract(pose, d, out);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) g.pose_new[7 * i + k] = out[k];
+    quat_to_R(out, R);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g.Rt_new[12 * i + k] = R[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) g.Rt_new[12 * i + 9 + k] = out[4 + k];
+  }
+  if (b == 0 && tid == 0) g.sc->pcg_iters += k_it;
+}
+
+size_t bcsr_smem_bytes(int n6, int max_cams, int max_blocks, bool in_smem) {
+  size_t d = (size_t)((n6 + 1) & ~1) + 6 * (size_t)6 * max_cams + 36 * (size_t)max_cams + (in_smem ? (size_t)max_blocks * kBlkStride : 0);
+  return d * sizeof(double) + ((size_t)max_blocks + max_cams + 1) * sizeof(int) + 64;
+}
+
+}  // namespace
+
+int ba_pcg_bcsr_plan(gb_ctx* ctx, gb_ba_graph* g, const int* s_rowptr) {
+  g->pcg_bcsr = false;
+  const int nc = g->d.nc, nnzb = g->d.s_nnzb, n6 = g->d.n6;
+  if (nc <= 0 || nnzb <= 0) return GB_OK;
+  {  // the shared-memory limit of a kernel is per-device state: raise it once per device, never lower it
+    static std::mutex mu;
+    static int state[64] = {0};
+    std::lock_guard<std::mutex> lk(mu);
+    const int dev = ctx->device;
+    if (dev < 0 || dev >= 64) return GB_OK;
+    if (state[dev] == 0) {
+      state[dev] = cudaFuncSetAttribute(ba_pcg_bcsr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin) == cudaSuccess ? 1 : 2;
+      cudaGetLastError();
+    }
+    if (state[dev] != 1) return GB_OK;
+  }
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+  if (!coop) return GB_OK;
+  // contiguous camera ranges balanced by block count; at most one CTA per SM (the kernel is launched cooperatively)
+  const int G = std::max(1, std::min(ctx->sm_count, nc));
+  std::vector<int> cta_cam(G + 1, nc);
+  cta_cam[0] = 0;
+  {
+    int cam = 0;
+    for (int c = 0; c < G; ++c) {
+      cta_cam[c] = cam;
+      const long long want = (long long)nnzb * (c + 1) / G;  // block count that should be covered after this CTA
+      const int left_ctas = G - 1 - c;
+      while (cam < nc - left_ctas && (s_rowptr[cam + 1] <= want || cam == cta_cam[c])) ++cam;  // at least one camera each
+    }
+    cta_cam[G] = nc;
+  }
+  int max_cams = 1, max_blocks = 1;
+  for (int c = 0; c < G; ++c) {
+    max_cams = std::max(max_cams, cta_cam[c + 1] - cta_cam[c]);
+    max_blocks = std::max(max_blocks, s_rowptr[cta_cam[c + 1]] - s_rowptr[cta_cam[c]]);
+  }
+  bool in_smem = true;
+  size_t smem = bcsr_smem_bytes(n6, max_cams, max_blocks, true);
+  if (smem > (size_t)ctx->max_smem_optin) {
+    in_smem = false;
+    smem = bcsr_smem_bytes(n6, max_cams, max_blocks, false);
+    if (smem > (size_t)ctx->max_smem_optin) return GB_OK;  // not even the vectors fit: generic path
+  }
+  int K = 32;
+  while (K > 1 && 6 * max_cams * K > kBcsrThreads) K >>= 1;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_pcg_bcsr_kernel, kBcsrThreads, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return GB_OK;
+  }
+  if ((long long)per_sm * ctx->sm_count < G) return GB_OK;
+  const size_t bytes = (size_t)(G + 1) * 4 + 256 + (size_t)2 * G * 8 + 256 + (size_t)n6 * 8 + 256 + 256;
+  uint8_t* base = nullptr;
+  GB_CUDA(ctx, cudaMalloc((void**)&base, bytes));
+  size_t off = 0;
+  auto take = [&](size_t n) { uint8_t* p = base + off; off = (off + n + 255) & ~(size_t)255; return p; };
+  g->bcsr_cta_cam = (int*)take((size_t)(G + 1) * 4);
+  g->bcsr_part = (double*)take((size_t)2 * G * 8);
+  g->bcsr_u = (double*)take((size_t)n6 * 8);
+  g->bcsr_bar = (unsigned int*)take(64);
+  GB_CUDA(ctx, cudaMemcpyAsync(g->bcsr_cta_cam, cta_cam.data(), (size_t)(G + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // (cta_cam is a stack-lifetime host vector)
+  g->bcsr_ctas = G; g->bcsr_K = K; g->bcsr_in_smem = in_smem ? 1 : 0; g->bcsr_smem = smem;
+  g->bcsr_max_cams = max_cams; g->bcsr_max_blocks = max_blocks;
+  g->pcg_bcsr = true;
+  return GB_OK;
+}
+
+void ba_pcg_bcsr_free(gb_ba_graph* g) {
+  if (g->bcsr_cta_cam) cudaFree(g->bcsr_cta_cam);  // (one allocation: cta_cam is its base)
+  g->bcsr_cta_cam = nullptr; g->bcsr_part = nullptr; g->bcsr_u = nullptr; g->bcsr_bar = nullptr;
+  g->pcg_bcsr = false;
+}
+
+int ba_pcg_bcsr_launch(gb_ctx* ctx, gb_ba_graph* g, const double* rbuf) {
+  if (!ctx || !g || !g->pcg_bcsr || !rbuf) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  BaDev d = g->d;
+  d.r_gt = (size_t)d.s_nnzb * 36;
+  BcsrArgs a;
+  a.cta_cam = g->bcsr_cta_cam; a.part = g->bcsr_part; a.u_glob = g->bcsr_u; a.bar = g->bcsr_bar;
+  a.K = g->bcsr_K; a.in_smem = g->bcsr_in_smem; a.maxit = g->opt.pcg_max_iters; a.max_cams = g->bcsr_max_cams; a.max_blocks = g->bcsr_max_blocks;
+  GB_CUDA(ctx, cudaMemsetAsync(g->bcsr_bar, 0, 4, ctx->stream));
+  double* rb = const_cast<double*>(rbuf);  // (the damped diagonal is written back when S stays in global memory)
+  void* args[3] = {(void*)&d, (void*)&rb, (void*)&a};
+  GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)ba_pcg_bcsr_kernel, dim3(g->bcsr_ctas), dim3(kBcsrThreads), args, g->bcsr_smem, ctx->stream));
+  GB_LAUNCH_CHECK(ctx);
+  return GB_OK;
+}

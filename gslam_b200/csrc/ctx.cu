@@ -89,13 +89,22 @@ int gb_ctx_create(int device, gb_ctx** out) {
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->eve);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  auto drop = [&]() {  // whatever was created before the failure
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->evs) cudaEventDestroy(ctx->evs);
+    if (ctx->eve) cudaEventDestroy(ctx->eve);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    delete ctx;
+  };
   if (e != cudaSuccess) {
     gb_set_error(nullptr, "gb_ctx_create(device %d) -> %s", device, cudaGetErrorString(e));
-    delete ctx;
+    drop();
     return GB_ERR_CUDA;
   }
   if (gb_stage_reserve(ctx, 8u << 20) != GB_OK) {
-    delete ctx;
+    drop();
     return GB_ERR_CUDA;
   }
   *out = ctx;

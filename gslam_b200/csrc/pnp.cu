@@ -317,6 +317,10 @@ int gb_pnp_ransac(gb_ctx* ctx, int n, const double* xyz, const double* xy, doubl
   if (stats) *stats = st;
   if (!ctx || n < 4 || !xyz || !xy || !pose_cw || max_hypotheses < 1 || max_hypotheses > (1 << 20)) return GB_ERR_INVALID;
   CtxLock lk(ctx);
+  if (!(threshold > 0.0) || !std::isfinite(threshold) || !(confidence > 0.0) || !(confidence < 1.0)) {  // (NaN fails every comparison)
+    gb_set_error(ctx, "gb_pnp_ransac: threshold must be > 0 and confidence in (0,1) (got %g, %g)", threshold, confidence);
+    return GB_ERR_INVALID;
+  }
   const double thr2 = threshold * threshold;
   const int H = max_hypotheses;
   // device buffers: points, measurements, per-hypothesis results (grow-only scratch owned by the ctx)

@@ -1,5 +1,5 @@
-"""PENDING (move to tests/ once tools/gpu_pnp_check.py has been seen green on a B200, ideally after one compute-sanitizer pass):
-GPU parity of gb_pnp_ransac and of Estimator::findPnP through the reference API against oracle/pnp_ref.c.
+"""GPU parity of gb_pnp_ransac and of Estimator::findPnP through the reference API against oracle/pnp_ref.c (first seen green on a
+B200 in round 2: tools/gpu_pnp_check.py, 30/30 cases, profiles/r02_pnp_check.log).
 
 Bar: same number of counted hypotheses, same winning hypothesis and root, identical inlier mask, pose within 1e-7 (the refinement is an LM solve on both sides: agreement at its convergence level; the minimal
 solver runs in fp64 on both sides with contraction disabled; only libm-vs-CUDA-math ulp differences in acos/cos/cbrt can move a
