@@ -3,18 +3,31 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A step is one frame through the whole hot path: ORB extract (2000 kp) of a NEW 1080p frame, 256-bit Hamming match against
-the previous frame's descriptors, and one local bundle adjustment (50 keyframes / 2000 landmarks / 10 000 observations,
-10 LM iterations, 50-iteration block-Jacobi PCG cap).  `value` is measured with every input already resident in HBM
-(a ring of frames larger than L2); `e2e` goes through the C-ABI host-buffer entry points (pinned host frame in, keypoints
-/ descriptors / matches / poses out, H2D + D2H inside the timed region).  N>1: independent replicas, one rank per GPU
-(frames and windows shard with no data-path collective) -> weak scaling.
+A step is one frame through the whole hot path: ORB extract (2000 kp) of a NEW 1080p frame, 256-bit Hamming match against the
+previous frame's descriptors, and one local bundle adjustment (50 keyframes / 2000 landmarks / 10 000 observations, 10 LM
+iterations, 50-iteration block-Jacobi PCG cap).
+
+  value        every input already resident in HBM (a ring of frames larger than L2), device time (CUDA events), the two stages
+               of a SLAM front/back end PIPELINED on one GPU exactly as their data dependencies allow: the tracking ctx
+               (extract + match) and the mapping ctx (local BA) are two streams; BA(k) waits for match(k), extract(k+1) does not
+               wait for BA(k).  `serial` holds the same K steps on ONE stream (round 1's definition).
+  e2e          the same pipeline through the C-ABI host-buffer entry points from two host threads (tracking / mapping) with
+               PAGEABLE host frames (GImage memory is malloc'd, GImage.h:394-402): H2D + D2H inside the timed region.
+  roofline     the BA Jacobian sweep at config-5 size (the BASELINE metric's second clause), outside the timed step.
+  global_ba    BASELINE config 5 (500 cams / 100k landmarks / 1M obs), landmark-sharded over the N ranks with one NCCL
+               all-reduce of the compact reduced camera system per LM iteration -- STRONG scaling (total work fixed).
+N>1 for the per-frame path: independent replicas, one rank per GPU, no data-path collective -> weak scaling.
+
+The timed block of K steps is repeated (each repetition bracketed by barrier + synchronize, max over ranks) and the MEDIAN block is
+reported, so that a 20-step run is not a 24 ms coin flip; the clock sampler starts before the warm-up.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
+import queue
 import subprocess
 import sys
 import threading
@@ -28,6 +41,8 @@ sys.path.insert(0, ROOT)
 W, H, NKP = 1920, 1080, 2000
 BA_CAMS, BA_PTS, BA_OBS_PER_PT, BA_ITERS, PCG_ITERS = 50, 2000, 5, 10, 50
 RING = 72  # frames resident in HBM: 72 * 2.07 MB = 149 MB > 126 MB L2
+GBA_CAMS, GBA_PTS, GBA_OBS_PER_PT, GBA_ITERS, GBA_PCG = 500, 100000, 10, 5, 30
+METRIC = "frames/sec detect+match+local-BA @1920x1080 mono"
 
 
 def level_sizes(w, h, nlevels=8, sf=1.2):
@@ -50,6 +65,14 @@ def algorithmic_bytes():
     return dict(extract=b_ext, match=b_match, ba_sweep=b_ba)
 
 
+def workload_config(world):
+    """The `config` object: identical keys in both arms (the driver compares them)."""
+    return {"workload": (f"{W}x{H} mono, {NKP} kp ORB extract + {NKP}x{NKP} Hamming match + local BA "
+                         f"({BA_CAMS} KF/{BA_PTS} pts/{BA_PTS * BA_OBS_PER_PT} obs, {BA_ITERS} LM it, PCG cap {PCG_ITERS})"),
+            "l2": f"input ring of {RING} frames ({RING * W * H / 1e6:.0f} MB) > 126 MB L2",
+            "parallelism": f"replicas x{world}; tracking (extract+match) and mapping (local BA) pipelined"}
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
@@ -57,19 +80,24 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.stop_flag = False
         self.proc = None
+        self.t_mark = None
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
-                self.samples.append([x.strip() for x in line.split(",")])
+                self.samples.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
         except Exception:
             pass
+
+    def mark(self):
+        """Samples from here on belong to the timed region."""
+        self.t_mark = time.perf_counter()
 
     def finish(self):
         self.stop_flag = True
@@ -79,7 +107,9 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
         sm, mx, reasons = [], 0, set()
-        for s in self.samples:
+        for t, s in self.samples:
+            if self.t_mark is not None and t < self.t_mark:
+                continue
             try:
                 sm.append(float(s[0])); mx = max(mx, float(s[1]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
@@ -88,12 +118,14 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "samples_total": len(self.samples)}
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU path, organised the way a CPU SLAM runs it -- a tracking thread (OpenCV ORB + BFMatcher, all
+# cores inside OpenCV) and a mapping thread (local BA) working concurrently, frame k+1's tracking overlapping window k's BA.
+# ---------------------------------------------------------------------------------------------------------------------------
 def cpu_path(frames, ba_problem, steps, threads):
-    """The CPU arm: OpenCV ORB + BFMatcher (the reference's external CPU dependency, when importable; else the oracle
-    restatement) + the oracle's ba_ref.  Returns (frames_per_s, description)."""
     import oracle
     try:
         import cv2
@@ -108,24 +140,39 @@ def cpu_path(frames, ba_problem, steps, threads):
             return bf.match(a, b)
         what = f"cv2 {cv2.__version__} ORB+BFMatcher ({threads} threads)"
     except Exception:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
-
         def extract(img):
             return oracle.orb_extract(img, NKP)[1]
 
         def match(a, b):
             return oracle.match_hamming(a, b)
-        what = f"oracle orb_ref+hamming_ref (OpenMP {threads} threads)"
+        what = "oracle orb_ref+hamming_ref (1 thread)"
     prev = extract(frames[0])
+    q: queue.Queue = queue.Queue(maxsize=2)
+
+    def mapper():
+        while True:
+            k = q.get()
+            if k is None:
+                return
+            pb = ba_problem.copy()
+            oracle.ba_solve(pb, max_iterations=BA_ITERS, function_tolerance=0.0, pcg_max_iters=PCG_ITERS, pcg_tol=1e-10)
+
+    th = threading.Thread(target=mapper, daemon=True)
     t0 = time.perf_counter()
+    th.start()
     for k in range(steps):
         d = extract(frames[(k + 1) % len(frames)])
         match(d, prev)
         prev = d
-        pb = ba_problem.copy()
-        oracle.ba_solve(pb, max_iterations=BA_ITERS, function_tolerance=0.0, pcg_max_iters=PCG_ITERS, pcg_tol=1e-10)
+        q.put(k)
+    q.put(None)
+    th.join()
     dt = time.perf_counter() - t0
-    return steps / dt, what + " + oracle ba_ref (1 thread)"
+    return steps / dt, what + " on the tracking thread || oracle ba_ref (1 thread) on the mapping thread"
+
+
+def median(xs):
+    return float(np.median(np.asarray(xs, dtype=np.float64)))
 
 
 def main():
@@ -134,27 +181,27 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-global-ba", action="store_true", help="skip the config-5 global BA section")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     from gslam_b200 import synth
     ba_problem = synth.synth_ba(BA_CAMS, BA_PTS, BA_OBS_PER_PT, seed=42, n_fixed=2)
     cores = os.cpu_count() or 1
-    workload = (f"{W}x{H} mono, {NKP} kp ORB extract + {NKP}x{NKP} Hamming match + local BA "
-                f"({BA_CAMS} KF/{BA_PTS} pts/{BA_PTS * BA_OBS_PER_PT} obs, {BA_ITERS} LM it, PCG cap {PCG_ITERS})")
 
     if args.impl == "reference":
         if rank != 0:
             return
         steps = max(1, min(args.steps, 20))
+        warm = max(1, min(args.warmup, 3))
         frames = synth.synth_stream(W, H, 4, seed=7)
-        for _ in range(max(1, min(args.warmup, 2))):
-            cpu_path(frames, ba_problem, 1, cores)
+        cpu_path(frames, ba_problem, warm, cores)
         fps, what = cpu_path(frames, ba_problem, steps, cores)
-        line = {"impl": "reference", "metric": "frames/sec detect+match+local-BA @1920x1080 mono", "value": fps, "unit": "frames/s",
-                "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 / fps,
+        line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / fps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
-                "config": {"workload": workload},
-                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": f"{steps} frames: {what}"},
+                "config": workload_config(world),
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                 "sample": f"{steps} frames after {warm} warm-up (bounded sample of the --steps/--warmup asked): {what}"},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -165,9 +212,23 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from gslam_b200.api import BAGraph, Context, Features, OptimzeConfig
-    ctx = Context(local)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()  # before the warm-up: nvidia-smi needs a few hundred ms to deliver its first sample
+    ctx = Context(local)    # tracking: extract + match
+    ctx_m = Context(local)  # mapping: local BA
     cfg = ctx.orb_cfg(nfeatures=NKP)
     ba_cfg = OptimzeConfig(maxIterations=BA_ITERS, functionTolerance=0.0, pcgMaxIterations=PCG_ITERS, pcgTolerance=1e-10)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+        return x
 
     # ---- device-resident inputs: a ring of distinct frames larger than L2 ----------------------------------------------
     base = synth.synth_stream(W, H, 8, seed=7 + rank)
@@ -175,86 +236,192 @@ def main():
     for k in range(RING):  # distinct content per slot: shifted copies of 8 generated frames (cheap, still cold in L2)
         ring[k] = torch.from_numpy(np.roll(base[k % 8], shift=(k // 8) * 7, axis=1)).cuda()
     feats = [Features(ctx, 2 * NKP + 256), Features(ctx, 2 * NKP + 256)]
-    graph = BAGraph(ctx, ba_problem)
+    graph_s = BAGraph(ctx, ba_problem)    # serial mode: BA on the tracking stream
+    graph_p = BAGraph(ctx_m, ba_problem)  # pipelined mode: BA on the mapping stream
     torch.cuda.synchronize()
 
-    def step_device(k):
+    def track(k):
         f, fp = feats[k & 1], feats[(k + 1) & 1]
         f.extract(ring[k % RING].data_ptr(), W, H, cfg, device_ptr=True, pitch=W)
         f.match(fp)
-        graph.reset()
-        graph.solve(ba_cfg)
+
+    def step_serial(k):
+        track(k)
+        graph_s.reset()
+        graph_s.solve(ba_cfg)
+
+    def run_serial(k0, n):
+        for k in range(k0, k0 + n):
+            step_serial(k)
+
+    def run_pipelined(k0, n):
+        """n frames; BA(k) waits for match(k); extract(k+1) is enqueued before the host blocks in solve(k)."""
+        track(k0)
+        for k in range(k0, k0 + n):
+            ctx_m.wait_for(ctx)          # BA(k) after match(k)
+            if k + 1 < k0 + n:
+                track(k + 1)             # overlaps BA(k) on the device
+            graph_p.reset()
+            graph_p.solve(ba_cfg)        # (one host synchronisation per window: the LM scalars come back with it)
+        ctx.wait_for(ctx_m)              # the timing events live on the tracking stream
+
+    def timed_blocks(run, steps):
+        """Repeat [barrier, K steps, barrier] and return the per-block ms (max over ranks each) and the launch count of a block."""
+        blocks, out, launches = None, [], 0
+        k0 = args.warmup
+        b = 0
+        while True:
+            barrier()
+            l0 = ctx.launch_count() + ctx_m.launch_count()
+            ctx.timer_begin()
+            run(k0, steps)
+            ms = ctx.timer_end()
+            torch.cuda.synchronize()
+            launches = ctx.launch_count() + ctx_m.launch_count() - l0
+            out.append(max_over_ranks(ms))
+            k0 += steps
+            b += 1
+            if blocks is None:  # enough repetitions for >= ~0.7 s of timed work and at least 5 blocks (every rank agrees: max'd time)
+                blocks = int(min(60, max(5, math.ceil(700.0 / max(out[0], 1e-3)))))
+            if b >= blocks:
+                return out, launches
 
     feats[1].extract(ring[RING - 1].data_ptr(), W, H, cfg, device_ptr=True, pitch=W)
-    for k in range(args.warmup):
-        step_device(k)
-    ctx.sync()
-    sampler = ClockSampler(local) if rank == 0 else None
+    run_serial(0, max(3, args.warmup))
+    run_pipelined(0, max(3, args.warmup))
+    ctx.sync(); ctx_m.sync()
     if sampler:
-        sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    l0 = ctx.launch_count()
-    ctx.timer_begin()
-    for k in range(args.steps):
-        step_device(args.warmup + k)
-    ms = ctx.timer_end()
-    torch.cuda.synchronize()
-    launches = ctx.launch_count() - l0
-    if world > 1:
-        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-        dist.barrier()
+        sampler.mark()
+    ser_ms, ser_launches = timed_blocks(run_serial, args.steps)
+    pip_ms, pip_launches = timed_blocks(run_pipelined, args.steps)
     clocks = sampler.finish() if sampler else None
+    ms_serial, ms_pipe = median(ser_ms), median(pip_ms)
 
     # ---- per-stage device timing (CUDA events on the ctx stream) ------------------------------------------------------------
-    def time_stage(fn, reps):
-        fn(); ctx.sync()
-        ctx.timer_begin()
+    def time_stage(fn, reps, c=ctx):
+        fn(); c.sync()
+        c.timer_begin()
         for r in range(reps):
             fn(r)
-        return ctx.timer_end() / reps
+        return c.timer_end() / reps
     reps = 50
     t_ext = time_stage(lambda r=0: feats[0].extract(ring[(r * 7 + 3) % RING].data_ptr(), W, H, cfg, device_ptr=True, pitch=W), reps)
     t_match = time_stage(lambda r=0: feats[0].match(feats[1]), reps)
+
     def ba_once(r=0):
-        graph.reset(); graph.solve(ba_cfg)
+        graph_s.reset(); graph_s.solve(ba_cfg)
     t_ba = time_stage(ba_once, 10)
-    t_sweep_local = time_stage(lambda r=0: graph.sweep(0.01), 50)
+    t_sweep_local = time_stage(lambda r=0: graph_s.sweep(0.01), 50)
+    popc_peak = ctx.popc_peak() if rank == 0 else None
     # the BASELINE metric's second clause, "BA Jacobian-eval HBM GB/s": the fused residual+Jacobian sweep (K6a+K6b) on the
     # config-5-shaped graph (500 cams / 100k landmarks / 1M observations: 177.7 MB algorithmic per sweep > L2, so every
-    # repetition is cold).  Rank 0 only.
+    # repetition is cold).  Rank 0 only.  NOT part of the timed step.
+    gba_problem = None
+    if rank == 0 or not args.no_global_ba:
+        gba_problem = synth.synth_ba(GBA_CAMS, GBA_PTS, GBA_OBS_PER_PT, seed=42, n_fixed=2)
     t_sweep_big, big_bytes = None, None
     if rank == 0:
-        big = synth.synth_ba(500, 100000, 10, seed=42, n_fixed=2)
-        gbig = BAGraph(ctx, big)
+        gbig = BAGraph(ctx, gba_problem)
         t_sweep_big = time_stage(lambda r=0: gbig.sweep(0.01), 20)
-        big_bytes = 168 * big.n_obs + 96 * big.n_points + 272 * big.n_cams
+        big_bytes = 168 * gba_problem.n_obs + 96 * gba_problem.n_points + 272 * gba_problem.n_cams
         gbig.close()
-        del big
 
-    # ---- end to end through the host-buffer C-ABI ------------------------------------------------------------------------
-    host_frames = [torch.from_numpy(base[k]).pin_memory() for k in range(8)]
-    hf = [x.numpy() for x in host_frames]
-    e2e_steps = max(10, args.steps // 4)
-    prev_desc = ctx.orb_extract(hf[0], NKP)[1]
-    def step_host(k):
-        nonlocal prev_desc
-        kps, desc = ctx.orb_extract(hf[(k + 1) % 8], NKP)
-        ctx.match_hamming(desc, prev_desc)
-        prev_desc = desc
-        pb = ba_problem.copy()
-        ctx.ba_solve(pb, ba_cfg)
-    for k in range(3):
-        step_host(k)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        step_host(k)
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    # ---- global BA, config 5, landmark-sharded over the ranks (strong scaling) ---------------------------------------------------
+    global_ba = None
+    if not args.no_global_ba:
+        from gslam_b200.dist import DistributedBA
+        gcfg = OptimzeConfig(maxIterations=GBA_ITERS, functionTolerance=0.0, pcgMaxIterations=GBA_PCG)
+        t_setup = time.perf_counter()
+        dba = DistributedBA(ctx, gba_problem, rank, world)
+        t_setup = time.perf_counter() - t_setup
+        times, res = [], None
+        for rep in range(4):  # rep 0 warms up (NCCL channels, first launches)
+            dba.graph.reset()
+            barrier()
+            ctx.timer_begin()
+            res = dba.solve(gcfg)
+            ms = max_over_ranks(ctx.timer_end())
+            if rep > 0:
+                times.append(ms)
+        global_ba = {"workload": f"{GBA_CAMS} cams / {GBA_PTS} landmarks / {gba_problem.n_obs} obs, {GBA_ITERS} LM it, PCG cap {GBA_PCG}",
+                     "nranks": world, "ms_per_lm_iteration": median(times) / GBA_ITERS, "ms_total": median(times),
+                     "allreduce_bytes": dba.reduce_bytes + 8, "cost": res.final_cost, "initial_cost": res.initial_cost,
+                     "accepted": res.accepted, "pcg_iterations": res.pcg_iterations, "scaling": "strong",
+                     "host_setup_ms": t_setup * 1e3,
+                     "collective": "NCCL all-reduce (f64 sum) of the compact block-CSR reduced camera system, under the C-ABI"}
+        dba.close()
+        if world > 1 and rank == 0:  # the same solve on rank 0's GPU alone: the strong-scaling denominator + the parity of the sharding
+            d1 = DistributedBA(ctx, gba_problem, 0, 1)
+            t1 = []
+            for rep in range(3):
+                d1.graph.reset(); ctx.sync()
+                ctx.timer_begin(); r1 = d1.solve(gcfg); t1.append(ctx.timer_end())
+            d1.close()
+            rel = abs(res.final_cost - r1.final_cost) / abs(r1.final_cost)
+            global_ba.update({"ms_per_lm_iteration_n1": median(t1[1:]) / GBA_ITERS, "cost_n1": r1.final_cost, "cost_rel_diff_vs_n1": rel,
+                              "cost_agrees_1e-12": bool(rel < 1e-12)})
+        if world > 1:
+            dist.barrier()
+    del gba_problem
+
+    # ---- end to end through the host-buffer C-ABI, PAGEABLE frames, tracking thread || mapping thread ---------------------------
+    pageable = [np.array(base[k], copy=True) for k in range(8)]           # malloc'd, like GImage (GImage.h:394-402)
+    pinned_t = [torch.from_numpy(base[k]).pin_memory() for k in range(8)]
+    pinned = [x.numpy() for x in pinned_t]
+    e2e_steps = max(10, min(args.steps, 100))
+
+    def e2e_serial(frames_h, n):
+        prev = ctx.orb_extract(frames_h[0], NKP)[1]
+        t0 = time.perf_counter()
+        for k in range(n):
+            kps, desc = ctx.orb_extract(frames_h[(k + 1) % 8], NKP)
+            ctx.match_hamming(desc, prev)
+            prev = desc
+            pb = ba_problem.copy()
+            ctx.ba_solve(pb, ba_cfg)
+        return time.perf_counter() - t0
+
+    def e2e_pipelined(frames_h, n):
+        prev = ctx.orb_extract(frames_h[0], NKP)[1]
+        qq: queue.Queue = queue.Queue(maxsize=2)
+        err = []
+
+        def mapper():
+            try:
+                while True:
+                    k = qq.get()
+                    if k is None:
+                        return
+                    pb = ba_problem.copy()
+                    ctx_m.ba_solve(pb, ba_cfg)
+            except Exception as e:  # surfaced after the join
+                err.append(e)
+        th = threading.Thread(target=mapper, daemon=True)
+        t0 = time.perf_counter()
+        th.start()
+        for k in range(n):
+            kps, desc = ctx.orb_extract(frames_h[(k + 1) % 8], NKP)
+            ctx.match_hamming(desc, prev)
+            prev = desc
+            qq.put(k)
+        qq.put(None)
+        th.join()
+        if err:
+            raise err[0]
+        return time.perf_counter() - t0
+
+    def e2e_measure(fn, frames_h):
+        fn(frames_h, 3)
+        ts = []
+        for rep in range(3):
+            if world > 1:
+                dist.barrier()
+            ts.append(max_over_ranks(fn(frames_h, e2e_steps)))
+        return world * e2e_steps / median(ts)
+    e2e_pipe_pageable = e2e_measure(e2e_pipelined, pageable)
+    e2e_pipe_pinned = e2e_measure(e2e_pipelined, pinned)
+    e2e_serial_pageable = e2e_measure(e2e_serial, pageable)
+    e2e_serial_pinned = e2e_measure(e2e_serial, pinned)
     h2d = W * H + 2 * NKP * 32 + ba_problem.n_cams * 57 + ba_problem.n_points * 25 + ba_problem.n_obs * (8 + 24)
     d2h = NKP * 60 + NKP * 12 + ba_problem.n_cams * 56 + ba_problem.n_points * 24
 
@@ -263,29 +430,42 @@ def main():
         dist.destroy_process_group()
     if rank != 0:
         return
-    fps = world * args.steps / (ms * 1e-3)
+    fps = world * args.steps / (ms_pipe * 1e-3)
     ab = algorithmic_bytes()
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     except Exception:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
     def gbs(nbytes, ms_):
         return nbytes / (ms_ * 1e-3) / 1e9
     ach = gbs(big_bytes, t_sweep_big)
-    line = {"metric": "frames/sec detect+match+local-BA @1920x1080 mono", "value": fps, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+    traffic = None
+    try:  # per-launch DRAM bytes of the sweep from the committed ncu capture of this round (profiles/r02_sweep_traffic.json)
+        traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r02_sweep_traffic.json")))["dram_bytes_per_launch"])
+        traffic_src = "profiles/r02_sweep_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full)"
+    except Exception:
+        traffic, traffic_src = 150.6e6, "profiles/r01_ncu_summary.md (44.25 MB read + 106.36 MB written, one launch, ncu --set full; round-1 kernel)"
+    line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_pipe / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8+f64", "data": "synthetic",
-            "config": {"workload": workload, "l2": f"input ring of {RING} frames ({RING * W * H / 1e6:.0f} MB) > 126 MB L2",
-                       "parallelism": f"replicas x{world}"},
-            "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": world * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps},
+            "config": workload_config(world),
+            "timing": {"blocks": len(pip_ms), "block_ms_median": ms_pipe, "block_ms_min": min(pip_ms), "block_ms_max": max(pip_ms),
+                       "rule": "each block = exactly --steps steps between barrier+synchronize, CUDA events, max over ranks; median block reported"},
+            "serial": {"value": world * args.steps / (ms_serial * 1e-3), "ms_per_step": ms_serial / args.steps, "blocks": len(ser_ms),
+                       "note": "the same steps on ONE stream (round-1 definition of `value`)", "gpu_launches": int(ser_launches)},
+            "clocks": clocks, "gpu_launches": int(pip_launches),
+            "e2e": {"value": e2e_pipe_pageable, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "host_memory": "pageable (malloc'd like GImage); tracking thread || mapping thread, two gb_ctx",
+                    "pinned": e2e_pipe_pinned, "serial_pageable": e2e_serial_pageable, "serial_pinned": e2e_serial_pinned},
             "stages_ms": {"extract": t_ext, "match": t_match, "local_ba": t_ba},
             # dominant HBM-bound kernel of the path = the BA Jacobian sweep (BASELINE metric, 2nd clause), at config-5 size
             "roofline": {"kernel": "BA Jacobian sweep K6 (ba_linearize_kernel: camera pass + landmark pass in one launch), 500 cams/100k pts/1M obs",
                          "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": 150.6e6, "traffic_source": "profiles/r01_ncu_summary.md (dram__bytes_read 44.25 MB + dram__bytes_write 106.36 MB of one launch, ncu --set full)",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "frac_on_measured_dram_bytes": (traffic / (t_sweep_big * 1e-3) / 1e9) / peak if traffic else None,
+                         "in_timed_step": False,
                          "peak_source": peak_src, "algorithmic_bytes": int(big_bytes), "ms_per_sweep": t_sweep_big},
             # the same quantity for the kernels as they run inside the timed step (one frame / one 10k-observation window:
             # launch-latency-bound, reported for completeness)
@@ -294,8 +474,13 @@ def main():
                               "ba_sweep_local": {"algorithmic_bytes": ab["ba_sweep"], "ms": t_sweep_local,
                                                  "achieved_gbs": gbs(ab["ba_sweep"], t_sweep_local), "frac": gbs(ab["ba_sweep"], t_sweep_local) / peak},
                               "match": {"algorithmic_bytes": ab["match"], "popc32": 8 * NKP * NKP, "ms": t_match,
-                                        "gpopc_per_s": 8 * NKP * NKP / (t_match * 1e-3) / 1e9, "bound": "integer POPC pipe"}},
+                                        "gpopc_per_s": 8 * NKP * NKP / (t_match * 1e-3) / 1e9, "bound": "integer POPC pipe",
+                                        "peak_gpopc_per_s": popc_peak / 1e9 if popc_peak else None,
+                                        "peak_source": "measured on this device (gb_dbg_popc_peak: 16 independent LOP3+POPC chains per thread, all SMs)",
+                                        "frac": (8 * NKP * NKP / (t_match * 1e-3)) / popc_peak if popc_peak else None}},
             }
+    if global_ba is not None:
+        line["global_ba"] = global_ba
     # CPU baseline on a bounded sample, rank 0 only, N=1 only
     if world == 1:
         try:

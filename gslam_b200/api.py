@@ -95,6 +95,16 @@ class Context:
     def sync(self):
         self._check(self._lib.gb_ctx_sync(self._h))
 
+    def wait_for(self, producer: "Context"):
+        """Order this ctx's stream after everything enqueued so far on `producer`'s stream (no host sync)."""
+        self._check(self._lib.gb_ctx_wait_for(self._h, producer._h))
+
+    def popc_peak(self) -> float:
+        """Measured POPC throughput of the device (popc32 per second): the matcher's roofline denominator."""
+        v = C.c_double()
+        self._check(self._lib.gb_dbg_popc_peak(self._h, C.byref(v)))
+        return float(v.value)
+
     def stream(self) -> int:
         return int(self._lib.gb_ctx_stream(self._h) or 0)
 
@@ -318,6 +328,76 @@ class BAGraph:
         self.ctx._check(self.ctx._lib.gb_dbg_ba_reduced(self.ctx._h, self._h, C.byref(o), ptr(S), ptr(gt), ptr(dc), C.byref(it)))
         return S, gt, dc, it.value
 
+
+
+class Comm:
+    """A rank of the multi-GPU communicator (gb_comm): NCCL under the C-ABI.  `unique_id` is the 128 bytes rank 0 obtained from
+    Comm.unique_id() and the host distributed (torch.distributed broadcast in bench.py / tests)."""
+
+    def __init__(self, ctx: Context, world: int = 1, rank: int = 0, unique_id: bytes | None = None):
+        self.ctx = ctx
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        ctx._check(ctx._lib.gb_comm_create(ctx._h, world, rank, C.cast(buf, C.c_void_p) if buf is not None else None, C.byref(h)))
+        self._h = h
+        self.rank, self.world = rank, world
+
+    @staticmethod
+    def unique_id() -> bytes:
+        L = capi.lib()
+        buf = (C.c_uint8 * 128)()
+        rc = L.gb_comm_unique_id(C.cast(buf, C.c_void_p))
+        if rc != capi.GB_OK:
+            raise GbError(rc, L.gb_last_error(None).decode())
+        return bytes(buf)
+
+    def allreduce_sum_f64(self, d_ptr: int, n: int):
+        self.ctx._check(self.ctx._lib.gb_comm_allreduce_sum_f64(self._h, C.c_void_p(d_ptr), n))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.gb_comm_destroy(self._h)
+            self._h = None
+
+
+class ShardedBAGraph(BAGraph):
+    """This rank's landmark shard of a global BA problem (gb_ba_shard_*): every rank passes the SAME full problem."""
+
+    def __init__(self, comm: Comm, pb: BAProblem):
+        self.ctx, self.comm = comm.ctx, comm
+        c, keep = _problem_c(pb)
+        h = C.c_void_p()
+        self.ctx._check(self.ctx._lib.gb_ba_shard_create(comm._h, C.byref(c), C.byref(h)))
+        self._h = h
+        lo, hi = C.c_int(), C.c_int()
+        self.ctx._check(self.ctx._lib.gb_ba_shard_range(self._h, C.byref(lo), C.byref(hi)))
+        self.lo, self.hi = lo.value, hi.value
+        self.n_cams, self.n_points = pb.n_cams, self.hi - self.lo
+        nb = C.c_size_t()
+        self.ctx._check(self.ctx._lib.gb_ba_shard_reduce_bytes(self._h, C.byref(nb)))
+        self.reduce_bytes = int(nb.value)
+
+    def solve(self, cfg: OptimzeConfig | None = None) -> capi.BaResult:
+        o = (cfg or OptimzeConfig()).to_c(); r = capi.BaResult()
+        self.ctx._check(self.ctx._lib.gb_ba_shard_solve(self.comm._h, self._h, C.byref(o), C.byref(r)))
+        return r
+
+
+def ba_solve_multi(ctxs, pb: BAProblem, cfg: OptimzeConfig | None = None) -> capi.BaResult:
+    """One process, len(ctxs) GPUs: gb_comm_create_all + gb_ba_solve_multi (what the optimizer plugin does for b200.devices)."""
+    L = capi.lib()
+    n = len(ctxs)
+    hs = (C.c_void_p * n)(*[c._h for c in ctxs])
+    comms = (C.c_void_p * n)()
+    ctxs[0]._check(L.gb_comm_create_all(n, hs, comms))
+    try:
+        c, keep = _problem_c(pb)
+        o = (cfg or OptimzeConfig()).to_c(); r = capi.BaResult()
+        ctxs[0]._check(L.gb_ba_solve_multi(n, comms, C.byref(c), C.byref(o), C.byref(r)))
+        return r
+    finally:
+        for k in range(n):
+            L.gb_comm_destroy(comms[k])
 
 class Optimizer:
     """Mirror of GSLAM::Optimizer (Optimizer.h:184-253): bool returns, graph / pose updated in place, `_config` public."""

@@ -65,6 +65,7 @@ _SIGNATURES = [
     ("gb_last_error", C.c_char_p, [_VP]),
     ("gb_ctx_stream", _VP, [_VP]),
     ("gb_ctx_sync", C.c_int, [_VP]),
+    ("gb_ctx_wait_for", C.c_int, [_VP, _VP]),
     ("gb_timer_begin", C.c_int, [_VP]),
     ("gb_timer_end", C.c_int, [_VP, C.POINTER(C.c_float)]),
     ("gb_launch_count", C.c_int64, [_VP]),
@@ -95,6 +96,18 @@ _SIGNATURES = [
     ("gb_ba_graph_commit", C.c_int, [_VP, _VP, _VP, _VP]),
     ("gb_ba_graph_finish", C.c_int, [_VP, _VP, C.POINTER(BaResult)]),
     ("gb_pnp_ransac", C.c_int, [_VP, C.c_int, _VP, _VP, C.c_double, C.c_double, C.c_int, C.c_uint64, _VP, _VP, C.POINTER(PnpStats)]),
+    ("gb_comm_unique_id", C.c_int, [_VP]),
+    ("gb_comm_create", C.c_int, [_VP, C.c_int, C.c_int, _VP, C.POINTER(_VP)]),
+    ("gb_comm_create_all", C.c_int, [C.c_int, C.POINTER(_VP), C.POINTER(_VP)]),
+    ("gb_comm_destroy", C.c_int, [_VP]),
+    ("gb_comm_rank", C.c_int, [_VP]),
+    ("gb_comm_world", C.c_int, [_VP]),
+    ("gb_comm_allreduce_sum_f64", C.c_int, [_VP, _VP, C.c_size_t]),
+    ("gb_ba_shard_create", C.c_int, [_VP, C.POINTER(BaProblem), C.POINTER(_VP)]),
+    ("gb_ba_shard_range", C.c_int, [_VP, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("gb_ba_shard_reduce_bytes", C.c_int, [_VP, C.POINTER(C.c_size_t)]),
+    ("gb_ba_shard_solve", C.c_int, [_VP, _VP, C.POINTER(BaOptions), C.POINTER(BaResult)]),
+    ("gb_ba_solve_multi", C.c_int, [C.c_int, C.POINTER(_VP), C.POINTER(BaProblem), C.POINTER(BaOptions), C.POINTER(BaResult)]),
 ]
 # test hooks (not part of the reference-facing surface)
 _DEBUG_SIGNATURES = [
@@ -107,6 +120,8 @@ _DEBUG_SIGNATURES = [
     ("gb_dbg_ba_sweep_part", C.c_int, [_VP, _VP, C.c_int]),
     ("gb_dbg_pnp_p3p_host", C.c_int, [_VP, _VP, _VP]),
     ("gb_dbg_pnp_minimal_host", C.c_int, [C.c_int, _VP, _VP, C.c_double, C.c_double, C.c_int, C.c_uint64, _VP, C.POINTER(PnpStats)]),
+    ("gb_dbg_ba_shard_bounds", C.c_int, [C.c_int, C.c_int, _VP, C.c_int, _VP]),
+    ("gb_dbg_popc_peak", C.c_int, [_VP, C.POINTER(C.c_double)]),
     ("gb_dbg_orb_level_size", C.c_int, [C.c_int, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 ]
 

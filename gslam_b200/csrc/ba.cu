@@ -1497,10 +1497,15 @@ static bool ba_raise_smem_limits(gb_ctx* ctx) {
   std::lock_guard<std::mutex> lk(mu);
   if (state[dev] == 0) {
     g_cluster16_ok[dev] = cudaFuncSetAttribute(ba_pcg_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
-    const int lim = ctx->max_smem_optin;
-    bool ok = cudaFuncSetAttribute(BA_SPARSE_SMALL, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) == cudaSuccess;
-    ok = (cudaFuncSetAttribute(BA_SPARSE_LARGE, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) == cudaSuccess) && ok;
-    ok = (cudaFuncSetAttribute(ba_pcg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim) == cudaSuccess) && ok;
+    // (the opt-in maximum covers static + dynamic shared memory: leave room for each kernel's static part)
+    auto raise = [&](const void* fn) {
+      cudaFuncAttributes fa;
+      if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) return false;
+      return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin - (int)fa.sharedSizeBytes) == cudaSuccess;
+    };
+    bool ok = raise((const void*)BA_SPARSE_SMALL);
+    ok = raise((const void*)BA_SPARSE_LARGE) && ok;
+    ok = raise((const void*)ba_pcg_cluster_kernel) && ok;
     cudaGetLastError();
     state[dev] = ok ? 1 : 2;
   }
@@ -1515,7 +1520,7 @@ static void ba_pick_pcg(gb_ctx* ctx, gb_ba_graph* g) {
   const bool smem_ok = ba_raise_smem_limits(ctx);
   if (nc > 0 && g->pcg_nact <= kSpMaxCams && g->d.s_nnzb > 0) {
     const size_t smem = ((size_t)g->d.s_nnzb * 36 + (size_t)nc * 36 + 3 * (size_t)n6) * sizeof(double) + (2 * (size_t)nc + 1 + g->d.s_nnzb) * sizeof(int) + 64;
-    if (smem <= (size_t)ctx->max_smem_optin && smem_ok) {
+    if (smem + 2048 <= (size_t)ctx->max_smem_optin && smem_ok) {
       g->pcg_sparse = true;
       g->pcg_sparse_smem = smem;
     }
@@ -1528,7 +1533,7 @@ static void ba_pick_pcg(gb_ctx* ctx, gb_ba_graph* g) {
     if (C == 16 && !np_ok) continue;
     const int cpc = (nc + C - 1) / C;
     const size_t smem = ((size_t)6 * cpc * n6 + (size_t)nc * 36 + 7 * (size_t)n6) * sizeof(double) + 64;
-    if (smem > (size_t)ctx->max_smem_optin || !smem_ok) continue;
+    if (smem + 2048 > (size_t)ctx->max_smem_optin || !smem_ok) continue;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(C); cfg.blockDim = dim3(kPcgThreads); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
     cudaLaunchAttribute at[1];
@@ -1599,6 +1604,29 @@ int gb_ba_graph_create(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out) 
 
 }  // extern "C"
 
+// first landmark of rank r's shard: the first landmark whose edge prefix count reaches r/world of the edges (monotone in r)
+static int ba_shard_bound(const std::vector<int>& pt_off, int n_obs, int n_points, int r, int world) {
+  if (r <= 0) return 0;
+  if (r >= world) return n_points;
+  const double target = (double)n_obs * (double)r / (double)world;
+  const int b = (int)(std::lower_bound(pt_off.begin(), pt_off.end(), target, [](int a, double t) { return (double)a < t; }) - pt_off.begin());
+  return std::min(b, n_points);
+}
+
+// host-only test hook: the shard boundaries (world+1 entries) ba_graph_create_impl would use -- no device needed
+extern "C" GB_API int gb_dbg_ba_shard_bounds(int n_points, int n_obs, const int32_t* obs_point, int world, int32_t* bounds) {
+  if (n_points < 0 || n_obs < 0 || world < 1 || !bounds || (n_obs > 0 && !obs_point)) return GB_ERR_INVALID;
+  std::vector<int> pt_off(n_points + 1, 0);
+  for (int k = 0; k < n_obs; ++k) {
+    if (obs_point[k] < 0 || obs_point[k] >= n_points) return GB_ERR_INVALID;
+    pt_off[obs_point[k] + 1]++;
+  }
+  for (int j = 0; j < n_points; ++j) pt_off[j + 1] += pt_off[j];
+  int prev = 0;
+  for (int r = 0; r <= world; ++r) { prev = std::max(prev, ba_shard_bound(pt_off, n_obs, n_points, r, world)); bounds[r] = prev; }
+  return GB_OK;
+}
+
 int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out, bool use_arena, int shard_rank, int shard_world) {
   if (!ctx || !out) return GB_ERR_INVALID;
   *out = nullptr;
@@ -1640,14 +1668,8 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   //      shard's edges are ONE contiguous slice [e_lo, e_hi) of the sorted order
   int lo = 0, hi = np_full;
   if (shard_world > 1) {
-    auto bound = [&](int r) {
-      if (r <= 0) return 0;
-      if (r >= shard_world) return np_full;
-      const double target = (double)no_full * (double)r / (double)shard_world;
-      return (int)(std::lower_bound(pt_off.begin(), pt_off.end(), target, [](int a, double t) { return (double)a < t; }) - pt_off.begin());
-    };
-    lo = std::min(bound(shard_rank), np_full);
-    hi = std::min(std::max(bound(shard_rank + 1), lo), np_full);
+    lo = ba_shard_bound(pt_off, no_full, np_full, shard_rank, shard_world);
+    hi = std::max(ba_shard_bound(pt_off, no_full, np_full, shard_rank + 1, shard_world), lo);
   }
   g->shard_lo = lo; g->shard_hi = hi; g->shard_rank = shard_rank; g->shard_world = shard_world;
   const int e_lo = pt_off[lo], e_hi = pt_off[hi];

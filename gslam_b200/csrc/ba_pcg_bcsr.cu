@@ -258,7 +258,9 @@ int ba_pcg_bcsr_plan(gb_ctx* ctx, gb_ba_graph* g, const int* s_rowptr) {
     const int dev = ctx->device;
     if (dev < 0 || dev >= 64) return GB_OK;
     if (state[dev] == 0) {
-      state[dev] = cudaFuncSetAttribute(ba_pcg_bcsr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin) == cudaSuccess ? 1 : 2;
+      cudaFuncAttributes fa;  // (the opt-in maximum covers static + dynamic shared memory)
+      state[dev] = (cudaFuncGetAttributes(&fa, ba_pcg_bcsr_kernel) == cudaSuccess &&
+                    cudaFuncSetAttribute(ba_pcg_bcsr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin - (int)fa.sharedSizeBytes) == cudaSuccess) ? 1 : 2;
       cudaGetLastError();
     }
     if (state[dev] != 1) return GB_OK;
@@ -287,10 +289,11 @@ int ba_pcg_bcsr_plan(gb_ctx* ctx, gb_ba_graph* g, const int* s_rowptr) {
   }
   bool in_smem = true;
   size_t smem = bcsr_smem_bytes(n6, max_cams, max_blocks, true);
-  if (smem > (size_t)ctx->max_smem_optin) {
+  const size_t budget = (size_t)ctx->max_smem_optin - 1024;  // (static shared memory of the kernel: 272 bytes)
+  if (smem > budget) {
     in_smem = false;
     smem = bcsr_smem_bytes(n6, max_cams, max_blocks, false);
-    if (smem > (size_t)ctx->max_smem_optin) return GB_OK;  // not even the vectors fit: generic path
+    if (smem > budget) return GB_OK;  // not even the vectors fit: generic path
   }
   int K = 32;
   while (K > 1 && 6 * max_cams * K > kBcsrThreads) K >>= 1;

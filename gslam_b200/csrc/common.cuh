@@ -22,6 +22,7 @@ struct gb_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // gb_timer_*
   cudaEvent_t evs = nullptr, eve = nullptr;   // internal (gb_ba_result.gpu_ms)
+  cudaEvent_t ev_x = nullptr;                 // gb_ctx_wait_for (cross-ctx ordering)
   std::recursive_mutex mu;
   std::string err;
   int64_t launches = 0;

@@ -128,6 +128,7 @@ int gb_ctx_destroy(gb_ctx* ctx) {
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->evs);
     cudaEventDestroy(ctx->eve);
+    if (ctx->ev_x) cudaEventDestroy(ctx->ev_x);
     cudaStreamDestroy(ctx->stream);
   }
   delete ctx;
@@ -142,6 +143,22 @@ int gb_ctx_sync(gb_ctx* ctx) {
   if (!ctx) return GB_ERR_INVALID;
   CtxLock lk(ctx);
   GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return GB_OK;
+}
+
+// Order `waiter`'s stream after everything enqueued so far on `producer`'s stream (event record + stream wait; no host sync).
+// This is how a tracking ctx (extract / match) and a mapping ctx (local BA) pipeline on one GPU: BA(k) waits for match(k) while
+// extract(k+1) already runs.
+int gb_ctx_wait_for(gb_ctx* waiter, gb_ctx* producer) {
+  if (!waiter || !producer) return GB_ERR_INVALID;
+  if (waiter == producer) return GB_OK;
+  std::lock(waiter->mu, producer->mu);
+  std::lock_guard<std::recursive_mutex> l0(waiter->mu, std::adopt_lock), l1(producer->mu, std::adopt_lock);
+  if (waiter->device != producer->device) { gb_set_error(waiter, "gb_ctx_wait_for: contexts on different devices"); return GB_ERR_INVALID; }
+  cudaSetDevice(producer->device);
+  if (!producer->ev_x) GB_CUDA(producer, cudaEventCreateWithFlags(&producer->ev_x, cudaEventDisableTiming));
+  GB_CUDA(producer, cudaEventRecord(producer->ev_x, producer->stream));
+  GB_CUDA(waiter, cudaStreamWaitEvent(waiter->stream, producer->ev_x, 0));
   return GB_OK;
 }
 

@@ -102,6 +102,24 @@ __global__ void __launch_bounds__(kQPerCta) match_kernel(const uint4* __restrict
   if (tid == 0) tickets[blockIdx.x] = 0;  // re-arm for the next launch on this stream
 }
 
+// POPC-pipe ceiling of this device, measured (bench.py: the matcher's roofline denominator): every thread keeps 16 independent
+// x = popc(x ^ m) chains in flight -- the same LOP3 + POPC pair as the matcher's inner loop, nothing else.
+__global__ void __launch_bounds__(256) popc_peak_kernel(unsigned int* __restrict__ out, int iters, unsigned int seed) {
+  unsigned int x[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) x[k] = seed * (threadIdx.x + 1u) + 0x9e3779b9u * (k + 1u) + blockIdx.x;
+  unsigned int m = seed | 0x80000001u;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = __popc(x[k] ^ m) | (x[k] << 7);  // (the shift/or keeps the chain from collapsing to a constant)
+    m = m * 1664525u + 1013904223u;
+  }
+  unsigned int acc = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc ^= x[k];
+  if (acc == 0x12345u) out[0] = acc;  // (never true in practice; keeps the loop alive)
+}
+
 }  // namespace
 
 struct MatchState {
@@ -155,6 +173,33 @@ int gb_match_launch(gb_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t,
 }
 
 extern "C" {
+
+// test / bench hook: measured POPC throughput of the device in popc32 per second (all SMs, 16 independent chains per thread)
+GB_API int gb_dbg_popc_peak(gb_ctx* ctx, double* popc_per_s) {
+  if (!ctx || !popc_per_s) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  unsigned int* d_out = nullptr;
+  GB_CUDA(ctx, cudaMalloc((void**)&d_out, 64));
+  const int ctas = ctx->sm_count * 8, iters = 4096;
+  cudaEvent_t e0, e1;
+  GB_CUDA(ctx, cudaEventCreate(&e0));
+  GB_CUDA(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {  // rep 0 warms up
+    GB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    popc_peak_kernel<<<ctas, 256, 0, ctx->stream>>>(d_out, iters, 12345u + rep);
+    GB_LAUNCH_CHECK(ctx);
+    GB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    GB_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    GB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *popc_per_s = (double)ctas * 256.0 * iters * 16.0 / (best * 1e-3);
+  return GB_OK;
+}
 
 int gb_match_features(gb_ctx* ctx, gb_features* fq, gb_features* ft) {
   if (!ctx || !fq || !ft) return GB_ERR_INVALID;

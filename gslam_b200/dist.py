@@ -1,10 +1,9 @@
-"""Landmark-sharded multi-GPU global bundle adjustment (BASELINE config 5).
+"""Landmark-sharded multi-GPU global bundle adjustment (BASELINE config 5) -- one process per GPU.
 
-Every rank holds ALL cameras and a shard of the landmarks with all their edges.  One LM iteration has exactly one real
-exchange: the sum over ranks of the shard's Schur contribution [S | g~ | diag U | cost] (one NCCL all-reduce, f64), plus a
-1-double all-reduce of the candidate cost.  PCG on the reduced camera system is replicated and deterministic, so every rank
-takes bit-identical accept/reject decisions without any broadcast.  torch.distributed is plumbing only: the buffers are
-plain device memory handed to the C-ABI stepwise entry points (gb_ba_graph_reduce_local / _step / _commit).
+Everything numeric AND the collective live under the C-ABI (csrc/ba_dist.cu: NCCL bound with dlopen, all-reduce of the compact
+block-CSR reduced camera system once per LM iteration, replicated bit-identical PCG).  What this module does is rendezvous only:
+rank 0 asks the C-ABI for an NCCL unique id and torch.distributed (any backend; gloo works) carries the 128 bytes to the other
+ranks.  The single-process front end (one process driving N GPUs, what the optimizer plugin uses) is api.ba_solve_multi.
 """
 from __future__ import annotations
 
@@ -13,17 +12,22 @@ import numpy as np
 from .synth import BAProblem
 
 
-def shard_landmarks(pb: BAProblem, rank: int, world: int):
-    """Contiguous landmark ranges balanced by observation count.  Returns (local problem, global ids of the local points)."""
+def shard_bounds(pb: BAProblem, world: int):
+    """The landmark ranges the C-ABI uses (contiguous, balanced by observation count) -- restated for tests."""
     counts = np.bincount(pb.obs_point, minlength=pb.n_points).astype(np.int64)
     csum = np.concatenate([[0], np.cumsum(counts)])
-    total = csum[-1]
-    # boundary b_r = first point whose prefix count reaches r/world of the edges
-    bounds = [int(np.searchsorted(csum, total * r / world, side="left")) for r in range(world + 1)]
-    bounds[0], bounds[-1] = 0, pb.n_points
-    for r in range(1, world + 1):
-        bounds[r] = max(bounds[r], bounds[r - 1])
-    lo, hi = bounds[rank], bounds[rank + 1]
+    total = int(csum[-1])
+    b = [0]
+    for r in range(1, world):
+        b.append(max(int(np.searchsorted(csum, total * r / world, side="left")), b[-1]))
+    b.append(pb.n_points)
+    return b
+
+
+def shard_landmarks(pb: BAProblem, rank: int, world: int):
+    """The rank's local problem as the C-ABI builds it internally: (local problem, global ids of the local points)."""
+    b = shard_bounds(pb, world)
+    lo, hi = b[rank], b[rank + 1]
     ids = np.arange(lo, hi, dtype=np.int64)
     sel = (pb.obs_point >= lo) & (pb.obs_point < hi)
     local = BAProblem(cam_pose_wc=pb.cam_pose_wc.copy(), cam_dof=pb.cam_dof.copy(),
@@ -34,38 +38,36 @@ def shard_landmarks(pb: BAProblem, rank: int, world: int):
     return local, ids
 
 
-class DistributedBA:
-    """One rank of the landmark-sharded solve.  `group` is a torch.distributed process group (NCCL on GPUs)."""
+def broadcast_unique_id(rank: int, world: int, group=None) -> bytes | None:
+    """Rank 0 creates the NCCL unique id under the C-ABI; torch.distributed broadcasts it (CPU tensor on gloo, CUDA on nccl)."""
+    if world == 1:
+        return None
+    import torch
+    import torch.distributed as dist
+    from .api import Comm
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(Comm.unique_id()), dtype=torch.uint8).to(dev)
+    dist.broadcast(t, src=0, group=group)
+    return bytes(t.cpu().numpy().tobytes())
 
-    def __init__(self, ctx, pb: BAProblem, rank: int, world: int, group=None):
-        import torch
-        import torch.distributed as dist
-        from .api import BAGraph
-        self.torch, self.dist = torch, dist
-        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
-        self.n_points_global = pb.n_points
-        self.local, self.ids = shard_landmarks(pb, rank, world)
-        self.graph = BAGraph(ctx, self.local)
-        self.stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", ctx.device))
-        n = self.graph.reduce_size()
-        self.buf = torch.zeros(n, dtype=torch.float64, device=torch.device("cuda", ctx.device))
-        self.cost = torch.zeros(8, dtype=torch.float64, device=torch.device("cuda", ctx.device))
-        self.reduce_bytes = n * 8
+
+class DistributedBA:
+    """One rank of the landmark-sharded solve: Comm + ShardedBAGraph."""
+
+    def __init__(self, ctx, pb: BAProblem, rank: int, world: int, group=None, unique_id: bytes | None = None):
+        from .api import Comm, ShardedBAGraph
+        self.ctx, self.rank, self.world = ctx, rank, world
+        if world > 1 and unique_id is None:
+            unique_id = broadcast_unique_id(rank, world, group)
+        self.comm = Comm(ctx, world, rank, unique_id)
+        self.graph = ShardedBAGraph(self.comm, pb)
+        self.ids = np.arange(self.graph.lo, self.graph.hi, dtype=np.int64)
+        self.reduce_bytes = self.graph.reduce_bytes
 
     def solve(self, cfg):
-        torch, dist = self.torch, self.dist
-        g = self.graph
-        with torch.cuda.stream(self.stream):  # collectives are ordered after / before our kernels on the ctx stream
-            g.begin(cfg)
-            for _ in range(cfg.maxIterations):
-                g.reduce_local(self.buf.data_ptr())
-                if self.world > 1:
-                    dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
-                g.step(self.buf.data_ptr(), self.cost.data_ptr())
-                if self.world > 1:
-                    dist.all_reduce(self.cost, op=dist.ReduceOp.SUM, group=self.group)
-                g.commit(self.buf.data_ptr(), self.cost.data_ptr())
-            return g.finish()
+        return self.graph.solve(cfg)
 
     def download(self):
         """(poses, local points, their global ids)"""
@@ -74,3 +76,4 @@ class DistributedBA:
 
     def close(self):
         self.graph.close()
+        self.comm.close()

@@ -7,11 +7,13 @@
 //   gslam_b200_host_test pnp  <plugin-dir> in.bin out.bin      optimizePnP(...)
 //   gslam_b200_host_test orb  <plugin-dir> in.bin out.bin      Registry::load("b200") -> gslam.b200.orb_extract + match_hamming
 //   gslam_b200_host_test findpnp <plugin-dir> in.bin out.bin   Estimator::create() -> findPnP (P3P + RANSAC), Estimator.h:158-164
+// Trailing "key=value" arguments become svar settings the plugins read (b200.devices=0,1 shards a global BA over two GPUs).
 #include <GSLAM/core/GSLAM.h>
 #include <GSLAM/core/Estimator.h>
 #include <GSLAM/core/Optimizer.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <vector>
 
@@ -141,6 +143,19 @@ static int runFindPnP(const std::string& dir, const char* in, const char* out) {
 
 int main(int argc, char** argv) {
   if (argc < 5) { fprintf(stderr, "usage: %s ba|pnp|orb|findpnp <plugin-dir> in.bin out.bin\n", argv[0]); return 64; }
+  // optional svar settings for the plugins, "key=value" (e.g. b200.devices=0,1  b200.multi_min_obs=1000)
+  for (int i = 5; i < argc; ++i) {
+    const std::string kv = argv[i];
+    const size_t eq = kv.find('=');
+    if (eq == std::string::npos) continue;
+    const std::string key = kv.substr(0, eq), val = kv.substr(eq + 1);
+    char* end = NULL;
+    const long iv = strtol(val.c_str(), &end, 10);
+    if (end && *end == 0 && !val.empty()) { svar.Set<int>(key, (int)iv); continue; }  // typed like `gslam -key value` would be read back
+    const double dv = strtod(val.c_str(), &end);
+    if (end && *end == 0 && !val.empty()) { svar.Set<double>(key, dv); continue; }
+    svar.Set<std::string>(key, val);
+  }
   const std::string mode = argv[1];
   if (mode == "ba") return runBA(argv[2], argv[3], argv[4], false);
   if (mode == "pnp") return runBA(argv[2], argv[3], argv[4], true);

@@ -10,8 +10,13 @@
 #include <GSLAM/core/GSLAM.h>
 #include <GSLAM/core/Optimizer.h>
 
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gslam_b200.h"
@@ -20,8 +25,11 @@ namespace {
 
 class OptimizerB200 : public GSLAM::Optimizer {
  public:
-  OptimizerB200() : ctx_(nullptr) {}
+  OptimizerB200() : ctx_(nullptr), multi_failed_(false) {}
   ~OptimizerB200() override {
+    for (size_t k = 0; k < comms_.size(); ++k) gb_comm_destroy(comms_[k]);
+    for (size_t k = 0; k < ctxs_.size(); ++k)
+      if (ctxs_[k] != ctx_) gb_ctx_destroy(ctxs_[k]);
     if (ctx_) gb_ctx_destroy(ctx_);
   }
 
@@ -43,9 +51,13 @@ class OptimizerB200 : public GSLAM::Optimizer {
       }
       if (!ensureContext()) return false;
       const size_t nc = graph.keyframes.size(), np = graph.mappoints.size(), no = graph.mappointObserves.size();
-      std::vector<double> pose(7 * nc), pts(3 * np), xyz(3 * no), info;
-      std::vector<uint8_t> dof(nc), pfree(np);
-      std::vector<int32_t> oc(no), op(no);
+      // AoS -> SoA repack into member buffers (capacity is kept across calls: a sliding window re-uses them without touching the
+      // allocator; the edge loop runs on all cores for global-BA-sized graphs: 48 MB of BundleEdge at config 5)
+      std::lock_guard<std::mutex> call_lock(call_mu_);
+      std::vector<double>&pose = pose_, &pts = pts_, &xyz = xyz_, &info = info_;
+      std::vector<uint8_t>&dof = dof_, &pfree = pfree_;
+      std::vector<int32_t>&oc = oc_, &op = op_;
+      pose.resize(7 * nc); pts.resize(3 * np); xyz.resize(3 * no); info.clear(); dof.resize(nc); pfree.resize(np); oc.resize(no); op.resize(no);
       for (size_t i = 0; i < nc; ++i) {
         // SIM3 memory = {SO3{x,y,z,w}, Point3d, scale}: the first 7 doubles are the SE3 T_wc (SE3.h:337-339, SIM3.h:290-291)
         const GSLAM::SE3& T = graph.keyframes[i].estimation.get_se3();
@@ -63,19 +75,34 @@ class OptimizerB200 : public GSLAM::Optimizer {
       bool any_info = false;
       for (size_t k = 0; k < no; ++k) any_info |= graph.mappointObserves[k].information != NULL;
       if (any_info) info.resize(4 * no);
-      for (size_t k = 0; k < no; ++k) {
-        const GSLAM::BundleEdge& e = graph.mappointObserves[k];
-        if (e.frameId >= nc || e.pointId >= np) {
-          LOG(ERROR) << "gslam_b200 optimizer: edge " << k << " references frame " << e.frameId << " / point " << e.pointId;
-          return false;
+      std::atomic<long> bad_edge_a(-1);
+      auto repack = [&](size_t k0, size_t k1) {
+        for (size_t k = k0; k < k1; ++k) {
+          const GSLAM::BundleEdge& e = graph.mappointObserves[k];
+          if (e.frameId >= nc || e.pointId >= np) { bad_edge_a = (long)k; continue; }
+          oc[k] = (int32_t)e.frameId; op[k] = (int32_t)e.pointId;
+          xyz[3 * k] = e.measurement.x; xyz[3 * k + 1] = e.measurement.y; xyz[3 * k + 2] = e.measurement.z;
+          if (any_info) {
+            double* L = &info[4 * k];
+            if (e.information) std::memcpy(L, e.information, 4 * sizeof(double));
+            else { L[0] = 1; L[1] = 0; L[2] = 0; L[3] = 1; }
+          }
         }
-        oc[k] = (int32_t)e.frameId; op[k] = (int32_t)e.pointId;
-        xyz[3 * k] = e.measurement.x; xyz[3 * k + 1] = e.measurement.y; xyz[3 * k + 2] = e.measurement.z;
-        if (any_info) {
-          double* L = &info[4 * k];
-          if (e.information) std::memcpy(L, e.information, 4 * sizeof(double));
-          else { L[0] = 1; L[1] = 0; L[2] = 0; L[3] = 1; }
-        }
+      };
+      if (no > 65536) {  // global-BA-sized: split the edge list over a few host threads
+        const size_t nt = std::min<size_t>(std::max(2u, std::thread::hardware_concurrency()), 16);
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nt; ++t) th.emplace_back(repack, no * t / nt, no * (t + 1) / nt);
+        repack(0, no / nt);
+        for (size_t t = 0; t < th.size(); ++t) th[t].join();
+      } else {
+        repack(0, no);
+      }
+      const long bad_edge = bad_edge_a;
+      if (bad_edge >= 0) {
+        const GSLAM::BundleEdge& e = graph.mappointObserves[bad_edge];
+        LOG(ERROR) << "gslam_b200 optimizer: edge " << bad_edge << " references frame " << e.frameId << " / point " << e.pointId;
+        return false;
       }
       gb_ba_problem pb;
       std::memset(&pb, 0, sizeof pb);
@@ -84,7 +111,13 @@ class OptimizerB200 : public GSLAM::Optimizer {
       pb.obs_cam = oc.data(); pb.obs_point = op.data(); pb.obs_xyz = xyz.data(); pb.obs_info = any_info ? info.data() : NULL;
       gb_ba_options opt = options();
       gb_ba_result res;
-      const int rc = gb_ba_solve(ctx_, &pb, &opt, &res);
+      // global-BA-sized graphs on several GPUs when the svar option `b200.devices` (e.g. "0,1,2,3") names more than one device:
+      // landmark-sharded solve, one NCCL all-reduce of the reduced camera system per LM iteration (gb_ba_solve_multi)
+      int rc;
+      if (no >= (size_t)svar.GetInt("b200.multi_min_obs", 200000) && ensureMulti())
+        rc = gb_ba_solve_multi((int)comms_.size(), comms_.data(), &pb, &opt, &res);
+      else
+        rc = gb_ba_solve(ctx_, &pb, &opt, &res);
       if (rc != GB_OK) {
         LOG(ERROR) << "gslam_b200 optimizer: " << gb_last_error(ctx_);
         return false;
@@ -145,6 +178,46 @@ class OptimizerB200 : public GSLAM::Optimizer {
     return true;
   }
 
+  // contexts + communicators for `b200.devices`; false (single-GPU path) when fewer than two devices are named or usable
+  bool ensureMulti() {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (!comms_.empty()) return true;
+    if (multi_failed_) return false;
+    const std::string list = svar.GetString("b200.devices", "");
+    std::vector<int> devs;
+    for (size_t i = 0; i < list.size();) {
+      size_t j = list.find(',', i);
+      if (j == std::string::npos) j = list.size();
+      if (j > i) devs.push_back(atoi(list.substr(i, j - i).c_str()));
+      i = j + 1;
+    }
+    if (devs.size() < 2) { multi_failed_ = true; return false; }
+    for (size_t k = 0; k < devs.size(); ++k) {
+      gb_ctx* c = nullptr;
+      if (ctx_ && devs[k] == svar.GetInt("b200.device", 0)) c = ctx_;
+      else if (gb_ctx_create(devs[k], &c) != GB_OK) {
+        LOG(ERROR) << "gslam_b200 optimizer: b200.devices names device " << devs[k] << " which is not usable (" << gb_last_error(NULL)
+                   << "); staying on one GPU";
+        for (size_t t = 0; t < ctxs_.size(); ++t)
+          if (ctxs_[t] != ctx_) gb_ctx_destroy(ctxs_[t]);
+        ctxs_.clear();
+        multi_failed_ = true;
+        return false;
+      }
+      ctxs_.push_back(c);
+    }
+    comms_.resize(ctxs_.size(), nullptr);
+    if (gb_comm_create_all((int)ctxs_.size(), ctxs_.data(), comms_.data()) != GB_OK) {
+      LOG(ERROR) << "gslam_b200 optimizer: communicator over b200.devices failed (" << gb_last_error(ctxs_[0]) << "); staying on one GPU";
+      for (size_t t = 0; t < ctxs_.size(); ++t)
+        if (ctxs_[t] != ctx_) gb_ctx_destroy(ctxs_[t]);
+      ctxs_.clear(); comms_.clear();
+      multi_failed_ = true;
+      return false;
+    }
+    return true;
+  }
+
   gb_ba_options options() const {
     gb_ba_options o;
     gb_ba_options_default(&o);
@@ -159,7 +232,13 @@ class OptimizerB200 : public GSLAM::Optimizer {
   }
 
   gb_ctx* ctx_;
-  std::mutex mu_;
+  std::mutex mu_, call_mu_;
+  std::vector<gb_ctx*> ctxs_;     // b200.devices
+  std::vector<gb_comm*> comms_;
+  bool multi_failed_;
+  std::vector<double> pose_, pts_, xyz_, info_;  // repack buffers (kept across calls)
+  std::vector<uint8_t> dof_, pfree_;
+  std::vector<int32_t> oc_, op_;
 };
 
 }  // namespace

@@ -67,6 +67,9 @@ GB_API const char* gb_last_error(const gb_ctx* ctx);
 /* The ctx's cudaStream_t (as void*) so a host can order its own work / record its own events on it. */
 GB_API void* gb_ctx_stream(gb_ctx* ctx);
 GB_API int gb_ctx_sync(gb_ctx* ctx);
+/* Order `waiter`'s stream after everything enqueued so far on `producer`'s stream (same device; no host synchronisation): the
+ * pipelining primitive between a tracking ctx (extract / match) and a mapping ctx (local BA). */
+GB_API int gb_ctx_wait_for(gb_ctx* waiter, gb_ctx* producer);
 /* CUDA-event stopwatch on the ctx stream (begin records an event; end records another, synchronises, returns ms). */
 GB_API int gb_timer_begin(gb_ctx* ctx);
 GB_API int gb_timer_end(gb_ctx* ctx, float* ms);
@@ -256,6 +259,42 @@ typedef struct gb_pnp_stats {
 } gb_pnp_stats;
 GB_API int gb_pnp_ransac(gb_ctx* ctx, int n, const double* xyz, const double* xy, double threshold, double confidence,
                          int max_hypotheses, uint64_t seed, double* pose_cw, uint8_t* mask, gb_pnp_stats* stats);
+
+/* =====================================================================================================================
+ * Multi-GPU global bundle adjustment (BASELINE config 5: 500 cameras / 100k landmarks / 1M observations).
+ * Still behind GSLAM::Optimizer::optimize(BundleGraph&) (GSLAM/core/Optimizer.h:229): the landmarks (and all their edges) are
+ * sharded over the ranks, every rank holds all cameras; per LM iteration ONE all-reduce (f64 sum over NVLink, NCCL bound at run
+ * time with dlopen) of the shard contributions to the compact reduced camera system [S in covisibility block-CSR | g~ | diag U |
+ * cost], then a replicated, bit-identical block-CSR PCG (so every rank takes the same LM decisions), the shard's
+ * back-substitution and a 1-double all-reduce of the candidate cost.  No host synchronisation inside the loop.
+ *
+ * Two front ends over the same engine:
+ *   one process per GPU : gb_comm_unique_id on rank 0, the host distributes the 128 bytes (torch.distributed broadcast, MPI,
+ *                         a file ...), every rank calls gb_comm_create; then gb_ba_shard_create / _solve / gb_ba_graph_download.
+ *   one process, N GPUs : gb_comm_create_all over N contexts, gb_ba_solve_multi(problem) -- one host thread per device inside;
+ *                         this is what libgslam_optimizer.so's optimize() calls when the svar option `b200.devices` names
+ *                         several devices.
+ * A communicator of world size 1 needs no NCCL and makes every call below a single-GPU call. */
+typedef struct gb_comm gb_comm;
+#define GB_COMM_ID_BYTES 128
+GB_API int gb_comm_unique_id(uint8_t* id128);
+GB_API int gb_comm_create(gb_ctx* ctx, int world, int rank, const uint8_t* id128, gb_comm** out);
+GB_API int gb_comm_create_all(int n_dev, gb_ctx* const* ctxs, gb_comm** out /* [n_dev] */);
+GB_API int gb_comm_destroy(gb_comm* comm);
+GB_API int gb_comm_rank(const gb_comm* comm);
+GB_API int gb_comm_world(const gb_comm* comm);
+/* In-place f64 sum over the ranks, enqueued on the communicator's ctx stream. */
+GB_API int gb_comm_allreduce_sum_f64(gb_comm* comm, double* d_buf, size_t n);
+/* The rank's shard of `full` (every rank passes the SAME full problem): a contiguous landmark range balanced by observation
+ * count, all cameras, the covisibility block structure of the whole graph.  Needs <= 2048 cameras. */
+GB_API int gb_ba_shard_create(gb_comm* comm, const gb_ba_problem* full, gb_ba_graph** out);
+/* Landmarks [lo, hi) of the full problem live on this rank; gb_ba_graph_download returns exactly those (hi-lo) x 3 points. */
+GB_API int gb_ba_shard_range(const gb_ba_graph* g, int* lo, int* hi);
+GB_API int gb_ba_shard_reduce_bytes(const gb_ba_graph* g, size_t* bytes); /* size of the per-iteration all-reduce */
+GB_API int gb_ba_shard_solve(gb_comm* comm, gb_ba_graph* g, const gb_ba_options* opt, gb_ba_result* result);
+/* Shard, solve and write poses / points back into `problem` (gpu_ms = max over the devices). */
+GB_API int gb_ba_solve_multi(int n_dev, gb_comm* const* comms, gb_ba_problem* problem, const gb_ba_options* opt,
+                             gb_ba_result* result);
 
 #ifdef __cplusplus
 }

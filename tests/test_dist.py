@@ -9,7 +9,7 @@ import pytest
 
 import oracle
 from gslam_b200 import synth
-from gslam_b200.dist import shard_landmarks
+from gslam_b200.dist import shard_bounds, shard_landmarks
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -28,6 +28,22 @@ def test_shards_partition_the_graph():
         assert np.array_equal(np.concatenate(seen_pts), np.arange(pb.n_points))   # every landmark exactly once
         assert n_obs == pb.n_obs                                                   # every edge exactly once
         assert max(loads) - min(loads) <= 2 * 6 + pb.n_obs // (10 * world)         # balanced by edge count
+
+
+def test_cabi_shard_bounds_equal_the_python_restatement():
+    """The landmark ranges ba_graph_create_impl uses (host-only hook, no device) == gslam_b200.dist.shard_bounds."""
+    import ctypes as C
+    from gslam_b200 import capi
+    L = capi.lib()
+    rng = np.random.default_rng(0)
+    for (nc, npts, opp, seed) in [(20, 500, 6, 3), (5, 37, 3, 1), (50, 2000, 5, 42), (8, 1, 8, 2)]:
+        pb = synth.synth_ba(nc, npts, obs_per_point=min(opp, nc), seed=seed)
+        op = np.ascontiguousarray(pb.obs_point[rng.permutation(pb.n_obs)], np.int32)   # edge order must not matter
+        for world in (1, 2, 3, 4, 8, 16):
+            out = np.zeros(world + 1, np.int32)
+            assert L.gb_dbg_ba_shard_bounds(pb.n_points, pb.n_obs, capi.ptr(op), world, capi.ptr(out)) == 0
+            assert out.tolist() == shard_bounds(pb, world), (nc, npts, world)
+            assert out[0] == 0 and out[-1] == pb.n_points and np.all(np.diff(out) >= 0)
 
 
 WORKER = r'''
@@ -119,8 +135,30 @@ def test_world2_nccl_global_ba_matches_oracle(tmp_path):
 
 
 @pytest.mark.gpu
+def test_single_process_multi_gpu_solve_matches_oracle():
+    """gb_comm_create_all + gb_ba_solve_multi: ONE process drives every visible GPU (1 GPU: world 1, no NCCL) -- the entry point
+    the optimizer plugin uses for `b200.devices`."""
+    import ctypes as C
+    from gslam_b200 import capi
+    from gslam_b200.api import Context, OptimzeConfig, ba_solve_multi
+    n = C.c_int(0)
+    assert capi.lib().gb_device_count(C.byref(n)) == 0
+    ndev = min(n.value, 8)
+    ctxs = [Context(k) for k in range(ndev)]
+    pb = synth.synth_ba(60, 6000, obs_per_point=8, seed=11, n_fixed=2)
+    ref = pb.copy()
+    r0 = oracle.ba_solve(ref, max_iterations=6, function_tolerance=0.0, pcg_max_iters=40)
+    r1 = ba_solve_multi(ctxs, pb, OptimzeConfig(maxIterations=6, functionTolerance=0.0, pcgMaxIterations=40))
+    assert r1.accepted == r0.accepted and abs(r1.final_cost - r0.final_cost) / r0.final_cost < 1e-5
+    assert np.abs(pb.cam_pose_wc - ref.cam_pose_wc).max() < 1e-5 * max(1.0, np.abs(ref.cam_pose_wc).max())
+    assert np.abs(pb.points - ref.points).max() / np.abs(ref.points).max() < 1e-5
+    for c in ctxs:
+        c.close()
+
+
+@pytest.mark.gpu
 def test_world1_stepwise_path_matches_oracle(tmp_path):
-    """The same stepwise kernels with world=1 (no collective): runs on a single-GPU box."""
+    """The sharded engine with world=1 (communicator without NCCL): runs on a single-GPU box."""
     script = tmp_path / "worker.py"
     script.write_text(GPU_WORKER)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=1", "--master-addr", "127.0.0.1",

@@ -30,8 +30,8 @@ def write_ba(path, pb, iters, ftol):
             f.write(np.ascontiguousarray(pb.obs_info, np.float64).tobytes())
 
 
-def run(mode, inp, out):
-    return subprocess.run([EXE, mode, LIB, inp, out], capture_output=True, text=True, timeout=300)
+def run(mode, inp, out, *svar_settings):
+    return subprocess.run([EXE, mode, LIB, inp, out, *svar_settings], capture_output=True, text=True, timeout=300)
 
 
 @needs_plugins
@@ -68,7 +68,7 @@ def test_estimator_discovery_and_failure_convention_without_gpu():
         pytest.skip("estimator plugin not built")
     n = ctypes.c_int(0)
     if capi.lib().gb_device_count(ctypes.byref(n)) == 0 and n.value > 0:
-        pytest.skip("GPU present: the kernel behind findPnP is validated by tools/gpu_pnp_check.py first (DESIGN.md section 1, row f)")
+        pytest.skip("GPU present: the no-device convention cannot be observed (findPnP on hardware: tests/test_pnp_gpu.py)")
     rng = np.random.default_rng(0)
     with tempfile.TemporaryDirectory() as d:
         with open(os.path.join(d, "in.bin"), "wb") as f:
@@ -102,6 +102,34 @@ def test_optimize_through_reference_api_matches_oracle():
         assert np.abs(poses[:, 4:7] - want.cam_pose_wc[:, 4:]).max() < 1e-5 * max(1.0, np.abs(want.cam_pose_wc[:, 4:]).max())
         assert np.abs(pts - want.points).max() < 1e-5 * np.abs(want.points).max()
         assert np.allclose(poses[:, 7], 1.0 + 0.01 * np.arange(pb.n_cams))   # SIM3 scale untouched (UPDATE_KF_SE3)
+
+
+@needs_plugins
+@pytest.mark.gpu
+def test_global_ba_sharded_over_all_gpus_through_reference_api():
+    """Optimizer::create()->optimize(BundleGraph&) (Optimizer.h:229) with the svar option b200.devices naming every visible GPU:
+    the plugin shards the landmarks itself (gb_ba_solve_multi: one NCCL all-reduce of the reduced camera system per LM iteration).
+    On a 1-GPU box the option names one device and the call must stay on the single-GPU path with the same result."""
+    import ctypes
+    n = ctypes.c_int(0)
+    assert capi.lib().gb_device_count(ctypes.byref(n)) == 0 and n.value > 0
+    ndev = min(n.value, 8)
+    pb = synth.synth_ba(n_cams=60, n_points=6000, obs_per_point=8, n_fixed=2, seed=11)
+    want = pb.copy()
+    oracle.ba_solve(want, max_iterations=6, function_tolerance=0.0, pcg_max_iters=40)
+    with tempfile.TemporaryDirectory() as d:
+        write_ba(os.path.join(d, "in.bin"), pb, 6, 0.0)
+        r = run("ba", os.path.join(d, "in.bin"), os.path.join(d, "out.bin"), "b200.devices=" + ",".join(str(k) for k in range(ndev)),
+                "b200.multi_min_obs=1000", "b200.pcg_iters=40")
+        assert r.returncode == 0, r.stderr
+        raw = open(os.path.join(d, "out.bin"), "rb").read()
+    assert struct.unpack("<i", raw[:4])[0] == 1
+    poses = np.frombuffer(raw[4:4 + 64 * pb.n_cams], np.float64).reshape(-1, 8)
+    pts = np.frombuffer(raw[4 + 64 * pb.n_cams:], np.float64).reshape(-1, 3)
+    s_ = np.sign(np.sum(poses[:, :4] * want.cam_pose_wc[:, :4], axis=1))[:, None]
+    assert np.abs(poses[:, :4] * s_ - want.cam_pose_wc[:, :4]).max() < 1e-5
+    assert np.abs(poses[:, 4:7] - want.cam_pose_wc[:, 4:]).max() < 1e-5 * max(1.0, np.abs(want.cam_pose_wc[:, 4:]).max())
+    assert np.abs(pts - want.points).max() < 1e-5 * np.abs(want.points).max()
 
 
 @needs_plugins

@@ -38,6 +38,7 @@ if rank == 0:
     sweep_bytes = 168 * n_obs + 96 * pb.n_points + 272 * pb.n_cams
     print(json.dumps({"workload": f"global BA {a.cams} cams / {a.points} pts / {n_obs} obs, {a.iters} LM it, PCG cap {a.pcg}", "n_gpus": world,
                       "ms_total": best, "ms_per_lm_iteration": best / a.iters, "final_cost": res.final_cost, "initial_cost": res.initial_cost,
-                      "allreduce_bytes_per_iteration": d.reduce_bytes + 64, "sweep_algorithmic_bytes": sweep_bytes}))
+                      "allreduce_bytes_per_iteration": d.reduce_bytes + 8, "sweep_algorithmic_bytes": sweep_bytes,
+                      "pcg_iterations": res.pcg_iterations, "accepted": res.accepted}))
 d.close()
 if world > 1: dist.destroy_process_group()
