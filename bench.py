@@ -216,7 +216,7 @@ def main():
     if sampler:
         sampler.start()  # before the warm-up: nvidia-smi needs a few hundred ms to deliver its first sample
     ctx = Context(local)    # tracking: extract + match
-    ctx_m = Context(local)  # mapping: local BA
+    ctx_m = Context(local, high_priority=True)  # mapping: local BA (its few-CTA kernels go ahead of the tracking grids)
     cfg = ctx.orb_cfg(nfeatures=NKP)
     ba_cfg = OptimzeConfig(maxIterations=BA_ITERS, functionTolerance=0.0, pcgMaxIterations=PCG_ITERS, pcgTolerance=1e-10)
 
@@ -255,14 +255,32 @@ def main():
             step_serial(k)
 
     def run_pipelined(k0, n):
-        """n frames; BA(k) waits for match(k); extract(k+1) is enqueued before the host blocks in solve(k)."""
-        track(k0)
+        """n frames from two host threads, like a SLAM's tracking and mapping threads: the tracking thread enqueues extract(k) +
+        match(k) (no host synchronisation: the matcher reads the keypoint counts on the device) and orders the mapping stream
+        after match(k); the mapping thread runs BA(k) (one host synchronisation per window: the LM scalars come back with it)."""
+        qq: queue.Queue = queue.Queue(maxsize=2)
+        err = []
+
+        def mapper():
+            try:
+                while True:
+                    k = qq.get()
+                    if k is None:
+                        return
+                    graph_p.reset()
+                    graph_p.solve(ba_cfg)
+            except Exception as e:
+                err.append(e)
+        th = threading.Thread(target=mapper, daemon=True)
+        th.start()
         for k in range(k0, k0 + n):
-            ctx_m.wait_for(ctx)          # BA(k) after match(k)
-            if k + 1 < k0 + n:
-                track(k + 1)             # overlaps BA(k) on the device
-            graph_p.reset()
-            graph_p.solve(ba_cfg)        # (one host synchronisation per window: the LM scalars come back with it)
+            track(k)
+            ctx_m.wait_for(ctx)          # BA(k) after match(k); extract(k+1) does not wait for BA(k)
+            qq.put(k)
+        qq.put(None)
+        th.join()
+        if err:
+            raise err[0]
         ctx.wait_for(ctx_m)              # the timing events live on the tracking stream
 
     def timed_blocks(run, steps):

@@ -64,10 +64,10 @@ def _problem_c(pb: BAProblem):
 class Context:
     """One device + one stream (gb_ctx)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, high_priority: bool = False):
         self._lib = capi.lib()
         h = C.c_void_p()
-        rc = self._lib.gb_ctx_create(device, C.byref(h))
+        rc = self._lib.gb_ctx_create_priority(device, 1 if high_priority else 0, C.byref(h))
         if rc != capi.GB_OK:
             raise GbError(rc, self._lib.gb_last_error(None).decode())
         self._h = h
@@ -154,6 +154,16 @@ class Context:
         self._check(self._lib.gb_match_hamming(self._h, ptr(q), nq, ptr(t), nt, ptr(idx), ptr(d1), ptr(d2)))
         return idx, d1, d2
 
+    def match_stereo(self, kps_left, desc_left, kps_right, desc_right, band=2.0, min_disp=0.0, max_disp=1e9):
+        """Rectified-stereo row-band match (left = query): (best_idx, best_dist, second_dist); idx -1 when no candidate."""
+        kl = np.ascontiguousarray(kps_left, KP_DTYPE); kr = np.ascontiguousarray(kps_right, KP_DTYPE)
+        dl = np.ascontiguousarray(desc_left, np.uint8).reshape(-1, 32); dr = np.ascontiguousarray(desc_right, np.uint8).reshape(-1, 32)
+        nl, nr = dl.shape[0], dr.shape[0]
+        idx = np.empty(nl, np.int32); d1 = np.empty(nl, np.int32); d2 = np.empty(nl, np.int32)
+        self._check(self._lib.gb_match_stereo(self._h, ptr(kl), ptr(dl), nl, ptr(kr), ptr(dr), nr, band, min_disp, max_disp,
+                                              ptr(idx), ptr(d1), ptr(d2)))
+        return idx, d1, d2
+
     # ---- BA ----------------------------------------------------------------------------------------------------------
     def pnp_ransac(self, xyz, xy, threshold=0.01, confidence=0.99, max_hypotheses=1024, seed=1):
         """Estimator::findPnP (P3P + RANSAC + refinement): -> (pose_cw[7] {qx,qy,qz,qw,tx,ty,tz}, mask[n] uint8, PnpStats)."""
@@ -228,6 +238,9 @@ class Features:
 
     def match(self, train: "Features"):
         self.ctx._check(self.ctx._lib.gb_match_features(self.ctx._h, self._h, train._h))
+
+    def match_stereo(self, right: "Features", band=2.0, min_disp=0.0, max_disp=1e9):
+        self.ctx._check(self.ctx._lib.gb_match_stereo_features(self.ctx._h, self._h, right._h, band, min_disp, max_disp))
 
     def matches(self):
         n = C.c_int(self.capacity)

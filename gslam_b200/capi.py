@@ -61,6 +61,7 @@ _SIGNATURES = [
     ("gb_version", C.c_int, []),
     ("gb_device_count", C.c_int, [C.POINTER(C.c_int)]),
     ("gb_ctx_create", C.c_int, [C.c_int, C.POINTER(_VP)]),
+    ("gb_ctx_create_priority", C.c_int, [C.c_int, C.c_int, C.POINTER(_VP)]),
     ("gb_ctx_destroy", C.c_int, [_VP]),
     ("gb_last_error", C.c_char_p, [_VP]),
     ("gb_ctx_stream", _VP, [_VP]),
@@ -80,6 +81,8 @@ _SIGNATURES = [
     ("gb_match_hamming", C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, _VP, _VP, _VP]),
     ("gb_match_features", C.c_int, [_VP, _VP, _VP]),
     ("gb_match_download", C.c_int, [_VP, _VP, _VP, _VP, _VP, C.POINTER(C.c_int)]),
+    ("gb_match_stereo", C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, C.c_int, C.c_float, C.c_float, C.c_float, _VP, _VP, _VP]),
+    ("gb_match_stereo_features", C.c_int, [_VP, _VP, _VP, C.c_float, C.c_float, C.c_float]),
     ("gb_ba_options_default", None, [C.POINTER(BaOptions)]),
     ("gb_ba_solve", C.c_int, [_VP, C.POINTER(BaProblem), C.POINTER(BaOptions), C.POINTER(BaResult)]),
     ("gb_ba_pnp", C.c_int, [_VP, C.c_int, _VP, _VP, _VP, C.c_int, _VP, C.POINTER(BaOptions), C.POINTER(BaResult)]),

@@ -437,6 +437,129 @@ __global__ void __launch_bounds__(128) ba_schur_blocks_kernel(BaDev g, double* _
   }
 }
 
+// ---- K7a (large graphs): Schur complement by LANDMARK CHUNKS -----------------------------------------------------------------------
+// The block-gather kernel above walks, for every block (i,i'), camera i's whole observation list: fine for a 50-keyframe window,
+// but at global-BA size (500 cameras x 2000 observations each, ~5000 upper blocks) it re-reads every W block ~10 times from L2
+// (794 us per LM iteration at config 5).  Here the landmarks are cut (on the host, once per graph) into chunks of consecutive
+// landmarks that together see at most 16 cameras; a CTA owns a chunk, thread s owns ONE block slot (la <= lb) of the chunk's
+// 16 x 16 upper triangle and walks the chunk's landmarks in order, accumulating Y_a W_b' (Y = W V^-1) for the landmarks both
+// cameras observe -- registers only, no atomics, fixed order.  Every W block is read once per slot that needs it and those reads
+// hit L1 (the ~10 blocks of a landmark are shared by the whole CTA).  The per-chunk partial blocks go to a staging area and
+// ba_schur_reduce_kernel folds them per block in ascending chunk order: bit-reproducible.
+// Slots are numbered column-major over the upper triangle (slot = lb(lb+1)/2 + la) so that a chunk that only sees n cameras keeps
+// its work in the first n(n+1)/2 threads and the remaining warps skip every landmark.
+constexpr int kChunkCams = 16, kChunkSlots = kChunkCams * (kChunkCams + 1) / 2, kChunkThreads = 160, kChunkBatch = 4;
+
+__global__ void __launch_bounds__(kChunkThreads) ba_schur_chunks_kernel(BaDev g) {
+  if (g.sc->stop) return;
+  // per batch of kChunkBatch landmarks: W and Y = W V^-1 of every observing camera, addressed by LOCAL camera index
+  __shared__ __align__(16) double sW[2][kChunkBatch][kChunkCams][18];
+  __shared__ __align__(16) double sY[2][kChunkBatch][kChunkCams][18];
+  __shared__ unsigned int s_mask[2][kChunkBatch];
+  __shared__ int s_lm[2][kChunkBatch];
+  const int s = threadIdx.x, chunk = blockIdx.x;
+  int lb = 0;
+  while (lb < kChunkCams - 1 && (lb + 1) * (lb + 2) / 2 <= s) ++lb;
+  const int la = s - lb * (lb + 1) / 2;
+  const bool slot = s < kChunkSlots;
+  const unsigned int need = slot ? ((1u << la) | (1u << lb)) : 0xffffffffu;
+  const int t0 = g.sp_pt0[chunk], t1 = g.sp_pt0[chunk + 1];
+  double acc[36], ga[6];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) ga[k] = 0.0;
+  bool used = false;
+  int buf = 0;
+  for (int tb = t0; tb < t1; tb += kChunkBatch, buf ^= 1) {
+    const int nb = min(kChunkBatch, t1 - tb);
+    // ---- stage W (coalesced: the blocks of a landmark are contiguous), masks, landmark ids
+    if (s < nb) {
+      s_mask[buf][s] = g.sp_mask[tb + s];
+      s_lm[buf][s] = g.sp_order[tb + s];
+    }
+    for (int w = s; w < nb * kChunkCams * 18; w += kChunkThreads) {
+      const int b = w / (kChunkCams * 18), r = w - b * (kChunkCams * 18), l = r / 18, k = r - 18 * l;
+      const unsigned int m = g.sp_mask[tb + b];
+      if ((m >> l) & 1u) {
+        const int j = g.sp_order[tb + b];
+        sW[buf][b][l][k] = g.W[18 * (size_t)(g.pt_off[j] + __popc(m & ((1u << l) - 1u))) + k];
+      }
+    }
+    __syncthreads();
+    // ---- Y = W V^-1 : one thread per (landmark, camera, row)
+    for (int w = s; w < nb * kChunkCams * 6; w += kChunkThreads) {
+      const int b = w / (kChunkCams * 6), r = w - b * (kChunkCams * 6), l = r / 6, a = r - 6 * l;
+      if ((s_mask[buf][b] >> l) & 1u) {
+        const double* Vi = g.Vinv + 9 * (size_t)s_lm[buf][b];
+        const double w0 = sW[buf][b][l][a * 3], w1 = sW[buf][b][l][a * 3 + 1], w2 = sW[buf][b][l][a * 3 + 2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sY[buf][b][l][a * 3 + c] = w0 * Vi[c] + w1 * Vi[3 + c] + w2 * Vi[6 + c];
+      }
+    }
+    __syncthreads();
+    // ---- accumulate: slot (la, lb) += Y_la W_lb'   (the other buffer is being refilled by nobody yet: one barrier pair per batch,
+    //      the double buffer lets the next batch's staging start while slow warps still accumulate)
+    if (slot) {
+      for (int b = 0; b < nb; ++b) {
+        if ((s_mask[buf][b] & need) != need) continue;
+        used = true;
+        const double2* Y2 = reinterpret_cast<const double2*>(&sY[buf][b][la][0]);
+        const double2* W2 = reinterpret_cast<const double2*>(&sW[buf][b][lb][0]);
+        double Y[18], wb[18];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { const double2 v = Y2[k]; Y[2 * k] = v.x; Y[2 * k + 1] = v.y; }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { const double2 v = W2[k]; wb[2 * k] = v.x; wb[2 * k + 1] = v.y; }
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+          for (int c = 0; c < 6; ++c) acc[a * 6 + c] += Y[a * 3] * wb[c * 3] + Y[a * 3 + 1] * wb[c * 3 + 1] + Y[a * 3 + 2] * wb[c * 3 + 2];
+        if (la == lb) {
+          const double* gp = g.gp + 3 * (size_t)s_lm[buf][b];
+          const double g0 = gp[0], g1 = gp[1], g2 = gp[2];
+#pragma unroll
+          for (int a = 0; a < 6; ++a) ga[a] += Y[a * 3] * g0 + Y[a * 3 + 1] * g1 + Y[a * 3 + 2] * g2;
+        }
+      }
+    }
+  }
+  if (!slot || !used) return;  // (the host lists exactly the slots some landmark of the chunk touches)
+  double2* dst = reinterpret_cast<double2*>(g.sp_stageS + ((size_t)chunk * kChunkSlots + s) * 36);
+#pragma unroll
+  for (int k = 0; k < 18; ++k) dst[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
+  if (la == lb) {
+    double* dg = g.sp_stageG + ((size_t)chunk * kChunkCams + la) * 6;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dg[k] = ga[k];
+  }
+}
+
+// one 64-thread CTA per upper block: S_blk = [U_i on the diagonal] - sum of the chunk partials (ascending chunk order), written with
+// its transpose; the diagonal CTAs also produce g~_i and diag U (same outputs as ba_schur_blocks_kernel)
+__global__ void __launch_bounds__(64) ba_schur_reduce_kernel(BaDev g, double* __restrict__ buf) {
+  if (g.sc->stop) return;
+  const int u = blockIdx.x, k = threadIdx.x;
+  const int blk = g.s_upper[u];
+  const int i = g.s_brow[blk], i2 = g.s_col[blk];
+  const bool diag = i == i2;
+  if (k < 36) {
+    double sum = 0.0;
+    for (int t = g.sp_boff[u]; t < g.sp_boff[u + 1]; ++t) sum += g.sp_stageS[(size_t)g.sp_bidx[t] * 36 + k];
+    const int a = k / 6, b = k - 6 * a;
+    const double v = (diag ? g.U[36 * i + k] : 0.0) - sum;
+    g.Sb[36 * (size_t)blk + k] = v;
+    if (!diag) g.Sb[36 * (size_t)g.s_tidx[blk] + b * 6 + a] = v;
+  } else if (diag && k < 42) {
+    const int a = k - 36;
+    double sum = 0.0;
+    for (int t = g.sp_coff[i]; t < g.sp_coff[i + 1]; ++t) sum += g.sp_stageG[(size_t)g.sp_cidx[t] * 6 + a];
+    const size_t n6 = g.n6;
+    buf[g.r_gt + 6 * i + a] = g.gc[6 * i + a] - sum;
+    buf[g.r_gt + n6 + 6 * i + a] = g.U[36 * i + a * 7];
+  }
+}
+
 // test hook helper: scatter the block-CSR values into the dense S of `buf`
 __global__ void ba_densify_kernel(BaDev g, double* __restrict__ buf) {
   const size_t n6 = g.n6, nS = n6 * n6;
@@ -1581,9 +1704,11 @@ void gb_ba_options_default(gb_ba_options* o) {
 
 int gb_ba_graph_destroy(gb_ctx* ctx, gb_ba_graph* g) {
   if (!g) return GB_OK;
-  if (g->bcsr_cta_cam) {
+  if (g->bcsr_cta_cam || g->sp_alloc) {
     if (ctx) { CtxLock lk(ctx); cudaStreamSynchronize(ctx->stream); }
-    ba_pcg_bcsr_free(g);
+    if (g->bcsr_cta_cam) ba_pcg_bcsr_free(g);
+    if (g->sp_alloc) cudaFree(g->sp_alloc);
+    g->sp_alloc = nullptr;
   }
   if (g->from_arena) {
     if (ctx) ctx->ba_arena_busy = false;
@@ -1603,6 +1728,121 @@ int gb_ba_graph_create(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out) 
 }
 
 }  // extern "C"
+
+// Landmark-chunk plan of the Schur complement (see ba_schur_chunks_kernel).  Returns false when it does not apply (a landmark with
+// more than 16 observers, no block structure): the block-gather kernel is used then.
+static bool ba_schur_plan(gb_ctx* ctx, gb_ba_graph* g, int np, const std::vector<int>& pt_off, const std::vector<int>& scam, const uint8_t* pfree_host,
+                          const std::vector<int>& s_rowptr, const std::vector<int>& s_col, const std::vector<int>& s_upper) {
+  BaDev& d = g->d;
+  d.sp_nchunks = 0;
+  if (np <= 0 || d.s_nnzb <= 0 || d.nc <= 0) return false;
+  // landmarks in the order of the trajectory (first observing camera, then last, then id): consecutive landmarks then share
+  // their cameras whatever order the caller numbered them in; fixed / unobserved landmarks contribute nothing and are left out
+  std::vector<int> ord;
+  ord.reserve(np);
+  for (int j = 0; j < np; ++j) {
+    const int a = pt_off[j], b = pt_off[j + 1];
+    if (b <= a || (pfree_host && !pfree_host[j])) continue;
+    if (b - a > kChunkCams) return false;
+    ord.push_back(j);
+  }
+  if (ord.empty()) return false;
+  std::sort(ord.begin(), ord.end(), [&](int x, int y) {
+    const int fx = scam[pt_off[x]], fy = scam[pt_off[y]];
+    if (fx != fy) return fx < fy;
+    const int lx = scam[pt_off[x + 1] - 1], ly = scam[pt_off[y + 1] - 1];
+    if (lx != ly) return lx < ly;
+    return x < y;
+  });
+  const int nl = (int)ord.size();
+  const int lmax = std::min(64, std::max(8, nl / (4 * std::max(ctx->sm_count, 1))));
+  std::vector<int> ch_pt0, ch_cams;  // ch_cams: 16 per chunk, ascending, -1 padded
+  std::vector<unsigned short> mask((size_t)nl, 0);
+  std::vector<int> cur, merged;  // sorted cameras of the open chunk
+  int open_from = 0;
+  auto close = [&](int upto) {
+    ch_pt0.push_back(open_from);
+    for (int k = 0; k < kChunkCams; ++k) ch_cams.push_back(k < (int)cur.size() ? cur[k] : -1);
+    open_from = upto;
+    cur.clear();
+  };
+  for (int t = 0; t < nl; ++t) {
+    const int j = ord[t], a = pt_off[j], b = pt_off[j + 1];
+    merged.clear();
+    std::set_union(cur.begin(), cur.end(), scam.begin() + a, scam.begin() + b, std::back_inserter(merged));  // (edges are camera-sorted, no duplicates)
+    if ((int)merged.size() > kChunkCams || t - open_from >= lmax) {
+      close(t);
+      merged.assign(scam.begin() + a, scam.begin() + b);
+    }
+    cur.swap(merged);
+  }
+  close(nl);
+  ch_pt0.push_back(nl);
+  const int nch = (int)ch_pt0.size() - 1;
+  // masks + the slots each chunk really touches
+  std::vector<std::vector<int>> blk_contrib(s_upper.size()), cam_contrib((size_t)d.nc);
+  std::vector<int> upper_of((size_t)d.s_nnzb, -1);
+  for (size_t u = 0; u < s_upper.size(); ++u) upper_of[s_upper[u]] = (int)u;
+  std::vector<uint8_t> used(kChunkSlots);
+  for (int c = 0; c < nch; ++c) {
+    const int* cams = &ch_cams[(size_t)c * kChunkCams];
+    std::fill(used.begin(), used.end(), 0);
+    for (int t = ch_pt0[c]; t < ch_pt0[c + 1]; ++t) {
+      const int j = ord[t], a = pt_off[j], b = pt_off[j + 1];
+      unsigned int m = 0;
+      int l = 0;
+      for (int e = a; e < b; ++e) {
+        while (cams[l] != scam[e]) ++l;
+        m |= 1u << l;
+      }
+      mask[t] = (unsigned short)m;
+      for (int lb = 0; lb < kChunkCams; ++lb)
+        if ((m >> lb) & 1)
+          for (int la = 0; la <= lb; ++la)
+            if ((m >> la) & 1) used[lb * (lb + 1) / 2 + la] = 1;
+    }
+    for (int lb = 0; lb < kChunkCams; ++lb)
+      for (int la = 0; la <= lb; ++la) {
+        if (!used[lb * (lb + 1) / 2 + la]) continue;
+        const int i = cams[la], i2 = cams[lb];
+        int t = s_rowptr[i];
+        while (t < s_rowptr[i + 1] && s_col[t] != i2) ++t;
+        if (t >= s_rowptr[i + 1]) return false;  // (cannot happen: the block structure covers every co-observed pair)
+        blk_contrib[upper_of[t]].push_back(c * kChunkSlots + lb * (lb + 1) / 2 + la);
+        if (la == lb) cam_contrib[i].push_back(c * kChunkCams + la);
+      }
+  }
+  std::vector<int> boff(s_upper.size() + 1, 0), bidx, coff((size_t)d.nc + 1, 0), cidx;
+  for (size_t u = 0; u < s_upper.size(); ++u) { bidx.insert(bidx.end(), blk_contrib[u].begin(), blk_contrib[u].end()); boff[u + 1] = (int)bidx.size(); }
+  for (int i = 0; i < d.nc; ++i) { cidx.insert(cidx.end(), cam_contrib[i].begin(), cam_contrib[i].end()); coff[i + 1] = (int)cidx.size(); }
+  // one device allocation: plan arrays + staging
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_pt0 = al((size_t)(nch + 1) * 4), b_mask = al((size_t)nl * 2), b_ord = al((size_t)nl * 4), b_boff = al(boff.size() * 4), b_bidx = al(bidx.size() * 4 + 4),
+               b_coff = al(coff.size() * 4), b_cidx = al(cidx.size() * 4 + 4), b_stS = al((size_t)nch * kChunkSlots * 36 * 8),
+               b_stG = al((size_t)nch * kChunkCams * 6 * 8);
+  uint8_t* base = nullptr;
+  if (cudaMalloc((void**)&base, b_pt0 + b_mask + b_ord + b_boff + b_bidx + b_coff + b_cidx + b_stS + b_stG) != cudaSuccess) { cudaGetLastError(); return false; }
+  g->sp_alloc = base;
+  size_t off = 0;
+  auto up = [&](const void* src, size_t bytes, size_t padded) {
+    uint8_t* p = base + off;
+    off += padded;
+    if (bytes) cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    return p;
+  };
+  d.sp_pt0 = (const int*)up(ch_pt0.data(), (size_t)(nch + 1) * 4, b_pt0);
+  d.sp_mask = (const unsigned short*)up(mask.data(), (size_t)nl * 2, b_mask);
+  d.sp_order = (const int*)up(ord.data(), (size_t)nl * 4, b_ord);
+  d.sp_boff = (const int*)up(boff.data(), boff.size() * 4, b_boff);
+  d.sp_bidx = (const int*)up(bidx.data(), bidx.size() * 4, b_bidx);
+  d.sp_coff = (const int*)up(coff.data(), coff.size() * 4, b_coff);
+  d.sp_cidx = (const int*)up(cidx.data(), cidx.size() * 4, b_cidx);
+  d.sp_stageS = (double*)(base + off); off += b_stS;
+  d.sp_stageG = (double*)(base + off); off += b_stG;
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return false; }  // (the host vectors die with this frame)
+  d.sp_nchunks = nch;
+  return true;
+}
 
 // first landmark of rank r's shard: the first landmark whose edge prefix count reaches r/world of the edges (monotone in r)
 static int ba_shard_bound(const std::vector<int>& pt_off, int n_obs, int n_points, int r, int world) {
@@ -1861,7 +2101,10 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   }
   GB_CHECK(gb_ba_graph_reset(ctx, g));
   ba_pick_pcg(ctx, g);
-  if (!g->pcg_sparse && d.s_nnzb > 0) GB_CHECK(ba_pcg_bcsr_plan(ctx, g, s_rowptr.data()));
+  if (!g->pcg_sparse && d.s_nnzb > 0) {
+    GB_CHECK(ba_pcg_bcsr_plan(ctx, g, s_rowptr.data()));
+    if (!getenv("GB_BA_NO_SCHUR_CHUNKS")) ba_schur_plan(ctx, g, np, pt_off, scam, h + o_pf, s_rowptr, s_col, s_upper);  // (optional: the block-gather kernel otherwise)
+  }
   if (compact_only && !g->pcg_bcsr) {
     gb_set_error(ctx, "gb_ba: the sharded solve needs the block-CSR reduced system (<= %d cameras)", kMaxBlockCams);
     return GB_ERR_INVALID;
@@ -1984,7 +2227,12 @@ int gb_ba_graph_reduce_local(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
     ba_prepare_schur_kernel<<<nblk, 256, 0, s>>>(d, buf, csr_only ? 0 : 1); GB_LAUNCH_CHECK(ctx);
   }
   if (have_blocks) {
-    ba_schur_blocks_kernel<<<d.s_nupper, 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+    if (d.sp_nchunks > 0) {
+      ba_schur_chunks_kernel<<<d.sp_nchunks, kChunkThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
+      ba_schur_reduce_kernel<<<d.s_nupper, 64, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+    } else {
+      ba_schur_blocks_kernel<<<d.s_nupper, 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
+    }
     if (!csr_only) { ba_densify_fill_kernel<<<gb_div_up(d.s_nnzb * 36, 256), 256, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx); }
   } else if (d.no > 0 && d.nc > 0) {
     ba_schur_accum_kernel<<<gb_div_up(d.no, 128), 128, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
@@ -2011,7 +2259,12 @@ int ba_reduce_local_compact(gb_ctx* ctx, gb_ba_graph* g, double* rbuf) {
     const int nblk = (int)std::min<size_t>(std::max<size_t>(((size_t)d.np + 255) / 256, 1), (size_t)ctx->sm_count * 8);
     ba_prepare_schur_kernel<<<nblk, 256, 0, s>>>(d, rbuf, 0); GB_LAUNCH_CHECK(ctx);
   }
-  ba_schur_blocks_kernel<<<d.s_nupper, 128, 0, s>>>(d, rbuf); GB_LAUNCH_CHECK(ctx);
+  if (d.sp_nchunks > 0) {
+    ba_schur_chunks_kernel<<<d.sp_nchunks, kChunkThreads, 0, s>>>(d); GB_LAUNCH_CHECK(ctx);
+    ba_schur_reduce_kernel<<<d.s_nupper, 64, 0, s>>>(d, rbuf); GB_LAUNCH_CHECK(ctx);
+  } else {
+    ba_schur_blocks_kernel<<<d.s_nupper, 128, 0, s>>>(d, rbuf); GB_LAUNCH_CHECK(ctx);
+  }
   return GB_OK;
 }
 

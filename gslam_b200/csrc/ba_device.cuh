@@ -44,6 +44,14 @@ struct BaDev {
   // where [g~ | diag U | cost] start inside the reduced-system buffer handed to a kernel, in doubles: n6*n6 for the dense
   // layout [S (6N x 6N) | ...], s_nnzb*36 for the compact layout [Sb | ...] of the multi-GPU path (set per launch)
   size_t r_gt;
+  // landmark-chunk Schur plan (large graphs; ba.cu: ba_schur_chunks_kernel + ba_schur_reduce_kernel), or sp_nchunks == 0
+  int sp_nchunks;
+  const int* sp_pt0;             // [nchunks+1] range of each chunk in the trajectory-sorted landmark list sp_order
+  const int* sp_order;           // [live landmarks] landmark ids sorted by (first camera, last camera, id)
+  const unsigned short* sp_mask; // [live landmarks] (same positions) which of the chunk's (<= 16, ascending) cameras observe it
+  double *sp_stageS, *sp_stageG; // [nchunks][136][36], [nchunks][16][6] per-chunk partial sums
+  const int *sp_boff, *sp_bidx;  // CSR over the UPPER blocks (order of s_upper): staging slots (chunk*136+slot) contributing, ascending
+  const int *sp_coff, *sp_cidx;  // CSR over cameras: staging rows (chunk*16+local cam) contributing to g~
   // linearisation
   double *V, *gp, *Vinv, *W, *U, *gc, *cost_pt, *cost_pt_new;
   // camera pass split: cam_split CTAs per camera, partial [27] sums + a per-camera ticket (the last CTA folds them in order)

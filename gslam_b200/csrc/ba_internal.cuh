@@ -30,7 +30,7 @@ struct gb_ba_graph {
   // multi-CTA block-CSR PCG (ba_pcg_bcsr.cu): plan made at graph creation when the block structure exists and the single-CTA
   // kernel does not apply
   bool pcg_bcsr = false;
-  int bcsr_ctas = 0, bcsr_K = 0, bcsr_in_smem = 0, bcsr_max_cams = 0, bcsr_max_blocks = 0;
+  int bcsr_ctas = 0, bcsr_K = 0, bcsr_in_smem = 0, bcsr_max_cams = 0, bcsr_max_blocks = 0, bcsr_cluster = 0, bcsr_blk_stride = 37;
   size_t bcsr_smem = 0;
   int* bcsr_cta_cam = nullptr;   // device [bcsr_ctas + 1]: first camera of each CTA's block-row range (base of one allocation)
   double* bcsr_part = nullptr;   // device [bcsr_ctas * 2]: per-CTA (gamma, delta) partials
@@ -38,6 +38,7 @@ struct gb_ba_graph {
   unsigned int* bcsr_bar = nullptr;  // device: grid barrier counter
   double* rbuf = nullptr;        // device: compact reduced system [Sb (nnzb*36) | g~ | diag U | cost | pad]
   size_t rbuf_doubles = 0;
+  void* sp_alloc = nullptr;      // device allocation holding the landmark-chunk Schur plan + staging (BaDev::sp_*), or null
   // landmark shard (multi-GPU global BA): this graph holds landmarks [shard_lo, shard_hi) of the caller's problem
   int shard_lo = 0, shard_hi = 0, shard_rank = 0, shard_world = 1;
 };

@@ -17,6 +17,8 @@
 //   every CTA): run-to-run and rank-to-rank bit-reproducible.
 #include "ba_internal.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <mutex>
 
@@ -32,7 +34,7 @@ struct BcsrArgs {
   double* part;         // [2G] per-CTA (gamma, delta)
   double* u_glob;       // [n6]
   unsigned int* bar;    // grid barrier counter (zeroed before the launch)
-  int K, in_smem, maxit, max_cams, max_blocks;
+  int K, in_smem, maxit, max_cams, max_blocks, blk_stride;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -54,11 +56,17 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ta
   __syncthreads();
 }
 
+// CLUSTER = true: the whole grid is ONE thread-block cluster (<= 16 CTAs, chosen on the host when S fits their shared memory):
+// u and the per-CTA (gamma, delta) partials travel through distributed shared memory and the two barriers per iteration are
+// hardware cluster barriers (~0.2 us) instead of a global-memory ticket barrier (~1-1.5 us with 148 CTAs).
+template <bool CLUSTER>
 __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, double* __restrict__ rbuf, BcsrArgs a) {
+  namespace cg = cooperative_groups;
   if (g.sc->stop) return;  // uniform over the grid
   extern __shared__ __align__(16) double sm[];
   __shared__ double s_warp[2][kBcsrThreads / 32];
   __shared__ double s_scal[4];  // gamma, delta (this iteration), broadcast
+  __shared__ double s_cpart[2][16];  // CLUSTER: (gamma, delta) partials of every CTA of the cluster, written by the peers
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x, b = blockIdx.x;
   const int n6 = g.n6;
   const int cam0 = a.cta_cam[b], cam1 = a.cta_cam[b + 1], ncl = cam1 - cam0, rows = 6 * ncl;
@@ -70,7 +78,7 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
   double *vr = vec, *vp = vec + vstride, *vs = vec + 2 * vstride, *vx = vec + 3 * vstride, *vw = vec + 4 * vstride, *vu = vec + 5 * vstride;
   double* Minv = vec + 6 * vstride;                            // [max_cams][36]
   double* Ssm = Minv + 36 * a.max_cams;                        // [max_blocks][37] when in_smem
-  int* col = reinterpret_cast<int*>(Ssm + (a.in_smem ? (size_t)a.max_blocks * kBlkStride : 0));  // [max_blocks]
+  int* col = reinterpret_cast<int*>(Ssm + (a.in_smem ? (size_t)a.max_blocks * a.blk_stride : 0));  // [max_blocks]
   int* rp = col + a.max_blocks;                                // [max_cams + 1]
   const size_t r_gt = (size_t)g.s_nnzb * 36;
   const double lambda = g.sc->lambda, tol = g.sc->pcg_tol;
@@ -81,11 +89,11 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
   double* Sg = rbuf + (size_t)blk0 * 36;  // the owned blocks in global memory
   if (a.in_smem) {
     const int n = nb * 36;
-    for (int t = tid; t < n; t += kBcsrThreads) Ssm[(t / 36) * kBlkStride + (t % 36)] = __ldcg(Sg + t);
+    for (int t = tid; t < n; t += kBcsrThreads) Ssm[(t / 36) * a.blk_stride + (t % 36)] = __ldcg(Sg + t);
   }
   __syncthreads();
   const double* Sp = a.in_smem ? Ssm : Sg;
-  const int bstride = a.in_smem ? kBlkStride : 36;
+  const int bstride = a.in_smem ? a.blk_stride : 36;
   // ---- B. Marquardt damping of the diagonal (fixed dofs: unit diagonal), then the 6x6 block-Jacobi inverses ----
   for (int r = tid; r < rows; r += kBcsrThreads) {
     const int c = r / 6, comp = r - 6 * c, cam = cam0 + c;
@@ -93,7 +101,7 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
     for (int t = rp[c]; t < rp[c + 1]; ++t)
       if (col[t] == cam) diag = t;
     if (diag >= 0) {
-      double* e = (a.in_smem ? Ssm + (size_t)diag * kBlkStride : Sg + (size_t)diag * 36) + comp * 7;
+      double* e = (a.in_smem ? Ssm + (size_t)diag * a.blk_stride : Sg + (size_t)diag * 36) + comp * 7;
       const double du = __ldcg(rbuf + r_gt + n6 + 6 * cam + comp);
       *e = ((g.dof[cam] >> comp) & 1) ? *e + lambda * clampd(du) : 1.0;
     }
@@ -128,12 +136,26 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
 #pragma unroll
       for (int k = 0; k < 6; ++k) s += Minv[36 * c + comp * 6 + k] * vr[6 * c + k];
       vu[r] = s;
-      a.u_glob[6 * cam0 + r] = s;
+      if (!CLUSTER) a.u_glob[6 * cam0 + r] = s;
+    }
+    if (CLUSTER) {  // push the owned rows into every CTA's copy of u (pairs of rows: 16-byte remote stores)
+      __syncthreads();
+      cg::cluster_group cluster = cg::this_cluster();
+      const int pairs = rows >> 1;  // rows = 6 * cameras: even
+      for (int t = tid; t < pairs * G; t += kBcsrThreads) {
+        const int peer = t / pairs, q = t - peer * pairs;
+        double* pu = cluster.map_shared_rank(u_full, peer);
+        *reinterpret_cast<double2*>(pu + 6 * cam0 + 2 * q) = make_double2(vu[2 * q], vu[2 * q + 1]);
+      }
     }
   };
-  apply_minv_publish();
   unsigned int target = 0;
-  grid_barrier(a.bar, target, G);
+  auto barrier = [&]() {
+    if (CLUSTER) cg::this_cluster().sync();
+    else grid_barrier(a.bar, target, G);
+  };
+  apply_minv_publish();
+  barrier();
 
   const int K = a.K, sub = tid & (K - 1), groups = kBcsrThreads / K;
   double gamma_prev = 0.0, gamma0 = 0.0, alpha_prev = 1.0;
@@ -141,8 +163,10 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
   bool first = true;
   for (;;) {
     // ---- C. w = S u on the owned rows ----
-    for (int t = tid; t < n6; t += kBcsrThreads) u_full[t] = __ldcg(a.u_glob + t);
-    __syncthreads();
+    if (!CLUSTER) {
+      for (int t = tid; t < n6; t += kBcsrThreads) u_full[t] = __ldcg(a.u_glob + t);
+      __syncthreads();
+    }
     double pg = 0.0, pd = 0.0;
     for (int rbase = 0; rbase < rows; rbase += groups) {  // (uniform trip count: whole groups of K lanes share a row)
       const int r = rbase + tid / K;
@@ -171,17 +195,31 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
     }
     if (lane == 0) { s_warp[0][warp] = pg; s_warp[1][warp] = pd; }
     __syncthreads();
-    if (tid == 0) {
+    if (CLUSTER) {
+      if (tid < G) {  // thread p hands this CTA's partial pair to peer p
+        double sg = 0.0, sd = 0.0;
+#pragma unroll
+        for (int w = 0; w < kBcsrThreads / 32; ++w) { sg += s_warp[0][w]; sd += s_warp[1][w]; }
+        cg::cluster_group cluster = cg::this_cluster();
+        double* pp = cluster.map_shared_rank(&s_cpart[0][0], tid);
+        pp[b] = sg;
+        pp[16 + b] = sd;
+      }
+    } else if (tid == 0) {
       double sg = 0.0, sd = 0.0;
 #pragma unroll
       for (int w = 0; w < kBcsrThreads / 32; ++w) { sg += s_warp[0][w]; sd += s_warp[1][w]; }
       a.part[2 * b] = sg;
       a.part[2 * b + 1] = sd;
     }
-    grid_barrier(a.bar, target, G);
+    barrier();
     if (warp == 0) {
       double sg = 0.0, sd = 0.0;
-      for (int c = lane; c < G; c += 32) { sg += __ldcg(a.part + 2 * c); sd += __ldcg(a.part + 2 * c + 1); }
+      if (CLUSTER) {
+        if (lane < G) { sg = s_cpart[0][lane]; sd = s_cpart[1][lane]; }
+      } else {
+        for (int c = lane; c < G; c += 32) { sg += __ldcg(a.part + 2 * c); sd += __ldcg(a.part + 2 * c + 1); }
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         sg += __shfl_down_sync(0xffffffffu, sg, o);
@@ -217,7 +255,7 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
     __syncthreads();
     apply_minv_publish();
     gamma_prev = gn; alpha_prev = alpha; first = false; ++k_it;
-    grid_barrier(a.bar, target, G);
+    barrier();
   }
   // ---- F. solution + retraction of the owned cameras ----
   for (int r = tid; r < rows; r += kBcsrThreads) g.x[6 * cam0 + r] = vx[r];
@@ -238,71 +276,109 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
     for (int k = 0; k < 3; ++k) g.Rt_new[12 * i + 9 + k] = out[4 + k];
   }
   if (b == 0 && tid == 0) g.sc->pcg_iters += k_it;
+  if (CLUSTER) cg::this_cluster().sync();  // nobody leaves while a peer could still address its shared memory
 }
 
-size_t bcsr_smem_bytes(int n6, int max_cams, int max_blocks, bool in_smem) {
-  size_t d = (size_t)((n6 + 1) & ~1) + 6 * (size_t)6 * max_cams + 36 * (size_t)max_cams + (in_smem ? (size_t)max_blocks * kBlkStride : 0);
+size_t bcsr_smem_bytes(int n6, int max_cams, int max_blocks, bool in_smem, int blk_stride = kBlkStride) {
+  size_t d = (size_t)((n6 + 1) & ~1) + 6 * (size_t)6 * max_cams + 36 * (size_t)max_cams + (in_smem ? (size_t)max_blocks * blk_stride : 0);
   return d * sizeof(double) + ((size_t)max_blocks + max_cams + 1) * sizeof(int) + 64;
 }
 
 }  // namespace
 
+// contiguous camera ranges for G CTAs, balanced by block count, at least one camera each
+static void bcsr_partition(int nc, int nnzb, const int* s_rowptr, int G, std::vector<int>& cta_cam, int* max_cams, int* max_blocks) {
+  cta_cam.assign(G + 1, nc);
+  int cam = 0;
+  for (int c = 0; c < G; ++c) {
+    cta_cam[c] = cam;
+    const long long want = (long long)nnzb * (c + 1) / G;  // block count that should be covered after this CTA
+    const int left_ctas = G - 1 - c;
+    while (cam < nc - left_ctas && (s_rowptr[cam + 1] <= want || cam == cta_cam[c])) ++cam;
+  }
+  cta_cam[G] = nc;
+  *max_cams = 1; *max_blocks = 1;
+  for (int c = 0; c < G; ++c) {
+    *max_cams = std::max(*max_cams, cta_cam[c + 1] - cta_cam[c]);
+    *max_blocks = std::max(*max_blocks, s_rowptr[cta_cam[c + 1]] - s_rowptr[cta_cam[c]]);
+  }
+}
+
 int ba_pcg_bcsr_plan(gb_ctx* ctx, gb_ba_graph* g, const int* s_rowptr) {
   g->pcg_bcsr = false;
   const int nc = g->d.nc, nnzb = g->d.s_nnzb, n6 = g->d.n6;
   if (nc <= 0 || nnzb <= 0) return GB_OK;
-  {  // the shared-memory limit of a kernel is per-device state: raise it once per device, never lower it
+  static bool cluster16_ok[64] = {false};
+  {  // function attributes are per-device state: set them once per device, never lower them
     static std::mutex mu;
     static int state[64] = {0};
     std::lock_guard<std::mutex> lk(mu);
     const int dev = ctx->device;
     if (dev < 0 || dev >= 64) return GB_OK;
     if (state[dev] == 0) {
-      cudaFuncAttributes fa;  // (the opt-in maximum covers static + dynamic shared memory)
-      state[dev] = (cudaFuncGetAttributes(&fa, ba_pcg_bcsr_kernel) == cudaSuccess &&
-                    cudaFuncSetAttribute(ba_pcg_bcsr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin - (int)fa.sharedSizeBytes) == cudaSuccess) ? 1 : 2;
+      auto raise = [&](const void* fn) {  // (the opt-in maximum covers static + dynamic shared memory)
+        cudaFuncAttributes fa;
+        return cudaFuncGetAttributes(&fa, fn) == cudaSuccess &&
+               cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->max_smem_optin - (int)fa.sharedSizeBytes) == cudaSuccess;
+      };
+      const bool ok = raise((const void*)ba_pcg_bcsr_kernel<false>) && raise((const void*)ba_pcg_bcsr_kernel<true>);
+      cluster16_ok[dev] = cudaFuncSetAttribute(ba_pcg_bcsr_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+      state[dev] = ok ? 1 : 2;
       cudaGetLastError();
     }
     if (state[dev] != 1) return GB_OK;
   }
-  int coop = 0;
-  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
-  if (!coop) return GB_OK;
-  // contiguous camera ranges balanced by block count; at most one CTA per SM (the kernel is launched cooperatively)
-  const int G = std::max(1, std::min(ctx->sm_count, nc));
-  std::vector<int> cta_cam(G + 1, nc);
-  cta_cam[0] = 0;
-  {
-    int cam = 0;
-    for (int c = 0; c < G; ++c) {
-      cta_cam[c] = cam;
-      const long long want = (long long)nnzb * (c + 1) / G;  // block count that should be covered after this CTA
-      const int left_ctas = G - 1 - c;
-      while (cam < nc - left_ctas && (s_rowptr[cam + 1] <= want || cam == cta_cam[c])) ++cam;  // at least one camera each
-    }
-    cta_cam[G] = nc;
-  }
-  int max_cams = 1, max_blocks = 1;
-  for (int c = 0; c < G; ++c) {
-    max_cams = std::max(max_cams, cta_cam[c + 1] - cta_cam[c]);
-    max_blocks = std::max(max_blocks, s_rowptr[cta_cam[c + 1]] - s_rowptr[cta_cam[c]]);
-  }
+  const size_t budget = (size_t)ctx->max_smem_optin - 2048;  // (static shared memory of the kernel: < 1 KB)
+  std::vector<int> cta_cam;
+  int G = 0, max_cams = 1, max_blocks = 1, cluster = 0, blk_stride = kBlkStride;
   bool in_smem = true;
-  size_t smem = bcsr_smem_bytes(n6, max_cams, max_blocks, true);
-  const size_t budget = (size_t)ctx->max_smem_optin - 1024;  // (static shared memory of the kernel: 272 bytes)
-  if (smem > budget) {
-    in_smem = false;
-    smem = bcsr_smem_bytes(n6, max_cams, max_blocks, false);
-    if (smem > budget) return GB_OK;  // not even the vectors fit: generic path
+  size_t smem = 0;
+  // 1) ONE thread-block cluster when S fits the shared memory of <= 16 (8 without the non-portable size) CTAs
+  if (!getenv("GB_BA_NO_PCG_CLUSTER")) {
+    const int sizes[2] = {16, 8};
+    for (int t = 0; t < 2 && !cluster; ++t) {
+      const int C = std::min(sizes[t], nc);
+      if (C > 8 && !cluster16_ok[ctx->device]) continue;
+      int mc, mb;
+      bcsr_partition(nc, nnzb, s_rowptr, C, cta_cam, &mc, &mb);
+      const int strides[2] = {kBlkStride, 36};
+      for (int q = 0; q < 2 && !cluster; ++q) {
+        const size_t need = bcsr_smem_bytes(n6, mc, mb, true, strides[q]);
+        if (need > budget) continue;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(C); cfg.blockDim = dim3(kBcsrThreads); cfg.dynamicSmemBytes = need; cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, ba_pcg_bcsr_kernel<true>, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
+        cluster = C; G = C; max_cams = mc; max_blocks = mb; blk_stride = strides[q]; smem = need;
+      }
+    }
+  }
+  // 2) otherwise a cooperative grid, one CTA per SM at most, global-memory barrier
+  if (!cluster) {
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+    if (!coop) return GB_OK;
+    G = std::max(1, std::min(ctx->sm_count, nc));
+    bcsr_partition(nc, nnzb, s_rowptr, G, cta_cam, &max_cams, &max_blocks);
+    smem = bcsr_smem_bytes(n6, max_cams, max_blocks, true);
+    if (smem > budget) {
+      in_smem = false;
+      smem = bcsr_smem_bytes(n6, max_cams, max_blocks, false);
+      if (smem > budget) return GB_OK;  // not even the vectors fit: generic path
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_pcg_bcsr_kernel<false>, kBcsrThreads, smem) != cudaSuccess || per_sm < 1) {
+      cudaGetLastError();
+      return GB_OK;
+    }
+    if ((long long)per_sm * ctx->sm_count < G) return GB_OK;
   }
   int K = 32;
   while (K > 1 && 6 * max_cams * K > kBcsrThreads) K >>= 1;
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_pcg_bcsr_kernel, kBcsrThreads, smem) != cudaSuccess || per_sm < 1) {
-    cudaGetLastError();
-    return GB_OK;
-  }
-  if ((long long)per_sm * ctx->sm_count < G) return GB_OK;
   const size_t bytes = (size_t)(G + 1) * 4 + 256 + (size_t)2 * G * 8 + 256 + (size_t)n6 * 8 + 256 + 256;
   uint8_t* base = nullptr;
   GB_CUDA(ctx, cudaMalloc((void**)&base, bytes));
@@ -315,7 +391,7 @@ int ba_pcg_bcsr_plan(gb_ctx* ctx, gb_ba_graph* g, const int* s_rowptr) {
   GB_CUDA(ctx, cudaMemcpyAsync(g->bcsr_cta_cam, cta_cam.data(), (size_t)(G + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // (cta_cam is a stack-lifetime host vector)
   g->bcsr_ctas = G; g->bcsr_K = K; g->bcsr_in_smem = in_smem ? 1 : 0; g->bcsr_smem = smem;
-  g->bcsr_max_cams = max_cams; g->bcsr_max_blocks = max_blocks;
+  g->bcsr_max_cams = max_cams; g->bcsr_max_blocks = max_blocks; g->bcsr_cluster = cluster; g->bcsr_blk_stride = blk_stride;
   g->pcg_bcsr = true;
   return GB_OK;
 }
@@ -334,10 +410,21 @@ int ba_pcg_bcsr_launch(gb_ctx* ctx, gb_ba_graph* g, const double* rbuf) {
   BcsrArgs a;
   a.cta_cam = g->bcsr_cta_cam; a.part = g->bcsr_part; a.u_glob = g->bcsr_u; a.bar = g->bcsr_bar;
   a.K = g->bcsr_K; a.in_smem = g->bcsr_in_smem; a.maxit = g->opt.pcg_max_iters; a.max_cams = g->bcsr_max_cams; a.max_blocks = g->bcsr_max_blocks;
-  GB_CUDA(ctx, cudaMemsetAsync(g->bcsr_bar, 0, 4, ctx->stream));
+  a.blk_stride = g->bcsr_blk_stride;
   double* rb = const_cast<double*>(rbuf);  // (the damped diagonal is written back when S stays in global memory)
-  void* args[3] = {(void*)&d, (void*)&rb, (void*)&a};
-  GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)ba_pcg_bcsr_kernel, dim3(g->bcsr_ctas), dim3(kBcsrThreads), args, g->bcsr_smem, ctx->stream));
+  if (g->bcsr_cluster > 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g->bcsr_cluster); cfg.blockDim = dim3(kBcsrThreads); cfg.dynamicSmemBytes = g->bcsr_smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = g->bcsr_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GB_CUDA(ctx, cudaLaunchKernelEx(&cfg, ba_pcg_bcsr_kernel<true>, d, rb, a));
+  } else {
+    GB_CUDA(ctx, cudaMemsetAsync(g->bcsr_bar, 0, 4, ctx->stream));
+    void* args[3] = {(void*)&d, (void*)&rb, (void*)&a};
+    GB_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)ba_pcg_bcsr_kernel<false>, dim3(g->bcsr_ctas), dim3(kBcsrThreads), args, g->bcsr_smem, ctx->stream));
+  }
   GB_LAUNCH_CHECK(ctx);
   return GB_OK;
 }

@@ -50,6 +50,7 @@ struct gb_features {
   int* d_count = nullptr;        // device-side keypoint count (written by extract)
   int* d_status = nullptr;       // device-side status word (0 ok, else required capacity)
   int h_count = -1;              // host copy (valid when >=0)
+  int expect = 0;                // expected row count while h_count is unknown (nfeatures of the extraction in flight): tunes launches
   int32_t* d_best = nullptr;     // match outputs [capacity]
   int32_t* d_dist = nullptr;
   int32_t* d_dist2 = nullptr;

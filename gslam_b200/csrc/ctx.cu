@@ -67,7 +67,16 @@ int gb_device_count(int* n) {
   return GB_OK;
 }
 
-int gb_ctx_create(int device, gb_ctx** out) {
+static int ctx_create_impl(int device, int high_priority, gb_ctx** out);
+
+int gb_ctx_create(int device, gb_ctx** out) { return ctx_create_impl(device, 0, out); }
+
+// A ctx whose stream has the device's greatest priority: the block scheduler hands free SM slots to its CTAs first.  For the
+// mapping ctx of a tracking/mapping pair: the few-CTA local-BA kernels then do not queue behind the thousands of CTAs of the
+// tracking ctx's FAST / describe grids (without it the two streams barely overlap).
+int gb_ctx_create_priority(int device, int high_priority, gb_ctx** out) { return ctx_create_impl(device, high_priority, out); }
+
+static int ctx_create_impl(int device, int high_priority, gb_ctx** out) {
   if (!out) return GB_ERR_INVALID;
   *out = nullptr;
   int n = 0;
@@ -82,7 +91,11 @@ int gb_ctx_create(int device, gb_ctx** out) {
   gb_ctx* ctx = new gb_ctx();
   ctx->device = device;
   cudaError_t e = cudaSetDevice(device);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) {
+    int lo = 0, hi = 0;  // (numerically lower = higher priority)
+    if (high_priority && cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, hi);
+    else e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  }
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->evs);

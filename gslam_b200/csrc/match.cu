@@ -24,12 +24,30 @@ __device__ __forceinline__ int ham256(const uint4& a0, const uint4& a1, const ui
          __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
+// d_nq / d_nt (nullable): device-side row counts of an extraction still in flight -- the launch is then sized for the capacities
+// passed as nq / nt and the kernel clips to the real counts, so that extract -> match chains without a host round trip.
+// STEREO (rectified pair, left = query, right = train): a right keypoint is a candidate of a left one iff
+// |y_R - y_L| <= band and min_disp <= x_L - x_R <= max_disp (level-0 pixel coordinates, float compares); everything else -- the
+// distance, the (distance, index) order, the tie rule -- is the matcher's.  The right keypoints' (x, y) ride along with the staged
+// descriptors; the popcounts are only evaluated for candidates (a few percent of the pairs).
+struct StereoArgs {
+  const gb_keypoint* qk;
+  const gb_keypoint* tk;
+  float band, min_disp, max_disp;
+};
+
+template <bool STEREO>
 __global__ void __launch_bounds__(kQPerCta) match_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t,
                                                          int nt, int chunk, MatchPartial* __restrict__ partial,
                                                          unsigned int* __restrict__ tickets, int32_t* __restrict__ best_idx,
-                                                         int32_t* __restrict__ best_dist, int32_t* __restrict__ second_dist) {
+                                                         int32_t* __restrict__ best_dist, int32_t* __restrict__ second_dist,
+                                                         const int* __restrict__ d_nq, const int* __restrict__ d_nt, StereoArgs st) {
   gb_pdl_launch_dependents();
   gb_pdl_wait();
+  const int pstride = nq;  // layout of the partials: [split][query capacity]
+  if (d_nq) nq = min(max(*d_nq, 0), nq);
+  if (d_nt) nt = min(max(*d_nt, 0), nt);
+  if ((int)(blockIdx.x * kQPerCta) >= nq) return;  // a query tile beyond the real count: none of its CTAs has anything to merge
   extern __shared__ uint4 s_train[];  // chunk rows x 2 uint4
   __shared__ bool s_last;
   const int tid = threadIdx.x;
@@ -39,22 +57,41 @@ __global__ void __launch_bounds__(kQPerCta) match_kernel(const uint4* __restrict
 
   // stage the train chunk: 2 uint4 per row, fully coalesced
   for (int i = tid; i < tn * 2; i += kQPerCta) s_train[i] = __ldg(t + (size_t)t0 * 2 + i);
+  float2* s_xy = reinterpret_cast<float2*>(s_train + 2 * chunk);  // STEREO: (x, y) of the staged right keypoints
+  if (STEREO)
+    for (int i = tid; i < tn; i += kQPerCta) s_xy[i] = make_float2(st.tk[t0 + i].x, st.tk[t0 + i].y);
   uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+  float qx = 0.f, qy = 0.f;
   if (qi < nq) {
     q0 = __ldg(q + (size_t)qi * 2);
     q1 = __ldg(q + (size_t)qi * 2 + 1);
+    if (STEREO) { qx = st.qk[qi].x; qy = st.qk[qi].y; }
   }
   __syncthreads();
 
   int d0 = 257, d1 = 257, b0 = -1;
+  if (STEREO) {
+    for (int j = 0; j < tn; ++j) {
+      const float2 p = s_xy[j];
+      const float disp = qx - p.x;
+      if (!(fabsf(p.y - qy) <= st.band && disp >= st.min_disp && disp <= st.max_disp)) continue;
+      const uint4 a = s_train[2 * j], b = s_train[2 * j + 1];
+      const int d = ham256(q0, q1, a, b);
+      const bool lt = d < d0;
+      d1 = lt ? d0 : min(d1, d);
+      b0 = lt ? (t0 + j) : b0;
+      d0 = lt ? d : d0;
+    }
+  } else {
 #pragma unroll 4
-  for (int j = 0; j < tn; ++j) {
-    const uint4 a = s_train[2 * j], b = s_train[2 * j + 1];
-    const int d = ham256(q0, q1, a, b);
-    const bool lt = d < d0;
-    d1 = lt ? d0 : min(d1, d);
-    b0 = lt ? (t0 + j) : b0;
-    d0 = lt ? d : d0;
+    for (int j = 0; j < tn; ++j) {
+      const uint4 a = s_train[2 * j], b = s_train[2 * j + 1];
+      const int d = ham256(q0, q1, a, b);
+      const bool lt = d < d0;
+      d1 = lt ? d0 : min(d1, d);
+      b0 = lt ? (t0 + j) : b0;
+      d0 = lt ? d : d0;
+    }
   }
 
   const int nsplit = gridDim.y;
@@ -71,7 +108,7 @@ __global__ void __launch_bounds__(kQPerCta) match_kernel(const uint4* __restrict
     p.d0 = d0;
     p.b0 = b0;
     p.d1 = d1;
-    partial[(size_t)blockIdx.y * nq + qi] = p;  // [split][query]: coalesced across the CTA
+    partial[(size_t)blockIdx.y * pstride + qi] = p;  // [split][query]: coalesced across the CTA
   }
   __threadfence();
   __syncthreads();
@@ -85,7 +122,7 @@ __global__ void __launch_bounds__(kQPerCta) match_kernel(const uint4* __restrict
   if (qi < nq) {
     int D0 = 257, D1 = 257, B0 = -1;
     for (int s = 0; s < nsplit; ++s) {  // ascending train index == sequential scan order
-      const MatchPartial* pp = partial + (size_t)s * nq + qi;
+      const MatchPartial* pp = partial + (size_t)s * pstride + qi;
       const int pd0 = __ldcg(&pp->d0), pb0 = __ldcg(&pp->b0), pd1 = __ldcg(&pp->d1);
       if (pd0 < D0) {
         D1 = min(D0, pd1);
@@ -138,20 +175,25 @@ void gb_match_state_free(gb_ctx* ctx) {
 }
 
 // Enqueue the match of (d_q, nq) against (d_t, nt) on the ctx stream.  Outputs are device pointers (may be null).
+// nq / nt: row counts, or -- with d_nq / d_nt -- CAPACITIES the launch must cover while the real counts are read on the device; the
+// work split is then tuned for the expected counts eq / et (<= 0: unknown, use the capacities).
 int gb_match_launch(gb_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int32_t* d_best, int32_t* d_dist,
-                    int32_t* d_dist2) {
+                    int32_t* d_dist2, const int* d_nq = nullptr, const int* d_nt = nullptr, const StereoArgs* stereo = nullptr, int eq = 0,
+                    int et = 0) {
   if (nq <= 0) return GB_OK;
   if (!ctx->match) ctx->match = new MatchState();
   MatchState* ms = ctx->match;
   const int qtiles = gb_div_up(nq, kQPerCta);
+  if (eq <= 0 || eq > nq) eq = nq;
+  if (et <= 0 || et > nt) et = nt;
   // split the train rows so that ~2 CTAs land on every SM; chunk is a multiple of 8 rows, at most 1024 rows (32 KB)
   int nsplit = 1, chunk = nt > 0 ? nt : 1;
   if (nt > 0) {
-    nsplit = gb_div_up(2 * ctx->sm_count, qtiles);
-    const int max_split = gb_div_up(nt, 32);
+    nsplit = gb_div_up(2 * ctx->sm_count, gb_div_up(eq, kQPerCta));
+    const int max_split = gb_div_up(et, 32);
     if (nsplit > max_split) nsplit = max_split;
     if (nsplit < 1) nsplit = 1;
-    chunk = gb_div_up(gb_div_up(nt, nsplit), 8) * 8;
+    chunk = gb_div_up(gb_div_up(et, nsplit), 8) * 8;
     if (chunk > 1024) chunk = 1024;
     nsplit = gb_div_up(nt, chunk);
   }
@@ -165,9 +207,15 @@ int gb_match_launch(gb_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t,
     GB_CUDA(ctx, cudaMemsetAsync(ms->d_tickets, 0, ms->tickets_cap, ctx->stream));
   }
   dim3 grid(qtiles, nsplit);
-  const size_t smem = (size_t)chunk * 32;
-  GB_CUDA(ctx, gb_launch_pdl(match_kernel, grid, dim3(kQPerCta), smem, ctx->stream, (const uint4*)d_q, nq, (const uint4*)d_t, nt > 0 ? nt : 0, chunk,
-                             (MatchPartial*)ms->d_partial, (unsigned int*)ms->d_tickets, d_best, d_dist, d_dist2));
+  const size_t smem = (size_t)chunk * (stereo ? 40 : 32);
+  StereoArgs sa = {};
+  if (stereo) sa = *stereo;
+  if (stereo)
+    GB_CUDA(ctx, gb_launch_pdl(match_kernel<true>, grid, dim3(kQPerCta), smem, ctx->stream, (const uint4*)d_q, nq, (const uint4*)d_t, nt > 0 ? nt : 0, chunk,
+                               (MatchPartial*)ms->d_partial, (unsigned int*)ms->d_tickets, d_best, d_dist, d_dist2, d_nq, d_nt, sa));
+  else
+    GB_CUDA(ctx, gb_launch_pdl(match_kernel<false>, grid, dim3(kQPerCta), smem, ctx->stream, (const uint4*)d_q, nq, (const uint4*)d_t, nt > 0 ? nt : 0, chunk,
+                               (MatchPartial*)ms->d_partial, (unsigned int*)ms->d_tickets, d_best, d_dist, d_dist2, d_nq, d_nt, sa));
   GB_LAUNCH_CHECK(ctx);
   return GB_OK;
 }
@@ -204,16 +252,56 @@ GB_API int gb_dbg_popc_peak(gb_ctx* ctx, double* popc_per_s) {
 int gb_match_features(gb_ctx* ctx, gb_features* fq, gb_features* ft) {
   if (!ctx || !fq || !ft) return GB_ERR_INVALID;
   CtxLock lk(ctx);
-  int nq = 0, nt = 0;
-  GB_CHECK(gb_features_count(ctx, fq, &nq));
-  GB_CHECK(gb_features_count(ctx, ft, &nt));
+  if (fq->h_count < 0 || ft->h_count < 0) {
+    // an extraction is still in flight: no host round trip -- launch for the capacities, the kernel reads the device-side counts
+    fq->n_matched = -1;  // resolved by gb_match_download
+    return gb_match_launch(ctx, fq->d_desc, fq->h_count >= 0 ? fq->h_count : fq->capacity, ft->d_desc, ft->h_count >= 0 ? ft->h_count : ft->capacity,
+                           fq->d_best, fq->d_dist, fq->d_dist2, fq->h_count >= 0 ? nullptr : fq->d_count, ft->h_count >= 0 ? nullptr : ft->d_count,
+                           nullptr, fq->expect, ft->expect);
+  }
+  const int nq = fq->h_count, nt = ft->h_count;
   fq->n_matched = nq;
   return gb_match_launch(ctx, fq->d_desc, nq, ft->d_desc, nt, fq->d_best, fq->d_dist, fq->d_dist2);
+}
+
+// Rectified-stereo row-band match, device-resident: left = query, right = train; results with gb_match_download(left).
+int gb_match_stereo_features(gb_ctx* ctx, gb_features* left, gb_features* right, float band_rows, float min_disparity, float max_disparity) {
+  if (!ctx || !left || !right || !(band_rows >= 0.f) || !(max_disparity >= min_disparity)) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  StereoArgs sa;
+  sa.qk = left->d_kps; sa.tk = right->d_kps; sa.band = band_rows; sa.min_disp = min_disparity; sa.max_disp = max_disparity;
+  const bool async = left->h_count < 0 || right->h_count < 0;
+  left->n_matched = async ? -1 : left->h_count;
+  return gb_match_launch(ctx, left->d_desc, left->h_count >= 0 ? left->h_count : left->capacity, right->d_desc,
+                         right->h_count >= 0 ? right->h_count : right->capacity, left->d_best, left->d_dist, left->d_dist2,
+                         left->h_count >= 0 ? nullptr : left->d_count, right->h_count >= 0 ? nullptr : right->d_count, &sa, left->expect, right->expect);
+}
+
+// Host-buffer variant (what the Svar module's match_stereo binds).
+int gb_match_stereo(gb_ctx* ctx, const gb_keypoint* kps_left, const uint8_t* desc_left, int nl, const gb_keypoint* kps_right, const uint8_t* desc_right,
+                    int nr, float band_rows, float min_disparity, float max_disparity, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist) {
+  if (!ctx || nl < 0 || nr < 0 || (nl > 0 && (!kps_left || !desc_left)) || (nr > 0 && (!kps_right || !desc_right))) return GB_ERR_INVALID;
+  if (nl == 0) return GB_OK;
+  CtxLock lk(ctx);
+  auto ensure = [&](gb_features** f, int n) -> int {
+    if (*f && (*f)->capacity >= n) return GB_OK;
+    if (*f) gb_features_destroy(ctx, *f);
+    *f = nullptr;
+    return gb_features_create(ctx, n + n / 4 + 64, f);
+  };
+  GB_CHECK(ensure(&ctx->tmp_q, nl));
+  GB_CHECK(ensure(&ctx->tmp_t, nr > 0 ? nr : 1));
+  GB_CHECK(gb_features_upload(ctx, ctx->tmp_q, kps_left, desc_left, nl));
+  GB_CHECK(gb_features_upload(ctx, ctx->tmp_t, nr > 0 ? kps_right : nullptr, nr > 0 ? desc_right : desc_left, nr));
+  GB_CHECK(gb_match_stereo_features(ctx, ctx->tmp_q, ctx->tmp_t, band_rows, min_disparity, max_disparity));
+  int n = nl;
+  return gb_match_download(ctx, ctx->tmp_q, best_idx, best_dist, second_dist, &n);
 }
 
 int gb_match_download(gb_ctx* ctx, gb_features* fq, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist, int* n) {
   if (!ctx || !fq || !n) return GB_ERR_INVALID;
   CtxLock lk(ctx);
+  if (fq->n_matched < 0) GB_CHECK(gb_features_count(ctx, fq, &fq->n_matched));  // (the match was enqueued behind an extraction in flight)
   const int cap = *n, cnt = fq->n_matched;
   *n = cnt;
   if (cnt > cap) {

@@ -759,6 +759,7 @@ static int orb_launch(gb_ctx* ctx, gb_features* out) {
                              s->d_kept_resp, d_kept, s->d_pattern, out->d_kps, out->d_desc, out->capacity, out->d_count, out->d_status, d_status));
   GB_LAUNCH_CHECK(ctx);
   out->h_count = -1;
+  out->expect = std::min(out->capacity, s->cfg.nfeatures + s->cfg.nfeatures / 64 + 8);  // (a few ties above nfeatures are usual)
   return GB_OK;
 }
 

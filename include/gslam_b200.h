@@ -61,6 +61,9 @@ typedef struct gb_ba_graph gb_ba_graph; /* a bundle-adjustment graph resident in
 GB_API int gb_version(void);
 GB_API int gb_device_count(int* n);
 GB_API int gb_ctx_create(int device, gb_ctx** out);
+/* high_priority != 0: the ctx's stream gets the device's greatest priority, so that its (few-CTA) kernels are scheduled ahead of
+ * the big grids of another ctx on the same GPU -- the mapping ctx (local BA) of a tracking / mapping pair. */
+GB_API int gb_ctx_create_priority(int device, int high_priority, gb_ctx** out);
 GB_API int gb_ctx_destroy(gb_ctx* ctx);
 /* Last error message of `ctx` (or of the calling thread when ctx==NULL).  Never NULL; valid until the next call. */
 GB_API const char* gb_last_error(const gb_ctx* ctx);
@@ -138,6 +141,20 @@ GB_API int gb_match_hamming(gb_ctx* ctx, const uint8_t* query, int nq, const uin
 GB_API int gb_match_features(gb_ctx* ctx, gb_features* fq, gb_features* ft);
 GB_API int gb_match_download(gb_ctx* ctx, gb_features* fq, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist,
                              int* n);
+
+/*
+ * Rectified-stereo row-band match (BASELINE config 4: EuRoC-shaped stereo 752x480): left = query,
+ * right = train.  A right keypoint is a candidate of a left one iff |y_R - y_L| <= band_rows and
+ * min_disparity <= x_L - x_R <= max_disparity (float compares on GSLAM::KeyPoint::pt, level-0 pixels, Map.h:180-194); among the
+ * candidates the same distance (hamming32, Vocabulary.h:485-491), (distance, index) order and tie rule as gb_match_hamming.
+ * best_idx = -1 / distances 257 when a left keypoint has no candidate.  The reference has no stereo matcher: this definition is
+ * ours.  Device-resident variant: results stay with `left` until gb_match_download(left).
+ */
+GB_API int gb_match_stereo(gb_ctx* ctx, const gb_keypoint* kps_left, const uint8_t* desc_left, int n_left,
+                           const gb_keypoint* kps_right, const uint8_t* desc_right, int n_right, float band_rows,
+                           float min_disparity, float max_disparity, int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
+GB_API int gb_match_stereo_features(gb_ctx* ctx, gb_features* left, gb_features* right, float band_rows, float min_disparity,
+                                    float max_disparity);
 
 /* ---- bundle adjustment ---------------------------------------------------------------------------------------------- */
 /*

@@ -85,6 +85,9 @@ def lib() -> C.CDLL:
         L.orc_hamming256.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_match_hamming.restype = None
         L.orc_match_hamming.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_match_stereo.restype = None
+        L.orc_match_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_ba_solve.restype = C.c_int
         L.orc_ba_solve.argtypes = [C.POINTER(BaProblemC), C.POINTER(BaOptionsC), C.POINTER(BaResultC)]
         L.orc_ba_linearize.restype = C.c_int
@@ -134,6 +137,15 @@ def ref() -> C.CDLL:
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def match_stereo(kps_left, desc_left, kps_right, desc_right, band=2.0, min_disp=0.0, max_disp=1e9):
+    kl = np.ascontiguousarray(kps_left, KP_DTYPE); kr = np.ascontiguousarray(kps_right, KP_DTYPE)
+    dl = np.ascontiguousarray(desc_left, np.uint8).reshape(-1, 32); dr = np.ascontiguousarray(desc_right, np.uint8).reshape(-1, 32)
+    nl, nr = dl.shape[0], dr.shape[0]
+    idx = np.empty(nl, np.int32); d1 = np.empty(nl, np.int32); d2 = np.empty(nl, np.int32)
+    lib().orc_match_stereo(_p(kl), _p(dl), nl, _p(kr), _p(dr), nr, band, min_disp, max_disp, _p(idx), _p(d1), _p(d2))
+    return idx, d1, d2
 
 
 # ---- Hamming -----------------------------------------------------------------------------------------------------

@@ -277,3 +277,50 @@ def test_global_ba_shape_property(ctx):
     assert r.final_cost < 0.1 * r.initial_cost
     c1 = oracle.ba_cost(pb)
     assert abs(c1 - r.final_cost) / c1 < 1e-9
+
+
+def _pose_err(a, b):
+    """max |translation difference| (relative to the scene scale) and max quaternion difference up to sign."""
+    s = np.sign(np.sum(a[:, :4] * b[:, :4], axis=1))[:, None]
+    return np.abs(a[:, 4:] - b[:, 4:]).max() / max(1.0, np.abs(b[:, 4:]).max()), np.abs(a[:, :4] * s - b[:, :4]).max()
+
+
+def test_large_graph_paths_agree_and_match_oracle(ctx, monkeypatch):
+    """The large-graph machinery of round 2 -- landmark-chunk Schur complement (ba_schur_chunks_kernel + reduce), block-CSR PCG in
+    one thread-block cluster (DSMEM) or as a cooperative grid -- against the block-gather / grid variants and the oracle.  PCG runs
+    to its tolerance so that summation order cannot be amplified by an unconverged Krylov solve."""
+    pb0 = synth.synth_ba(120, 12000, obs_per_point=8, n_fixed=2, seed=6)
+    want = pb0.copy()
+    r0 = oracle.ba_solve(want, max_iterations=5, function_tolerance=0.0, pcg_max_iters=600)
+    results = {}
+    for name, env in (("chunks+cluster", {}), ("gather+cluster", {"GB_BA_NO_SCHUR_CHUNKS": "1"}), ("chunks+grid", {"GB_BA_NO_PCG_CLUSTER": "1"})):
+        for k in ("GB_BA_NO_SCHUR_CHUNKS", "GB_BA_NO_PCG_CLUSTER"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        pb = pb0.copy()
+        r = ctx.ba_solve(pb, cfg(maxIterations=5, functionTolerance=0.0, pcgMaxIterations=600))
+        results[name] = (r, pb)
+        assert r.accepted == r0.accepted, name
+        assert abs(r.final_cost - r0.final_cost) / r0.final_cost < 1e-5, name
+        et, eq = _pose_err(pb.cam_pose_wc, want.cam_pose_wc)
+        assert et < 1e-5 and eq < 1e-5, (name, et, eq)
+        assert np.abs(pb.points - want.points).max() / np.abs(want.points).max() < 1e-5, name
+    base = results["chunks+cluster"][0].final_cost
+    for name, (r, pb) in results.items():
+        assert abs(r.final_cost - base) / base < 1e-9, name
+
+
+def test_global_ba_full_size_matches_oracle(ctx):
+    """BASELINE config 5 at FULL size (500 cameras / 100k landmarks / 1M observations), the bench's iteration counts (5 LM, PCG cap
+    30): final cost and every camera SE3 within 1e-5 of the CPU oracle after the same iteration counts."""
+    pb = synth.synth_ba(500, 100000, obs_per_point=10, n_fixed=2, seed=42)
+    want = pb.copy()
+    r0 = oracle.ba_solve(want, max_iterations=5, function_tolerance=0.0, pcg_max_iters=30)
+    r = ctx.ba_solve(pb, cfg(maxIterations=5, functionTolerance=0.0, pcgMaxIterations=30))
+    assert r.accepted == r0.accepted and r.iterations == r0.iterations
+    assert abs(r.initial_cost - r0.initial_cost) / r0.initial_cost < 1e-12
+    assert abs(r.final_cost - r0.final_cost) / r0.final_cost < 1e-5
+    et, eq = _pose_err(pb.cam_pose_wc, want.cam_pose_wc)
+    assert et < 1e-5 and eq < 1e-5, (et, eq)
+    assert np.abs(pb.points - want.points).max() / np.abs(want.points).max() < 1e-5

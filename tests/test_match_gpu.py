@@ -71,3 +71,48 @@ def test_device_resident_features(ctx):
     idx, d1, _ = fq.matches()
     assert np.array_equal(idx, np.arange(2000)) and (d1 == 0).all()
     fq.close(); ft.close()
+
+
+def _stereo_case(rng, nl, nr, dup=False):
+    kl = np.zeros(nl, oracle.KP_DTYPE); kr = np.zeros(nr, oracle.KP_DTYPE)
+    kl["x"] = rng.uniform(0, 752, nl).astype(np.float32); kl["y"] = np.round(rng.uniform(0, 480, nl) * 2) / 2
+    kr["x"] = rng.uniform(0, 752, nr).astype(np.float32); kr["y"] = np.round(rng.uniform(0, 480, nr) * 2) / 2
+    dl = rng.integers(0, 256, (nl, 32), dtype=np.uint8); dr = rng.integers(0, 256, (nr, 32), dtype=np.uint8)
+    if dup and nr > 8:
+        dr[5] = dr[2]; kr["y"][5] = kr["y"][2]; dr[7] = dr[2]; kr["y"][7] = kr["y"][2]
+    return kl, dl, kr, dr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nl,nr,band,mind,maxd,dup", [(300, 280, 2.0, 0.0, 96.0, False), (64, 500, 0.0, -5.0, 1e9, True), (200, 0, 2.0, 0.0, 50.0, False),
+                                                       (1, 1, 1000.0, -1e9, 1e9, False), (2000, 2000, 2.0, 0.0, 120.0, True), (2047, 1025, 2.5, 3.0, 200.0, True)])
+def test_stereo_rowband_match_matches_oracle(ctx, nl, nr, band, mind, maxd, dup):
+    """gb_match_stereo (row band + disparity window, BASELINE config 4's stereo association) bit-exact vs oracle/hamming_ref.c."""
+    rng = np.random.default_rng(nl * 7 + nr)
+    kl, dl, kr, dr = _stereo_case(rng, nl, nr, dup)
+    got = ctx.match_stereo(kl, dl, kr, dr, band, mind, maxd)
+    want = oracle.match_stereo(kl, dl, kr, dr, band, mind, maxd)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+
+
+@pytest.mark.gpu
+def test_stereo_match_on_extracted_pair_device_resident(ctx):
+    """Left / right frames extracted on the device and associated without a host round trip (extract -> extract -> stereo match
+    on one stream, device-side keypoint counts) == the oracle on the downloaded features."""
+    from gslam_b200 import synth
+    from gslam_b200.api import Features
+    left = synth.synth_frame(752, 480, seed=21)
+    right = np.roll(left, -14, axis=1)  # a fronto-parallel scene at constant disparity 14 px
+    cfg = ctx.orb_cfg(nfeatures=2000)
+    fl, fr = Features(ctx, 4256), Features(ctx, 4256)
+    fl.extract(left, 752, 480, cfg); fr.extract(right, 752, 480, cfg)
+    fl.match_stereo(fr, 2.0, 0.0, 96.0)
+    idx, d1, d2 = fl.matches()
+    kl, dl = fl.download(); kr, dr = fr.download()
+    want = oracle.match_stereo(kl, dl, kr, dr, 2.0, 0.0, 96.0)
+    assert np.array_equal(idx, want[0]) and np.array_equal(d1, want[1]) and np.array_equal(d2, want[2])
+    ok = idx >= 0
+    disp = kl["x"][ok] - kr["x"][idx[ok]]
+    assert ok.sum() > 1000 and np.median(np.abs(disp - 14.0)) < 1.0     # the association recovers the disparity
+    fl.close(); fr.close()

@@ -75,3 +75,49 @@ def test_edge_cases():
     assert (idx == 0).all() and d1[0] == 0 and (d2 == 257).all()
     idx, d1, d2 = oracle.match_hamming(np.zeros((0, 32), np.uint8), q)
     assert idx.size == 0
+
+
+def _stereo_numpy(kl, dl, kr, dr, band, mind, maxd):
+    """Independent restatement of the stereo row-band rule (vectorised numpy, stable argsort on (distance, index))."""
+    nl = len(kl)
+    idx = np.full(nl, -1, np.int32); d1 = np.full(nl, 257, np.int32); d2 = np.full(nl, 257, np.int32)
+    if len(kr) == 0:
+        return idx, d1, d2
+    bits_r = np.unpackbits(dr, axis=1)
+    for i in range(nl):
+        dy = np.abs(kr["y"] - kl["y"][i]).astype(np.float32)
+        disp = (kl["x"][i] - kr["x"]).astype(np.float32)
+        cand = np.nonzero((dy <= np.float32(band)) & (disp >= np.float32(mind)) & (disp <= np.float32(maxd)))[0]
+        if cand.size == 0:
+            continue
+        d = (np.unpackbits(dl[i])[None, :] != bits_r[cand]).sum(axis=1)
+        order = np.lexsort((cand, d))
+        idx[i] = cand[order[0]]; d1[i] = d[order[0]]
+        if cand.size > 1:
+            d2[i] = d[order[1]]
+    return idx, d1, d2
+
+
+def _stereo_case(rng, nl, nr, dup=False):
+    kl = np.zeros(nl, oracle.KP_DTYPE); kr = np.zeros(nr, oracle.KP_DTYPE)
+    kl["x"] = rng.uniform(0, 752, nl).astype(np.float32); kl["y"] = np.round(rng.uniform(0, 480, nl) * 2) / 2
+    kr["x"] = rng.uniform(0, 752, nr).astype(np.float32); kr["y"] = np.round(rng.uniform(0, 480, nr) * 2) / 2
+    dl = rng.integers(0, 256, (nl, 32), dtype=np.uint8); dr = rng.integers(0, 256, (nr, 32), dtype=np.uint8)
+    if dup and nr > 8:   # engineered ties: identical right descriptors on the same row
+        dr[5] = dr[2]; kr["y"][5] = kr["y"][2]; dr[7] = dr[2]; kr["y"][7] = kr["y"][2]
+    return kl, dl, kr, dr
+
+
+def test_stereo_rowband_match_equals_numpy_restatement():
+    rng = np.random.default_rng(3)
+    for (nl, nr, band, mind, maxd, dup) in [(300, 280, 2.0, 0.0, 96.0, False), (64, 500, 0.0, -5.0, 1e9, True), (200, 0, 2.0, 0.0, 50.0, False),
+                                            (1, 1, 1000.0, -1e9, 1e9, False), (500, 500, 2.5, 3.0, 200.0, True)]:
+        kl, dl, kr, dr = _stereo_case(rng, nl, nr, dup)
+        got = oracle.match_stereo(kl, dl, kr, dr, band, mind, maxd)
+        want = _stereo_numpy(kl, dl, kr, dr, band, mind, maxd)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+    # unrestricted band == the plain matcher
+    kl, dl, kr, dr = _stereo_case(rng, 100, 120)
+    a = oracle.match_stereo(kl, dl, kr, dr, 1e9, -1e9, 1e9); b = oracle.match_hamming(dl, dr)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
