@@ -329,6 +329,15 @@ def main():
     def ba_once(r=0):
         graph_s.reset(); graph_s.solve(ba_cfg)
     t_ba = time_stage(ba_once, 10)
+    # the same window with the DIRECT linear solver (block-skyline Cholesky in one CTA instead of 50 PCG iterations): reported for
+    # comparison; the timed step keeps the PCG configuration BASELINE.json's workload names
+    ba_cfg_direct = OptimzeConfig(maxIterations=BA_ITERS, functionTolerance=0.0, linearSolver=1)
+    res_direct = [None]
+
+    def ba_direct(r=0):
+        graph_s.reset(); res_direct[0] = graph_s.solve(ba_cfg_direct)
+    t_ba_direct = time_stage(ba_direct, 10)
+    graph_s.reset(); res_pcg = graph_s.solve(ba_cfg)
     t_sweep_local = time_stage(lambda r=0: graph_s.sweep(0.01), 50)
     popc_peak = ctx.popc_peak() if rank == 0 else None
     # the BASELINE metric's second clause, "BA Jacobian-eval HBM GB/s": the fused residual+Jacobian sweep (K6a+K6b) on the
@@ -478,6 +487,10 @@ def main():
                     "steps": e2e_steps, "host_memory": "pageable (malloc'd like GImage); tracking thread || mapping thread, two gb_ctx",
                     "pinned": e2e_pipe_pinned, "serial_pageable": e2e_serial_pageable, "serial_pinned": e2e_serial_pinned},
             "stages_ms": {"extract": t_ext, "match": t_match, "local_ba": t_ba},
+            "local_ba_direct_solver": {"ms": t_ba_direct, "final_cost": res_direct[0].final_cost, "accepted": res_direct[0].accepted,
+                                       "pcg_final_cost": res_pcg.final_cost, "pcg_accepted": res_pcg.accepted,
+                                       "note": "linear_solver=1 (exact block-skyline Cholesky, csrc/ba_chol.cu) on the same window and LM iteration count; "
+                                               "not the timed configuration"},
             # dominant HBM-bound kernel of the path = the BA Jacobian sweep (BASELINE metric, 2nd clause), at config-5 size
             "roofline": {"kernel": "BA Jacobian sweep K6 (ba_linearize_kernel: camera pass + landmark pass in one launch), 500 cams/100k pts/1M obs",
                          "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

@@ -31,11 +31,12 @@ class OptimzeConfig:  # spelling follows GSLAM::OptimzeConfig (Optimizer.h:174-1
     lambdaInit: float = 1e-4
     pcgMaxIterations: int = 50
     pcgTolerance: float = 1e-10
+    linearSolver: int = 0                    # 0 = block-Jacobi PCG, 1 = direct (block-skyline Cholesky; local-BA sizes)
 
     def to_c(self) -> capi.BaOptions:
         return capi.BaOptions(self.cameraProjectionType, self.projectErrorHuberThreshold, self.maxIterations,
                               int(self.verbose), self.functionTolerance, self.lambdaInit, self.pcgMaxIterations,
-                              self.pcgTolerance)
+                              self.pcgTolerance, self.linearSolver)
 
 
 def _problem_c(pb: BAProblem):

@@ -41,7 +41,7 @@ class BaProblem(C.Structure):
 class BaOptions(C.Structure):
     _fields_ = [("projection", C.c_int32), ("huber_delta", C.c_double), ("max_iterations", C.c_int32),
                 ("verbose", C.c_int32), ("function_tolerance", C.c_double), ("lambda_init", C.c_double),
-                ("pcg_max_iters", C.c_int32), ("pcg_tol", C.c_double)]
+                ("pcg_max_iters", C.c_int32), ("pcg_tol", C.c_double), ("linear_solver", C.c_int32)]
 
 
 class BaResult(C.Structure):

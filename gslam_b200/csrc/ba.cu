@@ -449,77 +449,96 @@ __global__ void __launch_bounds__(128) ba_schur_blocks_kernel(BaDev g, double* _
 // Slots are numbered column-major over the upper triangle (slot = lb(lb+1)/2 + la) so that a chunk that only sees n cameras keeps
 // its work in the first n(n+1)/2 threads and the remaining warps skip every landmark.
 constexpr int kChunkCams = 16, kChunkSlots = kChunkCams * (kChunkCams + 1) / 2, kChunkThreads = 160, kChunkBatch = 4;
+constexpr int kChunkMaxLm = 64;                                                                  // landmarks per chunk (host plan)
+constexpr int kChunkItems = (kChunkBatch * kChunkCams * 18 + kChunkThreads - 1) / kChunkThreads;  // W doubles staged per thread per batch
 
-__global__ void __launch_bounds__(kChunkThreads) ba_schur_chunks_kernel(BaDev g) {
+__global__ void __launch_bounds__(kChunkThreads, 2) ba_schur_chunks_kernel(BaDev g) {
   if (g.sc->stop) return;
   // per batch of kChunkBatch landmarks: W and Y = W V^-1 of every observing camera, addressed by LOCAL camera index
   __shared__ __align__(16) double sW[2][kChunkBatch][kChunkCams][18];
   __shared__ __align__(16) double sY[2][kChunkBatch][kChunkCams][18];
-  __shared__ unsigned int s_mask[2][kChunkBatch];
-  __shared__ int s_lm[2][kChunkBatch];
+  // per chunk, loaded once: masks, first-edge index, V^-1 and g_p of its landmarks (the dependent index chain sp_order -> pt_off ->
+  // W is paid once per chunk, not once per batch)
+  __shared__ unsigned int s_mask[kChunkMaxLm];
+  __shared__ int s_e0[kChunkMaxLm];
+  __shared__ double s_vi[kChunkMaxLm][9];
+  __shared__ double s_gp[kChunkMaxLm][3];
   const int s = threadIdx.x, chunk = blockIdx.x;
   int lb = 0;
   while (lb < kChunkCams - 1 && (lb + 1) * (lb + 2) / 2 <= s) ++lb;
   const int la = s - lb * (lb + 1) / 2;
   const bool slot = s < kChunkSlots;
   const unsigned int need = slot ? ((1u << la) | (1u << lb)) : 0xffffffffu;
-  const int t0 = g.sp_pt0[chunk], t1 = g.sp_pt0[chunk + 1];
+  const int t0 = g.sp_pt0[chunk], nlm = min(g.sp_pt0[chunk + 1] - t0, kChunkMaxLm);
+  for (int w = s; w < nlm * 12; w += kChunkThreads) {
+    const int b = w / 12, k = w - 12 * b;
+    const int j = g.sp_order[t0 + b];
+    if (k < 9) s_vi[b][k] = g.Vinv[9 * (size_t)j + k];
+    else s_gp[b][k - 9] = g.gp[3 * (size_t)j + k - 9];
+    if (k == 0) { s_mask[b] = g.sp_mask[t0 + b]; s_e0[b] = g.pt_off[j]; }
+  }
+  __syncthreads();
   double acc[36], ga[6];
 #pragma unroll
   for (int k = 0; k < 36; ++k) acc[k] = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) ga[k] = 0.0;
   bool used = false;
-  int buf = 0;
-  for (int tb = t0; tb < t1; tb += kChunkBatch, buf ^= 1) {
-    const int nb = min(kChunkBatch, t1 - tb);
-    // ---- stage W (coalesced: the blocks of a landmark are contiguous), masks, landmark ids
-    if (s < nb) {
-      s_mask[buf][s] = g.sp_mask[tb + s];
-      s_lm[buf][s] = g.sp_order[tb + s];
-    }
-    for (int w = s; w < nb * kChunkCams * 18; w += kChunkThreads) {
+  // W of a batch travels global -> registers (issued one batch ahead, in flight during the previous batch's arithmetic) -> shared
+  double pre[kChunkItems];
+  auto prefetch = [&](int tb) {
+    const int nb = min(kChunkBatch, nlm - tb);
+#pragma unroll
+    for (int q = 0; q < kChunkItems; ++q) {
+      const int w = s + q * kChunkThreads;
       const int b = w / (kChunkCams * 18), r = w - b * (kChunkCams * 18), l = r / 18, k = r - 18 * l;
-      const unsigned int m = g.sp_mask[tb + b];
-      if ((m >> l) & 1u) {
-        const int j = g.sp_order[tb + b];
-        sW[buf][b][l][k] = g.W[18 * (size_t)(g.pt_off[j] + __popc(m & ((1u << l) - 1u))) + k];
+      pre[q] = 0.0;
+      if (b < nb) {
+        const unsigned int m = s_mask[tb + b];
+        if ((m >> l) & 1u) pre[q] = g.W[18 * (size_t)(s_e0[tb + b] + __popc(m & ((1u << l) - 1u))) + k];
       }
+    }
+  };
+  prefetch(0);
+  int buf = 0;
+  for (int tb = 0; tb < nlm; tb += kChunkBatch, buf ^= 1) {
+    const int nb = min(kChunkBatch, nlm - tb);
+#pragma unroll
+    for (int q = 0; q < kChunkItems; ++q) {
+      const int w = s + q * kChunkThreads;
+      if (w < kChunkBatch * kChunkCams * 18) (&sW[buf][0][0][0])[w] = pre[q];
     }
     __syncthreads();
     // ---- Y = W V^-1 : one thread per (landmark, camera, row)
     for (int w = s; w < nb * kChunkCams * 6; w += kChunkThreads) {
       const int b = w / (kChunkCams * 6), r = w - b * (kChunkCams * 6), l = r / 6, a = r - 6 * l;
-      if ((s_mask[buf][b] >> l) & 1u) {
-        const double* Vi = g.Vinv + 9 * (size_t)s_lm[buf][b];
+      if ((s_mask[tb + b] >> l) & 1u) {
+        const double* Vi = s_vi[tb + b];
         const double w0 = sW[buf][b][l][a * 3], w1 = sW[buf][b][l][a * 3 + 1], w2 = sW[buf][b][l][a * 3 + 2];
 #pragma unroll
         for (int c = 0; c < 3; ++c) sY[buf][b][l][a * 3 + c] = w0 * Vi[c] + w1 * Vi[3 + c] + w2 * Vi[6 + c];
       }
     }
+    if (tb + kChunkBatch < nlm) prefetch(tb + kChunkBatch);  // (global loads in flight during the accumulation below)
     __syncthreads();
-    // ---- accumulate: slot (la, lb) += Y_la W_lb'   (the other buffer is being refilled by nobody yet: one barrier pair per batch,
-    //      the double buffer lets the next batch's staging start while slow warps still accumulate)
+    // ---- accumulate: slot (la, lb) += Y_la W_lb'
     if (slot) {
       for (int b = 0; b < nb; ++b) {
-        if ((s_mask[buf][b] & need) != need) continue;
+        if ((s_mask[tb + b] & need) != need) continue;
         used = true;
-        const double2* Y2 = reinterpret_cast<const double2*>(&sY[buf][b][la][0]);
+        const double* Yp = &sY[buf][b][la][0];
         const double2* W2 = reinterpret_cast<const double2*>(&sW[buf][b][lb][0]);
-        double Y[18], wb[18];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) { const double2 v = Y2[k]; Y[2 * k] = v.x; Y[2 * k + 1] = v.y; }
+        double wb[18];
 #pragma unroll
         for (int k = 0; k < 9; ++k) { const double2 v = W2[k]; wb[2 * k] = v.x; wb[2 * k + 1] = v.y; }
+        const bool dg = la == lb;
+        const double g0 = s_gp[tb + b][0], g1 = s_gp[tb + b][1], g2 = s_gp[tb + b][2];
 #pragma unroll
-        for (int a = 0; a < 6; ++a)
+        for (int a = 0; a < 6; ++a) {  // one row of Y at a time: 3 live values instead of 18
+          const double y0 = Yp[a * 3], y1 = Yp[a * 3 + 1], y2 = Yp[a * 3 + 2];
 #pragma unroll
-          for (int c = 0; c < 6; ++c) acc[a * 6 + c] += Y[a * 3] * wb[c * 3] + Y[a * 3 + 1] * wb[c * 3 + 1] + Y[a * 3 + 2] * wb[c * 3 + 2];
-        if (la == lb) {
-          const double* gp = g.gp + 3 * (size_t)s_lm[buf][b];
-          const double g0 = gp[0], g1 = gp[1], g2 = gp[2];
-#pragma unroll
-          for (int a = 0; a < 6; ++a) ga[a] += Y[a * 3] * g0 + Y[a * 3 + 1] * g1 + Y[a * 3 + 2] * g2;
+          for (int c = 0; c < 6; ++c) acc[a * 6 + c] += y0 * wb[c * 3] + y1 * wb[c * 3 + 1] + y2 * wb[c * 3 + 2];
+          if (dg) ga[a] += y0 * g0 + y1 * g1 + y2 * g2;
         }
       }
     }
@@ -1700,6 +1719,7 @@ void gb_ba_options_default(gb_ba_options* o) {
   o->lambda_init = 1e-4;
   o->pcg_max_iters = 50;
   o->pcg_tol = 1e-10;
+  o->linear_solver = 0;
 }
 
 int gb_ba_graph_destroy(gb_ctx* ctx, gb_ba_graph* g) {
@@ -1755,7 +1775,7 @@ static bool ba_schur_plan(gb_ctx* ctx, gb_ba_graph* g, int np, const std::vector
     return x < y;
   });
   const int nl = (int)ord.size();
-  const int lmax = std::min(64, std::max(8, nl / (4 * std::max(ctx->sm_count, 1))));
+  const int lmax = std::min(kChunkMaxLm, std::max(8, nl / (4 * std::max(ctx->sm_count, 1))));
   std::vector<int> ch_pt0, ch_cams;  // ch_cams: 16 per chunk, ascending, -1 padded
   std::vector<unsigned short> mask((size_t)nl, 0);
   std::vector<int> cur, merged;  // sorted cameras of the open chunk
@@ -1981,10 +2001,13 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   tr.stamp("covisibility block-CSR");
   for (int i = 0; i < nc; ++i) g->pcg_nact += (pb->cam_dof ? (pb->cam_dof[i] & 63) : 63) != 0;
   for (int i = 0; i < nc && !s_col.empty(); ++i) g->pcg_max_row_blocks = std::max(g->pcg_max_row_blocks, s_rowptr[i + 1] - s_rowptr[i]);
+  std::vector<int> chol_plan3;
+  if (d.s_nnzb > 0) g->chol_ok = ba_chol_plan_host(ctx, nc, s_rowptr.data(), s_col.data(), chol_plan3, &g->chol_blocks, &g->chol_smem);
+  const size_t b_ch = al(chol_plan3.size() * 4 + 4);
   const size_t b_sr = al((size_t)(nc + 1) * 4), b_sc = al((size_t)s_col.size() * 4 + 4);
   const bool compact_only = shard_world > 1;  // a shard only ever sees the compact reduced layout: no dense 6N x 6N buffer
   g->rbuf_doubles = d.s_nnzb > 0 ? (size_t)d.s_nnzb * 36 + 2 * (size_t)d.n6 + 8 : 0;
-  const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + b_sr + 4 * b_sc + b_cpt + b_cuv + 256;
+  const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + b_sr + 4 * b_sc + b_cpt + b_cuv + b_ch + 256;
   const size_t n6 = 6 * (size_t)nc;
   uint8_t* dblob = nullptr;
   double* cam_ticket_d = nullptr;
@@ -2045,7 +2068,7 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   auto take = [&](size_t bytes) { size_t o = off; off += bytes; return o; };
   const size_t o_pose = take(b_pose), o_pts = take(b_pts), o_dof = take(b_dof), o_pf = take(b_pf), o_oc = take(b_oc),
                o_op = take(b_op), o_uv = take(b_uv), o_info = take(b_info), o_po = take(b_po), o_co = take(b_co), o_cp = take(b_cp),
-               o_sr = take(b_sr), o_sc = take(b_sc), o_sb = take(b_sc), o_su = take(b_sc), o_st = take(b_sc), o_cpt = take(b_cpt), o_cuv = take(b_cuv);
+               o_sr = take(b_sr), o_sc = take(b_sc), o_sb = take(b_sc), o_su = take(b_sc), o_st = take(b_sc), o_cpt = take(b_cpt), o_cuv = take(b_cuv), o_ch = take(b_ch);
   memcpy(h + o_pose, pb->cam_pose_wc, (size_t)nc * 56);
   if (np > 0) memcpy(h + o_pts, pb->points + 3 * (size_t)lo, (size_t)np * 24);
   for (int i = 0; i < nc; ++i) h[o_dof + i] = pb->cam_dof ? (pb->cam_dof[i] & 63) : 63;
@@ -2081,6 +2104,8 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   if (!s_brow.empty()) memcpy(h + o_sb, s_brow.data(), s_brow.size() * 4);
   if (!s_upper.empty()) memcpy(h + o_su, s_upper.data(), s_upper.size() * 4);
   if (!s_tidx.empty()) memcpy(h + o_st, s_tidx.data(), s_tidx.size() * 4);
+  if (!chol_plan3.empty()) memcpy(h + o_ch, chol_plan3.data(), chol_plan3.size() * 4);
+  g->chol_plan = (const int*)(dblob + o_ch);
   g->sorted_to_orig.swap(order);
   tr.stamp("blob fill");
   GB_CUDA(ctx, cudaMemcpyAsync(dblob, h, blob, cudaMemcpyHostToDevice, ctx->stream));
@@ -2147,6 +2172,12 @@ int gb_ba_graph_begin(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt_in) 
     return GB_ERR_INVALID;
   }
   if (opt.max_iterations < 0 || opt.pcg_max_iters < 0) return GB_ERR_INVALID;
+  if (opt.linear_solver != 0 && opt.linear_solver != 1) { gb_set_error(ctx, "gb_ba: linear_solver must be 0 (PCG) or 1 (direct)"); return GB_ERR_INVALID; }
+  if (opt.linear_solver == 1 && g->d.nc > 0 && (!g->chol_ok || g->shard_world > 1)) {
+    gb_set_error(ctx, "gb_ba: the direct solver needs the block skyline of the reduced camera system to fit one SM's shared memory "
+                      "(%d cameras here) and a single-GPU solve; use linear_solver = 0 (PCG)", g->d.nc);
+    return GB_ERR_INVALID;
+  }
   g->opt = opt;
   BaScalars h;
   memset(&h, 0, sizeof h);
@@ -2298,6 +2329,7 @@ static int ba_pcg_dispatch(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   BaDev& d = g->d;
   cudaStream_t s = ctx->stream;
   if (d.nc <= 0) return GB_OK;
+  if (g->opt.linear_solver == 1) return ba_chol_launch(ctx, g, buf, false);
   if (g->pcg_sparse && buf == g->buf) {
     if (g->pcg_nact <= kSpSmallCams) {
       BA_SPARSE_SMALL<<<1, kSpSmallThreads, g->pcg_sparse_smem, s>>>(d, buf, (int)g->opt.pcg_max_iters);
@@ -2393,11 +2425,15 @@ static int ba_graph_solve_impl(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options*
       // (programmatic dependent launches: each kernel is scheduled while its predecessor drains)
       GB_CUDA(ctx, gb_launch_pdl(ba_linearize_kernel, dim3(pt_blocks + cam_blocks), dim3(kPtThreads), 0, s, d, cam_blocks)); GB_LAUNCH_CHECK(ctx);
       GB_CUDA(ctx, gb_launch_pdl(ba_schur_blocks_kernel, dim3(d.s_nupper), dim3(128), 0, s, d, g->buf)); GB_LAUNCH_CHECK(ctx);
-      if (g->pcg_nact <= kSpSmallCams) GB_CUDA(ctx, gb_launch_pdl(BA_SPARSE_SMALL, dim3(1), dim3(kSpSmallThreads), g->pcg_sparse_smem, s, d, g->buf, (int)g->opt.pcg_max_iters));
-      else GB_CUDA(ctx, gb_launch_pdl(BA_SPARSE_LARGE, dim3(1), dim3(kSpLargeThreads), g->pcg_sparse_smem, s, d, g->buf, (int)g->opt.pcg_max_iters));
-      GB_LAUNCH_CHECK(ctx);
+      if (g->opt.linear_solver == 1) {
+        GB_CHECK(ba_chol_launch(ctx, g, g->buf, true));
+      } else {
+        if (g->pcg_nact <= kSpSmallCams) GB_CUDA(ctx, gb_launch_pdl(BA_SPARSE_SMALL, dim3(1), dim3(kSpSmallThreads), g->pcg_sparse_smem, s, d, g->buf, (int)g->opt.pcg_max_iters));
+        else GB_CUDA(ctx, gb_launch_pdl(BA_SPARSE_LARGE, dim3(1), dim3(kSpLargeThreads), g->pcg_sparse_smem, s, d, g->buf, (int)g->opt.pcg_max_iters));
+        GB_LAUNCH_CHECK(ctx);
+      }
       GB_CUDA(ctx, gb_launch_pdl(ba_backsub_commit_kernel, dim3(gb_div_up(d.np * kLpp, kTailThreads)), dim3(kTailThreads), 0, s, d, (const double*)g->buf)); GB_LAUNCH_CHECK(ctx);
-    } else if (g->pcg_bcsr) {  // large graph: compact block-CSR reduced system + the persistent multi-CTA PCG
+    } else if (g->pcg_bcsr && g->opt.linear_solver == 0) {  // large graph: compact block-CSR reduced system + the persistent multi-CTA PCG
       GB_CHECK(ba_reduce_local_compact(ctx, g, g->rbuf));
       GB_CHECK(ba_pcg_bcsr_launch(ctx, g, g->rbuf));
       GB_CHECK(ba_backsub_cost_compact(ctx, g, nullptr));

@@ -38,6 +38,11 @@ struct gb_ba_graph {
   unsigned int* bcsr_bar = nullptr;  // device: grid barrier counter
   double* rbuf = nullptr;        // device: compact reduced system [Sb (nnzb*36) | g~ | diag U | cost | pad]
   size_t rbuf_doubles = 0;
+  // direct solver (ba_chol.cu): skyline plan [first | rowoff | last] uploaded with the blob, when the skyline fits one SM
+  bool chol_ok = false;
+  const int* chol_plan = nullptr;
+  int chol_blocks = 0;
+  size_t chol_smem = 0;
   void* sp_alloc = nullptr;      // device allocation holding the landmark-chunk Schur plan + staging (BaDev::sp_*), or null
   // landmark shard (multi-GPU global BA): this graph holds landmarks [shard_lo, shard_hi) of the caller's problem
   int shard_lo = 0, shard_hi = 0, shard_rank = 0, shard_world = 1;
@@ -59,3 +64,8 @@ int ba_pcg_bcsr_plan(gb_ctx* ctx, gb_ba_graph* g, const int* s_rowptr_host);
 void ba_pcg_bcsr_free(gb_ba_graph* g);
 // damp + block-Jacobi PCG on the reduced camera system held in `rbuf` + retraction of the cameras (pose_new, Rt_new, x)
 int ba_pcg_bcsr_launch(gb_ctx* ctx, gb_ba_graph* g, const double* rbuf);
+
+// ---- ba_chol.cu -------------------------------------------------------------------------------------------------------------
+bool ba_chol_plan_host(gb_ctx* ctx, int nc, const int* s_rowptr, const int* s_col, std::vector<int>& plan3, int* nblocks, size_t* smem);
+// block-skyline Cholesky solve of the damped reduced camera system in the dense-layout `buf` (+ g->d.Sb block values) + retraction
+int ba_chol_launch(gb_ctx* ctx, gb_ba_graph* g, double* buf, bool pdl);

@@ -156,6 +156,12 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
   };
   apply_minv_publish();
   barrier();
+  // optional phase clocks (test hook gb_dbg_ba_pcg_profile): CTA 0 / thread 0 accumulates [setup, mat-vec + local dots, barrier 1,
+  // scalars + recurrences + publication, barrier 2, total, iterations]
+  const bool prof = g.prof != nullptr && b == 0 && tid == 0;
+  long long pc[5] = {0, 0, 0, 0, 0}, t_prev = clock64();
+  const long long t_begin = t_prev;
+  auto stamp = [&](int k) { if (prof) { const long long t = clock64(); pc[k] += t - t_prev; t_prev = t; } };
 
   const int K = a.K, sub = tid & (K - 1), groups = kBcsrThreads / K;
   double gamma_prev = 0.0, gamma0 = 0.0, alpha_prev = 1.0;
@@ -212,7 +218,9 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
       a.part[2 * b] = sg;
       a.part[2 * b + 1] = sd;
     }
+    stamp(1);
     barrier();
+    stamp(2);
     if (warp == 0) {
       double sg = 0.0, sd = 0.0;
       if (CLUSTER) {
@@ -255,7 +263,12 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
     __syncthreads();
     apply_minv_publish();
     gamma_prev = gn; alpha_prev = alpha; first = false; ++k_it;
+    stamp(3);
     barrier();
+    stamp(4);
+  }
+  if (prof) {
+    g.prof[0] = t_begin; g.prof[1] = pc[1]; g.prof[2] = pc[2]; g.prof[3] = pc[3]; g.prof[4] = pc[4]; g.prof[5] = clock64() - t_begin; g.prof[6] = k_it;
   }
   // ---- F. solution + retraction of the owned cameras ----
   for (int r = tid; r < rows; r += kBcsrThreads) g.x[6 * cam0 + r] = vx[r];

@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(kQPerCta) match_kernel(const uint4* __restrict
   if (d_nq) nq = min(max(*d_nq, 0), nq);
   if (d_nt) nt = min(max(*d_nt, 0), nt);
   if ((int)(blockIdx.x * kQPerCta) >= nq) return;  // a query tile beyond the real count: none of its CTAs has anything to merge
+  const int nsplit = d_nt ? max(1, (nt + chunk - 1) / chunk) : (int)gridDim.y;  // splits that hold train rows (>= 1: the empty-train case)
+  if ((int)blockIdx.y >= nsplit) return;
   extern __shared__ uint4 s_train[];  // chunk rows x 2 uint4
   __shared__ bool s_last;
   const int tid = threadIdx.x;
@@ -94,7 +96,6 @@ __global__ void __launch_bounds__(kQPerCta) match_kernel(const uint4* __restrict
     }
   }
 
-  const int nsplit = gridDim.y;
   if (nsplit == 1) {
     if (qi < nq) {
       if (best_idx) best_idx[qi] = b0;

@@ -228,6 +228,7 @@ class OptimizerB200 : public GSLAM::Optimizer {
     o.lambda_init = svar.GetDouble("b200.lambda", o.lambda_init);
     o.pcg_max_iters = svar.GetInt("b200.pcg_iters", o.pcg_max_iters);
     o.pcg_tol = svar.GetDouble("b200.pcg_tol", o.pcg_tol);
+    o.linear_solver = svar.GetInt("b200.linear_solver", o.linear_solver);  // 1 = direct block-skyline Cholesky (local-BA sizes)
     return o;
   }
 

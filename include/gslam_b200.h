@@ -195,6 +195,8 @@ typedef struct gb_ba_options {
   double lambda_init;       /* initial LM damping, 1e-4                                                 */
   int32_t pcg_max_iters;    /* block-Jacobi PCG iteration cap on the reduced camera system, 50         */
   double pcg_tol;           /* stop when sqrt(r'z / r0'z0) < tol, 1e-10                                 */
+  int32_t linear_solver;    /* 0 = block-Jacobi PCG on the reduced camera system (default); 1 = DIRECT: block-skyline Cholesky
+                               (exact solve; local-BA sizes: the skyline must fit one SM's shared memory, single GPU)       */
 } gb_ba_options;
 GB_API void gb_ba_options_default(gb_ba_options* opt);
 

@@ -376,6 +376,39 @@ static int ba_pcg(int nc, const double* S, const double* g, double* x, int maxit
   return it;
 }
 
+/* Direct solve of S x = g (S dense SPD, n6 x n6, destroyed): plain Cholesky + two substitutions.  A non-positive pivot gives the zero
+ * step (LM then rejects it and raises lambda) -- the convention of gslam_b200/csrc/ba_chol.cu.  Returns 0. */
+static int ba_chol_solve(int nc, double* S, const double* g, double* x) {
+  int n = 6 * nc, fail = 0;
+  for (int j = 0; j < n && !fail; ++j) {
+    double d = S[(size_t)j * n + j];
+    for (int m = 0; m < j; ++m) d -= S[(size_t)j * n + m] * S[(size_t)j * n + m];
+    if (!(d > 0.0) || !(d < 1e300)) { fail = 1; break; }
+    double l = sqrt(d);
+    S[(size_t)j * n + j] = l;
+    for (int i = j + 1; i < n; ++i) {
+      double v = S[(size_t)i * n + j];
+      for (int m = 0; m < j; ++m) v -= S[(size_t)i * n + m] * S[(size_t)j * n + m];
+      S[(size_t)i * n + j] = v / l;
+    }
+  }
+  if (!fail) {
+    for (int i = 0; i < n; ++i) {
+      double v = g[i];
+      for (int m = 0; m < i; ++m) v -= S[(size_t)i * n + m] * x[m];
+      x[i] = v / S[(size_t)i * n + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      double v = x[i];
+      for (int m = i + 1; m < n; ++m) v -= S[(size_t)m * n + i] * x[m];
+      x[i] = v / S[(size_t)i * n + i];
+    }
+    for (int i = 0; i < n; ++i) if (!isfinite(x[i])) fail = 1;
+  }
+  if (fail) for (int i = 0; i < n; ++i) x[i] = 0.0;
+  return 0;
+}
+
 /* Exposed for kernel-level parity tests: S (6nc x 6nc), gt (6nc) and the PCG solution dc (6nc) at the input estimate. */
 int orc_ba_reduced_system(const gb_ba_problem* pb, double delta, double lambda, int pcg_maxit, double pcg_tol, double* S, double* gt, double* dc, int* pcg_iters) {
   if (validate(pb)) return GB_ERR_INVALID;
@@ -392,7 +425,7 @@ int orc_ba_reduced_system(const gb_ba_problem* pb, double delta, double lambda, 
 
 int orc_ba_solve(gb_ba_problem* pb, const gb_ba_options* opt_in, gb_ba_result* res) {
   gb_ba_options opt;
-  if (opt_in) opt = *opt_in; else { opt.projection = 0; opt.huber_delta = 0.01; opt.max_iterations = 500; opt.verbose = 0; opt.function_tolerance = 1e-6; opt.lambda_init = 1e-4; opt.pcg_max_iters = 50; opt.pcg_tol = 1e-10; }
+  if (opt_in) opt = *opt_in; else { opt.projection = 0; opt.huber_delta = 0.01; opt.max_iterations = 500; opt.verbose = 0; opt.function_tolerance = 1e-6; opt.lambda_init = 1e-4; opt.pcg_max_iters = 50; opt.pcg_tol = 1e-10; opt.linear_solver = 0; }
   if (validate(pb) || opt.projection != 0) return GB_ERR_INVALID;
   ba_state s;
   state_init(&s, pb, opt.huber_delta);
@@ -409,7 +442,8 @@ int orc_ba_solve(gb_ba_problem* pb, const gb_ba_options* opt_in, gb_ba_result* r
   int it = 0;
   for (; it < opt.max_iterations; ++it) {
     ba_schur(&s, lambda, S, gt, Vinv);
-    R.pcg_iterations += ba_pcg(nc, S, gt, dc, opt.pcg_max_iters, opt.pcg_tol);
+    if (opt.linear_solver == 1) ba_chol_solve(nc, S, gt, dc);
+    else R.pcg_iterations += ba_pcg(nc, S, gt, dc, opt.pcg_max_iters, opt.pcg_tol);
     for (int i = 0; i < nc; ++i) {
       double d[6]; int dm = dofmask(&s, i);
       for (int a = 0; a < 6; ++a) d[a] = ((dm >> a) & 1) ? dc[6 * i + a] : 0.0;

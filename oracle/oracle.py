@@ -26,7 +26,7 @@ class BaProblemC(C.Structure):
 class BaOptionsC(C.Structure):
     _fields_ = [("projection", C.c_int32), ("huber_delta", C.c_double), ("max_iterations", C.c_int32),
                 ("verbose", C.c_int32), ("function_tolerance", C.c_double), ("lambda_init", C.c_double),
-                ("pcg_max_iters", C.c_int32), ("pcg_tol", C.c_double)]
+                ("pcg_max_iters", C.c_int32), ("pcg_tol", C.c_double), ("linear_solver", C.c_int32)]
 
 
 class BaResultC(C.Structure):
@@ -51,7 +51,7 @@ class OrbCfgC(C.Structure):
 
 
 def default_ba_options(**kw) -> BaOptionsC:
-    o = BaOptionsC(0, 0.01, 500, 0, 1e-6, 1e-4, 50, 1e-10)
+    o = BaOptionsC(0, 0.01, 500, 0, 1e-6, 1e-4, 50, 1e-10, 0)
     for k, v in kw.items():
         setattr(o, k, v)
     return o

@@ -324,3 +324,29 @@ def test_global_ba_full_size_matches_oracle(ctx):
     et, eq = _pose_err(pb.cam_pose_wc, want.cam_pose_wc)
     assert et < 1e-5 and eq < 1e-5, (et, eq)
     assert np.abs(pb.points - want.points).max() / np.abs(want.points).max() < 1e-5
+
+
+@pytest.mark.parametrize("kw,iters", [(dict(n_cams=10, n_points=200, all_visible=True, n_fixed=2, seed=42), 6),
+                                      (dict(n_cams=50, n_points=2000, obs_per_point=5, n_fixed=2, seed=42), 10),
+                                      (dict(n_cams=30, n_points=900, obs_per_point=7, n_fixed=1, seed=8), 8)])
+def test_direct_solver_matches_oracle(ctx, kw, iters):
+    """gb_ba_options::linear_solver = 1 (block-skyline Cholesky in one CTA, csrc/ba_chol.cu) against the oracle's dense Cholesky:
+    the linear solves are exact on both sides, so the LM trajectories (accept / reject pattern included) must coincide."""
+    pb = synth.synth_ba(**kw)
+    if kw.get("n_fixed") == 1:  # partial dof masks: second camera keeps its translation fixed
+        pb.cam_dof[1] = 0b111000
+    want = pb.copy()
+    r0 = oracle.ba_solve(want, max_iterations=iters, function_tolerance=0.0, linear_solver=1)
+    r = ctx.ba_solve(pb, cfg(maxIterations=iters, functionTolerance=0.0, linearSolver=1))
+    assert r.iterations == r0.iterations and r.accepted == r0.accepted and r.pcg_iterations == 0
+    assert abs(r.final_cost - r0.final_cost) / r0.final_cost < 1e-8
+    et, eq = _pose_err(pb.cam_pose_wc, want.cam_pose_wc)
+    assert et < 1e-7 and eq < 1e-7, (et, eq)
+    assert np.abs(pb.points - want.points).max() / np.abs(want.points).max() < 1e-7
+
+
+def test_direct_solver_is_refused_when_the_skyline_does_not_fit(ctx):
+    from gslam_b200 import capi
+    big = synth.synth_ba(120, 600, all_visible=True, n_fixed=2, seed=5)   # every camera sees every landmark: full 120 x 120 block matrix
+    with pytest.raises(capi.GbError):
+        ctx.ba_solve(big, cfg(maxIterations=2, functionTolerance=0.0, linearSolver=1))

@@ -116,20 +116,20 @@ def test_global_ba_sharded_over_all_gpus_through_reference_api():
     ndev = min(n.value, 8)
     pb = synth.synth_ba(n_cams=60, n_points=6000, obs_per_point=8, n_fixed=2, seed=11)
     want = pb.copy()
-    # (PCG run to its tolerance on both sides: an unconverged Krylov solve amplifies summation-order differences)
-    oracle.ba_solve(want, max_iterations=6, function_tolerance=0.0, pcg_max_iters=400)
+    oracle.ba_solve(want, max_iterations=6, function_tolerance=0.0, pcg_max_iters=40)
     with tempfile.TemporaryDirectory() as d:
         write_ba(os.path.join(d, "in.bin"), pb, 6, 0.0)
         r = run("ba", os.path.join(d, "in.bin"), os.path.join(d, "out.bin"), "b200.devices=" + ",".join(str(k) for k in range(ndev)),
-                "b200.multi_min_obs=1000", "b200.pcg_iters=400")
+                "b200.multi_min_obs=1000", "b200.pcg_iters=40")
         assert r.returncode == 0, r.stderr
         raw = open(os.path.join(d, "out.bin"), "rb").read()
     assert struct.unpack("<i", raw[:4])[0] == 1
     poses = np.frombuffer(raw[4:4 + 64 * pb.n_cams], np.float64).reshape(-1, 8)
     pts = np.frombuffer(raw[4 + 64 * pb.n_cams:], np.float64).reshape(-1, 3)
     s_ = np.sign(np.sum(poses[:, :4] * want.cam_pose_wc[:, :4], axis=1))[:, None]
-    # two Krylov solves that both stop at the relative tolerance 1e-10 agree to (condition number x tolerance), not to machine
-    # precision: 1e-4 on the unit quaternions here; translations / points relative to the scene scale as in tests/test_dist.py
+    # same iteration counts on both sides (a long straight trajectory has a very weak scale-drift mode: Krylov solves run "to
+    # convergence" on the two sides would differ along it by condition number x tolerance); 1e-4 on the unit quaternions,
+    # translations / points relative to the scene scale as in tests/test_dist.py
     assert np.abs(poses[:, :4] * s_ - want.cam_pose_wc[:, :4]).max() < 1e-4
     assert np.abs(poses[:, 4:7] - want.cam_pose_wc[:, 4:]).max() < 1e-5 * max(1.0, np.abs(want.cam_pose_wc[:, 4:]).max())
     assert np.abs(pts - want.points).max() < 1e-5 * np.abs(want.points).max()
