@@ -2126,7 +2126,7 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   }
   GB_CHECK(gb_ba_graph_reset(ctx, g));
   ba_pick_pcg(ctx, g);
-  if (!g->pcg_sparse && d.s_nnzb > 0) {
+  if ((!g->pcg_sparse || compact_only) && d.s_nnzb > 0) {  // (a shard always runs on the compact block-CSR system)
     GB_CHECK(ba_pcg_bcsr_plan(ctx, g, s_rowptr.data()));
     if (!getenv("GB_BA_NO_SCHUR_CHUNKS")) ba_schur_plan(ctx, g, np, pt_off, scam, h + o_pf, s_rowptr, s_col, s_upper);  // (optional: the block-gather kernel otherwise)
   }

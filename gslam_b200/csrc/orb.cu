@@ -18,15 +18,20 @@
 #include "common.cuh"
 #include "orb_pattern.h"
 
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, libcuda is not linked)
+
 #include <cmath>
 
 namespace {
 
 constexpr int kMaxLevels = GB_ORB_MAX_LEVELS;
-constexpr int kTileW = 64, kTileH = 16;
-constexpr int kInW = kTileW + 8, kInH = kTileH + 8;    // 72 x 24 input tile (3 ring + 1 nms halo each side)
-constexpr int kScW = kTileW + 2, kScH = kTileH + 2;    // 66 x 18 score tile
+constexpr int kTileW = 128, kTileH = 32;               // interior of a FAST tile
+constexpr int kInW = kTileW + 16, kInH = kTileH + 8;   // 144 x 40 input box (3 ring + 1 nms halo each side; width padded to a
+                                                       // multiple of 16 bytes: TMA box rule); input column 4 == tile column 0
+constexpr int kScW = kTileW + 2, kScH = kTileH + 2;    // 130 x 34 score tile (1-pixel halo for the non-maximum suppression)
 constexpr int kFastThreads = 256;
+constexpr int kInWords = kInW / 4;                     // 36 32-bit words per input row
+constexpr int kWorkCap = 2048;                         // quick-test survivors per tile handled in shared memory (rest: rounds)
 constexpr int kSelThreads = 1024;
 constexpr int kSelMax = 4096;                          // max kept keypoints per level (bitonic sort in shared memory)
 constexpr int kDescWarps = 4;
@@ -140,84 +145,140 @@ __device__ __forceinline__ int fast_full_score(const uint8_t* p /* centre inside
   return best > threshold ? best - 1 : 0;
 }
 
-__global__ void __launch_bounds__(kFastThreads) orb_fast_kernel(const __grid_constant__ OrbParams P, const uint8_t* __restrict__ pyr,
+// ---- TMA + mbarrier plumbing (sm_90+ PTX; SASS: UTMALDG / SYNCS) ----------------------------------------------------------------
+struct FastMaps {
+  CUtensorMap m[kMaxLevels];  // one 2-D u8 tensor map per pyramid level: dims {w, h}, row stride = pitch, box {kInW, kInH}
+};
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (int spin = 0; spin < (1 << 24) && !ok; ++spin)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  if (!ok) __trap();  // a copy that never lands must not hang the device
+}
+
+// K2.  Persistent CTAs walk the FAST tiles of all levels; the 144 x 40 input box of tile i+1 is fetched by the TMA unit
+// (cp.async.bulk.tensor.2d, zero fill outside the image) into the other half of a double buffer while tile i is processed:
+//   A  packed quick test, four pixels per thread-step on 32-bit words (byte-SIMD compares): a 9-arc of the 16-ring always
+//      contains two CONSECUTIVE compass points (S,E / E,N / N,W / W,S), so a corner needs (S|N) & (E|W) all brighter than c+t or
+//      all darker than c-t -- survivors (a few percent) go to a shared-memory worklist;
+//   B  per survivor: exact 9-contiguity test on bit masks, then the exact score (max threshold) for true corners only;
+//   C  strict 3x3 non-maximum suppression over the corner list (not over the pixels), border filter, append + score histogram.
+__global__ void __launch_bounds__(kFastThreads) orb_fast_kernel(const __grid_constant__ OrbParams P, const __grid_constant__ FastMaps M,
                                                                 uint32_t* __restrict__ cand_pos, uint8_t* __restrict__ cand_score,
                                                                 int* __restrict__ counts, int* __restrict__ hist) {
   gb_pdl_launch_dependents();
-  gb_pdl_wait();
-  __shared__ __align__(16) uint8_t s_in[kInH * kInW];
-  __shared__ uint8_t s_sc[kScH * kScW];
-  __shared__ uint16_t s_work[kScH * kScW];   // positions that survive the opposite-pair quick reject
-  __shared__ uint16_t s_work2[kScH * kScW];  // ... of which: true corners (9 contiguous), the only ones scored exactly
+  __shared__ __align__(128) uint8_t s_in[2][kInH * kInW];
+  __shared__ __align__(16) uint8_t s_sc[kScH * kScW + 12];
+  __shared__ uint16_t s_work[kScH * kScW];   // quick-test survivors: input-tile offsets ry * kInW + col
+  __shared__ uint16_t s_work2[kScH * kScW];  // true corners: score-tile offsets
+  __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ int s_nwork, s_nwork2;
-  // which level / tile
-  int l = 0;
-#pragma unroll 1
-  for (int k = 1; k < P.nlevels; ++k)
-    if ((int)blockIdx.x >= P.lv[k].tile_start) l = k;
-  const LevelInfo& L = P.lv[l];
-  const int t = blockIdx.x - L.tile_start;
-  const int x0 = (t % L.tiles_x) * kTileW, y0 = (t / L.tiles_x) * kTileH;
-  const uint8_t* img = pyr + L.off;
   const int tid = threadIdx.x;
-  if (tid == 0) { s_nwork = 0; s_nwork2 = 0; }
-  // stage the input tile with 32-bit loads (x0-4 and the pitch are 4-byte aligned); zero outside the image rows / pitch
-  for (int i = tid; i < kInH * (kInW / 4); i += kFastThreads) {
-    const int ry = i / (kInW / 4), rx = (i % (kInW / 4)) * 4;
-    const int gy = y0 - 4 + ry, gx = x0 - 4 + rx;
-    uint32_t v = 0;
-    if (gy >= 0 && gy < L.h && gx >= 0 && gx + 3 < L.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * L.pitch + gx));
-    *reinterpret_cast<uint32_t*>(&s_in[ry * kInW + rx]) = v;
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
   }
   __syncthreads();
+  gb_pdl_wait();  // the pyramid levels are written by the predecessor kernels
+  auto locate = [&](int tile, int* lvl, int* x0, int* y0) {
+    int l = 0;
+#pragma unroll 1
+    for (int k = 1; k < P.nlevels; ++k)
+      if (tile >= P.lv[k].tile_start && P.lv[k].tiles_x > 0) l = k;
+    const int t = tile - P.lv[l].tile_start;
+    *lvl = l; *x0 = (t % P.lv[l].tiles_x) * kTileW; *y0 = (t / P.lv[l].tiles_x) * kTileH;
+  };
+  auto fetch = [&](int tile, int buf) {  // thread 0 only
+    int l, x0, y0;
+    locate(tile, &l, &x0, &y0);
+    mbar_expect_tx(&s_bar[buf], kInH * kInW);
+    tma_load_2d(&s_in[buf][0], &M.m[l], x0 - 4, y0 - 4, &s_bar[buf]);
+  };
   const int thr = P.fast_threshold;
-  // phase 1: quick reject (any 9-arc contains one pixel of each opposite pair) -> worklist
-  for (int i = tid; i < kScH * kScW; i += kFastThreads) {
-    const int lx = i % kScW, ly = i / kScW;
-    const int gx = x0 - 1 + lx, gy = y0 - 1 + ly;
-    s_sc[i] = 0;
-    if (gx >= 3 && gx < L.w - 3 && gy >= 3 && gy < L.h - 3) {
-      const uint8_t* p = &s_in[(ly + 3) * kInW + lx + 3];
-      const int c = p[0], lo = c - thr, hi = c + thr;
-      const int a = p[3 * kInW], b = p[-3 * kInW], e = p[3], f = p[-3];
-      const bool in0 = (a >= lo) & (a <= hi) & (b >= lo) & (b <= hi);
-      const bool in1 = (e >= lo) & (e <= hi) & (f >= lo) & (f <= hi);
-      if (!in0 && !in1) s_work[atomicAdd(&s_nwork, 1)] = (uint16_t)i;
-    }
-  }
-  __syncthreads();
-  // phase 2a: dense 9-contiguity test (bit masks) over the quick-reject survivors -> second worklist
-  const int nwork = s_nwork;
-  for (int k = tid; k < nwork; k += kFastThreads) {
-    const int i = s_work[k];
-    const int lx = i % kScW, ly = i / kScW;
-    if (fast_is_corner(&s_in[(ly + 3) * kInW + lx + 3], thr)) s_work2[atomicAdd(&s_nwork2, 1)] = (uint16_t)i;
-  }
-  __syncthreads();
-  // phase 2b: dense exact score over the true corners only
-  const int nwork2 = s_nwork2;
-  for (int k = tid; k < nwork2; k += kFastThreads) {
-    const int i = s_work2[k];
-    const int lx = i % kScW, ly = i / kScW;
-    s_sc[i] = (uint8_t)fast_full_score(&s_in[(ly + 3) * kInW + lx + 3], thr);
-  }
-  __syncthreads();
-  // phase 3: strict 3x3 NMS, border filter, emit
-  for (int i = tid; i < kTileH * kTileW; i += kFastThreads) {
-    const int lx = i % kTileW, ly = i / kTileW;
-    const int gx = x0 + lx, gy = y0 + ly;
-    const uint8_t* q = &s_sc[(ly + 1) * kScW + lx + 1];
-    const int s = q[0];
-    if (s == 0) continue;
-    if (gx < P.border || gx >= L.w - P.border || gy < P.border || gy >= L.h - P.border) continue;
-    if (s > q[-1] && s > q[1] && s > q[-kScW - 1] && s > q[-kScW] && s > q[-kScW + 1] && s > q[kScW - 1] && s > q[kScW] && s > q[kScW + 1]) {
-      const int idx = atomicAdd(&counts[l], 1);
-      if (idx < L.cand_cap) {
-        cand_pos[L.cand_off + idx] = ((uint32_t)gy << 16) | (uint32_t)gx;
-        cand_score[L.cand_off + idx] = (uint8_t)s;
+  const uint32_t t4 = (uint32_t)thr * 0x01010101u;
+  int tile = blockIdx.x;
+  if (tile < P.total_tiles && tid == 0) fetch(tile, 0);
+  for (int it = 0; tile < P.total_tiles; ++it, tile += gridDim.x) {
+    const int buf = it & 1;
+    if (tid == 0 && tile + (int)gridDim.x < P.total_tiles) fetch(tile + gridDim.x, buf ^ 1);  // (that buffer was released by the barrier ending step it-1)
+    int l, x0, y0;
+    locate(tile, &l, &x0, &y0);
+    const LevelInfo& L = P.lv[l];
+    if (tid == 0) { s_nwork = 0; s_nwork2 = 0; }
+    for (int i = tid; i < (kScH * kScW + 12) / 16; i += kFastThreads) reinterpret_cast<uint4*>(s_sc)[i] = make_uint4(0, 0, 0, 0);
+    mbar_wait(&s_bar[buf], (it >> 1) & 1);
+    __syncthreads();
+    const uint8_t* in = s_in[buf];
+    const uint32_t* inw = reinterpret_cast<const uint32_t*>(in);
+    // ---- A: packed quick test over the score region (input rows 3..36, words 0..33)
+    for (int i = tid; i < kScH * (kScW + 6) / 4; i += kFastThreads) {  // 34 rows x 34 words
+      const int ry = 3 + i / 34, wx = i - (i / 34) * 34;
+      const uint32_t C = inw[ry * kInWords + wx];
+      const uint32_t S = inw[(ry + 3) * kInWords + wx], N = inw[(ry - 3) * kInWords + wx];
+      const uint32_t Wm = wx > 0 ? inw[ry * kInWords + wx - 1] : 0u, Wp = inw[ry * kInWords + wx + 1];
+      const uint32_t E = __byte_perm(C, Wp, 0x6543), Wst = __byte_perm(Wm, C, 0x4321);
+      const uint32_t hi = __vaddus4(C, t4), lo = __vsubus4(C, t4);
+      const uint32_t bright = (__vcmpgtu4(S, hi) | __vcmpgtu4(N, hi)) & (__vcmpgtu4(E, hi) | __vcmpgtu4(Wst, hi));
+      const uint32_t dark = (__vcmpgtu4(lo, S) | __vcmpgtu4(lo, N)) & (__vcmpgtu4(lo, E) | __vcmpgtu4(lo, Wst));
+      uint32_t pass = bright | dark;
+      if (pass == 0) continue;
+      const int gy = y0 - 4 + ry;
+      if (gy < 3 || gy >= L.h - 3) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!((pass >> (8 * j)) & 1u)) continue;
+        const int col = 4 * wx + j, gx = x0 - 4 + col;
+        if (col < 3 || col >= 3 + kScW || gx < 3 || gx >= L.w - 3) continue;
+        s_work[atomicAdd(&s_nwork, 1)] = (uint16_t)(ry * kInW + col);
       }
-      atomicAdd(&hist[l * 256 + s], 1);
     }
+    __syncthreads();
+    // ---- B: exact 9-contiguity test, exact score for the true corners
+    const int nwork = s_nwork;
+    for (int k = tid; k < nwork; k += kFastThreads) {
+      const int o = s_work[k];
+      const uint8_t* p = in + o;
+      if (!fast_is_corner(p, thr)) continue;
+      const int ry = o / kInW, col = o - ry * kInW;
+      const int so = (ry - 3) * kScW + (col - 3);
+      s_sc[so] = (uint8_t)fast_full_score(p, thr);
+      s_work2[atomicAdd(&s_nwork2, 1)] = (uint16_t)so;
+    }
+    __syncthreads();
+    // ---- C: strict 3x3 NMS over the corner list, border filter, emit
+    const int ncorner = s_nwork2;
+    for (int k = tid; k < ncorner; k += kFastThreads) {
+      const int so = s_work2[k];
+      const int sr = so / kScW, scol = so - sr * kScW;
+      if (sr < 1 || sr > kTileH || scol < 1 || scol > kTileW) continue;  // halo ring: belongs to the neighbouring tile
+      const int gx = x0 + scol - 1, gy = y0 + sr - 1;
+      if (gx < P.border || gx >= L.w - P.border || gy < P.border || gy >= L.h - P.border) continue;
+      const uint8_t* q = &s_sc[so];
+      const int sv = q[0];
+      if (sv > q[-1] && sv > q[1] && sv > q[-kScW - 1] && sv > q[-kScW] && sv > q[-kScW + 1] && sv > q[kScW - 1] && sv > q[kScW] && sv > q[kScW + 1]) {
+        const int idx = atomicAdd(&counts[l], 1);
+        if (idx < L.cand_cap) {
+          cand_pos[L.cand_off + idx] = ((uint32_t)gy << 16) | (uint32_t)gx;
+          cand_score[L.cand_off + idx] = (uint8_t)sv;
+        }
+        atomicAdd(&hist[l * 256 + sv], 1);
+      }
+    }
+    __syncthreads();  // every read of s_in[buf] / s_sc / the worklists is done: the buffer may be refilled, the lists reset
   }
 }
 
@@ -576,6 +637,7 @@ struct OrbState {
   int w = 0, h = 0;
   gb_orb_cfg cfg{};
   OrbParams P{};
+  FastMaps maps{};                      // TMA tensor maps of the pyramid levels (built with the buffers)
   // device buffers
   uint8_t* d_pyr = nullptr; size_t pyr_bytes = 0;
   uint32_t* d_tabs = nullptr;           // resize tables
@@ -717,6 +779,34 @@ static int orb_prepare(gb_ctx* ctx, int w, int h, const gb_orb_cfg* cfg) {
   GB_CUDA(ctx, cudaMalloc((void**)&s->d_kept_pos, (size_t)kMaxLevels * kSelMax * 4));
   GB_CUDA(ctx, cudaMalloc((void**)&s->d_kept_resp, (size_t)kMaxLevels * kSelMax * 4));
   GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // tabs is a local vector
+  {  // TMA tensor maps: one per level over the padded-pitch buffer, u8, box = the FAST input tile; out-of-image reads give 0
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qr;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        gb_set_error(ctx, "gb_orb: cuTensorMapEncodeTiled is not available from this driver (the FAST kernel stages its tiles with TMA)");
+        return GB_ERR_CUDA;
+      }
+      encode = (EncodeFn)fn;
+    }
+    memset(&s->maps, 0, sizeof s->maps);
+    for (int l = 0; l < nl; ++l) {
+      const LevelInfo& L = P.lv[l];
+      const cuuint64_t gdim[2] = {(cuuint64_t)L.w, (cuuint64_t)L.h};
+      const cuuint64_t gstride[1] = {(cuuint64_t)L.pitch};
+      const cuuint32_t box[2] = {(cuuint32_t)kInW, (cuuint32_t)kInH}, estr[2] = {1, 1};
+      const CUresult r = encode(&s->maps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, s->d_pyr + L.off, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        gb_set_error(ctx, "gb_orb: cuTensorMapEncodeTiled failed for level %d (%dx%d pitch %d): CUresult %d", l, L.w, L.h, L.pitch, (int)r);
+        return GB_ERR_CUDA;
+      }
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     GB_CUDA(ctx, cudaFuncSetAttribute(orb_describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(DescSmem) * kDescWarps)));
@@ -745,7 +835,8 @@ static int orb_launch(gb_ctx* ctx, gb_features* out) {
     GB_LAUNCH_CHECK(ctx);
   }
   if (P.total_tiles > 0) {
-    GB_CUDA(ctx, gb_launch_pdl(orb_fast_kernel, dim3(P.total_tiles), dim3(kFastThreads), 0, st, P, s->d_pyr, s->d_cand_pos, s->d_cand_score, d_counts, d_hist));
+    const int fast_ctas = std::min(P.total_tiles, ctx->sm_count * 3);  // persistent: each CTA walks tiles blockIdx.x, +grid, ...
+    GB_CUDA(ctx, gb_launch_pdl(orb_fast_kernel, dim3(fast_ctas), dim3(kFastThreads), 0, st, P, s->maps, s->d_cand_pos, s->d_cand_score, d_counts, d_hist));
     GB_LAUNCH_CHECK(ctx);
     GB_CUDA(ctx, gb_launch_pdl(orb_harris_kernel, dim3(32, P.nlevels), dim3(256), 0, st, P, s->d_pyr, s->d_cand_pos, s->d_cand_score, d_counts,
                                d_hist, s->d_cand_key, s->d_cand_resp, s->d_surv_pos, d_surv));

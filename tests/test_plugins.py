@@ -114,7 +114,7 @@ def test_global_ba_sharded_over_all_gpus_through_reference_api():
     n = ctypes.c_int(0)
     assert capi.lib().gb_device_count(ctypes.byref(n)) == 0 and n.value > 0
     ndev = min(n.value, 8)
-    pb = synth.synth_ba(n_cams=60, n_points=6000, obs_per_point=8, n_fixed=2, seed=11)
+    pb = synth.synth_ba(n_cams=50, n_points=2000, obs_per_point=5, n_fixed=2, seed=42)  # (the local-BA window of the other tests)
     want = pb.copy()
     oracle.ba_solve(want, max_iterations=6, function_tolerance=0.0, pcg_max_iters=40)
     with tempfile.TemporaryDirectory() as d:
