@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
   if (g.sc->stop) return;  // uniform over the grid
   extern __shared__ __align__(16) double sm[];
   __shared__ double s_warp[2][kBcsrThreads / 32];
-  __shared__ double s_scal[4];  // gamma, delta (this iteration), broadcast
+  __shared__ double s_scal[4];  // gamma, delta, alpha, beta (this iteration), broadcast
+  __shared__ int s_go;
   __shared__ double s_cpart[2][16];  // CLUSTER: (gamma, delta) partials of every CTA of the cluster, written by the peers
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x, b = blockIdx.x;
   const int n6 = g.n6;
@@ -179,12 +180,18 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
       double acc = 0.0;
       if (r < rows) {
         const int c = r / 6, comp = r - 6 * c;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;  // three independent chains (the fp64 pipe is deep; a single chain is latency-bound)
         for (int t = rp[c] + sub; t < rp[c + 1]; t += K) {
           const double* row = Sp + (size_t)t * bstride + comp * 6;
           const double* uc = u_full + 6 * col[t];
-#pragma unroll
-          for (int q = 0; q < 6; ++q) acc += row[q] * uc[q];
+          a0 += row[0] * uc[0];
+          a1 += row[1] * uc[1];
+          a2 += row[2] * uc[2];
+          a0 += row[3] * uc[3];
+          a1 += row[4] * uc[4];
+          a2 += row[5] * uc[5];
         }
+        acc = (a0 + a1) + a2;
       }
       for (int o = K >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (r < rows && sub == 0) {
@@ -235,22 +242,32 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
       }
       if (lane == 0) { s_scal[0] = sg; s_scal[1] = sd; }
     }
-    __syncthreads();
-    const double gn = s_scal[0], dl = s_scal[1];
-    double alpha, beta;
-    if (first) {
-      gamma0 = gn;
-      if (!(gn > 0.0) || !(dl > 0.0)) break;
-      alpha = gn / dl;
-      beta = 0.0;
-    } else {
-      if (!(gn > 0.0) || gn < tol * tol * gamma0) break;  // convergence test of the previous update
-      beta = gn / gamma_prev;
-      const double den = dl - beta * gn / alpha_prev;
-      if (!(den > 0.0)) break;
-      alpha = gn / den;
+    // lane 0 of warp 0 alone runs the scalar recurrences (three fp64 divisions cost ~340 clk of dependent latency AND fp64-pipe
+    // time in every warp that repeats them); everybody reads (alpha, beta, verdict) after the barrier
+    if (tid == 0) {
+      const double gn = s_scal[0], dl = s_scal[1];
+      double alpha = 0.0, beta = 0.0;
+      int go = 1;
+      if (first) {
+        gamma0 = gn;
+        if (!(gn > 0.0) || !(dl > 0.0)) go = 0;
+        else alpha = gn / dl;
+      } else {
+        if (!(gn > 0.0) || gn < tol * tol * gamma0) go = 0;  // convergence test of the previous update
+        else {
+          beta = gn / gamma_prev;
+          const double den = dl - beta * gn / alpha_prev;
+          if (!(den > 0.0)) go = 0;
+          else alpha = gn / den;
+        }
+      }
+      if (k_it >= a.maxit) go = 0;
+      gamma_prev = gn; alpha_prev = alpha;
+      s_scal[2] = alpha; s_scal[3] = beta; s_go = go;
     }
-    if (k_it >= a.maxit) break;
+    __syncthreads();
+    if (!s_go) break;
+    const double alpha = s_scal[2], beta = s_scal[3];
     // ---- E. element-wise recurrences on the owned rows, u = Minv r, publish ----
     for (int r = tid; r < rows; r += kBcsrThreads) {
       const double pn = vu[r] + beta * vp[r];
@@ -262,7 +279,7 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
     }
     __syncthreads();
     apply_minv_publish();
-    gamma_prev = gn; alpha_prev = alpha; first = false; ++k_it;
+    first = false; ++k_it;
     stamp(3);
     barrier();
     stamp(4);
