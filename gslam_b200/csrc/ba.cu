@@ -449,28 +449,33 @@ __global__ void __launch_bounds__(128) ba_schur_blocks_kernel(BaDev g, double* _
 // Slots are numbered column-major over the upper triangle (slot = lb(lb+1)/2 + la) so that a chunk that only sees n cameras keeps
 // its work in the first n(n+1)/2 threads and the remaining warps skip every landmark.
 constexpr int kChunkCams = 16, kChunkSlots = kChunkCams * (kChunkCams + 1) / 2, kChunkThreads = 160, kChunkBatch = 4;
-constexpr int kChunkMaxLm = 64;                                                                  // landmarks per chunk (host plan)
-constexpr int kChunkItems = (kChunkBatch * kChunkCams * 18 + kChunkThreads - 1) / kChunkThreads;  // W doubles staged per thread per batch
+constexpr int kChunkMaxLm = 64;  // landmarks per chunk (host plan)
 
-__global__ void __launch_bounds__(kChunkThreads, 2) ba_schur_chunks_kernel(BaDev g) {
+// v4 (profiles/r02_ncu_summary.md: v3 issued 958 warp-instructions per landmark at 10 warps / SM -- index arithmetic of the
+// staging loops, idle lanes, DMUL+DADD around the DFMAs):
+//  * the W blocks of a batch are staged EDGE-indexed: a landmark's blocks are contiguous in global memory, so staging is a plain
+//    16-byte-granular copy; the slot threads find their two edges with one popcount each;
+//  * thread t works the t-th slot the chunk really uses (host table), so a chunk over 10 cameras keeps exactly 55 lanes busy;
+//  * batches of 4 landmarks per barrier pair (static shared memory stays under 48 KB: three CTAs per SM), loads of the next batch in flight during the arithmetic (registers);
+//  * acc = fma(y0, w0, fma(y1, w1, fma(y2, w2, acc))): 108 DFMA per (landmark, slot), nothing else on the fp64 pipe.
+__global__ void __launch_bounds__(kChunkThreads, 3) ba_schur_chunks_kernel(BaDev g) {
   if (g.sc->stop) return;
-  // per batch of kChunkBatch landmarks: W and Y = W V^-1 of every observing camera, addressed by LOCAL camera index
-  __shared__ __align__(16) double sW[2][kChunkBatch][kChunkCams][18];
+  __shared__ __align__(16) double sW[2][kChunkBatch][kChunkCams][18];  // [buffer][landmark of the batch][edge][6x3]
   __shared__ __align__(16) double sY[2][kChunkBatch][kChunkCams][18];
-  // per chunk, loaded once: masks, first-edge index, V^-1 and g_p of its landmarks (the dependent index chain sp_order -> pt_off ->
-  // W is paid once per chunk, not once per batch)
   __shared__ unsigned int s_mask[kChunkMaxLm];
   __shared__ int s_e0[kChunkMaxLm];
   __shared__ double s_vi[kChunkMaxLm][9];
   __shared__ double s_gp[kChunkMaxLm][3];
-  const int s = threadIdx.x, chunk = blockIdx.x;
+  const int t = threadIdx.x, chunk = blockIdx.x;
+  const int nused = g.sp_nused[chunk];
+  const bool slot = t < nused;
+  const int s = slot ? g.sp_slots[(size_t)chunk * kChunkSlots + t] : 0;
   int lb = 0;
   while (lb < kChunkCams - 1 && (lb + 1) * (lb + 2) / 2 <= s) ++lb;
   const int la = s - lb * (lb + 1) / 2;
-  const bool slot = s < kChunkSlots;
-  const unsigned int need = slot ? ((1u << la) | (1u << lb)) : 0xffffffffu;
+  const unsigned int need = slot ? ((1u << la) | (1u << lb)) : 0xffffffffu, below_a = (1u << la) - 1u, below_b = (1u << lb) - 1u;
   const int t0 = g.sp_pt0[chunk], nlm = min(g.sp_pt0[chunk + 1] - t0, kChunkMaxLm);
-  for (int w = s; w < nlm * 12; w += kChunkThreads) {
+  for (int w = t; w < nlm * 12; w += kChunkThreads) {
     const int b = w / 12, k = w - 12 * b;
     const int j = g.sp_order[t0 + b];
     if (k < 9) s_vi[b][k] = g.Vinv[9 * (size_t)j + k];
@@ -483,20 +488,16 @@ __global__ void __launch_bounds__(kChunkThreads, 2) ba_schur_chunks_kernel(BaDev
   for (int k = 0; k < 36; ++k) acc[k] = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) ga[k] = 0.0;
-  bool used = false;
-  // W of a batch travels global -> registers (issued one batch ahead, in flight during the previous batch's arithmetic) -> shared
-  double pre[kChunkItems];
+  // staging: per batch landmark b, edges 0..d_b-1, 9 double2 each -> items (b, q) with q < 9 * 16 (a landmark has <= 16 edges)
+  constexpr int kItems = (kChunkBatch * kChunkCams * 9 + kChunkThreads - 1) / kChunkThreads;
+  double2 pre[kItems];
   auto prefetch = [&](int tb) {
     const int nb = min(kChunkBatch, nlm - tb);
 #pragma unroll
-    for (int q = 0; q < kChunkItems; ++q) {
-      const int w = s + q * kChunkThreads;
-      const int b = w / (kChunkCams * 18), r = w - b * (kChunkCams * 18), l = r / 18, k = r - 18 * l;
-      pre[q] = 0.0;
-      if (b < nb) {
-        const unsigned int m = s_mask[tb + b];
-        if ((m >> l) & 1u) pre[q] = g.W[18 * (size_t)(s_e0[tb + b] + __popc(m & ((1u << l) - 1u))) + k];
-      }
+    for (int q = 0; q < kItems; ++q) {
+      const int w = t + q * kChunkThreads, b = w / (kChunkCams * 9), r = w - b * (kChunkCams * 9);
+      pre[q] = make_double2(0.0, 0.0);
+      if (b < nb && r < 9 * __popc(s_mask[tb + b])) pre[q] = reinterpret_cast<const double2*>(g.W + 18 * (size_t)s_e0[tb + b])[r];
     }
   };
   prefetch(0);
@@ -504,46 +505,45 @@ __global__ void __launch_bounds__(kChunkThreads, 2) ba_schur_chunks_kernel(BaDev
   for (int tb = 0; tb < nlm; tb += kChunkBatch, buf ^= 1) {
     const int nb = min(kChunkBatch, nlm - tb);
 #pragma unroll
-    for (int q = 0; q < kChunkItems; ++q) {
-      const int w = s + q * kChunkThreads;
-      if (w < kChunkBatch * kChunkCams * 18) (&sW[buf][0][0][0])[w] = pre[q];
+    for (int q = 0; q < kItems; ++q) {
+      const int w = t + q * kChunkThreads;
+      if (w < kChunkBatch * kChunkCams * 9) reinterpret_cast<double2*>(&sW[buf][0][0][0])[w] = pre[q];
     }
     __syncthreads();
-    // ---- Y = W V^-1 : one thread per (landmark, camera, row)
-    for (int w = s; w < nb * kChunkCams * 6; w += kChunkThreads) {
-      const int b = w / (kChunkCams * 6), r = w - b * (kChunkCams * 6), l = r / 6, a = r - 6 * l;
-      if ((s_mask[tb + b] >> l) & 1u) {
+    // Y = W V^-1 : one thread per (landmark, edge, row)
+    for (int w = t; w < nb * kChunkCams * 6; w += kChunkThreads) {
+      const int b = w / (kChunkCams * 6), r = w - b * (kChunkCams * 6), k = r / 6, a = r - 6 * k;
+      if (k < __popc(s_mask[tb + b])) {
         const double* Vi = s_vi[tb + b];
-        const double w0 = sW[buf][b][l][a * 3], w1 = sW[buf][b][l][a * 3 + 1], w2 = sW[buf][b][l][a * 3 + 2];
+        const double w0 = sW[buf][b][k][a * 3], w1 = sW[buf][b][k][a * 3 + 1], w2 = sW[buf][b][k][a * 3 + 2];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) sY[buf][b][l][a * 3 + c] = w0 * Vi[c] + w1 * Vi[3 + c] + w2 * Vi[6 + c];
+        for (int c = 0; c < 3; ++c) sY[buf][b][k][a * 3 + c] = w0 * Vi[c] + w1 * Vi[3 + c] + w2 * Vi[6 + c];
       }
     }
     if (tb + kChunkBatch < nlm) prefetch(tb + kChunkBatch);  // (global loads in flight during the accumulation below)
     __syncthreads();
-    // ---- accumulate: slot (la, lb) += Y_la W_lb'
     if (slot) {
       for (int b = 0; b < nb; ++b) {
-        if ((s_mask[tb + b] & need) != need) continue;
-        used = true;
-        const double* Yp = &sY[buf][b][la][0];
-        const double2* W2 = reinterpret_cast<const double2*>(&sW[buf][b][lb][0]);
+        const unsigned int m = s_mask[tb + b];
+        if ((m & need) != need) continue;
+        const double* Yp = &sY[buf][b][__popc(m & below_a)][0];
+        const double2* W2 = reinterpret_cast<const double2*>(&sW[buf][b][__popc(m & below_b)][0]);
         double wb[18];
 #pragma unroll
         for (int k = 0; k < 9; ++k) { const double2 v = W2[k]; wb[2 * k] = v.x; wb[2 * k + 1] = v.y; }
         const bool dg = la == lb;
         const double g0 = s_gp[tb + b][0], g1 = s_gp[tb + b][1], g2 = s_gp[tb + b][2];
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {  // one row of Y at a time: 3 live values instead of 18
+        for (int a = 0; a < 6; ++a) {
           const double y0 = Yp[a * 3], y1 = Yp[a * 3 + 1], y2 = Yp[a * 3 + 2];
 #pragma unroll
-          for (int c = 0; c < 6; ++c) acc[a * 6 + c] += y0 * wb[c * 3] + y1 * wb[c * 3 + 1] + y2 * wb[c * 3 + 2];
-          if (dg) ga[a] += y0 * g0 + y1 * g1 + y2 * g2;
+          for (int c = 0; c < 6; ++c) acc[a * 6 + c] = fma(y0, wb[c * 3], fma(y1, wb[c * 3 + 1], fma(y2, wb[c * 3 + 2], acc[a * 6 + c])));
+          if (dg) ga[a] = fma(y0, g0, fma(y1, g1, fma(y2, g2, ga[a])));
         }
       }
     }
   }
-  if (!slot || !used) return;  // (the host lists exactly the slots some landmark of the chunk touches)
+  if (!slot) return;
   double2* dst = reinterpret_cast<double2*>(g.sp_stageS + ((size_t)chunk * kChunkSlots + s) * 36);
 #pragma unroll
   for (int k = 0; k < 18; ++k) dst[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
@@ -1790,7 +1790,9 @@ static bool ba_schur_plan(gb_ctx* ctx, gb_ba_graph* g, int np, const std::vector
     const int j = ord[t], a = pt_off[j], b = pt_off[j + 1];
     merged.clear();
     std::set_union(cur.begin(), cur.end(), scam.begin() + a, scam.begin() + b, std::back_inserter(merged));  // (edges are camera-sorted, no duplicates)
-    if ((int)merged.size() > kChunkCams || t - open_from >= lmax) {
+    // close when the camera set would overflow, the chunk is full, or -- so that most chunks keep ONE camera set and their slot
+    // threads stay dense -- when the set would grow although the chunk already holds a fair number of landmarks
+    if ((int)merged.size() > kChunkCams || t - open_from >= lmax || (merged.size() > cur.size() && !cur.empty() && t - open_from >= lmax / 4)) {
       close(t);
       merged.assign(scam.begin() + a, scam.begin() + b);
     }
@@ -1803,7 +1805,8 @@ static bool ba_schur_plan(gb_ctx* ctx, gb_ba_graph* g, int np, const std::vector
   std::vector<std::vector<int>> blk_contrib(s_upper.size()), cam_contrib((size_t)d.nc);
   std::vector<int> upper_of((size_t)d.s_nnzb, -1);
   for (size_t u = 0; u < s_upper.size(); ++u) upper_of[s_upper[u]] = (int)u;
-  std::vector<uint8_t> used(kChunkSlots);
+  std::vector<uint8_t> used(kChunkSlots), slots((size_t)nch * kChunkSlots, 0);
+  std::vector<int> nused((size_t)nch, 0);
   for (int c = 0; c < nch; ++c) {
     const int* cams = &ch_cams[(size_t)c * kChunkCams];
     std::fill(used.begin(), used.end(), 0);
@@ -1830,6 +1833,7 @@ static bool ba_schur_plan(gb_ctx* ctx, gb_ba_graph* g, int np, const std::vector
         if (t >= s_rowptr[i + 1]) return false;  // (cannot happen: the block structure covers every co-observed pair)
         blk_contrib[upper_of[t]].push_back(c * kChunkSlots + lb * (lb + 1) / 2 + la);
         if (la == lb) cam_contrib[i].push_back(c * kChunkCams + la);
+        slots[(size_t)c * kChunkSlots + nused[c]++] = (uint8_t)(lb * (lb + 1) / 2 + la);
       }
   }
   std::vector<int> boff(s_upper.size() + 1, 0), bidx, coff((size_t)d.nc + 1, 0), cidx;
@@ -1837,11 +1841,11 @@ static bool ba_schur_plan(gb_ctx* ctx, gb_ba_graph* g, int np, const std::vector
   for (int i = 0; i < d.nc; ++i) { cidx.insert(cidx.end(), cam_contrib[i].begin(), cam_contrib[i].end()); coff[i + 1] = (int)cidx.size(); }
   // one device allocation: plan arrays + staging
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t b_pt0 = al((size_t)(nch + 1) * 4), b_mask = al((size_t)nl * 2), b_ord = al((size_t)nl * 4), b_boff = al(boff.size() * 4), b_bidx = al(bidx.size() * 4 + 4),
+  const size_t b_pt0 = al((size_t)(nch + 1) * 4), b_mask = al((size_t)nl * 2), b_ord = al((size_t)nl * 4), b_nu = al((size_t)nch * 4), b_sl = al(slots.size()), b_boff = al(boff.size() * 4), b_bidx = al(bidx.size() * 4 + 4),
                b_coff = al(coff.size() * 4), b_cidx = al(cidx.size() * 4 + 4), b_stS = al((size_t)nch * kChunkSlots * 36 * 8),
                b_stG = al((size_t)nch * kChunkCams * 6 * 8);
   uint8_t* base = nullptr;
-  if (cudaMalloc((void**)&base, b_pt0 + b_mask + b_ord + b_boff + b_bidx + b_coff + b_cidx + b_stS + b_stG) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (cudaMalloc((void**)&base, b_pt0 + b_mask + b_ord + b_nu + b_sl + b_boff + b_bidx + b_coff + b_cidx + b_stS + b_stG) != cudaSuccess) { cudaGetLastError(); return false; }
   g->sp_alloc = base;
   size_t off = 0;
   auto up = [&](const void* src, size_t bytes, size_t padded) {
@@ -1853,6 +1857,8 @@ static bool ba_schur_plan(gb_ctx* ctx, gb_ba_graph* g, int np, const std::vector
   d.sp_pt0 = (const int*)up(ch_pt0.data(), (size_t)(nch + 1) * 4, b_pt0);
   d.sp_mask = (const unsigned short*)up(mask.data(), (size_t)nl * 2, b_mask);
   d.sp_order = (const int*)up(ord.data(), (size_t)nl * 4, b_ord);
+  d.sp_nused = (const int*)up(nused.data(), (size_t)nch * 4, b_nu);
+  d.sp_slots = (const unsigned char*)up(slots.data(), slots.size(), b_sl);
   d.sp_boff = (const int*)up(boff.data(), boff.size() * 4, b_boff);
   d.sp_bidx = (const int*)up(bidx.data(), bidx.size() * 4, b_bidx);
   d.sp_coff = (const int*)up(coff.data(), coff.size() * 4, b_coff);

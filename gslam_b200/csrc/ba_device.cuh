@@ -49,6 +49,8 @@ struct BaDev {
   const int* sp_pt0;             // [nchunks+1] range of each chunk in the trajectory-sorted landmark list sp_order
   const int* sp_order;           // [live landmarks] landmark ids sorted by (first camera, last camera, id)
   const unsigned short* sp_mask; // [live landmarks] (same positions) which of the chunk's (<= 16, ascending) cameras observe it
+  const int* sp_nused;           // [nchunks] slots of the 16x16 upper triangle the chunk really touches ...
+  const unsigned char* sp_slots; // [nchunks][136] ... and which ones (thread t of the chunk's CTA works slot sp_slots[t])
   double *sp_stageS, *sp_stageG; // [nchunks][136][36], [nchunks][16][6] per-chunk partial sums
   const int *sp_boff, *sp_bidx;  // CSR over the UPPER blocks (order of s_upper): staging slots (chunk*136+slot) contributing, ascending
   const int *sp_coff, *sp_cidx;  // CSR over cameras: staging rows (chunk*16+local cam) contributing to g~

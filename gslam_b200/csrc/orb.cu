@@ -26,11 +26,14 @@ namespace {
 
 constexpr int kMaxLevels = GB_ORB_MAX_LEVELS;
 constexpr int kTileW = 128, kTileH = 32;               // interior of a FAST tile
-constexpr int kInW = kTileW + 16, kInH = kTileH + 8;   // 144 x 40 input box (3 ring + 1 nms halo each side; width padded to a
-                                                       // multiple of 16 bytes: TMA box rule); input column 4 == tile column 0
+constexpr int kInX0 = 16, kInY0 = 4;                   // input-box coordinates of tile pixel (0,0)
+constexpr int kInW = kTileW + 32, kInH = kTileH + 8;   // 160 x 40 input box: 3 ring + 1 nms halo each side; the box must START on a
+                                                       // 16-byte boundary of the image row (TMA: tools/mb/tma_probe.cu -- any other x
+                                                       // faults with "illegal instruction"), so 16 columns are fetched on the left and
+                                                       // the width is a multiple of 16 bytes
 constexpr int kScW = kTileW + 2, kScH = kTileH + 2;    // 130 x 34 score tile (1-pixel halo for the non-maximum suppression)
 constexpr int kFastThreads = 256;
-constexpr int kInWords = kInW / 4;                     // 36 32-bit words per input row
+constexpr int kInWords = kInW / 4;                     // 40 32-bit words per input row
 constexpr int kWorkCap = 2048;                         // quick-test survivors per tile handled in shared memory (rest: rounds)
 constexpr int kSelThreads = 1024;
 constexpr int kSelMax = 4096;                          // max kept keypoints per level (bitonic sort in shared memory)
@@ -169,7 +172,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (!ok) __trap();  // a copy that never lands must not hang the device
 }
 
-// K2.  Persistent CTAs walk the FAST tiles of all levels; the 144 x 40 input box of tile i+1 is fetched by the TMA unit
+// K2.  Persistent CTAs walk the FAST tiles of all levels; the 160 x 40 input box of tile i+1 is fetched by the TMA unit
 // (cp.async.bulk.tensor.2d, zero fill outside the image) into the other half of a double buffer while tile i is processed:
 //   A  packed quick test, four pixels per thread-step on 32-bit words (byte-SIMD compares): a 9-arc of the 16-ring always
 //      contains two CONSECUTIVE compass points (S,E / E,N / N,W / W,S), so a corner needs (S|N) & (E|W) all brighter than c+t or
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(kFastThreads) orb_fast_kernel(const __grid_con
     int l, x0, y0;
     locate(tile, &l, &x0, &y0);
     mbar_expect_tx(&s_bar[buf], kInH * kInW);
-    tma_load_2d(&s_in[buf][0], &M.m[l], x0 - 4, y0 - 4, &s_bar[buf]);
+    tma_load_2d(&s_in[buf][0], &M.m[l], x0 - kInX0, y0 - kInY0, &s_bar[buf]);
   };
   const int thr = P.fast_threshold;
   const uint32_t t4 = (uint32_t)thr * 0x01010101u;
@@ -224,25 +227,25 @@ __global__ void __launch_bounds__(kFastThreads) orb_fast_kernel(const __grid_con
     __syncthreads();
     const uint8_t* in = s_in[buf];
     const uint32_t* inw = reinterpret_cast<const uint32_t*>(in);
-    // ---- A: packed quick test over the score region (input rows 3..36, words 0..33)
-    for (int i = tid; i < kScH * (kScW + 6) / 4; i += kFastThreads) {  // 34 rows x 34 words
-      const int ry = 3 + i / 34, wx = i - (i / 34) * 34;
+    // ---- A: packed quick test over the score region (input rows 3..36; input columns 15..144 = words 3..36)
+    for (int i = tid; i < kScH * 34; i += kFastThreads) {  // 34 rows x 34 words
+      const int ry = 3 + i / 34, wx = 3 + i - (i / 34) * 34;
       const uint32_t C = inw[ry * kInWords + wx];
       const uint32_t S = inw[(ry + 3) * kInWords + wx], N = inw[(ry - 3) * kInWords + wx];
-      const uint32_t Wm = wx > 0 ? inw[ry * kInWords + wx - 1] : 0u, Wp = inw[ry * kInWords + wx + 1];
+      const uint32_t Wm = inw[ry * kInWords + wx - 1], Wp = inw[ry * kInWords + wx + 1];
       const uint32_t E = __byte_perm(C, Wp, 0x6543), Wst = __byte_perm(Wm, C, 0x4321);
       const uint32_t hi = __vaddus4(C, t4), lo = __vsubus4(C, t4);
       const uint32_t bright = (__vcmpgtu4(S, hi) | __vcmpgtu4(N, hi)) & (__vcmpgtu4(E, hi) | __vcmpgtu4(Wst, hi));
       const uint32_t dark = (__vcmpgtu4(lo, S) | __vcmpgtu4(lo, N)) & (__vcmpgtu4(lo, E) | __vcmpgtu4(lo, Wst));
       uint32_t pass = bright | dark;
       if (pass == 0) continue;
-      const int gy = y0 - 4 + ry;
+      const int gy = y0 - kInY0 + ry;
       if (gy < 3 || gy >= L.h - 3) continue;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (!((pass >> (8 * j)) & 1u)) continue;
-        const int col = 4 * wx + j, gx = x0 - 4 + col;
-        if (col < 3 || col >= 3 + kScW || gx < 3 || gx >= L.w - 3) continue;
+        const int col = 4 * wx + j, gx = x0 - kInX0 + col;
+        if (col < kInX0 - 1 || col >= kInX0 - 1 + kScW || gx < 3 || gx >= L.w - 3) continue;
         s_work[atomicAdd(&s_nwork, 1)] = (uint16_t)(ry * kInW + col);
       }
     }
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(kFastThreads) orb_fast_kernel(const __grid_con
       const uint8_t* p = in + o;
       if (!fast_is_corner(p, thr)) continue;
       const int ry = o / kInW, col = o - ry * kInW;
-      const int so = (ry - 3) * kScW + (col - 3);
+      const int so = (ry - (kInY0 - 1)) * kScW + (col - (kInX0 - 1));
       s_sc[so] = (uint8_t)fast_full_score(p, thr);
       s_work2[atomicAdd(&s_nwork2, 1)] = (uint16_t)so;
     }
