@@ -391,6 +391,53 @@ def main():
             dist.barrier()
     del gba_problem
 
+    # ---- BASELINE config 4: EuRoC-shaped stereo 752x480, 2000 kp per eye, stereo match + temporal match + PnP-RANSAC + local BA;
+    #      frames shard over the ranks (independent replicas, no collective).  Device-resident frames; the PnP call is the host-buffer
+    #      C-ABI entry point (its 80 KB of 3D-2D matches travel inside the timed region).
+    SW, SH = 752, 480
+    sbase = synth.synth_stream(SW, SH, 8, seed=21 + rank)
+    sring = torch.empty((16, 2, SH, SW), dtype=torch.uint8, device="cuda")
+    for k in range(16):
+        left = np.roll(sbase[k % 8], shift=(k // 8) * 5, axis=1)
+        sring[k, 0] = torch.from_numpy(left).cuda(); sring[k, 1] = torch.from_numpy(np.roll(left, -14, axis=1)).cuda()
+    fl = [Features(ctx, 2 * NKP + 256), Features(ctx, 2 * NKP + 256)]
+    fr_ = Features(ctx, 2 * NKP + 256)
+    rng4 = np.random.default_rng(4)
+    n4 = 2000   # 3D-2D matches of the tracking step: 30 % outliers, 1 px noise at f = 458 (EuRoC)
+    Xc = np.column_stack([rng4.uniform(-4, 4, n4), rng4.uniform(-3, 3, n4), rng4.uniform(3, 20, n4)])
+    xy4 = Xc[:, :2] / Xc[:, 2:3] + rng4.normal(0, 1 / 458.0, (n4, 2))
+    bad4 = rng4.permutation(n4)[:600]
+    xy4[bad4] = np.column_stack([rng4.uniform(-0.8, 0.8, 600), rng4.uniform(-0.5, 0.5, 600)])
+    Xw4 = np.ascontiguousarray(Xc + np.array([0.3, -0.1, 0.2])); xy4 = np.ascontiguousarray(xy4)
+    pnp_inliers = [0]
+
+    def step_config4(k):
+        a, b = fl[k & 1], fl[(k + 1) & 1]
+        a.extract(sring[k % 16, 0].data_ptr(), SW, SH, cfg, device_ptr=True, pitch=SW)
+        fr_.extract(sring[k % 16, 1].data_ptr(), SW, SH, cfg, device_ptr=True, pitch=SW)
+        a.match_stereo(fr_, 2.0, 0.0, 96.0)
+        a.match(b)
+        pose, mask, st = ctx.pnp_ransac(Xw4, xy4, threshold=4 / 458.0, confidence=0.99, max_hypotheses=512, seed=k + 1)
+        pnp_inliers[0] = int(st.inliers_refined)
+        graph_s.reset()
+        graph_s.solve(ba_cfg)
+    fl[1].extract(sring[15, 0].data_ptr(), SW, SH, cfg, device_ptr=True, pitch=SW)
+    for k in range(3):
+        step_config4(k)
+    c4_steps = max(10, min(args.steps, 50))
+    c4_ms = []
+    for rep in range(3):
+        barrier()
+        ctx.timer_begin()
+        for k in range(c4_steps):
+            step_config4(3 + k)
+        c4_ms.append(max_over_ranks(ctx.timer_end()))
+    config4 = {"workload": f"stereo {SW}x{SH}, {NKP} kp per eye: 2 x ORB extract + row-band stereo match + temporal match + PnP-RANSAC ({n4} matches, 30 % outliers, "
+                           f"<= 512 hypotheses) + local BA ({BA_CAMS} KF/{BA_PTS} pts/{BA_PTS * BA_OBS_PER_PT} obs, {BA_ITERS} LM it)",
+               "value": world * c4_steps / (median(c4_ms) * 1e-3), "unit": "frames/s", "ms_per_step": median(c4_ms) / c4_steps, "steps": c4_steps,
+               "scaling": "weak (frames shard over the ranks, no collective)", "n_gpus": world, "pnp_inliers": pnp_inliers[0],
+               "note": "single stream per rank; device-resident stereo pairs; BASELINE.json configs[3]"}
+
     # ---- end to end through the host-buffer C-ABI, PAGEABLE frames, tracking thread || mapping thread ---------------------------
     pageable = [np.array(base[k], copy=True) for k in range(8)]           # malloc'd, like GImage (GImage.h:394-402)
     pinned_t = [torch.from_numpy(base[k]).pin_memory() for k in range(8)]
@@ -510,6 +557,7 @@ def main():
                                         "peak_source": "measured on this device (gb_dbg_popc_peak: 16 independent LOP3+POPC chains per thread, all SMs)",
                                         "frac": (8 * NKP * NKP / (t_match * 1e-3)) / popc_peak if popc_peak else None}},
             }
+    line["config4_stereo"] = config4
     if global_ba is not None:
         line["global_ba"] = global_ba
     # CPU baseline on a bounded sample, rank 0 only, N=1 only

@@ -129,16 +129,19 @@ class Context:
         return cfg
 
     def orb_extract(self, img: np.ndarray, nfeatures: int = 500, capacity: int | None = None, **cfg_kw):
-        """img: (H, W) uint8.  Returns (keypoints[KP_DTYPE], descriptors (n,32) uint8) in canonical (octave,y,x) order."""
+        """img: (H, W) uint8 gray, or (H, W, 3|4) colour (B,G,R[,A] unless rgb=True).  Returns (keypoints[KP_DTYPE], descriptors
+        (n,32) uint8) in canonical (octave,y,x) order."""
+        rgb = bool(cfg_kw.pop("rgb", False))
         img = np.ascontiguousarray(img, dtype=np.uint8)
-        h, w = img.shape
+        h, w = img.shape[:2]
+        ch = 1 if img.ndim == 2 else img.shape[2]
         cfg = self.orb_cfg(nfeatures=nfeatures, **cfg_kw)
         cap = capacity or (2 * nfeatures + 256)
         while True:
             kps = np.zeros(cap, dtype=KP_DTYPE)
             desc = np.zeros((cap, 32), dtype=np.uint8)
             n = C.c_int(cap)
-            rc = self._lib.gb_orb_extract(self._h, ptr(img), w, h, C.byref(cfg), ptr(kps), ptr(desc), C.byref(n))
+            rc = self._lib.gb_orb_extract_image(self._h, ptr(img), w, h, ch, 1 if rgb else 0, C.byref(cfg), ptr(kps), ptr(desc), C.byref(n))
             if rc == capi.GB_ERR_CAPACITY and capacity is None and n.value > cap:
                 cap = n.value
                 continue

@@ -97,7 +97,7 @@ def build_plugins(force: bool = False) -> list[str]:
         return []
     stamp_path = os.path.join(LIBDIR, ".stamp_plugins")
     want = _hash(srcs + [os.path.join(REPO, "include", "gslam_b200.h")])
-    outs = [os.path.join(LIBDIR, n) for n in ("libgslam_optimizer.so", "libgslam_b200.so", "libgslam_estimator.so", "gslam_b200_host_test")]
+    outs = [os.path.join(LIBDIR, n) for n in ("libgslam_optimizer.so", "libgslam_b200.so", "libgslam_estimator.so", "libgslamDB_synth.so", "gslam_b200_host_test")]
     if not force and all(os.path.exists(o) for o in outs) and os.path.exists(stamp_path) and open(stamp_path).read() == want:
         return outs
     if not os.path.isdir(os.path.join(REFERENCE, "GSLAM", "core")):

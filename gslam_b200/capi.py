@@ -72,6 +72,7 @@ _SIGNATURES = [
     ("gb_launch_count", C.c_int64, [_VP]),
     ("gb_orb_cfg_default", None, [C.POINTER(OrbCfg)]),
     ("gb_orb_extract", C.c_int, [_VP, _VP, C.c_int, C.c_int, C.POINTER(OrbCfg), _VP, _VP, C.POINTER(C.c_int)]),
+    ("gb_orb_extract_image", C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(OrbCfg), _VP, _VP, C.POINTER(C.c_int)]),
     ("gb_features_create", C.c_int, [_VP, C.c_int, C.POINTER(_VP)]),
     ("gb_features_destroy", C.c_int, [_VP, _VP]),
     ("gb_orb_extract_to", C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(OrbCfg), _VP]),

@@ -86,6 +86,19 @@ __global__ void __launch_bounds__(256) orb_resize_kernel(const uint8_t* __restri
   *reinterpret_cast<uint32_t*>(dst + (size_t)y * dpitch + x4) = out;
 }
 
+// ---- K0: colour -> gray into pyramid level 0 (frames arrive BGR / BGRA / RGB / RGBA from the dataset plugins, IO.h:86-110) ----
+// OpenCV's 8-bit fixed point (cv2 4.13: 15-bit coefficients B 3735, G 19235, R 9798, round to nearest; pinned against
+// cv2.cvtColor in tests/test_oracle_orb.py::test_gray_conversion_equals_cv2).
+__global__ void __launch_bounds__(256) orb_gray_kernel(const uint8_t* __restrict__ src, int w, int h, int channels, int rgb_order,
+                                                       uint8_t* __restrict__ dst, int dpitch) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  const uint8_t* p = src + ((size_t)y * w + x) * channels;
+  const int c0 = p[0], c1 = p[1], c2 = p[2];
+  const int b = rgb_order ? c2 : c0, r = rgb_order ? c0 : c2;
+  dst[(size_t)y * dpitch + x] = (uint8_t)((b * 3735 + c1 * 19235 + r * 9798 + (1 << 14)) >> 15);
+}
+
 // ---- K2: FAST-9/16 -----------------------------------------------------------------------------------------------------
 // Corner score of one pixel: m = max over the 16 cyclic 9-arcs of max(min_i d_i, min_i -d_i), score = m-1 if m > t.
 // Sliding 9-window minimum over the ring by doubling (windows 2, 4, 8, then +1), once on d = ring - centre (bright arcs) and
@@ -643,6 +656,7 @@ struct OrbState {
   FastMaps maps{};                      // TMA tensor maps of the pyramid levels (built with the buffers)
   // device buffers
   uint8_t* d_pyr = nullptr; size_t pyr_bytes = 0;
+  void* d_color = nullptr; size_t color_cap = 0;  // packed colour frame before the gray conversion (grow-only)
   uint32_t* d_tabs = nullptr;           // resize tables
   uint32_t* d_cand_pos = nullptr; uint8_t* d_cand_score = nullptr; uint32_t* d_cand_key = nullptr; float* d_cand_resp = nullptr;
   uint32_t* d_surv_pos = nullptr;       // compact survivor lists share d_cand_key / d_cand_resp
@@ -655,6 +669,7 @@ struct OrbState {
 
 static void orb_free_buffers(OrbState* s) {
   cudaFree(s->d_surv_pos); s->d_surv_pos = nullptr;
+  cudaFree(s->d_color); s->d_color = nullptr; s->color_cap = 0;
   cudaFree(s->d_pyr); cudaFree(s->d_tabs); cudaFree(s->d_cand_pos); cudaFree(s->d_cand_score); cudaFree(s->d_cand_key);
   cudaFree(s->d_cand_resp); cudaFree(s->d_counts); cudaFree(s->d_kept_pos); cudaFree(s->d_kept_resp);
   s->d_pyr = nullptr; s->d_tabs = nullptr; s->d_cand_pos = nullptr; s->d_cand_score = nullptr; s->d_cand_key = nullptr;
@@ -874,9 +889,11 @@ void gb_orb_cfg_default(gb_orb_cfg* c) {
 
 // sync_after: a host image (or its staging copy) must have been consumed before the caller may touch it again; the one-shot
 // gb_orb_extract synchronises in its own download instead (one synchronisation per host-buffer extraction)
+// channels: 1 = gray (GImage 8UC1), 3 / 4 = packed colour (8UC3 / 8UC4), converted on the device; rgb_order: 0 = B,G,R[,A] (OpenCV,
+// GSLAM IMAGE_BGRA), 1 = R,G,B[,A].  `pitch` is in bytes (>= width * channels).
 static int orb_extract_to_impl(gb_ctx* ctx, const uint8_t* img, int img_is_device, int width, int height, int pitch, const gb_orb_cfg* cfg_in,
-                               gb_features* out, bool sync_after) {
-  if (!ctx || !img || !out || width < 1 || height < 1 || pitch < width) return GB_ERR_INVALID;
+                               gb_features* out, bool sync_after, int channels = 1, int rgb_order = 0) {
+  if (!ctx || !img || !out || width < 1 || height < 1 || (channels != 1 && channels != 3 && channels != 4) || pitch < width * channels) return GB_ERR_INVALID;
   CtxLock lk(ctx);
   gb_orb_cfg cfg;
   if (cfg_in) cfg = *cfg_in; else gb_orb_cfg_default(&cfg);
@@ -884,7 +901,30 @@ static int orb_extract_to_impl(gb_ctx* ctx, const uint8_t* img, int img_is_devic
   GB_CHECK(orb_prepare(ctx, width, height, &cfg));
   OrbState* s = ctx->orb;
   const LevelInfo& L0 = s->P.lv[0];
-  if (img_is_device) {
+  if (channels != 1) {
+    const size_t row = (size_t)width * channels, bytes = row * height;
+    GB_CHECK(gb_dev_realloc(ctx, &s->d_color, &s->color_cap, bytes));
+    if (img_is_device) {
+      GB_CUDA(ctx, cudaMemcpy2DAsync(s->d_color, row, img, pitch, row, height, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      cudaPointerAttributes at;
+      const bool pinned = cudaPointerGetAttributes(&at, img) == cudaSuccess && at.type == cudaMemoryTypeHost;
+      cudaGetLastError();
+      const uint8_t* src = img;
+      int spitch = pitch;
+      if (!pinned) {
+        GB_CHECK(gb_stage_reserve(ctx, ctx->h_stage_off + bytes + 1024));
+        uint8_t* hs = (uint8_t*)gb_stage_alloc(ctx, bytes);
+        for (int y = 0; y < height; ++y) memcpy(hs + (size_t)y * row, img + (size_t)y * pitch, row);
+        src = hs;
+        spitch = (int)row;
+      }
+      GB_CUDA(ctx, cudaMemcpy2DAsync(s->d_color, row, src, spitch, row, height, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    orb_gray_kernel<<<dim3(gb_div_up(width, 256), height), 256, 0, ctx->stream>>>((const uint8_t*)s->d_color, width, height, channels, rgb_order,
+                                                                                 s->d_pyr + L0.off, L0.pitch);
+    GB_LAUNCH_CHECK(ctx);
+  } else if (img_is_device) {
     GB_CUDA(ctx, cudaMemcpy2DAsync(s->d_pyr + L0.off, L0.pitch, img, pitch, width, height, cudaMemcpyDeviceToDevice, ctx->stream));
   } else {
     // pinned caller memory goes straight over PCIe; pageable memory is staged through the ctx's pinned buffer
@@ -912,8 +952,21 @@ int gb_orb_extract_to(gb_ctx* ctx, const uint8_t* img, int img_is_device, int wi
   return orb_extract_to_impl(ctx, img, img_is_device, width, height, pitch, cfg_in, out, true);
 }
 
+static int orb_extract_host(gb_ctx* ctx, const uint8_t* img, int width, int height, int channels, int rgb_order, const gb_orb_cfg* cfg_in, gb_keypoint* kps,
+                            uint8_t* desc, int* n);
+
 int gb_orb_extract(gb_ctx* ctx, const uint8_t* img, int width, int height, const gb_orb_cfg* cfg_in, gb_keypoint* kps, uint8_t* desc,
                    int* n) {
+  return orb_extract_host(ctx, img, width, height, 1, 0, cfg_in, kps, desc, n);
+}
+
+int gb_orb_extract_image(gb_ctx* ctx, const uint8_t* img, int width, int height, int channels, int rgb_order, const gb_orb_cfg* cfg_in, gb_keypoint* kps,
+                         uint8_t* desc, int* n) {
+  return orb_extract_host(ctx, img, width, height, channels, rgb_order, cfg_in, kps, desc, n);
+}
+
+static int orb_extract_host(gb_ctx* ctx, const uint8_t* img, int width, int height, int channels, int rgb_order, const gb_orb_cfg* cfg_in, gb_keypoint* kps,
+                            uint8_t* desc, int* n) {
   if (!ctx || !img || !n || *n < 0) return GB_ERR_INVALID;
   CtxLock lk(ctx);
   gb_orb_cfg cfg;
@@ -926,7 +979,7 @@ int gb_orb_extract(gb_ctx* ctx, const uint8_t* img, int width, int height, const
     GB_CHECK(gb_features_create(ctx, want_cap, &ctx->tmp_f));
   }
   gb_features* f = ctx->tmp_f;
-  GB_CHECK(orb_extract_to_impl(ctx, img, 0, width, height, width, &cfg, f, *n <= 0));
+  GB_CHECK(orb_extract_to_impl(ctx, img, 0, width, height, width * channels, &cfg, f, *n <= 0, channels, rgb_order));
   const int cap = *n;
   if (cap > 0) {  // one synchronisation: the count travels with the rows
     int m = cap;

@@ -7,13 +7,19 @@
 //   gslam_b200_host_test pnp  <plugin-dir> in.bin out.bin      optimizePnP(...)
 //   gslam_b200_host_test orb  <plugin-dir> in.bin out.bin      Registry::load("b200") -> gslam.b200.orb_extract + match_hamming
 //   gslam_b200_host_test findpnp <plugin-dir> in.bin out.bin   Estimator::create() -> findPnP (P3P + RANSAC), Estimator.h:158-164
+//   gslam_b200_host_test dataset <plugin-dir> x.synth out.bin  GSLAM::Dataset::open -> libgslamDB_synth.so -> grabFrame (Dataset.h:124-162)
+//   gslam_b200_host_test features <plugin-dir> x.synth out.bin dataset/frame -> gslam.apps.b200_features -> b200/curframe (Messenger)
 // Trailing "key=value" arguments become svar settings the plugins read (b200.devices=0,1 shards a global BA over two GPUs).
 #include <GSLAM/core/GSLAM.h>
+#include <GSLAM/core/Dataset.h>
 #include <GSLAM/core/Estimator.h>
 #include <GSLAM/core/Optimizer.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
+#include <thread>
 #include <fstream>
 #include <vector>
 
@@ -141,6 +147,77 @@ static int runFindPnP(const std::string& dir, const char* in, const char* out) {
   return ok ? 0 : 3;
 }
 
+// Dataset through the reference's loader: GSLAM::Dataset::open("x.synth") -> Registry::load("gslamDB_synth") (Dataset.h:124-162).
+// out: int32 n_frames, cams, w, h, then for every frame and camera w*h bytes.
+static int runDataset(const std::string& dir, const char* in, const char* out) {
+  svar.Set<std::string>("GSLAM_LIBRARY_PATH", dir);
+  Dataset ds;
+  if (!ds.open(in)) { fprintf(stderr, "Dataset::open(%s) failed\n", in); return 2; }
+  std::ofstream o(out, std::ios::binary);
+  std::vector<FramePtr> frames;
+  while (FramePtr fr = ds.grabFrame()) frames.push_back(fr);
+  if (frames.empty()) return 1;
+  GImage im0 = frames[0]->getImage(0);
+  int32_t hdr[4] = {(int32_t)frames.size(), frames[0]->cameraNum(), im0.cols, im0.rows};
+  wr(o, hdr, 4);
+  for (size_t k = 0; k < frames.size(); ++k)
+    for (int c = 0; c < hdr[1]; ++c) {
+      GImage im = frames[k]->getImage(c);
+      wr(o, im.data, (size_t)im.cols * im.rows);
+    }
+  return 0;
+}
+
+// The Messenger-level pipeline, wired the way `gslam play b200_features -dataset x.synth` wires it (gslam/main.cpp:12-46,
+// plugins/play/main.cpp:126-132): the app gslam.apps.b200_features of libgslam_b200.so runs on its own thread with OUR messenger
+// injected; this thread plays the dataset onto "dataset/frame", listens on "b200/curframe" / "b200/matches" and finally publishes
+// "messenger/stop".  out: int32 n_frames, then per frame: int32 id, int32 n_kp, n_kp x 28 B keypoints, n_kp x 32 B descriptors,
+// int32 n_match, n_match x int32 trainIdx, int32 n_stereo, n_stereo x int32 stereoIdx.
+static int runFeaturesApp(const std::string& dir, const char* in, const char* out) {
+  svar.Set<std::string>("GSLAM_LIBRARY_PATH", dir);
+  Svar mod = Registry::load("b200");
+  if (mod.isUndefined()) { fprintf(stderr, "Registry::load(\"b200\") failed\n"); return 2; }
+  Svar run = mod["gslam"]["apps"]["b200_features"];
+  if (!run.isFunction()) { fprintf(stderr, "gslam.apps.b200_features missing\n"); return 2; }
+  Svar setMsg = mod["gslam"]["setGlobalMessenger"], setLog = mod["gslam"]["setGlobalLogSinks"];
+  if (setLog.isFunction()) setLog(getLogSinksGlobal());
+  if (setMsg.isFunction()) setMsg(messenger);
+  Dataset ds;
+  if (!ds.open(in)) { fprintf(stderr, "Dataset::open(%s) failed\n", in); return 2; }
+  std::mutex mu;
+  std::vector<FramePtr> got;
+  std::vector<Svar> matches;
+  Subscriber s1 = messenger.subscribe("b200/curframe", 0, [&](FramePtr fr) { std::lock_guard<std::mutex> lk(mu); got.push_back(fr); });
+  Subscriber s2 = messenger.subscribe("b200/matches", 0, [&](Svar m) { std::lock_guard<std::mutex> lk(mu); matches.push_back(m); });
+  std::thread app([run]() { run(svar); });
+  // wait until the app subscribed (it has no ready signal: poll the subscriber count of the topic)
+  Publisher pub = messenger.advertise<FramePtr>("dataset/frame", 0);
+  for (int spin = 0; spin < 2000 && pub.getNumSubscribers() == 0; ++spin) std::this_thread::sleep_for(std::chrono::milliseconds(5));
+  int sent = 0;
+  while (FramePtr fr = ds.grabFrame()) { pub.publish(fr); ++sent; }
+  messenger.publish("messenger/stop", true);
+  app.join();
+  std::ofstream o(out, std::ios::binary);
+  int32_t n = (int32_t)got.size();
+  wr(o, &n, 1);
+  for (size_t k = 0; k < got.size(); ++k) {
+    std::vector<KeyPoint> kps;
+    got[k]->getKeyPoints(kps);
+    GImage d = got[k]->getDescriptor();
+    int32_t h2[2] = {(int32_t)got[k]->id(), (int32_t)kps.size()};
+    wr(o, h2, 2);
+    wr(o, kps.data(), kps.size());
+    if (d.rows) wr(o, d.data, (size_t)d.rows * 32);
+    std::vector<int> idx, st;
+    if (k < matches.size() && matches[k].exist("trainIdx")) idx = matches[k]["trainIdx"].castAs<std::vector<int> >();
+    if (k < matches.size() && matches[k].exist("stereoIdx")) st = matches[k]["stereoIdx"].castAs<std::vector<int> >();
+    int32_t nm = (int32_t)idx.size(), ns = (int32_t)st.size();
+    wr(o, &nm, 1); wr(o, idx.data(), idx.size());
+    wr(o, &ns, 1); wr(o, st.data(), st.size());
+  }
+  return (int)got.size() == sent ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
   if (argc < 5) { fprintf(stderr, "usage: %s ba|pnp|orb|findpnp <plugin-dir> in.bin out.bin\n", argv[0]); return 64; }
   // optional svar settings for the plugins, "key=value" (e.g. b200.devices=0,1  b200.multi_min_obs=1000)
@@ -161,5 +238,7 @@ int main(int argc, char** argv) {
   if (mode == "pnp") return runBA(argv[2], argv[3], argv[4], true);
   if (mode == "orb") return runORB(argv[2], argv[3], argv[4]);
   if (mode == "findpnp") return runFindPnP(argv[2], argv[3], argv[4]);
+  if (mode == "dataset") return runDataset(argv[2], argv[3], argv[4]);
+  if (mode == "features") return runFeaturesApp(argv[2], argv[3], argv[4]);
   return 64;
 }

@@ -54,20 +54,27 @@ gb_orb_cfg cfgFrom(GSLAM::Svar cfg) {
 }
 
 bool extract(const GSLAM::GImage& img, GSLAM::Svar cfg, std::vector<GSLAM::KeyPoint>& kps, GSLAM::GImage& desc) {
-  if (img.empty() || img.type() != GSLAM::GImageType<uchar, 1>::Type) {
-    LOG(ERROR) << "gslam_b200 orb_extract: need a non-empty 8UC1 image (convert colour frames to gray first)";
+  // 8UC1 gray, or the 8UC3 / 8UC4 colour frames GSLAM's dataset plugins deliver (B,G,R[,A] unless cfg.rgb): converted on the device
+  const int channels = img.channels();
+  if (img.empty() || img.elemSize1() != 1 || (channels != 1 && channels != 3 && channels != 4)) {
+    LOG(ERROR) << "gslam_b200 orb_extract: need a non-empty 8-bit image with 1, 3 or 4 channels";
     return false;
   }
+  const int rgb = cfg.isObject() ? (cfg.get<bool>("rgb", false) ? 1 : 0) : 0;
   gb_ctx* ctx = shared().get();
   if (!ctx) return false;
   gb_orb_cfg c = cfgFrom(cfg);
+  if (c.nfeatures <= 0 || c.nfeatures > (1 << 20)) {  // (validated before any buffer is sized from it: nothing may throw out of a Svar function)
+    LOG(ERROR) << "gslam_b200 orb_extract: nfeatures must be in 1 .. 1048576";
+    return false;
+  }
   int n = 2 * c.nfeatures + 256;
   for (int attempt = 0; attempt < 2; ++attempt) {
     kps.resize(n);
     std::vector<uint8_t> d((size_t)n * 32);
     int got = n;
     // GImage has no row stride: row i at data + i*cols (GImage.h:378)
-    const int rc = gb_orb_extract(ctx, img.data, img.cols, img.rows, &c, reinterpret_cast<gb_keypoint*>(kps.data()), d.data(), &got);
+    const int rc = gb_orb_extract_image(ctx, img.data, img.cols, img.rows, channels, rgb, &c, reinterpret_cast<gb_keypoint*>(kps.data()), d.data(), &got);
     if (rc == GB_ERR_CAPACITY && got > n) { n = got; continue; }
     if (rc != GB_OK) {
       LOG(ERROR) << "gslam_b200 orb_extract: " << gb_last_error(ctx);
@@ -78,6 +85,64 @@ bool extract(const GSLAM::GImage& img, GSLAM::Svar cfg, std::vector<GSLAM::KeyPo
     return true;
   }
   return false;
+}
+
+// ---- the Messenger-level application ---------------------------------------------------------------------
+// `gslam play b200_features [metric_time -slam b200] -dataset x.synth`: subscribes "dataset/frame" (published by the reference's
+// player, GSLAM/plugins/play/main.cpp:15,126-132), runs the B200 feature path on every frame -- ORB extract on each camera of the
+// frame, MapFrame::setKeyPoints (Map.h:311), Hamming match against the previous frame, row-band stereo match for two-camera frames
+// -- and publishes the frame on "<name>/curframe", the topic GSLAM's own latency tool listens to
+// (GSLAM/evaluation/metric_time/main.cpp:11-21), plus the associations on "<name>/matches".
+int runFeatures(GSLAM::Svar config) {
+  const std::string name = config.arg<std::string>("name", "b200", "topic prefix: frames leave on <name>/curframe, matches on <name>/matches");
+  const int nfeatures = config.arg<int>("nfeatures", 2000, "ORB keypoints per image");
+  const bool do_match = config.arg<bool>("match", true, "Hamming-match every frame against the previous one");
+  const double band = config.arg<double>("stereo_band", 2.0, "row band (pixels) of the stereo association");
+  const double max_disp = config.arg<double>("stereo_max_disparity", 128.0, "largest accepted disparity (pixels)");
+  if (config.get("help", false)) return config.help();
+  GSLAM::Svar cfg = GSLAM::Svar::object();
+  cfg["nfeatures"] = nfeatures;
+  GSLAM::Publisher pub_cur = messenger.advertise<GSLAM::FramePtr>(name + "/curframe", 0);
+  GSLAM::Publisher pub_match = messenger.advertise<GSLAM::Svar>(name + "/matches", 0);
+  GSLAM::GImage prev_desc;
+  std::mutex mu;
+  GSLAM::Subscriber sub = messenger.subscribe("dataset/frame", 0, [&](GSLAM::FramePtr fr) {
+    if (!fr || !fr->cameraNum()) return;
+    std::lock_guard<std::mutex> lk(mu);
+    std::vector<GSLAM::KeyPoint> kps, kps_r;
+    GSLAM::GImage desc, desc_r;
+    if (!extract(fr->getImage(0, GSLAM::IMAGE_GRAY), cfg, kps, desc)) return;
+    fr->setKeyPoints(kps, desc);  // Map.h:311-312
+    GSLAM::Svar out = GSLAM::Svar::object();
+    out["id"] = (int)fr->id();
+    out["keypoints"] = (int)kps.size();
+    gb_ctx* ctx = shared().get();
+    if (fr->cameraNum() > 1 && ctx && extract(fr->getImage(1, GSLAM::IMAGE_GRAY), cfg, kps_r, desc_r)) {
+      std::vector<int> idx(kps.size()), d1(kps.size()), d2(kps.size());
+      if (gb_match_stereo(ctx, reinterpret_cast<const gb_keypoint*>(kps.data()), desc.data, (int)kps.size(), reinterpret_cast<const gb_keypoint*>(kps_r.data()),
+                          desc_r.data, (int)kps_r.size(), (float)band, 0.f, (float)max_disp, idx.data(), d1.data(), d2.data()) == GB_OK) {
+        out["stereoIdx"] = idx;
+        out["stereoDistance"] = d1;
+      } else {
+        LOG(ERROR) << "gslam_b200 b200_features: " << gb_last_error(ctx);
+      }
+    }
+    if (do_match && ctx && !prev_desc.empty() && !desc.empty()) {
+      std::vector<int> idx(desc.rows), d1(desc.rows), d2(desc.rows);
+      if (gb_match_hamming(ctx, desc.data, desc.rows, prev_desc.data, prev_desc.rows, idx.data(), d1.data(), d2.data()) == GB_OK) {
+        out["trainIdx"] = idx;
+        out["distance"] = d1;
+        out["distance2"] = d2;
+      } else {
+        LOG(ERROR) << "gslam_b200 b200_features: " << gb_last_error(ctx);
+      }
+    }
+    prev_desc = desc;
+    pub_match.publish(out);
+    pub_cur.publish(fr);
+  });
+  LOG(INFO) << "gslam_b200 b200_features ready: dataset/frame -> " << name << "/curframe";
+  return GSLAM::Messenger::exec();  // until "messenger/stop" (Messenger.h:610-620)
 }
 
 }  // namespace
@@ -96,7 +161,7 @@ REGISTER_SVAR_MODULE(b200) {
     return out;
   });
   svar["gslam"]["b200"]["match_hamming"] = GSLAM::Svar::lambda([](GSLAM::GImage q, GSLAM::GImage t) -> GSLAM::Svar {
-    if (q.cols != 32 || (t.rows > 0 && t.cols != 32) || q.elemSize() != 1) {
+    if (q.cols != 32 || (t.rows > 0 && t.cols != 32) || q.elemSize() != 1 || (t.rows > 0 && t.elemSize() != 1)) {
       LOG(ERROR) << "gslam_b200 match_hamming: descriptors must be N x 32 8UC1";
       return GSLAM::Svar();
     }
@@ -109,6 +174,30 @@ REGISTER_SVAR_MODULE(b200) {
     }
     GSLAM::Svar out = GSLAM::Svar::object();
     out["trainIdx"] = idx;
+    out["distance"] = d1;
+    out["distance2"] = d2;
+    return out;
+  });
+  svar["gslam"]["apps"]["b200_features"] = GSLAM::SvarFunction(runFeatures);  // (what GSLAM_REGISTER_APPLICATION would register, GSLAM.h:26-33)
+  svar["gslam"]["b200"]["match_stereo"] = GSLAM::Svar::lambda([](std::vector<GSLAM::KeyPoint> kl, GSLAM::GImage dl, std::vector<GSLAM::KeyPoint> kr,
+                                                                   GSLAM::GImage dr, GSLAM::Svar cfg) -> GSLAM::Svar {
+    if ((int)kl.size() != dl.rows || (int)kr.size() != dr.rows || (dl.rows > 0 && (dl.cols != 32 || dl.elemSize() != 1)) ||
+        (dr.rows > 0 && (dr.cols != 32 || dr.elemSize() != 1))) {
+      LOG(ERROR) << "gslam_b200 match_stereo: keypoints / N x 32 8UC1 descriptors of the two images do not fit together";
+      return GSLAM::Svar();
+    }
+    gb_ctx* ctx = shared().get();
+    if (!ctx) return GSLAM::Svar();
+    const double band = cfg.isObject() ? cfg.get<double>("band", 2.0) : 2.0, mind = cfg.isObject() ? cfg.get<double>("minDisparity", 0.0) : 0.0,
+                 maxd = cfg.isObject() ? cfg.get<double>("maxDisparity", 1e9) : 1e9;
+    std::vector<int> idx(kl.size()), d1(kl.size()), d2(kl.size());
+    if (gb_match_stereo(ctx, reinterpret_cast<const gb_keypoint*>(kl.data()), dl.data, (int)kl.size(), reinterpret_cast<const gb_keypoint*>(kr.data()), dr.data,
+                        (int)kr.size(), (float)band, (float)mind, (float)maxd, idx.data(), d1.data(), d2.data()) != GB_OK) {
+      LOG(ERROR) << "gslam_b200 match_stereo: " << gb_last_error(ctx);
+      return GSLAM::Svar();
+    }
+    GSLAM::Svar out = GSLAM::Svar::object();
+    out["rightIdx"] = idx;
     out["distance"] = d1;
     out["distance2"] = d2;
     return out;

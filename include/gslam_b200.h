@@ -116,6 +116,12 @@ GB_API void gb_orb_cfg_default(gb_orb_cfg* cfg);
 GB_API int gb_orb_extract(gb_ctx* ctx, const uint8_t* img, int width, int height, const gb_orb_cfg* cfg,
                           gb_keypoint* kps, uint8_t* desc, int* n);
 
+/* Colour frames (GSLAM's dataset plugins deliver 8UC3 / 8UC4, GSLAM/plugins/datasets/IO.h:86-110): channels = 1, 3 or 4 interleaved
+ * bytes per pixel, rgb_order 0 = B,G,R[,A] (OpenCV / IMAGE_BGRA), 1 = R,G,B[,A]; the gray conversion is cv2.cvtColor's 8-bit fixed
+ * point, fused into the level-0 upload on the device.  channels = 1 is gb_orb_extract. */
+GB_API int gb_orb_extract_image(gb_ctx* ctx, const uint8_t* img, int width, int height, int channels, int rgb_order,
+                                const gb_orb_cfg* cfg, gb_keypoint* kps, uint8_t* desc, int* n);
+
 /* Device-resident variants: the frame and/or the results stay in HBM (bench `value`, chained pipelines). */
 GB_API int gb_features_create(gb_ctx* ctx, int capacity, gb_features** out);
 GB_API int gb_features_destroy(gb_ctx* ctx, gb_features* f);

@@ -148,6 +148,17 @@ def match_stereo(kps_left, desc_left, kps_right, desc_right, band=2.0, min_disp=
     return idx, d1, d2
 
 
+def to_gray(img: np.ndarray, rgb: bool = False) -> np.ndarray:
+    """Colour (H, W, 3|4) uint8 -> gray uint8 as cv2.cvtColor(..., COLOR_BGR[A]2GRAY / COLOR_RGB[A]2GRAY) computes it for 8-bit
+    images (cv2 4.13: 15-bit fixed point, B 3735 / G 19235 / R 9798, round to nearest) -- pinned against cv2 in
+    tests/test_oracle_orb.py::test_gray_conversion_equals_cv2.  The frames GSLAM's dataset plugins deliver are 8UC3 / 8UC4
+    (GSLAM/plugins/datasets/IO.h:86-110)."""
+    a = np.asarray(img, np.uint8)
+    c0, c1, c2 = (a[..., i].astype(np.int64) for i in range(3))
+    b, r = (c2, c0) if rgb else (c0, c2)
+    return ((b * 3735 + c1 * 19235 + r * 9798 + (1 << 14)) >> 15).astype(np.uint8)
+
+
 # ---- Hamming -----------------------------------------------------------------------------------------------------
 def match_hamming(query: np.ndarray, train: np.ndarray):
     q = np.ascontiguousarray(query, dtype=np.uint8).reshape(-1, 32)

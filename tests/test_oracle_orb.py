@@ -193,3 +193,16 @@ def test_degenerate_images():
     tiny = synth.synth_frame(40, 40, 1)  # smaller than 2*edgeThreshold: nothing can be kept
     kps, _ = oracle.orb_extract(tiny, 100)
     assert len(kps) == 0
+
+
+def test_gray_conversion_equals_cv2():
+    """oracle.to_gray (the rule the device-side conversion of colour frames follows) == cv2.cvtColor on 8-bit images."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    grid = np.stack(np.meshgrid(np.arange(0, 256, 5), np.arange(0, 256, 3), np.arange(0, 256, 7), indexing="ij"), -1).reshape(-1, 1, 3).astype(np.uint8)
+    assert np.array_equal(oracle.to_gray(grid), cv2.cvtColor(grid, cv2.COLOR_BGR2GRAY))
+    img3 = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8); img4 = rng.integers(0, 256, (64, 80, 4), dtype=np.uint8)
+    assert np.array_equal(oracle.to_gray(img3), cv2.cvtColor(img3, cv2.COLOR_BGR2GRAY))
+    assert np.array_equal(oracle.to_gray(img3, rgb=True), cv2.cvtColor(img3, cv2.COLOR_RGB2GRAY))
+    assert np.array_equal(oracle.to_gray(img4), cv2.cvtColor(img4, cv2.COLOR_BGRA2GRAY))
+    assert np.array_equal(oracle.to_gray(img4, rgb=True), cv2.cvtColor(img4, cv2.COLOR_RGBA2GRAY))

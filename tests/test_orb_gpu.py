@@ -159,3 +159,15 @@ def test_device_resident_extract_and_match(ctx):
     dx = k1["x"][good] - k0["x"][idx[good]]; dy = k1["y"][good] - k0["y"][idx[good]]
     assert np.median(np.abs(dx + 3)) < 1.5 and np.median(np.abs(dy + 5)) < 1.5
     f0.close(); f1.close()
+
+
+@pytest.mark.parametrize("channels,rgb", [(3, False), (4, False), (3, True), (4, True)])
+def test_colour_frames_are_converted_on_the_device(ctx, channels, rgb):
+    """8UC3 / 8UC4 frames (what GSLAM's dataset plugins deliver, IO.h:86-110): gb_orb_extract_image == gray extraction of the
+    cv2-rule gray image (oracle.to_gray), every field and every descriptor bit."""
+    rng = np.random.default_rng(channels * 2 + rgb)
+    base = synth.synth_frame(480, 360, seed=11).astype(np.int64)
+    col = np.stack([np.clip(base + rng.integers(-40, 41, base.shape), 0, 255) for _ in range(channels)], -1).astype(np.uint8)
+    kps, desc = ctx.orb_extract(col, 400, rgb=rgb)
+    k0, d0 = ctx.orb_extract(oracle.to_gray(col, rgb=rgb), 400)
+    assert len(kps) == len(k0) > 300 and np.array_equal(kps, k0) and np.array_equal(desc, d0)

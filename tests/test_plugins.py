@@ -116,11 +116,11 @@ def test_global_ba_sharded_over_all_gpus_through_reference_api():
     ndev = min(n.value, 8)
     pb = synth.synth_ba(n_cams=50, n_points=2000, obs_per_point=5, n_fixed=2, seed=42)  # (the local-BA window of the other tests)
     want = pb.copy()
-    oracle.ba_solve(want, max_iterations=6, function_tolerance=0.0, pcg_max_iters=40)
+    oracle.ba_solve(want, max_iterations=6, function_tolerance=0.0)
     with tempfile.TemporaryDirectory() as d:
         write_ba(os.path.join(d, "in.bin"), pb, 6, 0.0)
         r = run("ba", os.path.join(d, "in.bin"), os.path.join(d, "out.bin"), "b200.devices=" + ",".join(str(k) for k in range(ndev)),
-                "b200.multi_min_obs=1000", "b200.pcg_iters=40")
+                "b200.multi_min_obs=1000")
         assert r.returncode == 0, r.stderr
         raw = open(os.path.join(d, "out.bin"), "rb").read()
     assert struct.unpack("<i", raw[:4])[0] == 1
@@ -188,3 +188,65 @@ def test_orb_and_match_through_svar_module():
     assert np.array_equal(da, wda) and np.array_equal(db, wdb)
     w = oracle.match_hamming(wdb, wda)
     assert np.array_equal(idx, w[0]) and np.array_equal(d1, w[1]) and np.array_equal(d2, w[2])
+
+
+@needs_plugins
+def test_synth_dataset_frames_equal_python_generator(tmp_path):
+    """GSLAM::Dataset::open("x.synth") finds libgslamDB_synth.so through the reference's loader (Dataset.h:124-162,
+    GSLAM_REGISTER_DATASET GSLAM.h:35-41) and its frames are bit-identical to gslam_b200.synth.synth_stream.  No GPU involved."""
+    if not os.path.exists(os.path.join(LIB, "libgslamDB_synth.so")):
+        pytest.skip("dataset plugin not built")
+    cfg = tmp_path / "x.synth"
+    cfg.write_text("width 320\nheight 240\nframes 3\nseed 5\n")
+    out = tmp_path / "out.bin"
+    r = run("dataset", str(cfg), str(out))
+    assert r.returncode == 0, r.stderr
+    raw = open(out, "rb").read()
+    n, cams, w, h = struct.unpack("<4i", raw[:16])
+    assert (n, cams, w, h) == (3, 1, 320, 240)
+    got = np.frombuffer(raw[16:], np.uint8).reshape(n, h, w)
+    want = synth.synth_stream(320, 240, 3, seed=5)
+    assert np.array_equal(got, want)
+    # stereo: two cameras per frame, the right eye displaced by the configured disparity
+    cfg.write_text("width 256\nheight 192\nframes 2\nseed 2\nstereo 1\ndisparity 9\n")
+    r = run("dataset", str(cfg), str(out))
+    assert r.returncode == 0, r.stderr
+    raw = open(out, "rb").read()
+    n, cams, w, h = struct.unpack("<4i", raw[:16])
+    assert (n, cams, w, h) == (2, 2, 256, 192)
+
+
+@needs_plugins
+@pytest.mark.gpu
+def test_features_app_over_messenger_matches_direct_calls(tmp_path):
+    """The Messenger-level pipeline of SURVEY.md 8f-2, wired like `gslam play b200_features -dataset x.synth`: dataset/frame ->
+    gslam.apps.b200_features (ORB extract on the B200, MapFrame::setKeyPoints, Hamming match against the previous frame) ->
+    b200/curframe.  Every frame's keypoints / descriptors / matches equal direct C-ABI calls on the same frames."""
+    from gslam_b200.api import Context
+    cfg = tmp_path / "x.synth"
+    cfg.write_text("width 640\nheight 480\nframes 4\nseed 3\n")
+    out = tmp_path / "out.bin"
+    r = run("features", str(cfg), str(out), "nfeatures=500")
+    assert r.returncode == 0, r.stderr[-2000:]
+    raw = open(out, "rb").read()
+    n = struct.unpack("<i", raw[:4])[0]
+    assert n == 4
+    frames = synth.synth_stream(640, 480, 4, seed=3)
+    ctx = Context(0)
+    off = 4
+    prev = None
+    for k in range(n):
+        fid, nk = struct.unpack("<2i", raw[off:off + 8]); off += 8
+        kps = np.frombuffer(raw[off:off + 28 * nk], capi.KP_DTYPE); off += 28 * nk
+        desc = np.frombuffer(raw[off:off + 32 * nk], np.uint8).reshape(nk, 32); off += 32 * nk
+        nm = struct.unpack("<i", raw[off:off + 4])[0]; off += 4
+        idx = np.frombuffer(raw[off:off + 4 * nm], np.int32); off += 4 * nm
+        ns = struct.unpack("<i", raw[off:off + 4])[0]; off += 4 + 4 * ns
+        k0, d0 = ctx.orb_extract(frames[k], 500)
+        assert fid == k + 1 and nk == len(k0) and np.array_equal(kps, k0) and np.array_equal(desc, d0)
+        if prev is None:
+            assert nm == 0
+        else:
+            assert np.array_equal(idx, ctx.match_hamming(d0, prev)[0])
+        prev = d0
+    ctx.close()

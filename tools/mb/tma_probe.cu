@@ -51,8 +51,8 @@ int main(int argc, char** argv) {
   const int mode = argc > 1 ? atoi(argv[1]) : 0, bsel = argc > 2 ? atoi(argv[2]) : 0;
   const int x = argc > 3 ? atoi(argv[3]) : 0, y = argc > 4 ? atoi(argv[4]) : 0;
   const int w = argc > 5 ? atoi(argv[5]) : 1920, h = argc > 6 ? atoi(argv[6]) : 1080, pitch = argc > 7 ? atoi(argv[7]) : ((w + 127) & ~127);
-  const int BWs[4] = {144, 64, 128, 256}, BHs[4] = {40, 32, 32, 8};
-  const int BW = BWs[bsel & 3], BH = BHs[bsel & 3];
+  const int BWs[5] = {144, 64, 128, 256, 160}, BHs[5] = {40, 32, 32, 8, 40};
+  const int BW = BWs[bsel % 5], BH = BHs[bsel % 5];
   void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
   cudaFree(0);
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) { printf("no entry point\n"); return 2; }
