@@ -456,7 +456,8 @@ constexpr int kChunkMaxLm = 64;  // landmarks per chunk (host plan)
 //  * the W blocks of a batch are staged EDGE-indexed: a landmark's blocks are contiguous in global memory, so staging is a plain
 //    16-byte-granular copy; the slot threads find their two edges with one popcount each;
 //  * thread t works the t-th slot the chunk really uses (host table), so a chunk over 10 cameras keeps exactly 55 lanes busy;
-//  * batches of 4 landmarks per barrier pair (static shared memory stays under 48 KB: three CTAs per SM), loads of the next batch in flight during the arithmetic (registers);
+//  * batches of 4 landmarks per barrier pair (static shared memory stays under 48 KB: three CTAs per SM), the next batch's W
+//    blocks in flight (cp.async) during the arithmetic;
 //  * acc = fma(y0, w0, fma(y1, w1, fma(y2, w2, acc))): 108 DFMA per (landmark, slot), nothing else on the fp64 pipe.
 __global__ void __launch_bounds__(kChunkThreads, 3) ba_schur_chunks_kernel(BaDev g) {
   if (g.sc->stop) return;
@@ -488,28 +489,28 @@ __global__ void __launch_bounds__(kChunkThreads, 3) ba_schur_chunks_kernel(BaDev
   for (int k = 0; k < 36; ++k) acc[k] = 0.0;
 #pragma unroll
   for (int k = 0; k < 6; ++k) ga[k] = 0.0;
-  // staging: per batch landmark b, edges 0..d_b-1, 9 double2 each -> items (b, q) with q < 9 * 16 (a landmark has <= 16 edges)
-  constexpr int kItems = (kChunkBatch * kChunkCams * 9 + kChunkThreads - 1) / kChunkThreads;
-  double2 pre[kItems];
-  auto prefetch = [&](int tb) {
+  // staging: per batch landmark b, edges 0..d_b-1, nine 16-byte pieces each -- asynchronous global -> shared copies (cp.async /
+  // LDGSTS: no registers in between; a register-staged prefetch was spilled to local memory by ptxas and stalled on the load it was
+  // meant to hide, profiles/r02_ncu_summary.md), issued one batch ahead into the other buffer
+  auto stage = [&](int tb, int bsel) {
     const int nb = min(kChunkBatch, nlm - tb);
-#pragma unroll
-    for (int q = 0; q < kItems; ++q) {
-      const int w = t + q * kChunkThreads, b = w / (kChunkCams * 9), r = w - b * (kChunkCams * 9);
-      pre[q] = make_double2(0.0, 0.0);
-      if (b < nb && r < 9 * __popc(s_mask[tb + b])) pre[q] = reinterpret_cast<const double2*>(g.W + 18 * (size_t)s_e0[tb + b])[r];
+    for (int w = t; w < nb * kChunkCams * 9; w += kChunkThreads) {
+      const int b = w / (kChunkCams * 9), r = w - b * (kChunkCams * 9);
+      if (r < 9 * __popc(s_mask[tb + b])) {
+        const double2* src = reinterpret_cast<const double2*>(g.W + 18 * (size_t)s_e0[tb + b]) + r;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<double2*>(&sW[bsel][b][0][0]) + r);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  prefetch(0);
+  stage(0, 0);
   int buf = 0;
   for (int tb = 0; tb < nlm; tb += kChunkBatch, buf ^= 1) {
     const int nb = min(kChunkBatch, nlm - tb);
-#pragma unroll
-    for (int q = 0; q < kItems; ++q) {
-      const int w = t + q * kChunkThreads;
-      if (w < kChunkBatch * kChunkCams * 9) reinterpret_cast<double2*>(&sW[buf][0][0][0])[w] = pre[q];
-    }
-    __syncthreads();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // batch tb has landed in sW[buf]; everybody is done reading sW[buf ^ 1] / sY[buf ^ 1] (batch tb - 1)
+    if (tb + kChunkBatch < nlm) stage(tb + kChunkBatch, buf ^ 1);  // in flight during the Y step and the accumulation below
     // Y = W V^-1 : one thread per (landmark, edge, row)
     for (int w = t; w < nb * kChunkCams * 6; w += kChunkThreads) {
       const int b = w / (kChunkCams * 6), r = w - b * (kChunkCams * 6), k = r / 6, a = r - 6 * k;
@@ -520,7 +521,6 @@ __global__ void __launch_bounds__(kChunkThreads, 3) ba_schur_chunks_kernel(BaDev
         for (int c = 0; c < 3; ++c) sY[buf][b][k][a * 3 + c] = w0 * Vi[c] + w1 * Vi[3 + c] + w2 * Vi[6 + c];
       }
     }
-    if (tb + kChunkBatch < nlm) prefetch(tb + kChunkBatch);  // (global loads in flight during the accumulation below)
     __syncthreads();
     if (slot) {
       for (int b = 0; b < nb; ++b) {
