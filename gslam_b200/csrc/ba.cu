@@ -459,7 +459,12 @@ constexpr int kChunkMaxLm = 64;  // landmarks per chunk (host plan)
 //  * batches of 4 landmarks per barrier pair (static shared memory stays under 48 KB: three CTAs per SM), the next batch's W
 //    blocks in flight (cp.async) during the arithmetic;
 //  * acc = fma(y0, w0, fma(y1, w1, fma(y2, w2, acc))): 108 DFMA per (landmark, slot), nothing else on the fp64 pipe.
-__global__ void __launch_bounds__(kChunkThreads, 3) ba_schur_chunks_kernel(BaDev g) {
+//  * v6: TWO threads per slot (rows 0-2 / rows 3-5 of the 6x6 block): v5 kept 2 of a CTA's 5 warps busy in the accumulation and the
+//    fp64 pipe 18 % active (profiles/r02_ncu_summary.md); halving the per-thread accumulator also frees registers for 4 CTAs / SM.
+//    A chunk with more than 80 used slots (13+ cameras; the planner avoids it) is worked in passes of 80 slots.
+constexpr int kChunkSlotsPerPass = kChunkThreads / 2;
+
+__global__ void __launch_bounds__(kChunkThreads, 4) ba_schur_chunks_kernel(BaDev g) {
   if (g.sc->stop) return;
   __shared__ __align__(16) double sW[2][kChunkBatch][kChunkCams][18];  // [buffer][landmark of the batch][edge][6x3]
   __shared__ __align__(16) double sY[2][kChunkBatch][kChunkCams][18];
@@ -469,12 +474,6 @@ __global__ void __launch_bounds__(kChunkThreads, 3) ba_schur_chunks_kernel(BaDev
   __shared__ double s_gp[kChunkMaxLm][3];
   const int t = threadIdx.x, chunk = blockIdx.x;
   const int nused = g.sp_nused[chunk];
-  const bool slot = t < nused;
-  const int s = slot ? g.sp_slots[(size_t)chunk * kChunkSlots + t] : 0;
-  int lb = 0;
-  while (lb < kChunkCams - 1 && (lb + 1) * (lb + 2) / 2 <= s) ++lb;
-  const int la = s - lb * (lb + 1) / 2;
-  const unsigned int need = slot ? ((1u << la) | (1u << lb)) : 0xffffffffu, below_a = (1u << la) - 1u, below_b = (1u << lb) - 1u;
   const int t0 = g.sp_pt0[chunk], nlm = min(g.sp_pt0[chunk + 1] - t0, kChunkMaxLm);
   for (int w = t; w < nlm * 12; w += kChunkThreads) {
     const int b = w / 12, k = w - 12 * b;
@@ -484,14 +483,9 @@ __global__ void __launch_bounds__(kChunkThreads, 3) ba_schur_chunks_kernel(BaDev
     if (k == 0) { s_mask[b] = g.sp_mask[t0 + b]; s_e0[b] = g.pt_off[j]; }
   }
   __syncthreads();
-  double acc[36], ga[6];
-#pragma unroll
-  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) ga[k] = 0.0;
   // staging: per batch landmark b, edges 0..d_b-1, nine 16-byte pieces each -- asynchronous global -> shared copies (cp.async /
   // LDGSTS: no registers in between; a register-staged prefetch was spilled to local memory by ptxas and stalled on the load it was
-  // meant to hide, profiles/r02_ncu_summary.md), issued one batch ahead into the other buffer
+  // meant to hide), issued one batch ahead into the other buffer
   auto stage = [&](int tb, int bsel) {
     const int nb = min(kChunkBatch, nlm - tb);
     for (int w = t; w < nb * kChunkCams * 9; w += kChunkThreads) {
@@ -504,53 +498,70 @@ __global__ void __launch_bounds__(kChunkThreads, 3) ba_schur_chunks_kernel(BaDev
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  stage(0, 0);
-  int buf = 0;
-  for (int tb = 0; tb < nlm; tb += kChunkBatch, buf ^= 1) {
-    const int nb = min(kChunkBatch, nlm - tb);
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();  // batch tb has landed in sW[buf]; everybody is done reading sW[buf ^ 1] / sY[buf ^ 1] (batch tb - 1)
-    if (tb + kChunkBatch < nlm) stage(tb + kChunkBatch, buf ^ 1);  // in flight during the Y step and the accumulation below
-    // Y = W V^-1 : one thread per (landmark, edge, row)
-    for (int w = t; w < nb * kChunkCams * 6; w += kChunkThreads) {
-      const int b = w / (kChunkCams * 6), r = w - b * (kChunkCams * 6), k = r / 6, a = r - 6 * k;
-      if (k < __popc(s_mask[tb + b])) {
-        const double* Vi = s_vi[tb + b];
-        const double w0 = sW[buf][b][k][a * 3], w1 = sW[buf][b][k][a * 3 + 1], w2 = sW[buf][b][k][a * 3 + 2];
+  const int half = t & 1;
+  for (int pass = 0; pass * kChunkSlotsPerPass < nused; ++pass) {
+    const int si = pass * kChunkSlotsPerPass + (t >> 1);
+    const bool slot = si < nused;
+    const int s = slot ? g.sp_slots[(size_t)chunk * kChunkSlots + si] : 0;
+    int lb = 0;
+    while (lb < kChunkCams - 1 && (lb + 1) * (lb + 2) / 2 <= s) ++lb;
+    const int la = s - lb * (lb + 1) / 2;
+    const unsigned int need = slot ? ((1u << la) | (1u << lb)) : 0xffffffffu, below_a = (1u << la) - 1u, below_b = (1u << lb) - 1u;
+    double acc[18], ga[3];  // rows 3*half .. 3*half+2 of the slot's 6x6 block (and of g~ on the diagonal)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) sY[buf][b][k][a * 3 + c] = w0 * Vi[c] + w1 * Vi[3 + c] + w2 * Vi[6 + c];
+    for (int k = 0; k < 18; ++k) acc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ga[k] = 0.0;
+    __syncthreads();  // (a previous pass is done with the buffers)
+    stage(0, 0);
+    int buf = 0;
+    for (int tb = 0; tb < nlm; tb += kChunkBatch, buf ^= 1) {
+      const int nb = min(kChunkBatch, nlm - tb);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();  // batch tb has landed in sW[buf]; everybody is done reading sW[buf ^ 1] / sY[buf ^ 1] (batch tb - 1)
+      if (tb + kChunkBatch < nlm) stage(tb + kChunkBatch, buf ^ 1);  // in flight during the Y step and the accumulation below
+      // Y = W V^-1 : one thread per (landmark, edge, row)
+      for (int w = t; w < nb * kChunkCams * 6; w += kChunkThreads) {
+        const int b = w / (kChunkCams * 6), r = w - b * (kChunkCams * 6), k = r / 6, a = r - 6 * k;
+        if (k < __popc(s_mask[tb + b])) {
+          const double* Vi = s_vi[tb + b];
+          const double w0 = sW[buf][b][k][a * 3], w1 = sW[buf][b][k][a * 3 + 1], w2 = sW[buf][b][k][a * 3 + 2];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) sY[buf][b][k][a * 3 + c] = w0 * Vi[c] + w1 * Vi[3 + c] + w2 * Vi[6 + c];
+        }
       }
-    }
-    __syncthreads();
-    if (slot) {
-      for (int b = 0; b < nb; ++b) {
-        const unsigned int m = s_mask[tb + b];
-        if ((m & need) != need) continue;
-        const double* Yp = &sY[buf][b][__popc(m & below_a)][0];
-        const double2* W2 = reinterpret_cast<const double2*>(&sW[buf][b][__popc(m & below_b)][0]);
-        double wb[18];
+      __syncthreads();
+      if (slot) {
+        for (int b = 0; b < nb; ++b) {
+          const unsigned int m = s_mask[tb + b];
+          if ((m & need) != need) continue;
+          const double* Yp = &sY[buf][b][__popc(m & below_a)][9 * half];
+          const double2* W2 = reinterpret_cast<const double2*>(&sW[buf][b][__popc(m & below_b)][0]);
+          double wb[18];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) { const double2 v = W2[k]; wb[2 * k] = v.x; wb[2 * k + 1] = v.y; }
-        const bool dg = la == lb;
-        const double g0 = s_gp[tb + b][0], g1 = s_gp[tb + b][1], g2 = s_gp[tb + b][2];
+          for (int k = 0; k < 9; ++k) { const double2 v = W2[k]; wb[2 * k] = v.x; wb[2 * k + 1] = v.y; }
+          const bool dg = la == lb;
+          const double g0 = s_gp[tb + b][0], g1 = s_gp[tb + b][1], g2 = s_gp[tb + b][2];
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-          const double y0 = Yp[a * 3], y1 = Yp[a * 3 + 1], y2 = Yp[a * 3 + 2];
+          for (int a = 0; a < 3; ++a) {
+            const double y0 = Yp[a * 3], y1 = Yp[a * 3 + 1], y2 = Yp[a * 3 + 2];
 #pragma unroll
-          for (int c = 0; c < 6; ++c) acc[a * 6 + c] = fma(y0, wb[c * 3], fma(y1, wb[c * 3 + 1], fma(y2, wb[c * 3 + 2], acc[a * 6 + c])));
-          if (dg) ga[a] = fma(y0, g0, fma(y1, g1, fma(y2, g2, ga[a])));
+            for (int c = 0; c < 6; ++c) acc[a * 6 + c] = fma(y0, wb[c * 3], fma(y1, wb[c * 3 + 1], fma(y2, wb[c * 3 + 2], acc[a * 6 + c])));
+            if (dg) ga[a] = fma(y0, g0, fma(y1, g1, fma(y2, g2, ga[a])));
+          }
         }
       }
     }
-  }
-  if (!slot) return;
-  double2* dst = reinterpret_cast<double2*>(g.sp_stageS + ((size_t)chunk * kChunkSlots + s) * 36);
+    if (slot) {
+      double2* dst = reinterpret_cast<double2*>(g.sp_stageS + ((size_t)chunk * kChunkSlots + s) * 36 + 18 * half);
 #pragma unroll
-  for (int k = 0; k < 18; ++k) dst[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
-  if (la == lb) {
-    double* dg = g.sp_stageG + ((size_t)chunk * kChunkCams + la) * 6;
+      for (int k = 0; k < 9; ++k) dst[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
+      if (la == lb) {
+        double* dg = g.sp_stageG + ((size_t)chunk * kChunkCams + la) * 6 + 3 * half;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) dg[k] = ga[k];
+        for (int k = 0; k < 3; ++k) dg[k] = ga[k];
+      }
+    }
   }
 }
 
@@ -1792,7 +1803,9 @@ static bool ba_schur_plan(gb_ctx* ctx, gb_ba_graph* g, int np, const std::vector
     std::set_union(cur.begin(), cur.end(), scam.begin() + a, scam.begin() + b, std::back_inserter(merged));  // (edges are camera-sorted, no duplicates)
     // close when the camera set would overflow, the chunk is full, or -- so that most chunks keep ONE camera set and their slot
     // threads stay dense -- when the set would grow although the chunk already holds a fair number of landmarks
-    if ((int)merged.size() > kChunkCams || t - open_from >= lmax || (merged.size() > cur.size() && !cur.empty() && t - open_from >= lmax / 4)) {
+    // (12 cameras = 78 slots: one pass of the two-threads-per-slot kernel; only a landmark with 13..16 observers forces more)
+    const int cam_cap = std::max(12, b - a);
+    if ((int)merged.size() > std::min(kChunkCams, cam_cap) || t - open_from >= lmax || (merged.size() > cur.size() && !cur.empty() && t - open_from >= lmax / 4)) {
       close(t);
       merged.assign(scam.begin() + a, scam.begin() + b);
     }
@@ -2133,7 +2146,7 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   GB_CHECK(gb_ba_graph_reset(ctx, g));
   ba_pick_pcg(ctx, g);
   if ((!g->pcg_sparse || compact_only) && d.s_nnzb > 0) {  // (a shard always runs on the compact block-CSR system)
-    GB_CHECK(ba_pcg_bcsr_plan(ctx, g, s_rowptr.data()));
+    GB_CHECK(ba_pcg_bcsr_plan(ctx, g, s_rowptr.data(), s_col.data()));
     if (!getenv("GB_BA_NO_SCHUR_CHUNKS")) ba_schur_plan(ctx, g, np, pt_off, scam, h + o_pf, s_rowptr, s_col, s_upper);  // (optional: the block-gather kernel otherwise)
   }
   if (compact_only && !g->pcg_bcsr) {

@@ -32,6 +32,7 @@ struct gb_ba_graph {
   bool pcg_bcsr = false;
   int bcsr_ctas = 0, bcsr_K = 0, bcsr_in_smem = 0, bcsr_max_cams = 0, bcsr_max_blocks = 0, bcsr_cluster = 0, bcsr_blk_stride = 37;
   size_t bcsr_smem = 0;
+  unsigned short bcsr_need[16] = {0};  // cluster mode: bcsr_need[c] = CTAs that read the rows of u owned by CTA c
   int* bcsr_cta_cam = nullptr;   // device [bcsr_ctas + 1]: first camera of each CTA's block-row range (base of one allocation)
   double* bcsr_part = nullptr;   // device [bcsr_ctas * 2]: per-CTA (gamma, delta) partials
   double* bcsr_u = nullptr;      // device [n6]: the published u = Minv r
@@ -60,7 +61,7 @@ int ba_read_result(gb_ctx* ctx, gb_ba_graph* g, gb_ba_result* res);             
 
 // ---- ba_pcg_bcsr.cu ---------------------------------------------------------------------------------------------------------
 // Decide whether / how the multi-CTA block-CSR PCG applies to `g` (fills the bcsr_* fields, allocates its small device buffers).
-int ba_pcg_bcsr_plan(gb_ctx* ctx, gb_ba_graph* g, const int* s_rowptr_host);
+int ba_pcg_bcsr_plan(gb_ctx* ctx, gb_ba_graph* g, const int* s_rowptr_host, const int* s_col_host);
 void ba_pcg_bcsr_free(gb_ba_graph* g);
 // damp + block-Jacobi PCG on the reduced camera system held in `rbuf` + retraction of the cameras (pose_new, Rt_new, x)
 int ba_pcg_bcsr_launch(gb_ctx* ctx, gb_ba_graph* g, const double* rbuf);

@@ -27,7 +27,8 @@ using namespace ba;
 namespace {
 
 constexpr int kBcsrThreads = 512;
-constexpr int kBlkStride = 37;  // doubles per 6x6 block in shared memory (37: the K lanes of a row hit distinct banks)
+constexpr int kBlkStride = 38;  // doubles per 6x6 block in shared memory: 304 B keeps 16-byte alignment for LDS.128 and spreads the
+                                // lanes of a camera (consecutive blocks) over distinct bank groups
 
 struct BcsrArgs {
   const int* cta_cam;   // [G+1]
@@ -35,6 +36,7 @@ struct BcsrArgs {
   double* u_glob;       // [n6]
   unsigned int* bar;    // grid barrier counter (zeroed before the launch)
   int K, in_smem, maxit, max_cams, max_blocks, blk_stride;
+  unsigned short need[16];  // CLUSTER: need[c] = which CTAs of the cluster read camera rows owned by CTA c (covisibility), self included
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -143,8 +145,10 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
       __syncthreads();
       cg::cluster_group cluster = cg::this_cluster();
       const int pairs = rows >> 1;  // rows = 6 * cameras: even
+      const unsigned int need = a.need[b];
       for (int t = tid; t < pairs * G; t += kBcsrThreads) {
         const int peer = t / pairs, q = t - peer * pairs;
+        if (!((need >> peer) & 1u)) continue;  // that CTA has no block in these columns: it never reads them
         double* pu = cluster.map_shared_rank(u_full, peer);
         *reinterpret_cast<double2*>(pu + 6 * cam0 + 2 * q) = make_double2(vu[2 * q], vu[2 * q + 1]);
       }
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
   // optional phase clocks (test hook gb_dbg_ba_pcg_profile): CTA 0 / thread 0 accumulates [setup, mat-vec + local dots, barrier 1,
   // scalars + recurrences + publication, barrier 2, total, iterations]
   const bool prof = g.prof != nullptr && b == 0 && tid == 0;
-  long long pc[5] = {0, 0, 0, 0, 0}, t_prev = clock64();
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_prev = clock64();
   const long long t_begin = t_prev;
   auto stamp = [&](int k) { if (prof) { const long long t = clock64(); pc[k] += t - t_prev; t_prev = t; } };
 
@@ -174,32 +178,38 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
       for (int t = tid; t < n6; t += kBcsrThreads) u_full[t] = __ldcg(a.u_glob + t);
       __syncthreads();
     }
+    // K lanes per CAMERA (K = 2^k <= 32): lane `sub` takes whole blocks sub, sub+K, ... of the block row -- the 36 coefficients and
+    // the six entries of u with 16-byte shared-memory loads, 36 DFMA in six independent chains -- then a fixed xor tree over the K
+    // lanes.  (One lane per ROW re-read u six times per block and moved 8 bytes per load: the mat-vec was shared-memory-bound.)
     double pg = 0.0, pd = 0.0;
-    for (int rbase = 0; rbase < rows; rbase += groups) {  // (uniform trip count: whole groups of K lanes share a row)
-      const int r = rbase + tid / K;
-      double acc = 0.0;
-      if (r < rows) {
-        const int c = r / 6, comp = r - 6 * c;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;  // three independent chains (the fp64 pipe is deep; a single chain is latency-bound)
+    for (int cbase = 0; cbase < ncl; cbase += groups) {  // (uniform trip count: whole groups of K lanes share a camera)
+      const int c = cbase + tid / K;
+      double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0, r4 = 0.0, r5 = 0.0;
+      if (c < ncl) {
         for (int t = rp[c] + sub; t < rp[c + 1]; t += K) {
-          const double* row = Sp + (size_t)t * bstride + comp * 6;
-          const double* uc = u_full + 6 * col[t];
-          a0 += row[0] * uc[0];
-          a1 += row[1] * uc[1];
-          a2 += row[2] * uc[2];
-          a0 += row[3] * uc[3];
-          a1 += row[4] * uc[4];
-          a2 += row[5] * uc[5];
+          const double2* B2 = reinterpret_cast<const double2*>(Sp + (size_t)t * bstride);
+          const double2* U2 = reinterpret_cast<const double2*>(u_full + 6 * col[t]);
+          const double2 ua = U2[0], ub = U2[1], uc = U2[2];
+#define GB_ROW(acc, k)                                                                              \
+          { const double2 s0 = B2[3 * (k)], s1 = B2[3 * (k) + 1], s2 = B2[3 * (k) + 2];              \
+            acc = fma(s0.x, ua.x, fma(s0.y, ua.y, fma(s1.x, ub.x, fma(s1.y, ub.y, fma(s2.x, uc.x, fma(s2.y, uc.y, acc)))))); }
+          GB_ROW(r0, 0) GB_ROW(r1, 1) GB_ROW(r2, 2) GB_ROW(r3, 3) GB_ROW(r4, 4) GB_ROW(r5, 5)
+#undef GB_ROW
         }
-        acc = (a0 + a1) + a2;
       }
-      for (int o = K >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (r < rows && sub == 0) {
-        vw[r] = acc;
+      for (int o = K >> 1; o > 0; o >>= 1) {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, o); r1 += __shfl_xor_sync(0xffffffffu, r1, o); r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        r3 += __shfl_xor_sync(0xffffffffu, r3, o); r4 += __shfl_xor_sync(0xffffffffu, r4, o); r5 += __shfl_xor_sync(0xffffffffu, r5, o);
+      }
+      if (c < ncl && sub < 6) {  // (K >= 8 always holds here: lanes 0..5 of the camera publish one row each)
+        const double v = sub == 0 ? r0 : sub == 1 ? r1 : sub == 2 ? r2 : sub == 3 ? r3 : sub == 4 ? r4 : r5;
+        const int r = 6 * c + sub;
+        vw[r] = v;
         pg += vr[r] * vu[r];
-        pd += acc * vu[r];
+        pd += v * vu[r];
       }
     }
+    stamp(5);  // (own mat-vec + lane reduction done)
     // ---- D. (gamma, delta): fixed tree inside the CTA, per-CTA partials folded in CTA order by everybody ----
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -208,6 +218,7 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
     }
     if (lane == 0) { s_warp[0][warp] = pg; s_warp[1][warp] = pd; }
     __syncthreads();
+    stamp(6);  // (everybody's mat-vec done)
     if (CLUSTER) {
       if (tid < G) {  // thread p hands this CTA's partial pair to peer p
         double sg = 0.0, sd = 0.0;
@@ -285,7 +296,8 @@ __global__ void __launch_bounds__(kBcsrThreads, 1) ba_pcg_bcsr_kernel(BaDev g, d
     stamp(4);
   }
   if (prof) {
-    g.prof[0] = t_begin; g.prof[1] = pc[1]; g.prof[2] = pc[2]; g.prof[3] = pc[3]; g.prof[4] = pc[4]; g.prof[5] = clock64() - t_begin; g.prof[6] = k_it;
+    g.prof[0] = pc[5]; g.prof[1] = pc[1]; g.prof[2] = pc[2]; g.prof[3] = pc[3]; g.prof[4] = pc[4]; g.prof[5] = clock64() - t_begin; g.prof[6] = k_it;
+    g.prof[7] = pc[6];
   }
   // ---- F. solution + retraction of the owned cameras ----
   for (int r = tid; r < rows; r += kBcsrThreads) g.x[6 * cam0 + r] = vx[r];
@@ -334,7 +346,7 @@ static void bcsr_partition(int nc, int nnzb, const int* s_rowptr, int G, std::ve
   }
 }
 
-int ba_pcg_bcsr_plan(gb_ctx* ctx, gb_ba_graph* g, const int* s_rowptr) {
+int ba_pcg_bcsr_plan(gb_ctx* ctx, gb_ba_graph* g, const int* s_rowptr, const int* s_col_host) {
   g->pcg_bcsr = false;
   const int nc = g->d.nc, nnzb = g->d.s_nnzb, n6 = g->d.n6;
   if (nc <= 0 || nnzb <= 0) return GB_OK;
@@ -371,7 +383,7 @@ int ba_pcg_bcsr_plan(gb_ctx* ctx, gb_ba_graph* g, const int* s_rowptr) {
       if (C > 8 && !cluster16_ok[ctx->device]) continue;
       int mc, mb;
       bcsr_partition(nc, nnzb, s_rowptr, C, cta_cam, &mc, &mb);
-      const int strides[2] = {kBlkStride, 36};
+      const int strides[2] = {kBlkStride, 36};  // (36: 2-way bank conflicts on the block loads, but 6 % less shared memory)
       for (int q = 0; q < 2 && !cluster; ++q) {
         const size_t need = bcsr_smem_bytes(n6, mc, mb, true, strides[q]);
         if (need > budget) continue;
@@ -407,8 +419,8 @@ int ba_pcg_bcsr_plan(gb_ctx* ctx, gb_ba_graph* g, const int* s_rowptr) {
     }
     if ((long long)per_sm * ctx->sm_count < G) return GB_OK;
   }
-  int K = 32;
-  while (K > 1 && 6 * max_cams * K > kBcsrThreads) K >>= 1;
+  int K = 32;  // lanes per camera in the mat-vec (>= 8: lanes 0..5 publish the six rows)
+  while (K > 8 && max_cams * K > kBcsrThreads) K >>= 1;
   const size_t bytes = (size_t)(G + 1) * 4 + 256 + (size_t)2 * G * 8 + 256 + (size_t)n6 * 8 + 256 + 256;
   uint8_t* base = nullptr;
   GB_CUDA(ctx, cudaMalloc((void**)&base, bytes));
@@ -422,6 +434,17 @@ int ba_pcg_bcsr_plan(gb_ctx* ctx, gb_ba_graph* g, const int* s_rowptr) {
   GB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // (cta_cam is a stack-lifetime host vector)
   g->bcsr_ctas = G; g->bcsr_K = K; g->bcsr_in_smem = in_smem ? 1 : 0; g->bcsr_smem = smem;
   g->bcsr_max_cams = max_cams; g->bcsr_max_blocks = max_blocks; g->bcsr_cluster = cluster; g->bcsr_blk_stride = blk_stride;
+  // who reads whose rows of u (cluster mode: the publication of u only goes where it is needed)
+  for (int c = 0; c < 16; ++c) g->bcsr_need[c] = 0;
+  if (cluster) {
+    std::vector<int> owner(nc, 0);
+    for (int c = 0; c < G; ++c)
+      for (int i = cta_cam[c]; i < cta_cam[c + 1]; ++i) owner[i] = c;
+    for (int p = 0; p < G; ++p) {
+      g->bcsr_need[p] |= (unsigned short)(1u << p);
+      for (int t = s_rowptr[cta_cam[p]]; t < s_rowptr[cta_cam[p + 1]]; ++t) g->bcsr_need[owner[s_col_host[t]]] |= (unsigned short)(1u << p);
+    }
+  }
   g->pcg_bcsr = true;
   return GB_OK;
 }
@@ -441,6 +464,7 @@ int ba_pcg_bcsr_launch(gb_ctx* ctx, gb_ba_graph* g, const double* rbuf) {
   a.cta_cam = g->bcsr_cta_cam; a.part = g->bcsr_part; a.u_glob = g->bcsr_u; a.bar = g->bcsr_bar;
   a.K = g->bcsr_K; a.in_smem = g->bcsr_in_smem; a.maxit = g->opt.pcg_max_iters; a.max_cams = g->bcsr_max_cams; a.max_blocks = g->bcsr_max_blocks;
   a.blk_stride = g->bcsr_blk_stride;
+  for (int c = 0; c < 16; ++c) a.need[c] = g->bcsr_need[c];
   double* rb = const_cast<double*>(rbuf);  // (the damped diagonal is written back when S stays in global memory)
   if (g->bcsr_cluster > 0) {
     cudaLaunchConfig_t cfg = {};

@@ -23,5 +23,6 @@ for env in ({}, {"GB_BA_NO_PCG_CLUSTER": "1"}):
     L.gb_dbg_ba_pcg_profile(ctx._h, g._h, out.ctypes.data_as(C.c_void_p))   # read (last launch)
     it = max(int(out[6]), 1)
     print("mode", env or "cluster", "gpu_ms", r.gpu_ms, "iters", it, "clk/iter: matvec+dots", out[1] // it, "barrier1", out[2] // it, "update+publish", out[3] // it,
-          "barrier2", out[4] // it, "total clk", out[5])
+          "barrier2", out[4] // it, "total clk", out[5],
+          "| inside the first: own mat-vec", out[0] // it, "wait for the CTA", out[7] // it)
     g.close()
