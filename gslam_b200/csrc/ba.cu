@@ -1913,6 +1913,7 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   BaTrace tr;
   GB_CHECK(ba_validate(ctx, pb));
   if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return GB_ERR_INVALID;
+  if (use_arena && ctx->ba_cached) ba_cache_drop(ctx);  // (another host-buffer call wants the arena the cached graph lives in)
   tr.stamp("validate");
   const int nc = pb->n_cams, np_full = pb->n_points, no_full = pb->n_obs;
   gb_ba_graph* g = new gb_ba_graph();
@@ -2126,11 +2127,13 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   if (!chol_plan3.empty()) memcpy(h + o_ch, chol_plan3.data(), chol_plan3.size() * 4);
   g->chol_plan = (const int*)(dblob + o_ch);
   g->sorted_to_orig.swap(order);
+  g->cam_perm_h.swap(cam_perm);
   tr.stamp("blob fill");
   GB_CUDA(ctx, cudaMemcpyAsync(dblob, h, blob, cudaMemcpyHostToDevice, ctx->stream));
   d.cam_ticket = reinterpret_cast<unsigned int*>(cam_ticket_d);
   GB_CUDA(ctx, cudaMemsetAsync(d.cam_ticket, 0, ((size_t)nc / 2 + 1) * 8, ctx->stream));
   double* d_pose_wc = (double*)(dblob + o_pose);
+  g->pose_wc_in = d_pose_wc;
   g->pts_init = (double*)(dblob + o_pts);
   d.dof = dblob + o_dof; d.pfree = dblob + o_pf;
   d.o_cam = (int*)(dblob + o_oc); d.o_pt = (int*)(dblob + o_op); d.o_uv = (double*)(dblob + o_uv);
@@ -2536,18 +2539,119 @@ int gb_ba_graph_download(gb_ctx* ctx, gb_ba_graph* g, double* cam_pose_wc, doubl
   return GB_OK;
 }
 
-int gb_ba_solve(gb_ctx* ctx, gb_ba_problem* pb, const gb_ba_options* opt, gb_ba_result* res) {
+}  // extern "C"
+
+// ---- host-buffer solve with a topology cache ------------------------------------------------------------------------------------
+// A SLAM's mapping thread re-solves a sliding window whose graph changes by one keyframe now and then but mostly only in its
+// ESTIMATES.  gb_ba_solve keeps the graph of its previous call (and the arena it lives in); when the next problem has the same
+// cameras / landmarks / edges / masks (exact memcmp of the index arrays, ~10 us at the benchmark window) only poses, points and
+// measurements are uploaded -- the ~165 us of sorting, covisibility structure, plans and blob fill are skipped.
+struct BaCacheKey {
+  int nc = 0, np = 0, no = 0;
+  bool has_dof = false, has_pf = false, has_info = false;
+  std::vector<int32_t> oc, op;
+  std::vector<uint8_t> dof, pf;
+  bool matches(const gb_ba_problem* pb) const {
+    if (pb->n_cams != nc || pb->n_points != np || pb->n_obs != no) return false;
+    if ((pb->cam_dof != nullptr) != has_dof || (pb->point_free != nullptr) != has_pf || (pb->obs_info != nullptr) != has_info) return false;
+    if (no > 0 && (memcmp(oc.data(), pb->obs_cam, (size_t)no * 4) != 0 || memcmp(op.data(), pb->obs_point, (size_t)no * 4) != 0)) return false;
+    if (has_dof && nc > 0 && memcmp(dof.data(), pb->cam_dof, nc) != 0) return false;
+    if (has_pf && np > 0 && memcmp(pf.data(), pb->point_free, np) != 0) return false;
+    return true;
+  }
+  void fill(const gb_ba_problem* pb) {
+    nc = pb->n_cams; np = pb->n_points; no = pb->n_obs;
+    has_dof = pb->cam_dof != nullptr; has_pf = pb->point_free != nullptr; has_info = pb->obs_info != nullptr;
+    oc.assign(pb->obs_cam, pb->obs_cam + no); op.assign(pb->obs_point, pb->obs_point + no);
+    if (has_dof) dof.assign(pb->cam_dof, pb->cam_dof + nc); else dof.clear();
+    if (has_pf) pf.assign(pb->point_free, pb->point_free + np); else pf.clear();
+  }
+};
+
+void ba_cache_drop(gb_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->ba_cached) { gb_ba_graph_destroy(ctx, ctx->ba_cached); ctx->ba_cached = nullptr; }
+  delete (BaCacheKey*)ctx->ba_cache_key;
+  ctx->ba_cache_key = nullptr;
+}
+
+// new estimates / measurements into a cached graph of the same topology (one pinned blob, three H2D copies, no structure work)
+static int ba_graph_refresh(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_problem* pb) {
+  BaDev& d = g->d;
+  const int nc = d.nc, np = d.np, no = d.no;
+  for (int k = 0; k < no; ++k) {
+    const double z = pb->obs_xyz[3 * (size_t)k + 2];
+    if (!(z != 0.0) || !std::isfinite(z)) { gb_set_error(ctx, "gb_ba: edge %d has a zero/non-finite measurement z", k); return GB_ERR_INVALID; }
+  }
+  const size_t b_pose = (size_t)nc * 56, b_pts = (size_t)np * 24, b_uv = (size_t)no * 16, b_info = d.has_info ? (size_t)no * 24 : 0;
+  GB_CHECK(gb_stage_reserve(ctx, ctx->h_stage_off + b_pose + b_pts + 2 * b_uv + b_info + 4096));
+  double* h_pose = (double*)gb_stage_alloc(ctx, b_pose + 8);
+  double* h_pts = (double*)gb_stage_alloc(ctx, b_pts + 8);
+  double* h_uv = (double*)gb_stage_alloc(ctx, b_uv + 8);
+  double* h_cuv = (double*)gb_stage_alloc(ctx, b_uv + 8);
+  double* h_info = b_info ? (double*)gb_stage_alloc(ctx, b_info) : nullptr;
+  if (!h_pose || !h_pts || !h_uv || !h_cuv || (b_info && !h_info)) { gb_set_error(ctx, "gb_ba: staging exhausted"); return GB_ERR_CUDA; }
+  memcpy(h_pose, pb->cam_pose_wc, b_pose);
+  memcpy(h_pts, pb->points, b_pts);
+  for (int e = 0; e < no; ++e) {
+    const int k = g->sorted_to_orig[e];
+    const double* m = pb->obs_xyz + 3 * (size_t)k;
+    h_uv[2 * e] = m[0] / m[2];
+    h_uv[2 * e + 1] = m[1] / m[2];
+    if (h_info) {
+      const double* L = pb->obs_info + 4 * (size_t)k;
+      h_info[3 * e] = L[0]; h_info[3 * e + 1] = 0.5 * (L[1] + L[2]); h_info[3 * e + 2] = L[3];
+    }
+  }
+  for (int idx = 0; idx < no; ++idx) {
+    const int e = g->cam_perm_h[idx];
+    h_cuv[2 * idx] = h_uv[2 * e];
+    h_cuv[2 * idx + 1] = h_uv[2 * e + 1];
+  }
+  cudaStream_t s = ctx->stream;
+  if (nc > 0) GB_CUDA(ctx, cudaMemcpyAsync(g->pose_wc_in, h_pose, b_pose, cudaMemcpyHostToDevice, s));
+  if (np > 0) GB_CUDA(ctx, cudaMemcpyAsync(g->pts_init, h_pts, b_pts, cudaMemcpyHostToDevice, s));
+  if (no > 0) {
+    GB_CUDA(ctx, cudaMemcpyAsync((void*)d.o_uv, h_uv, b_uv, cudaMemcpyHostToDevice, s));
+    GB_CUDA(ctx, cudaMemcpyAsync((void*)d.c_uv, h_cuv, b_uv, cudaMemcpyHostToDevice, s));
+    if (h_info) GB_CUDA(ctx, cudaMemcpyAsync((void*)d.o_info, h_info, b_info, cudaMemcpyHostToDevice, s));
+  }
+  if (nc > 0) {
+    ba_prepare_kernel<<<gb_div_up(nc, 128), 128, 0, s>>>(nc, g->pose_wc_in, g->pose_init);
+    GB_LAUNCH_CHECK(ctx);
+  }
+  return gb_ba_graph_reset(ctx, g);
+}
+
+extern "C" int gb_ba_solve(gb_ctx* ctx, gb_ba_problem* pb, const gb_ba_options* opt, gb_ba_result* res) {
   if (!ctx || !pb) return GB_ERR_INVALID;
   CtxLock lk(ctx);
-  gb_ba_graph* g = nullptr;
-  GB_CHECK(ba_graph_create_impl(ctx, pb, &g, true, 0, 1));
   BaTrace tr;
+  gb_ba_graph* g = nullptr;
+  BaCacheKey* key = (BaCacheKey*)ctx->ba_cache_key;
+  const bool cacheable = pb->n_obs > 0 && pb->n_obs <= (1 << 22) && pb->obs_cam && pb->obs_point && pb->obs_xyz && pb->cam_pose_wc && pb->points &&
+                         !getenv("GB_BA_NO_CACHE");
+  if (cacheable && ctx->ba_cached && key && key->matches(pb)) {
+    g = ctx->ba_cached;
+    GB_CHECK(ba_graph_refresh(ctx, g, pb));
+    tr.stamp("cached topology: refresh");
+  } else {
+    ba_cache_drop(ctx);
+    GB_CHECK(ba_graph_create_impl(ctx, pb, &g, true, 0, 1));
+    if (cacheable && g->from_arena) {
+      key = new BaCacheKey();
+      key->fill(pb);
+      ctx->ba_cache_key = key;
+      ctx->ba_cached = g;
+    }
+  }
   const int rc = ba_graph_solve_impl(ctx, g, opt, res, g->d.nc > 0 ? pb->cam_pose_wc : nullptr, g->d.np > 0 ? pb->points : nullptr);
   tr.stamp("solve + download (one sync)");
-  gb_ba_graph_destroy(ctx, g);
-  tr.stamp("destroy");
+  if (g != ctx->ba_cached) gb_ba_graph_destroy(ctx, g);
   return rc;
 }
+
+extern "C" {
 
 int gb_ba_pnp(gb_ctx* ctx, int n, const double* xyz, const double* xy1, double* pose_wc, int dof, double* info6x6,
               const gb_ba_options* opt, gb_ba_result* res) {

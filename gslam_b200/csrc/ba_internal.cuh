@@ -18,6 +18,8 @@ struct gb_ba_graph {
   size_t buf_doubles = 0;
   gb_ba_options opt{};
   std::vector<int> sorted_to_orig;  // sorted observation slot -> caller's edge index
+  std::vector<int> cam_perm_h;      // host copy of cam_perm (camera-sorted slot -> sorted slot): refresh of a cached graph
+  double* pose_wc_in = nullptr;     // device: the uploaded T_wc poses (blob), source of ba_prepare_kernel
   bool begun = false;
   // PCG dispatch: single-CTA block-sparse kernel, else one-cluster kernel (pcg_cluster = 8/16), else generic multi-kernel
   bool pcg_sparse = false;
@@ -70,3 +72,6 @@ int ba_pcg_bcsr_launch(gb_ctx* ctx, gb_ba_graph* g, const double* rbuf);
 bool ba_chol_plan_host(gb_ctx* ctx, int nc, const int* s_rowptr, const int* s_col, std::vector<int>& plan3, int* nblocks, size_t* smem);
 // block-skyline Cholesky solve of the damped reduced camera system in the dense-layout `buf` (+ g->d.Sb block values) + retraction
 int ba_chol_launch(gb_ctx* ctx, gb_ba_graph* g, double* buf, bool pdl);
+
+// host-buffer solve cache (ba.cu): drop the graph gb_ba_solve kept from its previous call on this ctx
+void ba_cache_drop(gb_ctx* ctx);

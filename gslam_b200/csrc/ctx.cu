@@ -49,6 +49,7 @@ int gb_dev_realloc(gb_ctx* ctx, void** p, size_t* cap, size_t bytes) {
 }
 
 extern void gb_orb_state_free(gb_ctx* ctx);
+extern void ba_cache_drop(gb_ctx* ctx);
 extern void gb_match_state_free(gb_ctx* ctx);
 
 extern "C" {
@@ -132,6 +133,7 @@ int gb_ctx_destroy(gb_ctx* ctx) {
     if (ctx->tmp_q) gb_features_destroy(ctx, ctx->tmp_q);
     if (ctx->tmp_t) gb_features_destroy(ctx, ctx->tmp_t);
     if (ctx->tmp_f) gb_features_destroy(ctx, ctx->tmp_f);
+    ba_cache_drop(ctx);
     gb_orb_state_free(ctx);
     gb_match_state_free(ctx);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);

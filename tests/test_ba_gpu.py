@@ -350,3 +350,28 @@ def test_direct_solver_is_refused_when_the_skyline_does_not_fit(ctx):
     big = synth.synth_ba(120, 600, all_visible=True, n_fixed=2, seed=5)   # every camera sees every landmark: full 120 x 120 block matrix
     with pytest.raises(capi.GbError):
         ctx.ba_solve(big, cfg(maxIterations=2, functionTolerance=0.0, linearSolver=1))
+
+
+def test_host_buffer_solve_topology_cache(ctx, monkeypatch):
+    """gb_ba_solve keeps the graph of its previous call while the topology stays the same (a sliding window re-solved with new
+    estimates): a cache hit uploads estimates and measurements only and must give bit-identical results to a cold solve; a topology
+    change (one more edge, another mask) must miss."""
+    c = cfg(maxIterations=6, functionTolerance=0.0)
+    rng = np.random.default_rng(3)
+    pb1 = synth.synth_ba(50, 2000, obs_per_point=5, n_fixed=2, seed=42)
+    pb2 = pb1.copy()
+    pb2.cam_pose_wc[2:, 4:] += rng.normal(0, 0.01, pb2.cam_pose_wc[2:, 4:].shape)
+    pb2.points += rng.normal(0, 0.02, pb2.points.shape)
+    pb2.obs_xyz[:, :2] += rng.normal(0, 1e-4, (pb2.n_obs, 2))
+    pb3 = pb2.copy(); pb3.point_free[5] = 0                      # mask change -> different topology
+    pb4 = synth.synth_ba(40, 1500, obs_per_point=6, n_fixed=2, seed=7)
+    seq = [pb1, pb2, pb2, pb3, pb4, pb1]
+    monkeypatch.setenv("GB_BA_NO_CACHE", "1")
+    cold = []
+    for p in seq:
+        q = p.copy(); r = ctx.ba_solve(q, c); cold.append((r.final_cost, r.accepted, q.cam_pose_wc.copy(), q.points.copy()))
+    monkeypatch.delenv("GB_BA_NO_CACHE")
+    for p, want in zip(seq, cold):
+        q = p.copy(); r = ctx.ba_solve(q, c)
+        assert r.final_cost == want[0] and r.accepted == want[1]
+        assert np.array_equal(q.cam_pose_wc, want[2]) and np.array_equal(q.points, want[3])
