@@ -194,6 +194,30 @@ class Context:
         return pose, r, info
 
 
+class Remap:
+    """A bilinear remap table resident in HBM (gb_remap): GSLAM::Undistorter::undistort on the device."""
+
+    def __init__(self, ctx: Context, w_in, h_in, w_out, h_out, idx4, coef4, remap_x):
+        self.ctx = ctx
+        self.shape_in, self.shape_out = (h_in, w_in), (h_out, w_out)
+        idx4 = np.ascontiguousarray(idx4, np.int32); coef4 = np.ascontiguousarray(coef4, np.float32); rx = np.ascontiguousarray(remap_x, np.float32)
+        h = C.c_void_p()
+        ctx._check(ctx._lib.gb_remap_create(ctx._h, w_in, h_in, w_out, h_out, ptr(idx4), ptr(coef4), ptr(rx), C.byref(h)))
+        self._h = h
+
+    def apply(self, img: np.ndarray) -> np.ndarray:
+        img = np.ascontiguousarray(img, np.uint8)
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        out = np.zeros(self.shape_out + ((ch,) if img.ndim == 3 else ()), np.uint8)
+        self.ctx._check(self.ctx._lib.gb_remap_apply(self.ctx._h, self._h, ptr(img), ch, ptr(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self.ctx._lib.gb_remap_destroy(self.ctx._h, self._h)
+        self._h = None
+
+
 class Features:
     """A frame's keypoints + descriptors resident in HBM (gb_features)."""
 

@@ -84,6 +84,9 @@ _SIGNATURES = [
     ("gb_match_download", C.c_int, [_VP, _VP, _VP, _VP, _VP, C.POINTER(C.c_int)]),
     ("gb_match_stereo", C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, C.c_int, C.c_float, C.c_float, C.c_float, _VP, _VP, _VP]),
     ("gb_match_stereo_features", C.c_int, [_VP, _VP, _VP, C.c_float, C.c_float, C.c_float]),
+    ("gb_remap_create", C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, C.POINTER(_VP)]),
+    ("gb_remap_destroy", C.c_int, [_VP, _VP]),
+    ("gb_remap_apply", C.c_int, [_VP, _VP, _VP, C.c_int, _VP]),
     ("gb_ba_options_default", None, [C.POINTER(BaOptions)]),
     ("gb_ba_solve", C.c_int, [_VP, C.POINTER(BaProblem), C.POINTER(BaOptions), C.POINTER(BaResult)]),
     ("gb_ba_pnp", C.c_int, [_VP, C.c_int, _VP, _VP, _VP, C.c_int, _VP, C.POINTER(BaOptions), C.POINTER(BaResult)]),

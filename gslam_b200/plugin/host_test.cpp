@@ -9,15 +9,18 @@
 //   gslam_b200_host_test findpnp <plugin-dir> in.bin out.bin   Estimator::create() -> findPnP (P3P + RANSAC), Estimator.h:158-164
 //   gslam_b200_host_test dataset <plugin-dir> x.synth out.bin  GSLAM::Dataset::open -> libgslamDB_synth.so -> grabFrame (Dataset.h:124-162)
 //   gslam_b200_host_test features <plugin-dir> x.synth out.bin dataset/frame -> gslam.apps.b200_features -> b200/curframe (Messenger)
+//   gslam_b200_host_test undistort <plugin-dir> in.bin out.bin  gslam.b200.undistort next to the reference's own GSLAM::Undistorter
 // Trailing "key=value" arguments become svar settings the plugins read (b200.devices=0,1 shards a global BA over two GPUs).
 #include <GSLAM/core/GSLAM.h>
 #include <GSLAM/core/Dataset.h>
 #include <GSLAM/core/Estimator.h>
 #include <GSLAM/core/Optimizer.h>
+#include <GSLAM/core/Undistorter.h>
 
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <thread>
 #include <fstream>
@@ -112,6 +115,48 @@ static int runORB(const std::string& dir, const char* in, const char* out) {
   wr(o, ka.data(), ka.size()); wr(o, da.data, (size_t)da.rows * 32);
   wr(o, kb.data(), kb.size()); wr(o, db.data, (size_t)db.rows * 32);
   wr(o, idx.data(), idx.size()); wr(o, d1.data(), d1.size()); wr(o, d2.data(), d2.size());
+  return 0;
+}
+
+// in : int32 w, h, channels, n_in_params, n_out_params, 3 x pad; doubles camera_in params, doubles camera_out params; image bytes
+// out: int32 w_out, h_out, channels, mismatching_inside_pixels; plugin image bytes; reference image bytes; inside mask bytes
+// The plugin's output and the reference's own Undistorter::undistort run side by side in this process (the reference is a header).
+static int runUndistort(const std::string& dir, const char* in, const char* out) {
+  svar.Set<std::string>("GSLAM_LIBRARY_PATH", dir);
+  Svar mod = Registry::load("b200");
+  if (mod.isUndefined()) { fprintf(stderr, "Registry::load(\"b200\") failed\n"); return 2; }
+  Svar und = mod["gslam"]["b200"]["undistort"];
+  std::ifstream f(in, std::ios::binary);
+  int32_t hdr[8];
+  rd(f, hdr, 8);
+  const int w = hdr[0], h = hdr[1], ch = hdr[2];
+  std::vector<double> pi(hdr[3]), po(hdr[4]);
+  rd(f, pi.data(), pi.size()); rd(f, po.data(), po.size());
+  Camera cin(pi), cout_(po);
+  // (one spare row behind the image: the reference's last-row taps read there)
+  std::vector<uchar> buf((size_t)w * (h + 2) * ch, 0);
+  rd(f, buf.data(), (size_t)w * h * ch);
+  GImage img(h, w, ch == 1 ? GImageType<uchar, 1>::Type : GImageType<uchar, 3>::Type, buf.data(), false);
+  Svar r = und(img, cin, cout_);
+  if (!r.is<GImage>()) return 1;
+  GImage mine = r.castAs<GImage>();
+  if (mine.empty()) return 1;
+  Svar again = und(img, cin, cout_);  // the cached table
+  if (std::memcmp(again.castAs<GImage>().data, mine.data, (size_t)mine.total() * mine.elemSize()) != 0) return 3;
+  UndistorterImpl ref(cin, cout_);
+  GImage want;
+  if (!ref.undistort(img, want)) return 4;
+  const int wo = cout_.width(), ho = cout_.height();
+  std::vector<uchar> inside((size_t)wo * ho);
+  int32_t bad = 0;
+  for (int i = 0; i < wo * ho; ++i) {
+    inside[i] = ch == 1 ? !(ref.remapX[i] < 0) : (ref.remapX[i] > 0);
+    if (inside[i] && std::memcmp(mine.data + (size_t)i * ch, want.data + (size_t)i * ch, ch) != 0) ++bad;
+  }
+  std::ofstream o(out, std::ios::binary);
+  int32_t oh[4] = {wo, ho, ch, bad};
+  wr(o, oh, 4);
+  wr(o, mine.data, (size_t)wo * ho * ch); wr(o, want.data, (size_t)wo * ho * ch); wr(o, inside.data(), inside.size());
   return 0;
 }
 
@@ -239,6 +284,7 @@ int main(int argc, char** argv) {
   if (mode == "orb") return runORB(argv[2], argv[3], argv[4]);
   if (mode == "findpnp") return runFindPnP(argv[2], argv[3], argv[4]);
   if (mode == "dataset") return runDataset(argv[2], argv[3], argv[4]);
+  if (mode == "undistort") return runUndistort(argv[2], argv[3], argv[4]);
   if (mode == "features") return runFeaturesApp(argv[2], argv[3], argv[4]);
   return 64;
 }

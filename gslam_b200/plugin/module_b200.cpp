@@ -7,9 +7,13 @@
 //                                                                                    "distance2": vector<int>}
 //   svar["gslam"]["b200"]["extract_to_frame"] (FramePtr, Svar cfg) -> bool : getImage() -> orb_extract -> setKeyPoints()
 //                                                                     (Map.h:287,311-312)
+//   svar["gslam"]["b200"]["match_stereo"]  (kps_left, desc_left, kps_right, desc_right, Svar cfg) -> {"rightIdx", "distance", "distance2"}
+//   svar["gslam"]["b200"]["undistort"]     (GImage, Camera in, Camera out) -> GImage : GSLAM::Undistorter::undistort (Undistorter.h:271-348)
+//   svar["gslam"]["apps"]["b200_features"] the Messenger application: "dataset/frame" -> extract -> "b200_features/curframe"
 // Outputs are the reference's own carrier types: GSLAM::KeyPoint (Map.h:122-195) and an owning GImage (GImage.h:160-443).
 // Functions do not throw; on failure they return an undefined Svar / false and log through GSLAM's LOG.
 #include <GSLAM/core/GSLAM.h>
+#include <GSLAM/core/Undistorter.h>
 
 #include <cstring>
 #include <mutex>
@@ -201,6 +205,40 @@ REGISTER_SVAR_MODULE(b200) {
     out["distance"] = d1;
     out["distance2"] = d2;
     return out;
+  });
+  // undistort(image, camera_in, camera_out) -> image: GSLAM::Undistorter::undistort (GSLAM/core/Undistorter.h:271-348) with the table
+  // of the reference's own prepareReMap (:120-203; every camera model stays the reference's) applied on the device.  The table of the
+  // last camera pair is kept resident in HBM.
+  svar["gslam"]["b200"]["undistort"] = GSLAM::Svar::lambda([](GSLAM::GImage img, GSLAM::Camera in, GSLAM::Camera out) -> GSLAM::GImage {
+    static std::mutex mtx;
+    static std::string cached_key;
+    static gb_remap* cached_map = nullptr;  // lives as long as the process-wide context it was created on
+    if (img.empty() || (img.channels() != 1 && img.channels() != 3) || img.elemSize1() != 1 || !in.isValid() || !out.isValid() ||
+        img.cols != in.width() || img.rows != in.height()) {
+      LOG(ERROR) << "gslam_b200 undistort: needs an 8-bit 1- or 3-channel image of camera_in's size and two valid cameras";
+      return GSLAM::GImage();
+    }
+    gb_ctx* ctx = shared().get();
+    if (!ctx) return GSLAM::GImage();
+    std::lock_guard<std::mutex> lk(mtx);
+    const std::string key = in.info() + "|" + out.info();
+    if (cached_key != key || !cached_map) {
+      if (cached_map) gb_remap_destroy(ctx, cached_map);
+      cached_map = nullptr;
+      GSLAM::UndistorterImpl table(in, out);
+      if (!table.valid || gb_remap_create(ctx, in.width(), in.height(), out.width(), out.height(), table.remapIdx, table.remapCoef, table.remapX,
+                                          &cached_map) != GB_OK) {
+        LOG(ERROR) << "gslam_b200 undistort: " << gb_last_error(ctx);
+        return GSLAM::GImage();
+      }
+      cached_key = key;
+    }
+    GSLAM::GImage result(out.height(), out.width(), img.type());
+    if (gb_remap_apply(ctx, cached_map, img.data, img.channels(), result.data) != GB_OK) {
+      LOG(ERROR) << "gslam_b200 undistort: " << gb_last_error(ctx);
+      return GSLAM::GImage();
+    }
+    return result;
   });
   svar["gslam"]["b200"]["extract_to_frame"] = GSLAM::Svar::lambda([](GSLAM::FramePtr fr, GSLAM::Svar cfg) -> bool {
     if (!fr) return false;

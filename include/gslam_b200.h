@@ -162,6 +162,19 @@ GB_API int gb_match_stereo(gb_ctx* ctx, const gb_keypoint* kps_left, const uint8
 GB_API int gb_match_stereo_features(gb_ctx* ctx, gb_features* left, gb_features* right, float band_rows, float min_disparity,
                                     float max_disparity);
 
+/* ---- frame undistortion -----------------------------------------------------------------------------------
+ * The bilinear LUT remap of GSLAM::Undistorter::undistort (GSLAM/core/Undistorter.h:271-348).  The table is the reference's own
+ * (UndistorterImpl::prepareReMap :120-203 -- remapIdx, remapCoef, remapX; the plugin builds it with the reference's camera models):
+ * per output pixel four source pixel indices (row-major, in pixels, >= 0) and four float weights; remap_x < 0 marks output pixels
+ * that fall outside the input image.  gb_remap_apply: src = w_in*h_in*channels bytes, dst = w_out*h_out*channels bytes, host
+ * buffers, channels 1 or 3; out = p[i0]*c0 + p[i1]*c1 + p[i2]*c2 + p[i3]*c3 in float, left to right, truncated to uchar --
+ * bit-identical to the reference wherever the reference is defined (taps beyond the input image count as 0; outside pixels are 0). */
+typedef struct gb_remap gb_remap;
+GB_API int gb_remap_create(gb_ctx* ctx, int w_in, int h_in, int w_out, int h_out, const int32_t* idx4, const float* coef4,
+                           const float* remap_x, gb_remap** out);
+GB_API int gb_remap_destroy(gb_ctx* ctx, gb_remap* map);
+GB_API int gb_remap_apply(gb_ctx* ctx, gb_remap* map, const uint8_t* src, int channels, uint8_t* dst);
+
 /* ---- bundle adjustment ---------------------------------------------------------------------------------------------- */
 /*
  * SoA mirror of GSLAM::BundleGraph's mappoint part (Optimizer.h:150-172).  The C++ plugin repacks the graph's AoS

@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
         L.orc_hamming256.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_match_hamming.restype = None
         L.orc_match_hamming.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_remap_apply.restype = None
+        L.orc_remap_apply.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_match_stereo.restype = None
         L.orc_match_stereo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p]
@@ -127,6 +129,8 @@ def ref() -> C.CDLL:
             getattr(R, name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         R.ref_sim3_raw.restype = None
         R.ref_sim3_raw.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
+        R.ref_undistort.restype = C.c_int
+        R.ref_undistort.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         R.ref_sizeof.restype = C.c_int
         R.ref_sizeof.argtypes = [C.c_char_p]
         R.ref_keypoint_offsets.restype = C.c_int
@@ -146,6 +150,35 @@ def match_stereo(kps_left, desc_left, kps_right, desc_right, band=2.0, min_disp=
     idx = np.empty(nl, np.int32); d1 = np.empty(nl, np.int32); d2 = np.empty(nl, np.int32)
     lib().orc_match_stereo(_p(kl), _p(dl), nl, _p(kr), _p(dr), nr, band, min_disp, max_disp, _p(idx), _p(d1), _p(d2))
     return idx, d1, d2
+
+
+def remap_apply(img: np.ndarray, idx4, coef4, remap_x, out_shape) -> np.ndarray:
+    """The bilinear LUT remap (orc_remap_apply): img (H,W) or (H,W,3) uint8 -> out_shape (+channels)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    ch = 1 if img.ndim == 2 else img.shape[2]
+    n_in = img.shape[0] * img.shape[1]; n_out = out_shape[0] * out_shape[1]
+    idx4 = np.ascontiguousarray(idx4, np.int32); coef4 = np.ascontiguousarray(coef4, np.float32); rx = np.ascontiguousarray(remap_x, np.float32)
+    out = np.zeros(tuple(out_shape) + ((ch,) if img.ndim == 3 else ()), np.uint8)
+    lib().orc_remap_apply(n_in, n_out, ch, _p(idx4), _p(coef4), _p(rx), _p(img), _p(out))
+    return out
+
+
+def ref_undistort(cam_in, cam_out, img=None):
+    """The UNMODIFIED reference (oracle/_ref): remap tables of UndistorterImpl::prepareReMap and, with an image, Undistorter::undistort.
+    cam_*: GSLAM camera parameter vectors [w, h, fx, fy, cx, cy(, ...)].  -> (idx4, coef4, remap_x, out or None)"""
+    ci = np.ascontiguousarray(cam_in, np.float64); co = np.ascontiguousarray(cam_out, np.float64)
+    wo, ho = int(co[0]), int(co[1])
+    idx4 = np.zeros((ho * wo, 4), np.int32); coef4 = np.zeros((ho * wo, 4), np.float32); rx = np.zeros(ho * wo, np.float32)
+    out = None
+    ch = 1
+    if img is not None:
+        img = np.ascontiguousarray(img, np.uint8)
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        out = np.zeros((ho, wo) + ((ch,) if img.ndim == 3 else ()), np.uint8)
+    rc = ref().ref_undistort(_p(ci), ci.size, _p(co), co.size, _p(img), ch, _p(idx4), _p(coef4), _p(rx), _p(out))
+    if rc != 0:
+        raise RuntimeError(f"ref_undistort failed rc={rc}")
+    return idx4, coef4, rx, out
 
 
 def to_gray(img: np.ndarray, rgb: bool = False) -> np.ndarray:

@@ -4,11 +4,14 @@
 //   * Vocabulary::DistanceFactory::hamming32          GSLAM/core/Vocabulary.h:485-491
 //   * SE3 inverse / point transform / product / exp / log   GSLAM/core/SE3.h:100-131,205-287  (pose conventions of BA)
 //   * sizeof / layout of the carrier PODs             Map.h:122-195, Optimizer.h:106-172, SE3.h:337-339, SIM3.h:290-291
+//   * Undistorter::undistort + the remap table of prepareReMap   GSLAM/core/Undistorter.h:120-348 (the frame-undistortion row)
 // No reference source is copied into this repository; the .so is git-ignored and travels to the GPU box prebuilt.
 #include <cstring>
 #include <GSLAM/core/GSLAM.h>
 #include <GSLAM/core/Optimizer.h>
 #include <GSLAM/core/Vocabulary.h>
+#include <GSLAM/core/Undistorter.h>
+#include <sstream>
 
 using namespace GSLAM;
 
@@ -62,5 +65,31 @@ __attribute__((visibility("default"))) int ref_keypoint_offsets(int* o7) {
   o7[0] = (char*)&k.pt.x - b; o7[1] = (char*)&k.pt.y - b; o7[2] = (char*)&k.size - b; o7[3] = (char*)&k.angle - b;
   o7[4] = (char*)&k.response - b; o7[5] = (char*)&k.octave - b; o7[6] = (char*)&k.class_id - b;
   return 7;
+}
+
+// The reference's undistorter, run as is: cameras from parameter vectors (Camera.h:435-444), tables from prepareReMap, output from
+// undistort().  tables: idx4 / coef4 / remap_x may be NULL; out may be NULL.  Returns 0 when both cameras are valid.
+__attribute__((visibility("default"))) int ref_undistort(const double* cam_in, int n_in, const double* cam_out, int n_out, const unsigned char* img,
+                                                         int channels, int* idx4, float* coef4, float* remap_x, unsigned char* out) {
+  Camera in(std::vector<double>(cam_in, cam_in + n_in)), outc(std::vector<double>(cam_out, cam_out + n_out));
+  if (!in.isValid() || !outc.isValid()) return 1;
+  UndistorterImpl u(in, outc);  // (prepareReMap prints the two camera models on stdout)
+  if (!u.valid) return 2;
+  const size_t n = (size_t)outc.width() * outc.height();
+  if (idx4) std::memcpy(idx4, u.remapIdx, n * 16);
+  if (coef4) std::memcpy(coef4, u.remapCoef, n * 16);
+  if (remap_x) std::memcpy(remap_x, u.remapX, n * 4);
+  if (img && out) {
+    // the reference reads up to one row + one pixel past the end of the image for taps of the last row: let it read zeros from a
+    // padded buffer it does not own (GImage.h:169, copy = false) -- which is the value the product defines for those taps
+    const size_t bytes = (size_t)in.width() * in.height() * channels;
+    std::vector<unsigned char> padded(bytes + (size_t)(in.width() + 2) * channels, 0);
+    std::memcpy(padded.data(), img, bytes);
+    GImage src(in.height(), in.width(), channels == 1 ? GImageType<uchar, 1>::Type : GImageType<uchar, 3>::Type, padded.data(), false);
+    GImage dst;
+    if (!u.undistort(src, dst)) return 3;
+    std::memcpy(out, dst.data, n * channels);
+  }
+  return 0;
 }
 }

@@ -250,3 +250,32 @@ def test_features_app_over_messenger_matches_direct_calls(tmp_path):
             assert np.array_equal(idx, ctx.match_hamming(d0, prev)[0])
         prev = d0
     ctx.close()
+
+
+@needs_plugins
+@pytest.mark.gpu
+@pytest.mark.parametrize("ch", [1, 3])
+def test_undistort_function_equals_the_reference_undistorter_in_process(tmp_path, ch):
+    """gslam.b200.undistort(GImage, Camera, Camera) next to the UNMODIFIED GSLAM::Undistorter (a header: host_test runs both on the
+    same frame): every pixel the reference defines is bit-identical, at the benchmark's frame size, for the OpenCV camera model."""
+    w, h = 1920, 1080
+    cam_in = [w, h, 1400.0, 1402.0, 961.5, 539.25, -0.28, 0.07, 0.0002, 0.00002, 0.0]
+    cam_out = [w, h, 1250.0, 1250.0, 960.0, 540.0]
+    img = synth.synth_frame(w, h, seed=4)
+    if ch == 3:
+        img = np.stack([img, np.roll(img, 11, axis=1), 255 - img], axis=2)
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<8i", w, h, ch, len(cam_in), len(cam_out), 0, 0, 0))
+        f.write(np.array(cam_in, np.float64).tobytes()); f.write(np.array(cam_out, np.float64).tobytes())
+        f.write(np.ascontiguousarray(img).tobytes())
+    r = run("undistort", str(inp), str(out))
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    raw = open(out, "rb").read()
+    wo, ho, c, bad = struct.unpack("<4i", raw[:16])
+    n = wo * ho * c
+    mine = np.frombuffer(raw[16:16 + n], np.uint8).reshape(ho, wo, c)
+    want = np.frombuffer(raw[16 + n:16 + 2 * n], np.uint8).reshape(ho, wo, c)
+    inside = np.frombuffer(raw[16 + 2 * n:], np.uint8).reshape(ho, wo).astype(bool)
+    assert (wo, ho, c, bad) == (w, h, ch, 0)
+    assert inside.mean() > 0.9 and np.array_equal(mine[inside], want[inside]) and mine[inside].std() > 10
