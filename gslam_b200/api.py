@@ -356,6 +356,10 @@ class BAGraph:
         """CTAs per camera of the sweep's camera pass (test hook, 1..4; production graphs pick it from the longest camera)."""
         self.ctx._check(self.ctx._lib.gb_dbg_ba_set_cam_split(self.ctx._h, self._h, int(split)))
 
+    def set_sweep(self, mode: int):
+        """Sweep kernel (test hook): 0 by size, 1 the latency-tuned local-BA kernel, 2 the bandwidth-tuned large-graph kernel."""
+        self.ctx._check(self.ctx._lib.gb_dbg_ba_set_sweep(self.ctx._h, self._h, int(mode)))
+
     def pcg_sparse_blocks(self) -> int:
         return int(self.ctx._lib.gb_dbg_ba_pcg_sparse(self.ctx._h, self._h))
 

@@ -2008,6 +2008,10 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
                b_oc = al((size_t)no * 4), b_op = al((size_t)no * 4), b_uv = al((size_t)no * 16),
                b_info = d.has_info ? al((size_t)no * 24) : 0, b_po = al((size_t)(np + 1) * 4), b_co = al((size_t)(nc + 1) * 4),
                b_cp = al((size_t)no * 4), b_cpt = al((size_t)no * 4), b_cuv = al((size_t)no * 16);
+  std::vector<int> lm_goff;  // landmark groups of the large-graph sweep (ba_sweep.cu)
+  ba_sweep_plan_host(pt_off, np, lm_goff);
+  d.lm_ngroups = (int)lm_goff.size() - 1;
+  const size_t b_lg = al(lm_goff.size() * 4);
   d.s_nnzb = (int)s_col.size();
   std::vector<int> s_upper, s_tidx(s_col.size(), 0);
   for (int blk = 0; blk < (int)s_col.size(); ++blk) {
@@ -2027,7 +2031,7 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   const size_t b_sr = al((size_t)(nc + 1) * 4), b_sc = al((size_t)s_col.size() * 4 + 4);
   const bool compact_only = shard_world > 1;  // a shard only ever sees the compact reduced layout: no dense 6N x 6N buffer
   g->rbuf_doubles = d.s_nnzb > 0 ? (size_t)d.s_nnzb * 36 + 2 * (size_t)d.n6 + 8 : 0;
-  const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + b_sr + 4 * b_sc + b_cpt + b_cuv + b_ch + 256;
+  const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + b_sr + 4 * b_sc + b_cpt + b_cuv + b_ch + b_lg + 256;
   const size_t n6 = 6 * (size_t)nc;
   uint8_t* dblob = nullptr;
   double* cam_ticket_d = nullptr;
@@ -2047,7 +2051,7 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
     sl.take(&d.V, (size_t)np * 9); sl.take(&d.gp, (size_t)np * 3); sl.take(&d.Vinv, (size_t)np * 9);
     sl.take(&d.W, (size_t)no * 18); sl.take(&d.U, (size_t)nc * 36); sl.take(&d.gc, (size_t)nc * 6);
     sl.take(&d.cost_pt, (size_t)np); sl.take(&d.cost_pt_new, (size_t)np);
-    sl.take(&d.cam_part, (size_t)nc * std::max(d.cam_split, 4) * 27); sl.take(&cam_ticket_d, (size_t)nc / 2 + 1);
+    sl.take(&d.cam_part, (size_t)nc * std::max(d.cam_split, 4) * 27); sl.take(&cam_ticket_d, (size_t)nc / 2 + 2);
     sl.take(&d.Minv, (size_t)nc * 36);
     sl.take(&d.Sb, (size_t)d.s_nnzb * 36);
     sl.take(&d.x, n6); sl.take(&d.r, n6); sl.take(&d.z, n6); sl.take(&d.p, n6); sl.take(&d.q, n6); sl.take(&d.sv, n6);
@@ -2088,7 +2092,7 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   auto take = [&](size_t bytes) { size_t o = off; off += bytes; return o; };
   const size_t o_pose = take(b_pose), o_pts = take(b_pts), o_dof = take(b_dof), o_pf = take(b_pf), o_oc = take(b_oc),
                o_op = take(b_op), o_uv = take(b_uv), o_info = take(b_info), o_po = take(b_po), o_co = take(b_co), o_cp = take(b_cp),
-               o_sr = take(b_sr), o_sc = take(b_sc), o_sb = take(b_sc), o_su = take(b_sc), o_st = take(b_sc), o_cpt = take(b_cpt), o_cuv = take(b_cuv), o_ch = take(b_ch);
+               o_sr = take(b_sr), o_sc = take(b_sc), o_sb = take(b_sc), o_su = take(b_sc), o_st = take(b_sc), o_cpt = take(b_cpt), o_cuv = take(b_cuv), o_ch = take(b_ch), o_lg = take(b_lg);
   memcpy(h + o_pose, pb->cam_pose_wc, (size_t)nc * 56);
   if (np > 0) memcpy(h + o_pts, pb->points + 3 * (size_t)lo, (size_t)np * 24);
   for (int i = 0; i < nc; ++i) h[o_dof + i] = pb->cam_dof ? (pb->cam_dof[i] & 63) : 63;
@@ -2126,12 +2130,15 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   if (!s_tidx.empty()) memcpy(h + o_st, s_tidx.data(), s_tidx.size() * 4);
   if (!chol_plan3.empty()) memcpy(h + o_ch, chol_plan3.data(), chol_plan3.size() * 4);
   g->chol_plan = (const int*)(dblob + o_ch);
+  memcpy(h + o_lg, lm_goff.data(), lm_goff.size() * 4);
+  d.lm_goff = (const int*)(dblob + o_lg);
   g->sorted_to_orig.swap(order);
   g->cam_perm_h.swap(cam_perm);
   tr.stamp("blob fill");
   GB_CUDA(ctx, cudaMemcpyAsync(dblob, h, blob, cudaMemcpyHostToDevice, ctx->stream));
   d.cam_ticket = reinterpret_cast<unsigned int*>(cam_ticket_d);
-  GB_CUDA(ctx, cudaMemsetAsync(d.cam_ticket, 0, ((size_t)nc / 2 + 1) * 8, ctx->stream));
+  GB_CUDA(ctx, cudaMemsetAsync(d.cam_ticket, 0, ((size_t)nc / 2 + 2) * 8, ctx->stream));
+  d.sweep_ticket = reinterpret_cast<unsigned int*>(cam_ticket_d + (size_t)nc / 2 + 1);  // (two words after the per-camera tickets)
   double* d_pose_wc = (double*)(dblob + o_pose);
   g->pose_wc_in = d_pose_wc;
   g->pts_init = (double*)(dblob + o_pts);
@@ -2243,6 +2250,21 @@ static int ba_pcg_cluster(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   return GB_OK;
 }
 
+}  // extern "C"
+
+// The residual + Jacobian sweep outside the local-BA launch chain: graphs with enough observations to fill the machine take the
+// bandwidth-tuned persistent kernel (ba_sweep.cu), small ones the latency-tuned one above.  which: 3 whole, 1 cameras, 2 landmarks.
+constexpr int kSweepLargeObs = 65536;
+static int ba_launch_sweep(gb_ctx* ctx, gb_ba_graph* g, const BaDev& d, cudaStream_t s, int which) {
+  const bool large = g->sweep_mode == 2 || (g->sweep_mode == 0 && d.no >= kSweepLargeObs && !getenv("GB_BA_SWEEP_OLD"));
+  if (large) return ba_sweep_launch(ctx, g, d, s, which);
+  const int pt_blocks = (which & 2) ? gb_div_up(d.np * kLpp, kPtThreads) : 0, cam_blocks = (which & 1) ? d.nc * d.cam_split : 0;
+  if (pt_blocks + cam_blocks > 0) { ba_linearize_kernel<<<pt_blocks + cam_blocks, kPtThreads, 0, s>>>(d, cam_blocks); GB_LAUNCH_CHECK(ctx); }
+  return GB_OK;
+}
+
+extern "C" {
+
 int gb_ba_graph_sweep(gb_ctx* ctx, gb_ba_graph* g, double huber_delta) {
   if (!ctx || !g) return GB_ERR_INVALID;
   CtxLock lk(ctx);
@@ -2254,8 +2276,7 @@ int gb_ba_graph_sweep(gb_ctx* ctx, gb_ba_graph* g, double huber_delta) {
     g->sweep_only = true;
   }
   BaDev& d = g->d;
-  const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads), cam_blocks = d.nc * d.cam_split;
-  if (pt_blocks + cam_blocks > 0) { ba_linearize_kernel<<<pt_blocks + cam_blocks, kPtThreads, 0, ctx->stream>>>(d, cam_blocks); GB_LAUNCH_CHECK(ctx); }
+  GB_CHECK(ba_launch_sweep(ctx, g, d, ctx->stream, 3));
   return GB_OK;
 }
 
@@ -2265,10 +2286,7 @@ int gb_ba_graph_reduce_local(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   BaDev& d = g->d;
   if (!buf) buf = g->buf;
   cudaStream_t s = ctx->stream;
-  {
-    const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads), cam_blocks = d.nc * d.cam_split;
-    if (pt_blocks + cam_blocks > 0) { ba_linearize_kernel<<<pt_blocks + cam_blocks, kPtThreads, 0, s>>>(d, cam_blocks); GB_LAUNCH_CHECK(ctx); }
-  }
+  GB_CHECK(ba_launch_sweep(ctx, g, d, s, 3));
   // Schur complement.  With the covisibility block structure at hand (<= 1024 cameras) S is formed block by block without
   // atomics (deterministic); the local-BA solver consumes the block-CSR directly, every other consumer (one-cluster / generic
   // PCG, the multi-GPU all-reduce) gets it scattered into the dense layout of `buf`.
@@ -2306,8 +2324,7 @@ int ba_reduce_local_compact(gb_ctx* ctx, gb_ba_graph* g, double* rbuf) {
   d.Sb = rbuf;
   d.r_gt = (size_t)d.s_nnzb * 36;
   cudaStream_t s = ctx->stream;
-  const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads), cam_blocks = d.nc * d.cam_split;
-  if (pt_blocks + cam_blocks > 0) { ba_linearize_kernel<<<pt_blocks + cam_blocks, kPtThreads, 0, s>>>(d, cam_blocks); GB_LAUNCH_CHECK(ctx); }
+  GB_CHECK(ba_launch_sweep(ctx, g, d, s, 3));
   {
     const int nblk = (int)std::min<size_t>(std::max<size_t>(((size_t)d.np + 255) / 256, 1), (size_t)ctx->sm_count * 8);
     ba_prepare_schur_kernel<<<nblk, 256, 0, s>>>(d, rbuf, 0); GB_LAUNCH_CHECK(ctx);
@@ -2765,11 +2782,16 @@ GB_API int gb_dbg_ba_sweep_part(gb_ctx* ctx, gb_ba_graph* g, int which) {
   if (!ctx || !g || !g->begun) return GB_ERR_INVALID;
   CtxLock lk(ctx);
   BaDev& d = g->d;
-  const int pt_blocks = gb_div_up(d.np * kLpp, kPtThreads), cam_blocks = d.nc * d.cam_split;
-  if (which == 1 && cam_blocks > 0) ba_linearize_kernel<<<cam_blocks, kPtThreads, 0, ctx->stream>>>(d, cam_blocks);
-  if (which == 2 && pt_blocks > 0) ba_linearize_kernel<<<pt_blocks, kPtThreads, 0, ctx->stream>>>(d, 0);
-  if (which == 3) ba_linearize_kernel<<<pt_blocks + cam_blocks, kPtThreads, 0, ctx->stream>>>(d, cam_blocks);
-  GB_LAUNCH_CHECK(ctx);
+  if (which < 1 || which > 3) return GB_ERR_INVALID;
+  return ba_launch_sweep(ctx, g, d, ctx->stream, which);
+}
+
+// 0 = pick by size, 1 = the latency-tuned kernel of this file, 2 = the bandwidth-tuned kernel of ba_sweep.cu (tests cover both on
+// the same graphs)
+GB_API int gb_dbg_ba_set_sweep(gb_ctx* ctx, gb_ba_graph* g, int mode) {
+  if (!ctx || !g || mode < 0 || mode > 2) return GB_ERR_INVALID;
+  CtxLock lk(ctx);
+  g->sweep_mode = mode;
   return GB_OK;
 }
 

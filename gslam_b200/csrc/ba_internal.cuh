@@ -25,6 +25,7 @@ struct gb_ba_graph {
   bool pcg_sparse = false;
   size_t pcg_sparse_smem = 0;
   int pcg_max_row_blocks = 0;  // longest block row of S
+  int sweep_mode = 0;           // 0 = by size (ba_sweep.cu from 64k observations), 1 = ba.cu's latency-tuned kernel, 2 = ba_sweep.cu
   bool sweep_only = false;     // the last begin came from gb_ba_graph_sweep and nothing else ran since
   int pcg_nact = 0;            // cameras with at least one free dof (the sparse PCG kernel gives lanes to these only)
   int pcg_cluster = 0;
@@ -60,6 +61,11 @@ int ba_reduce_local_compact(gb_ctx* ctx, gb_ba_graph* g, double* rbuf);         
 int ba_backsub_cost_compact(gb_ctx* ctx, gb_ba_graph* g, double* d_cost);         // back-substitution + candidate cost of the shard
 int ba_commit_compact(gb_ctx* ctx, gb_ba_graph* g, const double* rbuf, const double* d_cost);  // LM accept / reject + install
 int ba_read_result(gb_ctx* ctx, gb_ba_graph* g, gb_ba_result* res);               // one sync; fills res from the device scalars
+
+// ---- ba_sweep.cu ------------------------------------------------------------------------------------------------------------
+// the bandwidth-tuned residual + Jacobian sweep of large graphs (persistent CTAs, pose table in shared memory, bulk-copied W tiles)
+void ba_sweep_plan_host(const std::vector<int>& pt_off, int np, std::vector<int>& goff);  // landmark groups of <= 256 observations
+int ba_sweep_launch(gb_ctx* ctx, gb_ba_graph* g, const BaDev& d, cudaStream_t s, int which /* 3 whole, 1 cameras, 2 landmarks */);
 
 // ---- ba_pcg_bcsr.cu ---------------------------------------------------------------------------------------------------------
 // Decide whether / how the multi-CTA block-CSR PCG applies to `g` (fills the bcsr_* fields, allocates its small device buffers).

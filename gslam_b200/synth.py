@@ -164,7 +164,7 @@ def synth_ba(n_cams: int = 50, n_points: int = 2000, obs_per_point: int = 5, see
     R_wc = _quat_to_R(q_wc)
 
     first = rng.integers(0, n_cams - d + 1, n_points)
-    depth = rng.uniform(5.0 + spacing * d, 50.0, n_points)
+    depth = rng.uniform(5.0 + spacing * d, max(50.0, 25.0 + spacing * d), n_points)  # (50 m unless the track is longer)
     lat = rng.uniform(-0.35, 0.35, n_points) * depth
     ver = rng.uniform(-0.15, 0.15, n_points) * depth
     mid = first + d // 2

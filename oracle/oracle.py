@@ -66,7 +66,7 @@ def default_orb_cfg(**kw) -> OrbCfgC:
 
 def build(force: bool = False) -> None:
     """Compile liboracle.so (always possible) and _ref/libgslam_ref.so (only where /root/reference exists)."""
-    srcs = [os.path.join(_HERE, f) for f in ("hamming_ref.c", "ba_ref.c", "orb_ref.c", "pnp_ref.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("hamming_ref.c", "ba_ref.c", "orb_ref.c", "pnp_ref.c", "bow_ref.c", "Makefile")]
     lib = os.path.join(_HERE, "liboracle.so")
     if force or not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "liboracle.so", "CC=gcc"])
@@ -102,6 +102,9 @@ def lib() -> C.CDLL:
         L.orc_ba_pnp.restype = C.c_int
         L.orc_ba_pnp.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                  C.POINTER(BaOptionsC), C.POINTER(BaResultC)]
+        L.orc_bow_transform.restype = C.c_int
+        L.orc_bow_transform.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
         L.orc_se3_inverse.restype = None
         L.orc_se3_inverse.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_se3_retract.restype = None
@@ -131,6 +134,21 @@ def ref() -> C.CDLL:
         R.ref_sim3_raw.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         R.ref_undistort.restype = C.c_int
         R.ref_undistort.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        R.ref_voc_train.restype = C.c_void_p
+        R.ref_voc_train.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        R.ref_voc_from_arrays.restype = C.c_void_p
+        R.ref_voc_from_arrays.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+        R.ref_voc_destroy.restype = None
+        R.ref_voc_destroy.argtypes = [C.c_void_p]
+        R.ref_voc_info.restype = C.c_int
+        R.ref_voc_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        R.ref_voc_export.restype = None
+        R.ref_voc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        R.ref_voc_transform.restype = C.c_int
+        R.ref_voc_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double)]
+        R.ref_voc_transform_one.restype = None
+        R.ref_voc_transform_one.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         R.ref_sizeof.restype = C.c_int
         R.ref_sizeof.argtypes = [C.c_char_p]
         R.ref_keypoint_offsets.restype = C.c_int
@@ -445,3 +463,112 @@ def pnp_ransac(xyz, xy, threshold=0.01, confidence=0.99, max_hypotheses=1024, se
     if rc != 0:
         raise RuntimeError(f"orc_pnp_ransac failed rc={rc}")
     return pose, mask, st
+
+
+# ---- bag-of-words transform (bow_ref.c restates GSLAM/core/Vocabulary.h:1558-1736; RefVocabulary IS the reference, oracle/_ref) -------
+W_TF_IDF, W_TF, W_IDF, W_BINARY = 0, 1, 2, 3                                  # Vocabulary.h:88-94
+S_L1, S_L2, S_CHI_SQUARE, S_KL, S_BHATTACHARYYA, S_DOT_PRODUCT = 0, 1, 2, 3, 4, 5  # Vocabulary.h:97-105
+
+
+class VocabularyArrays:
+    """The vocabulary tree as the flat arrays the reference keeps (Vocabulary.h:583-601): children of node p are rows
+    p*k+1 .. p*k+child_num[p] of `desc`; the word id of a leaf is its node id."""
+
+    def __init__(self, k, L, weighting, scoring, child_num, weight, desc):
+        self.k, self.L, self.weighting, self.scoring = int(k), int(L), int(weighting), int(scoring)
+        self.child_num = np.ascontiguousarray(child_num, np.uint32)
+        self.weight = np.ascontiguousarray(weight, np.float32)
+        self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        assert self.child_num.shape[0] == self.weight.shape[0] == self.desc.shape[0]
+
+    @property
+    def n_nodes(self):
+        return int(self.child_num.shape[0])
+
+
+def synth_vocabulary(k=10, L=4, seed=1, weighting=W_TF_IDF, scoring=S_L1, prune=0.0, stop=0.0) -> VocabularyArrays:
+    """A complete k-ary tree of depth L with random 256-bit node descriptors and idf-like weights in (0.2, 9); `prune`: fraction of
+    the inner nodes below the root turned into leaves (unbalanced tree), `stop`: fraction of the words with weight 0 (stopped)."""
+    rng = np.random.default_rng(seed)
+    n = (k ** (L + 1) - 1) // (k - 1)
+    inner = (k ** L - 1) // (k - 1)
+    child = np.zeros(n, np.uint32)
+    child[:inner] = k
+    if prune > 0:
+        cut = rng.random(inner) < prune
+        cut[0] = False
+        # a pruned node keeps no children; its would-be descendants stay in the arrays but are unreachable
+        child[:inner][cut] = 0
+        short = rng.random(inner) < prune  # and some inner nodes have fewer than k children
+        child[:inner][short & ~cut] = rng.integers(1, k + 1, int((short & ~cut).sum()))
+    weight = rng.uniform(0.2, 9.0, n).astype(np.float32)
+    if stop > 0:
+        weight[rng.random(n) < stop] = 0.0
+    desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    # make near-ties common: siblings share most of their bits
+    base = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    parent = (np.arange(n) - 1) // k
+    parent[0] = 0
+    flip = (rng.random((n, 32)) < 0.12)
+    desc = np.where(flip, desc, base[parent]).astype(np.uint8)
+    return VocabularyArrays(k, L, weighting, scoring, child, weight, desc)
+
+
+def bow_transform(voc: VocabularyArrays, feats, levelsup=0):
+    """-> dict(words int64[nw], values float32[nw], fv_node int64[m], fv_feat int32[m], f_word int64[n], f_node int64[n])"""
+    f = np.ascontiguousarray(feats, np.uint8).reshape(-1, 32)
+    n = f.shape[0]
+    words = np.zeros(max(n, 1), np.int64); values = np.zeros(max(n, 1), np.float32)
+    fvn = np.zeros(max(n, 1), np.int64); fvf = np.zeros(max(n, 1), np.int32)
+    fw = np.zeros(max(n, 1), np.int64); fn = np.zeros(max(n, 1), np.int64)
+    m = C.c_int(0)
+    nw = lib().orc_bow_transform(voc.k, voc.L, voc.weighting, voc.scoring, _p(voc.child_num), _p(voc.weight), _p(voc.desc), _p(f), n, int(levelsup),
+                                 _p(words), _p(values), _p(fvn), _p(fvf), C.byref(m), _p(fw), _p(fn))
+    return dict(words=words[:nw], values=values[:nw], fv_node=fvn[:m.value], fv_feat=fvf[:m.value], f_word=fw[:n], f_node=fn[:n])
+
+
+class RefVocabulary:
+    """GSLAM::Vocabulary itself (oracle/_ref): trained by Vocabulary::create or loaded from arrays by Vocabulary::load."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise RuntimeError("reference vocabulary could not be created")
+        self._h = C.c_void_p(handle)
+
+    @classmethod
+    def train(cls, descriptors, n_images, k, L, weighting=W_TF_IDF, scoring=S_L1):
+        d = np.ascontiguousarray(descriptors, np.uint8).reshape(n_images, -1, 32)
+        return cls(ref().ref_voc_train(_p(d), n_images, d.shape[1], k, L, weighting, scoring))
+
+    @classmethod
+    def from_arrays(cls, v: VocabularyArrays):
+        return cls(ref().ref_voc_from_arrays(v.k, v.L, v.weighting, v.scoring, v.n_nodes, _p(v.child_num), _p(v.weight), _p(v.desc)))
+
+    def arrays(self) -> VocabularyArrays:
+        k, L, w, s = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        n = ref().ref_voc_info(self._h, C.byref(k), C.byref(L), C.byref(w), C.byref(s))
+        child = np.zeros(n, np.uint32); weight = np.zeros(n, np.float32); desc = np.zeros((n, 32), np.uint8)
+        ref().ref_voc_export(self._h, _p(child), _p(weight), _p(desc))
+        return VocabularyArrays(k.value, L.value, w.value, s.value, child, weight, desc)
+
+    def transform(self, feats, levelsup=0, repeat=1):
+        f = np.ascontiguousarray(feats, np.uint8).reshape(-1, 32)
+        n = f.shape[0]
+        words = np.zeros(max(n, 1), np.uint64); values = np.zeros(max(n, 1), np.float32)
+        fvn = np.zeros(max(n, 1), np.uint64); fvf = np.zeros(max(n, 1), np.uint32)
+        nw, m, sec = C.c_int(0), C.c_int(0), C.c_double(0)
+        ref().ref_voc_transform(self._h, _p(f), n, int(levelsup), _p(words), _p(values), C.byref(nw), _p(fvn), _p(fvf), C.byref(m), int(repeat),
+                                C.byref(sec))
+        return dict(words=words[:nw.value].astype(np.int64), values=values[:nw.value], fv_node=fvn[:m.value].astype(np.int64),
+                    fv_feat=fvf[:m.value].astype(np.int32), seconds=sec.value)
+
+    def transform_one(self, feat, levelsup=0):
+        f = np.ascontiguousarray(feat, np.uint8).reshape(32)
+        w, n, val = C.c_ulonglong(0), C.c_ulonglong(0), C.c_float(0)
+        ref().ref_voc_transform_one(self._h, _p(f), int(levelsup), C.byref(w), C.byref(val), C.byref(n))
+        return int(w.value), float(val.value), int(n.value)
+
+    def close(self):
+        if self._h:
+            ref().ref_voc_destroy(self._h)
+            self._h = None

@@ -5,6 +5,7 @@
 //   * SE3 inverse / point transform / product / exp / log   GSLAM/core/SE3.h:100-131,205-287  (pose conventions of BA)
 //   * sizeof / layout of the carrier PODs             Map.h:122-195, Optimizer.h:106-172, SE3.h:337-339, SIM3.h:290-291
 //   * Undistorter::undistort + the remap table of prepareReMap   GSLAM/core/Undistorter.h:120-348 (the frame-undistortion row)
+//   * Vocabulary::create / load / transform (BoW + feature vector)  GSLAM/core/Vocabulary.h:1051-1130,1890-1930,1558-1736 (the BoW row)
 // No reference source is copied into this repository; the .so is git-ignored and travels to the GPU box prebuilt.
 #include <cstring>
 #include <GSLAM/core/GSLAM.h>
@@ -91,5 +92,76 @@ __attribute__((visibility("default"))) int ref_undistort(const double* cam_in, i
     std::memcpy(out, dst.data, n * channels);
   }
   return 0;
+}
+
+// ---- the reference's vocabulary, run as is (BoW row) ---------------------------------------------------------------------------
+// ref_voc_train: Vocabulary::create (hierarchical k-medians + idf weights) on n_images x per_image 32-byte descriptors.
+// ref_voc_from_arrays: any tree, through the reference's own binary loader (Vocabulary::load(std::istream&), :1890-1930).
+__attribute__((visibility("default"))) void* ref_voc_train(const unsigned char* desc, int n_images, int per_image, int k, int L, int weighting, int scoring) {
+  std::vector<TinyMat> imgs;
+  for (int i = 0; i < n_images; ++i) {
+    TinyMat m(per_image, 32, GImageType<uchar, 1>::Type, nullptr, false, 32);
+    std::memcpy(m.data, desc + (size_t)i * per_image * 32, (size_t)per_image * 32);
+    imgs.push_back(m);
+  }
+  std::shared_ptr<Vocabulary> v = Vocabulary::create(imgs, k, L, (Vocabulary::WeightingType)weighting, (Vocabulary::ScoringType)scoring);
+  return v ? new std::shared_ptr<Vocabulary>(v) : nullptr;
+}
+__attribute__((visibility("default"))) void* ref_voc_from_arrays(int k, int L, int weighting, int scoring, unsigned nnodes, const unsigned* child_num,
+                                                                const float* weight, const unsigned char* desc32) {
+  std::stringstream ss;
+  const uint64_t sig = 88877711233ull;
+  const bool compressed = false;
+  ss.write((const char*)&sig, sizeof sig); ss.write((const char*)&compressed, sizeof compressed); ss.write((const char*)&nnodes, sizeof nnodes);
+  Vocabulary::ScoringType sc = (Vocabulary::ScoringType)scoring; Vocabulary::WeightingType we = (Vocabulary::WeightingType)weighting;
+  ss.write((const char*)&k, sizeof k); ss.write((const char*)&L, sizeof L); ss.write((const char*)&sc, sizeof sc); ss.write((const char*)&we, sizeof we);
+  const int cols = 32, rows = 1, type = GImageType<uchar, 1>::Type;
+  ss.write((const char*)&cols, sizeof cols); ss.write((const char*)&rows, sizeof rows); ss.write((const char*)&type, sizeof type);
+  std::vector<Vocabulary::Node> nodes(nnodes);
+  for (unsigned i = 0; i < nnodes; ++i) { nodes[i].childNum = child_num[i]; nodes[i].weight = weight[i]; }
+  ss.write((const char*)nodes.data(), sizeof(Vocabulary::Node) * nnodes);
+  ss.write((const char*)desc32, (size_t)nnodes * 32);
+  std::shared_ptr<Vocabulary> v(new Vocabulary());
+  if (!v->load(ss)) return nullptr;
+  return new std::shared_ptr<Vocabulary>(v);
+}
+__attribute__((visibility("default"))) void ref_voc_destroy(void* h) { delete (std::shared_ptr<Vocabulary>*)h; }
+__attribute__((visibility("default"))) int ref_voc_info(void* h, int* k, int* L, int* weighting, int* scoring) {
+  Vocabulary& v = **(std::shared_ptr<Vocabulary>*)h;
+  *k = v.m_k; *L = v.m_L; *weighting = (int)v.m_weighting; *scoring = (int)v.m_scoring;
+  return (int)v.m_nodes.size();
+}
+__attribute__((visibility("default"))) void ref_voc_export(void* h, unsigned* child_num, float* weight, unsigned char* desc32) {
+  Vocabulary& v = **(std::shared_ptr<Vocabulary>*)h;
+  for (size_t i = 0; i < v.m_nodes.size(); ++i) { child_num[i] = v.m_nodes[i].childNum; weight[i] = v.m_nodes[i].weight; }
+  std::memcpy(desc32, v.m_nodeDescriptors.data, v.m_nodes.size() * 32);
+}
+// Vocabulary::transform(features, BowVector&, FeatureVector&, levelsup) (:1558-1622).  words/values: the BowVector in map order;
+// fv_node/fv_feat: the FeatureVector flattened in map order (node ascending, feature indices in insertion order).
+__attribute__((visibility("default"))) int ref_voc_transform(void* h, const unsigned char* feats, int n, int levelsup, unsigned long long* words, float* values,
+                                                             int* n_words, unsigned long long* fv_node, unsigned* fv_feat, int* n_fv, int repeat,
+                                                             double* seconds) {
+  Vocabulary& v = **(std::shared_ptr<Vocabulary>*)h;
+  TinyMat f(n, 32, GImageType<uchar, 1>::Type, nullptr, false, 32);
+  std::memcpy(f.data, feats, (size_t)n * 32);
+  BowVector bv; FeatureVector fv;
+  auto t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < (repeat > 0 ? repeat : 1); ++r) v.transform(f, bv, fv, levelsup);
+  if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / (repeat > 0 ? repeat : 1);
+  int a = 0, b = 0;
+  for (auto& it : bv) { if (words) { words[a] = it.first; values[a] = it.second; } ++a; }
+  for (auto& it : fv) for (unsigned idx : it.second) { if (fv_node) { fv_node[b] = it.first; fv_feat[b] = idx; } ++b; }
+  *n_words = a; *n_fv = b;
+  return 0;
+}
+// one descriptor down the tree (:1692-1736): word id, weight, node id `levelsup` levels above the leaf
+__attribute__((visibility("default"))) void ref_voc_transform_one(void* h, const unsigned char* feat, int levelsup, unsigned long long* word, float* weight,
+                                                                 unsigned long long* node) {
+  Vocabulary& v = **(std::shared_ptr<Vocabulary>*)h;
+  TinyMat f(1, 32, GImageType<uchar, 1>::Type, nullptr, false, 32);
+  std::memcpy(f.data, feat, 32);
+  WordId w; WordValue val; NodeId nid = (NodeId)-1;
+  v.transform(f, w, val, &nid, levelsup);
+  *word = w; *weight = val; *node = nid;
 }
 }

@@ -55,6 +55,74 @@ def test_linearisation_matches_oracle(ctx, name):
     g.close()
 
 
+SWEEP2_PROBLEMS = dict(PROBLEMS)
+SWEEP2_PROBLEMS.update({
+    # a landmark with more observations than one 256-lane chunk (swept in two chunks), groups cut at 64 landmarks
+    "300cam_all_visible": dict(n_cams=300, n_points=40, all_visible=True, n_fixed=2, seed=5),
+    "ragged_3obs": dict(n_cams=40, n_points=3000, obs_per_point=3, n_fixed=2, seed=13),
+    "more_than_512_cams": dict(n_cams=600, n_points=2400, obs_per_point=6, n_fixed=2, seed=17),  # pose table stays in global memory
+})
+
+
+@pytest.mark.parametrize("name", list(SWEEP2_PROBLEMS))
+def test_large_graph_sweep_kernel_matches_oracle(ctx, name):
+    """csrc/ba_sweep.cu (persistent CTAs, pose table in shared memory, one lane per observation, W tiles leaving through the bulk-copy
+    engine) forced onto small graphs: U, g_c, V, g_p, W against the oracle, bit-identical run to run, and -- per-landmark sums run in
+    observation order on both sides -- V / g_p / W no further from the oracle than rounding."""
+    pb = synth.synth_ba(**SWEEP2_PROBLEMS[name])
+    want = oracle.ba_linearize(pb, 0.01)
+    g = BAGraph(ctx, pb)
+    g.set_sweep(2)
+    got = g.dbg_linearize(0.01)
+    again = g.dbg_linearize(0.01)
+    for k in ("U", "gc", "V", "gp", "W"):
+        assert rel(got[k], want[k]) < 1e-11, k
+        assert np.array_equal(got[k], again[k]), k
+    assert abs(got["cost"] - want["cost"]) / want["cost"] < 1e-12
+    g.set_sweep(1)
+    old = g.dbg_linearize(0.01)
+    for k in ("U", "gc", "V", "gp", "W"):
+        assert rel(got[k], old[k]) < 1e-12, k
+    g.close()
+
+
+@pytest.mark.parametrize("split", [2, 4])
+def test_large_graph_sweep_kernel_sliced_cameras(ctx, split):
+    pb = synth.synth_ba(**PROBLEMS["config1_10cam_200pt"])
+    want = oracle.ba_linearize(pb, 0.01)
+    g = BAGraph(ctx, pb)
+    g.set_sweep(2)
+    g.set_cam_split(split)
+    got = g.dbg_linearize(0.01)
+    again = g.dbg_linearize(0.01)
+    for k in ("U", "gc"):
+        assert rel(got[k], want[k]) < 1e-11
+        assert np.array_equal(got[k], again[k])
+    g.close()
+
+
+def test_large_graph_sweep_kernel_in_a_solve(ctx):
+    """The pending-candidate installation, the rejected-step path and the info-matrix / partial-dof inputs through ba_sweep.cu."""
+    a = synth.synth_ba(n_cams=12, n_points=150, obs_per_point=4, n_fixed=2, seed=1, pose_sigma_t=1.0, pose_sigma_deg=10, point_sigma=2.0)
+    rng = np.random.default_rng(3)
+    a.obs_info = np.ascontiguousarray(np.tile(np.eye(2).reshape(1, 4), (a.n_obs, 1)) * rng.uniform(0.5, 2.0, (a.n_obs, 1)))
+    a.cam_dof[5] = 7
+    a.cam_dof[9] = 56
+    a.point_free[::7] = 0
+    b = a.copy()
+    r0 = oracle.ba_solve(a, max_iterations=12, function_tolerance=0.0, pcg_max_iters=400, pcg_tol=1e-13)
+    assert 0 < r0.accepted < r0.iterations
+    g = BAGraph(ctx, b)
+    g.force_generic_pcg(1)
+    g.set_sweep(2)
+    r1 = g.solve(cfg(maxIterations=12, functionTolerance=0.0, pcgMaxIterations=400, pcgTolerance=1e-13))
+    b.cam_pose_wc[...], b.points[...] = g.download()
+    g.close()
+    assert r1.iterations == r0.iterations and r1.accepted == r0.accepted
+    assert abs(r1.final_cost - r0.final_cost) / r0.final_cost < RTOL
+    pose_close(b.cam_pose_wc, a.cam_pose_wc, RTOL)
+
+
 PCG_MODES = {"sparse_pcg": 0, "cluster_pcg": 2, "generic_pcg": 1}
 
 
