@@ -218,6 +218,44 @@ class Remap:
         self._h = None
 
 
+class Vocabulary:
+    """A GSLAM::Vocabulary tree resident in HBM (gb_vocabulary); method names follow the reference (Vocabulary.h:168-193)."""
+
+    def __init__(self, ctx: Context, k, L, weighting, scoring, child_num, weight, desc):
+        self.ctx = ctx
+        child = np.ascontiguousarray(child_num, np.uint32); w = np.ascontiguousarray(weight, np.float32)
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        h = C.c_void_p()
+        ctx._check(ctx._lib.gb_voc_create(ctx._h, int(k), int(L), int(weighting), int(scoring), child.shape[0], ptr(child), ptr(w), ptr(d), C.byref(h)))
+        self._h = h
+
+    def transform(self, features, levelsup: int = 0):
+        """features: (N,32) uint8 host array, or a `Features` object resident in HBM.
+        -> dict(words int64[nw], values float32[nw], fv_node int64[m], fv_feat int32[m]) in std::map order."""
+        c = self.ctx
+        if isinstance(features, Features):
+            n = features.capacity
+        else:
+            features = np.ascontiguousarray(features, np.uint8).reshape(-1, 32)
+            n = features.shape[0]
+        words = np.zeros(max(n, 1), np.uint64); values = np.zeros(max(n, 1), np.float32)
+        fvn = np.zeros(max(n, 1), np.uint64); fvf = np.zeros(max(n, 1), np.uint32)
+        nw, m = C.c_int(0), C.c_int(0)
+        if isinstance(features, Features):
+            c._check(c._lib.gb_bow_transform_features(c._h, self._h, features._h, int(levelsup), ptr(words), ptr(values), C.byref(nw), ptr(fvn), ptr(fvf),
+                                                      C.byref(m)))
+        else:
+            c._check(c._lib.gb_bow_transform(c._h, self._h, ptr(features), n, int(levelsup), ptr(words), ptr(values), C.byref(nw), ptr(fvn), ptr(fvf),
+                                             C.byref(m)))
+        return dict(words=words[:nw.value].astype(np.int64), values=values[:nw.value], fv_node=fvn[:m.value].astype(np.int64),
+                    fv_feat=fvf[:m.value].astype(np.int32))
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self.ctx._lib.gb_voc_destroy(self.ctx._h, self._h)
+        self._h = None
+
+
 class Features:
     """A frame's keypoints + descriptors resident in HBM (gb_features)."""
 

@@ -87,6 +87,10 @@ _SIGNATURES = [
     ("gb_remap_create", C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, C.POINTER(_VP)]),
     ("gb_remap_destroy", C.c_int, [_VP, _VP]),
     ("gb_remap_apply", C.c_int, [_VP, _VP, _VP, C.c_int, _VP]),
+    ("gb_voc_create", C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, _VP, _VP, _VP, C.POINTER(_VP)]),
+    ("gb_voc_destroy", C.c_int, [_VP, _VP]),
+    ("gb_bow_transform", C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP, C.POINTER(C.c_int), _VP, _VP, C.POINTER(C.c_int)]),
+    ("gb_bow_transform_features", C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, C.POINTER(C.c_int), _VP, _VP, C.POINTER(C.c_int)]),
     ("gb_ba_options_default", None, [C.POINTER(BaOptions)]),
     ("gb_ba_solve", C.c_int, [_VP, C.POINTER(BaProblem), C.POINTER(BaOptions), C.POINTER(BaResult)]),
     ("gb_ba_pnp", C.c_int, [_VP, C.c_int, _VP, _VP, _VP, C.c_int, _VP, C.POINTER(BaOptions), C.POINTER(BaResult)]),

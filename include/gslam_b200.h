@@ -175,6 +175,27 @@ GB_API int gb_remap_create(gb_ctx* ctx, int w_in, int h_in, int w_out, int h_out
 GB_API int gb_remap_destroy(gb_ctx* ctx, gb_remap* map);
 GB_API int gb_remap_apply(gb_ctx* ctx, gb_remap* map, const uint8_t* src, int channels, uint8_t* dst);
 
+/* ---- bag-of-words transform --------------------------------------------------------------------------------
+ * GSLAM::Vocabulary::transform(features, BowVector&, FeatureVector&, levelsup)  (GSLAM/core/Vocabulary.h:1558-1622; tree walk
+ * :1692-1736; distance hamming32 :485-491).  gb_voc_create uploads the reference's own flat tree (the public members
+ * Vocabulary::m_k, m_L, m_weighting, m_scoring, m_nodes[].childNum / .weight, m_nodeDescriptors, :583-601): children of node p are rows
+ * p*k+1 .. p*k+child_num[p] of desc32 (32-byte rows: ORB / 256-bit vocabularies), k <= 32; weighting / scoring are the reference's
+ * enum values (:88-105).  gb_bow_transform: desc = n x 32 bytes (the N x 32 8UC1 descriptor GImage of MapFrame::getDescriptor,
+ * Map.h:321), host memory.  Outputs, caller-owned, capacity n each: the BowVector (std::map<WordId,float>, :47) as parallel arrays
+ * in map order (words ascending) and the FeatureVector (std::map<NodeId,std::vector<unsigned>>, :48) flattened in map order (node
+ * ascending, feature indices ascending).  Word / node / feature indices are bit-exact with the reference; values are the reference's
+ * floats (accumulated and normalised with the same operations).  A leaf above level L - levelsup files under itself (the reference
+ * reads an uninitialised node id there).  gb_bow_transform_features: the same for descriptors already resident in HBM (the output
+ * of gb_orb_extract_features), no host round trip before the walk. */
+typedef struct gb_vocabulary gb_vocabulary;
+GB_API int gb_voc_create(gb_ctx* ctx, int k, int L, int weighting, int scoring, uint32_t n_nodes, const uint32_t* child_num, const float* weight,
+                         const uint8_t* desc32, gb_vocabulary** out);
+GB_API int gb_voc_destroy(gb_ctx* ctx, gb_vocabulary* voc);
+GB_API int gb_bow_transform(gb_ctx* ctx, gb_vocabulary* voc, const uint8_t* desc, int n, int levelsup, uint64_t* words, float* values, int* n_words,
+                            uint64_t* fv_node, uint32_t* fv_feat, int* n_fv);
+GB_API int gb_bow_transform_features(gb_ctx* ctx, gb_vocabulary* voc, gb_features* f, int levelsup, uint64_t* words, float* values, int* n_words,
+                                     uint64_t* fv_node, uint32_t* fv_feat, int* n_fv);
+
 /* ---- bundle adjustment ---------------------------------------------------------------------------------------------- */
 /*
  * SoA mirror of GSLAM::BundleGraph's mappoint part (Optimizer.h:150-172).  The C++ plugin repacks the graph's AoS
