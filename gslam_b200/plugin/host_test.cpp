@@ -10,12 +10,15 @@
 //   gslam_b200_host_test dataset <plugin-dir> x.synth out.bin  GSLAM::Dataset::open -> libgslamDB_synth.so -> grabFrame (Dataset.h:124-162)
 //   gslam_b200_host_test features <plugin-dir> x.synth out.bin dataset/frame -> gslam.apps.b200_features -> b200/curframe (Messenger)
 //   gslam_b200_host_test undistort <plugin-dir> in.bin out.bin  gslam.b200.undistort next to the reference's own GSLAM::Undistorter
+//   gslam_b200_host_test bow <plugin-dir> in.bin out.bin        gslam.b200.vocabulary(Vocabulary::create(...))->transform next to the
+//                                                               reference's own Vocabulary::transform (Vocabulary.h:1558-1622)
 // Trailing "key=value" arguments become svar settings the plugins read (b200.devices=0,1 shards a global BA over two GPUs).
 #include <GSLAM/core/GSLAM.h>
 #include <GSLAM/core/Dataset.h>
 #include <GSLAM/core/Estimator.h>
 #include <GSLAM/core/Optimizer.h>
 #include <GSLAM/core/Undistorter.h>
+#include <GSLAM/core/Vocabulary.h>
 
 #include <chrono>
 #include <cstdio>
@@ -160,6 +163,58 @@ static int runUndistort(const std::string& dir, const char* in, const char* out)
   return 0;
 }
 
+// in : int32 n_images, per_image, k, L, n_query, levelsup, weighting, scoring; training descriptors (n_images*per_image*32 bytes); queries
+// out: int32 equal_bow, equal_fv, equal_bow_only_overload, n_words, n_fv_nodes, microseconds reference, microseconds plugin, pad;
+//      words (uint64 x n_words), values (float x n_words)
+// The vocabulary is TRAINED by the reference (Vocabulary::create), handed to the plugin as the VocabularyPtr any GSLAM code holds, and
+// both objects transform the same descriptors in this process; the std::maps must compare equal, key for key and float for float.
+static int runBow(const std::string& dir, const char* in, const char* out) {
+  svar.Set<std::string>("GSLAM_LIBRARY_PATH", dir);
+  Svar mod = Registry::load("b200");
+  if (mod.isUndefined()) { fprintf(stderr, "Registry::load(\"b200\") failed\n"); return 2; }
+  std::ifstream f(in, std::ios::binary);
+  int32_t hdr[8];
+  rd(f, hdr, 8);
+  const int n_images = hdr[0], per = hdr[1], k = hdr[2], L = hdr[3], nq = hdr[4], levelsup = hdr[5];
+  std::vector<TinyMat> imgs;
+  for (int i = 0; i < n_images; ++i) {
+    TinyMat m(per, 32, GImageType<uchar, 1>::Type, nullptr, false, 32);
+    rd(f, m.data, (size_t)per * 32);
+    imgs.push_back(m);
+  }
+  TinyMat q(nq, 32, GImageType<uchar, 1>::Type, nullptr, false, 32);
+  rd(f, q.data, (size_t)nq * 32);
+  std::shared_ptr<Vocabulary> ref = Vocabulary::create(imgs, k, L, (Vocabulary::WeightingType)hdr[6], (Vocabulary::ScoringType)hdr[7]);
+  if (!ref) return 3;
+  Svar made = mod["gslam"]["b200"]["vocabulary"](ref);
+  if (!made.is<std::shared_ptr<Vocabulary> >()) return 4;
+  std::shared_ptr<Vocabulary> dev = made.castAs<std::shared_ptr<Vocabulary> >();
+  if (!dev || dev->size() != ref->size()) return 5;
+  BowVector v0, v1, v2, v3;
+  FeatureVector f0, f1;
+  dev->transform(q, v1, f1, levelsup);  // (first call uploads the tree)
+  auto t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < 20; ++r) ref->transform(q, v0, f0, levelsup);
+  auto t1 = std::chrono::steady_clock::now();
+  for (int r = 0; r < 20; ++r) dev->transform(q, v1, f1, levelsup);
+  auto t2 = std::chrono::steady_clock::now();
+  ref->transform(q, v2);
+  dev->transform(q, v3);
+  // the untouched parts of the interface still answer from the same tree
+  WordId w0, w1; WordValue a0, a1;
+  ref->transform(q.row(0), w0, a0);
+  dev->transform(q.row(0), w1, a1);
+  if (w0 != w1 || a0 != a1 || dev->getWordWeight(w1) != ref->getWordWeight(w0) || dev->getEffectiveLevels() != ref->getEffectiveLevels()) return 6;
+  if (v1.empty()) return 7;
+  std::ofstream o(out, std::ios::binary);
+  int32_t oh[8] = {v0 == v1, f0 == f1, v2 == v3, (int32_t)v1.size(), (int32_t)f1.size(),
+                   (int32_t)(std::chrono::duration<double>(t1 - t0).count() / 20 * 1e6), (int32_t)(std::chrono::duration<double>(t2 - t1).count() / 20 * 1e6), 0};
+  wr(o, oh, 8);
+  for (auto& it : v1) { uint64_t w = it.first; wr(o, &w, 1); }
+  for (auto& it : v1) { float x = it.second; wr(o, &x, 1); }
+  return 0;
+}
+
 // in : int32 n, 3 x int32 pad, double threshold, double confidence, n x 3 doubles (world points), n x 2 doubles (normalised image points)
 // out: int32 ok, 7 doubles world2camera {qx,qy,qz,qw,tx,ty,tz}, n bytes mask
 static int runFindPnP(const std::string& dir, const char* in, const char* out) {
@@ -264,7 +319,7 @@ static int runFeaturesApp(const std::string& dir, const char* in, const char* ou
 }
 
 int main(int argc, char** argv) {
-  if (argc < 5) { fprintf(stderr, "usage: %s ba|pnp|orb|findpnp <plugin-dir> in.bin out.bin\n", argv[0]); return 64; }
+  if (argc < 5) { fprintf(stderr, "usage: %s ba|pnp|orb|findpnp|dataset|undistort|features|bow <plugin-dir> in.bin out.bin\n", argv[0]); return 64; }
   // optional svar settings for the plugins, "key=value" (e.g. b200.devices=0,1  b200.multi_min_obs=1000)
   for (int i = 5; i < argc; ++i) {
     const std::string kv = argv[i];
@@ -286,5 +341,6 @@ int main(int argc, char** argv) {
   if (mode == "dataset") return runDataset(argv[2], argv[3], argv[4]);
   if (mode == "undistort") return runUndistort(argv[2], argv[3], argv[4]);
   if (mode == "features") return runFeaturesApp(argv[2], argv[3], argv[4]);
+  if (mode == "bow") return runBow(argv[2], argv[3], argv[4]);
   return 64;
 }

@@ -9,11 +9,15 @@
 //                                                                     (Map.h:287,311-312)
 //   svar["gslam"]["b200"]["match_stereo"]  (kps_left, desc_left, kps_right, desc_right, Svar cfg) -> {"rightIdx", "distance", "distance2"}
 //   svar["gslam"]["b200"]["undistort"]     (GImage, Camera in, Camera out) -> GImage : GSLAM::Undistorter::undistort (Undistorter.h:271-348)
+//   svar["gslam"]["b200"]["vocabulary"]    (std::shared_ptr<Vocabulary>) -> std::shared_ptr<Vocabulary> : the same vocabulary with the
+//                                          batch transforms (Vocabulary.h:174,192: virtual) answered by the device; any code holding
+//                                          a GSLAM::Vocabulary* / VocabularyPtr keeps working unchanged
 //   svar["gslam"]["apps"]["b200_features"] the Messenger application: "dataset/frame" -> extract -> "b200_features/curframe"
 // Outputs are the reference's own carrier types: GSLAM::KeyPoint (Map.h:122-195) and an owning GImage (GImage.h:160-443).
 // Functions do not throw; on failure they return an undefined Svar / false and log through GSLAM's LOG.
 #include <GSLAM/core/GSLAM.h>
 #include <GSLAM/core/Undistorter.h>
+#include <GSLAM/core/Vocabulary.h>
 
 #include <cstring>
 #include <mutex>
@@ -90,6 +94,73 @@ bool extract(const GSLAM::GImage& img, GSLAM::Svar cfg, std::vector<GSLAM::KeyPo
   }
   return false;
 }
+
+// ---- the vocabulary -----------------------------------------------------------------------------------------
+// A GSLAM::Vocabulary whose batch transforms (virtual, Vocabulary.h:174-175,192-193) run on the device.  Everything else -- load /
+// save, single-descriptor transform, score, getWord ... -- is the base class, working on the same tree.  The tree is uploaded once,
+// on the first transform (gb_voc_create); the BowVector / FeatureVector are std::maps as the reference defines them (:47-48), filled in
+// ascending key order with an end() hint (amortised O(1) per entry).
+class B200Vocabulary : public GSLAM::Vocabulary {
+ public:
+  explicit B200Vocabulary(const GSLAM::Vocabulary& src) : GSLAM::Vocabulary(src) {}
+  ~B200Vocabulary() {
+    if (dev_ && ctx_) gb_voc_destroy(ctx_, dev_);
+  }
+  virtual void transform(const GSLAM::TinyMat& features, GSLAM::BowVector& v) const {
+    GSLAM::FeatureVector fv;
+    if (!run(features, v, fv, 0, false)) GSLAM::Vocabulary::transform(features, v);
+  }
+  virtual void transform(const GSLAM::TinyMat& features, GSLAM::BowVector& v, GSLAM::FeatureVector& fv, int levelsup = 0) const {
+    if (!run(features, v, fv, levelsup, true)) GSLAM::Vocabulary::transform(features, v, fv, levelsup);
+  }
+
+ private:
+  // false: this input is not the device path's (not 32-byte 8-bit rows, k > 32): the caller forwards to the base class -- the same
+  // answer from the reference's own code, NOT a fallback for a missing device (a missing device is an error: empty vectors + LOG)
+  bool run(const GSLAM::TinyMat& features, GSLAM::BowVector& v, GSLAM::FeatureVector& fv, int levelsup, bool want_fv) const {
+    if (m_nodeDescriptors.cols != 32 || m_nodeDescriptors.elemSize() != 1 || m_k > 32) return false;
+    v.clear(); fv.clear();
+    if (empty() || features.rows <= 0) return true;
+    if (features.cols != 32 || features.elemSize() != 1) { LOG(ERROR) << "gslam_b200 vocabulary: features must be N x 32 8UC1"; return true; }
+    std::lock_guard<std::mutex> lk(mu_);
+    if (!dev_) {
+      ctx_ = shared().get();
+      if (!ctx_) return true;  // logged by shared(): no CPU fallback
+      std::vector<uint32_t> child(m_nodes.size());
+      std::vector<float> weight(m_nodes.size());
+      for (size_t i = 0; i < m_nodes.size(); ++i) { child[i] = m_nodes[i].childNum; weight[i] = m_nodes[i].weight; }
+      if (gb_voc_create(ctx_, m_k, m_L, (int)m_weighting, (int)m_scoring, (uint32_t)m_nodes.size(), child.data(), weight.data(), m_nodeDescriptors.data,
+                        &dev_) != GB_OK) {
+        LOG(ERROR) << "gslam_b200 vocabulary: " << gb_last_error(ctx_);
+        dev_ = nullptr;
+        return true;
+      }
+    }
+    const int n = features.rows;
+    words_.resize(n); values_.resize(n); fv_node_.resize(n); fv_feat_.resize(n);
+    int nw = 0, m = 0;
+    if (gb_bow_transform(ctx_, dev_, features.data, n, levelsup, words_.data(), values_.data(), &nw, fv_node_.data(), fv_feat_.data(), &m) != GB_OK) {
+      LOG(ERROR) << "gslam_b200 vocabulary: " << gb_last_error(ctx_);
+      return true;
+    }
+    for (int i = 0; i < nw; ++i) v.insert(v.end(), GSLAM::BowVector::value_type((GSLAM::WordId)words_[i], values_[i]));
+    if (want_fv)
+      for (int i = 0; i < m;) {
+        int j = i;
+        while (j < m && fv_node_[j] == fv_node_[i]) ++j;
+        GSLAM::FeatureVector::iterator it = fv.insert(fv.end(), GSLAM::FeatureVector::value_type((GSLAM::NodeId)fv_node_[i], std::vector<unsigned int>()));
+        it->second.assign(fv_feat_.begin() + i, fv_feat_.begin() + j);
+        i = j;
+      }
+    return true;
+  }
+  mutable std::mutex mu_;
+  mutable gb_ctx* ctx_ = nullptr;
+  mutable gb_vocabulary* dev_ = nullptr;
+  mutable std::vector<uint64_t> words_, fv_node_;
+  mutable std::vector<float> values_;
+  mutable std::vector<uint32_t> fv_feat_;
+};
 
 // ---- the Messenger-level application ---------------------------------------------------------------------
 // `gslam play b200_features [metric_time -slam b200] -dataset x.synth`: subscribes "dataset/frame" (published by the reference's
@@ -239,6 +310,10 @@ REGISTER_SVAR_MODULE(b200) {
       return GSLAM::GImage();
     }
     return result;
+  });
+  svar["gslam"]["b200"]["vocabulary"] = GSLAM::Svar::lambda([](std::shared_ptr<GSLAM::Vocabulary> src) -> std::shared_ptr<GSLAM::Vocabulary> {
+    if (!src) return std::shared_ptr<GSLAM::Vocabulary>();
+    return std::shared_ptr<GSLAM::Vocabulary>(new B200Vocabulary(*src));
   });
   svar["gslam"]["b200"]["extract_to_frame"] = GSLAM::Svar::lambda([](GSLAM::FramePtr fr, GSLAM::Svar cfg) -> bool {
     if (!fr) return false;

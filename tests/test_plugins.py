@@ -279,3 +279,30 @@ def test_undistort_function_equals_the_reference_undistorter_in_process(tmp_path
     inside = np.frombuffer(raw[16 + 2 * n:], np.uint8).reshape(ho, wo).astype(bool)
     assert (wo, ho, c, bad) == (w, h, ch, 0)
     assert inside.mean() > 0.9 and np.array_equal(mine[inside], want[inside]) and mine[inside].std() > 10
+
+
+@needs_plugins
+@pytest.mark.gpu
+@pytest.mark.parametrize("weighting,scoring,levelsup", [(0, 0, 0), (0, 0, 2), (1, 1, 1), (2, 5, 0)])
+def test_vocabulary_from_the_module_equals_the_reference_vocabulary_in_process(tmp_path, weighting, scoring, levelsup):
+    """gslam.b200.vocabulary(VocabularyPtr) returns a GSLAM::Vocabulary whose virtual batch transforms run on the device: the
+    reference TRAINS the tree (Vocabulary::create), both objects transform the same 2000 descriptors in one process, and the
+    BowVector / FeatureVector std::maps must be equal key for key and float for float (host_test compares them with ==)."""
+    rng = np.random.default_rng(11)
+    centres = rng.integers(0, 256, (400, 32), dtype=np.uint8)
+    n_images, per, k, L, nq = 50, 200, 10, 3, 2000
+    train = centres[rng.integers(0, 400, (n_images, per))] ^ np.packbits(rng.random((n_images, per, 256)) < 0.06, axis=2)
+    q = centres[rng.integers(0, 400, nq)] ^ np.packbits(rng.random((nq, 256)) < 0.08, axis=1)
+    inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as f:
+        f.write(struct.pack("<8i", n_images, per, k, L, nq, levelsup, weighting, scoring))
+        f.write(np.ascontiguousarray(train).tobytes()); f.write(np.ascontiguousarray(q).tobytes())
+    r = run("bow", str(inp), str(out))
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    raw = open(out, "rb").read()
+    eq_bow, eq_fv, eq_bow_only, nw, nfv, us_ref, us_dev, _ = struct.unpack("<8i", raw[:32])
+    assert (eq_bow, eq_fv, eq_bow_only) == (1, 1, 1)
+    assert 50 < nw <= nq and 0 < nfv <= nw
+    words = np.frombuffer(raw[32:32 + 8 * nw], np.uint64); values = np.frombuffer(raw[32 + 8 * nw:32 + 12 * nw], np.float32)
+    assert np.all(np.diff(words.astype(np.int64)) > 0) and np.all(values > 0)
+    print(f"bow transform of {nq} descriptors: reference {us_ref} us, plugin {us_dev} us")
