@@ -130,6 +130,7 @@ _DEBUG_SIGNATURES = [
     ("gb_dbg_ba_set_cam_split", C.c_int, [_VP, _VP, C.c_int]),
     ("gb_dbg_ba_sweep_part", C.c_int, [_VP, _VP, C.c_int]),
     ("gb_dbg_ba_set_sweep", C.c_int, [_VP, _VP, C.c_int]),
+    ("gb_dbg_ba_sweep_plan", C.c_int, [C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int, _VP, C.c_int, _VP, C.POINTER(C.c_int)]),
     ("gb_dbg_pnp_p3p_host", C.c_int, [_VP, _VP, _VP]),
     ("gb_dbg_pnp_minimal_host", C.c_int, [C.c_int, _VP, _VP, C.c_double, C.c_double, C.c_int, C.c_uint64, _VP, C.POINTER(PnpStats)]),
     ("gb_dbg_ba_shard_bounds", C.c_int, [C.c_int, C.c_int, _VP, C.c_int, _VP]),

@@ -1735,11 +1735,12 @@ void gb_ba_options_default(gb_ba_options* o) {
 
 int gb_ba_graph_destroy(gb_ctx* ctx, gb_ba_graph* g) {
   if (!g) return GB_OK;
-  if (g->bcsr_cta_cam || g->sp_alloc) {
+  if (g->bcsr_cta_cam || g->sp_alloc || g->sw_alloc) {
     if (ctx) { CtxLock lk(ctx); cudaStreamSynchronize(ctx->stream); }
     if (g->bcsr_cta_cam) ba_pcg_bcsr_free(g);
     if (g->sp_alloc) cudaFree(g->sp_alloc);
     g->sp_alloc = nullptr;
+    ba_sweep_plan_drop(g);
   }
   if (g->from_arena) {
     if (ctx) ctx->ba_arena_busy = false;
@@ -2008,10 +2009,6 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
                b_oc = al((size_t)no * 4), b_op = al((size_t)no * 4), b_uv = al((size_t)no * 16),
                b_info = d.has_info ? al((size_t)no * 24) : 0, b_po = al((size_t)(np + 1) * 4), b_co = al((size_t)(nc + 1) * 4),
                b_cp = al((size_t)no * 4), b_cpt = al((size_t)no * 4), b_cuv = al((size_t)no * 16);
-  std::vector<int> lm_goff;  // landmark groups of the large-graph sweep (ba_sweep.cu)
-  ba_sweep_plan_host(pt_off, np, lm_goff);
-  d.lm_ngroups = (int)lm_goff.size() - 1;
-  const size_t b_lg = al(lm_goff.size() * 4);
   d.s_nnzb = (int)s_col.size();
   std::vector<int> s_upper, s_tidx(s_col.size(), 0);
   for (int blk = 0; blk < (int)s_col.size(); ++blk) {
@@ -2031,7 +2028,7 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   const size_t b_sr = al((size_t)(nc + 1) * 4), b_sc = al((size_t)s_col.size() * 4 + 4);
   const bool compact_only = shard_world > 1;  // a shard only ever sees the compact reduced layout: no dense 6N x 6N buffer
   g->rbuf_doubles = d.s_nnzb > 0 ? (size_t)d.s_nnzb * 36 + 2 * (size_t)d.n6 + 8 : 0;
-  const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + b_sr + 4 * b_sc + b_cpt + b_cuv + b_ch + b_lg + 256;
+  const size_t blob = b_pose + b_pts + b_dof + b_pf + b_oc + b_op + b_uv + b_info + b_po + b_co + b_cp + b_sr + 4 * b_sc + b_cpt + b_cuv + b_ch + 256;
   const size_t n6 = 6 * (size_t)nc;
   uint8_t* dblob = nullptr;
   double* cam_ticket_d = nullptr;
@@ -2051,7 +2048,7 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
     sl.take(&d.V, (size_t)np * 9); sl.take(&d.gp, (size_t)np * 3); sl.take(&d.Vinv, (size_t)np * 9);
     sl.take(&d.W, (size_t)no * 18); sl.take(&d.U, (size_t)nc * 36); sl.take(&d.gc, (size_t)nc * 6);
     sl.take(&d.cost_pt, (size_t)np); sl.take(&d.cost_pt_new, (size_t)np);
-    sl.take(&d.cam_part, (size_t)nc * std::max(d.cam_split, 4) * 27); sl.take(&cam_ticket_d, (size_t)nc / 2 + 2);
+    sl.take(&d.cam_part, (size_t)nc * std::max(d.cam_split, 4) * 27); sl.take(&cam_ticket_d, (size_t)nc / 2 + 1);
     sl.take(&d.Minv, (size_t)nc * 36);
     sl.take(&d.Sb, (size_t)d.s_nnzb * 36);
     sl.take(&d.x, n6); sl.take(&d.r, n6); sl.take(&d.z, n6); sl.take(&d.p, n6); sl.take(&d.q, n6); sl.take(&d.sv, n6);
@@ -2092,7 +2089,7 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   auto take = [&](size_t bytes) { size_t o = off; off += bytes; return o; };
   const size_t o_pose = take(b_pose), o_pts = take(b_pts), o_dof = take(b_dof), o_pf = take(b_pf), o_oc = take(b_oc),
                o_op = take(b_op), o_uv = take(b_uv), o_info = take(b_info), o_po = take(b_po), o_co = take(b_co), o_cp = take(b_cp),
-               o_sr = take(b_sr), o_sc = take(b_sc), o_sb = take(b_sc), o_su = take(b_sc), o_st = take(b_sc), o_cpt = take(b_cpt), o_cuv = take(b_cuv), o_ch = take(b_ch), o_lg = take(b_lg);
+               o_sr = take(b_sr), o_sc = take(b_sc), o_sb = take(b_sc), o_su = take(b_sc), o_st = take(b_sc), o_cpt = take(b_cpt), o_cuv = take(b_cuv), o_ch = take(b_ch);
   memcpy(h + o_pose, pb->cam_pose_wc, (size_t)nc * 56);
   if (np > 0) memcpy(h + o_pts, pb->points + 3 * (size_t)lo, (size_t)np * 24);
   for (int i = 0; i < nc; ++i) h[o_dof + i] = pb->cam_dof ? (pb->cam_dof[i] & 63) : 63;
@@ -2130,15 +2127,13 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   if (!s_tidx.empty()) memcpy(h + o_st, s_tidx.data(), s_tidx.size() * 4);
   if (!chol_plan3.empty()) memcpy(h + o_ch, chol_plan3.data(), chol_plan3.size() * 4);
   g->chol_plan = (const int*)(dblob + o_ch);
-  memcpy(h + o_lg, lm_goff.data(), lm_goff.size() * 4);
-  d.lm_goff = (const int*)(dblob + o_lg);
   g->sorted_to_orig.swap(order);
   g->cam_perm_h.swap(cam_perm);
+  g->pt_off_h = pt_off; g->cam_off_h = cam_off;  // (the large-graph sweep cuts its work items from these on first use)
   tr.stamp("blob fill");
   GB_CUDA(ctx, cudaMemcpyAsync(dblob, h, blob, cudaMemcpyHostToDevice, ctx->stream));
   d.cam_ticket = reinterpret_cast<unsigned int*>(cam_ticket_d);
-  GB_CUDA(ctx, cudaMemsetAsync(d.cam_ticket, 0, ((size_t)nc / 2 + 2) * 8, ctx->stream));
-  d.sweep_ticket = reinterpret_cast<unsigned int*>(cam_ticket_d + (size_t)nc / 2 + 1);  // (two words after the per-camera tickets)
+  GB_CUDA(ctx, cudaMemsetAsync(d.cam_ticket, 0, ((size_t)nc / 2 + 1) * 8, ctx->stream));
   double* d_pose_wc = (double*)(dblob + o_pose);
   g->pose_wc_in = d_pose_wc;
   g->pts_init = (double*)(dblob + o_pts);
@@ -2774,6 +2769,7 @@ GB_API int gb_dbg_ba_set_cam_split(gb_ctx* ctx, gb_ba_graph* g, int split) {
   if (!ctx || !g || split < 1 || split > 4) return GB_ERR_INVALID;
   CtxLock lk(ctx);
   g->d.cam_split = split;
+  ba_sweep_plan_drop(g);  // (the large-graph sweep's items are cut per slice)
   return GB_OK;
 }
 

@@ -54,10 +54,11 @@ struct BaDev {
   double *sp_stageS, *sp_stageG; // [nchunks][136][36], [nchunks][16][6] per-chunk partial sums
   const int *sp_boff, *sp_bidx;  // CSR over the UPPER blocks (order of s_upper): staging slots (chunk*136+slot) contributing, ascending
   const int *sp_coff, *sp_cidx;  // CSR over cameras: staging rows (chunk*16+local cam) contributing to g~
-  // large-graph sweep (ba_sweep.cu): landmark groups [lm_goff[g], lm_goff[g+1]) of <= 256 observations; work ticket + exit count
-  int lm_ngroups;
-  const int* lm_goff;
-  unsigned int* sweep_ticket;
+  // large-graph sweep (ba_sweep.cu): host-made item records (int4 each) dealt to sw_nteams teams, team k owns
+  // [sw_team_off[k], sw_team_off[k+1])
+  int sw_nteams, sw_nitems;
+  const int* sw_items;
+  const int* sw_team_off;
   // linearisation
   double *V, *gp, *Vinv, *W, *U, *gc, *cost_pt, *cost_pt_new;
   // camera pass split: cam_split CTAs per camera, partial [27] sums + a per-camera ticket (the last CTA folds them in order)

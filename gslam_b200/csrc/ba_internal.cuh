@@ -48,6 +48,8 @@ struct gb_ba_graph {
   int chol_blocks = 0;
   size_t chol_smem = 0;
   void* sp_alloc = nullptr;      // device allocation holding the landmark-chunk Schur plan + staging (BaDev::sp_*), or null
+  void* sw_alloc = nullptr;      // device allocation holding the large-graph sweep's item plan (BaDev::sw_*), made on first use
+  std::vector<int> pt_off_h, cam_off_h;  // host copies of pt_off / cam_off (the sweep plan is cut from them)
   // landmark shard (multi-GPU global BA): this graph holds landmarks [shard_lo, shard_hi) of the caller's problem
   int shard_lo = 0, shard_hi = 0, shard_rank = 0, shard_world = 1;
 };
@@ -64,7 +66,9 @@ int ba_read_result(gb_ctx* ctx, gb_ba_graph* g, gb_ba_result* res);             
 
 // ---- ba_sweep.cu ------------------------------------------------------------------------------------------------------------
 // the bandwidth-tuned residual + Jacobian sweep of large graphs (persistent CTAs, pose table in shared memory, bulk-copied W tiles)
-void ba_sweep_plan_host(const std::vector<int>& pt_off, int np, std::vector<int>& goff);  // landmark groups of <= 256 observations
+void ba_sweep_plan_host(int nc, int np, int cam_split, const std::vector<int>& cam_off, const std::vector<int>& pt_off, int n_teams,
+                        std::vector<int>& items4, std::vector<int>& team_off);  // host-only: item records + per-team ranges
+void ba_sweep_plan_drop(gb_ba_graph* g);  // (cam_split changed / graph destroyed)
 int ba_sweep_launch(gb_ctx* ctx, gb_ba_graph* g, const BaDev& d, cudaStream_t s, int which /* 3 whole, 1 cameras, 2 landmarks */);
 
 // ---- ba_pcg_bcsr.cu ---------------------------------------------------------------------------------------------------------

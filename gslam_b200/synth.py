@@ -198,3 +198,69 @@ def synth_ba(n_cams: int = 50, n_points: int = 2000, obs_per_point: int = 5, see
                      obs_cam=np.ascontiguousarray(obs_cam[perm]), obs_point=np.ascontiguousarray(obs_point[perm]),
                      obs_xyz=np.ascontiguousarray(obs_xyz[perm]), obs_info=None,
                      gt_pose_wc=np.concatenate([q_wc, t_wc], axis=1), gt_points=pts)
+
+
+# ---- pose-graph terms (GSLAM::SE3Edge / GPSEdge, Optimizer.h:127-148) -------------------------------------------------------------
+@dataclasses.dataclass
+class PoseEdges:
+    """Python-side mirror of gb_pose_edges (include/gslam_b200.h)."""
+    se3_first: np.ndarray            # (n_se3,) i32
+    se3_second: np.ndarray           # (n_se3,) i32
+    se3_meas: np.ndarray             # (n_se3, 7) f64  SE3_12 = SE3_1^-1 SE3_2
+    se3_info: np.ndarray | None      # (n_se3, 36) f64 or None
+    gps_frame: np.ndarray            # (n_gps,) i32
+    gps_meas: np.ndarray             # (n_gps, 7) f64  prior on T_wc
+    gps_info: np.ndarray | None      # (n_gps, 36) f64 or None
+
+    @property
+    def n_se3(self): return int(self.se3_first.shape[0])
+    @property
+    def n_gps(self): return int(self.gps_frame.shape[0])
+
+
+def _quat_rot(q: np.ndarray, v: np.ndarray) -> np.ndarray:
+    return np.einsum("...ij,...j->...i", _quat_to_R(q), v)
+
+
+def se3_mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """(…,7) x (…,7): rotation product, translation a.R b.t + a.t (SE3.h:129-131)."""
+    return np.concatenate([_quat_mul(a[..., :4], b[..., :4]), _quat_rot(a[..., :4], b[..., 4:]) + a[..., 4:]], axis=-1)
+
+
+def se3_inv(a: np.ndarray) -> np.ndarray:
+    qi = a[..., :4] * np.array([-1.0, -1.0, -1.0, 1.0])
+    return np.concatenate([qi, -_quat_rot(qi, a[..., 4:])], axis=-1)
+
+
+def _small_se3(rng, n, sigma_t, sigma_r):
+    w = sigma_r * rng.standard_normal((n, 3))
+    q = np.concatenate([0.5 * w, np.ones((n, 1))], axis=1)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    return np.concatenate([q, sigma_t * rng.standard_normal((n, 3))], axis=1)
+
+
+def synth_pose_edges(pb: BAProblem, seed: int = 0, odometry: bool = True, n_loops: int = 0, gps_every: int = 0, sigma_t: float = 0.02,
+                     sigma_r: float = 0.002, with_info: bool = False) -> PoseEdges:
+    """Pose-graph terms for the trajectory of `pb`, measured on its ground truth with small noise: odometry edges between consecutive
+    keyframes, `n_loops` random loop closures, a GPS prior on every `gps_every`-th keyframe; optional random SPD 6x6 information."""
+    rng = np.random.default_rng(seed)
+    T = pb.gt_pose_wc
+    n = T.shape[0]
+    first, second = [], []
+    if odometry:
+        first += list(range(n - 1)); second += list(range(1, n))
+    for _ in range(n_loops):
+        a, b = rng.choice(n, 2, replace=False)
+        first.append(int(a)); second.append(int(b))
+    first = np.array(first, np.int32); second = np.array(second, np.int32)
+    meas = se3_mul(se3_mul(se3_inv(T[first]), T[second]), _small_se3(rng, first.shape[0], sigma_t, sigma_r)) if first.shape[0] else np.zeros((0, 7))
+    gps = np.arange(0, n, gps_every, dtype=np.int32) if gps_every > 0 else np.zeros(0, np.int32)
+    gmeas = se3_mul(T[gps], _small_se3(rng, gps.shape[0], 5 * sigma_t, 5 * sigma_r)) if gps.shape[0] else np.zeros((0, 7))
+
+    def spd(m):
+        A = rng.standard_normal((m, 6, 6))
+        M = np.einsum("nij,nkj->nik", A, A) + 6.0 * np.eye(6)
+        M[:, :3, :3] *= 4.0
+        return np.ascontiguousarray(M.reshape(m, 36))
+    return PoseEdges(first, second, np.ascontiguousarray(meas), spd(first.shape[0]) if with_info else None, gps, np.ascontiguousarray(gmeas),
+                     spd(gps.shape[0]) if with_info else None)

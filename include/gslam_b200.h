@@ -225,6 +225,25 @@ typedef struct gb_ba_problem {
   const double* obs_info;
 } gb_ba_problem;
 
+/* Pose-graph terms of a BundleGraph: GSLAM::SE3Edge (Optimizer.h:127-133, BundleGraph::se3Graph :163-164) and
+ * GSLAM::GPSEdge (:143-148, gpsGraph :167-168).  All indices are keyframe indices of the gb_ba_problem they accompany.
+ *   se3_meas : n_se3 x 7 doubles, SE3_12 := SE3_1^-1 * SE3_2 (T_wc conventions, SE3 layout {qx,qy,qz,qw,tx,ty,tz});
+ *   gps_meas : n_gps x 7 doubles, SE3_gps := SE3_frame (a prior on T_wc of the frame);
+ *   *_info   : row-major 6x6 information matrices in the tangent order [v(3), w(3)] (SE3.h:205-262), one per edge, or NULL = identity.
+ * Residual e = Log(Z^-1 * T_wc,1^-1 * T_wc,2) resp. Log(Z^-1 * T_wc), cost term e' Omega e (no robust kernel), Jacobians with the
+ * first-order approximation of the logarithm's Jacobian (our definition -- the reference fixes only the types). */
+typedef struct gb_pose_edges {
+  int32_t n_se3;
+  const int32_t* se3_first;
+  const int32_t* se3_second;
+  const double* se3_meas;
+  const double* se3_info;
+  int32_t n_gps;
+  const int32_t* gps_frame;
+  const double* gps_meas;
+  const double* gps_info;
+} gb_pose_edges;
+
 /* GSLAM::OptimzeConfig (Optimizer.h:174-182) + the solver knobs the reference leaves to its (absent) Ceres plugin. */
 typedef struct gb_ba_options {
   int32_t projection;       /* 0 = PROJECTION_PINHOLE (only 0 supported)                               */

@@ -17,6 +17,8 @@
  *   q = R_cw p + t_cw (T_cw = T_wc^-1);  r = (q.x/q.z - u, q.y/q.z - v);  e^2 = r' L r;  Huber IRLS weight
  *   w = e<=d ? 1 : d/e;  rho = e<=d ? e^2 : 2 d e - d^2;  cost = 0.5 sum rho;  observations with q.z <= 0 are skipped.
  *   Left update T_cw <- Exp([v,w]) T_cw:  J_cam = Jpi [I | -[q]x],  J_pt = Jpi R_cw.
+ *   Pose-graph terms (SE3Edge / GPSEdge, Optimizer.h:127-148) add e = Log(Z^-1 T_1^-1 T_2) / Log(Z^-1 T) with e' Omega e to the cost
+ *   and J' Omega J / J' Omega e to the camera blocks (pose_edge_eval below); a graph may hold them alone (a pose graph).
  *   Levenberg-Marquardt with Marquardt scaling lambda*clamp(diag,1e-6,1e32) on U and V; Schur complement onto the cameras;
  *   block-Jacobi PCG; back-substitution; accept iff cost decreases (lambda/=3, nu=2) else (lambda*=nu, nu*=2).
  */
@@ -87,6 +89,118 @@ void orc_se3_retract(const double* pose, const double* d, double* out) {
 }
 
 static double clampd(double d) { return d < 1e-6 ? 1e-6 : (d > 1e32 ? 1e32 : d); }
+
+/* ---- pose-graph terms (row f3: GSLAM::SE3Edge / GPSEdge, Optimizer.h:127-148; our definition, see the header) ------------------- */
+/* Log of an SE3 given as pose7, tangent order [v, w]: restates the reference's SE3::log (GSLAM/core/SE3.h:205-246, NEAR_ZERO = 1e-10
+ * SO3.h:43) -- pinned against the reference class through oracle/_ref in tests/test_oracle_ba.py. */
+void orc_se3_log(const double* T, double* out6) {
+  const double x = T[0], y = T[1], z = T[2], w = T[3];
+  const double* t = T + 4;
+  const double n = sqrt(x * x + y * y + z * z);
+  double A_inv, r[3], c1[3], c2[3];
+  if (n < 1e-10) {
+    A_inv = 2.0 / w - 2.0 * (1.0 - w * w) / (w * w * w);
+    r[0] = x * A_inv; r[1] = y * A_inv; r[2] = z * A_inv;
+    c1[0] = r[1] * t[2] - r[2] * t[1]; c1[1] = r[2] * t[0] - r[0] * t[2]; c1[2] = r[0] * t[1] - r[1] * t[0];
+    c2[0] = r[1] * c1[2] - r[2] * c1[1]; c2[1] = r[2] * c1[0] - r[0] * c1[2]; c2[2] = r[0] * c1[1] - r[1] * c1[0];
+    for (int k = 0; k < 3; ++k) out6[k] = t[k] - 0.5 * c1[k] + (1.0 / 12.0) * c2[k];
+  } else {
+    if (fabs(w) < 1e-10) A_inv = (w > 0 ? 3.14159265358979323846 : -3.14159265358979323846) / n;
+    else A_inv = 2.0 * atan(n / w) / n;
+    const double theta = A_inv * n;
+    r[0] = x * A_inv; r[1] = y * A_inv; r[2] = z * A_inv;
+    const double a[3] = {r[0] / theta, r[1] / theta, r[2] / theta};
+    c1[0] = r[1] * t[2] - r[2] * t[1]; c1[1] = r[2] * t[0] - r[0] * t[2]; c1[2] = r[0] * t[1] - r[1] * t[0];
+    double a1[3] = {a[1] * t[2] - a[2] * t[1], a[2] * t[0] - a[0] * t[2], a[0] * t[1] - a[1] * t[0]};
+    c2[0] = a[1] * a1[2] - a[2] * a1[1]; c2[1] = a[2] * a1[0] - a[0] * a1[2]; c2[2] = a[0] * a1[1] - a[1] * a1[0];
+    const double k2 = 1.0 - theta / (2.0 * tan(0.5 * theta));
+    for (int k = 0; k < 3; ++k) out6[k] = t[k] - 0.5 * c1[k] + k2 * c2[k];
+  }
+  out6[3] = r[0]; out6[4] = r[1]; out6[5] = r[2];
+}
+/* out = a * b (SE3.h:129-131: rotation product, translation a.R * b.t + a.t) */
+void orc_se3_mul(const double* a, const double* b, double* out) {
+  double q[4], t[3];
+  quat_mul(a, b, q);
+  quat_rot(a, b + 4, t);
+  out[0] = q[0]; out[1] = q[1]; out[2] = q[2]; out[3] = q[3];
+  out[4] = t[0] + a[4]; out[5] = t[1] + a[5]; out[6] = t[2] + a[6];
+}
+/* 6x6 adjoint of T for the tangent order [v, w]: Ad = [[R, [t]x R], [0, R]]  (Exp(d) T = T Exp(Ad(T^-1) d)) */
+static void se3_adjoint(const double* T, double* Ad) {
+  double R[9];
+  quat_to_R(T, R);
+  const double* t = T + 4;
+  const double tx[9] = {0.0, -t[2], t[1], t[2], 0.0, -t[0], -t[1], t[0], 0.0};
+  memset(Ad, 0, sizeof(double) * 36);
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      Ad[a * 6 + b] = R[a * 3 + b];
+      Ad[(3 + a) * 6 + 3 + b] = R[a * 3 + b];
+      Ad[a * 6 + 3 + b] = tx[a * 3] * R[b] + tx[a * 3 + 1] * R[3 + b] + tx[a * 3 + 2] * R[6 + b];
+    }
+}
+static void mat6_mul(const double* A, const double* B, double* C) {
+  for (int a = 0; a < 6; ++a)
+    for (int b = 0; b < 6; ++b) {
+      double x = 0.0;
+      for (int k = 0; k < 6; ++k) x += A[a * 6 + k] * B[k * 6 + b];
+      C[a * 6 + b] = x;
+    }
+}
+/* Inverse left Jacobian of SE3 at xi = [v, w]:  Log(Exp(d) Exp(xi)) = xi + Jl^-1(xi) d + O(d^2).  Bernoulli series in the adjoint
+ * ad(xi) = [[w^, v^], [0, w^]]:  I - ad/2 + ad^2/12 - ad^4/720 + ad^6/30240 - ad^8/1209600  (next term 2e-8 |ad|^10: residuals of a
+ * pose graph near its optimum are far inside the radius where this is double precision). */
+static void se3_jl_inv(const double* xi, double* J) {
+  const double* v = xi; const double* w = xi + 3;
+  double A[36], A2[36], A4[36], A6[36], A8[36];
+  memset(A, 0, sizeof A);
+  const double wx[9] = {0.0, -w[2], w[1], w[2], 0.0, -w[0], -w[1], w[0], 0.0};
+  const double vx[9] = {0.0, -v[2], v[1], v[2], 0.0, -v[0], -v[1], v[0], 0.0};
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) { A[a * 6 + b] = wx[a * 3 + b]; A[(3 + a) * 6 + 3 + b] = wx[a * 3 + b]; A[a * 6 + 3 + b] = vx[a * 3 + b]; }
+  mat6_mul(A, A, A2); mat6_mul(A2, A2, A4); mat6_mul(A4, A2, A6); mat6_mul(A4, A4, A8);
+  for (int k = 0; k < 36; ++k)
+    J[k] = ((k % 7) == 0 ? 1.0 : 0.0) - 0.5 * A[k] + A2[k] * (1.0 / 12.0) - A4[k] * (1.0 / 720.0) + A6[k] * (1.0 / 30240.0) - A8[k] * (1.0 / 1209600.0);
+}
+/* One pose-graph term at the internal estimate (T_cw per camera).
+ *   SE3Edge (first = i, second = j, Z = T_wc,i^-1 T_wc,j, Optimizer.h:127-133):  E = Z^-1 T_cw,i T_cw,j^-1,  e = Log(E)
+ *        left updates T_cw <- Exp(d) T_cw give  E' = Exp(Ad(Z^-1) d_i) Exp(-Ad(E) d_j) E,  so  J_i = Jl^-1(e) Ad(Z^-1),  J_j = -Jl^-1(e) Ad(E)
+ *   GPSEdge (frame i, Z = T_wc,i prior, Optimizer.h:143-148):                    E = Z^-1 T_cw,i^-1,  e = Log(E),  J_i = -Jl^-1(e) Ad(E)
+ * Cost term e' Omega e, no robust kernel.  Ji / Jj are 6x6 row-major; Jj unused for a GPS edge. */
+static void pose_edge_eval(const double* Zinv, const double* Ti_cw, const double* Tj_cw, int is_gps, double* e, double* Ji, double* Jj) {
+  double E[7], tmp[7], inv[7];
+  if (is_gps) {
+    orc_se3_inverse(Ti_cw, inv);
+    orc_se3_mul(Zinv, inv, E);
+  } else {
+    orc_se3_inverse(Tj_cw, inv);
+    orc_se3_mul(Ti_cw, inv, tmp);
+    orc_se3_mul(Zinv, tmp, E);
+  }
+  orc_se3_log(E, e);
+  if (!Ji) return;
+  double AdE[36], AdZ[36], Jl[36], T[36];
+  se3_adjoint(E, AdE);
+  se3_jl_inv(e, Jl);
+  mat6_mul(Jl, AdE, T);
+  if (is_gps) {
+    for (int k = 0; k < 36; ++k) Ji[k] = -T[k];
+  } else {
+    se3_adjoint(Zinv, AdZ);
+    mat6_mul(Jl, AdZ, Ji);
+    for (int k = 0; k < 36; ++k) Jj[k] = -T[k];
+  }
+}
+static double quad6(const double* info, const double* e) { /* e' Omega e, Omega = identity when info == NULL */
+  double s = 0.0;
+  for (int a = 0; a < 6; ++a) {
+    double r = 0.0;
+    if (info) for (int b = 0; b < 6; ++b) r += 0.5 * (info[a * 6 + b] + info[b * 6 + a]) * e[b]; else r = e[a];
+    s += e[a] * r;
+  }
+  return s;
+}
 
 /* Cholesky-based inverse of a small SPD matrix (n<=6), row-major, in place.  Returns 0 on success. */
 static int spd_inverse(double* A, int n) {
@@ -167,6 +281,11 @@ typedef struct {
   double *U, *gc, *V, *gp, *W; /* nc x 36, nc x 6, np x 9, np x 3, no x 18 */
   /* point -> obs lists */
   int *poff, *plist;
+  /* pose-graph terms: SE3 edges then GPS edges; Zinv = measurement^-1; P = off-diagonal block J_i' Omega J_j of each SE3 edge */
+  int nse, ngps;
+  const int32_t *se_i, *se_j, *gps_i;
+  const double *se_info, *gps_info;
+  double *se_Zinv, *gps_Zinv, *P;
 } ba_state;
 
 static int dofmask(const ba_state* s, int i) { return s->dof ? (s->dof[i] & 63) : 63; }
@@ -183,7 +302,51 @@ static double ba_cost(const ba_state* s, const double* pose, const double* pts) 
     c += o.rho;
   }
   free(Rs);
+  for (int k = 0; k < s->nse; ++k) {
+    double e[6];
+    pose_edge_eval(s->se_Zinv + 7 * k, pose + 7 * s->se_i[k], pose + 7 * s->se_j[k], 0, e, NULL, NULL);
+    c += quad6(s->se_info ? s->se_info + 36 * k : NULL, e);
+  }
+  for (int k = 0; k < s->ngps; ++k) {
+    double e[6];
+    pose_edge_eval(s->gps_Zinv + 7 * k, pose + 7 * s->gps_i[k], NULL, 1, e, NULL, NULL);
+    c += quad6(s->gps_info ? s->gps_info + 36 * k : NULL, e);
+  }
   return 0.5 * c;
+}
+
+/* H_ab += Ja' Omega Jb (6x6), g_a -= Ja' Omega e, with the fixed dofs' columns of the Jacobians zeroed */
+static void pose_term_accumulate(const double* info, const double* e, double* Ja, int dma, double* Jb, int dmb, double* Uaa, double* ga, double* Ubb,
+                                 double* gb, double* Pab) {
+  for (int d = 0; d < 6; ++d) {
+    if (!((dma >> d) & 1)) for (int r = 0; r < 6; ++r) Ja[r * 6 + d] = 0.0;
+    if (Jb && !((dmb >> d) & 1)) for (int r = 0; r < 6; ++r) Jb[r * 6 + d] = 0.0;
+  }
+  double Om[36], OJa[36], OJb[36], Oe[6];
+  for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) Om[a * 6 + b] = info ? 0.5 * (info[a * 6 + b] + info[b * 6 + a]) : (a == b ? 1.0 : 0.0);
+  for (int a = 0; a < 6; ++a) {
+    Oe[a] = 0.0;
+    for (int b = 0; b < 6; ++b) Oe[a] += Om[a * 6 + b] * e[b];
+    for (int c = 0; c < 6; ++c) {
+      double x = 0.0, y = 0.0;
+      for (int b = 0; b < 6; ++b) { x += Om[a * 6 + b] * Ja[b * 6 + c]; if (Jb) y += Om[a * 6 + b] * Jb[b * 6 + c]; }
+      OJa[a * 6 + c] = x; OJb[a * 6 + c] = y;
+    }
+  }
+  for (int a = 0; a < 6; ++a) {
+    double x = 0.0, y = 0.0;
+    for (int r = 0; r < 6; ++r) { x += Ja[r * 6 + a] * Oe[r]; if (Jb) y += Jb[r * 6 + a] * Oe[r]; }
+    ga[a] -= x; if (Jb) gb[a] -= y;
+    for (int c = 0; c < 6; ++c) {
+      double haa = 0.0, hbb = 0.0, hab = 0.0;
+      for (int r = 0; r < 6; ++r) {
+        haa += Ja[r * 6 + a] * OJa[r * 6 + c];
+        if (Jb) { hbb += Jb[r * 6 + a] * OJb[r * 6 + c]; hab += Ja[r * 6 + a] * OJb[r * 6 + c]; }
+      }
+      Uaa[a * 6 + c] += haa;
+      if (Jb) { Ubb[a * 6 + c] += hbb; Pab[a * 6 + c] = hab; }
+    }
+  }
 }
 
 static double ba_linearize(ba_state* s) {
@@ -220,12 +383,28 @@ static double ba_linearize(ba_state* s) {
     }
   }
   free(Rs);
+  for (int k = 0; k < s->nse; ++k) {
+    double e[6], Ji[36], Jj[36];
+    const int i = s->se_i[k], j = s->se_j[k];
+    const double* info = s->se_info ? s->se_info + 36 * k : NULL;
+    pose_edge_eval(s->se_Zinv + 7 * k, s->pose + 7 * i, s->pose + 7 * j, 0, e, Ji, Jj);
+    c += quad6(info, e);
+    pose_term_accumulate(info, e, Ji, dofmask(s, i), Jj, dofmask(s, j), s->U + 36 * i, s->gc + 6 * i, s->U + 36 * j, s->gc + 6 * j, s->P + 36 * (size_t)k);
+  }
+  for (int k = 0; k < s->ngps; ++k) {
+    double e[6], Ji[36];
+    const int i = s->gps_i[k];
+    const double* info = s->gps_info ? s->gps_info + 36 * k : NULL;
+    pose_edge_eval(s->gps_Zinv + 7 * k, s->pose + 7 * i, NULL, 1, e, Ji, NULL);
+    c += quad6(info, e);
+    pose_term_accumulate(info, e, Ji, dofmask(s, i), NULL, 0, s->U + 36 * i, s->gc + 6 * i, NULL, NULL, NULL);
+  }
   return 0.5 * c;
 }
 
 /* Exposed for kernel-level parity tests: linearise `problem` at its estimate. Outputs may be NULL.
  * U: nc*36, gc: nc*6, V: np*9, gp: np*3, W: no*18 (in the caller's observation order). */
-static void state_init(ba_state* s, const gb_ba_problem* pb, double delta) {
+static void state_init_ex(ba_state* s, const gb_ba_problem* pb, const gb_pose_edges* pe, double delta) {
   memset(s, 0, sizeof *s);
   s->nc = pb->n_cams; s->np = pb->n_points; s->no = pb->n_obs;
   s->dof = pb->cam_dof; s->pfree = pb->point_free; s->oc = pb->obs_cam; s->op = pb->obs_point; s->om = pb->obs_xyz; s->oi = pb->obs_info;
@@ -243,9 +422,29 @@ static void state_init(ba_state* s, const gb_ba_problem* pb, double delta) {
   int* fill = (int*)calloc((size_t)s->np + 1, sizeof(int));
   for (int k = 0; k < s->no; ++k) { int j = s->op[k]; s->plist[s->poff[j] + fill[j]++] = k; }
   free(fill);
+  if (pe) {
+    s->nse = pe->n_se3; s->ngps = pe->n_gps;
+    s->se_i = pe->se3_first; s->se_j = pe->se3_second; s->gps_i = pe->gps_frame; s->se_info = pe->se3_info; s->gps_info = pe->gps_info;
+  }
+  s->se_Zinv = (double*)malloc(sizeof(double) * 7 * (size_t)(s->nse + 1));
+  s->gps_Zinv = (double*)malloc(sizeof(double) * 7 * (size_t)(s->ngps + 1));
+  s->P = (double*)calloc(36 * (size_t)(s->nse + 1), sizeof(double));
+  for (int k = 0; k < s->nse; ++k) orc_se3_inverse(pe->se3_meas + 7 * k, s->se_Zinv + 7 * k);
+  for (int k = 0; k < s->ngps; ++k) orc_se3_inverse(pe->gps_meas + 7 * k, s->gps_Zinv + 7 * k);
 }
+static void state_init(ba_state* s, const gb_ba_problem* pb, double delta) { state_init_ex(s, pb, NULL, delta); }
 static void state_free(ba_state* s) {
   free(s->pose); free(s->pts); free(s->U); free(s->gc); free(s->V); free(s->gp); free(s->W); free(s->poff); free(s->plist);
+  free(s->se_Zinv); free(s->gps_Zinv); free(s->P);
+}
+static int validate_edges(const gb_ba_problem* pb, const gb_pose_edges* pe) {
+  if (!pe) return 0;
+  if (pe->n_se3 < 0 || pe->n_gps < 0) return 1;
+  for (int k = 0; k < pe->n_se3; ++k)
+    if (pe->se3_first[k] < 0 || pe->se3_first[k] >= pb->n_cams || pe->se3_second[k] < 0 || pe->se3_second[k] >= pb->n_cams || pe->se3_first[k] == pe->se3_second[k]) return 1;
+  for (int k = 0; k < pe->n_gps; ++k)
+    if (pe->gps_frame[k] < 0 || pe->gps_frame[k] >= pb->n_cams) return 1;
+  return 0;
 }
 
 static int validate(const gb_ba_problem* pb) {
@@ -255,10 +454,10 @@ static int validate(const gb_ba_problem* pb) {
   return 0;
 }
 
-int orc_ba_linearize(const gb_ba_problem* pb, double delta, double* U, double* gc, double* V, double* gp, double* W, double* cost) {
-  if (validate(pb)) return GB_ERR_INVALID;
+int orc_ba_linearize_ex(const gb_ba_problem* pb, const gb_pose_edges* pe, double delta, double* U, double* gc, double* V, double* gp, double* W, double* cost) {
+  if (validate(pb) || validate_edges(pb, pe)) return GB_ERR_INVALID;
   ba_state s;
-  state_init(&s, pb, delta);
+  state_init_ex(&s, pb, pe, delta);
   double c = ba_linearize(&s);
   if (U) memcpy(U, s.U, sizeof(double) * 36 * (size_t)s.nc);
   if (gc) memcpy(gc, s.gc, sizeof(double) * 6 * (size_t)s.nc);
@@ -270,14 +469,20 @@ int orc_ba_linearize(const gb_ba_problem* pb, double delta, double* U, double* g
   return GB_OK;
 }
 
-int orc_ba_cost(const gb_ba_problem* pb, double delta, double* cost) {
-  if (validate(pb)) return GB_ERR_INVALID;
+int orc_ba_linearize(const gb_ba_problem* pb, double delta, double* U, double* gc, double* V, double* gp, double* W, double* cost) {
+  return orc_ba_linearize_ex(pb, NULL, delta, U, gc, V, gp, W, cost);
+}
+
+int orc_ba_cost_ex(const gb_ba_problem* pb, const gb_pose_edges* pe, double delta, double* cost) {
+  if (validate(pb) || validate_edges(pb, pe)) return GB_ERR_INVALID;
   ba_state s;
-  state_init(&s, pb, delta);
+  state_init_ex(&s, pb, pe, delta);
   *cost = ba_cost(&s, s.pose, s.pts);
   state_free(&s);
   return GB_OK;
 }
+
+int orc_ba_cost(const gb_ba_problem* pb, double delta, double* cost) { return orc_ba_cost_ex(pb, NULL, delta, cost); }
 
 /* Build the damped reduced camera system: S (n6 x n6 dense, row-major), gt (n6), Vinv (np x 9). */
 static void ba_schur(const ba_state* s, double lambda, double* S, double* gt, double* Vinv) {
@@ -291,6 +496,15 @@ static void ba_schur(const ba_state* s, double lambda, double* S, double* gt, do
       else S[(size_t)(6 * i + a) * n6 + 6 * i + a] = 1.0;
       gt[6 * i + a] = s->gc[6 * i + a];
     }
+  }
+  for (int k = 0; k < s->nse; ++k) { /* pose-graph coupling: S_ij += J_i' Omega J_j, S_ji += its transpose */
+    const int i = s->se_i[k], j = s->se_j[k];
+    const double* P = s->P + 36 * (size_t)k;
+    for (int a = 0; a < 6; ++a)
+      for (int b = 0; b < 6; ++b) {
+        S[(size_t)(6 * i + a) * n6 + 6 * j + b] += P[a * 6 + b];
+        S[(size_t)(6 * j + b) * n6 + 6 * i + a] += P[a * 6 + b];
+      }
   }
   for (int j = 0; j < np; ++j) {
     double* Vi = Vinv + 9 * j;
@@ -410,10 +624,10 @@ static int ba_chol_solve(int nc, double* S, const double* g, double* x) {
 }
 
 /* Exposed for kernel-level parity tests: S (6nc x 6nc), gt (6nc) and the PCG solution dc (6nc) at the input estimate. */
-int orc_ba_reduced_system(const gb_ba_problem* pb, double delta, double lambda, int pcg_maxit, double pcg_tol, double* S, double* gt, double* dc, int* pcg_iters) {
-  if (validate(pb)) return GB_ERR_INVALID;
+int orc_ba_reduced_system_ex(const gb_ba_problem* pb, const gb_pose_edges* pe, double delta, double lambda, int pcg_maxit, double pcg_tol, double* S, double* gt, double* dc, int* pcg_iters) {
+  if (validate(pb) || validate_edges(pb, pe)) return GB_ERR_INVALID;
   ba_state s;
-  state_init(&s, pb, delta);
+  state_init_ex(&s, pb, pe, delta);
   ba_linearize(&s);
   double* Vinv = (double*)malloc(sizeof(double) * 9 * (size_t)(s.np + 1));
   ba_schur(&s, lambda, S, gt, Vinv);
@@ -423,12 +637,19 @@ int orc_ba_reduced_system(const gb_ba_problem* pb, double delta, double lambda, 
   return GB_OK;
 }
 
-int orc_ba_solve(gb_ba_problem* pb, const gb_ba_options* opt_in, gb_ba_result* res) {
+int orc_ba_reduced_system(const gb_ba_problem* pb, double delta, double lambda, int pcg_maxit, double pcg_tol, double* S, double* gt, double* dc, int* pcg_iters) {
+  return orc_ba_reduced_system_ex(pb, NULL, delta, lambda, pcg_maxit, pcg_tol, S, gt, dc, pcg_iters);
+}
+
+int orc_ba_solve_ex(gb_ba_problem* pb, const gb_pose_edges* pe, const gb_ba_options* opt_in, gb_ba_result* res);
+int orc_ba_solve(gb_ba_problem* pb, const gb_ba_options* opt_in, gb_ba_result* res) { return orc_ba_solve_ex(pb, NULL, opt_in, res); }
+
+int orc_ba_solve_ex(gb_ba_problem* pb, const gb_pose_edges* pe, const gb_ba_options* opt_in, gb_ba_result* res) {
   gb_ba_options opt;
   if (opt_in) opt = *opt_in; else { opt.projection = 0; opt.huber_delta = 0.01; opt.max_iterations = 500; opt.verbose = 0; opt.function_tolerance = 1e-6; opt.lambda_init = 1e-4; opt.pcg_max_iters = 50; opt.pcg_tol = 1e-10; opt.linear_solver = 0; }
-  if (validate(pb) || opt.projection != 0) return GB_ERR_INVALID;
+  if (validate(pb) || validate_edges(pb, pe) || opt.projection != 0) return GB_ERR_INVALID;
   ba_state s;
-  state_init(&s, pb, opt.huber_delta);
+  state_init_ex(&s, pb, pe, opt.huber_delta);
   int nc = s.nc, np = s.np, n6 = 6 * nc;
   double* S = (double*)malloc(sizeof(double) * ((size_t)n6 * n6 + 1));
   double *gt = (double*)malloc(sizeof(double) * (size_t)(n6 + 1)), *dc = (double*)malloc(sizeof(double) * (size_t)(n6 + 1));

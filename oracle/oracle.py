@@ -23,6 +23,11 @@ class BaProblemC(C.Structure):
                 ("obs_cam", i32p), ("obs_point", i32p), ("obs_xyz", f64p), ("obs_info", f64p)]
 
 
+class PoseEdgesC(C.Structure):
+    _fields_ = [("n_se3", C.c_int32), ("se3_first", i32p), ("se3_second", i32p), ("se3_meas", f64p), ("se3_info", f64p),
+                ("n_gps", C.c_int32), ("gps_frame", i32p), ("gps_meas", f64p), ("gps_info", f64p)]
+
+
 class BaOptionsC(C.Structure):
     _fields_ = [("projection", C.c_int32), ("huber_delta", C.c_double), ("max_iterations", C.c_int32),
                 ("verbose", C.c_int32), ("function_tolerance", C.c_double), ("lambda_init", C.c_double),
@@ -99,6 +104,19 @@ def lib() -> C.CDLL:
         L.orc_ba_reduced_system.restype = C.c_int
         L.orc_ba_reduced_system.argtypes = [C.POINTER(BaProblemC), C.c_double, C.c_double, C.c_int, C.c_double,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.orc_ba_solve_ex.restype = C.c_int
+        L.orc_ba_solve_ex.argtypes = [C.POINTER(BaProblemC), C.POINTER(PoseEdgesC), C.POINTER(BaOptionsC), C.POINTER(BaResultC)]
+        L.orc_ba_linearize_ex.restype = C.c_int
+        L.orc_ba_linearize_ex.argtypes = [C.POINTER(BaProblemC), C.POINTER(PoseEdgesC), C.c_double] + [C.c_void_p] * 6
+        L.orc_ba_cost_ex.restype = C.c_int
+        L.orc_ba_cost_ex.argtypes = [C.POINTER(BaProblemC), C.POINTER(PoseEdgesC), C.c_double, f64p]
+        L.orc_ba_reduced_system_ex.restype = C.c_int
+        L.orc_ba_reduced_system_ex.argtypes = [C.POINTER(BaProblemC), C.POINTER(PoseEdgesC), C.c_double, C.c_double, C.c_int, C.c_double,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.orc_se3_log.restype = None
+        L.orc_se3_log.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_se3_mul.restype = None
+        L.orc_se3_mul.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_ba_pnp.restype = C.c_int
         L.orc_ba_pnp.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                  C.POINTER(BaOptionsC), C.POINTER(BaResultC)]
@@ -242,40 +260,76 @@ def ba_problem_c(pb) -> tuple[BaProblemC, list]:
     return c, keep
 
 
-def ba_solve(pb, **opts):
+def pose_edges_c(edges):
+    """edges: an object with se3_first / se3_second / se3_meas / se3_info / gps_frame / gps_meas / gps_info (gslam_b200.synth.PoseEdges)
+    or None -> (ctypes struct or None, keep-alive list)"""
+    if edges is None:
+        return None, []
+    f = np.ascontiguousarray(edges.se3_first, np.int32); s_ = np.ascontiguousarray(edges.se3_second, np.int32)
+    m = np.ascontiguousarray(edges.se3_meas, np.float64).reshape(-1, 7)
+    si = None if edges.se3_info is None else np.ascontiguousarray(edges.se3_info, np.float64).reshape(-1, 36)
+    gf = np.ascontiguousarray(edges.gps_frame, np.int32); gm = np.ascontiguousarray(edges.gps_meas, np.float64).reshape(-1, 7)
+    gi = None if edges.gps_info is None else np.ascontiguousarray(edges.gps_info, np.float64).reshape(-1, 36)
+    cast = lambda a, t: None if a is None else a.ctypes.data_as(t)
+    c = PoseEdgesC(f.shape[0], cast(f, i32p), cast(s_, i32p), cast(m, f64p), cast(si, f64p), gf.shape[0], cast(gf, i32p), cast(gm, f64p), cast(gi, f64p))
+    return c, [f, s_, m, si, gf, gm, gi]
+
+
+def _pe(edges):
+    c, keep = pose_edges_c(edges)
+    return (C.byref(c) if c is not None else None), (c, keep)
+
+
+def ba_solve(pb, edges=None, **opts):
     c, keep = ba_problem_c(pb)
     o = default_ba_options(**opts)
     r = BaResultC()
-    rc = lib().orc_ba_solve(C.byref(c), C.byref(o), C.byref(r))
+    e, keep2 = _pe(edges)
+    rc = lib().orc_ba_solve_ex(C.byref(c), e, C.byref(o), C.byref(r))
     if rc != 0:
         raise RuntimeError(f"orc_ba_solve failed rc={rc}")
     return r
 
 
-def ba_linearize(pb, delta=0.01):
+def ba_linearize(pb, delta=0.01, edges=None):
     c, keep = ba_problem_c(pb)
     U = np.zeros((pb.n_cams, 6, 6)); gc = np.zeros((pb.n_cams, 6)); V = np.zeros((pb.n_points, 3, 3)); gp = np.zeros((pb.n_points, 3))
     W = np.zeros((pb.n_obs, 6, 3)); cost = np.zeros(1)
-    rc = lib().orc_ba_linearize(C.byref(c), delta, _p(U), _p(gc), _p(V), _p(gp), _p(W), _p(cost))
+    e, keep2 = _pe(edges)
+    rc = lib().orc_ba_linearize_ex(C.byref(c), e, delta, _p(U), _p(gc), _p(V), _p(gp), _p(W), _p(cost))
     assert rc == 0
     return dict(U=U, gc=gc, V=V, gp=gp, W=W, cost=float(cost[0]))
 
 
-def ba_cost(pb, delta=0.01) -> float:
+def ba_cost(pb, delta=0.01, edges=None) -> float:
     c, keep = ba_problem_c(pb)
     out = C.c_double()
-    rc = lib().orc_ba_cost(C.byref(c), delta, C.byref(out))
+    e, keep2 = _pe(edges)
+    rc = lib().orc_ba_cost_ex(C.byref(c), e, delta, C.byref(out))
     assert rc == 0
     return out.value
 
 
-def ba_reduced_system(pb, delta=0.01, lam=1e-4, pcg_max_iters=50, pcg_tol=1e-10):
+def ba_reduced_system(pb, delta=0.01, lam=1e-4, pcg_max_iters=50, pcg_tol=1e-10, edges=None):
     c, keep = ba_problem_c(pb)
     n6 = 6 * pb.n_cams
     S = np.zeros((n6, n6)); gt = np.zeros(n6); dc = np.zeros(n6); it = C.c_int()
-    rc = lib().orc_ba_reduced_system(C.byref(c), delta, lam, pcg_max_iters, pcg_tol, _p(S), _p(gt), _p(dc), C.byref(it))
+    e, keep2 = _pe(edges)
+    rc = lib().orc_ba_reduced_system_ex(C.byref(c), e, delta, lam, pcg_max_iters, pcg_tol, _p(S), _p(gt), _p(dc), C.byref(it))
     assert rc == 0
     return S, gt, dc, it.value
+
+
+def se3_log(pose7):
+    p = np.ascontiguousarray(pose7, np.float64); out = np.zeros(6)
+    lib().orc_se3_log(_p(p), _p(out))
+    return out
+
+
+def se3_mul(a7, b7):
+    a = np.ascontiguousarray(a7, np.float64); b = np.ascontiguousarray(b7, np.float64); out = np.zeros(7)
+    lib().orc_se3_mul(_p(a), _p(b), _p(out))
+    return out
 
 
 def ba_pnp(xyz, xy1, pose_wc, dof=63, want_info=False, **opts):

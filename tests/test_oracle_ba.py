@@ -151,3 +151,44 @@ def test_invalid_indices_rejected():
     pb.obs_cam[0] = 99
     with pytest.raises(RuntimeError):
         oracle.ba_solve(pb, max_iterations=1)
+
+
+@pytest.mark.parametrize("shape", [dict(nc=500, np_=100000, lo=8, hi=12, split=1), dict(nc=60, np_=5000, lo=1, hi=6, split=1),
+                                   dict(nc=300, np_=300, lo=0, hi=300, split=2), dict(nc=7, np_=3, lo=200, hi=400, split=4)])
+def test_large_graph_sweep_plan_covers_everything_once_and_is_balanced(shape):
+    """Host logic of csrc/ba_sweep.cu (no device): the items dealt to the teams cover every camera slice and every landmark exactly
+    once, landmark groups hold <= 128 observations / <= 32 landmarks (or are one long landmark), and the teams' costs are balanced."""
+    import ctypes as C
+    from gslam_b200 import capi
+    rng = np.random.default_rng(shape["nc"])
+    nc, npts, split = shape["nc"], shape["np_"], shape["split"]
+    per_pt = rng.integers(shape["lo"], shape["hi"] + 1, npts)
+    pt_off = np.concatenate([[0], np.cumsum(per_pt)]).astype(np.int32)
+    no = int(pt_off[-1])
+    cam_of = rng.integers(0, nc, no)
+    cam_off = np.concatenate([[0], np.cumsum(np.bincount(cam_of, minlength=nc))]).astype(np.int32)
+    n_teams = 592
+    items = np.zeros((npts + nc * split + 8, 4), np.int32); team_off = np.zeros(n_teams + 1, np.int32); n = C.c_int(0)
+    rc = capi.lib().gb_dbg_ba_sweep_plan(nc, npts, split, cam_off.ctypes.data, pt_off.ctypes.data, n_teams, items.ctypes.data, items.shape[0],
+                                         team_off.ctypes.data, C.byref(n))
+    assert rc == 0
+    items = items[:n.value]
+    assert team_off[0] == 0 and team_off[-1] == n.value and np.all(np.diff(team_off) >= 0)
+    cams = items[items[:, 0] < 0]; grps = items[items[:, 0] >= 0]
+    seen = sorted((int(-1 - a), int(b)) for a, b, _, _ in cams)
+    assert seen == [(i, s) for i in range(nc) for s in range(split)]
+    for a, b, s0, s1 in cams:                                  # the slices of a camera tile its observation range
+        i = -1 - a
+        assert cam_off[i] <= s0 <= s1 <= cam_off[i + 1]
+    assert sum(int(s1 - s0) for _, _, s0, s1 in cams) == no
+    order = np.argsort(grps[:, 0], kind="stable"); g = grps[order]
+    assert g[0, 0] == 0 and g[-1, 1] == npts and np.array_equal(g[1:, 0], g[:-1, 1])     # landmarks: a partition, in order
+    assert np.array_equal(g[:, 2], pt_off[g[:, 0]]) and np.array_equal(g[:, 3], pt_off[g[:, 1]])
+    L = g[:, 1] - g[:, 0]; obs = g[:, 3] - g[:, 2]
+    assert np.all(L <= 32) and np.all((obs <= 128) | (L == 1))
+    cost = np.zeros(n_teams)
+    for k in range(n_teams):
+        for a, b, c, d in items[team_off[k]:team_off[k + 1]]:
+            cost[k] += (0.4 * (d - c) + 150.0) if a < 0 else ((d - c) + 40.0)
+    if n.value > 4 * n_teams:
+        assert cost.max() < 1.25 * cost.mean() + 700.0
