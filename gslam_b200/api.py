@@ -39,6 +39,21 @@ class OptimzeConfig:  # spelling follows GSLAM::OptimzeConfig (Optimizer.h:174-1
                               self.pcgTolerance, self.linearSolver)
 
 
+def _edges_c(edges):
+    """gslam_b200.synth.PoseEdges -> (capi.PoseEdges or None, keep-alive list)"""
+    if edges is None:
+        return None, []
+    f = np.ascontiguousarray(edges.se3_first, np.int32); s_ = np.ascontiguousarray(edges.se3_second, np.int32)
+    m = np.ascontiguousarray(edges.se3_meas, np.float64).reshape(-1, 7)
+    si = None if edges.se3_info is None else np.ascontiguousarray(edges.se3_info, np.float64).reshape(-1, 36)
+    gf = np.ascontiguousarray(edges.gps_frame, np.int32); gm = np.ascontiguousarray(edges.gps_meas, np.float64).reshape(-1, 7)
+    gi = None if edges.gps_info is None else np.ascontiguousarray(edges.gps_info, np.float64).reshape(-1, 36)
+    cast = lambda a, t: None if a is None else a.ctypes.data_as(t)
+    c = capi.PoseEdges(f.shape[0], cast(f, capi.i32p), cast(s_, capi.i32p), cast(m, capi.f64p), cast(si, capi.f64p), gf.shape[0], cast(gf, capi.i32p),
+                       cast(gm, capi.f64p), cast(gi, capi.f64p))
+    return c, [f, s_, m, si, gf, gm, gi]
+
+
 def _problem_c(pb: BAProblem):
     keep = []
 
@@ -184,6 +199,15 @@ class Context:
         self._check(self._lib.gb_ba_solve(self._h, C.byref(c), C.byref(o), C.byref(r)))
         return r
 
+    def ba_solve_posegraph(self, pb: BAProblem, edges, cfg: OptimzeConfig | None = None) -> capi.BaResult:
+        """Optimizer::optimize on a BundleGraph with SE3 / GPS edges (`edges`: gslam_b200.synth.PoseEdges)."""
+        c, keep = _problem_c(pb)
+        e, keep2 = _edges_c(edges)
+        o = (cfg or OptimzeConfig()).to_c()
+        r = capi.BaResult()
+        self._check(self._lib.gb_ba_solve_posegraph(self._h, C.byref(c), C.byref(e) if e is not None else None, C.byref(o), C.byref(r)))
+        return r
+
     def ba_pnp(self, xyz, xy1, pose_wc, dof: int = 63, want_info: bool = False, cfg: OptimzeConfig | None = None):
         xyz = np.ascontiguousarray(xyz, np.float64); xy1 = np.ascontiguousarray(xy1, np.float64)
         pose = np.ascontiguousarray(pose_wc, np.float64).copy()
@@ -318,12 +342,16 @@ class Features:
 class BAGraph:
     """A bundle-adjustment graph resident in HBM (gb_ba_graph)."""
 
-    def __init__(self, ctx: Context, pb: BAProblem):
+    def __init__(self, ctx: Context, pb: BAProblem, edges=None):
         self.ctx = ctx
         self.n_cams, self.n_points, self.n_obs = pb.n_cams, pb.n_points, pb.n_obs
         c, keep = _problem_c(pb)
         h = C.c_void_p()
-        ctx._check(ctx._lib.gb_ba_graph_create(ctx._h, C.byref(c), C.byref(h)))
+        if edges is None:
+            ctx._check(ctx._lib.gb_ba_graph_create(ctx._h, C.byref(c), C.byref(h)))
+        else:
+            e, keep2 = _edges_c(edges)
+            ctx._check(ctx._lib.gb_ba_graph_create_ex(ctx._h, C.byref(c), C.byref(e), C.byref(h)))
         self._h = h
 
     def close(self):

@@ -38,6 +38,11 @@ class BaProblem(C.Structure):
                 ("obs_cam", i32p), ("obs_point", i32p), ("obs_xyz", f64p), ("obs_info", f64p)]
 
 
+class PoseEdges(C.Structure):
+    _fields_ = [("n_se3", C.c_int32), ("se3_first", i32p), ("se3_second", i32p), ("se3_meas", f64p), ("se3_info", f64p),
+                ("n_gps", C.c_int32), ("gps_frame", i32p), ("gps_meas", f64p), ("gps_info", f64p)]
+
+
 class BaOptions(C.Structure):
     _fields_ = [("projection", C.c_int32), ("huber_delta", C.c_double), ("max_iterations", C.c_int32),
                 ("verbose", C.c_int32), ("function_tolerance", C.c_double), ("lambda_init", C.c_double),
@@ -95,6 +100,8 @@ _SIGNATURES = [
     ("gb_ba_solve", C.c_int, [_VP, C.POINTER(BaProblem), C.POINTER(BaOptions), C.POINTER(BaResult)]),
     ("gb_ba_pnp", C.c_int, [_VP, C.c_int, _VP, _VP, _VP, C.c_int, _VP, C.POINTER(BaOptions), C.POINTER(BaResult)]),
     ("gb_ba_graph_create", C.c_int, [_VP, C.POINTER(BaProblem), C.POINTER(_VP)]),
+    ("gb_ba_graph_create_ex", C.c_int, [_VP, C.POINTER(BaProblem), C.POINTER(PoseEdges), C.POINTER(_VP)]),
+    ("gb_ba_solve_posegraph", C.c_int, [_VP, C.POINTER(BaProblem), C.POINTER(PoseEdges), C.POINTER(BaOptions), C.POINTER(BaResult)]),
     ("gb_ba_graph_destroy", C.c_int, [_VP, _VP]),
     ("gb_ba_graph_reset", C.c_int, [_VP, _VP]),
     ("gb_ba_graph_solve", C.c_int, [_VP, _VP, C.POINTER(BaOptions), C.POINTER(BaResult)]),

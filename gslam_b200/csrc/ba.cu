@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(256) ba_prepare_schur_kernel(BaDev g, double* 
   }
   if (blockIdx.x == 0) {  // deterministic cost reduction (strided partials + fixed tree)
     double v = 0.0;
-    for (int k = threadIdx.x; k < g.np; k += 256) v += g.cost_pt[k];
+    for (int k = threadIdx.x; k < g.np + g.npe; k += 256) v += g.cost_pt[k];
     const double t = block_sum<256>(v, s_part);
     if (threadIdx.x == 0) buf[g.r_gt + 2 * n6] = 0.5 * t;
   }
@@ -1735,12 +1735,13 @@ void gb_ba_options_default(gb_ba_options* o) {
 
 int gb_ba_graph_destroy(gb_ctx* ctx, gb_ba_graph* g) {
   if (!g) return GB_OK;
-  if (g->bcsr_cta_cam || g->sp_alloc || g->sw_alloc) {
+  if (g->bcsr_cta_cam || g->sp_alloc || g->sw_alloc || g->pe_alloc) {
     if (ctx) { CtxLock lk(ctx); cudaStreamSynchronize(ctx->stream); }
     if (g->bcsr_cta_cam) ba_pcg_bcsr_free(g);
     if (g->sp_alloc) cudaFree(g->sp_alloc);
     g->sp_alloc = nullptr;
     ba_sweep_plan_drop(g);
+    ba_pose_free(g);
   }
   if (g->from_arena) {
     if (ctx) ctx->ba_arena_busy = false;
@@ -1757,6 +1758,11 @@ int gb_ba_graph_destroy(gb_ctx* ctx, gb_ba_graph* g) {
 
 int gb_ba_graph_create(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out) {
   return ba_graph_create_impl(ctx, pb, out, false, 0, 1);
+}
+
+// a BundleGraph with pose-graph terms (se3Graph / gpsGraph, Optimizer.h:163-168); `edges` may be NULL
+int gb_ba_graph_create_ex(gb_ctx* ctx, const gb_ba_problem* pb, const gb_pose_edges* edges, gb_ba_graph** out) {
+  return ba_graph_create_impl(ctx, pb, out, false, 0, 1, edges);
 }
 
 }  // extern "C"
@@ -1907,13 +1913,17 @@ extern "C" GB_API int gb_dbg_ba_shard_bounds(int n_points, int n_obs, const int3
   return GB_OK;
 }
 
-int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out, bool use_arena, int shard_rank, int shard_world) {
+int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out, bool use_arena, int shard_rank, int shard_world,
+                         const gb_pose_edges* pose_edges) {
   if (!ctx || !out) return GB_ERR_INVALID;
   *out = nullptr;
   CtxLock lk(ctx);
   BaTrace tr;
   GB_CHECK(ba_validate(ctx, pb));
   if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return GB_ERR_INVALID;
+  GB_CHECK(ba_pose_validate(ctx, pb, pose_edges));
+  const int npe = pose_edges ? pose_edges->n_se3 + pose_edges->n_gps : 0;
+  if (npe > 0 && shard_world > 1) { gb_set_error(ctx, "gb_ba: pose-graph terms are not sharded (single-GPU solve)"); return GB_ERR_INVALID; }
   if (use_arena && ctx->ba_cached) ba_cache_drop(ctx);  // (another host-buffer call wants the arena the cached graph lives in)
   tr.stamp("validate");
   const int nc = pb->n_cams, np_full = pb->n_points, no_full = pb->n_obs;
@@ -2047,7 +2057,7 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
     sl.take(&d.pts, (size_t)np * 3); sl.take(&d.pts_new, (size_t)np * 3);
     sl.take(&d.V, (size_t)np * 9); sl.take(&d.gp, (size_t)np * 3); sl.take(&d.Vinv, (size_t)np * 9);
     sl.take(&d.W, (size_t)no * 18); sl.take(&d.U, (size_t)nc * 36); sl.take(&d.gc, (size_t)nc * 6);
-    sl.take(&d.cost_pt, (size_t)np); sl.take(&d.cost_pt_new, (size_t)np);
+    sl.take(&d.cost_pt, (size_t)np + npe); sl.take(&d.cost_pt_new, (size_t)np + npe);
     sl.take(&d.cam_part, (size_t)nc * std::max(d.cam_split, 4) * 27); sl.take(&cam_ticket_d, (size_t)nc / 2 + 1);
     sl.take(&d.Minv, (size_t)nc * 36);
     sl.take(&d.Sb, (size_t)d.s_nnzb * 36);
@@ -2150,7 +2160,11 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   }
   GB_CHECK(gb_ba_graph_reset(ctx, g));
   ba_pick_pcg(ctx, g);
-  if ((!g->pcg_sparse || compact_only) && d.s_nnzb > 0) {  // (a shard always runs on the compact block-CSR system)
+  if (npe > 0) {  // pose-graph terms: the stepwise path on the dense reduced system (one-cluster / generic PCG)
+    g->pcg_sparse = false;
+    GB_CHECK(ba_pose_attach(ctx, g, pose_edges));
+  }
+  if (npe == 0 && (!g->pcg_sparse || compact_only) && d.s_nnzb > 0) {  // (a shard always runs on the compact block-CSR system)
     GB_CHECK(ba_pcg_bcsr_plan(ctx, g, s_rowptr.data(), s_col.data()));
     if (!getenv("GB_BA_NO_SCHUR_CHUNKS")) ba_schur_plan(ctx, g, np, pt_off, scam, h + o_pf, s_rowptr, s_col, s_upper);  // (optional: the block-gather kernel otherwise)
   }
@@ -2197,6 +2211,7 @@ int gb_ba_graph_begin(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt_in) 
   }
   if (opt.max_iterations < 0 || opt.pcg_max_iters < 0) return GB_ERR_INVALID;
   if (opt.linear_solver != 0 && opt.linear_solver != 1) { gb_set_error(ctx, "gb_ba: linear_solver must be 0 (PCG) or 1 (direct)"); return GB_ERR_INVALID; }
+  if (opt.linear_solver == 1 && g->d.npe > 0) { gb_set_error(ctx, "gb_ba: graphs with pose-graph terms use linear_solver = 0 (PCG)"); return GB_ERR_INVALID; }
   if (opt.linear_solver == 1 && g->d.nc > 0 && (!g->chol_ok || g->shard_world > 1)) {
     gb_set_error(ctx, "gb_ba: the direct solver needs the block skyline of the reduced camera system to fit one SM's shared memory "
                       "(%d cameras here) and a single-GPU solve; use linear_solver = 0 (PCG)", g->d.nc);
@@ -2282,6 +2297,7 @@ int gb_ba_graph_reduce_local(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   if (!buf) buf = g->buf;
   cudaStream_t s = ctx->stream;
   GB_CHECK(ba_launch_sweep(ctx, g, d, s, 3));
+  GB_CHECK(ba_pose_linearize(ctx, g, s));  // (pose-graph terms, if any: into U, g_c and the cost terms before they are consumed)
   // Schur complement.  With the covisibility block structure at hand (<= 1024 cameras) S is formed block by block without
   // atomics (deterministic); the local-BA solver consumes the block-CSR directly, every other consumer (one-cluster / generic
   // PCG, the multi-GPU all-reduce) gets it scattered into the dense layout of `buf`.
@@ -2305,6 +2321,7 @@ int gb_ba_graph_reduce_local(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
     const int nblk = (int)std::min<size_t>(((size_t)d.n6 * d.n6 + 255) / 256, (size_t)ctx->sm_count * 8);
     ba_mirror_kernel<<<nblk, 256, 0, s>>>(d, buf); GB_LAUNCH_CHECK(ctx);
   }
+  GB_CHECK(ba_pose_offdiag(ctx, g, buf, s));
   return GB_OK;
 }
 
@@ -2394,7 +2411,8 @@ int gb_ba_graph_step(gb_ctx* ctx, gb_ba_graph* g, const double* buf_in, double* 
   double* buf = buf_in ? (double*)buf_in : g->buf;
   if (!d_cost) d_cost = g->d_cost;
   GB_CHECK(ba_step_core(ctx, g, buf));
-  ba_reduce_cost_kernel<<<1, kRedThreads, 0, ctx->stream>>>(d.sc, d.cost_pt_new, d.np, d_cost); GB_LAUNCH_CHECK(ctx);
+  GB_CHECK(ba_pose_cost(ctx, g, ctx->stream));
+  ba_reduce_cost_kernel<<<1, kRedThreads, 0, ctx->stream>>>(d.sc, d.cost_pt_new, d.np + d.npe, d_cost); GB_LAUNCH_CHECK(ctx);
   return GB_OK;
 }
 
@@ -2448,7 +2466,7 @@ static int ba_graph_solve_impl(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options*
   GB_CUDA(ctx, cudaEventRecord(ctx->evs, ctx->stream));
   const bool poll = g->opt.function_tolerance > 0.0 || g->opt.verbose;
   // one fused commit kernel while the estimate fits a single CTA's copy loop; the stepwise kernels otherwise
-  const bool fused_commit = (size_t)g->d.np * 3 + (size_t)g->d.nc * 19 <= (size_t)1 << 16;
+  const bool fused_commit = g->d.npe == 0 && (size_t)g->d.np * 3 + (size_t)g->d.nc * 19 <= (size_t)1 << 16;
   // local-BA fast path (block-CSR Schur + single-CTA PCG): 4 launches per LM iteration
   const bool local4 = fused_commit && g->pcg_sparse && g->d.s_nnzb > 0 && g->d.nc > 0 && g->d.np > 0;
   for (int it = 0; it < g->opt.max_iterations; ++it) {
@@ -2663,6 +2681,18 @@ extern "C" int gb_ba_solve(gb_ctx* ctx, gb_ba_problem* pb, const gb_ba_options* 
   return rc;
 }
 
+// Optimizer::optimize(BundleGraph&) for graphs with SE3 / GPS edges (pose graph, or bundle adjustment + pose-graph terms)
+extern "C" int gb_ba_solve_posegraph(gb_ctx* ctx, gb_ba_problem* pb, const gb_pose_edges* edges, const gb_ba_options* opt, gb_ba_result* res) {
+  if (!ctx || !pb) return GB_ERR_INVALID;
+  if (!edges || edges->n_se3 + edges->n_gps <= 0) return gb_ba_solve(ctx, pb, opt, res);
+  CtxLock lk(ctx);
+  gb_ba_graph* g = nullptr;
+  GB_CHECK(ba_graph_create_impl(ctx, pb, &g, false, 0, 1, edges));
+  const int rc = ba_graph_solve_impl(ctx, g, opt, res, g->d.nc > 0 ? pb->cam_pose_wc : nullptr, g->d.np > 0 ? pb->points : nullptr);
+  gb_ba_graph_destroy(ctx, g);
+  return rc;
+}
+
 extern "C" {
 
 int gb_ba_pnp(gb_ctx* ctx, int n, const double* xyz, const double* xy1, double* pose_wc, int dof, double* info6x6,
@@ -2755,6 +2785,7 @@ GB_API int gb_dbg_ba_force_generic_pcg(gb_ctx* ctx, gb_ba_graph* g, int on) {
   if (!ctx || !g) return GB_ERR_INVALID;
   CtxLock lk(ctx);
   ba_pick_pcg(ctx, g);
+  if (g->d.npe > 0) g->pcg_sparse = false;  // (pose-graph terms live on the dense reduced system)
   if (on == 1) { g->pcg_cluster = 0; g->pcg_sparse = false; }
   if (on == 2) g->pcg_sparse = false;
   if (on == 3) g->pcg_cluster = 0;

@@ -59,7 +59,14 @@ struct BaDev {
   int sw_nteams, sw_nitems;
   const int* sw_items;
   const int* sw_team_off;
-  // linearisation
+  // pose-graph terms (ba_pose.cu): npe = SE3 edges then GPS edges (pe_j = -1); staging records pe_H [npe][121]; gather plans
+  int npe, pe_npairs;
+  const int *pe_i, *pe_j;
+  const double *pe_Zinv, *pe_info;
+  double* pe_H;
+  const int *pc_off, *pc_ent;           // camera -> incident (edge << 1 | side) in edge order
+  const int *pp_off, *pp_ij, *pp_ent;   // unordered camera pair -> (edge << 1 | flipped) in edge order
+  // linearisation (cost_pt / cost_pt_new hold np landmark terms followed by npe pose-graph terms)
   double *V, *gp, *Vinv, *W, *U, *gc, *cost_pt, *cost_pt_new;
   // camera pass split: cam_split CTAs per camera, partial [27] sums + a per-camera ticket (the last CTA folds them in order)
   int cam_split;

@@ -48,6 +48,7 @@ struct gb_ba_graph {
   int chol_blocks = 0;
   size_t chol_smem = 0;
   void* sp_alloc = nullptr;      // device allocation holding the landmark-chunk Schur plan + staging (BaDev::sp_*), or null
+  void* pe_alloc = nullptr;      // device allocation holding the pose-graph edges and their gather plans (BaDev::pe_* / pc_* / pp_*)
   void* sw_alloc = nullptr;      // device allocation holding the large-graph sweep's item plan (BaDev::sw_*), made on first use
   std::vector<int> pt_off_h, cam_off_h;  // host copies of pt_off / cam_off (the sweep plan is cut from them)
   // landmark shard (multi-GPU global BA): this graph holds landmarks [shard_lo, shard_hi) of the caller's problem
@@ -57,12 +58,22 @@ struct gb_ba_graph {
 // ---- ba.cu ------------------------------------------------------------------------------------------------------------------
 // shard_world > 1: keep only the landmarks of `shard_rank` (contiguous range balanced by observation count) and their edges;
 // all cameras and the GLOBAL covisibility block structure are kept, so that every rank's reduced system has the same layout.
-int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out, bool use_arena, int shard_rank, int shard_world);
+int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out, bool use_arena, int shard_rank, int shard_world,
+                         const gb_pose_edges* pose_edges = nullptr);
 // one LM iteration in pieces, on the COMPACT reduced layout rbuf = [Sb | g~ | diag U | cost | pad] (g->rbuf_doubles doubles):
 int ba_reduce_local_compact(gb_ctx* ctx, gb_ba_graph* g, double* rbuf);           // sweep (if needed) + Schur blocks of the shard
 int ba_backsub_cost_compact(gb_ctx* ctx, gb_ba_graph* g, double* d_cost);         // back-substitution + candidate cost of the shard
 int ba_commit_compact(gb_ctx* ctx, gb_ba_graph* g, const double* rbuf, const double* d_cost);  // LM accept / reject + install
 int ba_read_result(gb_ctx* ctx, gb_ba_graph* g, gb_ba_result* res);               // one sync; fills res from the device scalars
+
+// ---- ba_pose.cu -------------------------------------------------------------------------------------------------------------
+// pose-graph terms (SE3Edge / GPSEdge, Optimizer.h:127-148) on the stepwise dense-layout solver path
+int ba_pose_validate(gb_ctx* ctx, const gb_ba_problem* pb, const gb_pose_edges* pe);
+int ba_pose_attach(gb_ctx* ctx, gb_ba_graph* g, const gb_pose_edges* pe);   // upload edges + gather plans (graph creation)
+void ba_pose_free(gb_ba_graph* g);
+int ba_pose_linearize(gb_ctx* ctx, gb_ba_graph* g, cudaStream_t s);         // after the sweep: records -> U, g_c, cost terms
+int ba_pose_offdiag(gb_ctx* ctx, gb_ba_graph* g, double* buf, cudaStream_t s);  // after the Schur complement: S_ij += J_i' Omega J_j
+int ba_pose_cost(gb_ctx* ctx, gb_ba_graph* g, cudaStream_t s);              // candidate cost terms at pose_new
 
 // ---- ba_sweep.cu ------------------------------------------------------------------------------------------------------------
 // the bandwidth-tuned residual + Jacobian sweep of large graphs (persistent CTAs, pose table in shared memory, bulk-copied W tiles)

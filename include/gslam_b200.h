@@ -272,6 +272,9 @@ typedef struct gb_ba_result {
 
 /* Host-buffer entry point (what libgslam_optimizer.so's optimize() binds): uploads, solves, writes poses/points back. */
 GB_API int gb_ba_solve(gb_ctx* ctx, gb_ba_problem* problem, const gb_ba_options* opt, gb_ba_result* result);
+/* The same for a BundleGraph that carries SE3 / GPS edges (BundleGraph::se3Graph / gpsGraph, Optimizer.h:163-168): a pose graph
+ * (n_points == n_obs == 0) or a bundle adjustment with pose-graph terms.  edges == NULL or empty == gb_ba_solve. */
+GB_API int gb_ba_solve_posegraph(gb_ctx* ctx, gb_ba_problem* problem, const gb_pose_edges* edges, const gb_ba_options* opt, gb_ba_result* result);
 
 /*
  * Pose-only refinement from 3D-2D matches (Optimizer::optimizePnP, Optimizer.h:202-207).
@@ -285,6 +288,8 @@ GB_API int gb_ba_pnp(gb_ctx* ctx, int n, const double* xyz, const double* xy1, d
 
 /* Device-resident graph: upload once (host-side ordering + H2D), solve many times from the same initial estimate. */
 GB_API int gb_ba_graph_create(gb_ctx* ctx, const gb_ba_problem* problem, gb_ba_graph** out);
+/* ... with pose-graph terms (`edges` may be NULL); such a graph runs the stepwise solver on the dense reduced camera system */
+GB_API int gb_ba_graph_create_ex(gb_ctx* ctx, const gb_ba_problem* problem, const gb_pose_edges* edges, gb_ba_graph** out);
 GB_API int gb_ba_graph_destroy(gb_ctx* ctx, gb_ba_graph* g);
 GB_API int gb_ba_graph_reset(gb_ctx* ctx, gb_ba_graph* g); /* restore the uploaded estimate (device-to-device) */
 GB_API int gb_ba_graph_solve(gb_ctx* ctx, gb_ba_graph* g, const gb_ba_options* opt, gb_ba_result* result);
