@@ -873,7 +873,7 @@ __global__ void __launch_bounds__(256) ba_prepare_schur_kernel(BaDev g, double* 
     buf[g.r_gt + n6 + d] = g.U[36 * (d / 6) + (d % 6) * 7];
   }
   const double lambda = g.sc->lambda;
-  const bool fresh = g.sc->need_linearize != 0;  // the sweep of this iteration already produced Vinv with this lambda
+  const bool fresh = g.sc->need_linearize != 0 && g.vinv_in_sweep != 0;  // the sweep of this iteration already produced Vinv with this lambda
   for (size_t j = t0; !fresh && j < (size_t)g.np; j += stride) {
     double Vi[9];
     const bool active = g.pfree[j] != 0 && g.pt_off[j + 1] > g.pt_off[j];
@@ -1966,6 +1966,7 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   const int e_lo = pt_off[lo], e_hi = pt_off[hi];
   const int np = hi - lo, no = e_hi - e_lo;
   d.nc = nc; d.np = np; d.no = no; d.n6 = 6 * nc; d.has_info = pb->obs_info ? 1 : 0;
+  d.vinv_in_sweep = 1;
   d.r_gt = (size_t)d.n6 * d.n6;  // dense layout unless a launch says otherwise (ba_reduce_local_compact / ba_commit_compact)
   g->buf_doubles = ba_buf_doubles(nc);
   // covisibility block structure of S over the WHOLE graph (every rank of a sharded solve must agree on the layout): block
@@ -2265,9 +2266,11 @@ static int ba_pcg_cluster(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
 // The residual + Jacobian sweep outside the local-BA launch chain: graphs with enough observations to fill the machine take the
 // bandwidth-tuned persistent kernel (ba_sweep.cu), small ones the latency-tuned one above.  which: 3 whole, 1 cameras, 2 landmarks.
 constexpr int kSweepLargeObs = 65536;
+static bool ba_sweep_is_large(const gb_ba_graph* g) {
+  return g->sweep_mode == 2 || (g->sweep_mode == 0 && g->d.no >= kSweepLargeObs && !getenv("GB_BA_SWEEP_OLD"));
+}
 static int ba_launch_sweep(gb_ctx* ctx, gb_ba_graph* g, const BaDev& d, cudaStream_t s, int which) {
-  const bool large = g->sweep_mode == 2 || (g->sweep_mode == 0 && d.no >= kSweepLargeObs && !getenv("GB_BA_SWEEP_OLD"));
-  if (large) return ba_sweep_launch(ctx, g, d, s, which);
+  if (ba_sweep_is_large(g)) return ba_sweep_launch(ctx, g, d, s, which);
   const int pt_blocks = (which & 2) ? gb_div_up(d.np * kLpp, kPtThreads) : 0, cam_blocks = (which & 1) ? d.nc * d.cam_split : 0;
   if (pt_blocks + cam_blocks > 0) { ba_linearize_kernel<<<pt_blocks + cam_blocks, kPtThreads, 0, s>>>(d, cam_blocks); GB_LAUNCH_CHECK(ctx); }
   return GB_OK;
@@ -2296,6 +2299,7 @@ int gb_ba_graph_reduce_local(gb_ctx* ctx, gb_ba_graph* g, double* buf) {
   BaDev& d = g->d;
   if (!buf) buf = g->buf;
   cudaStream_t s = ctx->stream;
+  d.vinv_in_sweep = ba_sweep_is_large(g) ? 0 : 1;
   GB_CHECK(ba_launch_sweep(ctx, g, d, s, 3));
   GB_CHECK(ba_pose_linearize(ctx, g, s));  // (pose-graph terms, if any: into U, g_c and the cost terms before they are consumed)
   // Schur complement.  With the covisibility block structure at hand (<= 1024 cameras) S is formed block by block without
@@ -2336,6 +2340,7 @@ int ba_reduce_local_compact(gb_ctx* ctx, gb_ba_graph* g, double* rbuf) {
   d.Sb = rbuf;
   d.r_gt = (size_t)d.s_nnzb * 36;
   cudaStream_t s = ctx->stream;
+  d.vinv_in_sweep = ba_sweep_is_large(g) ? 0 : 1;
   GB_CHECK(ba_launch_sweep(ctx, g, d, s, 3));
   {
     const int nblk = (int)std::min<size_t>(std::max<size_t>(((size_t)d.np + 255) / 256, 1), (size_t)ctx->sm_count * 8);

@@ -56,6 +56,7 @@ struct BaDev {
   const int *sp_coff, *sp_cidx;  // CSR over cameras: staging rows (chunk*16+local cam) contributing to g~
   // large-graph sweep (ba_sweep.cu): host-made item records (int4 each) dealt to sw_nteams teams, team k owns
   // [sw_team_off[k], sw_team_off[k+1])
+  int vinv_in_sweep;  // 1: the sweep wrote the damped V^-1 (ba.cu's kernel); 0: ba_prepare_schur_kernel forms it (ba_sweep.cu's does not)
   int sw_nteams, sw_nitems;
   const int* sw_items;
   const int* sw_team_off;

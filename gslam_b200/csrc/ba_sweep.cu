@@ -113,7 +113,7 @@ __device__ __forceinline__ void stage_fill(const BaDev& g, const SweepCtx& cx, d
 
 // ---- landmark item: landmarks [j0, j1), observations [e0, e1) in chunks of 128; chunk 0 is already staged in `st` ---------------
 template <bool POSE_SMEM>
-__device__ __forceinline__ void sweep_landmarks(const BaDev& g, const SweepCtx& cx, double* tm, double* st, int team, int t, int j0, int j1, int e0, int e1) {
+__device__ __noinline__ void sweep_landmarks(const BaDev& g, const SweepCtx cx, double* tm, double* st, int team, int t, int j0, int j1, int e0, int e1) {
   double* s_w = tm + kOffW;
   double* s_c = tm + kOffC;
   double* s_acc = tm + kOffAcc;
@@ -178,46 +178,41 @@ __device__ __forceinline__ void sweep_landmarks(const BaDev& g, const SweepCtx& 
     team_sync(team);
     const int nobs = min(kTeam, e1 - c0);
     if (t == 0 && nobs > 0) bulk_store(g.W + 18 * (size_t)c0, s_w, (uint32_t)nobs * 144u);
-    // per-landmark sums in ascending observation order: thread = (landmark l, term k)
+    // per-landmark sums: thread = (landmark l, term k); the observations of a landmark are added in ascending order, even and odd
+    // positions in two chains (fixed order, half the dependent latency).  The sums leave straight from the threads that made them:
+    // k = 0..5 the upper triangle of V_j (mirrored), 6..8 g_p,j, 9 cost_j.  (V^-1 is NOT formed here: ba_prepare_schur_kernel does it
+    // for every landmark in parallel -- BaDev::vinv_in_sweep = 0 -- instead of one lane per landmark behind a team barrier.)
+    const bool last = c0 + kTeam >= e1, first = c0 == e0;
     for (int it = t; it < L * 10; it += kTeam) {
       const int l = it / 10, k = it - l * 10;
       const int a = max(s_off[l], c0) - c0, b = min(s_off[l + 1], c0 + kTeam) - c0;
-      double s = (c0 == e0) ? 0.0 : s_acc[it];
       const double* col = s_c + k * kTeam;
-      for (int o = a; o < b; ++o) s += col[o];
-      s_acc[it] = s;
-    }
-  }
-  team_sync(team);
-  // V_j, g_p,j, cost_j, the damped inverse, and the installation of an accepted candidate point
-  if (t < L) {
-    const int l = t, j = j0 + l;
-    const double* a = s_acc + 10 * l;
-    double V[9] = {a[0], a[1], a[2], a[1], a[3], a[4], a[2], a[4], a[5]};
-    double* Vg = g.V + 9 * (size_t)j;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) Vg[k] = V[k];
-    g.gp[3 * (size_t)j] = a[6]; g.gp[3 * (size_t)j + 1] = a[7]; g.gp[3 * (size_t)j + 2] = a[8];
-    g.cost_pt[j] = a[9];
-    if (cx.pend) { g.pts[3 * (size_t)j] = s_pts[3 * l]; g.pts[3 * (size_t)j + 1] = s_pts[3 * l + 1]; g.pts[3 * (size_t)j + 2] = s_pts[3 * l + 2]; }
-    const double lambda = g.sc->lambda;
-    const bool active = s_pf[l] != 0 && s_off[l + 1] > s_off[l];
-    if (active) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) V[d * 4] += lambda * clampd(V[d * 4]);
-      if (!spd_inverse<3>(V)) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) V[k] = 0.0;
+      double s0 = 0.0, s1 = 0.0;
+      int o = a;
+      for (; o + 1 < b; o += 2) { s0 += col[o]; s1 += col[o + 1]; }
+      if (o < b) s0 += col[o];
+      double s = s0 + s1;
+      if (!first) s += s_acc[it];
+      if (!last) { s_acc[it] = s; continue; }
+      const int j = j0 + l;
+      if (k < 6) {
+        const int r = k < 3 ? 0 : (k < 5 ? 1 : 2), c = k < 3 ? k : (k < 5 ? k - 2 : 2);  // (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
+        double* Vg = g.V + 9 * (size_t)j;
+        Vg[r * 3 + c] = s;
+        if (r != c) Vg[c * 3 + r] = s;
+      } else if (k < 9) {
+        g.gp[3 * (size_t)j + (k - 6)] = s;
+        if (cx.pend) g.pts[3 * (size_t)j + (k - 6)] = s_pts[3 * l + (k - 6)];  // install the accepted candidate point
+      } else {
+        g.cost_pt[j] = s;
       }
     }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) g.Vinv[9 * (size_t)j + k] = active ? V[k] : 0.0;
   }
 }
 
 // ---- camera item: slice `slice` of camera i, observations [s0, s1) of the camera-sorted list -----------------------------------
 template <bool POSE_SMEM>
-__device__ __forceinline__ void sweep_camera(const BaDev& g, const SweepCtx& cx, double* tm, int team, int t, int i, int slice, int s0, int s1) {
+__device__ __noinline__ void sweep_camera(const BaDev& g, const SweepCtx cx, double* tm, int team, int t, int i, int slice, int s0, int s1) {
   const int K = g.cam_split;
   const int dm = cx.dof_tab[i];
   double Rt[12];
@@ -313,7 +308,7 @@ __device__ __forceinline__ void sweep_camera(const BaDev& g, const SweepCtx& cx,
 // item records (host plan): landmark group {j0, j1, e0, e1}; camera slice {-1 - camera, slice, s0, s1}
 // which: 3 = whole sweep, 1 = camera items only, 2 = landmark items only (timing experiments)
 template <bool POSE_SMEM>
-__global__ void __launch_bounds__(kSwThreads, 1) ba_sweep_kernel(BaDev g, int which) {
+__global__ void __launch_bounds__(kSwThreads, 1) ba_sweep_kernel(const __grid_constant__ BaDev g, int which) {
   extern __shared__ __align__(128) double sm[];
   if (g.sc->stop || !g.sc->need_linearize) return;
   const int team = threadIdx.x / kTeam, t = threadIdx.x % kTeam;

@@ -187,8 +187,8 @@ static int runBow(const std::string& dir, const char* in, const char* out) {
   std::shared_ptr<Vocabulary> ref = Vocabulary::create(imgs, k, L, (Vocabulary::WeightingType)hdr[6], (Vocabulary::ScoringType)hdr[7]);
   if (!ref) return 3;
   Svar made = mod["gslam"]["b200"]["vocabulary"](ref);
-  if (!made.is<std::shared_ptr<Vocabulary> >()) return 4;
-  std::shared_ptr<Vocabulary> dev = made.castAs<std::shared_ptr<Vocabulary> >();
+  std::shared_ptr<Vocabulary> dev;
+  try { dev = made.castAs<std::shared_ptr<Vocabulary> >(); } catch (...) { return 4; }  // (Svar holds shared_ptr<T> as a pointer holder of T, Svar.h:2834-2850)
   if (!dev || dev->size() != ref->size()) return 5;
   BowVector v0, v1, v2, v3;
   FeatureVector f0, f1;
