@@ -53,7 +53,9 @@ constexpr int kOffC = kOffW + kTeam * 18;              // [10][128]  per-observa
 constexpr int kOffAcc = kOffC + kTeam * 10;            // [32][10]   per-landmark sums of the group; camera fold result [27]
 constexpr int kOffStage = kOffAcc + kSwMaxPts * 10;    // [2] stages
 constexpr int kOffMisc = kOffStage + 2 * kStage;       // flag
-constexpr int kTeamDoubles = kOffMisc + 4;
+constexpr int kRecs = 32;                              // item records of the team kept in shared memory
+constexpr int kOffRec = kOffMisc + 4;                  // [32] int4
+constexpr int kTeamDoubles = kOffRec + 2 * kRecs;
 static_assert(kTeam * 28 >= 27 * kTeam, "camera fold scratch spans the W and contribution tiles");
 static_assert((kTeamDoubles % 2) == 0 && (kStage % 2) == 0, "16-byte alignment of the team regions and stages");
 constexpr int kOffPose = kTeams * kTeamDoubles;        // [nc][12] pose table, then [nc] dof bytes (POSE_SMEM)
@@ -113,7 +115,7 @@ __device__ __forceinline__ void stage_fill(const BaDev& g, const SweepCtx& cx, d
 
 // ---- landmark item: landmarks [j0, j1), observations [e0, e1) in chunks of 128; chunk 0 is already staged in `st` ---------------
 template <bool POSE_SMEM>
-__device__ __noinline__ void sweep_landmarks(const BaDev& g, const SweepCtx cx, double* tm, double* st, int team, int t, int j0, int j1, int e0, int e1) {
+__device__ __forceinline__ void sweep_landmarks(const BaDev& g, const SweepCtx& cx, double* tm, double* st, int team, int t, int j0, int j1, int e0, int e1) {
   double* s_w = tm + kOffW;
   double* s_c = tm + kOffC;
   double* s_acc = tm + kOffAcc;
@@ -212,7 +214,7 @@ __device__ __noinline__ void sweep_landmarks(const BaDev& g, const SweepCtx cx, 
 
 // ---- camera item: slice `slice` of camera i, observations [s0, s1) of the camera-sorted list -----------------------------------
 template <bool POSE_SMEM>
-__device__ __noinline__ void sweep_camera(const BaDev& g, const SweepCtx cx, double* tm, int team, int t, int i, int slice, int s0, int s1) {
+__device__ __forceinline__ void sweep_camera(const BaDev& g, const SweepCtx& cx, double* tm, int team, int t, int i, int slice, int s0, int s1) {
   const int K = g.cam_split;
   const int dm = cx.dof_tab[i];
   double Rt[12];
@@ -224,22 +226,28 @@ __device__ __noinline__ void sweep_camera(const BaDev& g, const SweepCtx cx, dou
   double acc[27];
 #pragma unroll
   for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+  // software pipeline over the camera's (camera-sorted) observations: the landmark INDEX is fetched two iterations ahead, the
+  // measurement and the landmark coordinates one iteration ahead, so that neither the index -> address dependency nor the gather
+  // latency sits in the iteration that consumes them
   int idx = s0 + t;
   double2 uv = make_double2(0.0, 0.0);
   double p[3] = {0.0, 0.0, 0.0};
+  int j_nx = 0;
   if (idx < s1) {
     const int j = g.c_pt[idx];
     uv = *reinterpret_cast<const double2*>(g.c_uv + 2 * (size_t)idx);
+    if (idx + kTeam < s1) j_nx = g.c_pt[idx + kTeam];
     p[0] = cx.PTS[3 * (size_t)j]; p[1] = cx.PTS[3 * (size_t)j + 1]; p[2] = cx.PTS[3 * (size_t)j + 2];
   }
   while (idx < s1) {
     const int nx = idx + kTeam;
     double2 uv_n = make_double2(0.0, 0.0);
     double pn[3] = {0.0, 0.0, 0.0};
+    int j_nx2 = 0;
     if (nx < s1) {
-      const int jn = g.c_pt[nx];
       uv_n = *reinterpret_cast<const double2*>(g.c_uv + 2 * (size_t)nx);
-      pn[0] = cx.PTS[3 * (size_t)jn]; pn[1] = cx.PTS[3 * (size_t)jn + 1]; pn[2] = cx.PTS[3 * (size_t)jn + 2];
+      pn[0] = cx.PTS[3 * (size_t)j_nx]; pn[1] = cx.PTS[3 * (size_t)j_nx + 1]; pn[2] = cx.PTS[3 * (size_t)j_nx + 2];
+      if (nx + kTeam < s1) j_nx2 = g.c_pt[nx + kTeam];
     }
     const ObsLin o = eval_obs(Rt, p, uv.x, uv.y, g.has_info ? g.o_info + 3 * (size_t)g.cam_perm[idx] : nullptr, cx.delta);
     if (o.valid) {
@@ -260,7 +268,7 @@ __device__ __noinline__ void sweep_camera(const BaDev& g, const SweepCtx cx, dou
 #pragma unroll
       for (int a = 0; a < 6; ++a) acc[21 + a] -= Jc[a] * Ar0 + Jc[6 + a] * Ar1;
     }
-    idx = nx; uv = uv_n; p[0] = pn[0]; p[1] = pn[1]; p[2] = pn[2];
+    idx = nx; uv = uv_n; p[0] = pn[0]; p[1] = pn[1]; p[2] = pn[2]; j_nx = j_nx2;
   }
   // fixed-order fold: term-major scratch [27][128]; warp w folds terms w, w+4, ...: four strided entries per lane in order, then a
   // fixed shuffle tree
@@ -308,7 +316,7 @@ __device__ __noinline__ void sweep_camera(const BaDev& g, const SweepCtx cx, dou
 // item records (host plan): landmark group {j0, j1, e0, e1}; camera slice {-1 - camera, slice, s0, s1}
 // which: 3 = whole sweep, 1 = camera items only, 2 = landmark items only (timing experiments)
 template <bool POSE_SMEM>
-__global__ void __launch_bounds__(kSwThreads, 1) ba_sweep_kernel(const __grid_constant__ BaDev g, int which) {
+__global__ void __launch_bounds__(kSwThreads, 1) ba_sweep_kernel(BaDev g, int which) {
   extern __shared__ __align__(128) double sm[];
   if (g.sc->stop || !g.sc->need_linearize) return;
   const int team = threadIdx.x / kTeam, t = threadIdx.x % kTeam;
@@ -333,22 +341,30 @@ __global__ void __launch_bounds__(kSwThreads, 1) ba_sweep_kernel(const __grid_co
   const int gteam = blockIdx.x * kTeams + team;
   const int n0 = g.sw_team_off[gteam], n1 = g.sw_team_off[gteam + 1];
   const int4* items = reinterpret_cast<const int4*>(g.sw_items);
-  const int4 none = make_int4(0, 0, 0, 0);
+  // the team's item records: the first kRecs of them into shared memory once (a team gets ~15), the rest (if any) from global memory
+  int4* s_rec = reinterpret_cast<int4*>(tm + kOffRec);
+  if (t < min(n1 - n0, kRecs)) s_rec[t] = items[n0 + t];
+  team_sync(team);
+  auto record = [&](int n) -> int4 { return n - n0 < kRecs ? s_rec[n - n0] : items[n]; };
   auto wanted = [&](const int4& r) { return r.x < 0 ? (which & 1) != 0 : (which & 2) != 0; };
-  int4 rec0 = n0 < n1 ? items[n0] : none, rec1 = n0 + 1 < n1 ? items[n0 + 1] : none;
-  if (n0 < n1 && rec0.x >= 0 && wanted(rec0)) stage_fill(g, cx, tm + kOffStage, t, rec0.x, rec0.y, rec0.z, rec0.w, true);
+  if (n0 < n1) {
+    const int4 r = record(n0);
+    if (r.x >= 0 && wanted(r)) stage_fill(g, cx, tm + kOffStage, t, r.x, r.y, r.z, r.w, true);
+  }
   for (int n = n0; n < n1; ++n) {
-    const int4 rec2 = n + 2 < n1 ? items[n + 2] : none;  // in flight while this item is worked on
-    cp_async_wait_all();                                  // this thread's share of item n's stage
-    if (t == 0) bulk_wait_read();                         // the W tile of the previous landmark item has left
+    cp_async_wait_all();           // this thread's share of item n's stage
+    if (t == 0) bulk_wait_read();  // the W tile of the previous landmark item has left
     team_sync(team);
     double* st = tm + kOffStage + ((n - n0) & 1) * kStage;
-    if (n + 1 < n1 && rec1.x >= 0 && wanted(rec1)) stage_fill(g, cx, tm + kOffStage + ((n + 1 - n0) & 1) * kStage, t, rec1.x, rec1.y, rec1.z, rec1.w, true);
-    if (wanted(rec0)) {
-      if (rec0.x < 0) sweep_camera<POSE_SMEM>(g, cx, tm, team, t, -1 - rec0.x, rec0.y, rec0.z, rec0.w);
-      else sweep_landmarks<POSE_SMEM>(g, cx, tm, st, team, t, rec0.x, rec0.y, rec0.z, rec0.w);
+    if (n + 1 < n1) {
+      const int4 r = record(n + 1);
+      if (r.x >= 0 && wanted(r)) stage_fill(g, cx, tm + kOffStage + ((n + 1 - n0) & 1) * kStage, t, r.x, r.y, r.z, r.w, true);
     }
-    rec0 = rec1; rec1 = rec2;
+    const int4 rec = record(n);
+    if (wanted(rec)) {
+      if (rec.x < 0) sweep_camera<POSE_SMEM>(g, cx, tm, team, t, -1 - rec.x, rec.y, rec.z, rec.w);
+      else sweep_landmarks<POSE_SMEM>(g, cx, tm, st, team, t, rec.x, rec.y, rec.z, rec.w);
+    }
   }
   cp_async_wait_all();
   if (t == 0) bulk_wait_all();

@@ -53,6 +53,12 @@ static int runBA(const std::string& dir, const char* in, const char* out, bool p
   rd(f, pose.data(), pose.size()); rd(f, dof.data(), dof.size()); rd(f, pts.data(), pts.size()); rd(f, pf.data(), pf.size());
   rd(f, oc.data(), oc.size()); rd(f, op.data(), op.size()); rd(f, xyz.data(), xyz.size());
   if (has_info) rd(f, info.data(), info.size());
+  // optional pose-graph terms (Optimizer.h:127-148): hdr[5] SE3 edges, hdr[6] GPS edges, hdr[7] != 0: 6x6 information matrices follow
+  const int nse = hdr[5], ngps = hdr[6], pinfo = hdr[7];
+  std::vector<int32_t> sa(nse), sb(nse), gf(ngps);
+  std::vector<double> sm(7 * (size_t)nse), si(pinfo ? 36 * (size_t)nse : 0), gm(7 * (size_t)ngps), gi(pinfo ? 36 * (size_t)ngps : 0);
+  rd(f, sa.data(), sa.size()); rd(f, sb.data(), sb.size()); rd(f, sm.data(), sm.size()); rd(f, si.data(), si.size());
+  rd(f, gf.data(), gf.size()); rd(f, gm.data(), gm.size()); rd(f, gi.data(), gi.size());
   bool ok;
   std::ofstream o(out, std::ios::binary);
   if (pnp) {
@@ -78,6 +84,19 @@ static int runBA(const std::string& dir, const char* in, const char* out, bool p
     BundleEdge& e = g.mappointObserves[k];
     e.pointId = op[k]; e.frameId = oc[k]; e.measurement = CameraAnchor(xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2]);
     e.information = has_info ? &info[4 * (size_t)k] : NULL;
+  }
+  g.se3Graph.resize(nse); g.gpsGraph.resize(ngps);
+  for (int k = 0; k < nse; ++k) {
+    const double* p = &sm[7 * (size_t)k];
+    g.se3Graph[k].firstId = sa[k]; g.se3Graph[k].secondId = sb[k];
+    g.se3Graph[k].measurement = SE3(SO3(p[0], p[1], p[2], p[3]), Point3d(p[4], p[5], p[6]));
+    g.se3Graph[k].information = pinfo ? &si[36 * (size_t)k] : NULL;
+  }
+  for (int k = 0; k < ngps; ++k) {
+    const double* p = &gm[7 * (size_t)k];
+    g.gpsGraph[k].frameId = gf[k];
+    g.gpsGraph[k].measurement = SE3(SO3(p[0], p[1], p[2], p[3]), Point3d(p[4], p[5], p[6]));
+    g.gpsGraph[k].information = pinfo ? &gi[36 * (size_t)k] : NULL;
   }
   g.cameraDOF = UPDATE_CAMERA_NONE;
   ok = opt->optimize(g);

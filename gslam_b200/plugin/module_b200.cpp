@@ -19,6 +19,7 @@
 #include <GSLAM/core/Undistorter.h>
 #include <GSLAM/core/Vocabulary.h>
 
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -121,7 +122,11 @@ class B200Vocabulary : public GSLAM::Vocabulary {
     if (m_nodeDescriptors.cols != 32 || m_nodeDescriptors.elemSize() != 1 || m_k > 32) return false;
     v.clear(); fv.clear();
     if (empty() || features.rows <= 0) return true;
-    if (features.cols != 32 || features.elemSize() != 1) { LOG(ERROR) << "gslam_b200 vocabulary: features must be N x 32 8UC1"; return true; }
+    if (features.cols != 32 || features.elemSize() != 1) {
+      LOG(ERROR) << "gslam_b200 vocabulary: features must be N x 32 8UC1";
+      fprintf(stderr, "gslam_b200 vocabulary: features must be N x 32 8UC1 (got %d cols, elemSize %d)\n", features.cols, (int)features.elemSize());
+      return true;
+    }
     std::lock_guard<std::mutex> lk(mu_);
     if (!dev_) {
       ctx_ = shared().get();
@@ -132,6 +137,7 @@ class B200Vocabulary : public GSLAM::Vocabulary {
       if (gb_voc_create(ctx_, m_k, m_L, (int)m_weighting, (int)m_scoring, (uint32_t)m_nodes.size(), child.data(), weight.data(), m_nodeDescriptors.data,
                         &dev_) != GB_OK) {
         LOG(ERROR) << "gslam_b200 vocabulary: " << gb_last_error(ctx_);
+        fprintf(stderr, "gslam_b200 vocabulary: %s\n", gb_last_error(ctx_));
         dev_ = nullptr;
         return true;
       }
@@ -141,6 +147,7 @@ class B200Vocabulary : public GSLAM::Vocabulary {
     int nw = 0, m = 0;
     if (gb_bow_transform(ctx_, dev_, features.data, n, levelsup, words_.data(), values_.data(), &nw, fv_node_.data(), fv_feat_.data(), &m) != GB_OK) {
       LOG(ERROR) << "gslam_b200 vocabulary: " << gb_last_error(ctx_);
+      fprintf(stderr, "gslam_b200 vocabulary: %s\n", gb_last_error(ctx_));
       return true;
     }
     for (int i = 0; i < nw; ++i) v.insert(v.end(), GSLAM::BowVector::value_type((GSLAM::WordId)words_[i], values_[i]));

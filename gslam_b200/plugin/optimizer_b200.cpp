@@ -33,12 +33,12 @@ class OptimizerB200 : public GSLAM::Optimizer {
     if (ctx_) gb_ctx_destroy(ctx_);
   }
 
-  // MAPPING: bundle adjustment over BundleGraph::keyframes / mappoints / mappointObserves (Optimizer.h:150-172,229)
+  // MAPPING: bundle adjustment over BundleGraph::keyframes / mappoints / mappointObserves, pose-graph terms se3Graph / gpsGraph --
+  // BUNDLEADJUST and POSEGRAPH of Optimizer.h:227-229 (graph PODs :106-172)
   bool optimize(GSLAM::BundleGraph& graph) override {
     try {
-      if (!graph.invDepths.empty() || !graph.invDepthObserves.empty() || !graph.se3Graph.empty() || !graph.sim3Graph.empty() ||
-          !graph.gpsGraph.empty()) {
-        LOG(ERROR) << "gslam_b200 optimizer: inverse-depth / pose-graph / GPS edges are not implemented (SURVEY.md §8f)";
+      if (!graph.invDepths.empty() || !graph.invDepthObserves.empty() || !graph.sim3Graph.empty()) {
+        LOG(ERROR) << "gslam_b200 optimizer: inverse-depth landmarks and SIM3 edges are not implemented (SURVEY.md §8f-3)";
         return false;
       }
       if (graph.camera.isValid() && graph.cameraDOF != GSLAM::UPDATE_CAMERA_NONE) {
@@ -109,12 +109,50 @@ class OptimizerB200 : public GSLAM::Optimizer {
       pb.n_cams = (int32_t)nc; pb.n_points = (int32_t)np; pb.n_obs = (int32_t)no;
       pb.cam_pose_wc = pose.data(); pb.cam_dof = dof.data(); pb.points = pts.data(); pb.point_free = pfree.data();
       pb.obs_cam = oc.data(); pb.obs_point = op.data(); pb.obs_xyz = xyz.data(); pb.obs_info = any_info ? info.data() : NULL;
+      // pose-graph terms: SE3Edge {firstId, secondId, SE3_12, information 6x6} and GPSEdge {frameId, SE3_gps, information 6x6}
+      // (Optimizer.h:127-148) -> gb_pose_edges; a NULL information is the identity, a mix of NULL and non-NULL is filled in
+      const size_t nse = graph.se3Graph.size(), ngps = graph.gpsGraph.size();
+      std::vector<int32_t> se_a(nse), se_b(nse), gps_f(ngps);
+      std::vector<double> se_m(7 * nse), gps_m(7 * ngps), se_i, gps_i;
+      auto put7 = [](const GSLAM::SE3& T, double* p) {
+        const GSLAM::SO3& r = T.get_rotation();
+        const GSLAM::Point3d& t = T.get_translation();
+        p[0] = r.x; p[1] = r.y; p[2] = r.z; p[3] = r.w; p[4] = t.x; p[5] = t.y; p[6] = t.z;
+      };
+      auto put36 = [](const double* info, double* dst) {
+        for (int k = 0; k < 36; ++k) dst[k] = info ? info[k] : ((k % 7) == 0 ? 1.0 : 0.0);
+      };
+      bool se_info = false, gps_info = false;
+      for (size_t k = 0; k < nse; ++k) se_info |= graph.se3Graph[k].information != NULL;
+      for (size_t k = 0; k < ngps; ++k) gps_info |= graph.gpsGraph[k].information != NULL;
+      if (se_info) se_i.resize(36 * nse);
+      if (gps_info) gps_i.resize(36 * ngps);
+      for (size_t k = 0; k < nse; ++k) {
+        const GSLAM::SE3Edge& e = graph.se3Graph[k];
+        if (e.firstId >= nc || e.secondId >= nc) { LOG(ERROR) << "gslam_b200 optimizer: SE3 edge " << k << " references a missing keyframe"; return false; }
+        se_a[k] = (int32_t)e.firstId; se_b[k] = (int32_t)e.secondId;
+        put7(e.measurement, &se_m[7 * k]);
+        if (se_info) put36(e.information, &se_i[36 * k]);
+      }
+      for (size_t k = 0; k < ngps; ++k) {
+        const GSLAM::GPSEdge& e = graph.gpsGraph[k];
+        if (e.frameId >= nc) { LOG(ERROR) << "gslam_b200 optimizer: GPS edge " << k << " references a missing keyframe"; return false; }
+        gps_f[k] = (int32_t)e.frameId;
+        put7(e.measurement, &gps_m[7 * k]);
+        if (gps_info) put36(e.information, &gps_i[36 * k]);
+      }
+      gb_pose_edges pe;
+      std::memset(&pe, 0, sizeof pe);
+      pe.n_se3 = (int32_t)nse; pe.se3_first = se_a.data(); pe.se3_second = se_b.data(); pe.se3_meas = se_m.data(); pe.se3_info = se_info ? se_i.data() : NULL;
+      pe.n_gps = (int32_t)ngps; pe.gps_frame = gps_f.data(); pe.gps_meas = gps_m.data(); pe.gps_info = gps_info ? gps_i.data() : NULL;
       gb_ba_options opt = options();
       gb_ba_result res;
       // global-BA-sized graphs on several GPUs when the svar option `b200.devices` (e.g. "0,1,2,3") names more than one device:
       // landmark-sharded solve, one NCCL all-reduce of the reduced camera system per LM iteration (gb_ba_solve_multi)
       int rc;
-      if (no >= (size_t)svar.GetInt("b200.multi_min_obs", 200000) && ensureMulti())
+      if (nse + ngps > 0)
+        rc = gb_ba_solve_posegraph(ctx_, &pb, &pe, &opt, &res);
+      else if (no >= (size_t)svar.GetInt("b200.multi_min_obs", 200000) && ensureMulti())
         rc = gb_ba_solve_multi((int)comms_.size(), comms_.data(), &pb, &opt, &res);
       else
         rc = gb_ba_solve(ctx_, &pb, &opt, &res);

@@ -19,15 +19,26 @@ needs_plugins = pytest.mark.skipif(not all(os.path.exists(os.path.join(LIB, f)) 
                                    reason="plugins not built (they need the reference headers: built in the build container)")
 
 
-def write_ba(path, pb, iters, ftol):
+def write_ba(path, pb, iters, ftol, edges=None):
     with open(path, "wb") as f:
-        f.write(struct.pack("<8i", pb.n_cams, pb.n_points, pb.n_obs, iters, 0 if pb.obs_info is None else 1, 0, 0, 0))
+        nse = 0 if edges is None else edges.n_se3; ngps = 0 if edges is None else edges.n_gps
+        pinfo = 0 if edges is None or edges.se3_info is None else 1
+        f.write(struct.pack("<8i", pb.n_cams, pb.n_points, pb.n_obs, iters, 0 if pb.obs_info is None else 1, nse, ngps, pinfo))
         f.write(struct.pack("<d", ftol))
         for a, dt in ((pb.cam_pose_wc, np.float64), (pb.cam_dof, np.uint8), (pb.points, np.float64), (pb.point_free, np.uint8),
                       (pb.obs_cam, np.int32), (pb.obs_point, np.int32), (pb.obs_xyz, np.float64)):
             f.write(np.ascontiguousarray(a, dt).tobytes())
         if pb.obs_info is not None:
             f.write(np.ascontiguousarray(pb.obs_info, np.float64).tobytes())
+        if edges is not None:
+            for a, dt in ((edges.se3_first, np.int32), (edges.se3_second, np.int32), (edges.se3_meas, np.float64)):
+                f.write(np.ascontiguousarray(a, dt).tobytes())
+            if pinfo:
+                f.write(np.ascontiguousarray(edges.se3_info, np.float64).tobytes())
+            for a, dt in ((edges.gps_frame, np.int32), (edges.gps_meas, np.float64)):
+                f.write(np.ascontiguousarray(a, dt).tobytes())
+            if pinfo:
+                f.write(np.ascontiguousarray(edges.gps_info, np.float64).tobytes())
 
 
 def run(mode, inp, out, *svar_settings):
@@ -306,3 +317,29 @@ def test_vocabulary_from_the_module_equals_the_reference_vocabulary_in_process(t
     words = np.frombuffer(raw[32:32 + 8 * nw], np.uint64); values = np.frombuffer(raw[32 + 8 * nw:32 + 12 * nw], np.float32)
     assert np.all(np.diff(words.astype(np.int64)) > 0) and np.all(values > 0)
     print(f"bow transform of {nq} descriptors: reference {us_ref} us, plugin {us_dev} us")
+
+
+@needs_plugins
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw,ekw", [(dict(n_cams=20, n_points=300, obs_per_point=4, n_fixed=2, seed=3), dict(seed=1, n_loops=5, gps_every=4, with_info=True)),
+                                    (dict(n_cams=40, n_points=0, n_fixed=1, seed=7, pose_sigma_t=0.05, pose_sigma_deg=0.5), dict(seed=2, n_loops=12, gps_every=0, with_info=False))])
+def test_pose_graph_edges_through_reference_api(kw, ekw):
+    """BundleGraph::se3Graph / gpsGraph (Optimizer.h:163-168) through GSLAM::Optimizer::create()->optimize(BundleGraph&): a bundle
+    adjustment with odometry / loop-closure / GPS terms and a pure POSEGRAPH, against the oracle after the same iteration counts."""
+    pb = synth.synth_ba(**kw)
+    pe = synth.synth_pose_edges(pb, **ekw)
+    want = pb.copy()
+    r0 = oracle.ba_solve(want, pe, max_iterations=8, function_tolerance=0.0)
+    with tempfile.TemporaryDirectory() as d:
+        write_ba(os.path.join(d, "in.bin"), pb, 8, 0.0, pe)
+        r = run("ba", os.path.join(d, "in.bin"), os.path.join(d, "out.bin"))
+        assert r.returncode == 0, r.stderr
+        raw = open(os.path.join(d, "out.bin"), "rb").read()
+    assert struct.unpack("<i", raw[:4])[0] == 1
+    poses = np.frombuffer(raw[4:4 + 64 * pb.n_cams], np.float64).reshape(-1, 8)
+    sgn = np.sign(np.sum(poses[:, :4] * want.cam_pose_wc[:, :4], axis=1))[:, None]
+    assert np.abs(poses[:, :4] * sgn - want.cam_pose_wc[:, :4]).max() < 1e-5
+    assert np.abs(poses[:, 4:7] - want.cam_pose_wc[:, 4:]).max() < 1e-5 * max(1.0, np.abs(want.cam_pose_wc[:, 4:]).max())
+    assert r0.final_cost < r0.initial_cost
+    moved = np.abs(poses[:, 4:7] - pb.cam_pose_wc[:, 4:]).max()
+    assert moved > 1e-4        # the graph was really optimised

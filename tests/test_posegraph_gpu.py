@@ -64,9 +64,12 @@ def test_solve_matches_oracle(ctx, name):
     pbk, pek = CASES[name]
     pb = synth.synth_ba(**pbk); pe = synth.synth_pose_edges(pb, **pek)
     a = pb.copy(); b = pb.copy()
-    kw = dict(max_iterations=12, function_tolerance=0.0, pcg_max_iters=600, pcg_tol=1e-13)
+    # (a pose graph converges to rounding level within a few iterations; beyond that accept / reject is decided by the last bit of
+    #  the cost on either side, so the trajectories are compared while the cost still moves)
+    iters = 12 if pb.n_points else 4
+    kw = dict(max_iterations=iters, function_tolerance=0.0, pcg_max_iters=600, pcg_tol=1e-13)
     r0 = O.ba_solve(a, pe, **kw)
-    r1 = ctx.ba_solve_posegraph(b, pe, cfg(maxIterations=12, functionTolerance=0.0, pcgMaxIterations=600, pcgTolerance=1e-13))
+    r1 = ctx.ba_solve_posegraph(b, pe, cfg(maxIterations=iters, functionTolerance=0.0, pcgMaxIterations=600, pcgTolerance=1e-13))
     assert r1.iterations == r0.iterations and r1.accepted == r0.accepted
     assert abs(r1.initial_cost - r0.initial_cost) <= 1e-11 * r0.initial_cost
     assert abs(r1.final_cost - r0.final_cost) <= RTOL * r0.final_cost
