@@ -438,6 +438,54 @@ def main():
                "scaling": "weak (frames shard over the ranks, no collective)", "n_gpus": world, "pnp_inliers": pnp_inliers[0],
                "note": "single stream per rank; device-resident stereo pairs; BASELINE.json configs[3]"}
 
+    # ---- bag-of-words transform (published CPU figure 615.5 us, doc/doxygen/4_2_tools.dox:43 "Trans ORB-4"):
+    #      GSLAM::Vocabulary::transform(features, BowVector&, FeatureVector&, levelsup) of the frame's 2000 descriptors on a k = 10,
+    #      L = 5 vocabulary (111 111 nodes, 3.6 MB of node descriptors), through the host-buffer C-ABI (descriptors in, maps out) and
+    #      chained on the device after the extraction.  Rank 0 only.
+    bow = None
+    if rank == 0:
+        from gslam_b200.api import Vocabulary
+        vt = synth.synth_vocabulary(10, 5, seed=1)
+        dv = Vocabulary(ctx, vt.k, vt.L, vt.weighting, vt.scoring, vt.child_num, vt.weight, vt.desc)
+        rngb = np.random.default_rng(0)
+        fb = np.ascontiguousarray(vt.desc[rngb.integers(1, vt.n_nodes, NKP)] ^ np.packbits(rngb.random((NKP, 256)) < 0.05, axis=1))
+        for _ in range(5):
+            dv.transform(fb, 2)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            out_b = dv.transform(fb, 2)
+        bow_host_us = (time.perf_counter() - t0) / 200 * 1e6
+        fcur = feats[0]
+        fcur.extract(ring[0].data_ptr(), W, H, cfg, device_ptr=True, pitch=W)
+        for _ in range(3):
+            dv.transform(fcur, 2)
+        t0 = time.perf_counter()
+        for _ in range(100):
+            dv.transform(fcur, 2)
+        bow_dev_us = (time.perf_counter() - t0) / 100 * 1e6
+        bow = {"workload": f"{NKP} ORB descriptors -> BowVector + FeatureVector (levelsup 2), vocabulary k=10 L=5 ({vt.n_nodes} nodes), TF_IDF / L1",
+               "us_per_transform_host_buffers": bow_host_us, "us_per_transform_device_resident_descriptors": bow_dev_us,
+               "words": int(out_b["words"].shape[0]), "published_cpu_us": 615.5,
+               "note": "wall clock of the Python call around gb_bow_transform (ctypes + numpy allocation of the outputs included); "
+                       "outputs are the reference's std::map contents in map order"}
+        try:
+            import oracle
+            from oracle import oracle as O
+            va = O.VocabularyArrays(vt.k, vt.L, vt.weighting, vt.scoring, vt.child_num, vt.weight, vt.desc)
+            if oracle.have_ref():
+                R = O.RefVocabulary.from_arrays(va)
+                bow["cpu_reference_us"] = R.transform(fb, 2, repeat=20)["seconds"] * 1e6
+                bow["cpu_reference_kind"] = "reference (GSLAM::Vocabulary::transform compiled from the reference headers, oracle/_ref, 1 thread)"
+                R.close()
+            else:
+                t0 = time.perf_counter(); O.bow_transform(va, fb, 2); bow["cpu_reference_us"] = (time.perf_counter() - t0) * 1e6
+                bow["cpu_reference_kind"] = "port (oracle/bow_ref.c, 1 thread)"
+            want_b = O.bow_transform(va, fb, 2)
+            bow["parity"] = bool(all(np.array_equal(out_b[k], want_b[k]) for k in ("words", "values", "fv_node", "fv_feat")))
+        except Exception as e:  # the GPU numbers stand on their own
+            bow["cpu_reference_error"] = repr(e)
+        dv.close()
+
     # ---- end to end through the host-buffer C-ABI, PAGEABLE frames, tracking thread || mapping thread ---------------------------
     pageable = [np.array(base[k], copy=True) for k in range(8)]           # malloc'd, like GImage (GImage.h:394-402)
     pinned_t = [torch.from_numpy(base[k]).pin_memory() for k in range(8)]
@@ -539,7 +587,7 @@ def main():
                                        "note": "linear_solver=1 (exact block-skyline Cholesky, csrc/ba_chol.cu) on the same window and LM iteration count; "
                                                "not the timed configuration"},
             # dominant HBM-bound kernel of the path = the BA Jacobian sweep (BASELINE metric, 2nd clause), at config-5 size
-            "roofline": {"kernel": "BA Jacobian sweep K6 (ba_linearize_kernel: camera pass + landmark pass in one launch), 500 cams/100k pts/1M obs",
+            "roofline": {"kernel": "BA Jacobian sweep K6 (ba_sweep_kernel: camera items + landmark items in one persistent launch), 500 cams/100k pts/1M obs",
                          "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
                          "frac_on_measured_dram_bytes": (traffic / (t_sweep_big * 1e-3) / 1e9) / peak if traffic else None,
@@ -558,6 +606,7 @@ def main():
                                         "frac": (8 * NKP * NKP / (t_match * 1e-3)) / popc_peak if popc_peak else None}},
             }
     line["config4_stereo"] = config4
+    line["bow_transform"] = bow
     if global_ba is not None:
         line["global_ba"] = global_ba
     # CPU baseline on a bounded sample, rank 0 only, N=1 only

@@ -189,11 +189,15 @@ __device__ __forceinline__ void sweep_landmarks(const BaDev& g, const SweepCtx& 
       const int l = it / 10, k = it - l * 10;
       const int a = max(s_off[l], c0) - c0, b = min(s_off[l + 1], c0 + kTeam) - c0;
       const double* col = s_c + k * kTeam;
-      double s0 = 0.0, s1 = 0.0;
-      int o = a;
-      for (; o + 1 < b; o += 2) { s0 += col[o]; s1 += col[o + 1]; }
-      if (o < b) s0 += col[o];
-      double s = s0 + s1;
+      // eight observations at a time: the loads leave together (zero for positions past the landmark's end), the adds form a fixed
+      // three-level tree -- one shared-memory latency and three add latencies per batch instead of eight dependent ones
+      double s = 0.0;
+      for (int o = a; o < b; o += 8) {
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = o + q < b ? col[o + q] : 0.0;
+        s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+      }
       if (!first) s += s_acc[it];
       if (!last) { s_acc[it] = s; continue; }
       const int j = j0 + l;
@@ -217,8 +221,10 @@ template <bool POSE_SMEM>
 __device__ __forceinline__ void sweep_camera(const BaDev& g, const SweepCtx& cx, double* tm, int team, int t, int i, int slice, int s0, int s1) {
   const int K = g.cam_split;
   const int dm = cx.dof_tab[i];
-  double Rt[12];
-  load_rt<POSE_SMEM>(cx.pose_tab, i, Rt);
+  // (the camera's pose stays in the shared-memory table: broadcast LDS per use instead of 24 registers next to the 54 of the sums)
+  double Rt_reg[12];
+  if (!POSE_SMEM) load_rt<false>(cx.pose_tab, i, Rt_reg);
+  const double* Rt = POSE_SMEM ? cx.pose_tab + 12 * (size_t)i : Rt_reg;
   if (cx.pend && slice == 0) {  // install this camera's accepted pose
     if (t < 12) g.Rt[12 * i + t] = g.Rt_new[12 * i + t];
     else if (t >= 32 && t < 39) g.pose[7 * i + t - 32] = g.pose_new[7 * i + t - 32];
@@ -249,7 +255,9 @@ __device__ __forceinline__ void sweep_camera(const BaDev& g, const SweepCtx& cx,
       pn[0] = cx.PTS[3 * (size_t)j_nx]; pn[1] = cx.PTS[3 * (size_t)j_nx + 1]; pn[2] = cx.PTS[3 * (size_t)j_nx + 2];
       if (nx + kTeam < s1) j_nx2 = g.c_pt[nx + kTeam];
     }
-    const ObsLin o = eval_obs(Rt, p, uv.x, uv.y, g.has_info ? g.o_info + 3 * (size_t)g.cam_perm[idx] : nullptr, cx.delta);
+    const double* Rt_it = Rt;
+    if (POSE_SMEM) asm volatile("" : "+l"(Rt_it));  // (opaque per iteration: keeps the pose loads in the loop instead of 24 live registers)
+    const ObsLin o = eval_obs(Rt_it, p, uv.x, uv.y, g.has_info ? g.o_info + 3 * (size_t)g.cam_perm[idx] : nullptr, cx.delta);
     if (o.valid) {
       double Jc[12], AJc[12];
       jac_cam(o, dm, Jc);

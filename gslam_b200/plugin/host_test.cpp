@@ -224,7 +224,7 @@ static int runBow(const std::string& dir, const char* in, const char* out) {
   ref->transform(q.row(0), w0, a0);
   dev->transform(q.row(0), w1, a1);
   if (w0 != w1 || a0 != a1 || dev->getWordWeight(w1) != ref->getWordWeight(w0) || dev->getEffectiveLevels() != ref->getEffectiveLevels()) return 6;
-  if (v1.empty()) return 7;
+  if (v1.empty()) { fprintf(stderr, "bow: reference %zu words, plugin %zu words, vocabulary %u words, %d query rows x %d cols\n", v0.size(), v1.size(), dev->size(), q.rows, q.cols); return 7; }
   std::ofstream o(out, std::ios::binary);
   int32_t oh[8] = {v0 == v1, f0 == f1, v2 == v3, (int32_t)v1.size(), (int32_t)f1.size(),
                    (int32_t)(std::chrono::duration<double>(t1 - t0).count() / 20 * 1e6), (int32_t)(std::chrono::duration<double>(t2 - t1).count() / 20 * 1e6), 0};

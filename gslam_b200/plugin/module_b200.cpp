@@ -20,6 +20,7 @@
 #include <GSLAM/core/Vocabulary.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -121,7 +122,7 @@ class B200Vocabulary : public GSLAM::Vocabulary {
   bool run(const GSLAM::TinyMat& features, GSLAM::BowVector& v, GSLAM::FeatureVector& fv, int levelsup, bool want_fv) const {
     if (m_nodeDescriptors.cols != 32 || m_nodeDescriptors.elemSize() != 1 || m_k > 32) return false;
     v.clear(); fv.clear();
-    if (empty() || features.rows <= 0) return true;
+    if (empty() || features.rows <= 0) { if (getenv("GB_DEBUG")) fprintf(stderr, "gslam_b200 vocabulary: empty input (%zu nodes, %d rows)\n", m_nodes.size(), features.rows); return true; }
     if (features.cols != 32 || features.elemSize() != 1) {
       LOG(ERROR) << "gslam_b200 vocabulary: features must be N x 32 8UC1";
       fprintf(stderr, "gslam_b200 vocabulary: features must be N x 32 8UC1 (got %d cols, elemSize %d)\n", features.cols, (int)features.elemSize());
@@ -130,7 +131,7 @@ class B200Vocabulary : public GSLAM::Vocabulary {
     std::lock_guard<std::mutex> lk(mu_);
     if (!dev_) {
       ctx_ = shared().get();
-      if (!ctx_) return true;  // logged by shared(): no CPU fallback
+      if (!ctx_) { fprintf(stderr, "gslam_b200 vocabulary: no device context\n"); return true; }  // (also logged by shared(): no CPU fallback)
       std::vector<uint32_t> child(m_nodes.size());
       std::vector<float> weight(m_nodes.size());
       for (size_t i = 0; i < m_nodes.size(); ++i) { child[i] = m_nodes[i].childNum; weight[i] = m_nodes[i].weight; }
@@ -150,6 +151,7 @@ class B200Vocabulary : public GSLAM::Vocabulary {
       fprintf(stderr, "gslam_b200 vocabulary: %s\n", gb_last_error(ctx_));
       return true;
     }
+    if (getenv("GB_DEBUG")) fprintf(stderr, "gslam_b200 vocabulary: %d rows -> %d words, %d feature entries\n", n, nw, m);
     for (int i = 0; i < nw; ++i) v.insert(v.end(), GSLAM::BowVector::value_type((GSLAM::WordId)words_[i], values_[i]));
     if (want_fv)
       for (int i = 0; i < m;) {

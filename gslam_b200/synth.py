@@ -264,3 +264,46 @@ def synth_pose_edges(pb: BAProblem, seed: int = 0, odometry: bool = True, n_loop
         return np.ascontiguousarray(M.reshape(m, 36))
     return PoseEdges(first, second, np.ascontiguousarray(meas), spd(first.shape[0]) if with_info else None, gps, np.ascontiguousarray(gmeas),
                      spd(gps.shape[0]) if with_info else None)
+
+
+# ---- vocabulary tree (GSLAM::Vocabulary's flat layout, Vocabulary.h:583-601) --------------------------------------------------------
+@dataclasses.dataclass
+class VocabularyTree:
+    k: int
+    L: int
+    weighting: int             # Vocabulary::WeightingType (Vocabulary.h:88-94)
+    scoring: int               # Vocabulary::ScoringType (:97-105)
+    child_num: np.ndarray      # (n_nodes,) u32: children of node p are rows p*k+1 .. p*k+child_num[p]
+    weight: np.ndarray         # (n_nodes,) f32
+    desc: np.ndarray           # (n_nodes, 32) u8
+
+    @property
+    def n_nodes(self): return int(self.child_num.shape[0])
+
+
+def synth_vocabulary(k=10, L=4, seed=1, weighting=0, scoring=0, prune=0.0, stop=0.0) -> VocabularyTree:
+    """A complete k-ary tree of depth L with 256-bit node descriptors (siblings share most of their bits, so near-ties are common) and
+    idf-like weights in (0.2, 9); `prune`: fraction of the inner nodes below the root turned into leaves or given fewer than k children
+    (an unbalanced tree), `stop`: fraction of the nodes with weight 0 (stopped words)."""
+    rng = np.random.default_rng(seed)
+    n = (k ** (L + 1) - 1) // (k - 1)
+    inner = (k ** L - 1) // (k - 1)
+    child = np.zeros(n, np.uint32)
+    child[:inner] = k
+    if prune > 0:
+        cut = rng.random(inner) < prune
+        cut[0] = False
+        child[:inner][cut] = 0
+        short = rng.random(inner) < prune
+        sel = short & ~cut
+        child[:inner][sel] = rng.integers(1, k + 1, int(sel.sum()))
+    weight = rng.uniform(0.2, 9.0, n).astype(np.float32)
+    if stop > 0:
+        weight[rng.random(n) < stop] = 0.0
+    noise = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    base = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    parent = (np.arange(n) - 1) // k
+    parent[0] = 0
+    flip = rng.random((n, 32)) < 0.12
+    desc = np.where(flip, noise, base[parent]).astype(np.uint8)
+    return VocabularyTree(int(k), int(L), int(weighting), int(scoring), child, weight, np.ascontiguousarray(desc))

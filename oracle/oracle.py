@@ -541,31 +541,10 @@ class VocabularyArrays:
 
 
 def synth_vocabulary(k=10, L=4, seed=1, weighting=W_TF_IDF, scoring=S_L1, prune=0.0, stop=0.0) -> VocabularyArrays:
-    """A complete k-ary tree of depth L with random 256-bit node descriptors and idf-like weights in (0.2, 9); `prune`: fraction of
-    the inner nodes below the root turned into leaves (unbalanced tree), `stop`: fraction of the words with weight 0 (stopped)."""
-    rng = np.random.default_rng(seed)
-    n = (k ** (L + 1) - 1) // (k - 1)
-    inner = (k ** L - 1) // (k - 1)
-    child = np.zeros(n, np.uint32)
-    child[:inner] = k
-    if prune > 0:
-        cut = rng.random(inner) < prune
-        cut[0] = False
-        # a pruned node keeps no children; its would-be descendants stay in the arrays but are unreachable
-        child[:inner][cut] = 0
-        short = rng.random(inner) < prune  # and some inner nodes have fewer than k children
-        child[:inner][short & ~cut] = rng.integers(1, k + 1, int((short & ~cut).sum()))
-    weight = rng.uniform(0.2, 9.0, n).astype(np.float32)
-    if stop > 0:
-        weight[rng.random(n) < stop] = 0.0
-    desc = rng.integers(0, 256, (n, 32), dtype=np.uint8)
-    # make near-ties common: siblings share most of their bits
-    base = rng.integers(0, 256, (n, 32), dtype=np.uint8)
-    parent = (np.arange(n) - 1) // k
-    parent[0] = 0
-    flip = (rng.random((n, 32)) < 0.12)
-    desc = np.where(flip, desc, base[parent]).astype(np.uint8)
-    return VocabularyArrays(k, L, weighting, scoring, child, weight, desc)
+    """gslam_b200.synth.synth_vocabulary (the bench and the tests share one generator) as VocabularyArrays."""
+    from gslam_b200 import synth
+    v = synth.synth_vocabulary(k, L, seed, weighting, scoring, prune, stop)
+    return VocabularyArrays(v.k, v.L, v.weighting, v.scoring, v.child_num, v.weight, v.desc)
 
 
 def bow_transform(voc: VocabularyArrays, feats, levelsup=0):
