@@ -302,7 +302,10 @@ def test_vocabulary_from_the_module_equals_the_reference_vocabulary_in_process(t
     rng = np.random.default_rng(11)
     centres = rng.integers(0, 256, (400, 32), dtype=np.uint8)
     n_images, per, k, L, nq = 50, 200, 10, 3, 2000
-    train = centres[rng.integers(0, 400, (n_images, per))] ^ np.packbits(rng.random((n_images, per, 256)) < 0.06, axis=2)
+    # every training image sees only 80 of the 400 centres: document frequencies below 1, so the idf weights ln(N / Ni) are positive
+    # (words present in every image get weight 0 and are dropped as stopped words by the reference, Vocabulary.h:1585)
+    which = np.stack([rng.choice(400, 80, replace=False)[rng.integers(0, 80, per)] for _ in range(n_images)])
+    train = centres[which] ^ np.packbits(rng.random((n_images, per, 256)) < 0.06, axis=2)
     q = centres[rng.integers(0, 400, nq)] ^ np.packbits(rng.random((nq, 256)) < 0.08, axis=1)
     inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
     with open(inp, "wb") as f:
