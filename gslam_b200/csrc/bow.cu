@@ -142,9 +142,14 @@ __global__ void __launch_bounds__(kRedThreads, 1) bow_reduce_kernel(int n, const
   __shared__ int s_warp[32];
   __shared__ double s_part[33];
   __shared__ int s_same;
-  if (d_count) n = min(n, *d_count);
   unsigned long long* kw = gkeys ? gkeys : s_keys;  // word keys
-  unsigned long long* kn = kw + npad;               // node keys
+  unsigned long long* kn = kw + npad;               // node keys (npad = the allocated power of two, sized for the capacity)
+  if (d_count) {  // descriptors of an extraction in flight: the launch was sized for the capacity, sort only what the count needs
+    n = max(0, min(n, *d_count));
+    int p2 = 2;
+    while (p2 < n) p2 <<= 1;
+    npad = min(npad, p2);
+  }
   if (threadIdx.x == 0) s_same = 1;
   __syncthreads();
   int differ = 0;

@@ -27,6 +27,7 @@
 #include <mutex>
 #include <thread>
 #include <fstream>
+#include <sstream>
 #include <vector>
 
 using namespace GSLAM;
@@ -182,11 +183,14 @@ static int runUndistort(const std::string& dir, const char* in, const char* out)
   return 0;
 }
 
-// in : int32 n_images, per_image, k, L, n_query, levelsup, weighting, scoring; training descriptors (n_images*per_image*32 bytes); queries
+// in : int32 k, L, weighting, scoring, n_nodes, n_query, levelsup, pad; child counts (uint32 x n_nodes), weights (float x n_nodes), node
+//      descriptors (n_nodes x 32 bytes), queries (n_query x 32 bytes)
 // out: int32 equal_bow, equal_fv, equal_bow_only_overload, n_words, n_fv_nodes, microseconds reference, microseconds plugin, pad;
 //      words (uint64 x n_words), values (float x n_words)
-// The vocabulary is TRAINED by the reference (Vocabulary::create), handed to the plugin as the VocabularyPtr any GSLAM code holds, and
-// both objects transform the same descriptors in this process; the std::maps must compare equal, key for key and float for float.
+// The tree enters the REFERENCE class through its own binary loader (Vocabulary::load(std::istream&), Vocabulary.h:1890-1930), is
+// handed to the plugin as the VocabularyPtr any GSLAM code holds, and both objects transform the same descriptors in this process;
+// the std::maps must compare equal, key for key and float for float.  (Training stays out of this program: Vocabulary::create leaves
+// the descriptor rows of unused cluster slots uninitialised, so a tree trained in a fresh process differs from one trained elsewhere.)
 static int runBow(const std::string& dir, const char* in, const char* out) {
   svar.Set<std::string>("GSLAM_LIBRARY_PATH", dir);
   Svar mod = Registry::load("b200");
@@ -194,17 +198,31 @@ static int runBow(const std::string& dir, const char* in, const char* out) {
   std::ifstream f(in, std::ios::binary);
   int32_t hdr[8];
   rd(f, hdr, 8);
-  const int n_images = hdr[0], per = hdr[1], k = hdr[2], L = hdr[3], nq = hdr[4], levelsup = hdr[5];
-  std::vector<TinyMat> imgs;
-  for (int i = 0; i < n_images; ++i) {
-    TinyMat m(per, 32, GImageType<uchar, 1>::Type, nullptr, false, 32);
-    rd(f, m.data, (size_t)per * 32);
-    imgs.push_back(m);
-  }
+  const int k = hdr[0], L = hdr[1], nq = hdr[5], levelsup = hdr[6];
+  const uint32_t nnodes = (uint32_t)hdr[4];
+  std::vector<uint32_t> child(nnodes);
+  std::vector<float> weight(nnodes);
+  std::vector<uchar> desc((size_t)nnodes * 32);
+  rd(f, child.data(), child.size()); rd(f, weight.data(), weight.size()); rd(f, desc.data(), desc.size());
   TinyMat q(nq, 32, GImageType<uchar, 1>::Type, nullptr, false, 32);
   rd(f, q.data, (size_t)nq * 32);
-  std::shared_ptr<Vocabulary> ref = Vocabulary::create(imgs, k, L, (Vocabulary::WeightingType)hdr[6], (Vocabulary::ScoringType)hdr[7]);
-  if (!ref) return 3;
+  std::shared_ptr<Vocabulary> ref(new Vocabulary());
+  {
+    std::stringstream ss;
+    const uint64_t sig = 88877711233ull;
+    const bool compressed = false;
+    Vocabulary::ScoringType sc = (Vocabulary::ScoringType)hdr[3];
+    Vocabulary::WeightingType we = (Vocabulary::WeightingType)hdr[2];
+    const int cols = 32, rows = 1, type = GImageType<uchar, 1>::Type;
+    ss.write((const char*)&sig, sizeof sig); ss.write((const char*)&compressed, sizeof compressed); ss.write((const char*)&nnodes, sizeof nnodes);
+    ss.write((const char*)&k, sizeof k); ss.write((const char*)&L, sizeof L); ss.write((const char*)&sc, sizeof sc); ss.write((const char*)&we, sizeof we);
+    ss.write((const char*)&cols, sizeof cols); ss.write((const char*)&rows, sizeof rows); ss.write((const char*)&type, sizeof type);
+    std::vector<Vocabulary::Node> nodes(nnodes);
+    for (uint32_t i = 0; i < nnodes; ++i) { nodes[i].childNum = child[i]; nodes[i].weight = weight[i]; }
+    ss.write((const char*)nodes.data(), sizeof(Vocabulary::Node) * nnodes);
+    ss.write((const char*)desc.data(), desc.size());
+    if (!ref->load(ss)) return 3;
+  }
   Svar made = mod["gslam"]["b200"]["vocabulary"](ref);
   std::shared_ptr<Vocabulary> dev;
   try { dev = made.castAs<std::shared_ptr<Vocabulary> >(); } catch (...) { return 4; }  // (Svar holds shared_ptr<T> as a pointer holder of T, Svar.h:2834-2850)

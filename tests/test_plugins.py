@@ -294,23 +294,28 @@ def test_undistort_function_equals_the_reference_undistorter_in_process(tmp_path
 
 @needs_plugins
 @pytest.mark.gpu
-@pytest.mark.parametrize("weighting,scoring,levelsup", [(0, 0, 0), (0, 0, 2), (1, 1, 1), (2, 5, 0)])
-def test_vocabulary_from_the_module_equals_the_reference_vocabulary_in_process(tmp_path, weighting, scoring, levelsup):
-    """gslam.b200.vocabulary(VocabularyPtr) returns a GSLAM::Vocabulary whose virtual batch transforms run on the device: the
-    reference TRAINS the tree (Vocabulary::create), both objects transform the same 2000 descriptors in one process, and the
-    BowVector / FeatureVector std::maps must be equal key for key and float for float (host_test compares them with ==)."""
+@pytest.mark.parametrize("tree,weighting,scoring,levelsup", [("trained", 0, 0, 0), ("trained", 0, 0, 2), ("synthetic", 1, 1, 1), ("synthetic", 2, 5, 0),
+                                                            ("synthetic", 0, 3, 4)])
+def test_vocabulary_from_the_module_equals_the_reference_vocabulary_in_process(tmp_path, tree, weighting, scoring, levelsup):
+    """gslam.b200.vocabulary(VocabularyPtr) returns a GSLAM::Vocabulary whose virtual batch transforms run on the device.  host_test
+    loads a tree into the REFERENCE class with its own binary loader -- the one tests/golden/bow_golden.npz holds (trained by the
+    reference's Vocabulary::create) or a synthetic 10^4-word one --, hands it to the module, lets both objects transform the same 2000
+    descriptors in one process and compares the BowVector / FeatureVector std::maps with ==: key for key, float for float."""
+    from gslam_b200 import synth as S
+    if tree == "trained":
+        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bow_golden.npz"))
+        k, L, child, weight, desc = int(z["k"]), int(z["L"]), z["child_num"], z["weight"], z["desc"]
+    else:
+        v = S.synth_vocabulary(10, 4, seed=21, stop=0.05, prune=0.05)
+        k, L, child, weight, desc = v.k, v.L, v.child_num, v.weight, v.desc
     rng = np.random.default_rng(11)
-    centres = rng.integers(0, 256, (400, 32), dtype=np.uint8)
-    n_images, per, k, L, nq = 50, 200, 10, 3, 2000
-    # every training image sees only 80 of the 400 centres: document frequencies below 1, so the idf weights ln(N / Ni) are positive
-    # (words present in every image get weight 0 and are dropped as stopped words by the reference, Vocabulary.h:1585)
-    which = np.stack([rng.choice(400, 80, replace=False)[rng.integers(0, 80, per)] for _ in range(n_images)])
-    train = centres[which] ^ np.packbits(rng.random((n_images, per, 256)) < 0.06, axis=2)
-    q = centres[rng.integers(0, 400, nq)] ^ np.packbits(rng.random((nq, 256)) < 0.08, axis=1)
+    nq = 2000
+    q = desc[rng.integers(1, desc.shape[0], nq)] ^ np.packbits(rng.random((nq, 256)) < 0.06, axis=1)
     inp, out = tmp_path / "in.bin", tmp_path / "out.bin"
     with open(inp, "wb") as f:
-        f.write(struct.pack("<8i", n_images, per, k, L, nq, levelsup, weighting, scoring))
-        f.write(np.ascontiguousarray(train).tobytes()); f.write(np.ascontiguousarray(q).tobytes())
+        f.write(struct.pack("<8i", k, L, weighting, scoring, child.shape[0], nq, levelsup, 0))
+        f.write(np.ascontiguousarray(child, np.uint32).tobytes()); f.write(np.ascontiguousarray(weight, np.float32).tobytes())
+        f.write(np.ascontiguousarray(desc, np.uint8).tobytes()); f.write(np.ascontiguousarray(q, np.uint8).tobytes())
     r = run("bow", str(inp), str(out))
     assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
     raw = open(out, "rb").read()
@@ -319,6 +324,10 @@ def test_vocabulary_from_the_module_equals_the_reference_vocabulary_in_process(t
     assert 50 < nw <= nq and 0 < nfv <= nw
     words = np.frombuffer(raw[32:32 + 8 * nw], np.uint64); values = np.frombuffer(raw[32 + 8 * nw:32 + 12 * nw], np.float32)
     assert np.all(np.diff(words.astype(np.int64)) > 0) and np.all(values > 0)
+    # ... and equal to the oracle on the same tree (itself pinned to the reference in tests/test_oracle_bow.py)
+    from oracle import oracle as O
+    want = O.bow_transform(O.VocabularyArrays(k, L, weighting, scoring, child, weight, desc), q, levelsup)
+    assert np.array_equal(words.astype(np.int64), want["words"]) and np.array_equal(values, want["values"])
     print(f"bow transform of {nq} descriptors: reference {us_ref} us, plugin {us_dev} us")
 
 
