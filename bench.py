@@ -146,6 +146,9 @@ def cpu_path(frames, ba_problem, steps, threads):
         def match(a, b):
             return oracle.match_hamming(a, b)
         what = "oracle orb_ref+hamming_ref (1 thread)"
+    ba_threads = max(1, min(16, threads // 4))  # the BA port's OpenMP loops (linearisation, Schur complement, dense mat-vec)
+    oracle.ba_set_threads(ba_threads)
+    what += f" on the tracking thread || oracle ba_ref ({ba_threads} OpenMP threads) on the mapping thread"
     prev = extract(frames[0])
     q: queue.Queue = queue.Queue(maxsize=2)
 
@@ -168,7 +171,8 @@ def cpu_path(frames, ba_problem, steps, threads):
     q.put(None)
     th.join()
     dt = time.perf_counter() - t0
-    return steps / dt, what + " on the tracking thread || oracle ba_ref (1 thread) on the mapping thread"
+    oracle.ba_set_threads(1)
+    return steps / dt, what
 
 
 def median(xs):

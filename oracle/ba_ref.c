@@ -26,6 +26,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "../include/gslam_b200.h"
 
@@ -89,6 +92,19 @@ void orc_se3_retract(const double* pose, const double* d, double* out) {
 }
 
 static double clampd(double d) { return d < 1e-6 ? 1e-6 : (d > 1e32 ? 1e32 : d); }
+
+/* Threads of the solver's heavy loops (the reference arm of bench.py: "OpenMP, all cores" next to the 1-thread figure).  Default 1:
+ * the tests compare against the strictly sequential summation order.  With n > 1 the Schur complement accumulates per-thread partial
+ * systems (static schedule, folded in thread order: deterministic for a fixed n), the dense mat-vec of the PCG is split by rows
+ * (bitwise the same), the cost is a per-thread partial sum. */
+static int g_ba_threads = 1;
+void orc_ba_set_threads(int n) {
+#ifdef _OPENMP
+  g_ba_threads = n < 1 ? 1 : (n > 64 ? 64 : n);
+#else
+  (void)n;
+#endif
+}
 
 /* ---- pose-graph terms (row f3: GSLAM::SE3Edge / GPSEdge, Optimizer.h:127-148; our definition, see the header) ------------------- */
 /* Log of an SE3 given as pose7, tangent order [v, w]: restates the reference's SE3::log (GSLAM/core/SE3.h:205-246, NEAR_ZERO = 1e-10
@@ -279,8 +295,8 @@ typedef struct {
   double delta;
   /* linearisation */
   double *U, *gc, *V, *gp, *W; /* nc x 36, nc x 6, np x 9, np x 3, no x 18 */
-  /* point -> obs lists */
-  int *poff, *plist;
+  /* point -> obs lists, camera -> obs lists (observation indices ascending inside each list) */
+  int *poff, *plist, *coff, *clist;
   /* pose-graph terms: SE3 edges then GPS edges; Zinv = measurement^-1; P = off-diagonal block J_i' Omega J_j of each SE3 edge */
   int nse, ngps;
   const int32_t *se_i, *se_j, *gps_i;
@@ -295,6 +311,24 @@ static double ba_cost(const ba_state* s, const double* pose, const double* pts) 
   double c = 0.0;
   double* Rs = (double*)malloc(sizeof(double) * 9 * (size_t)s->nc);
   for (int i = 0; i < s->nc; ++i) quat_to_R(pose + 7 * i, Rs + 9 * i);
+  if (g_ba_threads > 1 && s->no > 4096) {
+    double part[64] = {0};
+#ifdef _OPENMP
+#pragma omp parallel num_threads(g_ba_threads)
+    {
+      double acc = 0.0;
+#pragma omp for schedule(static)
+      for (int k = 0; k < s->no; ++k) {
+        obs_lin o;
+        int i = s->oc[k], j = s->op[k];
+        eval_obs(Rs + 9 * i, pose + 7 * i + 4, pts + 3 * j, s->om + 3 * k, s->oi ? s->oi + 4 * k : NULL, s->delta, 0, &o);
+        acc += o.rho;
+      }
+      part[omp_get_thread_num()] = acc;
+    }
+#endif
+    for (int t = 0; t < 64; ++t) c += part[t];
+  } else
   for (int k = 0; k < s->no; ++k) {
     obs_lin o;
     int i = s->oc[k], j = s->op[k];
@@ -357,6 +391,63 @@ static double ba_linearize(ba_state* s) {
   double* Rs = (double*)malloc(sizeof(double) * 9 * (size_t)nc);
   for (int i = 0; i < nc; ++i) quat_to_R(s->pose + 7 * i, Rs + 9 * i);
   double c = 0.0;
+#ifdef _OPENMP
+  if (g_ba_threads > 1 && no > 4096) {
+    /* the same sums as the loop below, regrouped so that threads own disjoint outputs: landmarks (V, g_p, W, cost) then cameras (U, g_c);
+     * inside a landmark / camera the observations are visited in ascending index order, i.e. in the sequential loop's order */
+    double part[64] = {0};
+#pragma omp parallel num_threads(g_ba_threads)
+    {
+      double acc = 0.0;
+#pragma omp for schedule(static)
+      for (int j = 0; j < np; ++j) {
+        const int pf = ptfree(s, j);
+        double* V = s->V + 9 * j;
+        for (int e = s->poff[j]; e < s->poff[j + 1]; ++e) {
+          const int k = s->plist[e], i = s->oc[k];
+          obs_lin o;
+          eval_obs(Rs + 9 * i, s->pose + 7 * i + 4, s->pts + 3 * j, s->om + 3 * k, s->oi ? s->oi + 4 * k : NULL, s->delta, 1, &o);
+          if (!o.valid) continue;
+          acc += o.rho;
+          const int dm = dofmask(s, i);
+          for (int d = 0; d < 6; ++d) if (!((dm >> d) & 1)) { o.Jc[d] = 0.0; o.Jc[6 + d] = 0.0; }
+          if (!pf) for (int d = 0; d < 6; ++d) o.Jp[d] = 0.0;
+          double AJp[6], Ar[2];
+          for (int d = 0; d < 3; ++d) { AJp[d] = o.A[0] * o.Jp[d] + o.A[1] * o.Jp[3 + d]; AJp[3 + d] = o.A[1] * o.Jp[d] + o.A[2] * o.Jp[3 + d]; }
+          Ar[0] = o.A[0] * o.r[0] + o.A[1] * o.r[1]; Ar[1] = o.A[1] * o.r[0] + o.A[2] * o.r[1];
+          double* W = s->W + 18 * (size_t)k;
+          for (int a = 0; a < 6; ++a) for (int b = 0; b < 3; ++b) W[a * 3 + b] = o.Jc[a] * AJp[b] + o.Jc[6 + a] * AJp[3 + b];
+          for (int a = 0; a < 3; ++a) {
+            for (int b = 0; b < 3; ++b) V[a * 3 + b] += o.Jp[a] * AJp[b] + o.Jp[3 + a] * AJp[3 + b];
+            s->gp[3 * j + a] -= o.Jp[a] * Ar[0] + o.Jp[3 + a] * Ar[1];
+          }
+        }
+      }
+      part[omp_get_thread_num()] = acc;
+#pragma omp for schedule(static)
+      for (int i = 0; i < nc; ++i) {
+        const int dm = dofmask(s, i);
+        double* U = s->U + 36 * i;
+        for (int e = s->coff[i]; e < s->coff[i + 1]; ++e) {
+          const int k = s->clist[e], j = s->op[k];
+          obs_lin o;
+          eval_obs(Rs + 9 * i, s->pose + 7 * i + 4, s->pts + 3 * j, s->om + 3 * k, s->oi ? s->oi + 4 * k : NULL, s->delta, 1, &o);
+          if (!o.valid) continue;
+          for (int d = 0; d < 6; ++d) if (!((dm >> d) & 1)) { o.Jc[d] = 0.0; o.Jc[6 + d] = 0.0; }
+          double AJc[12], Ar[2];
+          for (int d = 0; d < 6; ++d) { AJc[d] = o.A[0] * o.Jc[d] + o.A[1] * o.Jc[6 + d]; AJc[6 + d] = o.A[1] * o.Jc[d] + o.A[2] * o.Jc[6 + d]; }
+          Ar[0] = o.A[0] * o.r[0] + o.A[1] * o.r[1]; Ar[1] = o.A[1] * o.r[0] + o.A[2] * o.r[1];
+          for (int a = 0; a < 6; ++a) {
+            for (int b = 0; b < 6; ++b) U[a * 6 + b] += o.Jc[a] * AJc[b] + o.Jc[6 + a] * AJc[6 + b];
+            s->gc[6 * i + a] -= o.Jc[a] * Ar[0] + o.Jc[6 + a] * Ar[1];
+          }
+        }
+      }
+    }
+    for (int t = 0; t < 64; ++t) c += part[t];
+    no = 0;  /* (the sequential loop below has nothing left to do) */
+  }
+#endif
   for (int k = 0; k < no; ++k) {
     obs_lin o;
     int i = s->oc[k], j = s->op[k];
@@ -422,6 +513,12 @@ static void state_init_ex(ba_state* s, const gb_ba_problem* pb, const gb_pose_ed
   int* fill = (int*)calloc((size_t)s->np + 1, sizeof(int));
   for (int k = 0; k < s->no; ++k) { int j = s->op[k]; s->plist[s->poff[j] + fill[j]++] = k; }
   free(fill);
+  s->coff = (int*)calloc((size_t)s->nc + 2, sizeof(int)); s->clist = (int*)calloc((size_t)s->no + 1, sizeof(int));
+  for (int k = 0; k < s->no; ++k) s->coff[s->oc[k] + 1]++;
+  for (int i = 0; i < s->nc; ++i) s->coff[i + 1] += s->coff[i];
+  fill = (int*)calloc((size_t)s->nc + 1, sizeof(int));
+  for (int k = 0; k < s->no; ++k) { int i = s->oc[k]; s->clist[s->coff[i] + fill[i]++] = k; }
+  free(fill);
   if (pe) {
     s->nse = pe->n_se3; s->ngps = pe->n_gps;
     s->se_i = pe->se3_first; s->se_j = pe->se3_second; s->gps_i = pe->gps_frame; s->se_info = pe->se3_info; s->gps_info = pe->gps_info;
@@ -434,7 +531,7 @@ static void state_init_ex(ba_state* s, const gb_ba_problem* pb, const gb_pose_ed
 }
 static void state_init(ba_state* s, const gb_ba_problem* pb, double delta) { state_init_ex(s, pb, NULL, delta); }
 static void state_free(ba_state* s) {
-  free(s->pose); free(s->pts); free(s->U); free(s->gc); free(s->V); free(s->gp); free(s->W); free(s->poff); free(s->plist);
+  free(s->pose); free(s->pts); free(s->U); free(s->gc); free(s->V); free(s->gp); free(s->W); free(s->poff); free(s->plist); free(s->coff); free(s->clist);
   free(s->se_Zinv); free(s->gps_Zinv); free(s->P);
 }
 static int validate_edges(const gb_ba_problem* pb, const gb_pose_edges* pe) {
@@ -506,6 +603,20 @@ static void ba_schur(const ba_state* s, double lambda, double* S, double* gt, do
         S[(size_t)(6 * j + b) * n6 + 6 * i + a] += P[a * 6 + b];
       }
   }
+  int T = 1;
+#ifdef _OPENMP
+  if (g_ba_threads > 1 && np > 256) T = g_ba_threads;
+#endif
+  double* Sall = T > 1 ? (double*)calloc((size_t)T * ((size_t)n6 * n6 + n6), sizeof(double)) : NULL;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(T) if (T > 1)
+#endif
+  {
+  double* S_acc = S; double* gt_acc = gt;  /* thread-local partial system when T > 1 (folded in thread order below) */
+#ifdef _OPENMP
+  if (T > 1) { S_acc = Sall + (size_t)omp_get_thread_num() * ((size_t)n6 * n6 + n6); gt_acc = S_acc + (size_t)n6 * n6; }
+#pragma omp for schedule(static)
+#endif
   for (int j = 0; j < np; ++j) {
     double* Vi = Vinv + 9 * j;
     memset(Vi, 0, sizeof(double) * 9);
@@ -521,15 +632,28 @@ static void ba_schur(const ba_state* s, double lambda, double* S, double* gt, do
       for (int a = 0; a < 6; ++a)
         for (int b = 0; b < 3; ++b) Y[a * 3 + b] = Wk[a * 3] * Vi[b] + Wk[a * 3 + 1] * Vi[3 + b] + Wk[a * 3 + 2] * Vi[6 + b];
       for (int a = 0; a < 6; ++a)
-        gt[6 * i + a] -= Y[a * 3] * s->gp[3 * j] + Y[a * 3 + 1] * s->gp[3 * j + 1] + Y[a * 3 + 2] * s->gp[3 * j + 2];
+        gt_acc[6 * i + a] -= Y[a * 3] * s->gp[3 * j] + Y[a * 3 + 1] * s->gp[3 * j + 1] + Y[a * 3 + 2] * s->gp[3 * j + 2];
       for (int f = 0; f < n; ++f) {
         int k2 = s->plist[s->poff[j] + f], i2 = s->oc[k2];
         const double* W2 = s->W + 18 * (size_t)k2;
         for (int a = 0; a < 6; ++a)
           for (int b = 0; b < 6; ++b)
-            S[(size_t)(6 * i + a) * n6 + 6 * i2 + b] -= Y[a * 3] * W2[b * 3] + Y[a * 3 + 1] * W2[b * 3 + 1] + Y[a * 3 + 2] * W2[b * 3 + 2];
+            S_acc[(size_t)(6 * i + a) * n6 + 6 * i2 + b] -= Y[a * 3] * W2[b * 3] + Y[a * 3 + 1] * W2[b * 3 + 1] + Y[a * 3 + 2] * W2[b * 3 + 2];
       }
     }
+  }
+  }
+  if (T > 1) { /* fold the partial systems in thread order */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(T)
+#endif
+    for (int r = 0; r < n6; ++r)
+      for (int t = 0; t < T; ++t) {
+        const double* P = Sall + (size_t)t * ((size_t)n6 * n6 + n6);
+        for (int c = 0; c < n6; ++c) S[(size_t)r * n6 + c] += P[(size_t)r * n6 + c];
+        gt[r] += P[(size_t)n6 * n6 + r];
+      }
+    free(Sall);
   }
 }
 
@@ -552,6 +676,7 @@ static int ba_pcg(int nc, const double* S, const double* g, double* x, int maxit
 #define APPLY_MINV(src, dst) \
   for (int i = 0; i < nc; ++i) for (int a = 0; a < 6; ++a) { double sacc = 0.0; for (int b = 0; b < 6; ++b) sacc += Minv[36 * i + a * 6 + b] * (src)[6 * i + b]; (dst)[6 * i + a] = sacc; }
 #define MATVEC(src, dst) \
+  _Pragma("omp parallel for schedule(static) num_threads(g_ba_threads) if (g_ba_threads > 1 && n6 >= 192)") \
   for (int a = 0; a < n6; ++a) { double sacc = 0.0; const double* row = S + (size_t)a * n6; for (int b = 0; b < n6; ++b) sacc += row[b] * (src)[b]; (dst)[a] = sacc; }
   int it = 0;
   for (int a = 0; a < n6; ++a) { x[a] = 0.0; r[a] = g[a]; }

@@ -113,6 +113,8 @@ def lib() -> C.CDLL:
         L.orc_ba_reduced_system_ex.restype = C.c_int
         L.orc_ba_reduced_system_ex.argtypes = [C.POINTER(BaProblemC), C.POINTER(PoseEdgesC), C.c_double, C.c_double, C.c_int, C.c_double,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        L.orc_ba_set_threads.restype = None
+        L.orc_ba_set_threads.argtypes = [C.c_int]
         L.orc_se3_log.restype = None
         L.orc_se3_log.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_se3_mul.restype = None
@@ -278,6 +280,11 @@ def pose_edges_c(edges):
 def _pe(edges):
     c, keep = pose_edges_c(edges)
     return (C.byref(c) if c is not None else None), (c, keep)
+
+
+def ba_set_threads(n: int) -> None:
+    """OpenMP threads of the BA oracle's heavy loops (default 1 = the strictly sequential order the parity tests compare against)."""
+    lib().orc_ba_set_threads(int(n))
 
 
 def ba_solve(pb, edges=None, **opts):

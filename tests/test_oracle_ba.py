@@ -192,3 +192,25 @@ def test_large_graph_sweep_plan_covers_everything_once_and_is_balanced(shape):
             cost[k] += (0.4 * (d - c) + 150.0) if a < 0 else ((d - c) + 40.0)
     if n.value > 4 * n_teams:
         assert cost.max() < 1.25 * cost.mean() + 700.0
+
+
+def test_multithreaded_oracle_equals_the_sequential_one():
+    """bench.py's reference arm runs the BA port with OpenMP threads (orc_ba_set_threads); the regrouped loops must give the sequential
+    sums (blocks bit for bit where only the loop nest changed, the cost and the Schur complement to rounding) and the same solve."""
+    pb = synth.synth_ba(50, 2000, obs_per_point=5, n_fixed=2, seed=42)
+    seq = oracle.ba_linearize(pb, 0.01)
+    a = pb.copy(); r1 = oracle.ba_solve(a, max_iterations=6, function_tolerance=0.0)
+    S1, g1, d1, _ = oracle.ba_reduced_system(pb, 0.01, 1e-4, 50, 1e-10)
+    try:
+        oracle.ba_set_threads(4)
+        par = oracle.ba_linearize(pb, 0.01)
+        for k in ("U", "gc", "V", "gp", "W"):
+            assert np.array_equal(par[k], seq[k]), k
+        assert abs(par["cost"] - seq["cost"]) <= 1e-14 * seq["cost"]
+        S4, g4, d4, _ = oracle.ba_reduced_system(pb, 0.01, 1e-4, 50, 1e-10)
+        assert np.abs(S4 - S1).max() <= 1e-12 * np.abs(S1).max() and np.abs(g4 - g1).max() <= 1e-12 * np.abs(g1).max()
+        b = pb.copy(); r4 = oracle.ba_solve(b, max_iterations=6, function_tolerance=0.0)
+    finally:
+        oracle.ba_set_threads(1)
+    assert r4.accepted == r1.accepted and abs(r4.final_cost - r1.final_cost) <= 1e-9 * r1.final_cost
+    assert np.abs(b.cam_pose_wc - a.cam_pose_wc).max() < 1e-8
