@@ -306,7 +306,7 @@ def test_vocabulary_from_the_module_equals_the_reference_vocabulary_in_process(t
         z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bow_golden.npz"))
         k, L, child, weight, desc = int(z["k"]), int(z["L"]), z["child_num"], z["weight"], z["desc"]
     else:
-        v = S.synth_vocabulary(10, 4, seed=21, stop=0.05, prune=0.05)
+        v = S.synth_vocabulary(10, 4, seed=21, stop=0.05)   # (complete tree: the node id "levelsup levels up" is defined for every word)
         k, L, child, weight, desc = v.k, v.L, v.child_num, v.weight, v.desc
     rng = np.random.default_rng(11)
     nq = 2000
