@@ -281,15 +281,38 @@ __global__ void __launch_bounds__(kCamThreads) ba_linearize_cams_kernel(BaDev g)
   ba_linearize_cams_body(g, blockIdx.x);
 }
 
-// out[0] = 0.5 * sum(src[0..n)) — single CTA, deterministic
-__global__ void __launch_bounds__(kRedThreads) ba_reduce_cost_kernel(const BaScalars* sc, const double* __restrict__ src, int n,
-                                                                     double* __restrict__ out) {
-  if (sc->stop) return;
-  __shared__ double s_part[kRedThreads / 32 + 1];
+// Deterministic grid-wide sum: block b adds its contiguous slice of src (thread-strided, fixed block tree), the LAST block to finish
+// (ticket) folds the gridDim partials in block order and writes scale * sum to out[0].  The order depends on the launch geometry
+// only.  All threads of every block must call it; `part` holds >= gridDim doubles, `ticket` is left at 0.
+constexpr int kRedPartials = 2048;
+template <int NT>
+__device__ __forceinline__ void grid_sum_to(const double* __restrict__ src, int n, double scale, double* __restrict__ part, unsigned int* ticket,
+                                            double* __restrict__ out, double* s_part /* NT/32 + 1 */, int* s_flag) {
+  const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int a = min((int)blockIdx.x * per, n), b = min(a + per, n);
   double v = 0.0;
-  for (int k = threadIdx.x; k < n; k += kRedThreads) v += src[k];
-  const double t = block_sum<kRedThreads>(v, s_part);
-  if (threadIdx.x == 0) out[0] = 0.5 * t;
+  for (int k = a + (int)threadIdx.x; k < b; k += NT) v += src[k];
+  const double t = block_sum<NT>(v, s_part);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = t;
+    __threadfence();
+    *s_flag = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!*s_flag) return;
+  __threadfence();
+  double w = 0.0;
+  for (int k = threadIdx.x; k < (int)gridDim.x; k += NT) w += __ldcg(part + k);
+  const double total = block_sum<NT>(w, s_part);
+  if (threadIdx.x == 0) { out[0] = scale * total; *ticket = 0u; }
+}
+
+// out[0] = 0.5 * sum(src[0..n)) — any grid up to kRedPartials blocks, deterministic
+__global__ void __launch_bounds__(kRedThreads) ba_reduce_cost_kernel(BaDev g, const double* __restrict__ src, int n, double* __restrict__ out) {
+  if (g.sc->stop) return;
+  __shared__ double s_part[kRedThreads / 32 + 1];
+  __shared__ int s_flag;
+  grid_sum_to<kRedThreads>(src, n, 0.5, g.red_part, g.red_ticket, out, s_part, &s_flag);
 }
 
 // one thread per observation e=(i,j): Y = W_e Vinv_j;  g~_i -= Y g_p,j;  S_{i,i'} -= Y W_f' for every f=(i',j)
@@ -890,12 +913,9 @@ __global__ void __launch_bounds__(256) ba_prepare_schur_kernel(BaDev g, double* 
 #pragma unroll
     for (int k = 0; k < 9; ++k) g.Vinv[9 * j + k] = Vi[k];
   }
-  if (blockIdx.x == 0) {  // deterministic cost reduction (strided partials + fixed tree)
-    double v = 0.0;
-    for (int k = threadIdx.x; k < g.np + g.npe; k += 256) v += g.cost_pt[k];
-    const double t = block_sum<256>(v, s_part);
-    if (threadIdx.x == 0) buf[g.r_gt + 2 * n6] = 0.5 * t;
-  }
+  // deterministic cost reduction over the whole grid (every block adds a slice, the last one folds the partials in block order)
+  __shared__ int s_flag;
+  grid_sum_to<256>(g.cost_pt, g.np + g.npe, 0.5, g.red_part, g.red_ticket, buf + g.r_gt + 2 * n6, s_part, &s_flag);
 }
 
 // back-substitution of landmark j followed by its robustified cost at the candidate estimate; 8 lanes per landmark
@@ -2064,6 +2084,7 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
     sl.take(&d.Sb, (size_t)d.s_nnzb * 36);
     sl.take(&d.x, n6); sl.take(&d.r, n6); sl.take(&d.z, n6); sl.take(&d.p, n6); sl.take(&d.q, n6); sl.take(&d.sv, n6);
     sl.take(&d.sc, 1);
+    sl.take(&d.red_part, (size_t)kRedPartials + 2);
     sl.take(&g->buf, compact_only ? 8 : g->buf_doubles);
     sl.take(&g->d_cost, 8);
     sl.take(&g->rbuf, g->rbuf_doubles);
@@ -2144,6 +2165,8 @@ int ba_graph_create_impl(gb_ctx* ctx, const gb_ba_problem* pb, gb_ba_graph** out
   tr.stamp("blob fill");
   GB_CUDA(ctx, cudaMemcpyAsync(dblob, h, blob, cudaMemcpyHostToDevice, ctx->stream));
   d.cam_ticket = reinterpret_cast<unsigned int*>(cam_ticket_d);
+  d.red_ticket = reinterpret_cast<unsigned int*>(d.red_part + kRedPartials);
+  GB_CUDA(ctx, cudaMemsetAsync(d.red_ticket, 0, 16, ctx->stream));
   GB_CUDA(ctx, cudaMemsetAsync(d.cam_ticket, 0, ((size_t)nc / 2 + 1) * 8, ctx->stream));
   double* d_pose_wc = (double*)(dblob + o_pose);
   g->pose_wc_in = d_pose_wc;
@@ -2355,13 +2378,15 @@ int ba_reduce_local_compact(gb_ctx* ctx, gb_ba_graph* g, double* rbuf) {
   return GB_OK;
 }
 
+static int ba_red_blocks(const gb_ctx* ctx, int n) { return std::max(1, std::min(std::min(ctx->sm_count, kRedPartials), (n + 8 * kRedThreads - 1) / (8 * kRedThreads))); }
+
 int ba_backsub_cost_compact(gb_ctx* ctx, gb_ba_graph* g, double* d_cost) {
   if (!ctx || !g || !g->begun) return GB_ERR_INVALID;
   CtxLock lk(ctx);
   BaDev& d = g->d;
   if (!d_cost) d_cost = g->d_cost;
   if (d.np > 0) { ba_backsub_cost_kernel<<<gb_div_up(d.np * kLpp, 128), 128, 0, ctx->stream>>>(d); GB_LAUNCH_CHECK(ctx); }
-  ba_reduce_cost_kernel<<<1, kRedThreads, 0, ctx->stream>>>(d.sc, d.cost_pt_new, d.np, d_cost); GB_LAUNCH_CHECK(ctx);
+  ba_reduce_cost_kernel<<<ba_red_blocks(ctx, d.np), kRedThreads, 0, ctx->stream>>>(d, d.cost_pt_new, d.np, d_cost); GB_LAUNCH_CHECK(ctx);
   return GB_OK;
 }
 
@@ -2417,7 +2442,7 @@ int gb_ba_graph_step(gb_ctx* ctx, gb_ba_graph* g, const double* buf_in, double* 
   if (!d_cost) d_cost = g->d_cost;
   GB_CHECK(ba_step_core(ctx, g, buf));
   GB_CHECK(ba_pose_cost(ctx, g, ctx->stream));
-  ba_reduce_cost_kernel<<<1, kRedThreads, 0, ctx->stream>>>(d.sc, d.cost_pt_new, d.np + d.npe, d_cost); GB_LAUNCH_CHECK(ctx);
+  ba_reduce_cost_kernel<<<ba_red_blocks(ctx, d.np + d.npe), kRedThreads, 0, ctx->stream>>>(d, d.cost_pt_new, d.np + d.npe, d_cost); GB_LAUNCH_CHECK(ctx);
   return GB_OK;
 }
 

@@ -75,6 +75,9 @@ struct BaDev {
   unsigned int* cam_ticket;
   // PCG
   double *Minv, *x, *r, *z, *p, *q, *sv;  // generic PCG: z = u = Minv r, q = w = S u, sv = S p
+  // grid-wide deterministic sums (cost reductions): per-block partials + a ticket, reused launch after launch
+  double* red_part;        // [kRedPartials]
+  unsigned int* red_ticket;
   BaScalars* sc;
   long long* prof;  // optional clock64 stamps of the cluster PCG (test hook), or nullptr
 };
