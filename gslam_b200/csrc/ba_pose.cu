@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(128) ba_pose_gather_kernel(BaDev g) {
 }
 
 // thread = (unordered camera pair, entry of the 6x6 block): S_ij += sum J_i' Omega J_j, S_ji += its transpose, in edge order.  `buf`
-// is the dense reduced system; runs after the Schur complement of EVERY iteration (rejected steps rebuild S from U).  The diagonal
-// of U it also refreshes in the [diag U] slot when the dense layout copied it before the gather... (no: the gather runs first).
+// is the dense reduced system; runs after the Schur complement of EVERY iteration (rejected steps rebuild S from U, so the staged
+// blocks of the last linearisation are added again).  The diagonal blocks need nothing here: they went into U before S was formed.
 __global__ void __launch_bounds__(128) ba_pose_offdiag_kernel(BaDev g, double* __restrict__ buf) {
   if (g.sc->stop) return;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -38,6 +38,8 @@ constexpr int kTeams = 4;        // teams per CTA
 constexpr int kSwThreads = kTeam * kTeams;
 constexpr int kSwMaxPts = 32;    // landmarks per group (host plan)
 constexpr int kSwPoseCams = 512; // pose table in shared memory up to this many cameras
+constexpr int kPoseStride = 14;  // doubles per camera row of the shared-memory table (12 used): an ODD number of 16-byte chunks, so that
+                                 // the rows of a warp's 32 different cameras spread over all eight chunk slots of the banks (12 -> only four)
 
 // one stage of prefetched item data, in doubles
 constexpr int kStUv = 0;                         // [128] double2
@@ -78,7 +80,7 @@ __device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0,
 
 template <bool POSE_SMEM>
 __device__ __forceinline__ void load_rt(const double* __restrict__ table, int i, double* Rt) {
-  const double2* src = reinterpret_cast<const double2*>(table + 12 * (size_t)i);
+  const double2* src = reinterpret_cast<const double2*>(table + (POSE_SMEM ? kPoseStride : 12) * (size_t)i);
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
     const double2 v = POSE_SMEM ? src[k] : __ldg(src + k);
@@ -224,7 +226,7 @@ __device__ __forceinline__ void sweep_camera(const BaDev& g, const SweepCtx& cx,
   // (the camera's pose stays in the shared-memory table: broadcast LDS per use instead of 24 registers next to the 54 of the sums)
   double Rt_reg[12];
   if (!POSE_SMEM) load_rt<false>(cx.pose_tab, i, Rt_reg);
-  const double* Rt = POSE_SMEM ? cx.pose_tab + 12 * (size_t)i : Rt_reg;
+  const double* Rt = POSE_SMEM ? cx.pose_tab + kPoseStride * (size_t)i : Rt_reg;
   if (cx.pend && slice == 0) {  // install this camera's accepted pose
     if (t < 12) g.Rt[12 * i + t] = g.Rt_new[12 * i + t];
     else if (t >= 32 && t < 39) g.pose[7 * i + t - 32] = g.pose_new[7 * i + t - 32];
@@ -338,8 +340,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) ba_sweep_kernel(BaDev g, int wh
   if (POSE_SMEM) {
     double2* dst = reinterpret_cast<double2*>(sm + kOffPose);
     const double2* src = reinterpret_cast<const double2*>(RT);
-    for (int k = threadIdx.x; k < g.nc * 6; k += kSwThreads) dst[k] = src[k];
-    uint8_t* sd = reinterpret_cast<uint8_t*>(sm + kOffPose + 12 * (size_t)g.nc);
+    for (int k = threadIdx.x; k < g.nc * 6; k += kSwThreads) dst[(k / 6) * (kPoseStride / 2) + (k % 6)] = src[k];
+    uint8_t* sd = reinterpret_cast<uint8_t*>(sm + kOffPose + kPoseStride * (size_t)g.nc);
     for (int k = threadIdx.x; k < g.nc; k += kSwThreads) sd[k] = g.dof[k];
     cx.pose_tab = sm + kOffPose;
     cx.dof_tab = sd;
@@ -436,7 +438,7 @@ int ba_sweep_teams(const gb_ctx* ctx) { return ctx->sm_count * kTeams; }
 
 static size_t ba_sweep_smem(int nc) {
   const bool pose = nc <= kSwPoseCams;
-  return (size_t)kOffPose * sizeof(double) + (pose ? (size_t)nc * 96 + (((size_t)nc + 15) & ~(size_t)15) : 0);
+  return (size_t)kOffPose * sizeof(double) + (pose ? (size_t)nc * kPoseStride * 8 + (((size_t)nc + 15) & ~(size_t)15) : 0);
 }
 
 static int ba_sweep_setup(gb_ctx* ctx) {  // once per device: opt in to the large dynamic shared memory (never lowered)

@@ -51,6 +51,21 @@ def test_vs_oracle(ctx, w, h, n, kw):
     assert_same(kps, desc, wk, wd)
 
 
+from _images import KIND_CASES, image_of_kind  # noqa: E402  (tests/ is on sys.path under pytest's rootdir conftest)
+
+
+@pytest.mark.parametrize("kind,w,h,seed,n,nl,sf,ft", KIND_CASES)
+def test_other_image_statistics_match_oracle(ctx, kind, w, h, seed, n, nl, sf, ft):
+    """Image families unlike synth_frame -- white noise, binary noise, checkerboards (exact ties in FAST scores, Harris responses and
+    moments everywhere), blurred noise, constant blocks, low contrast -- on which the oracle is pinned to live cv2
+    (tests/test_oracle_orb.py::test_live_cv2_image_kinds): every keypoint field and descriptor bit against the oracle."""
+    img = np.ascontiguousarray(image_of_kind(kind, w, h, seed))
+    kw = dict(nlevels=nl, scale_factor=sf, fast_threshold=ft)
+    wk, wd = oracle.orb_extract(img, n, **kw)
+    kps, desc = ctx.orb_extract(img, n, **kw)
+    assert_same(kps, desc, wk, wd)
+
+
 def _dbg_level(ctx, level, cap):
     L = capi.lib()
     L.gb_dbg_orb_level.restype = C.c_int
