@@ -186,7 +186,8 @@ GB_API int gb_remap_apply(gb_ctx* ctx, gb_remap* map, const uint8_t* src, int ch
  * ascending, feature indices ascending).  Word / node / feature indices are bit-exact with the reference; values are the reference's
  * floats (accumulated and normalised with the same operations).  A leaf above level L - levelsup files under itself (the reference
  * reads an uninitialised node id there).  gb_bow_transform_features: the same for descriptors already resident in HBM (the output
- * of gb_orb_extract_features), no host round trip before the walk. */
+ * of gb_orb_extract_to), no host round trip before the walk; the output arrays must hold the CAPACITY of `f` entries (the row
+ * count of an extraction still in flight is only known on the device; the launch is clipped by it). */
 typedef struct gb_vocabulary gb_vocabulary;
 GB_API int gb_voc_create(gb_ctx* ctx, int k, int L, int weighting, int scoring, uint32_t n_nodes, const uint32_t* child_num, const float* weight,
                          const uint8_t* desc32, gb_vocabulary** out);
