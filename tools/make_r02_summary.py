@@ -43,7 +43,8 @@ hit 32 different 96-byte rows, 2-3-way bank conflicts; 7.7 M conflicts), long sc
 prefetch and the spill removal), wait 2.0 (dependent fp64 chains), barrier 0.7 (was 2.6 before the per-landmark V^-1 left the team's
 critical path).  History of the kernel on this graph (`tools/sweep_bench.py`, CUDA events, 20 launches): ba.cu kernel 106.4 us ->
 persistent 2x256-thread CTAs + ticket 102.5 -> 4 teams + host plan + cp.async stages 106.6 -> sums written by their threads, V^-1 moved
-to the Schur preparation 95.5 -> camera pose re-read from shared memory (no spills), tree sums 88.4 us (2.01 TB/s, 31 % of 6484.6 GB/s).
+to the Schur preparation 95.5 -> camera pose re-read from shared memory (no spills), tree sums 88.4 us -> pose-table rows padded to an
+odd number of 16-byte chunks 86.3 us (2.06 TB/s, 31.8 % of 6484.6 GB/s).  The ncu capture above predates the padding (bank conflicts 7.7 M).
 
 ## 5. SASS evidence
 
