@@ -35,16 +35,16 @@ w("## 3. One global-BA solve at config 5 (ncu launch list of `tools/global_ba_be
 w(run("tools/summarize_launches.py", "profiles/r02_globalba_launches.csv"))
 w("## 4. The BA sweep at config 5 (`ba_sweep_kernel`, one `ncu --set full` launch, `r02_sweep_kernel.ncu-rep`)\n")
 w(run("tools/sweep_ncu_table.py"))
-w("""Reading: 148 CTAs x 512 threads (16 warps/SM at 126 registers), 208 KB of dynamic shared memory per CTA.  Issue slots 34 % busy, fp64
-pipe 24 %, tensor pipe 0 (nothing here is a GEMM: K = 2-3 contractions per observation, see DESIGN.md section 4).  DRAM traffic 143.9 MB
+w("""Reading: 148 CTAs x 512 threads (16 warps/SM at 126 registers), 216 KB of dynamic shared memory per CTA.  Issue slots 35 % busy, fp64
+pipe 24 %, tensor pipe 0 (nothing here is a GEMM: K = 2-3 contractions per observation, see DESIGN.md section 4).  DRAM traffic 145.4 MB
 per launch against 177.7 MB algorithmic (part of the 144 MB of W blocks is still in the 126 MB L2 when the kernel ends) -> no wasted
-traffic.  Stall profile per issued instruction: short scoreboard 2.6 + MIO throttle 1.6 (shared memory: the pose-table gathers of a warp
-hit 32 different 96-byte rows, 2-3-way bank conflicts; 7.7 M conflicts), long scoreboard 2.0 (was 4.7 before the cp.async stage
+traffic.  Stall profile per issued instruction: short scoreboard 2.5 + MIO throttle 1.5 (shared memory: pose-table gathers of 32
+different camera rows per warp, term-major contribution tile, staged item data; 7.2 M bank conflicts -- 7.7 M before the rows were padded), long scoreboard 2.0 (was 4.7 before the cp.async stage
 prefetch and the spill removal), wait 2.0 (dependent fp64 chains), barrier 0.7 (was 2.6 before the per-landmark V^-1 left the team's
 critical path).  History of the kernel on this graph (`tools/sweep_bench.py`, CUDA events, 20 launches): ba.cu kernel 106.4 us ->
 persistent 2x256-thread CTAs + ticket 102.5 -> 4 teams + host plan + cp.async stages 106.6 -> sums written by their threads, V^-1 moved
 to the Schur preparation 95.5 -> camera pose re-read from shared memory (no spills), tree sums 88.4 us -> pose-table rows padded to an
-odd number of 16-byte chunks 86.3 us (2.06 TB/s, 31.8 % of 6484.6 GB/s).  The ncu capture above predates the padding (bank conflicts 7.7 M).
+odd number of 16-byte chunks 86.3 us (2.06 TB/s, 31.8 % of 6484.6 GB/s).
 
 ## 5. SASS evidence
 
