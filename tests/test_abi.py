@@ -70,3 +70,21 @@ def test_estimator_plugin_exports_the_reference_factory():
     L = ctypes.CDLL(path)
     L.createEstimatorInstance.restype = ctypes.c_void_p
     assert L.createEstimatorInstance()
+
+
+def test_header_is_plain_c_and_cpp():
+    """include/gslam_b200.h is the boundary other hosts bind (cgo / JNI / ctypes): it must parse as C99 and as C++11 on its own."""
+    import shutil
+    import subprocess
+    import tempfile
+    hdr = os.path.join(ROOT, "include", "gslam_b200.h")
+    with tempfile.TemporaryDirectory() as d:
+        for cc, std, ext in (("gcc", "-std=c99", "c"), ("g++", "-std=c++11", "cpp")):
+            if not shutil.which(cc):
+                pytest.skip(f"{cc} not available")
+            src = os.path.join(d, f"probe.{ext}")
+            with open(src, "w") as f:
+                f.write('#include "%s"\nint probe(void) { gb_ba_problem p; gb_pose_edges e; gb_orb_cfg c; gb_keypoint k; (void)p; (void)e; (void)c; '
+                        '(void)k; return (int)sizeof(gb_keypoint) == 28 ? GB_OK : GB_ERR_INVALID; }\n' % hdr)
+            r = subprocess.run([cc, std, "-Wall", "-Werror", "-pedantic", "-fsyntax-only", src], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
