@@ -21,3 +21,16 @@ def test_reference_arm_under_torchrun_prints_one_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and "OpenMP" in d["cpu_baseline"]["sample"]
     assert set(d["config"]) >= {"workload", "l2", "parallelism"}
+
+
+def test_gpu_arm_refuses_to_run_without_a_device():
+    """No CPU fallback: on a box without a GPU the product arm of bench.py exits non-zero and prints no result line."""
+    import ctypes
+    from gslam_b200 import capi
+    n = ctypes.c_int(0)
+    if capi.lib().gb_device_count(ctypes.byref(n)) == 0 and n.value > 0:
+        import pytest
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode != 0
+    assert not any(l.startswith("{") for l in r.stdout.splitlines())
